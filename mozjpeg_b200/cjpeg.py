@@ -1,0 +1,215 @@
+"""Host-side mirror of the reference's ``cjpeg`` front end.
+
+``params_from_switches`` turns a cjpeg command line (the switches of
+cjpeg.c:315-765 that concern the encode hot path) into a ``b200jpeg_params``
+block by making the same API calls, in the same order, as cjpeg's ``main``:
+
+    jpeg_create_compress (profile JCP_MAX_COMPRESSION, jcapimin.c:107-109)
+    in_color_space = JCS_RGB ; jpeg_set_defaults            cjpeg.c:860-861
+    parse_switches(for_real=FALSE)                          cjpeg.c:869
+    <image header: dimensions, colour space>                cjpeg.c:921-928
+    jpeg_default_colorspace                                 cjpeg.c:931
+    parse_switches(for_real=TRUE)                           cjpeg.c:934
+    jpeg_start_compress (optimize_scans off w/o script)     jcapistd.c:53-56
+
+so that the parity tests read like the reference's own bit tests
+(CMakeLists.txt:1426-1736: ``cjpeg <switches> testorig.ppm`` -> md5).
+All parameter arithmetic happens in libb200jpeg (params.cpp); this file only
+sequences the calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+from . import _abi as A
+
+
+class UsageError(ValueError):
+    """cjpeg would have printed usage() and exited."""
+
+
+def _keymatch(arg: str, keyword: str, minchars: int) -> bool:
+    """cdjpeg.c keymatch(): case-insensitive prefix match of >= minchars."""
+    a = arg.lower()
+    if len(a) > len(keyword) or len(a) < minchars:
+        return False
+    return keyword.startswith(a)
+
+
+def _set_sample_factors(p: A.Params, arg: str) -> None:
+    """rdswitch.c:611-645: listed components, then 1x1 for the rest."""
+    parts = arg.split(",") if arg else []
+    for ci in range(A.MAX_COMPONENTS):
+        if ci < len(parts):
+            hv = parts[ci].lower().split("x")
+            if len(hv) != 2:
+                raise UsageError("can't set sample factors")
+            h, v = int(hv[0]), int(hv[1])
+            if not (1 <= h <= 4 and 1 <= v <= 4):
+                raise UsageError("JPEG sampling factors must be 1..4")
+        else:
+            h, v = 1, 1
+        p.comp_info[ci].h_samp_factor = h
+        p.comp_info[ci].v_samp_factor = v
+
+
+def _parse(p: A.Params, argv: Sequence[str], for_real: bool) -> None:
+    lib = A.load()
+    force_baseline = False
+    simple_progressive = p.num_scans != 0          # cjpeg.c:343
+    qualityarg = samplearg = None
+    i = 0
+    n = len(argv)
+
+    def nextarg(what: str) -> str:
+        nonlocal i
+        i += 1
+        if i >= n:
+            raise UsageError(f"missing argument for {what}")
+        return argv[i]
+
+    while i < n:
+        arg = argv[i]
+        if not arg.startswith("-"):
+            raise UsageError(f"unexpected file argument {arg!r}")
+        a = arg[1:]
+        if _keymatch(a, "baseline", 1):
+            force_baseline = True
+            simple_progressive = False
+            p.num_scans = 0
+        elif _keymatch(a, "dct", 2):
+            v = nextarg("dct")
+            if _keymatch(v, "int", 1): p.dct_method = A.DCT_ISLOW
+            elif _keymatch(v, "fast", 2): p.dct_method = A.DCT_IFAST
+            elif _keymatch(v, "float", 2): p.dct_method = A.DCT_FLOAT
+            else: raise UsageError("invalid argument for dct")
+        elif _keymatch(a, "fastcrush", 4):
+            p.optimize_scans = 0
+        elif _keymatch(a, "grayscale", 2) or _keymatch(a, "greyscale", 2):
+            A.check(lib.b200jpeg_set_colorspace(C.byref(p), A.CS_GRAYSCALE), "set_colorspace")
+        elif _keymatch(a, "rgb", 3):
+            A.check(lib.b200jpeg_set_colorspace(C.byref(p), A.CS_RGB), "set_colorspace")
+        elif _keymatch(a, "lambda1", 7):
+            p.lambda_log_scale1 = float(nextarg("lambda1"))
+        elif _keymatch(a, "lambda2", 7):
+            p.lambda_log_scale2 = float(nextarg("lambda2"))
+        elif _keymatch(a, "dc-scan-opt", 3):
+            p.dc_scan_opt_mode = int(nextarg("dc-scan-opt"))
+        elif _keymatch(a, "optimize", 1) or _keymatch(a, "optimise", 1):
+            p.optimize_coding = 1
+        elif _keymatch(a, "progressive", 1):
+            simple_progressive = True
+        elif _keymatch(a, "quality", 1):
+            qualityarg = nextarg("quality")
+        elif _keymatch(a, "quant-table", 7):
+            v = int(nextarg("quant-table"))
+            if not 0 <= v <= 8:
+                raise UsageError(f"{v} is invalid argument for quant-table")
+            p.quant_tbl_master_idx = v                       # jcext.c JINT_BASE_QUANT_TBL_IDX
+            lib.b200jpeg_set_quality(C.byref(p), 75, 1)      # cjpeg.c:595
+        elif _keymatch(a, "quant-baseline", 7):
+            force_baseline = True
+        elif _keymatch(a, "restart", 1):
+            v = nextarg("restart")
+            if v[-1:] in "bB":
+                p.restart_interval = int(v[:-1]); p.restart_in_rows = 0
+            else:
+                p.restart_in_rows = int(v)
+        elif _keymatch(a, "revert", 3):
+            w, h = p.image_width, p.image_height
+            lib.b200jpeg_set_defaults(C.byref(p), A.PROFILE_FASTEST)   # cjpeg.c:623-626
+            p.image_width, p.image_height = w, h
+        elif _keymatch(a, "sample", 2):
+            samplearg = nextarg("sample")
+        elif _keymatch(a, "smooth", 2):
+            p.smoothing_factor = int(nextarg("smooth"))
+        elif _keymatch(a, "notrellis-dc", 11):
+            p.trellis_quant_dc = 0
+        elif _keymatch(a, "notrellis", 1):
+            p.trellis_quant = 0
+        elif _keymatch(a, "trellis-dc", 9):
+            p.trellis_quant_dc = 1
+        elif _keymatch(a, "tune-psnr", 6):
+            p.quant_tbl_master_idx = 1; p.lambda_log_scale1 = 9.0; p.lambda_log_scale2 = 0.0; p.use_lambda_weight_tbl = 0
+            lib.b200jpeg_set_quality(C.byref(p), 75, 1)
+        elif _keymatch(a, "tune-ssim", 6):
+            p.quant_tbl_master_idx = 1; p.lambda_log_scale1 = 11.5; p.lambda_log_scale2 = 12.75; p.use_lambda_weight_tbl = 0
+            lib.b200jpeg_set_quality(C.byref(p), 75, 1)
+        elif _keymatch(a, "tune-ms-ssim", 6):
+            p.quant_tbl_master_idx = 3; p.lambda_log_scale1 = 12.0; p.lambda_log_scale2 = 13.0; p.use_lambda_weight_tbl = 1
+            lib.b200jpeg_set_quality(C.byref(p), 75, 1)
+        elif _keymatch(a, "tune-hvs-psnr", 6):
+            p.quant_tbl_master_idx = 3; p.lambda_log_scale1 = 14.75; p.lambda_log_scale2 = 16.5; p.use_lambda_weight_tbl = 1
+            lib.b200jpeg_set_quality(C.byref(p), 75, 1)
+        elif _keymatch(a, "noovershoot", 11):
+            p.overshoot_deringing = 0
+        elif _keymatch(a, "nojfif", 6):
+            p.write_JFIF_header = 0
+        else:
+            raise UsageError(f"unknown or out-of-scope option {arg!r}")
+        i += 1
+
+    if for_real:
+        if qualityarg is not None:
+            # rdswitch.c:524-573 set_quality_ratings
+            vals = qualityarg.split(",")
+            val = 75.0
+            for t in range(A.NUM_QUANT_TBLS):
+                if t < len(vals):
+                    val = float(vals[t])
+                p.q_scale_factor[t] = int(lib.b200jpeg_float_quality_scaling(val))
+            lib.b200jpeg_default_qtables(C.byref(p), int(force_baseline))
+            if val >= 90:
+                _set_sample_factors(p, "1x1")
+            elif val >= 80:
+                _set_sample_factors(p, "2x1")
+        if samplearg is not None:
+            _set_sample_factors(p, samplearg)
+        if simple_progressive:
+            A.check(lib.b200jpeg_simple_progression(C.byref(p)), "simple_progression")
+
+
+def params_from_switches(switches: Sequence[str], width: int, height: int,
+                         input_components: int = 3) -> A.Params:
+    """What cjpeg's cinfo looks like at jpeg_start_compress for ``switches``."""
+    lib = A.load()
+    p = A.Params()
+    p.in_color_space = A.CS_RGB
+    p.input_components = 3
+    p.data_precision = 8
+    lib.b200jpeg_set_defaults(C.byref(p), A.PROFILE_MAX_COMPRESSION)
+    _parse(p, list(switches), False)
+    # image header (rdppm.c start_input_ppm): P5 -> grayscale, P6 -> RGB
+    p.in_color_space = A.CS_GRAYSCALE if input_components == 1 else A.CS_RGB
+    p.input_components = input_components
+    p.image_width, p.image_height = width, height
+    A.check(lib.b200jpeg_default_colorspace(C.byref(p)), "default_colorspace")
+    _parse(p, list(switches), True)
+    # jpeg_start_compress (jcapistd.c:53-56)
+    if p.num_scans == 0:
+        p.optimize_scans = 0
+    return p
+
+
+def read_ppm(data: bytes) -> Tuple[int, int, int, bytes]:
+    """Minimal binary PGM/PPM reader (P5/P6, maxval 255) -> (w, h, ncomp, samples)."""
+    toks: List[bytes] = []
+    pos = 0
+    while len(toks) < 4:
+        while data[pos:pos + 1].isspace():
+            pos += 1
+        if data[pos:pos + 1] == b"#":
+            while data[pos:pos + 1] not in (b"\n", b""):
+                pos += 1
+            continue
+        st = pos
+        while not data[pos:pos + 1].isspace():
+            pos += 1
+        toks.append(data[st:pos])
+    pos += 1
+    magic, w, h, maxv = toks[0], int(toks[1]), int(toks[2]), int(toks[3])
+    if magic not in (b"P5", b"P6") or maxv != 255:
+        raise ValueError("only binary 8-bit PGM/PPM supported")
+    nc = 3 if magic == b"P6" else 1
+    return w, h, nc, data[pos:pos + w * h * nc]
