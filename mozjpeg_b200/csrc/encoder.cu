@@ -1,0 +1,738 @@
+// encoder.cu -- host side of libb200jpeg: HBM arenas, the pass plan of
+// jcmaster.c restated as batch-wide kernel launches, and the C-ABI entry points
+// of include/b200jpeg.h.  One encoder = one CUDA device + one stream; every
+// launch covers the whole batch, so the reference's per-image "passes"
+// (jcmaster.c:612-715) become one launch per phase for all images.
+#include "b200jpeg.h"
+#include "internal.h"
+#include "kernels.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace b200 {
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return B200JPEG_ERR_CUDA; } } while (0)
+
+static const int kZigzag[64] = {
+   0,  1,  8, 16,  9,  2,  3, 10, 17, 24, 32, 25, 18, 11,  4,  5,
+  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,  6,  7, 14, 21, 28,
+  35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+  58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct DevBuf {
+  void *p = nullptr; size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return B200JPEG_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return B200JPEG_ERR_CUDA; }
+    cap = want; return B200JPEG_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T *as() { return static_cast<T *>(p); }
+};
+struct PinBuf {
+  void *p = nullptr; size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return B200JPEG_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) { p = nullptr; set_error("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e)); return B200JPEG_ERR_CUDA; }
+    cap = want; return B200JPEG_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T *as() { return static_cast<T *>(p); }
+};
+
+// host copy of a DHT payload (first 288 bytes of DevHuff)
+struct HostHuff { uint8_t bits[17]; uint8_t huffval[256]; uint8_t nsym; uint8_t pad[12]; uint16_t nsym16; };
+static_assert(sizeof(HostHuff) == 288, "HostHuff");
+
+struct Plan {                // everything derived from b200jpeg_params
+  Geom g;
+  std::vector<ScanDesc> scans;
+  bool progressive = false, optimize = false, trellis = false, dering = false;
+  size_t coef_bytes[4] = {0, 0, 0, 0};
+  long long max_scan_blocks = 0, max_real_blocks = 0;
+};
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200jpeg_encoder {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  b200jpeg_params params;           // of the last batch
+  Plan plan;
+  int n = 0;
+  bool keep_plain = false;
+  // device arenas
+  DevBuf d_src, d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_scan, d_tabs_trellis, d_tabs_fixed, d_rec, d_bt;
+  DevBuf d_blk_bits, d_blk_aux, d_total_bits, d_status, d_out_pos, d_scan_size, d_bitbuf, d_out, d_qt, d_tc;
+  size_t bitbuf_words_per_image = 0, out_cap_per_image = 0;
+  double cap_factor = 0.25;
+  // pinned host mirrors
+  PinBuf h_qt, h_tc, h_fixed, h_status, h_out_pos, h_scan_size, h_tabs, h_out, h_stage;
+  // results of the last batch
+  std::vector<std::vector<uint8_t>> files;
+  size_t last_scan_bytes = 0;
+  unsigned long long launches_at_create = 0;
+  // timing
+  std::vector<cudaEvent_t> ev; std::vector<const char *> ev_names; std::vector<float> stage_ms;
+  // streaming shim state
+  int st_state = 0, st_next_row = 0;
+  b200jpeg_params st_params;
+};
+
+namespace b200 {
+
+static int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_stride, Plan &pl)
+{
+  Geom &g = pl.g;
+  memset(&g, 0, sizeof g);
+  g.W = p->image_width; g.H = p->image_height; g.nc = p->num_components; g.in_comps = p->input_components;
+  g.hmax = g.vmax = 1;
+  for (int ci = 0; ci < g.nc; ci++) { g.hmax = std::max(g.hmax, p->comp_info[ci].h_samp_factor); g.vmax = std::max(g.vmax, p->comp_info[ci].v_samp_factor); }
+  g.mcus_per_row = div_up(g.W, g.hmax * 8); g.mcu_rows = div_up(g.H, g.vmax * 8);
+  g.row_pitch = row_pitch; g.image_stride = image_stride;
+  if (p->in_color_space == B200JPEG_CS_RGB && p->jpeg_color_space == B200JPEG_CS_YCbCr) g.cs_mode = 0;
+  else if (p->in_color_space == B200JPEG_CS_RGB && p->jpeg_color_space == B200JPEG_CS_GRAYSCALE) g.cs_mode = 1;
+  else g.cs_mode = 2;
+  pl.max_real_blocks = 0;
+  for (int ci = 0; ci < g.nc; ci++) {
+    CompGeom &c = g.c[ci]; const b200jpeg_component_info &ic = p->comp_info[ci];
+    c.h = ic.h_samp_factor; c.v = ic.v_samp_factor; c.hx = g.hmax / c.h; c.vx = g.vmax / c.v;
+    c.wib = div_up((long long)g.W * c.h, g.hmax * 8); c.hib = div_up((long long)g.H * c.v, g.vmax * 8);   // jcmaster.c:221-226
+    c.wpad = g.mcus_per_row * c.h; c.hpad = g.mcu_rows * c.v;
+    c.qt = ic.quant_tbl_no; c.dc_tbl = ic.dc_tbl_no; c.ac_tbl = ic.ac_tbl_no;
+    c.rows_avail = div_up(g.H, g.vmax) * c.v;
+    c.blocks_per_image = (long long)c.wpad * c.hpad;
+    pl.coef_bytes[ci] = (size_t)c.blocks_per_image * 128;
+    pl.max_real_blocks = std::max(pl.max_real_blocks, (long long)c.wib * c.hib);
+  }
+  // scan list (select_scan_parameters jcmaster.c:443-515 + per_scan_setup :518-601)
+  pl.scans.clear();
+  int nscans = p->num_scans > 0 ? p->num_scans : 1;
+  pl.max_scan_blocks = 0;
+  for (int si = 0; si < nscans; si++) {
+    ScanDesc sd; memset(&sd, 0, sizeof sd);
+    if (p->num_scans > 0) {
+      const b200jpeg_scan_info &s = p->scan_info[si];
+      sd.ncomps = s.comps_in_scan; for (int k = 0; k < 4; k++) sd.ci[k] = s.component_index[k];
+      sd.Ss = s.Ss; sd.Se = s.Se; sd.Ah = s.Ah; sd.Al = s.Al;
+    } else { sd.ncomps = g.nc; for (int k = 0; k < 4; k++) sd.ci[k] = k; sd.Ss = 0; sd.Se = 63; }
+    if (sd.ncomps == 1) {
+      const CompGeom &c = g.c[sd.ci[0]];
+      sd.bim = 1; sd.k_comp[0] = 0; sd.k_first[0] = 0; sd.k_count[0] = 1;
+      sd.per_row = c.wib; sd.rows = c.hib;
+    } else {
+      int k = 0;
+      for (int i = 0; i < sd.ncomps; i++) {
+        const CompGeom &c = g.c[sd.ci[i]];
+        sd.k_first[i] = k; sd.k_count[i] = c.h * c.v;
+        for (int y = 0; y < c.v; y++) for (int x = 0; x < c.h; x++) { sd.k_comp[k] = i; sd.k_y[k] = y; sd.k_x[k] = x; k++; }
+      }
+      sd.bim = k; sd.per_row = g.mcus_per_row; sd.rows = g.mcu_rows;
+    }
+    sd.nblocks = (long long)sd.per_row * sd.rows * sd.bim;
+    pl.max_scan_blocks = std::max(pl.max_scan_blocks, sd.nblocks);
+    pl.scans.push_back(sd);
+  }
+  pl.progressive = p->num_scans > 0 && (p->scan_info[0].Ss != 0 || p->scan_info[0].Se != 63);
+  pl.optimize = p->optimize_coding || pl.progressive;           // jcmaster.c:1091-1094
+  pl.trellis = p->trellis_quant != 0;
+  pl.dering = p->overshoot_deringing != 0;
+  return B200JPEG_OK;
+}
+
+// exact floor((|x| + d/2) / d) for |x| + d/2 < 2^18 by multiply-shift:
+// k = 18 + ceil(log2 d), m = ceil(2^k / d)  (Granlund-Montgomery round-up method)
+static void make_quant_consts(const b200jpeg_params *p, QuantTables *qt)
+{
+  memset(qt, 0, sizeof *qt);
+  for (int t = 0; t < 4; t++) {
+    if (!p->quant_tbl_present[t]) continue;
+    for (int i = 0; i < 64; i++) {
+      unsigned d = 8u * p->quant_tbl[t][i];
+      int l = 0; while ((1ull << l) < d) l++;
+      int k = 18 + l;
+      unsigned long long m = ((1ull << k) + d - 1) / d;
+      QuantConst &q = qt->q[t][i];
+      q.mul = (uint32_t)m; q.shift = (uint16_t)k; q.bias = d / 2; q.d = d; q.pad = 0;
+    }
+  }
+}
+static void make_trellis_consts(const b200jpeg_params *p, TrellisConsts *tc)
+{
+  memset(tc, 0, sizeof *tc);
+  for (int t = 0; t < 4; t++) {
+    if (!p->quant_tbl_present[t]) continue;
+    for (int k = 0; k < 64; k++) {
+      int q = p->quant_tbl[t][kZigzag[k]];
+      tc->w_zz[t][k] = (float)(1.0 / (q * q));                       // jcdctmgr.c:1020 (double divide, float store)
+      tc->q8_zz[t][k] = 8 * q;
+    }
+  }
+  tc->use_norm = p->lambda_log_scale2 > 0.0f;
+  tc->p1 = pow(2.0, (double)p->lambda_log_scale1);
+  tc->p2 = pow(2.0, (double)p->lambda_log_scale2);
+  tc->lambda_const = (float)(pow(2.0, (double)p->lambda_log_scale1 - 12.0) * 1.0f);
+  tc->max_coef_bits = p->data_precision + 2;
+  tc->dc_trellis = p->trellis_quant_dc;
+}
+// jpeg_make_c_derived_tbl (jchuff.c:231-318) for caller-supplied tables
+static int make_fixed_table(const b200jpeg_huff_tbl &t, bool is_dc, DevHuff *out)
+{
+  memset(out, 0, sizeof *out);
+  if (!t.present) return 0;
+  memcpy(out->bits, t.bits, 17); memcpy(out->huffval, t.huffval, 256);
+  int n = 0; unsigned code = 0;
+  for (int l = 1; l <= 16; l++) {
+    for (int c = 0; c < t.bits[l]; c++) {
+      if (n >= 256) return -1;
+      int sym = t.huffval[n++];
+      if ((is_dc && sym > 15) || out->size[sym]) return -1;
+      out->code[sym] = (uint16_t)code; out->size[sym] = (uint8_t)l; code++;
+    }
+    if (code > (1u << l)) return -1;
+    code <<= 1;
+  }
+  out->nsym16 = (uint16_t)n; out->nsym = (uint8_t)n;
+  return 0;
+}
+
+struct Timer {
+  b200jpeg_encoder *e; size_t idx = 0;
+  void mark(const char *name) {
+    if (idx >= e->ev.size()) { cudaEvent_t ev; cudaEventCreate(&ev); e->ev.push_back(ev); }
+    cudaEventRecord(e->ev[idx], e->stream);
+    if (idx >= e->ev_names.size()) e->ev_names.push_back(name); else e->ev_names[idx] = name;
+    idx++;
+  }
+};
+
+static uint32_t scan_slot_mask(const Plan &pl, const ScanDesc &sd)
+{
+  uint32_t m = 0;
+  for (int i = 0; i < sd.ncomps; i++) {
+    const CompGeom &c = pl.g.c[sd.ci[i]];
+    bool want_dc = !pl.progressive || (sd.Ss == 0 && sd.Ah == 0);
+    bool want_ac = !pl.progressive || (sd.Ss != 0);
+    if (want_dc) m |= 1u << c.dc_tbl;
+    if (want_ac) m |= 1u << (4 + c.ac_tbl);
+  }
+  return m;
+}
+
+// The device pipeline for one batch.  src_dev: pixels already in HBM.
+static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
+{
+  Plan &pl = e->plan; const b200jpeg_params *p = &e->params; const int n = e->n; cudaStream_t s = e->stream;
+  Geom &g = pl.g;
+  const int nscans = (int)pl.scans.size();
+  if (pl.progressive) { set_error("progressive scans are not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
+  if (p->restart_interval || p->restart_in_rows) { set_error("restart intervals are not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
+
+  int rc;
+  for (int ci = 0; ci < g.nc; ci++) {
+    if ((rc = e->d_coef[ci].reserve(pl.coef_bytes[ci] * n))) return rc;
+    if ((rc = e->d_raw[ci].reserve(pl.coef_bytes[ci] * n))) return rc;
+    g.c[ci].coef = e->d_coef[ci].as<int16_t>(); g.c[ci].raw = e->d_raw[ci].as<int16_t>();
+    if (e->keep_plain && pl.trellis) { if ((rc = e->d_plain[ci].reserve(pl.coef_bytes[ci] * n))) return rc; }
+  }
+  const size_t hist_bytes = (size_t)n * HIST_SLOTS * HIST_BINS * 4;
+  if ((rc = e->d_hist.reserve(hist_bytes))) return rc;
+  const size_t tabset = sizeof(DevHuff) * HIST_SLOTS;
+  if ((rc = e->d_tabs_scan.reserve(tabset * nscans * n))) return rc;
+  if ((rc = e->d_tabs_trellis.reserve(tabset * 4 * n))) return rc;
+  if ((rc = e->d_tabs_fixed.reserve(tabset))) return rc;
+  if ((rc = e->d_rec.reserve((size_t)n * pl.max_real_blocks * sizeof(DcRec)))) return rc;
+  if ((rc = e->d_bt.reserve((size_t)n * pl.max_real_blocks * 8))) return rc;
+  if ((rc = e->d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
+  if ((rc = e->d_total_bits.reserve((size_t)n * 8))) return rc;
+  if ((rc = e->d_status.reserve((size_t)n * 4))) return rc;
+  if ((rc = e->d_out_pos.reserve((size_t)n * 8))) return rc;
+  if ((rc = e->d_scan_size.reserve((size_t)n * nscans * 4))) return rc;
+  long long total_blocks = 0; for (int ci = 0; ci < g.nc; ci++) total_blocks += g.c[ci].blocks_per_image;
+  size_t cap = (size_t)((double)total_blocks * 64 * e->cap_factor) + 65536;
+  cap = (cap + 255) & ~(size_t)255;
+  e->bitbuf_words_per_image = cap / 4; e->out_cap_per_image = cap + cap / 64 + 4096;
+  if ((rc = e->d_bitbuf.reserve(cap * n))) return rc;
+  if ((rc = e->d_out.reserve(e->out_cap_per_image * n))) return rc;
+  if ((rc = e->d_qt.reserve(sizeof(QuantTables)))) return rc;
+  if ((rc = e->d_tc.reserve(sizeof(TrellisConsts)))) return rc;
+  if ((rc = e->h_qt.reserve(sizeof(QuantTables)))) return rc;
+  if ((rc = e->h_tc.reserve(sizeof(TrellisConsts)))) return rc;
+  if ((rc = e->h_fixed.reserve(tabset))) return rc;
+
+  make_quant_consts(p, e->h_qt.as<QuantTables>());
+  make_trellis_consts(p, e->h_tc.as<TrellisConsts>());
+  {
+    DevHuff *f = e->h_fixed.as<DevHuff>();
+    for (int t = 0; t < 4; t++) {
+      if (make_fixed_table(p->dc_huff_tbl[t], true, &f[t]) || make_fixed_table(p->ac_huff_tbl[t], false, &f[4 + t])) { set_error("Bogus Huffman table definition"); return B200JPEG_ERR_PARAM; }
+    }
+  }
+  CU(cudaMemcpyAsync(e->d_qt.p, e->h_qt.p, sizeof(QuantTables), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(e->d_tc.p, e->h_tc.p, sizeof(TrellisConsts), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(e->d_tabs_fixed.p, e->h_fixed.p, tabset, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(e->d_status.p, 0, (size_t)n * 4, s));
+  CU(cudaMemsetAsync(e->d_out_pos.p, 0, (size_t)n * 8, s));
+  uint32_t *status = e->d_status.as<uint32_t>();
+
+  // ---- pass 0 data path: colour/downsample/FDCT/quantize (compress_first_pass) ----
+  tm.mark("forward");
+  for (int ci = 0; ci < g.nc; ci++) launch_forward(g, ci, src_dev, e->d_qt.as<QuantTables>(), pl.dering, n, s);
+  for (int ci = 0; ci < g.nc; ci++) launch_dummy(g, ci, n, s);
+
+  // ---- trellis phase (jcmaster.c pass list): per component:
+  //      statistics on the plain-quantized coefficients -> optimal tables ->
+  //      quantize_trellis (AC per block, DC Viterbi per block row) -> dummy blocks ----
+  if (pl.trellis) {
+    tm.mark("trellis");
+    for (int ci = 0; ci < g.nc; ci++) {
+      if (e->keep_plain) CU(cudaMemcpyAsync(e->d_plain[ci].p, e->d_coef[ci].p, pl.coef_bytes[ci] * n, cudaMemcpyDeviceToDevice, s));
+      ScanDesc ts; memset(&ts, 0, sizeof ts);
+      ts.ncomps = 1; ts.ci[0] = ci; ts.Ss = 0; ts.Se = 63; ts.bim = 1; ts.k_count[0] = 1;
+      ts.per_row = g.c[ci].wib; ts.rows = g.c[ci].hib; ts.nblocks = (long long)ts.per_row * ts.rows;
+      CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes, s));
+      launch_gather_seq(g, ts, e->d_hist.as<uint32_t>(), status, n, s);
+      DevHuff *tset = e->d_tabs_trellis.as<DevHuff>() + (size_t)ci * HIST_SLOTS;          // [img][ci][8]
+      size_t tstride = tabset * 4;
+      launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tstride, (1u << g.c[ci].dc_tbl) | (1u << (4 + g.c[ci].ac_tbl)), n, s);
+      launch_trellis_ac(g, ci, e->d_tc.as<TrellisConsts>(), tset, tstride, e->d_rec.as<DcRec>(), n, s);
+      if (p->trellis_quant_dc)
+        launch_trellis_dc(g, ci, e->d_tc.as<TrellisConsts>(), tset, tstride, e->d_rec.as<DcRec>(), e->d_bt.as<unsigned long long>(), n, s);
+      launch_dummy(g, ci, n, s);
+    }
+  }
+
+  // ---- scans: huff_opt_pass (statistics -> tables) + output_pass ----
+  tm.mark("entropy");
+  for (int si = 0; si < nscans; si++) {
+    const ScanDesc &sd = pl.scans[si];
+    const DevHuff *tabs; size_t tstride;
+    if (pl.optimize) {
+      DevHuff *tset = e->d_tabs_scan.as<DevHuff>() + (size_t)si * HIST_SLOTS;             // [img][scan][8]
+      tstride = tabset * nscans;
+      CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes, s));
+      launch_gather_seq(g, sd, e->d_hist.as<uint32_t>(), status, n, s);
+      launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tstride, scan_slot_mask(pl, sd), n, s);
+      tabs = tset;
+    } else { tabs = e->d_tabs_fixed.as<DevHuff>(); tstride = 0; }
+    launch_block_bits(g, sd, tabs, tstride, 0, e->d_blk_bits.as<uint32_t>(), nullptr, status, n, s);
+    launch_scan_offsets(e->d_blk_bits.as<uint32_t>(), sd.nblocks, e->d_total_bits.as<unsigned long long>(), (size_t)e->bitbuf_words_per_image * 32, status, n, s);
+    CU(cudaMemsetAsync(e->d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
+    launch_encode(g, sd, tabs, tstride, 0, e->d_blk_bits.as<uint32_t>(), nullptr, e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, status, n, s);
+    launch_stuff(e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, e->d_total_bits.as<unsigned long long>(),
+                 e->d_out.as<uint8_t>(), e->out_cap_per_image, e->out_cap_per_image, e->d_out_pos.as<unsigned long long>(),
+                 e->d_scan_size.as<uint32_t>() + (size_t)si * n, status, n, s);
+  }
+  tm.mark("end");
+  CU(cudaGetLastError());
+  return B200JPEG_OK;
+}
+
+// ------------------------------------------------------------------ host-side file assembly (jcmarker.c)
+struct Bytes {
+  std::vector<uint8_t> &v;
+  void b(int x) { v.push_back((uint8_t)x); }
+  void w(int x) { v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); }
+};
+
+static void write_file_header(const b200jpeg_params *p, Bytes o)                     // jcmarker.c:649-663
+{
+  o.w(0xFFD8);
+  if (p->write_JFIF_header) {                                                         // :529-561
+    o.w(0xFFE0); o.w(16); o.b('J'); o.b('F'); o.b('I'); o.b('F'); o.b(0);
+    o.b(p->JFIF_major_version); o.b(p->JFIF_minor_version); o.b(p->density_unit);
+    o.w(p->X_density); o.w(p->Y_density); o.b(0); o.b(0);
+  }
+  if (p->write_Adobe_marker) {                                                        // :564-620
+    o.w(0xFFEE); o.w(14); o.b('A'); o.b('d'); o.b('o'); o.b('b'); o.b('e'); o.w(100); o.w(0); o.w(0);
+    o.b(p->jpeg_color_space == B200JPEG_CS_YCbCr ? 1 : 0);
+  }
+}
+static void write_frame_header(const b200jpeg_params *p, bool progressive, Bytes o)   // jcmarker.c:674-735
+{
+  int nc = p->num_components, prec = 0;
+  bool multi = p->compress_profile != B200JPEG_PROFILE_FASTEST;                       // emit_multi_dqt :189-254
+  bool sent[4] = {false, false, false, false};
+  if (multi) {
+    int precs[4] = {0, 0, 0, 0}, size = 0; bool seen[4] = {false, false, false, false};
+    for (int ci = 0; ci < nc; ci++) { int t = p->comp_info[ci].quant_tbl_no; for (int i = 0; i < 64; i++) if (p->quant_tbl[t][i] > 255) precs[ci] = 1; prec += precs[ci]; }
+    o.w(0xFFDB);
+    for (int ci = 0; ci < nc; ci++) { int t = p->comp_info[ci].quant_tbl_no; if (!seen[t]) { size += 64 * (precs[ci] + 1) + 1; seen[t] = true; } }
+    o.w(size + 2);
+    for (int ci = 0; ci < nc; ci++) {
+      int t = p->comp_info[ci].quant_tbl_no;
+      if (sent[t]) continue;
+      o.b(t + (precs[ci] << 4));
+      for (int i = 0; i < 64; i++) { unsigned q = p->quant_tbl[t][kZigzag[i]]; if (precs[ci]) o.b(q >> 8); o.b(q & 0xFF); }
+      sent[t] = true;
+    }
+  } else {
+    for (int ci = 0; ci < nc; ci++) {                                                  // emit_dqt :140-187
+      int t = p->comp_info[ci].quant_tbl_no, pr = 0;
+      for (int i = 0; i < 64; i++) if (p->quant_tbl[t][i] > 255) pr = 1;
+      if (!sent[t]) {
+        o.w(0xFFDB); o.w(pr ? 64 * 2 + 1 + 2 : 64 + 1 + 2); o.b(t + (pr << 4));
+        for (int i = 0; i < 64; i++) { unsigned q = p->quant_tbl[t][kZigzag[i]]; if (pr) o.b(q >> 8); o.b(q & 0xFF); }
+        sent[t] = true;
+      }
+      prec += pr;
+    }
+  }
+  bool is_baseline;
+  if (progressive || p->data_precision != 8) is_baseline = false;
+  else {
+    is_baseline = true;
+    for (int ci = 0; ci < nc; ci++) if (p->comp_info[ci].dc_tbl_no > 1 || p->comp_info[ci].ac_tbl_no > 1) is_baseline = false;
+    if (prec && is_baseline) is_baseline = false;
+  }
+  o.w(progressive ? 0xFFC2 : (is_baseline ? 0xFFC0 : 0xFFC1));                          // emit_sof :464-491
+  o.w(3 * nc + 2 + 5 + 1); o.b(p->data_precision); o.w(p->image_height); o.w(p->image_width); o.b(nc);
+  for (int ci = 0; ci < nc; ci++) { o.b(p->comp_info[ci].component_id); o.b((p->comp_info[ci].h_samp_factor << 4) + p->comp_info[ci].v_samp_factor); o.b(p->comp_info[ci].quant_tbl_no); }
+}
+// table state across scans (JHUFF_TBL.sent_table)
+struct TblState { const HostHuff *dc[4]; const HostHuff *ac[4]; bool dc_sent[4]; bool ac_sent[4]; };
+
+static int huff_len(const HostHuff *h) { int n = 0; for (int l = 1; l <= 16; l++) n += h->bits[l]; return n; }
+static void write_scan_header(const b200jpeg_params *p, const ScanDesc &sd, TblState &ts, int &last_ri, unsigned ri, Bytes o)   // jcmarker.c:744-784
+{
+  bool multi = p->compress_profile != B200JPEG_PROFILE_FASTEST;
+  bool done_multi = false;
+  if (multi) {                                                                           // emit_multi_dht :293-401
+    int length = 2, dclens[4] = {0, 0, 0, 0}, aclens[4] = {0, 0, 0, 0}; int dcseen[4] = {-1, -1, -1, -1}, acseen[4] = {-1, -1, -1, -1};
+    for (int i = 0; i < sd.ncomps; i++) {
+      const b200jpeg_component_info &c = p->comp_info[sd.ci[i]];
+      int dcidx = c.dc_tbl_no, acidx = c.ac_tbl_no, seen = 0;
+      if (sd.Ss == 0 && sd.Ah == 0) {
+        if (ts.dc_sent[dcidx]) continue;
+        for (int j = 0; j < 4; j++) seen += (dcseen[j] == dcidx);
+        if (seen) continue;
+        dcseen[i] = dcidx; dclens[i] = huff_len(ts.dc[dcidx]); length += dclens[i] + 16 + 1;
+      }
+      if (sd.Se) {
+        if (ts.ac_sent[acidx]) continue;
+        seen = 0; for (int j = 0; j < 4; j++) seen += (acseen[j] == acidx);
+        if (seen) continue;
+        acseen[i] = acidx; aclens[i] = huff_len(ts.ac[acidx]); length += aclens[i] + 16 + 1;
+      }
+    }
+    if (length <= 65535) {
+      o.w(0xFFC4); o.w(length);
+      for (int i = 0; i < sd.ncomps; i++) {
+        const b200jpeg_component_info &c = p->comp_info[sd.ci[i]];
+        int dcidx = c.dc_tbl_no, acidx = c.ac_tbl_no;
+        if (sd.Ss == 0 && sd.Ah == 0 && !ts.dc_sent[dcidx]) {
+          o.b(dcidx); for (int j = 1; j <= 16; j++) o.b(ts.dc[dcidx]->bits[j]); for (int j = 0; j < dclens[i]; j++) o.b(ts.dc[dcidx]->huffval[j]);
+          ts.dc_sent[dcidx] = true;
+        }
+        if (sd.Se && !ts.ac_sent[acidx]) {
+          o.b(acidx + 0x10); for (int j = 1; j <= 16; j++) o.b(ts.ac[acidx]->bits[j]); for (int j = 0; j < aclens[i]; j++) o.b(ts.ac[acidx]->huffval[j]);
+          ts.ac_sent[acidx] = true;
+        }
+      }
+      done_multi = true;
+    }
+  }
+  if (!done_multi) {
+    for (int i = 0; i < sd.ncomps; i++) {                                                // emit_dht :256-291
+      const b200jpeg_component_info &c = p->comp_info[sd.ci[i]];
+      for (int z = 0; z < 2; z++) {
+        bool is_ac = z == 1;
+        if (!is_ac && !(sd.Ss == 0 && sd.Ah == 0)) continue;
+        if (is_ac && !sd.Se) continue;
+        int idx = is_ac ? c.ac_tbl_no : c.dc_tbl_no;
+        bool &sent = is_ac ? ts.ac_sent[idx] : ts.dc_sent[idx];
+        const HostHuff *h = is_ac ? ts.ac[idx] : ts.dc[idx];
+        if (sent) continue;
+        int len = huff_len(h);
+        o.w(0xFFC4); o.w(len + 2 + 1 + 16); o.b(idx + (is_ac ? 0x10 : 0));
+        for (int j = 1; j <= 16; j++) o.b(h->bits[j]);
+        for (int j = 0; j < len; j++) o.b(h->huffval[j]);
+        sent = true;
+      }
+    }
+  }
+  if ((int)ri != last_ri) { o.w(0xFFDD); o.w(4); o.w((int)ri); last_ri = (int)ri; }       // emit_dri
+  o.w(0xFFDA); o.w(2 * sd.ncomps + 2 + 1 + 3); o.b(sd.ncomps);                          // emit_sos :494-526
+  for (int i = 0; i < sd.ncomps; i++) {
+    const b200jpeg_component_info &c = p->comp_info[sd.ci[i]];
+    int td = (sd.Ss == 0 && sd.Ah == 0) ? c.dc_tbl_no : 0, ta = sd.Se ? c.ac_tbl_no : 0;
+    o.b(c.component_id); o.b((td << 4) + ta);
+  }
+  o.b(sd.Ss); o.b(sd.Se); o.b((sd.Ah << 4) + sd.Al);
+}
+
+static int collect_outputs(b200jpeg_encoder *e)
+{
+  Plan &pl = e->plan; const b200jpeg_params *p = &e->params; const int n = e->n; cudaStream_t s = e->stream;
+  const int nscans = (int)pl.scans.size();
+  int rc;
+  if ((rc = e->h_status.reserve((size_t)n * 4))) return rc;
+  if ((rc = e->h_out_pos.reserve((size_t)n * 8))) return rc;
+  if ((rc = e->h_scan_size.reserve((size_t)n * nscans * 4))) return rc;
+  CU(cudaMemcpyAsync(e->h_status.p, e->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(e->h_out_pos.p, e->d_out_pos.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(e->h_scan_size.p, e->d_scan_size.p, (size_t)n * nscans * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  const uint32_t *st = e->h_status.as<uint32_t>();
+  bool overflow = false;
+  for (int i = 0; i < n; i++) {
+    if (st[i] & 2u) { set_error("DCT coefficient out of range (image %d)", i); return B200JPEG_ERR_BAD_DCT_COEF; }
+    if (st[i] & 4u) overflow = true;
+  }
+  if (overflow) return 1;          // caller grows the buffers and reruns
+  // Huffman tables of every scan (DHT payloads only: first 288 bytes of each DevHuff)
+  const size_t tabset = sizeof(DevHuff) * HIST_SLOTS;
+  size_t ntab = pl.optimize ? (size_t)n * nscans * HIST_SLOTS : HIST_SLOTS;
+  if ((rc = e->h_tabs.reserve(ntab * sizeof(HostHuff)))) return rc;
+  if (pl.optimize)
+    CU(cudaMemcpy2DAsync(e->h_tabs.p, sizeof(HostHuff), e->d_tabs_scan.p, sizeof(DevHuff), sizeof(HostHuff), ntab, cudaMemcpyDeviceToHost, s));
+  else
+    CU(cudaMemcpy2DAsync(e->h_tabs.p, sizeof(HostHuff), e->d_tabs_fixed.p, sizeof(DevHuff), sizeof(HostHuff), ntab, cudaMemcpyDeviceToHost, s));
+  (void)tabset;
+  const unsigned long long *pos = e->h_out_pos.as<unsigned long long>();
+  size_t total = 0; std::vector<size_t> off(n);
+  for (int i = 0; i < n; i++) { off[i] = total; total += (size_t)pos[i]; }
+  e->last_scan_bytes = total;
+  if ((rc = e->h_out.reserve(total + 16))) return rc;
+  for (int i = 0; i < n; i++)
+    if (pos[i]) CU(cudaMemcpyAsync(e->h_out.as<uint8_t>() + off[i], e->d_out.as<uint8_t>() + (size_t)i * e->out_cap_per_image, (size_t)pos[i], cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  // assemble the files (write_file_header / write_frame_header / write_scan_header / EOI)
+  e->files.resize(n);
+  const HostHuff *ht = e->h_tabs.as<HostHuff>();
+  const uint32_t *ss = e->h_scan_size.as<uint32_t>();
+  for (int i = 0; i < n; i++) {
+    std::vector<uint8_t> &f = e->files[i];
+    f.clear(); f.reserve((size_t)pos[i] + 2048);
+    Bytes o{f};
+    write_file_header(p, o);
+    TblState ts;
+    const HostHuff *fixed = pl.optimize ? nullptr : ht;
+    for (int t = 0; t < 4; t++) { ts.dc[t] = fixed ? &fixed[t] : nullptr; ts.ac[t] = fixed ? &fixed[4 + t] : nullptr; ts.dc_sent[t] = ts.ac_sent[t] = false; }
+    int last_ri = 0;
+    const uint8_t *data = e->h_out.as<uint8_t>() + off[i];
+    for (int si = 0; si < nscans; si++) {
+      const ScanDesc &sd = pl.scans[si];
+      if (pl.optimize) {
+        uint32_t m = scan_slot_mask(pl, sd);
+        const HostHuff *set = ht + ((size_t)i * nscans + si) * HIST_SLOTS;
+        for (int t = 0; t < 4; t++) {
+          if (m & (1u << t)) { ts.dc[t] = &set[t]; ts.dc_sent[t] = false; }               // jpeg_gen_optimal_table clears sent_table (jchuff.c:1105)
+          if (m & (1u << (4 + t))) { ts.ac[t] = &set[4 + t]; ts.ac_sent[t] = false; }
+        }
+      }
+      if (si == 0) write_frame_header(p, pl.progressive, o);
+      write_scan_header(p, sd, ts, last_ri, 0, o);
+      size_t sz = ss[(size_t)si * n + i];
+      f.insert(f.end(), data, data + sz);
+      data += sz;
+    }
+    o.w(0xFFD9);
+  }
+  return B200JPEG_OK;
+}
+
+static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const void *pixels, int on_device,
+                         size_t row_pitch, size_t image_stride, int n_images, bool device_only)
+{
+  if (!e || !p || !pixels || n_images <= 0) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  int rc = b200jpeg_validate(p);
+  if (rc) return rc;
+  if (row_pitch < (size_t)p->image_width * p->input_components) { set_error("row_pitch smaller than a row"); return B200JPEG_ERR_PARAM; }
+  if (n_images > 1 && image_stride < row_pitch * (size_t)(p->image_height - 1) + (size_t)p->image_width * p->input_components) { set_error("image_stride smaller than an image"); return B200JPEG_ERR_PARAM; }
+  CU(cudaSetDevice(e->device));
+  e->params = *p; e->n = n_images;
+  if ((rc = build_plan(p, row_pitch, image_stride, e->plan))) return rc;
+  Timer tm{e};
+  const uint8_t *src_dev;
+  tm.mark("h2d");
+  if (on_device) src_dev = static_cast<const uint8_t *>(pixels);
+  else {
+    size_t bytes = image_stride * (size_t)(n_images - 1) + row_pitch * (size_t)(p->image_height - 1) + (size_t)p->image_width * p->input_components;
+    if ((rc = e->d_src.reserve(bytes))) return rc;
+    CU(cudaMemcpyAsync(e->d_src.p, pixels, bytes, cudaMemcpyHostToDevice, e->stream));
+    src_dev = e->d_src.as<uint8_t>();
+  }
+  for (int attempt = 0; attempt < 6; attempt++) {
+    tm.idx = 1;
+    if ((rc = run_pipeline(e, src_dev, tm))) return rc;
+    if (device_only) {
+      CU(cudaStreamSynchronize(e->stream));
+      // the overflow flag still matters for a meaningful timing run
+      if ((rc = e->h_status.reserve((size_t)n_images * 4))) return rc;
+      CU(cudaMemcpy(e->h_status.p, e->d_status.p, (size_t)n_images * 4, cudaMemcpyDeviceToHost));
+      bool ovf = false; for (int i = 0; i < n_images; i++) if (e->h_status.as<uint32_t>()[i] & 4u) ovf = true;
+      if (!ovf) { rc = B200JPEG_OK; break; }
+      rc = 1;
+    } else rc = collect_outputs(e);
+    if (rc != 1) break;
+    e->cap_factor *= 4.0;          // entropy-coded data did not fit: grow and rerun
+  }
+  if (rc == 1) { set_error("output does not fit even after growing buffers"); return B200JPEG_ERR_BUFFER; }
+  if (rc) return rc;
+  // stage timings
+  e->stage_ms.assign(tm.idx > 0 ? tm.idx - 1 : 0, 0.f);
+  for (size_t i = 0; i + 1 < tm.idx; i++) cudaEventElapsedTime(&e->stage_ms[i], e->ev[i], e->ev[i + 1]);
+  return B200JPEG_OK;
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int b200jpeg_encoder_create(b200jpeg_encoder **enc, int device)
+{
+  if (!enc) return B200JPEG_ERR_PARAM;
+  *enc = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) { set_error("no usable CUDA device (%s); libb200jpeg has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"); return B200JPEG_ERR_NO_DEVICE; }
+  if (device < 0 || device >= count) { set_error("device %d out of range (0..%d)", device, count - 1); return B200JPEG_ERR_PARAM; }
+  CU(cudaSetDevice(device));
+  b200jpeg_encoder *o = new b200jpeg_encoder();
+  o->device = device;
+  cudaError_t e2 = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking);
+  if (e2 != cudaSuccess) { set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e2)); delete o; return B200JPEG_ERR_CUDA; }
+  o->launches_at_create = g_kernel_launches;
+  const char *dbg = getenv("B200JPEG_KEEP_PLAIN");
+  o->keep_plain = dbg && dbg[0] == '1';
+  *enc = o;
+  return B200JPEG_OK;
+}
+
+void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
+{
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  DevBuf *db[] = {&e->d_src, &e->d_hist, &e->d_tabs_scan, &e->d_tabs_trellis, &e->d_tabs_fixed, &e->d_rec, &e->d_bt, &e->d_blk_bits, &e->d_blk_aux,
+                  &e->d_total_bits, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_bitbuf, &e->d_out, &e->d_qt, &e->d_tc};
+  for (DevBuf *b : db) b->release();
+  for (int i = 0; i < 4; i++) { e->d_coef[i].release(); e->d_raw[i].release(); e->d_plain[i].release(); }
+  PinBuf *pb[] = {&e->h_qt, &e->h_tc, &e->h_fixed, &e->h_status, &e->h_out_pos, &e->h_scan_size, &e->h_tabs, &e->h_out, &e->h_stage};
+  for (PinBuf *b : pb) b->release();
+  for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int b200jpeg_encode_batch(b200jpeg_encoder *enc, const b200jpeg_params *p, const void *pixels, int pixels_on_device,
+                          size_t row_pitch, size_t image_stride, int n_images)
+{
+  return encode_common(enc, p, pixels, pixels_on_device, row_pitch, image_stride, n_images, false);
+}
+int b200jpeg_encode_batch_device_only(b200jpeg_encoder *enc, const b200jpeg_params *p, const void *pixels_device,
+                                      size_t row_pitch, size_t image_stride, int n_images)
+{
+  return encode_common(enc, p, pixels_device, 1, row_pitch, image_stride, n_images, true);
+}
+
+int b200jpeg_get_output(b200jpeg_encoder *e, int i, const uint8_t **data, size_t *size)
+{
+  if (!e || i < 0 || i >= (int)e->files.size()) { set_error("no such output"); return B200JPEG_ERR_PARAM; }
+  if (data) *data = e->files[i].data();
+  if (size) *size = e->files[i].size();
+  return B200JPEG_OK;
+}
+size_t b200jpeg_last_scan_bytes(const b200jpeg_encoder *e) { return e ? e->last_scan_bytes : 0; }
+unsigned long long b200jpeg_kernel_launches(const b200jpeg_encoder *e) { return e ? g_kernel_launches - e->launches_at_create : 0; }
+int b200jpeg_last_stage_times(const b200jpeg_encoder *e, const char **names, float *ms, int max)
+{
+  if (!e) return 0;
+  int n = (int)e->stage_ms.size();
+  for (int i = 0; i < n && i < max; i++) { if (names) names[i] = e->ev_names[i]; if (ms) ms[i] = e->stage_ms[i]; }
+  return n < max ? n : max;
+}
+
+long b200jpeg_debug_get_coefs(b200jpeg_encoder *e, int image, int component, int plane, int16_t *dst, size_t dst_blocks,
+                              int *width_in_blocks, int *height_in_blocks)
+{
+  if (!e || image < 0 || image >= e->n || component < 0 || component >= e->plan.g.nc) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  const CompGeom &c = e->plan.g.c[component];
+  if (width_in_blocks) *width_in_blocks = c.wpad;
+  if (height_in_blocks) *height_in_blocks = c.hpad;
+  size_t nb = (size_t)c.blocks_per_image;
+  if (!dst) return (long)nb;
+  if (dst_blocks < nb) { set_error("buffer too small"); return B200JPEG_ERR_BUFFER; }
+  DevBuf *src = plane == 0 ? &e->d_coef[component] : plane == 1 ? &e->d_raw[component] : &e->d_plain[component];
+  if (plane == 2 && !(e->keep_plain && e->plan.trellis)) src = &e->d_coef[component];
+  if (!src->p) { set_error("plane not available"); return B200JPEG_ERR_STATE; }
+  std::vector<int16_t> tmp(nb * 64);
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemcpy(tmp.data(), src->as<int16_t>() + (size_t)image * nb * 64, nb * 128, cudaMemcpyDeviceToHost));
+  for (size_t b = 0; b < nb; b++) for (int k = 0; k < 64; k++) dst[b * 64 + kZigzag[k]] = tmp[b * 64 + k];   // zigzag -> natural
+  return (long)nb;
+}
+
+int b200jpeg_debug_get_huff(b200jpeg_encoder *e, int image, int scan, int is_ac, int tbl_no, b200jpeg_huff_tbl *out)
+{
+  if (!e || !out || image < 0 || image >= e->n || tbl_no < 0 || tbl_no > 3) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  const int nscans = (int)e->plan.scans.size();
+  DevHuff h;
+  CU(cudaSetDevice(e->device));
+  if (scan < 0) {          // scan = -1-ci : the trellis-phase tables of component ci
+    int ci = -1 - scan;
+    if (ci >= e->plan.g.nc) { set_error("bad component"); return B200JPEG_ERR_PARAM; }
+    CU(cudaMemcpy(&h, e->d_tabs_trellis.as<DevHuff>() + ((size_t)image * 4 + ci) * HIST_SLOTS + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));
+  } else {
+    if (scan >= nscans) { set_error("bad scan"); return B200JPEG_ERR_PARAM; }
+    if (e->plan.optimize) CU(cudaMemcpy(&h, e->d_tabs_scan.as<DevHuff>() + ((size_t)image * nscans + scan) * HIST_SLOTS + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));
+    else CU(cudaMemcpy(&h, e->d_tabs_fixed.as<DevHuff>() + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));
+  }
+  memset(out, 0, sizeof *out);
+  memcpy(out->bits, h.bits, 17); memcpy(out->huffval, h.huffval, 256); out->present = 1;
+  return B200JPEG_OK;
+}
+
+// ---- streaming shim: jpeg_start_compress / jpeg_write_scanlines / jpeg_finish_compress ----
+int b200jpeg_start_compress(b200jpeg_encoder *e, const b200jpeg_params *p)
+{
+  if (!e || !p) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  if (e->st_state != 0) { set_error("Improper call to JPEG library in state %d", 100 + e->st_state); return B200JPEG_ERR_STATE; }   // JERR_BAD_STATE
+  int rc = b200jpeg_validate(p);
+  if (rc) return rc;
+  size_t bytes = (size_t)p->image_width * p->input_components * p->image_height;
+  if ((rc = e->h_stage.reserve(bytes))) return rc;
+  e->st_params = *p; e->st_state = 1; e->st_next_row = 0;
+  return B200JPEG_OK;
+}
+int b200jpeg_write_scanlines(b200jpeg_encoder *e, const uint8_t *const *scanlines, int num_lines)
+{
+  if (!e || e->st_state != 1) { set_error("Improper call to JPEG library in state %d", e ? 100 + e->st_state : -1); return B200JPEG_ERR_STATE; }
+  const b200jpeg_params &p = e->st_params;
+  size_t rowbytes = (size_t)p.image_width * p.input_components;
+  int left = p.image_height - e->st_next_row;            // extra rows are ignored (jcapistd.c:120-123)
+  if (num_lines > left) num_lines = left;
+  for (int i = 0; i < num_lines; i++) memcpy(e->h_stage.as<uint8_t>() + (size_t)(e->st_next_row + i) * rowbytes, scanlines[i], rowbytes);
+  e->st_next_row += num_lines;
+  return num_lines;
+}
+int b200jpeg_finish_compress(b200jpeg_encoder *e, const uint8_t **jpeg, size_t *size)
+{
+  if (!e || e->st_state != 1) { set_error("Improper call to JPEG library in state %d", e ? 100 + e->st_state : -1); return B200JPEG_ERR_STATE; }
+  const b200jpeg_params &p = e->st_params;
+  if (e->st_next_row < p.image_height) { set_error("Application transferred too few scanlines"); return B200JPEG_ERR_STATE; }   // JERR_TOO_LITTLE_DATA
+  size_t rowbytes = (size_t)p.image_width * p.input_components;
+  e->st_state = 0;
+  int rc = encode_common(e, &p, e->h_stage.p, 0, rowbytes, rowbytes * p.image_height, 1, false);
+  if (rc) return rc;
+  return b200jpeg_get_output(e, 0, jpeg, size);
+}
+
+}  // extern "C"

@@ -1,0 +1,896 @@
+// kernels.cu -- sm_100a kernels of the JPEG-encode hot path (see kernels.cuh).
+// Compile with: -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
+#include "kernels.cuh"
+#include <cstdio>
+
+namespace b200 {
+
+unsigned long long g_kernel_launches = 0;
+#define LAUNCHED() (++g_kernel_launches)
+
+// zigzag index -> natural index (jutils.c:59-70) and its inverse
+__constant__ uint8_t c_zz[64] = {
+   0,  1,  8, 16,  9,  2,  3, 10, 17, 24, 32, 25, 18, 11,  4,  5,
+  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,  6,  7, 14, 21, 28,
+  35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+  58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+#define ZZ_LIST \
+  X(0,0) X(1,1) X(2,8) X(3,16) X(4,9) X(5,2) X(6,3) X(7,10) X(8,17) X(9,24) X(10,32) X(11,25) X(12,18) X(13,11) X(14,4) X(15,5) \
+  X(16,12) X(17,19) X(18,26) X(19,33) X(20,40) X(21,48) X(22,41) X(23,34) X(24,27) X(25,20) X(26,13) X(27,6) X(28,7) X(29,14) X(30,21) X(31,28) \
+  X(32,35) X(33,42) X(34,49) X(35,56) X(36,57) X(37,50) X(38,43) X(39,36) X(40,29) X(41,22) X(42,15) X(43,23) X(44,30) X(45,37) X(46,44) X(47,51) \
+  X(48,58) X(49,59) X(50,52) X(51,45) X(52,38) X(53,31) X(54,39) X(55,46) X(56,53) X(57,60) X(58,61) X(59,54) X(60,47) X(61,55) X(62,62) X(63,63)
+
+__device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(v); }   // v >= 0 ; JPEG_NBITS (jpeg_nbits.h)
+
+// =====================================================================
+// K1: colour conversion + downsampling + deringing + FDCT + quantization
+//     one thread per 8x8 block of one component.
+//     reference: jccolor.c:213-246 / jccolext.c:30-75, jcsample.c,
+//     jcprepct.c:135-192 (edge rules), jcdctmgr.c:416-498,576-604,611-682,
+//     693-772, jfdctint.c:142-286.
+// =====================================================================
+__device__ __forceinline__ int load_component(const uint8_t *__restrict__ px, int cs_mode, int comp)
+{
+  if (cs_mode == 2) return px[comp];
+  int r = px[0], g = px[1], b = px[2];
+  if (comp == 0) return (19595 * r + 38470 * g + 7471 * b + 32768) >> 16;
+  if (comp == 1) return (-11059 * r - 21709 * g + 32768 * b + (128 << 16) + 32767) >> 16;
+  return (32768 * r - 27439 * g - 5329 * b + (128 << 16) + 32767) >> 16;
+}
+
+#define DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
+template <int PASS>
+__device__ __forceinline__ void fdct_1d(int &d0, int &d1, int &d2, int &d3, int &d4, int &d5, int &d6, int &d7)
+{
+  int t0 = d0 + d7, t7 = d0 - d7, t1 = d1 + d6, t6 = d1 - d6;
+  int t2 = d2 + d5, t5 = d2 - d5, t3 = d3 + d4, t4 = d3 - d4;
+  int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+  constexpr int SH = PASS == 0 ? 13 - 2 : 13 + 2;
+  if (PASS == 0) { d0 = (t10 + t11) << 2; d4 = (t10 - t11) << 2; }
+  else { d0 = DESCALE(t10 + t11, 2); d4 = DESCALE(t10 - t11, 2); }
+  int z1 = (t12 + t13) * 4433;
+  d2 = DESCALE(z1 + t13 * 6270, SH);
+  d6 = DESCALE(z1 + t12 * (-15137), SH);
+  z1 = t4 + t7; int z2 = t5 + t6, z3 = t4 + t6, z4 = t5 + t7;
+  int z5 = (z3 + z4) * 9633;
+  t4 *= 2446; t5 *= 16819; t6 *= 25172; t7 *= 12299;
+  z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
+  z3 += z5; z4 += z5;
+  d7 = DESCALE(t4 + z1 + z3, SH);
+  d5 = DESCALE(t5 + z2 + z4, SH);
+  d3 = DESCALE(t6 + z2 + z3, SH);
+  d1 = DESCALE(t7 + z1 + z4, SH);
+}
+
+// jcdctmgr.c:387-403 (fp32, no contraction: this TU is built with -fmad=false)
+__device__ __noinline__ float catmull_rom(int v1, int v2, int v3, int v4, float t, int size)
+{
+  const int tan1 = (v3 - v1) * size, tan2 = (v4 - v2) * size;
+  const float t2 = t * t, t3 = t2 * t;
+  const float f1 = 2.f * t3 - 3.f * t2 + 1.f;
+  const float f2 = -2.f * t3 + 3.f * t2;
+  const float f3 = t3 - 2.f * t2 + t;
+  const float f4 = t3 - t2;
+  return (float)v2 * f1 + (float)tan1 * f3 + (float)v3 * f2 + (float)tan2 * f4;
+}
+// jcdctmgr.c:416-498; data[] natural order, dynamic indexing (rare slow path)
+__device__ __noinline__ void deringing_slow(int *data, int q0, int sum, int cnt)
+{
+  const int maxsample = 127, size = 64;
+  int m = min(min(31, 2 * q0), (maxsample * size - sum) / cnt);
+  int maxover = maxsample + m;
+  int n = 0;
+  do {
+    if (data[c_zz[n]] < maxsample) { n++; continue; }
+    int start = n;
+    while (++n < size && data[c_zz[n]] >= maxsample) {}
+    int end = n;
+    int f1 = data[c_zz[start >= 1 ? start - 1 : 0]];
+    int f2 = data[c_zz[start >= 2 ? start - 2 : 0]];
+    int l1 = data[c_zz[end < size - 1 ? end : size - 1]];
+    int l2 = data[c_zz[end < size - 2 ? end + 1 : size - 1]];
+    int fslope = max(f1 - f2, maxsample - f1);
+    int lslope = max(l1 - l2, maxsample - l1);
+    if (start == 0) fslope = lslope;
+    if (end == size) lslope = fslope;
+    int length = end - start;
+    float step = 1.f / (float)(length + 1);
+    float position = step;
+    for (int i = start; i < end; i++, position += step) {
+      int tmp = (int)ceilf(catmull_rom(maxsample - fslope, maxsample, maxsample, maxsample - lslope, position, length));
+      data[c_zz[i]] = min(tmp, maxover);
+    }
+    n++;
+  } while (n < size);
+}
+
+__device__ __forceinline__ unsigned quant_one(int x, QuantConst k, int dering)
+{
+  unsigned a = (unsigned)abs(x) + k.bias;
+  int q = (int)(((unsigned long long)a * k.mul) >> k.shift);
+  if (dering) q = min(q, 1023);            // (1 << (8 + 2)) - 1
+  return (unsigned)(x < 0 ? -q : q);
+}
+
+__global__ void __launch_bounds__(128) k_forward(Geom g, int ci, const uint8_t *__restrict__ src,
+                                                 const QuantTables *__restrict__ qt, int dering)
+{
+  const CompGeom &c = g.c[ci];
+  int bx = blockIdx.x * blockDim.x + threadIdx.x;
+  int by = blockIdx.y, img = blockIdx.z;
+  if (bx >= c.wib) return;
+  const uint8_t *base = src + (size_t)img * g.image_stride;
+  int ws[64];
+  const int comp = g.cs_mode == 1 ? 0 : ci;
+#pragma unroll
+  for (int y = 0; y < 8; y++) {
+    int yo = by * 8 + y;
+    int yy = min(yo, c.rows_avail - 1);                   // expand_bottom_edge on downsampled rows
+    int grp = yy / c.v, sub = yy - grp * c.v;
+    int iy0 = grp * g.vmax + sub * c.vx;
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+      int xo = bx * 8 + x;
+      int sum = 0;
+      for (int dv = 0; dv < c.vx; dv++) {
+        int iy = min(iy0 + dv, g.H - 1);                  // bottom row replication inside the row group
+        const uint8_t *row = base + (size_t)iy * g.row_pitch;
+        for (int du = 0; du < c.hx; du++) {
+          int ix = min(xo * c.hx + du, g.W - 1);          // expand_right_edge (jcsample.c:98-116)
+          sum += load_component(row + (size_t)ix * g.in_comps, g.cs_mode, comp);
+        }
+      }
+      int val;
+      if (c.hx == 1 && c.vx == 1) val = sum;
+      else if (c.hx == 2 && c.vx == 1) val = (sum + (xo & 1)) >> 1;          // jcsample.c:226-254
+      else if (c.hx == 2 && c.vx == 2) val = (sum + 1 + (xo & 1)) >> 2;      // jcsample.c:263-295
+      else { int np = c.hx * c.vx; val = (sum + np / 2) / np; }              // jcsample.c:151-190
+      ws[8 * y + x] = val - 128;                                             // convsamp
+    }
+  }
+  if (dering) {
+    int sum = 0, cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 64; i++) { sum += ws[i]; cnt += (ws[i] >= 127); }
+    if (cnt != 0 && cnt != 64) {
+      int tmp[64];
+#pragma unroll
+      for (int i = 0; i < 64; i++) tmp[i] = ws[i];
+      deringing_slow(tmp, (int)qt->q[c.qt][0].d >> 3, sum, cnt);
+#pragma unroll
+      for (int i = 0; i < 64; i++) ws[i] = tmp[i];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+    fdct_1d<0>(ws[8 * r], ws[8 * r + 1], ws[8 * r + 2], ws[8 * r + 3], ws[8 * r + 4], ws[8 * r + 5], ws[8 * r + 6], ws[8 * r + 7]);
+#pragma unroll
+  for (int col = 0; col < 8; col++)
+    fdct_1d<1>(ws[col], ws[8 + col], ws[16 + col], ws[24 + col], ws[32 + col], ws[40 + col], ws[48 + col], ws[56 + col]);
+
+  // quantize (jcdctmgr.c:611-682 == sign(x)*floor((|x| + d/2)/d), d = 8Q) + deringing clamp (:761-770),
+  // packed two int16 per 32-bit word in ZIGZAG order
+  size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
+  uint4 *dq = reinterpret_cast<uint4 *>(c.coef + blk * 64);
+  uint4 *dr = reinterpret_cast<uint4 *>(c.raw + blk * 64);
+  const QuantConst *qc = qt->q[c.qt];
+  unsigned pq[32], pr[32];
+#define X(k, n) { unsigned qq = quant_one(ws[n], qc[n], dering) & 0xFFFFu, rr = (unsigned)ws[n] & 0xFFFFu; \
+                  if ((k) & 1) { pq[(k) >> 1] |= qq << 16; pr[(k) >> 1] |= rr << 16; } else { pq[(k) >> 1] = qq; pr[(k) >> 1] = rr; } }
+  ZZ_LIST
+#undef X
+#pragma unroll
+  for (int v = 0; v < 8; v++) {
+    dq[v] = make_uint4(pq[4 * v], pq[4 * v + 1], pq[4 * v + 2], pq[4 * v + 3]);
+    dr[v] = make_uint4(pr[4 * v], pr[4 * v + 1], pr[4 * v + 2], pr[4 * v + 3]);
+  }
+}
+
+void launch_forward(const Geom &g, int ci, const uint8_t *src, const QuantTables *qt, int dering, int n, cudaStream_t s)
+{
+  const CompGeom &c = g.c[ci];
+  dim3 grid((c.wib + 127) / 128, c.hib, n);
+  k_forward<<<grid, 128, 0, s>>>(g, ci, src, qt, dering);
+  LAUNCHED();
+}
+
+// =====================================================================
+// dummy blocks (jccoefct.c:312-345 == :443-476): AC = 0; right-edge dummies
+// take the DC of the last real block of the row, bottom dummy rows take, per
+// MCU, the DC of the last block of that MCU in the row above.
+// =====================================================================
+__global__ void k_dummy(Geom g, int ci)
+{
+  const CompGeom &c = g.c[ci];
+  int img = blockIdx.y;
+  long long nd_right = (long long)c.hib * (c.wpad - c.wib);
+  long long nd = nd_right + (long long)(c.hpad - c.hib) * c.wpad;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nd) return;
+  int r, b, srow, scol;
+  if (t < nd_right) { r = (int)(t / (c.wpad - c.wib)); b = c.wib + (int)(t % (c.wpad - c.wib)); srow = r; scol = c.wib - 1; }
+  else {
+    long long u = t - nd_right; r = c.hib + (int)(u / c.wpad); b = (int)(u % c.wpad);
+    srow = c.hib - 1; scol = min((b / c.h) * c.h + c.h - 1, c.wib - 1);
+  }
+  int16_t *dst = c.coef + (((size_t)img * c.hpad + r) * c.wpad + b) * 64;
+  int16_t dc = c.coef[(((size_t)img * c.hpad + srow) * c.wpad + scol) * 64];
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+  d4[0] = make_uint4((unsigned)(uint16_t)dc, 0, 0, 0);
+  for (int v = 1; v < 8; v++) d4[v] = make_uint4(0, 0, 0, 0);
+}
+void launch_dummy(const Geom &g, int ci, int n, cudaStream_t s)
+{
+  const CompGeom &c = g.c[ci];
+  long long nd = (long long)c.hib * (c.wpad - c.wib) + (long long)(c.hpad - c.hib) * c.wpad;
+  if (nd == 0) return;
+  dim3 grid((unsigned)((nd + 127) / 128), n);
+  k_dummy<<<grid, 128, 0, s>>>(g, ci);
+  LAUNCHED();
+}
+
+// =====================================================================
+// scan-order block addressing (compress_output, jccoefct.c:498-553)
+// =====================================================================
+struct BlockRef { const int16_t *blk; int sci; int mcu; int k; };
+
+__device__ __forceinline__ const int16_t *block_ptr(const Geom &g, const ScanDesc &sd, int img, long long t, int &sci, long long &mcu, int &k)
+{
+  mcu = t / sd.bim; k = (int)(t - mcu * sd.bim);
+  sci = sd.k_comp[k];
+  const CompGeom &c = g.c[sd.ci[sci]];
+  long long mrow = mcu / sd.per_row; int mcol = (int)(mcu - mrow * sd.per_row);
+  int mh = sd.ncomps == 1 ? 1 : c.v, mw = sd.ncomps == 1 ? 1 : c.h;
+  long long row = mrow * mh + sd.k_y[k]; int col = mcol * mw + sd.k_x[k];
+  return c.coef + (((size_t)img * c.hpad + row) * c.wpad + col) * 64;
+}
+// DC value of the previous block of the same component in scan order (or 0)
+__device__ __forceinline__ int prev_dc(const Geom &g, const ScanDesc &sd, int img, long long t, int sci, long long mcu, int k)
+{
+  long long tp;
+  if (k > sd.k_first[sci]) tp = t - 1;
+  else if (mcu > 0) tp = t - sd.bim + sd.k_count[sci] - 1;
+  else return 0;
+  int s2, k2; long long m2;
+  const int16_t *p = block_ptr(g, sd, img, tp, s2, m2, k2);
+  return p[0];
+}
+
+// Walks one block the way encode_one_block (jchuff.c:563-661) / htest_one_block
+// (jchuff.c:812-878) do, calling sink.dc(nbits, valuebits) and
+// sink.ac(symbol, nbits, valuebits) in stream order.
+template <class Sink>
+__device__ __forceinline__ void walk_seq_block(const int16_t *__restrict__ blk, int last_dc, Sink &sink)
+{
+  const uint4 *b4 = reinterpret_cast<const uint4 *>(blk);
+  int r = 0;
+#pragma unroll
+  for (int v = 0; v < 8; v++) {
+    uint4 q = b4[v];
+    unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      int val = (int)(int16_t)((w[j >> 1] >> ((j & 1) * 16)) & 0xFFFF);
+      if (v == 0 && j == 0) {
+        int temp = val - last_dc, temp2 = temp;
+        if (temp < 0) { temp = -temp; temp2--; }
+        int nb = nbits_of(temp);
+        sink.dc(nb, temp2);
+      } else if (val == 0) {
+        r++;
+      } else {
+        while (r > 15) { sink.ac(0xF0, 0, 0); r -= 16; }
+        int temp = val, temp2 = val;
+        if (temp < 0) { temp = -temp; temp2--; }
+        int nb = nbits_of(temp);
+        sink.ac((r << 4) + nb, nb, temp2);
+        r = 0;
+      }
+    }
+  }
+  if (r > 0) sink.ac(0, 0, 0);
+}
+
+// ---------------------------------------------------------------------
+// statistics pass (encode_mcu_gather, jchuff.c:886-915)
+// ---------------------------------------------------------------------
+struct HistSink {
+  unsigned *dc_hist, *ac_hist; int bad;
+  __device__ void dc(int nb, int) { if (nb > 11) bad = 1; atomicAdd(&dc_hist[nb], 1u); }
+  __device__ void ac(int sym, int nb, int) { if (nb > 10) bad = 1; atomicAdd(&ac_hist[sym], 1u); }
+};
+
+__global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
+{
+  __shared__ unsigned sh[HIST_SLOTS * HIST_BINS];
+  int img = blockIdx.y;
+  for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < sd.nblocks) {
+    int sci, k; long long mcu;
+    const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+    int last = prev_dc(g, sd, img, t, sci, mcu, k);
+    const CompGeom &c = g.c[sd.ci[sci]];
+    HistSink sink{sh + c.dc_tbl * HIST_BINS, sh + (4 + c.ac_tbl) * HIST_BINS, 0};
+    walk_seq_block(blk, last, sink);
+    if (sink.bad) atomicOr(&status[img], 2u);          // JERR_BAD_DCT_COEF
+  }
+  __syncthreads();
+  uint32_t *gh = hist + (size_t)img * HIST_SLOTS * HIST_BINS;
+  for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&gh[i], sh[i]);
+}
+void launch_gather_seq(const Geom &g, const ScanDesc &sd, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
+{
+  dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
+  k_gather_seq<<<grid, 256, 0, s>>>(g, sd, hist, status);
+  LAUNCHED();
+}
+
+// =====================================================================
+// optimal Huffman table from counts: jpeg_gen_optimal_table (jchuff.c:947-1106)
+// + jpeg_make_c_derived_tbl (jchuff.c:231-318).  One warp per (image, slot).
+// The two-smallest search of :997-1011 ("<=" => the LARGER index wins ties,
+// c1 = overall minimum, c2 = minimum of the rest) runs across the warp; the
+// code-size chains (:1021-1034) are replaced by a reverse sweep over the
+// recorded merge list, which yields the same leaf depths.
+// =====================================================================
+__global__ void __launch_bounds__(32) k_gen_tables(const uint32_t *__restrict__ hist, DevHuff *__restrict__ tabs,
+                                                   size_t tabs_image_stride, uint32_t slot_mask)
+{
+  int img = blockIdx.y, slot = blockIdx.x, lane = threadIdx.x;
+  if (!((slot_mask >> slot) & 1)) return;
+  __shared__ long long freq[257];
+  __shared__ short nz_index[257];
+  __shared__ short m1[257], m2[257];
+  __shared__ int depth[257];
+  __shared__ int nnz_s;
+  const uint32_t *h = hist + ((size_t)img * HIST_SLOTS + slot) * HIST_BINS;
+  if (lane == 0) {
+    int n = 0;
+    for (int i = 0; i < 257; i++) {
+      long long f = (i == 256) ? 1 : (long long)(h[i]);
+      if (f) { nz_index[n] = (short)i; freq[n] = f; n++; }
+    }
+    nnz_s = n;
+  }
+  __syncwarp();
+  const int nnz = nnz_s;
+  int nmerge = 0;
+  for (;;) {
+    // key = (freq << 9) | (511 - idx): min key == smallest freq, largest index on ties
+    unsigned long long best = ~0ull;
+    for (int i = lane; i < nnz; i += 32) {
+      long long f = freq[i];
+      if (f <= 1000000000LL) { unsigned long long key = ((unsigned long long)f << 9) | (unsigned)(511 - i); if (key < best) best = key; }
+    }
+    for (int o = 16; o; o >>= 1) { unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); if (other < best) best = other; }
+    if (best == ~0ull) break;
+    int c1 = 511 - (int)(best & 511);
+    unsigned long long best2 = ~0ull;
+    for (int i = lane; i < nnz; i += 32) {
+      long long f = freq[i];
+      if (i != c1 && f <= 1000000000LL) { unsigned long long key = ((unsigned long long)f << 9) | (unsigned)(511 - i); if (key < best2) best2 = key; }
+    }
+    for (int o = 16; o; o >>= 1) { unsigned long long other = __shfl_xor_sync(0xffffffffu, best2, o); if (other < best2) best2 = other; }
+    if (best2 == ~0ull) break;
+    int c2 = 511 - (int)(best2 & 511);
+    if (lane == 0) { freq[c1] += freq[c2]; freq[c2] = 1000000001LL; m1[nmerge] = (short)c1; m2[nmerge] = (short)c2; }
+    nmerge++;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    DevHuff *out = reinterpret_cast<DevHuff *>(reinterpret_cast<char *>(tabs) + (size_t)img * tabs_image_stride) + slot;
+    for (int i = 0; i < nnz; i++) depth[i] = 0;
+    for (int t = nmerge - 1; t >= 0; t--) { int d = depth[m1[t]] + 1; depth[m1[t]] = d; depth[m2[t]] = d; }
+    unsigned char bits[33]; int bit_pos[33];
+    for (int i = 0; i <= 32; i++) bits[i] = 0;
+    for (int i = 0; i < nnz; i++) { int d = depth[i] > 32 ? 32 : depth[i]; bits[d]++; }
+    int p = 0;
+    for (int i = 1; i <= 32; i++) { bit_pos[i] = p; p += bits[i]; }
+    int i;
+    for (i = 32; i > 16; i--) {
+      while (bits[i] > 0) {
+        int j = i - 2;
+        while (bits[j] == 0) j--;
+        bits[i] -= 2; bits[i - 1]++; bits[j + 1] += 2; bits[j]--;
+      }
+    }
+    while (bits[i] == 0) i--;
+    bits[i]--;
+    for (int l = 0; l <= 16; l++) out->bits[l] = bits[l];
+    for (int s = 0; s < nnz - 1; s++) { int d = depth[s] > 32 ? 32 : depth[s]; out->huffval[bit_pos[d]] = (uint8_t)nz_index[s]; bit_pos[d]++; }
+    // derived table (C.1-C.3)
+    for (int s = 0; s < 256; s++) { out->code[s] = 0; out->size[s] = 0; }
+    int nsym = 0; unsigned code = 0;
+    for (int l = 1; l <= 16; l++) {
+      for (int c = 0; c < bits[l]; c++) { int sym = out->huffval[nsym++]; out->code[sym] = (uint16_t)code; out->size[sym] = (uint8_t)l; code++; }
+      code <<= 1;
+    }
+    out->nsym16 = (uint16_t)nsym; out->nsym = (uint8_t)nsym;
+  }
+}
+void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_image_stride, uint32_t slot_mask, int n, cudaStream_t s)
+{
+  dim3 grid(HIST_SLOTS, n);
+  k_gen_tables<<<grid, 32, 0, s>>>(hist, tabs, tabs_image_stride, slot_mask);
+  LAUNCHED();
+}
+
+// jcphuff.c:257-264: in trellis passes every symbol 16*i+j (i<16, j<12) starts with count 1
+__global__ void k_seed_hist(uint32_t *hist, int slot)
+{
+  int img = blockIdx.x, t = threadIdx.x;
+  if ((t & 15) < 12) hist[((size_t)img * HIST_SLOTS + slot) * HIST_BINS + t] = 1;
+}
+void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s) { k_seed_hist<<<n, 256, 0, s>>>(hist, slot); LAUNCHED(); }
+
+// =====================================================================
+// trellis quantization, AC part: quantize_trellis (jcdctmgr.c:936-1330)
+// restricted to its default option set.  One thread per block.
+//   phase 1: norm (natural order, serial fp32), lambda, accumulated zero
+//            distortion (zigzag order, serial fp32), compact list of the
+//            positions whose plain-quantized value is non-zero;
+//   phase 2: for each listed position the best (predecessor, candidate) pair,
+//            strict '<' in (predecessor, candidate) order  (:1157-1184);
+//   phase 3: best end-of-block position (:1187-1207) and back-tracking
+//            (:1211-1222).
+// =====================================================================
+#define TRELLIS_THREADS 128
+__global__ void __launch_bounds__(TRELLIS_THREADS) k_trellis_ac(Geom g, int ci, const TrellisConsts *__restrict__ tc,
+                                                                const DevHuff *__restrict__ tabs, size_t tabs_image_stride,
+                                                                DcRec *__restrict__ rec)
+{
+  const CompGeom &c = g.c[ci];
+  __shared__ uint8_t acsi[256];
+  int img = blockIdx.z, by = blockIdx.y;
+  {
+    const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)img * tabs_image_stride) + (4 + c.ac_tbl);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) acsi[i] = ac->size[i];
+  }
+  __syncthreads();
+  int bx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bx >= c.wib) return;
+  size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
+  const uint4 *r4 = reinterpret_cast<const uint4 *>(c.raw + blk * 64);
+  uint4 *q4 = reinterpret_cast<uint4 *>(c.coef + blk * 64);
+  unsigned rw[32], qw[32];
+#pragma unroll
+  for (int v = 0; v < 8; v++) {
+    uint4 a = r4[v]; rw[4 * v] = a.x; rw[4 * v + 1] = a.y; rw[4 * v + 2] = a.z; rw[4 * v + 3] = a.w;
+    uint4 b = q4[v]; qw[4 * v] = b.x; qw[4 * v + 1] = b.y; qw[4 * v + 2] = b.z; qw[4 * v + 3] = b.w;
+  }
+#define RAWZ(k) ((int)(int16_t)((rw[(k) >> 1] >> (((k) & 1) * 16)) & 0xFFFF))
+#define QNTZ(k) ((int)(int16_t)((qw[(k) >> 1] >> (((k) & 1) * 16)) & 0xFFFF))
+  // norm over natural order i = 1..63  (:1026-1030)
+  float norm = 0.0f;
+  {
+    int nat[64];
+#define X(k, n) nat[n] = RAWZ(k);
+    ZZ_LIST
+#undef X
+#pragma unroll
+    for (int i = 1; i < 64; i++) norm += (float)(nat[i] * nat[i]);
+  }
+  norm = (float)((double)norm / 63.0);
+  float lambda;
+  if (tc->use_norm) lambda = (float)(tc->p1 / (tc->p2 + (double)norm));     // :1032-1035 (lambda_base == 1)
+  else lambda = tc->lambda_const;
+  const float *wz = tc->w_zz[c.qt];
+  const int *q8 = tc->q8_zz[c.qt];
+  {
+    DcRec rr; rr.lambda_dc = lambda * wz[0]; rr.raw_dc = (int16_t)RAWZ(0); rr.pad = 0;
+    rec[((size_t)img * c.hib + by) * c.wib + bx] = rr;
+  }
+
+  // phase 1
+  float e_azd_at[64], e_azd_before[64], e_acc[64];
+  uint8_t e_pos[64], e_rs[64], e_k[64];
+  short e_qv[64], e_x[64];
+  int m = 0;
+  float azd = 0.0f;
+  const int maxq = (1 << tc->max_coef_bits) - 1;
+#pragma unroll
+  for (int i = 1; i < 64; i++) {
+    int x = abs(RAWZ(i));
+    float before = azd;
+    azd = (float)(x * x) * lambda * wz[i] + azd;                               // :1134
+    int qv = abs(QNTZ(i));
+    if (qv != 0) {
+      e_pos[m] = (uint8_t)i; e_x[m] = (short)RAWZ(i); e_qv[m] = (short)min(qv, maxq); e_azd_at[m] = azd; e_azd_before[m] = before; m++;
+    }
+  }
+  const float azd63 = azd;
+  const int zrl_bits = acsi[0xF0];
+
+  // phase 2
+  for (int t = 0; t < m; t++) {
+    int i = e_pos[t];
+    int x = abs((int)e_x[t]);
+    int q = q8[i], qv = e_qv[t];
+    int nc = nbits_of(qv);
+    float wl = wz[i];
+    float best = 1e38f; int best_s = 0, best_k = -1;
+    float before = e_azd_before[t];
+    float cand_dist[16];
+    for (int k = 0; k < nc; k++) {
+      int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
+      int delta = cand * q - x;
+      cand_dist[k] = (float)(delta * delta) * lambda * wl;                     // :1151
+    }
+    for (int s = -1; s < t; s++) {                                             // s = -1: "block start" (j = Ss-1)
+      int j = s < 0 ? 0 : e_pos[s];
+      int zero_run = i - 1 - j;
+      if ((zero_run >> 4) && zrl_bits == 0) continue;
+      int run_bits = (zero_run >> 4) * zrl_bits;
+      zero_run &= 15;
+      float tail = s < 0 ? (before - 0.0f) + 0.0f : (before - e_azd_at[s]) + e_acc[s];
+      for (int k = 0; k < nc; k++) {
+        int coef_bits = acsi[16 * zero_run + k + 1];
+        if (coef_bits == 0) continue;
+        float cost = (float)(coef_bits + (k + 1) + run_bits) + cand_dist[k];
+        cost += tail;
+        if (cost < best) { best = cost; best_s = s + 1; best_k = k; }
+      }
+    }
+    e_acc[t] = best; e_rs[t] = (uint8_t)best_s; e_k[t] = (uint8_t)(best_k < 0 ? 255 : best_k);
+  }
+
+  // phase 3
+  int last = 0;                                  // 1-based entry index, 0 = none
+  {
+    float best_cost = azd63 + (float)acsi[0];
+    for (int t = 0; t < m; t++) {
+      float cst = e_acc[t] + azd63 - e_azd_at[t];
+      if (e_pos[t] < 63) cst += (float)acsi[0];
+      if (cst < best_cost) { best_cost = cst; last = t + 1; }
+    }
+  }
+  // output: zeros except the back-tracked chain; DC slot untouched here
+  unsigned ow[32];
+#pragma unroll
+  for (int v = 0; v < 32; v++) ow[v] = 0;
+  ow[0] = qw[0] & 0xFFFFu;
+  uint4 *o4 = q4;
+#pragma unroll
+  for (int v = 0; v < 8; v++) o4[v] = make_uint4(ow[4 * v], ow[4 * v + 1], ow[4 * v + 2], ow[4 * v + 3]);
+  int16_t *o16 = c.coef + blk * 64;
+  while (last != 0) {
+    int t = last - 1;
+    int i = e_pos[t], qv = e_qv[t], nc = nbits_of(qv), k = e_k[t];
+    int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
+    int sgn = ((int)e_x[t]) >> 31;
+    o16[i] = (int16_t)((cand ^ sgn) - sgn);
+    last = e_rs[t];
+  }
+}
+#undef RAWZ
+#undef QNTZ
+
+
+void launch_trellis_ac(const Geom &g, int ci, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_image_stride,
+                       DcRec *rec, int n, cudaStream_t s)
+{
+  const CompGeom &c = g.c[ci];
+  dim3 grid((c.wib + TRELLIS_THREADS - 1) / TRELLIS_THREADS, c.hib, n);
+  k_trellis_ac<<<grid, TRELLIS_THREADS, 0, s>>>(g, ci, tc, tabs, tabs_image_stride, rec);
+  LAUNCHED();
+}
+
+// =====================================================================
+// trellis quantization, DC part (jcdctmgr.c:1045-1118 forward, :1308-1327
+// back-track).  The Viterbi chain runs along one block row; last_dc carries
+// from block row to block row inside an iMCU row (jccoefct.c:418, :1320).
+// One thread per (image, iMCU row).  bt[] holds, per block, the 9 back
+// pointers (4 bits each), the unsigned quantized value and the sign.
+// =====================================================================
+__global__ void __launch_bounds__(64) k_trellis_dc(Geom g, int ci, const TrellisConsts *__restrict__ tc,
+                                                   const DevHuff *__restrict__ tabs, size_t tabs_image_stride,
+                                                   const DcRec *__restrict__ rec, unsigned long long *__restrict__ bt)
+{
+  const CompGeom &c = g.c[ci];
+  __shared__ uint8_t dcsi[32];
+  int img = blockIdx.y;
+  {
+    const DevHuff *dc = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)img * tabs_image_stride) + c.dc_tbl;
+    if (threadIdx.x < 32) dcsi[threadIdx.x] = dc->size[threadIdx.x];
+  }
+  __syncthreads();
+  int imcu = blockIdx.x * blockDim.x + threadIdx.x;
+  int n_imcu = (c.hib + c.v - 1) / c.v;
+  if (imcu >= n_imcu) return;
+  const int q = tc->q8_zz[c.qt][0];
+  int ncand = (2 + 60 / (q >> 3)) | 1; if (ncand > 9) ncand = 9;     // get_num_dc_trellis_candidates (:929-933)
+  const int half = ncand / 2;
+  const int lim = 1 << tc->max_coef_bits;
+  int last_dc = 0;
+  for (int br = 0; br < c.v; br++) {
+    int row = imcu * c.v + br;
+    if (row >= c.hib) break;
+    size_t rbase = ((size_t)img * c.hib + row) * c.wib;
+    float acc[9]; int prevc[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) { acc[k] = 0.f; prevc[k] = 0; }
+    for (int bi = 0; bi < c.wib; bi++) {
+      DcRec r = rec[rbase + bi];
+      int raw = r.raw_dc, sign = raw >> 31, x = abs(raw);
+      int qval = (x + q / 2) / q;
+      float nacc[9]; int cand[9];
+      unsigned long long w = 0;
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        nacc[k] = 0.f; cand[k] = 0;
+        if (k < ncand) {
+          int cd = qval - half + k;
+          if (cd >= lim) cd = lim - 1;
+          if (cd <= -lim) cd = -lim + 1;
+          int delta = cd * q - x;
+          float dist = (float)(delta * delta) * r.lambda_dc;
+          cd *= 1 + 2 * sign;
+          cand[k] = cd;
+          if (bi == 0) {
+            int bits = nbits_of(abs(cd - last_dc));
+            nacc[k] = (float)(bits + dcsi[bits]) + dist;
+          } else {
+            float best = 0.f; int bl = 0;
+#pragma unroll
+            for (int l = 0; l < 9; l++) {
+              if (l < ncand) {
+                int bits = nbits_of(abs(cd - prevc[l]));
+                float cost = (float)(bits + dcsi[bits]) + dist + acc[l];
+                if (l == 0 || cost < best) { best = cost; bl = l; }
+              }
+            }
+            nacc[k] = best; w |= (unsigned long long)bl << (4 * k);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 9; k++) { acc[k] = nacc[k]; prevc[k] = cand[k]; }
+      w |= (unsigned long long)(qval & 0xFFF) << 36;
+      w |= (unsigned long long)(sign & 1) << 48;
+      bt[rbase + bi] = w;
+    }
+    int j = 0; float bj = acc[0];
+#pragma unroll
+    for (int i = 1; i < 9; i++) if (i < ncand && acc[i] < bj) { bj = acc[i]; j = i; }
+    for (int bi = c.wib - 1; bi >= 0; bi--) {
+      unsigned long long w = bt[rbase + bi];
+      int qval = (int)((w >> 36) & 0xFFF), sg = (int)((w >> 48) & 1);
+      int cd = qval - half + j;
+      if (cd >= lim) cd = lim - 1;
+      if (cd <= -lim) cd = -lim + 1;
+      if (sg) cd = -cd;
+      c.coef[(((size_t)img * c.hpad + row) * c.wpad + bi) * 64] = (int16_t)cd;
+      if (bi == c.wib - 1) last_dc = cd;
+      j = (int)((w >> (4 * j)) & 0xF);
+    }
+  }
+}
+void launch_trellis_dc(const Geom &g, int ci, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_image_stride,
+                       const DcRec *rec, unsigned long long *bt, int n, cudaStream_t s)
+{
+  const CompGeom &c = g.c[ci];
+  int n_imcu = (c.hib + c.v - 1) / c.v;
+  dim3 grid((n_imcu + 63) / 64, n);
+  k_trellis_dc<<<grid, 64, 0, s>>>(g, ci, tc, tabs, tabs_image_stride, rec, bt);
+  LAUNCHED();
+}
+
+// =====================================================================
+// entropy coding, pass A: bits per block; pass B: exclusive scan;
+// pass C: bit packing; pass D: 0xFF byte stuffing + end-of-scan padding.
+// (encode_mcu_huff/encode_one_block jchuff.c:563-763, flush_bits :479-533)
+// =====================================================================
+struct ScanTables {            // the 8 table slots of one image, staged in shared memory
+  uint16_t code[HIST_SLOTS][256];
+  uint8_t size[HIST_SLOTS][256];
+};
+__device__ __forceinline__ void load_scan_tables(ScanTables &st, const DevHuff *tabs, size_t stride, int img, const Geom &g, const ScanDesc &sd, bool want_codes)
+{
+  const DevHuff *t = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)img * stride);
+  for (int i = 0; i < sd.ncomps; i++) {
+    const CompGeom &c = g.c[sd.ci[i]];
+    int slots[2] = {c.dc_tbl, 4 + c.ac_tbl};
+    for (int z = 0; z < 2; z++) {
+      int sl = slots[z];
+      for (int k = threadIdx.x; k < 256; k += blockDim.x) { st.size[sl][k] = t[sl].size[k]; if (want_codes) st.code[sl][k] = t[sl].code[k]; }
+    }
+  }
+}
+
+struct CountSink {
+  const uint8_t *dsz, *asz; unsigned bits; int bad;
+  __device__ void dc(int nb, int) { int s = dsz[nb]; if (!s) bad = 1; bits += s + nb; }
+  __device__ void ac(int sym, int nb, int) { int s = asz[sym]; if (!s) bad = 1; bits += s + nb; }
+};
+
+__global__ void __launch_bounds__(256) k_block_bits_seq(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
+                                                        uint32_t *__restrict__ blk_bits, uint32_t *__restrict__ status)
+{
+  __shared__ ScanTables st;
+  int img = blockIdx.y;
+  load_scan_tables(st, tabs, stride, img, g, sd, false);
+  __syncthreads();
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= sd.nblocks) return;
+  int sci, k; long long mcu;
+  const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+  int last = prev_dc(g, sd, img, t, sci, mcu, k);
+  const CompGeom &c = g.c[sd.ci[sci]];
+  CountSink sink{st.size[c.dc_tbl], st.size[4 + c.ac_tbl], 0u, 0};
+  walk_seq_block(blk, last, sink);
+  if (sink.bad) atomicOr(&status[img], 2u);
+  blk_bits[(size_t)img * sd.nblocks + t] = sink.bits;
+}
+
+struct BitSink {
+  uint32_t *buf; unsigned long long widx; unsigned long long acc; int nacc;
+  const uint16_t *dco, *aco; const uint8_t *dsz, *asz;
+  __device__ void put(unsigned code, int size) {
+    acc = (acc << size) | (code & ((1u << size) - 1u)); nacc += size;
+    if (nacc >= 32) { unsigned w = (unsigned)(acc >> (nacc - 32)); if (w) atomicOr(&buf[widx], w); widx++; nacc -= 32; }
+  }
+  __device__ void dc(int nb, int v) { put(dco[nb], dsz[nb]); if (nb) put((unsigned)v, nb); }
+  __device__ void ac(int sym, int nb, int v) { put(aco[sym], asz[sym]); if (nb) put((unsigned)v, nb); }
+  __device__ void finish() { if (nacc > 0) { unsigned w = (unsigned)(acc << (32 - nacc)); if (w) atomicOr(&buf[widx], w); } }
+};
+
+__global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
+                                                    const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ bitbuf,
+                                                    size_t bitbuf_stride_words, const uint32_t *__restrict__ status)
+{
+  __shared__ ScanTables st;
+  int img = blockIdx.y;
+  load_scan_tables(st, tabs, stride, img, g, sd, true);
+  __syncthreads();
+  if (status[img] & ~1u) return;            // an earlier stage flagged this image (overflow / bad coefficient)
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= sd.nblocks) return;
+  int sci, k; long long mcu;
+  const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+  int last = prev_dc(g, sd, img, t, sci, mcu, k);
+  const CompGeom &c = g.c[sd.ci[sci]];
+  unsigned off = blk_off[(size_t)img * sd.nblocks + t];
+  BitSink sink;
+  sink.buf = bitbuf + (size_t)img * bitbuf_stride_words; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
+  sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
+  walk_seq_block(blk, last, sink);
+  sink.finish();
+}
+
+// in-place exclusive scan of blk_bits[img][0..nblocks); one CTA per image
+__global__ void __launch_bounds__(1024) k_scan_offsets(uint32_t *__restrict__ blk_bits, long long nblocks,
+                                                       unsigned long long *__restrict__ total_bits,
+                                                       size_t capacity_bits, uint32_t *__restrict__ status)
+{
+  __shared__ unsigned long long warp_sums[32];
+  __shared__ unsigned long long carry_s;
+  int img = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t *a = blk_bits + (size_t)img * nblocks;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (long long base = 0; base < nblocks; base += 1024) {
+    long long i = base + threadIdx.x;
+    unsigned long long v = i < nblocks ? a[i] : 0, x = v;
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long s = warp_sums[lane], z = s;
+      for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+      warp_sums[lane] = z - s;            // exclusive
+    }
+    __syncthreads();
+    unsigned long long carry = carry_s;
+    unsigned long long excl = carry + warp_sums[wid] + (x - v);
+    if (i < nblocks) a[i] = (uint32_t)excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long tb = carry_s;
+    total_bits[img] = tb;
+    if (tb + 64 > capacity_bits || tb >= (1ull << 32)) atomicOr(&status[img], 4u);    // does not fit: host retries with a larger buffer
+  }
+}
+
+// byte stuffing (jchuff.c:386-435 emit byte / 0xFF00) + final 1-bit padding
+// (flush_bits: 7 one-bits, then drop the partial byte).  One CTA per image;
+// appends at out[img][out_pos[img]] and advances out_pos.
+__global__ void __launch_bounds__(1024) k_stuff(const uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
+                                                const unsigned long long *__restrict__ total_bits,
+                                                uint8_t *__restrict__ out, size_t out_stride, size_t out_capacity,
+                                                unsigned long long *__restrict__ out_pos, uint32_t *__restrict__ scan_size,
+                                                uint32_t *__restrict__ status)
+{
+  __shared__ unsigned warp_sums[32];
+  __shared__ unsigned long long carry_s;
+  int img = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (status[img] & ~1u) { if (threadIdx.x == 0) *scan_size = 0, scan_size[img] = 0; return; }
+  const uint32_t *src = bitbuf + (size_t)img * bitbuf_stride_words;
+  unsigned long long bits = total_bits[img];
+  unsigned long long nbytes = (bits + 7) >> 3;
+  unsigned padbits = (unsigned)(nbytes * 8 - bits);           // low bits of the last byte to set to 1
+  unsigned long long nwords = (nbytes + 3) >> 2;
+  unsigned long long start = out_pos[img];
+  uint8_t *dst = out + (size_t)img * out_stride;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (unsigned long long base = 0; base < nwords; base += 1024) {
+    unsigned long long wi = base + threadIdx.x;
+    unsigned w = 0; int nb = 0;
+    if (wi < nwords) {
+      w = src[wi];
+      unsigned long long rem = nbytes - wi * 4;
+      nb = rem >= 4 ? 4 : (int)rem;
+      if (wi == nwords - 1 && padbits) w |= ((1u << padbits) - 1u) << (8 * (4 - nb));
+    }
+    unsigned ff = 0;
+    for (int j = 0; j < nb; j++) ff += (((w >> (24 - 8 * j)) & 0xFF) == 0xFF);
+    unsigned x = ff;
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned s = warp_sums[lane], z = s;
+      for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+      warp_sums[lane] = z - s;
+    }
+    __syncthreads();
+    unsigned long long carry = carry_s;
+    unsigned long long ffbefore = carry + warp_sums[wid] + (x - ff);
+    if (nb) {
+      unsigned long long o = start + wi * 4 + ffbefore;
+      if (o + 8 <= out_capacity) {
+        for (int j = 0; j < nb; j++) {
+          unsigned b = (w >> (24 - 8 * j)) & 0xFF;
+          dst[o++] = (uint8_t)b;
+          if (b == 0xFF) dst[o++] = 0;
+        }
+      } else atomicOr(&status[img], 4u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = ffbefore + ff;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long total = nbytes + carry_s;
+    scan_size[img] = (uint32_t)total;
+    out_pos[img] = start + total;
+  }
+}
+
+void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, int progressive,
+                       uint32_t *blk_bits, uint32_t *blk_aux, uint32_t *status, int n, cudaStream_t s)
+{
+  dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
+  (void)progressive; (void)blk_aux;
+  k_block_bits_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, status);
+  LAUNCHED();
+}
+void launch_scan_offsets(uint32_t *blk_bits, long long nblocks, unsigned long long *total_bits, size_t capacity_bits,
+                         uint32_t *status, int n, cudaStream_t s)
+{
+  k_scan_offsets<<<n, 1024, 0, s>>>(blk_bits, nblocks, total_bits, capacity_bits, status);
+  LAUNCHED();
+}
+void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, int progressive,
+                   const uint32_t *blk_off, const uint32_t *blk_aux, uint32_t *bitbuf, size_t bitbuf_stride_words,
+                   const uint32_t *status, int n, cudaStream_t s)
+{
+  dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
+  (void)progressive; (void)blk_aux;
+  k_encode_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_off, bitbuf, bitbuf_stride_words, status);
+  LAUNCHED();
+}
+void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_stride_words, const unsigned long long *total_bits,
+                  uint8_t *out, size_t out_stride, size_t out_capacity, unsigned long long *out_pos, uint32_t *scan_size,
+                  uint32_t *status, int n, cudaStream_t s)
+{
+  k_stuff<<<n, 1024, 0, s>>>(bitbuf, bitbuf_stride_words, total_bits, out, out_stride, out_capacity, out_pos, scan_size, status);
+  LAUNCHED();
+}
+
+}  // namespace b200

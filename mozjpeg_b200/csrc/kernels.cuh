@@ -1,0 +1,106 @@
+// kernels.cuh -- sm_100a device code of the JPEG-encode hot path.
+//
+// Everything here is integer / bit-serial or un-fused fp32 work: no tensor
+// cores.  The file is compiled with -fmad=false because the trellis rate/
+// distortion costs and the deringing filter must reproduce the reference's
+// x86-64 (no FMA contraction) fp32 results bit for bit.
+//
+// Data layout in HBM (per batch of n images sharing one geometry):
+//   coef[c] : int16 [n][hpad_c][wpad_c][64]   quantized coefficients, ZIGZAG order
+//   raw[c]  : int16 [n][hpad_c][wpad_c][64]   FDCT output (x8 scale),  ZIGZAG order
+// (one 128-byte line per 8x8 block; wpad/hpad include the dummy blocks that
+// pad each component to whole interleaved MCUs, jccoefct.c:312-345).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+// ---------------------------------------------------------------- geometry
+struct CompGeom {
+  int wib, hib;        // real blocks            (jcmaster.c:221-226)
+  int wpad, hpad;      // incl. dummy blocks
+  int h, v;            // sampling factors
+  int hx, vx;          // hmax/h, vmax/v (downsampling box)
+  int qt;              // quant table slot
+  int dc_tbl, ac_tbl;  // Huffman table slots
+  int rows_avail;      // downsampled rows holding real data (jcprepct.c:135-192)
+  long long blocks_per_image;   // wpad*hpad
+  int16_t *coef, *raw;
+};
+struct Geom {
+  int W, H, nc, hmax, vmax;
+  int mcus_per_row, mcu_rows;
+  int in_comps;        // samples per input pixel
+  int cs_mode;         // 0: RGB->YCbCr  1: RGB->gray  2: pass-through
+  size_t row_pitch, image_stride;
+  CompGeom c[4];
+};
+
+struct ScanDesc {
+  int ncomps, ci[4];
+  int Ss, Se, Ah, Al;
+  int bim;                         // blocks per MCU in this scan
+  int k_comp[10], k_y[10], k_x[10];
+  int k_first[4], k_count[4];      // first k / number of blocks of scan-component i in the MCU
+  int per_row, rows;               // MCUs per row / MCU rows of the scan (jcmaster.c:518-601)
+  long long nblocks;               // per image
+};
+
+// quantizer constants per (table, natural index): exact floor((a + bias)/d)
+// by multiply-shift (d = 8*Q, a < 2^18), see encoder.cu make_quant_consts().
+struct QuantConst { uint32_t mul; uint16_t shift; uint16_t pad; uint32_t bias; uint32_t d; };
+struct QuantTables { QuantConst q[4][64]; };                 // natural order
+struct TrellisConsts {
+  float w_zz[4][64];      // (float)(1.0/(Q*Q)) per zigzag position   jcdctmgr.c:1017-1021
+  int   q8_zz[4][64];     // 8*Q per zigzag position
+  double p1, p2;          // pow(2, lambda_log_scale1), pow(2, lambda_log_scale2)
+  float lambda_const;     // used when lambda_log_scale2 <= 0
+  int   use_norm;         // lambda_log_scale2 > 0
+  int   max_coef_bits;    // data_precision + 2
+  int   dc_trellis;       // trellis_quant_dc
+};
+
+// Huffman table as the device keeps it: DHT payload + derived encode table.
+struct DevHuff {
+  uint8_t  bits[17];
+  uint8_t  huffval[256];
+  uint8_t  nsym;          // low 8 bits of the symbol count (count can be 256 -> see nsym16)
+  uint8_t  pad0[12];
+  uint16_t nsym16;
+  uint16_t code[256];     // ehufco (jchuff.h:32-36)
+  uint8_t  size[256];     // ehufsi; 0 = symbol has no code
+};
+static_assert(sizeof(DevHuff) == 17 + 256 + 1 + 12 + 2 + 512 + 256, "DevHuff layout");
+
+// per-block record the AC trellis leaves for the DC trellis
+struct DcRec { float lambda_dc; int16_t raw_dc; int16_t pad; };
+
+#define HIST_BINS 257
+#define HIST_SLOTS 8          // [is_ac*4 + tbl_no]
+
+// ---------------------------------------------------------------- launches (defined in kernels.cu)
+// status[img] bits: 2 = JERR_BAD_DCT_COEF / missing Huffman code, 4 = output buffer too small (host retries)
+void launch_forward(const Geom &g, int ci, const uint8_t *src, const QuantTables *qt, int dering, int n, cudaStream_t s);
+void launch_dummy(const Geom &g, int ci, int n, cudaStream_t s);
+void launch_gather_seq(const Geom &g, const ScanDesc &sd, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
+void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s);
+void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_image_stride, uint32_t slot_mask, int n, cudaStream_t s);
+void launch_trellis_ac(const Geom &g, int ci, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_image_stride,
+                       DcRec *rec, int n, cudaStream_t s);
+void launch_trellis_dc(const Geom &g, int ci, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_image_stride,
+                       const DcRec *rec, unsigned long long *bt, int n, cudaStream_t s);
+void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
+                       uint32_t *blk_bits, uint32_t *blk_aux, uint32_t *status, int n, cudaStream_t s);
+void launch_scan_offsets(uint32_t *blk_bits, long long nblocks, unsigned long long *total_bits, size_t capacity_bits,
+                         uint32_t *status, int n, cudaStream_t s);
+void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
+                   const uint32_t *blk_off, const uint32_t *blk_aux, uint32_t *bitbuf, size_t bitbuf_image_stride_words,
+                   const uint32_t *status, int n, cudaStream_t s);
+void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_image_stride_words, const unsigned long long *total_bits,
+                  uint8_t *out, size_t out_image_stride, size_t out_capacity, unsigned long long *out_pos, uint32_t *scan_size,
+                  uint32_t *status, int n, cudaStream_t s);
+
+extern unsigned long long g_kernel_launches;
+
+}  // namespace b200

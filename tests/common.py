@@ -1,0 +1,50 @@
+"""Shared helpers for the parity tests."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_cases():
+    with open(os.path.join(GOLD, "golden.json")) as f:
+        return json.load(f)["cases"]
+
+
+def case_id(c):
+    im = c["image"] if isinstance(c["image"], str) else "synth%dx%d" % (c["image"][1], c["image"][2])
+    return im + ":" + "_".join(s.lstrip("-") for s in c["switches"])
+
+
+_img_cache = {}
+
+
+def case_image(c):
+    from oracle import oracle as O
+    import mozjpeg_b200 as mj
+    key = json.dumps(c["image"])
+    if key not in _img_cache:
+        if c["image"] == "testorig":
+            w, h, nc, data = mj.read_ppm(open(os.path.join(GOLD, "testorig.ppm"), "rb").read())
+            _img_cache[key] = np.frombuffer(data, dtype=np.uint8).reshape(h, w, nc)
+        else:
+            seed, w, h = c["image"]
+            _img_cache[key] = O.synth_image(seed, w, h)
+    return _img_cache[key]
+
+
+def md5(b):
+    return hashlib.md5(b).hexdigest()
+
+
+def device_supports(p):
+    """Switch sets the device path does not cover yet are skipped, not faked."""
+    import ctypes as C
+    from mozjpeg_b200 import _abi as A
+    return A.load().b200jpeg_validate(C.byref(p)) == 0

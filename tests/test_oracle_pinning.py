@@ -1,0 +1,74 @@
+"""CPU: pin the oracle (oracle/jpeg_oracle.c) to the reference.
+
+* against the reference's own golden vector (testimages/testimgint.jpg ==
+  `cjpeg -revert -dct int testorig.ppm`, md5 in CMakeLists.txt:1391) and the
+  md5s recorded from the unmodified reference by tools/make_golden.py;
+* live, byte for byte, against oracle/_ref when it is built (container and GPU
+  box both carry it; skipped otherwise).
+"""
+import numpy as np
+import pytest
+
+from common import case_id, case_image, golden_cases, md5
+
+CASES = golden_cases()
+SMALL = [c for c in CASES if c["image"] == "testorig" or c["image"][1] * c["image"][2] <= 200 * 136]
+
+
+def test_reference_golden_md5_is_the_cmake_one():
+    assert CASES[0]["switches"] == ["-revert", "-dct", "int"] and CASES[0]["image"] == "testorig"
+    assert CASES[0]["md5"] == "9a68f56bc76e466aa7e52f415d0f4a5f"      # MD5_JPEG_420_ISLOW
+
+
+@pytest.mark.parametrize("case", SMALL, ids=case_id)
+def test_oracle_matches_recorded_reference(built, case):
+    import mozjpeg_b200 as mj
+    from oracle import oracle as O
+    img = case_image(case)
+    nc = 1 if img.ndim == 2 else img.shape[2]
+    p = mj.params_from_switches(case["switches"], img.shape[1], img.shape[0], nc)
+    out = O.oracle_encode(p, img).jpeg
+    assert len(out) == case["size"] and md5(out) == case["md5"]
+
+
+@pytest.mark.parametrize("size", [(640, 480), (1920, 1080)], ids=lambda s: "%dx%d" % s)
+def test_oracle_large_cases(built, size):
+    import mozjpeg_b200 as mj
+    from oracle import oracle as O
+    for c in CASES:
+        if c["image"] != "testorig" and tuple(c["image"][1:]) == size and c["switches"][0] in ("-baseline", "-fastcrush") and "75" in c["switches"] and "2x2" in c["switches"]:
+            img = case_image(c)
+            p = mj.params_from_switches(c["switches"], img.shape[1], img.shape[0], 3)
+            assert md5(O.oracle_encode(p, img).jpeg) == c["md5"]
+
+
+def test_oracle_live_vs_reference_random_shapes(built):
+    """Odd shapes x profiles, live against the compiled reference."""
+    import mozjpeg_b200 as mj
+    from oracle import oracle as O
+    if not O.ref_available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(7)
+    sws = [["-baseline", "-quality", "70"], ["-fastcrush", "-quality", "80"], ["-revert", "-optimize"],
+           ["-baseline", "-quality", "75", "-sample", "2x1"], ["-baseline", "-quality", "75", "-sample", "1x2"]]
+    for _ in range(12):
+        w, h = int(rng.integers(1, 97)), int(rng.integers(1, 97))
+        img = O.synth_image(int(rng.integers(0, 1 << 30)), w, h)
+        for sw in sws:
+            p = mj.params_from_switches(sw, w, h)
+            assert O.oracle_encode(p, img).jpeg == O.ref_encode(img, sw), (w, h, sw)
+
+
+def test_stage_oracles_vs_reference_internals(built):
+    """jpeg_fdct_islow of the reference library vs our restatement."""
+    import ctypes as C
+    from oracle import oracle as O
+    if not O.ref_available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        blk = rng.integers(-128, 160, 64).astype(np.int32)
+        a = blk.copy(); b = blk.copy()
+        O.orc().orc_fdct_islow(a.ctypes.data_as(C.POINTER(C.c_int)))
+        O.ref().refshim_fdct_islow(b.ctypes.data_as(C.POINTER(C.c_int)))
+        assert (a == b).all()

@@ -1,0 +1,87 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/golden.json from the UNMODIFIED reference.
+
+Runs only where /root/reference exists (oracle/_ref built by oracle/Makefile).
+For every case it records the md5 and size of what the reference encoder
+produces; the tests then hold the CPU oracle and the CUDA path to those
+numbers on machines where the reference is absent.
+
+Inputs are either the reference's own test image (testimages/testorig.ppm,
+copied to tests/golden/ as a data fixture) or synthetic images generated from
+a seed by oracle.synth_image.
+"""
+import hashlib, json, os, shutil, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from oracle import oracle as O
+import mozjpeg_b200 as cjpeg
+
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+SWITCH_SETS = [
+    ["-revert", "-dct", "int"],                       # == testimages/testimgint.jpg, CMakeLists.txt:1391 (config 1)
+    ["-revert", "-optimize"],
+    ["-revert", "-progressive"],
+    ["-revert", "-quality", "90", "-sample", "2x2"],
+    ["-revert", "-sample", "1x1"],                    # ~ 444-islow family
+    ["-revert", "-sample", "2x1", "-optimize"],       # ~ 422-*-opt family
+    ["-revert", "-sample", "1x2"],                    # ~ 440-islow
+    ["-revert", "-grayscale"],                        # ~ gray-islow
+    ["-revert", "-grayscale", "-progressive"],
+    ["-baseline", "-quality", "75"],                  # config 2 semantics (4:2:0 is the default)
+    ["-baseline", "-quality", "75", "-sample", "2x2"],
+    ["-baseline", "-quality", "50", "-sample", "2x2"],
+    ["-baseline", "-quality", "90", "-sample", "2x2"],
+    ["-baseline", "-quality", "75", "-sample", "1x1"],
+    ["-baseline", "-quality", "85"],
+    ["-baseline", "-quality", "95"],
+    ["-baseline", "-quality", "100"],
+    ["-baseline", "-quality", "20"],
+    ["-baseline", "-notrellis", "-quality", "75"],
+    ["-baseline", "-notrellis-dc", "-quality", "75"],
+    ["-baseline", "-noovershoot", "-quality", "75"],
+    ["-baseline", "-grayscale", "-quality", "75"],
+    ["-baseline", "-quant-table", "2", "-quality", "80"],
+    ["-baseline", "-lambda1", "12.0", "-lambda2", "13.0", "-quality", "75"],
+    ["-fastcrush", "-quality", "75"],                 # config 3 semantics
+    ["-fastcrush", "-quality", "75", "-sample", "2x2"],
+    ["-fastcrush", "-quality", "50", "-sample", "2x2"],
+    ["-fastcrush", "-quality", "90", "-sample", "2x2"],
+    ["-fastcrush", "-quality", "92"],
+    ["-fastcrush", "-grayscale", "-quality", "75"],
+    ["-fastcrush", "-notrellis", "-quality", "75"],
+    ["-baseline", "-quality", "75", "-restart", "1"],
+    ["-fastcrush", "-quality", "75", "-restart", "2"],
+    ["-revert", "-restart", "3B"],
+]
+SYNTH = [(11, 16, 16), (12, 33, 17), (13, 200, 136), (14, 640, 480), (15, 1, 1), (16, 8, 8), (17, 1920, 1080)]
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    shutil.copyfile(os.path.join(REF, "testimages", "testorig.ppm"), os.path.join(GOLD, "testorig.ppm"))
+    cases = []
+    ppm = os.path.join(GOLD, "testorig.ppm")
+    w, h, nc, data = cjpeg.read_ppm(open(ppm, "rb").read())
+    img = np.frombuffer(data, dtype=np.uint8).reshape(h, w, nc)
+    for sw in SWITCH_SETS:
+        a = O.ref_cjpeg(ppm, sw)                   # the reference's own cjpeg binary
+        b = O.ref_encode(img, sw)                  # our driver around the reference library
+        assert a == b, ("refshim disagrees with cjpeg", sw)
+        cases.append({"image": "testorig", "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
+    for (seed, sw_, sh_) in SYNTH:
+        im = O.synth_image(seed, sw_, sh_)
+        sets = SWITCH_SETS if sw_ * sh_ <= 640 * 480 else [s for s in SWITCH_SETS if s in (["-revert", "-dct", "int"], ["-baseline", "-quality", "75", "-sample", "2x2"], ["-fastcrush", "-quality", "75", "-sample", "2x2"], ["-baseline", "-quality", "90", "-sample", "2x2"])]
+        for sw in sets:
+            a = O.ref_encode(im, sw)
+            cases.append({"image": [seed, sw_, sh_], "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
+    assert cases[0]["md5"] == "9a68f56bc76e466aa7e52f415d0f4a5f", "reference build does not reproduce MD5_JPEG_420_ISLOW"
+    json.dump({"generator": "tools/make_golden.py", "reference": "mozilla/mozjpeg 5.0.0 (C path, WITH_SIMD=0), oracle/_ref", "cases": cases},
+              open(os.path.join(GOLD, "golden.json"), "w"), indent=0)
+    print("wrote", len(cases), "cases")
+
+
+if __name__ == "__main__":
+    main()
