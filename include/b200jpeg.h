@@ -172,6 +172,10 @@ typedef struct b200jpeg_encoder b200jpeg_encoder;
 /* Create an encoder bound to CUDA device `device` (own stream, own HBM arenas). */
 int  b200jpeg_encoder_create(b200jpeg_encoder **enc, int device);
 void b200jpeg_encoder_destroy(b200jpeg_encoder *enc);
+/* Run on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL = the
+ * legacy default stream) instead of the encoder's own, so that the caller can
+ * bracket the work with its own events. */
+int  b200jpeg_encoder_set_stream(b200jpeg_encoder *enc, void *cuda_stream);
 
 /*
  * Encode a batch of `n_images` images that share one parameter set and one
@@ -205,7 +209,8 @@ size_t b200jpeg_last_scan_bytes(const b200jpeg_encoder *enc);
 /* Number of kernels this library launched since the encoder was created. */
 unsigned long long b200jpeg_kernel_launches(const b200jpeg_encoder *enc);
 /* Milliseconds (CUDA events on the encoder's stream) spent in each pipeline
- * stage during the last batch; names[] are static strings. Returns the count. */
+ * stage during the last batch, summed per stage name (one stage = one kernel,
+ * except "h2d"); names[] are static strings. Returns the count. */
 int  b200jpeg_last_stage_times(const b200jpeg_encoder *enc, const char **names, float *ms, int max);
 
 /* Debug/parity taps: copy intermediate device state of image `i` of the last

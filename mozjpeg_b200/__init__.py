@@ -39,6 +39,10 @@ class Encoder:
         except Exception:
             pass
 
+    def set_stream(self, cuda_stream: int) -> None:
+        """Launch on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        A.check(_lib.b200jpeg_encoder_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")
+
     # -- batch API -------------------------------------------------------
     def encode_batch(self, p: Params, images: np.ndarray) -> List[bytes]:
         """images: (N, H, W, C) or (N, H, W) uint8 host array -> N JPEG files.
@@ -96,8 +100,8 @@ class Encoder:
         return int(_lib.b200jpeg_last_scan_bytes(self._h))
 
     def stage_times(self) -> dict:
-        names = (C.c_char_p * 16)(); ms = (C.c_float * 16)()
-        k = _lib.b200jpeg_last_stage_times(self._h, names, ms, 16)
+        names = (C.c_char_p * 32)(); ms = (C.c_float * 32)()
+        k = _lib.b200jpeg_last_stage_times(self._h, names, ms, 32)
         return {names[i].decode(): float(ms[i]) for i in range(k)}
 
     def debug_coefs(self, image: int, component: int, plane: int = 0) -> np.ndarray:

@@ -61,7 +61,7 @@ struct Plan {                // everything derived from b200jpeg_params
   std::vector<ScanDesc> scans;
   bool progressive = false, optimize = false, trellis = false, dering = false;
   size_t coef_bytes[4] = {0, 0, 0, 0};
-  long long max_scan_blocks = 0, max_real_blocks = 0;
+  long long max_scan_blocks = 0, max_real_blocks = 0, sum_real_blocks = 0;
 };
 
 }  // namespace b200
@@ -87,7 +87,8 @@ struct b200jpeg_encoder {
   size_t last_scan_bytes = 0;
   unsigned long long launches_at_create = 0;
   // timing
-  std::vector<cudaEvent_t> ev; std::vector<const char *> ev_names; std::vector<float> stage_ms;
+  std::vector<cudaEvent_t> ev; std::vector<const char *> ev_names, stage_names; std::vector<float> stage_ms; std::vector<int> stage_calls;
+  bool own_stream = true;
   // streaming shim state
   int st_state = 0, st_next_row = 0;
   b200jpeg_params st_params;
@@ -109,7 +110,7 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
   if (p->in_color_space == B200JPEG_CS_RGB && p->jpeg_color_space == B200JPEG_CS_YCbCr) g.cs_mode = 0;
   else if (p->in_color_space == B200JPEG_CS_RGB && p->jpeg_color_space == B200JPEG_CS_GRAYSCALE) g.cs_mode = 1;
   else g.cs_mode = 2;
-  pl.max_real_blocks = 0;
+  pl.max_real_blocks = 0; pl.sum_real_blocks = 0;
   for (int ci = 0; ci < g.nc; ci++) {
     CompGeom &c = g.c[ci]; const b200jpeg_component_info &ic = p->comp_info[ci];
     c.h = ic.h_samp_factor; c.v = ic.v_samp_factor; c.hx = g.hmax / c.h; c.vx = g.vmax / c.v;
@@ -119,7 +120,7 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
     c.rows_avail = div_up(g.H, g.vmax) * c.v;
     c.blocks_per_image = (long long)c.wpad * c.hpad;
     pl.coef_bytes[ci] = (size_t)c.blocks_per_image * 128;
-    pl.max_real_blocks = std::max(pl.max_real_blocks, (long long)c.wib * c.hib);
+    pl.max_real_blocks = std::max(pl.max_real_blocks, (long long)c.wib * c.hib); pl.sum_real_blocks += (long long)c.wib * c.hib;
   }
   // scan list (select_scan_parameters jcmaster.c:443-515 + per_scan_setup :518-601)
   pl.scans.clear();
@@ -252,13 +253,13 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
     if (e->keep_plain && pl.trellis) { if ((rc = e->d_plain[ci].reserve(pl.coef_bytes[ci] * n))) return rc; }
   }
   const size_t hist_bytes = (size_t)n * HIST_SLOTS * HIST_BINS * 4;
-  if ((rc = e->d_hist.reserve(hist_bytes))) return rc;
+  if ((rc = e->d_hist.reserve(hist_bytes * g.nc))) return rc;
   const size_t tabset = sizeof(DevHuff) * HIST_SLOTS;
   if ((rc = e->d_tabs_scan.reserve(tabset * nscans * n))) return rc;
   if ((rc = e->d_tabs_trellis.reserve(tabset * 4 * n))) return rc;
   if ((rc = e->d_tabs_fixed.reserve(tabset))) return rc;
-  if ((rc = e->d_rec.reserve((size_t)n * pl.max_real_blocks * sizeof(DcRec)))) return rc;
-  if ((rc = e->d_bt.reserve((size_t)n * pl.max_real_blocks * 8))) return rc;
+  if ((rc = e->d_rec.reserve((size_t)n * pl.sum_real_blocks * sizeof(DcRec)))) return rc;
+  if ((rc = e->d_bt.reserve((size_t)n * pl.sum_real_blocks * 8))) return rc;
   if ((rc = e->d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
   if ((rc = e->d_total_bits.reserve((size_t)n * 8))) return rc;
   if ((rc = e->d_status.reserve((size_t)n * 4))) return rc;
@@ -293,48 +294,60 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
 
   // ---- pass 0 data path: colour/downsample/FDCT/quantize (compress_first_pass) ----
   tm.mark("forward");
-  for (int ci = 0; ci < g.nc; ci++) launch_forward(g, ci, src_dev, e->d_qt.as<QuantTables>(), pl.dering, n, s);
-  for (int ci = 0; ci < g.nc; ci++) launch_dummy(g, ci, n, s);
+  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), pl.dering, n, s);
+  tm.mark("dummy");
+  launch_dummy(g, n, s);
 
-  // ---- trellis phase (jcmaster.c pass list): per component:
-  //      statistics on the plain-quantized coefficients -> optimal tables ->
-  //      quantize_trellis (AC per block, DC Viterbi per block row) -> dummy blocks ----
+  // ---- trellis phase (jcmaster.c pass list).  The three
+  //      per-component chains (statistics on the plain-quantized coefficients
+  //      -> optimal tables -> quantize_trellis) are independent, so each step
+  //      is ONE launch over all components of all images. ----
   if (pl.trellis) {
-    tm.mark("trellis");
-    for (int ci = 0; ci < g.nc; ci++) {
-      if (e->keep_plain) CU(cudaMemcpyAsync(e->d_plain[ci].p, e->d_coef[ci].p, pl.coef_bytes[ci] * n, cudaMemcpyDeviceToDevice, s));
-      ScanDesc ts; memset(&ts, 0, sizeof ts);
-      ts.ncomps = 1; ts.ci[0] = ci; ts.Ss = 0; ts.Se = 63; ts.bim = 1; ts.k_count[0] = 1;
-      ts.per_row = g.c[ci].wib; ts.rows = g.c[ci].hib; ts.nblocks = (long long)ts.per_row * ts.rows;
-      CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes, s));
-      launch_gather_seq(g, ts, e->d_hist.as<uint32_t>(), status, n, s);
-      DevHuff *tset = e->d_tabs_trellis.as<DevHuff>() + (size_t)ci * HIST_SLOTS;          // [img][ci][8]
-      size_t tstride = tabset * 4;
-      launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tstride, (1u << g.c[ci].dc_tbl) | (1u << (4 + g.c[ci].ac_tbl)), n, s);
-      launch_trellis_ac(g, ci, e->d_tc.as<TrellisConsts>(), tset, tstride, e->d_rec.as<DcRec>(), n, s);
-      if (p->trellis_quant_dc)
-        launch_trellis_dc(g, ci, e->d_tc.as<TrellisConsts>(), tset, tstride, e->d_rec.as<DcRec>(), e->d_bt.as<unsigned long long>(), n, s);
-      launch_dummy(g, ci, n, s);
+    if (e->keep_plain) for (int ci = 0; ci < g.nc; ci++) CU(cudaMemcpyAsync(e->d_plain[ci].p, e->d_coef[ci].p, pl.coef_bytes[ci] * n, cudaMemcpyDeviceToDevice, s));
+    RecLayout rl; memset(&rl, 0, sizeof rl);
+    for (int ci = 0; ci < g.nc; ci++) { rl.comp_off[ci] = rl.per_image; rl.per_image += (long long)g.c[ci].wib * g.c[ci].hib; }
+    const size_t hist_bytes_t = hist_bytes * g.nc;
+    tm.mark("trellis_stats");
+    CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes_t, s));
+    launch_gather_comp(g, e->d_hist.as<uint32_t>(), status, n, s);
+    tm.mark("trellis_tables");
+    SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = g.nc;
+    for (int ci = 0; ci < g.nc; ci++) masks.m[ci] = (1u << g.c[ci].dc_tbl) | (1u << (4 + g.c[ci].ac_tbl));
+    DevHuff *tset = e->d_tabs_trellis.as<DevHuff>();                                       // [img*nc + ci][8]
+    launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tabset, masks, n * g.nc, s);
+    tm.mark("trellis_ac");
+    launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, e->d_rec.as<DcRec>(), rl, n, s);
+    if (p->trellis_quant_dc) {
+      tm.mark("trellis_dc");
+      launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), tset, tabset, e->d_rec.as<DcRec>(), e->d_bt.as<unsigned long long>(), rl, n, s);
     }
+    tm.mark("dummy");
+    launch_dummy(g, n, s);
   }
 
   // ---- scans: huff_opt_pass (statistics -> tables) + output_pass ----
-  tm.mark("entropy");
   for (int si = 0; si < nscans; si++) {
     const ScanDesc &sd = pl.scans[si];
     const DevHuff *tabs; size_t tstride;
     if (pl.optimize) {
       DevHuff *tset = e->d_tabs_scan.as<DevHuff>() + (size_t)si * HIST_SLOTS;             // [img][scan][8]
       tstride = tabset * nscans;
+      tm.mark("scan_stats");
       CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes, s));
       launch_gather_seq(g, sd, e->d_hist.as<uint32_t>(), status, n, s);
-      launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tstride, scan_slot_mask(pl, sd), n, s);
+      tm.mark("scan_tables");
+      SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = scan_slot_mask(pl, sd);
+      launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tstride, masks, n, s);
       tabs = tset;
     } else { tabs = e->d_tabs_fixed.as<DevHuff>(); tstride = 0; }
+    tm.mark("block_bits");
     launch_block_bits(g, sd, tabs, tstride, 0, e->d_blk_bits.as<uint32_t>(), nullptr, status, n, s);
+    tm.mark("scan_offsets");
     launch_scan_offsets(e->d_blk_bits.as<uint32_t>(), sd.nblocks, e->d_total_bits.as<unsigned long long>(), (size_t)e->bitbuf_words_per_image * 32, status, n, s);
+    tm.mark("encode");
     CU(cudaMemsetAsync(e->d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
     launch_encode(g, sd, tabs, tstride, 0, e->d_blk_bits.as<uint32_t>(), nullptr, e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, status, n, s);
+    tm.mark("stuff");
     launch_stuff(e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, e->d_total_bits.as<unsigned long long>(),
                  e->d_out.as<uint8_t>(), e->out_cap_per_image, e->out_cap_per_image, e->d_out_pos.as<unsigned long long>(),
                  e->d_scan_size.as<uint32_t>() + (size_t)si * n, status, n, s);
@@ -587,8 +600,15 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   if (rc == 1) { set_error("output does not fit even after growing buffers"); return B200JPEG_ERR_BUFFER; }
   if (rc) return rc;
   // stage timings
-  e->stage_ms.assign(tm.idx > 0 ? tm.idx - 1 : 0, 0.f);
-  for (size_t i = 0; i + 1 < tm.idx; i++) cudaEventElapsedTime(&e->stage_ms[i], e->ev[i], e->ev[i + 1]);
+  // per-stage device times (CUDA events on the encoder's stream), summed by stage name
+  e->stage_names.clear(); e->stage_ms.clear(); e->stage_calls.clear();
+  for (size_t i = 0; i + 1 < tm.idx; i++) {
+    float ms = 0.f; cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]);
+    size_t k = 0;
+    for (; k < e->stage_names.size(); k++) if (!strcmp(e->stage_names[k], e->ev_names[i])) break;
+    if (k == e->stage_names.size()) { e->stage_names.push_back(e->ev_names[i]); e->stage_ms.push_back(0.f); e->stage_calls.push_back(0); }
+    e->stage_ms[k] += ms; e->stage_calls[k]++;
+  }
   return B200JPEG_OK;
 }
 
@@ -628,8 +648,19 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
   PinBuf *pb[] = {&e->h_qt, &e->h_tc, &e->h_fixed, &e->h_status, &e->h_out_pos, &e->h_scan_size, &e->h_tabs, &e->h_out, &e->h_stage};
   for (PinBuf *b : pb) b->release();
   for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
-  cudaStreamDestroy(e->stream);
+  if (e->own_stream) cudaStreamDestroy(e->stream);
   delete e;
+}
+
+int b200jpeg_encoder_set_stream(b200jpeg_encoder *e, void *cuda_stream)
+{
+  if (!e) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  if (e->own_stream) cudaStreamDestroy(e->stream);
+  e->stream = static_cast<cudaStream_t>(cuda_stream);
+  e->own_stream = false;
+  return B200JPEG_OK;
 }
 
 int b200jpeg_encode_batch(b200jpeg_encoder *enc, const b200jpeg_params *p, const void *pixels, int pixels_on_device,
@@ -656,7 +687,7 @@ int b200jpeg_last_stage_times(const b200jpeg_encoder *e, const char **names, flo
 {
   if (!e) return 0;
   int n = (int)e->stage_ms.size();
-  for (int i = 0; i < n && i < max; i++) { if (names) names[i] = e->ev_names[i]; if (ms) ms[i] = e->stage_ms[i]; }
+  for (int i = 0; i < n && i < max; i++) { if (names) names[i] = e->stage_names[i]; if (ms) ms[i] = e->stage_ms[i]; }
   return n < max ? n : max;
 }
 
@@ -689,7 +720,7 @@ int b200jpeg_debug_get_huff(b200jpeg_encoder *e, int image, int scan, int is_ac,
   if (scan < 0) {          // scan = -1-ci : the trellis-phase tables of component ci
     int ci = -1 - scan;
     if (ci >= e->plan.g.nc) { set_error("bad component"); return B200JPEG_ERR_PARAM; }
-    CU(cudaMemcpy(&h, e->d_tabs_trellis.as<DevHuff>() + ((size_t)image * 4 + ci) * HIST_SLOTS + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&h, e->d_tabs_trellis.as<DevHuff>() + ((size_t)image * e->plan.g.nc + ci) * HIST_SLOTS + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));
   } else {
     if (scan >= nscans) { set_error("bad scan"); return B200JPEG_ERR_PARAM; }
     if (e->plan.optimize) CU(cudaMemcpy(&h, e->d_tabs_scan.as<DevHuff>() + ((size_t)image * nscans + scan) * HIST_SLOTS + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));

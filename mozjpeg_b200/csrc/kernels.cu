@@ -112,13 +112,14 @@ __device__ __forceinline__ unsigned quant_one(int x, QuantConst k, int dering)
   return (unsigned)(x < 0 ? -q : q);
 }
 
-__global__ void __launch_bounds__(128) k_forward(Geom g, int ci, const uint8_t *__restrict__ src,
+__global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restrict__ src,
                                                  const QuantTables *__restrict__ qt, int dering)
 {
+  const int ci = blockIdx.z % g.nc, img = blockIdx.z / g.nc;
   const CompGeom &c = g.c[ci];
   int bx = blockIdx.x * blockDim.x + threadIdx.x;
-  int by = blockIdx.y, img = blockIdx.z;
-  if (bx >= c.wib) return;
+  int by = blockIdx.y;
+  if (bx >= c.wib || by >= c.hib) return;
   const uint8_t *base = src + (size_t)img * g.image_stride;
   int ws[64];
   const int comp = g.cs_mode == 1 ? 0 : ci;
@@ -186,11 +187,12 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, int ci, const uint8_t *
   }
 }
 
-void launch_forward(const Geom &g, int ci, const uint8_t *src, const QuantTables *qt, int dering, int n, cudaStream_t s)
+void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, int n, cudaStream_t s)
 {
-  const CompGeom &c = g.c[ci];
-  dim3 grid((c.wib + 127) / 128, c.hib, n);
-  k_forward<<<grid, 128, 0, s>>>(g, ci, src, qt, dering);
+  int mw = 0, mh = 0;
+  for (int ci = 0; ci < g.nc; ci++) { mw = max(mw, g.c[ci].wib); mh = max(mh, g.c[ci].hib); }
+  dim3 grid((mw + 127) / 128, mh, n * g.nc);
+  k_forward<<<grid, 128, 0, s>>>(g, src, qt, dering);
   LAUNCHED();
 }
 
@@ -199,10 +201,10 @@ void launch_forward(const Geom &g, int ci, const uint8_t *src, const QuantTables
 // take the DC of the last real block of the row, bottom dummy rows take, per
 // MCU, the DC of the last block of that MCU in the row above.
 // =====================================================================
-__global__ void k_dummy(Geom g, int ci)
+__global__ void k_dummy(Geom g)
 {
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
   const CompGeom &c = g.c[ci];
-  int img = blockIdx.y;
   long long nd_right = (long long)c.hib * (c.wpad - c.wib);
   long long nd = nd_right + (long long)(c.hpad - c.hib) * c.wpad;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,13 +221,13 @@ __global__ void k_dummy(Geom g, int ci)
   d4[0] = make_uint4((unsigned)(uint16_t)dc, 0, 0, 0);
   for (int v = 1; v < 8; v++) d4[v] = make_uint4(0, 0, 0, 0);
 }
-void launch_dummy(const Geom &g, int ci, int n, cudaStream_t s)
+void launch_dummy(const Geom &g, int n, cudaStream_t s)
 {
-  const CompGeom &c = g.c[ci];
-  long long nd = (long long)c.hib * (c.wpad - c.wib) + (long long)(c.hpad - c.hib) * c.wpad;
+  long long nd = 0;
+  for (int ci = 0; ci < g.nc; ci++) { const CompGeom &c = g.c[ci]; nd = max(nd, (long long)c.hib * (c.wpad - c.wib) + (long long)(c.hpad - c.hib) * c.wpad); }
   if (nd == 0) return;
-  dim3 grid((unsigned)((nd + 127) / 128), n);
-  k_dummy<<<grid, 128, 0, s>>>(g, ci);
+  dim3 grid((unsigned)((nd + 127) / 128), n * g.nc);
+  k_dummy<<<grid, 128, 0, s>>>(g);
   LAUNCHED();
 }
 
@@ -320,6 +322,45 @@ __global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, uint32_
   uint32_t *gh = hist + (size_t)img * HIST_SLOTS * HIST_BINS;
   for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&gh[i], sh[i]);
 }
+// Trellis-phase statistics: every component as its own non-interleaved scan
+// (jcmaster.c:443-467), all components of all images in one launch;
+// histogram set index = img*nc + ci.
+__global__ void __launch_bounds__(256) k_gather_comp(Geom g, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
+{
+  __shared__ unsigned sh[2 * HIST_BINS];
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
+  const CompGeom &c = g.c[ci];
+  long long nblk = (long long)c.wib * c.hib;
+  if ((long long)blockIdx.x * blockDim.x >= nblk) return;
+  for (int i = threadIdx.x; i < 2 * HIST_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nblk) {
+    int row = (int)(t / c.wib), col = (int)(t - (long long)row * c.wib);
+    const int16_t *base = c.coef + (size_t)img * c.blocks_per_image * 64;
+    const int16_t *blk = base + ((size_t)row * c.wpad + col) * 64;
+    int last = 0;
+    if (t > 0) { int pr = col > 0 ? row : row - 1, pc = col > 0 ? col - 1 : c.wib - 1; last = base[((size_t)pr * c.wpad + pc) * 64]; }
+    HistSink sink{sh, sh + HIST_BINS, 0};
+    walk_seq_block(blk, last, sink);
+    if (sink.bad) atomicOr(&status[img], 2u);
+  }
+  __syncthreads();
+  uint32_t *gh = hist + ((size_t)img * g.nc + ci) * HIST_SLOTS * HIST_BINS;
+  for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) {
+    if (sh[i]) atomicAdd(&gh[c.dc_tbl * HIST_BINS + i], sh[i]);
+    if (sh[HIST_BINS + i]) atomicAdd(&gh[(4 + c.ac_tbl) * HIST_BINS + i], sh[HIST_BINS + i]);
+  }
+}
+void launch_gather_comp(const Geom &g, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
+{
+  long long mb = 0;
+  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
+  dim3 grid((unsigned)((mb + 255) / 256), n * g.nc);
+  k_gather_comp<<<grid, 256, 0, s>>>(g, hist, status);
+  LAUNCHED();
+}
+
 void launch_gather_seq(const Geom &g, const ScanDesc &sd, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
@@ -335,11 +376,14 @@ void launch_gather_seq(const Geom &g, const ScanDesc &sd, uint32_t *hist, uint32
 // code-size chains (:1021-1034) are replaced by a reverse sweep over the
 // recorded merge list, which yields the same leaf depths.
 // =====================================================================
+// blockIdx.y enumerates histogram/table SETS (one per image, or one per
+// (image, component) in the trellis phase); masks.m[set % masks.period] says which of
+// the 8 slots of that set are to be built.
 __global__ void __launch_bounds__(32) k_gen_tables(const uint32_t *__restrict__ hist, DevHuff *__restrict__ tabs,
-                                                   size_t tabs_image_stride, uint32_t slot_mask)
+                                                   size_t tabs_set_stride, SlotMasks masks)
 {
   int img = blockIdx.y, slot = blockIdx.x, lane = threadIdx.x;
-  if (!((slot_mask >> slot) & 1)) return;
+  if (!((masks.m[img % masks.period] >> slot) & 1)) return;
   __shared__ long long freq[257];
   __shared__ short nz_index[257];
   __shared__ short m1[257], m2[257];
@@ -380,7 +424,7 @@ __global__ void __launch_bounds__(32) k_gen_tables(const uint32_t *__restrict__ 
     __syncwarp();
   }
   if (lane == 0) {
-    DevHuff *out = reinterpret_cast<DevHuff *>(reinterpret_cast<char *>(tabs) + (size_t)img * tabs_image_stride) + slot;
+    DevHuff *out = reinterpret_cast<DevHuff *>(reinterpret_cast<char *>(tabs) + (size_t)img * tabs_set_stride) + slot;
     for (int i = 0; i < nnz; i++) depth[i] = 0;
     for (int t = nmerge - 1; t >= 0; t--) { int d = depth[m1[t]] + 1; depth[m1[t]] = d; depth[m2[t]] = d; }
     unsigned char bits[33]; int bit_pos[33];
@@ -410,10 +454,10 @@ __global__ void __launch_bounds__(32) k_gen_tables(const uint32_t *__restrict__ 
     out->nsym16 = (uint16_t)nsym; out->nsym = (uint8_t)nsym;
   }
 }
-void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_image_stride, uint32_t slot_mask, int n, cudaStream_t s)
+void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_set_stride, const SlotMasks &masks, int nsets, cudaStream_t s)
 {
-  dim3 grid(HIST_SLOTS, n);
-  k_gen_tables<<<grid, 32, 0, s>>>(hist, tabs, tabs_image_stride, slot_mask);
+  dim3 grid(HIST_SLOTS, nsets);
+  k_gen_tables<<<grid, 32, 0, s>>>(hist, tabs, tabs_set_stride, masks);
   LAUNCHED();
 }
 
@@ -437,15 +481,17 @@ void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s) { k_seed_
 //            (:1211-1222).
 // =====================================================================
 #define TRELLIS_THREADS 128
-__global__ void __launch_bounds__(TRELLIS_THREADS) k_trellis_ac(Geom g, int ci, const TrellisConsts *__restrict__ tc,
-                                                                const DevHuff *__restrict__ tabs, size_t tabs_image_stride,
-                                                                DcRec *__restrict__ rec)
+__global__ void __launch_bounds__(TRELLIS_THREADS) k_trellis_ac(Geom g, const TrellisConsts *__restrict__ tc,
+                                                                const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
+                                                                DcRec *__restrict__ rec, RecLayout rl)
 {
+  const int ci = blockIdx.z % g.nc, img = blockIdx.z / g.nc;
   const CompGeom &c = g.c[ci];
   __shared__ uint8_t acsi[256];
-  int img = blockIdx.z, by = blockIdx.y;
+  int by = blockIdx.y;
+  if (by >= c.hib || blockIdx.x * blockDim.x >= c.wib) return;
   {
-    const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)img * tabs_image_stride) + (4 + c.ac_tbl);
+    const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.z * tabs_set_stride) + (4 + c.ac_tbl);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) acsi[i] = ac->size[i];
   }
   __syncthreads();
@@ -480,7 +526,7 @@ __global__ void __launch_bounds__(TRELLIS_THREADS) k_trellis_ac(Geom g, int ci, 
   const int *q8 = tc->q8_zz[c.qt];
   {
     DcRec rr; rr.lambda_dc = lambda * wz[0]; rr.raw_dc = (int16_t)RAWZ(0); rr.pad = 0;
-    rec[((size_t)img * c.hib + by) * c.wib + bx] = rr;
+    rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)by * c.wib + bx] = rr;
   }
 
   // phase 1
@@ -568,12 +614,13 @@ __global__ void __launch_bounds__(TRELLIS_THREADS) k_trellis_ac(Geom g, int ci, 
 #undef QNTZ
 
 
-void launch_trellis_ac(const Geom &g, int ci, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_image_stride,
-                       DcRec *rec, int n, cudaStream_t s)
+void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
+                       DcRec *rec, const RecLayout &rl, int n, cudaStream_t s)
 {
-  const CompGeom &c = g.c[ci];
-  dim3 grid((c.wib + TRELLIS_THREADS - 1) / TRELLIS_THREADS, c.hib, n);
-  k_trellis_ac<<<grid, TRELLIS_THREADS, 0, s>>>(g, ci, tc, tabs, tabs_image_stride, rec);
+  int mw = 0, mh = 0;
+  for (int ci = 0; ci < g.nc; ci++) { mw = max(mw, g.c[ci].wib); mh = max(mh, g.c[ci].hib); }
+  dim3 grid((mw + TRELLIS_THREADS - 1) / TRELLIS_THREADS, mh, n * g.nc);
+  k_trellis_ac<<<grid, TRELLIS_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl);
   LAUNCHED();
 }
 
@@ -584,15 +631,15 @@ void launch_trellis_ac(const Geom &g, int ci, const TrellisConsts *tc, const Dev
 // One thread per (image, iMCU row).  bt[] holds, per block, the 9 back
 // pointers (4 bits each), the unsigned quantized value and the sign.
 // =====================================================================
-__global__ void __launch_bounds__(64) k_trellis_dc(Geom g, int ci, const TrellisConsts *__restrict__ tc,
-                                                   const DevHuff *__restrict__ tabs, size_t tabs_image_stride,
-                                                   const DcRec *__restrict__ rec, unsigned long long *__restrict__ bt)
+__global__ void __launch_bounds__(64) k_trellis_dc(Geom g, const TrellisConsts *__restrict__ tc,
+                                                   const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
+                                                   const DcRec *__restrict__ rec, unsigned long long *__restrict__ bt, RecLayout rl)
 {
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
   const CompGeom &c = g.c[ci];
   __shared__ uint8_t dcsi[32];
-  int img = blockIdx.y;
   {
-    const DevHuff *dc = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)img * tabs_image_stride) + c.dc_tbl;
+    const DevHuff *dc = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + c.dc_tbl;
     if (threadIdx.x < 32) dcsi[threadIdx.x] = dc->size[threadIdx.x];
   }
   __syncthreads();
@@ -607,7 +654,7 @@ __global__ void __launch_bounds__(64) k_trellis_dc(Geom g, int ci, const Trellis
   for (int br = 0; br < c.v; br++) {
     int row = imcu * c.v + br;
     if (row >= c.hib) break;
-    size_t rbase = ((size_t)img * c.hib + row) * c.wib;
+    size_t rbase = (size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * c.wib;
     float acc[9]; int prevc[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) { acc[k] = 0.f; prevc[k] = 0; }
@@ -667,13 +714,13 @@ __global__ void __launch_bounds__(64) k_trellis_dc(Geom g, int ci, const Trellis
     }
   }
 }
-void launch_trellis_dc(const Geom &g, int ci, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_image_stride,
-                       const DcRec *rec, unsigned long long *bt, int n, cudaStream_t s)
+void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
+                       const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int n, cudaStream_t s)
 {
-  const CompGeom &c = g.c[ci];
-  int n_imcu = (c.hib + c.v - 1) / c.v;
-  dim3 grid((n_imcu + 63) / 64, n);
-  k_trellis_dc<<<grid, 64, 0, s>>>(g, ci, tc, tabs, tabs_image_stride, rec, bt);
+  int n_imcu = 0;
+  for (int ci = 0; ci < g.nc; ci++) n_imcu = max(n_imcu, (g.c[ci].hib + g.c[ci].v - 1) / g.c[ci].v);
+  dim3 grid((n_imcu + 63) / 64, n * g.nc);
+  k_trellis_dc<<<grid, 64, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, bt, rl);
   LAUNCHED();
 }
 

@@ -75,21 +75,26 @@ static_assert(sizeof(DevHuff) == 17 + 256 + 1 + 12 + 2 + 512 + 256, "DevHuff lay
 
 // per-block record the AC trellis leaves for the DC trellis
 struct DcRec { float lambda_dc; int16_t raw_dc; int16_t pad; };
+// where component ci's records start inside an image's record array
+struct RecLayout { long long per_image; long long comp_off[4]; };
+// which of the 8 table slots to (re)build for set i: m[i % period]
+struct SlotMasks { uint32_t m[4]; int period; };
 
 #define HIST_BINS 257
 #define HIST_SLOTS 8          // [is_ac*4 + tbl_no]
 
 // ---------------------------------------------------------------- launches (defined in kernels.cu)
 // status[img] bits: 2 = JERR_BAD_DCT_COEF / missing Huffman code, 4 = output buffer too small (host retries)
-void launch_forward(const Geom &g, int ci, const uint8_t *src, const QuantTables *qt, int dering, int n, cudaStream_t s);
-void launch_dummy(const Geom &g, int ci, int n, cudaStream_t s);
+void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, int n, cudaStream_t s);
+void launch_dummy(const Geom &g, int n, cudaStream_t s);
+void launch_gather_comp(const Geom &g, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_gather_seq(const Geom &g, const ScanDesc &sd, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s);
-void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_image_stride, uint32_t slot_mask, int n, cudaStream_t s);
-void launch_trellis_ac(const Geom &g, int ci, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_image_stride,
-                       DcRec *rec, int n, cudaStream_t s);
-void launch_trellis_dc(const Geom &g, int ci, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_image_stride,
-                       const DcRec *rec, unsigned long long *bt, int n, cudaStream_t s);
+void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_set_stride, const SlotMasks &masks, int nsets, cudaStream_t s);
+void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
+                       DcRec *rec, const RecLayout &rl, int n, cudaStream_t s);
+void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
+                       const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int n, cudaStream_t s);
 void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
                        uint32_t *blk_bits, uint32_t *blk_aux, uint32_t *status, int n, cudaStream_t s);
 void launch_scan_offsets(uint32_t *blk_bits, long long nblocks, unsigned long long *total_bits, size_t capacity_bits,

@@ -227,23 +227,4 @@ def ref_cjpeg(ppm_path: str, switches: Sequence[str]) -> bytes:
     return r.stdout
 
 
-def synth_image(seed: int, width: int, height: int) -> np.ndarray:
-    """SURVEY 8(d) synthetic input: smooth sinusoid field per channel (periods
-    33-143 px) + N(0, 12) noise, clipped, plus a saturated white rectangle with
-    thin black lines (~1% of the area) to exercise deringing."""
-    rng = np.random.default_rng(seed)
-    y, x = np.mgrid[0:height, 0:width].astype(np.float32)
-    img = np.empty((height, width, 3), dtype=np.float32)
-    for c in range(3):
-        px, py = rng.uniform(33, 143, 2)
-        ph = rng.uniform(0, 6.28, 2)
-        amp = rng.uniform(40, 90)
-        img[..., c] = 128 + amp * np.sin(x * (6.2831853 / px) + ph[0]) * np.cos(y * (6.2831853 / py) + ph[1])
-    img += rng.normal(0, 12, img.shape).astype(np.float32)
-    out = np.clip(img, 0, 255).astype(np.uint8)
-    rw, rh = max(8, width // 10), max(8, height // 10)
-    x0 = int(rng.integers(0, max(1, width - rw))); y0 = int(rng.integers(0, max(1, height - rh)))
-    out[y0:y0 + rh, x0:x0 + rw] = 255
-    out[y0 + rh // 3:y0 + rh // 3 + 1, x0:x0 + rw] = 0
-    out[y0:y0 + rh, x0 + rw // 2:x0 + rw // 2 + 1] = 0
-    return out
+from mozjpeg_b200.synth import synth_image  # noqa: E402,F401  (input generator shared with bench.py)
