@@ -77,7 +77,7 @@ struct b200jpeg_encoder {
   bool keep_plain = false;
   // device arenas
   DevBuf d_src, d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_scan, d_tabs_trellis, d_tabs_fixed, d_rec, d_bt;
-  DevBuf d_blk_bits, d_blk_aux, d_total_bits, d_status, d_out_pos, d_scan_size, d_bitbuf, d_out, d_qt, d_tc;
+  DevBuf d_blk_bits, d_blk_aux, d_blk_run, d_total_bits, d_status, d_out_pos, d_scan_size, d_bitbuf, d_out, d_qt, d_tc;
   size_t bitbuf_words_per_image = 0, out_cap_per_image = 0;
   double cap_factor = 0.25;
   // pinned host mirrors
@@ -242,7 +242,6 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
   Plan &pl = e->plan; const b200jpeg_params *p = &e->params; const int n = e->n; cudaStream_t s = e->stream;
   Geom &g = pl.g;
   const int nscans = (int)pl.scans.size();
-  if (pl.progressive) { set_error("progressive scans are not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
   if (p->restart_interval || p->restart_in_rows) { set_error("restart intervals are not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
 
   int rc;
@@ -261,6 +260,7 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
   if ((rc = e->d_rec.reserve((size_t)n * pl.sum_real_blocks * sizeof(DcRec)))) return rc;
   if ((rc = e->d_bt.reserve((size_t)n * pl.sum_real_blocks * 8))) return rc;
   if ((rc = e->d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
+  if (pl.progressive) { if ((rc = e->d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = e->d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
   if ((rc = e->d_total_bits.reserve((size_t)n * 8))) return rc;
   if ((rc = e->d_status.reserve((size_t)n * 4))) return rc;
   if ((rc = e->d_out_pos.reserve((size_t)n * 8))) return rc;
@@ -307,19 +307,38 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
     RecLayout rl; memset(&rl, 0, sizeof rl);
     for (int ci = 0; ci < g.nc; ci++) { rl.comp_off[ci] = rl.per_image; rl.per_image += (long long)g.c[ci].wib * g.c[ci].hib; }
     const size_t hist_bytes_t = hist_bytes * g.nc;
-    tm.mark("trellis_stats");
-    CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes_t, s));
-    launch_gather_comp(g, e->d_hist.as<uint32_t>(), status, n, s);
-    tm.mark("trellis_tables");
-    SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = g.nc;
-    for (int ci = 0; ci < g.nc; ci++) masks.m[ci] = (1u << g.c[ci].dc_tbl) | (1u << (4 + g.c[ci].ac_tbl));
     DevHuff *tset = e->d_tabs_trellis.as<DevHuff>();                                       // [img*nc + ci][8]
-    launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tabset, masks, n * g.nc, s);
+    if (!pl.progressive) {
+      tm.mark("trellis_stats");
+      CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes_t, s));
+      launch_gather_comp(g, e->d_hist.as<uint32_t>(), status, n, s);
+      tm.mark("trellis_tables");
+      SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = g.nc;
+      for (int ci = 0; ci < g.nc; ci++) masks.m[ci] = (1u << g.c[ci].dc_tbl) | (1u << (4 + g.c[ci].ac_tbl));
+      launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tabset, masks, n * g.nc, s);
+    } else {
+      // jcphuff statistics with Ss=1..63, Al=0 (jcmaster.c:462-466), every AC symbol
+      // pre-counted once (jcphuff.c:257-264); the DC table stays the supplied one.
+      for (int ci = 0; ci < g.nc; ci++) {
+        ScanDesc ts; memset(&ts, 0, sizeof ts);
+        ts.ncomps = 1; ts.ci[0] = ci; ts.Ss = 1; ts.Se = 63; ts.bim = 1; ts.k_count[0] = 1;
+        ts.per_row = g.c[ci].wib; ts.rows = g.c[ci].hib; ts.nblocks = (long long)ts.per_row * ts.rows;
+        tm.mark("trellis_stats");
+        CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes, s));
+        launch_seed_hist(e->d_hist.as<uint32_t>(), 4 + g.c[ci].ac_tbl, n, s);
+        launch_prog_prepare(g, ts, e->d_blk_aux.as<uint32_t>(), e->d_blk_run.as<uint32_t>(), n, s);
+        launch_gather_prog(g, ts, e->d_blk_aux.as<uint32_t>(), e->d_blk_run.as<uint32_t>(), e->d_hist.as<uint32_t>(), status, n, s);
+        tm.mark("trellis_tables");
+        SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = 1u << (4 + g.c[ci].ac_tbl);
+        launch_gen_tables(e->d_hist.as<uint32_t>(), tset + (size_t)ci * HIST_SLOTS, tabset * g.nc, masks, n, s);
+      }
+    }
     tm.mark("trellis_ac");
     launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, e->d_rec.as<DcRec>(), rl, n, s);
     if (p->trellis_quant_dc) {
       tm.mark("trellis_dc");
-      launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), tset, tabset, e->d_rec.as<DcRec>(), e->d_bt.as<unsigned long long>(), rl, n, s);
+      if (pl.progressive) launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, e->d_rec.as<DcRec>(), e->d_bt.as<unsigned long long>(), rl, n, s);
+      else launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), tset, tabset, e->d_rec.as<DcRec>(), e->d_bt.as<unsigned long long>(), rl, n, s);
     }
     tm.mark("dummy");
     launch_dummy(g, n, s);
@@ -329,24 +348,30 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
   for (int si = 0; si < nscans; si++) {
     const ScanDesc &sd = pl.scans[si];
     const DevHuff *tabs; size_t tstride;
+    const bool dc_refine = pl.progressive && sd.Ss == 0 && sd.Ah != 0;
+    uint32_t *aux = e->d_blk_aux.as<uint32_t>(), *run_e = e->d_blk_run.as<uint32_t>();
+    if (pl.progressive && sd.Ss != 0) { tm.mark("eobrun_runs"); launch_prog_prepare(g, sd, aux, run_e, n, s); }
     if (pl.optimize) {
       DevHuff *tset = e->d_tabs_scan.as<DevHuff>() + (size_t)si * HIST_SLOTS;             // [img][scan][8]
       tstride = tabset * nscans;
-      tm.mark("scan_stats");
-      CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes, s));
-      launch_gather_seq(g, sd, e->d_hist.as<uint32_t>(), status, n, s);
-      tm.mark("scan_tables");
-      SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = scan_slot_mask(pl, sd);
-      launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tstride, masks, n, s);
+      if (!dc_refine) {                                                                    // jcmaster.c:650-662
+        tm.mark("scan_stats");
+        CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes, s));
+        if (pl.progressive) launch_gather_prog(g, sd, aux, run_e, e->d_hist.as<uint32_t>(), status, n, s);
+        else launch_gather_seq(g, sd, e->d_hist.as<uint32_t>(), status, n, s);
+        tm.mark("scan_tables");
+        SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = scan_slot_mask(pl, sd);
+        launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tstride, masks, n, s);
+      }
       tabs = tset;
     } else { tabs = e->d_tabs_fixed.as<DevHuff>(); tstride = 0; }
     tm.mark("block_bits");
-    launch_block_bits(g, sd, tabs, tstride, 0, e->d_blk_bits.as<uint32_t>(), nullptr, status, n, s);
+    launch_block_bits(g, sd, tabs, tstride, pl.progressive, e->d_blk_bits.as<uint32_t>(), aux, run_e, status, n, s);
     tm.mark("scan_offsets");
     launch_scan_offsets(e->d_blk_bits.as<uint32_t>(), sd.nblocks, e->d_total_bits.as<unsigned long long>(), (size_t)e->bitbuf_words_per_image * 32, status, n, s);
     tm.mark("encode");
     CU(cudaMemsetAsync(e->d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
-    launch_encode(g, sd, tabs, tstride, 0, e->d_blk_bits.as<uint32_t>(), nullptr, e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, status, n, s);
+    launch_encode(g, sd, tabs, tstride, pl.progressive, e->d_blk_bits.as<uint32_t>(), aux, run_e, e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, status, n, s);
     tm.mark("stuff");
     launch_stuff(e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, e->d_total_bits.as<unsigned long long>(),
                  e->d_out.as<uint8_t>(), e->out_cap_per_image, e->out_cap_per_image, e->d_out_pos.as<unsigned long long>(),
@@ -641,7 +666,7 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf *db[] = {&e->d_src, &e->d_hist, &e->d_tabs_scan, &e->d_tabs_trellis, &e->d_tabs_fixed, &e->d_rec, &e->d_bt, &e->d_blk_bits, &e->d_blk_aux,
+  DevBuf *db[] = {&e->d_src, &e->d_hist, &e->d_tabs_scan, &e->d_tabs_trellis, &e->d_tabs_fixed, &e->d_rec, &e->d_bt, &e->d_blk_bits, &e->d_blk_aux, &e->d_blk_run,
                   &e->d_total_bits, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_bitbuf, &e->d_out, &e->d_qt, &e->d_tc};
   for (DevBuf *b : db) b->release();
   for (int i = 0; i < 4; i++) { e->d_coef[i].release(); e->d_raw[i].release(); e->d_plain[i].release(); }

@@ -909,12 +909,271 @@ __global__ void __launch_bounds__(1024) k_stuff(const uint32_t *__restrict__ bit
   }
 }
 
-void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, int progressive,
-                       uint32_t *blk_bits, uint32_t *blk_aux, uint32_t *status, int n, cudaStream_t s)
+// =====================================================================
+// progressive scans (jcphuff.c).  DC scans walk blocks in MCU order like
+// the sequential coder.  AC scans are non-interleaved; their cross-block
+// state (EOBRUN, and in refinement scans the buffered correction bits with
+// the forced flush of jcphuff.c:998-1000) is resolved in three steps:
+//   k_prog_flags : per block  brk (the block calls emit_eobrun before one of
+//                  its own symbols), contrib (the block ends with EOBRUN++),
+//                  tailBR (correction bits it appends to the pending run);
+//   k_prog_runs  : one walker per breaker (and one for the scan start) follows
+//                  the non-breaking blocks after it, applies the 0x7FFF /
+//                  BE>937 forced flushes, and stores each sub-run's EOBRUN value
+//                  at the sub-run's FIRST block;
+//   walk_prog_ac : every block then emits, in stream order, its own symbols,
+//                  the EOBRUN symbol it owns, and its tail correction bits.
+// =====================================================================
+#define AUX_BRK 1u
+#define AUX_CONTRIB 2u
+
+__device__ __forceinline__ void load_block64(const int16_t *__restrict__ blk, int *v)
+{
+  const uint4 *b4 = reinterpret_cast<const uint4 *>(blk);
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    uint4 a = b4[q]; unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[8 * q + j] = (int)(int16_t)((w[j >> 1] >> ((j & 1) * 16)) & 0xFFFF);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_prog_flags(Geom g, ScanDesc sd, uint32_t *__restrict__ aux, uint32_t *__restrict__ run_e)
+{
+  int img = blockIdx.y;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= sd.nblocks) return;
+  int sci, k; long long mcu;
+  const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+  int v[64];
+  load_block64(blk, v);
+  unsigned brk = 0, contrib, tail = 0;
+  if (sd.Ah == 0) {
+    int lastnz = 0;
+#pragma unroll
+    for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && (abs(v[i]) >> sd.Al) != 0) { brk = 1; lastnz = i; }
+    contrib = (lastnz != sd.Se);
+  } else {
+    int lastone = 0;
+#pragma unroll
+    for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && (abs(v[i]) >> sd.Al) == 1) { brk = 1; lastone = i; }
+#pragma unroll
+    for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && i > lastone && (abs(v[i]) >> sd.Al) > 1) tail++;
+    contrib = (lastone != sd.Se);
+  }
+  aux[(size_t)img * sd.nblocks + t] = brk | (contrib << 1) | (tail << 2);
+  run_e[(size_t)img * sd.nblocks + t] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_prog_runs(ScanDesc sd, const uint32_t *__restrict__ aux, uint32_t *__restrict__ run_e)
+{
+  int img = blockIdx.y;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= sd.nblocks) return;
+  const uint32_t *a = aux + (size_t)img * sd.nblocks;
+  uint32_t *re = run_e + (size_t)img * sd.nblocks;
+  unsigned f = a[t];
+  if (!(f & AUX_BRK) && t != 0) return;
+  unsigned E = 0, B = 0; long long first = -1, j;
+  if (f & AUX_BRK) { if (f & AUX_CONTRIB) { E = 1; B = f >> 2; first = t; } j = t + 1; }
+  else j = 0;
+  for (; j < sd.nblocks; j++) {
+    unsigned fj = a[j];
+    if (fj & AUX_BRK) break;
+    if (E == 0) first = j;
+    E += 1; B += fj >> 2;
+    if (E == 0x7FFF || B > 937) { re[first] = E; E = 0; B = 0; }     // jcphuff.c:727-729, :998-1000
+  }
+  if (E > 0) re[first] = E;
+}
+
+// One block of a progressive scan, in stream order.  Sink: dc(nbits, bits),
+// ac(symbol, nbits, bits), raw(bits, n).
+template <class Sink>
+__device__ __forceinline__ void walk_prog_block(const int16_t *__restrict__ blk, const ScanDesc &sd, int last_dc_shifted,
+                                                unsigned aux, unsigned runE, Sink &sink)
+{
+  if (sd.Ss == 0) {
+    int dc = (int)blk[0] >> sd.Al;                       // arithmetic shift (jcphuff.c:497)
+    if (sd.Ah == 0) {                                    // encode_mcu_DC_first :468-548
+      int temp = dc - last_dc_shifted, temp2 = temp;
+      if (temp < 0) { temp = -temp; temp2--; }
+      sink.dc(nbits_of(temp), temp2);
+    } else sink.raw((unsigned)dc & 1u, 1);               // encode_mcu_DC_refine :746-786
+    return;
+  }
+  int v[64];
+  load_block64(blk, v);
+  if (sd.Ah == 0) {                                      // encode_mcu_AC_first :648-737
+    if (aux & AUX_BRK) {
+      int r = 0;
+#pragma unroll
+      for (int i = 1; i < 64; i++) {
+        if (i < sd.Ss || i > sd.Se) continue;
+        int temp = v[i], temp2 = temp >> 31;
+        temp = (temp ^ temp2) - temp2; temp >>= sd.Al;
+        if (temp == 0) { r++; continue; }
+        temp2 ^= temp;
+        while (r > 15) { sink.ac(0xF0, 0, 0); r -= 16; }
+        int nb = nbits_of(temp);
+        sink.ac((r << 4) + nb, nb, temp2);
+        r = 0;
+      }
+    }
+  } else {                                               // encode_mcu_AC_refine :817-1017
+    unsigned long long br = 0; int nbr = 0;
+    if (aux & AUX_BRK) {
+      int EOB = 0;
+#pragma unroll
+      for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && (abs(v[i]) >> sd.Al) == 1) EOB = i;
+      int r = 0;
+#pragma unroll
+      for (int i = 1; i < 64; i++) {
+        if (i < sd.Ss || i > sd.Se) continue;
+        int a = abs(v[i]) >> sd.Al;
+        if (a == 0) { r++; continue; }
+        while (r > 15 && i <= EOB) {
+          sink.ac(0xF0, 0, 0); r -= 16;
+          if (nbr > 32) sink.raw((unsigned)(br >> 32), nbr - 32);
+          if (nbr) sink.raw((unsigned)br, nbr > 32 ? 32 : nbr);
+          br = 0; nbr = 0;
+        }
+        if (a > 1) { br = (br << 1) | (unsigned)(a & 1); nbr++; continue; }
+        sink.ac((r << 4) + 1, 0, 0);
+        sink.raw(v[i] < 0 ? 0u : 1u, 1);
+        if (nbr > 32) sink.raw((unsigned)(br >> 32), nbr - 32);
+        if (nbr) sink.raw((unsigned)br, nbr > 32 ? 32 : nbr);
+        br = 0; nbr = 0; r = 0;
+      }
+    } else {
+#pragma unroll
+      for (int i = 1; i < 64; i++) { if (i < sd.Ss || i > sd.Se) continue; int a = abs(v[i]) >> sd.Al; if (a > 1) { br = (br << 1) | (unsigned)(a & 1); nbr++; } }
+    }
+    // the EOBRUN symbol this block owns, then this block's tail correction bits
+    if (runE) { int nb = nbits_of((int)runE) - 1; sink.ac(nb << 4, nb, (int)runE); }
+    if (nbr > 32) sink.raw((unsigned)(br >> 32), nbr - 32);
+    if (nbr) sink.raw((unsigned)br, nbr > 32 ? 32 : nbr);
+    return;
+  }
+  if (runE) { int nb = nbits_of((int)runE) - 1; sink.ac(nb << 4, nb, (int)runE); }   // emit_eobrun :409-431
+}
+
+__device__ __forceinline__ int prev_dc_shifted(const Geom &g, const ScanDesc &sd, int img, long long t, int sci, long long mcu, int k)
+{
+  if (sd.Ss != 0 || sd.Ah != 0) return 0;
+  long long tp;
+  if (k > sd.k_first[sci]) tp = t - 1;
+  else if (mcu > 0) tp = t - sd.bim + sd.k_count[sci] - 1;
+  else return 0;
+  int s2, k2; long long m2;
+  const int16_t *p = block_ptr(g, sd, img, tp, s2, m2, k2);
+  return (int)p[0] >> sd.Al;
+}
+
+struct HistSinkP {
+  unsigned *dc_hist, *ac_hist; int bad;
+  __device__ void dc(int nb, int) { if (nb > 11) bad = 1; atomicAdd(&dc_hist[nb], 1u); }
+  __device__ void ac(int sym, int nb, int) { if (nb > 14) bad = 1; atomicAdd(&ac_hist[sym], 1u); }
+  __device__ void raw(unsigned, int) {}
+};
+struct CountSinkP {
+  const uint8_t *dsz, *asz; unsigned bits; int bad;
+  __device__ void dc(int nb, int) { int s = dsz[nb]; if (!s) bad = 1; bits += s + nb; }
+  __device__ void ac(int sym, int nb, int) { int s = asz[sym]; if (!s) bad = 1; bits += s + nb; }
+  __device__ void raw(unsigned, int n) { bits += n; }
+};
+struct BitSinkP : BitSink {
+  __device__ void raw(unsigned v, int n) { if (n == 32) { put(v >> 16, 16); put(v & 0xFFFFu, 16); } else put(v, n); }
+};
+
+__global__ void __launch_bounds__(256) k_gather_prog(Geom g, ScanDesc sd, const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
+                                                     uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
+{
+  __shared__ unsigned sh[HIST_SLOTS * HIST_BINS];
+  int img = blockIdx.y;
+  for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < sd.nblocks) {
+    int sci, k; long long mcu;
+    const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+    int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
+    const CompGeom &c = g.c[sd.ci[sci]];
+    HistSinkP sink{sh + c.dc_tbl * HIST_BINS, sh + (4 + c.ac_tbl) * HIST_BINS, 0};
+    unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
+    walk_prog_block(blk, sd, last, a, re, sink);
+    if (sink.bad) atomicOr(&status[img], 2u);
+  }
+  __syncthreads();
+  uint32_t *gh = hist + (size_t)img * HIST_SLOTS * HIST_BINS;
+  for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&gh[i], sh[i]);
+}
+
+__global__ void __launch_bounds__(256) k_block_bits_prog(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
+                                                         const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
+                                                         uint32_t *__restrict__ blk_bits, uint32_t *__restrict__ status)
+{
+  __shared__ ScanTables st;
+  int img = blockIdx.y;
+  if (!(sd.Ss == 0 && sd.Ah != 0)) load_scan_tables(st, tabs, stride, img, g, sd, false);
+  __syncthreads();
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= sd.nblocks) return;
+  int sci, k; long long mcu;
+  const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+  int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
+  const CompGeom &c = g.c[sd.ci[sci]];
+  CountSinkP sink{st.size[c.dc_tbl], st.size[4 + c.ac_tbl], 0u, 0};
+  unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
+  walk_prog_block(blk, sd, last, a, re, sink);
+  if (sink.bad) atomicOr(&status[img], 2u);
+  blk_bits[(size_t)img * sd.nblocks + t] = sink.bits;
+}
+
+__global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
+                                                     const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
+                                                     const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ bitbuf,
+                                                     size_t bitbuf_stride_words, const uint32_t *__restrict__ status)
+{
+  __shared__ ScanTables st;
+  int img = blockIdx.y;
+  if (!(sd.Ss == 0 && sd.Ah != 0)) load_scan_tables(st, tabs, stride, img, g, sd, true);
+  __syncthreads();
+  if (status[img] & ~1u) return;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= sd.nblocks) return;
+  int sci, k; long long mcu;
+  const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+  int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
+  const CompGeom &c = g.c[sd.ci[sci]];
+  unsigned off = blk_off[(size_t)img * sd.nblocks + t];
+  BitSinkP sink;
+  sink.buf = bitbuf + (size_t)img * bitbuf_stride_words; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
+  sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
+  unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
+  walk_prog_block(blk, sd, last, a, re, sink);
+  sink.finish();
+}
+
+void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int n, cudaStream_t s)
+{
+  if (sd.Ss == 0) return;
+  dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
+  k_prog_flags<<<grid, 256, 0, s>>>(g, sd, aux, run_e); LAUNCHED();
+  k_prog_runs<<<grid, 256, 0, s>>>(sd, aux, run_e); LAUNCHED();
+}
+void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  (void)progressive; (void)blk_aux;
-  k_block_bits_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, status);
+  k_gather_prog<<<grid, 256, 0, s>>>(g, sd, aux, run_e, hist, status); LAUNCHED();
+}
+
+void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, int progressive,
+                       uint32_t *blk_bits, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *status, int n, cudaStream_t s)
+{
+  dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
+  if (progressive) k_block_bits_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, status);
+  else k_block_bits_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, status);
   LAUNCHED();
 }
 void launch_scan_offsets(uint32_t *blk_bits, long long nblocks, unsigned long long *total_bits, size_t capacity_bits,
@@ -924,12 +1183,12 @@ void launch_scan_offsets(uint32_t *blk_bits, long long nblocks, unsigned long lo
   LAUNCHED();
 }
 void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, int progressive,
-                   const uint32_t *blk_off, const uint32_t *blk_aux, uint32_t *bitbuf, size_t bitbuf_stride_words,
+                   const uint32_t *blk_off, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *bitbuf, size_t bitbuf_stride_words,
                    const uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  (void)progressive; (void)blk_aux;
-  k_encode_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_off, bitbuf, bitbuf_stride_words, status);
+  if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_off, bitbuf, bitbuf_stride_words, status);
+  else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_off, bitbuf, bitbuf_stride_words, status);
   LAUNCHED();
 }
 void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_stride_words, const unsigned long long *total_bits,

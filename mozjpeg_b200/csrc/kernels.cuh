@@ -95,12 +95,14 @@ void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *ta
                        DcRec *rec, const RecLayout &rl, int n, cudaStream_t s);
 void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                        const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int n, cudaStream_t s);
+void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int n, cudaStream_t s);
+void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
-                       uint32_t *blk_bits, uint32_t *blk_aux, uint32_t *status, int n, cudaStream_t s);
+                       uint32_t *blk_bits, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *status, int n, cudaStream_t s);
 void launch_scan_offsets(uint32_t *blk_bits, long long nblocks, unsigned long long *total_bits, size_t capacity_bits,
                          uint32_t *status, int n, cudaStream_t s);
 void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
-                   const uint32_t *blk_off, const uint32_t *blk_aux, uint32_t *bitbuf, size_t bitbuf_image_stride_words,
+                   const uint32_t *blk_off, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *bitbuf, size_t bitbuf_image_stride_words,
                    const uint32_t *status, int n, cudaStream_t s);
 void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_image_stride_words, const unsigned long long *total_bits,
                   uint8_t *out, size_t out_image_stride, size_t out_capacity, unsigned long long *out_pos, uint32_t *scan_size,
