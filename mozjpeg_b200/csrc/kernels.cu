@@ -14,6 +14,12 @@ __constant__ uint8_t c_zz[64] = {
   12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,  6,  7, 14, 21, 28,
   35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
   58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+// natural index -> zigzag position
+__constant__ uint8_t c_izz[64] = {
+   0,  1,  5,  6, 14, 15, 27, 28,  2,  4,  7, 13, 16, 26, 29, 42,
+   3,  8, 12, 17, 25, 30, 41, 43,  9, 11, 18, 24, 31, 40, 44, 53,
+  10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60,
+  21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
 #define ZZ_LIST \
   X(0,0) X(1,1) X(2,8) X(3,16) X(4,9) X(5,2) X(6,3) X(7,10) X(8,17) X(9,24) X(10,32) X(11,25) X(12,18) X(13,11) X(14,4) X(15,5) \
   X(16,12) X(17,19) X(18,26) X(19,33) X(20,40) X(21,48) X(22,41) X(23,34) X(24,27) X(25,20) X(26,13) X(27,6) X(28,7) X(29,14) X(30,21) X(31,28) \
@@ -187,8 +193,184 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
   }
 }
 
+// =====================================================================
+// K1, tiled fast path (the common layouts: RGB->YCbCr with full-size luma
+// and 1x1-sampled chroma, i.e. 4:4:4 / 4:2:2 / 4:4:0 / 4:2:0, and grayscale).
+// One CTA = one strip of an iMCU row, 128 pixels wide:
+//   A. coalesced 16-byte loads of the RGB strip into shared memory;
+//   B. colour conversion + box downsampling into int16 sample planes (smem);
+//   C. 8 threads per 8x8 block: row pass of the FDCT (after the deringing
+//      pre-filter), transposed through shared memory;
+//   D. column pass, quantization, zigzag placement into a staging buffer;
+//   E. coalesced 16-byte stores of whole 128-byte blocks.
+// Same arithmetic as k_forward (the generic one-thread-per-block kernel).
+// =====================================================================
+template <int HMAX, int VMAX, int NC>
+__global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *__restrict__ src,
+                                                      const QuantTables *__restrict__ qt, int dering)
+{
+  constexpr int TW = 128, TR = 8 * VMAX;
+  constexpr int YBW = TW / 8, YB = YBW * VMAX;           // luma blocks in the tile
+  constexpr int CW = TW / HMAX, CBW = CW / 8;            // chroma samples / blocks per tile row
+  constexpr int NB = YB + (NC == 3 ? 2 * CBW : 0);
+  constexpr int YP = TW + 8, CP = CW + 8;                // padded plane pitches (int16 elements)
+  __shared__ __align__(16) int16_t sY[TR * YP];
+  __shared__ __align__(16) int16_t sC[NC == 3 ? 2 * 8 * CP : 8];
+  __shared__ __align__(16) int16_t sW[NB * 72];
+  __shared__ __align__(16) unsigned char sIO[NB * 256];   // phase A: RGB strip; phases D/E: output staging
+  static_assert(NB * 256 >= TR * TW * 3, "staging buffer too small for the RGB strip");
+
+  const int tid = threadIdx.x;
+  const int tx = blockIdx.x, ty = blockIdx.y, img = blockIdx.z;
+  const int x0 = tx * TW, y0 = ty * TR;
+  const uint8_t *base = src + (size_t)img * g.image_stride;
+  const int ic = g.in_comps;
+
+  // ---- A: load the strip (rows clamped to H-1, columns clamped to W-1) ----
+  uint8_t *sRGB = sIO;
+  {
+    const int rowbytes = TW * ic;
+    const bool full = (x0 + TW <= g.W) && ((g.row_pitch & 15) == 0) && ((((size_t)base) & 15) == 0) && (((size_t)x0 * ic & 15) == 0);
+    if (full) {
+      const int vec_per_row = rowbytes / 16;
+      for (int i = tid; i < TR * vec_per_row; i += 128) {
+        int r = i / vec_per_row, v = i - r * vec_per_row;
+        int iy = min(y0 + r, g.H - 1);
+        const uint4 *p = reinterpret_cast<const uint4 *>(base + (size_t)iy * g.row_pitch + (size_t)x0 * ic) + v;
+        reinterpret_cast<uint4 *>(sRGB + r * rowbytes)[v] = __ldg(p);
+      }
+    } else {
+      for (int i = tid; i < TR * rowbytes; i += 128) {
+        int r = i / rowbytes, b = i - r * rowbytes;
+        int px = b / ic, ch = b - px * ic;
+        int iy = min(y0 + r, g.H - 1), ix = min(x0 + px, g.W - 1);
+        sRGB[i] = base[(size_t)iy * g.row_pitch + (size_t)ix * ic + ch];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- B: colour conversion + downsampling into centred int16 planes ----
+#pragma unroll 2
+  for (int i = tid; i < TR * TW; i += 128) {
+    int r = i / TW, x = i - r * TW;
+    const uint8_t *px = sRGB + (r * TW + x) * ic;
+    int yv = (g.cs_mode == 2) ? px[0] : (19595 * px[0] + 38470 * px[1] + 7471 * px[2] + 32768) >> 16;
+    sY[r * YP + x] = (int16_t)(yv - 128);
+  }
+  if (NC == 3) {
+    const CompGeom &cc = g.c[1];
+    // chroma rows past the last real row group replicate the last real chroma row (jcprepct.c:167-179)
+    const int last_real = cc.rows_avail - 1 - ty * 8;
+#pragma unroll 1
+    for (int i = tid; i < 8 * CW; i += 128) {
+      int cr = i / CW, cx = i - cr * CW;
+      int er = min(cr, last_real);
+      int sb = 0, sr = 0;
+#pragma unroll
+      for (int dv = 0; dv < VMAX; dv++)
+#pragma unroll
+        for (int du = 0; du < HMAX; du++) {
+          const uint8_t *px = sRGB + ((er * VMAX + dv) * TW + cx * HMAX + du) * 3;
+          int R = px[0], G = px[1], B = px[2];
+          sb += (-11059 * R - 21709 * G + 32768 * B + (128 << 16) + 32767) >> 16;
+          sr += (32768 * R - 27439 * G - 5329 * B + (128 << 16) + 32767) >> 16;
+        }
+      int xo = x0 / HMAX + cx;
+      if (HMAX == 2 && VMAX == 1) { sb = (sb + (xo & 1)) >> 1; sr = (sr + (xo & 1)) >> 1; }
+      else if (HMAX == 2 && VMAX == 2) { sb = (sb + 1 + (xo & 1)) >> 2; sr = (sr + 1 + (xo & 1)) >> 2; }
+      else if (HMAX * VMAX > 1) { sb = (sb + HMAX * VMAX / 2) / (HMAX * VMAX); sr = (sr + HMAX * VMAX / 2) / (HMAX * VMAX); }
+      sC[cr * CP + cx] = (int16_t)(sb - 128);
+      sC[8 * CP + cr * CP + cx] = (int16_t)(sr - 128);
+    }
+  }
+  __syncthreads();
+
+  // ---- C: deringing + row pass; 8 lanes per block, lane j owns row j ----
+  const int j = tid & 7;
+#pragma unroll 1
+  for (int b = tid >> 3; b < NB; b += 16) {
+    int16_t *plane; int pitch, bx, byl;
+    if (b < YB) { plane = sY; pitch = YP; byl = b / YBW; bx = b - byl * YBW; }
+    else { int cb = b - YB; int which = cb / CBW; plane = sC + which * 8 * CP; pitch = CP; byl = 0; bx = cb - which * CBW; }
+    int16_t *rowp = plane + (byl * 8 + j) * pitch + bx * 8;
+    int d0 = rowp[0], d1 = rowp[1], d2 = rowp[2], d3 = rowp[3], d4 = rowp[4], d5 = rowp[5], d6 = rowp[6], d7 = rowp[7];
+    if (dering) {
+      int sum = d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7;
+      int cnt = (d0 >= 127) + (d1 >= 127) + (d2 >= 127) + (d3 >= 127) + (d4 >= 127) + (d5 >= 127) + (d6 >= 127) + (d7 >= 127);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1); cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2); cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4); cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+      if (cnt != 0 && cnt != 64) {
+        if (j == 0) {
+          int tmp[64];
+          for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) tmp[8 * r + c] = plane[(byl * 8 + r) * pitch + bx * 8 + c];
+          const int ci = b < YB ? 0 : (1 + (b - YB) / CBW);
+          deringing_slow(tmp, (int)qt->q[g.c[ci].qt][0].d >> 3, sum, cnt);
+          for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) plane[(byl * 8 + r) * pitch + bx * 8 + c] = (int16_t)tmp[8 * r + c];
+        }
+        __syncwarp(0xFFu << (threadIdx.x & 24));          // the 8 lanes of this block
+        d0 = rowp[0]; d1 = rowp[1]; d2 = rowp[2]; d3 = rowp[3]; d4 = rowp[4]; d5 = rowp[5]; d6 = rowp[6]; d7 = rowp[7];
+      }
+    }
+    fdct_1d<0>(d0, d1, d2, d3, d4, d5, d6, d7);
+    int16_t *w = sW + b * 72 + j * 8;
+    w[0] = (int16_t)d0; w[1] = (int16_t)d1; w[2] = (int16_t)d2; w[3] = (int16_t)d3;
+    w[4] = (int16_t)d4; w[5] = (int16_t)d5; w[6] = (int16_t)d6; w[7] = (int16_t)d7;
+  }
+  __syncthreads();
+
+  // ---- D: column pass + quantize; lane j owns column j; zigzag placement in the staging buffer ----
+  int16_t *sQ = reinterpret_cast<int16_t *>(sIO);              // [NB][64] quantized, then [NB][64] raw
+  int16_t *sR = sQ + NB * 64;
+#pragma unroll 1
+  for (int b = tid >> 3; b < NB; b += 16) {
+    const int16_t *w = sW + b * 72 + j;
+    int d0 = w[0], d1 = w[8], d2 = w[16], d3 = w[24], d4 = w[32], d5 = w[40], d6 = w[48], d7 = w[56];
+    fdct_1d<1>(d0, d1, d2, d3, d4, d5, d6, d7);
+    const int ci = b < YB ? 0 : (1 + (b - YB) / CBW);
+    const QuantConst *qc = qt->q[g.c[ci].qt];
+    int dd[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      int nat = 8 * r + j;
+      int k = c_izz[nat];
+      sQ[b * 64 + k] = (int16_t)quant_one(dd[r], qc[nat], dering);
+      sR[b * 64 + k] = (int16_t)dd[r];
+    }
+  }
+  __syncthreads();
+
+  // ---- E: whole blocks out, 16 bytes per thread-store ----
+  for (int i = tid; i < NB * 8; i += 128) {
+    int b = i >> 3, v = i & 7;
+    int ci, row, col;
+    if (b < YB) { ci = 0; int byl = b / YBW; row = ty * VMAX + byl; col = tx * YBW + (b - byl * YBW); }
+    else { int cb = b - YB; int which = cb / CBW; ci = 1 + which; row = ty; col = tx * CBW + (cb - which * CBW); }
+    const CompGeom &c = g.c[ci];
+    if (row >= c.hib || col >= c.wib) continue;
+    size_t blk = ((size_t)img * c.hpad + row) * c.wpad + col;
+    reinterpret_cast<uint4 *>(c.coef + blk * 64)[v] = reinterpret_cast<const uint4 *>(sQ + b * 64)[v];
+    reinterpret_cast<uint4 *>(c.raw + blk * 64)[v] = reinterpret_cast<const uint4 *>(sR + b * 64)[v];
+  }
+}
+
 void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, int n, cudaStream_t s)
 {
+  // fast path: full-size first component, (for colour) two 1x1-sampled chroma components
+  bool gray = g.nc == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
+  bool ycc = g.nc == 3 && g.cs_mode == 0 && g.in_comps == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax &&
+             g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
+  if ((gray && g.hmax == 1 && g.vmax == 1) || ycc) {
+    dim3 grid((g.W + 127) / 128, g.mcu_rows, n);
+    if (gray) k_forward_tile<1, 1, 1><<<grid, 128, 0, s>>>(g, src, qt, dering);
+    else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3><<<grid, 128, 0, s>>>(g, src, qt, dering);
+    else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3><<<grid, 128, 0, s>>>(g, src, qt, dering);
+    else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3><<<grid, 128, 0, s>>>(g, src, qt, dering);
+    else k_forward_tile<2, 2, 3><<<grid, 128, 0, s>>>(g, src, qt, dering);
+    LAUNCHED();
+    return;
+  }
   int mw = 0, mh = 0;
   for (int ci = 0; ci < g.nc; ci++) { mw = max(mw, g.c[ci].wib); mh = max(mh, g.c[ci].hib); }
   dim3 grid((mw + 127) / 128, mh, n * g.nc);
