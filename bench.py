@@ -135,10 +135,20 @@ def cpu_reference_run(images, switches, threads, reps):
 
 
 def host_threads():
+    """Host threads the reference arm can really use: the CPU affinity mask,
+    capped by the cgroup CPU quota (the GPU boxes expose 128 logical CPUs but
+    cap the container at 16 CPUs' worth of time; more threads only thrash)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(round(int(quota) / int(period)))))
+    except Exception:
+        pass
+    return n
 
 
 def run_reference_arm(a, rank, world):

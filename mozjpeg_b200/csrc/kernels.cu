@@ -2,6 +2,7 @@
 // Compile with: -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
 #include "kernels.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 namespace b200 {
 
@@ -69,7 +70,7 @@ __device__ __forceinline__ void fdct_1d(int &d0, int &d1, int &d2, int &d3, int 
 }
 
 // jcdctmgr.c:387-403 (fp32, no contraction: this TU is built with -fmad=false)
-__device__ __noinline__ float catmull_rom(int v1, int v2, int v3, int v4, float t, int size)
+__device__ __forceinline__ float catmull_rom(int v1, int v2, int v3, int v4, float t, int size)
 {
   const int tan1 = (v3 - v1) * size, tan2 = (v4 - v2) * size;
   const float t2 = t * t, t3 = t2 * t;
@@ -79,22 +80,24 @@ __device__ __noinline__ float catmull_rom(int v1, int v2, int v3, int v4, float 
   const float f4 = t3 - t2;
   return (float)v2 * f1 + (float)tan1 * f3 + (float)v3 * f2 + (float)tan2 * f4;
 }
-// jcdctmgr.c:416-498; data[] natural order, dynamic indexing (rare slow path)
-__device__ __noinline__ void deringing_slow(int *data, int q0, int sum, int cnt)
+// jcdctmgr.c:416-498 preprocess_deringing on one block; A(n) reads/writes the
+// centred sample at NATURAL index n.  Rare path (blocks touching max white).
+template <class Acc>
+__device__ __forceinline__ void deringing_block(Acc A, int q0, int sum, int cnt)
 {
   const int maxsample = 127, size = 64;
   int m = min(min(31, 2 * q0), (maxsample * size - sum) / cnt);
   int maxover = maxsample + m;
   int n = 0;
   do {
-    if (data[c_zz[n]] < maxsample) { n++; continue; }
+    if (A.get(c_zz[n]) < maxsample) { n++; continue; }
     int start = n;
-    while (++n < size && data[c_zz[n]] >= maxsample) {}
+    while (++n < size && A.get(c_zz[n]) >= maxsample) {}
     int end = n;
-    int f1 = data[c_zz[start >= 1 ? start - 1 : 0]];
-    int f2 = data[c_zz[start >= 2 ? start - 2 : 0]];
-    int l1 = data[c_zz[end < size - 1 ? end : size - 1]];
-    int l2 = data[c_zz[end < size - 2 ? end + 1 : size - 1]];
+    int f1 = A.get(c_zz[start >= 1 ? start - 1 : 0]);
+    int f2 = A.get(c_zz[start >= 2 ? start - 2 : 0]);
+    int l1 = A.get(c_zz[end < size - 1 ? end : size - 1]);
+    int l2 = A.get(c_zz[end < size - 2 ? end + 1 : size - 1]);
     int fslope = max(f1 - f2, maxsample - f1);
     int lslope = max(l1 - l2, maxsample - l1);
     if (start == 0) fslope = lslope;
@@ -104,11 +107,17 @@ __device__ __noinline__ void deringing_slow(int *data, int q0, int sum, int cnt)
     float position = step;
     for (int i = start; i < end; i++, position += step) {
       int tmp = (int)ceilf(catmull_rom(maxsample - fslope, maxsample, maxsample, maxsample - lslope, position, length));
-      data[c_zz[i]] = min(tmp, maxover);
+      A.set(c_zz[i], min(tmp, maxover));
     }
     n++;
   } while (n < size);
 }
+struct LocalAcc { int *d; __device__ int get(int n) const { return d[n]; } __device__ void set(int n, int v) const { d[n] = v; } };
+struct PlaneAcc {      // 8x8 block inside an int16 sample plane in shared memory
+  int16_t *p; int pitch;
+  __device__ int get(int n) const { return p[(n >> 3) * pitch + (n & 7)]; }
+  __device__ void set(int n, int v) const { p[(n >> 3) * pitch + (n & 7)] = (int16_t)v; }
+};
 
 __device__ __forceinline__ unsigned quant_one(int x, QuantConst k, int dering)
 {
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
       int tmp[64];
 #pragma unroll
       for (int i = 0; i < 64; i++) tmp[i] = ws[i];
-      deringing_slow(tmp, (int)qt->q[c.qt][0].d >> 3, sum, cnt);
+      deringing_block(LocalAcc{tmp}, (int)qt->q[c.qt][0].d >> 3, sum, cnt);
 #pragma unroll
       for (int i = 0; i < 64; i++) ws[i] = tmp[i];
     }
@@ -303,11 +312,8 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
       sum += __shfl_xor_sync(0xffffffffu, sum, 4); cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
       if (cnt != 0 && cnt != 64) {
         if (j == 0) {
-          int tmp[64];
-          for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) tmp[8 * r + c] = plane[(byl * 8 + r) * pitch + bx * 8 + c];
           const int ci = b < YB ? 0 : (1 + (b - YB) / CBW);
-          deringing_slow(tmp, (int)qt->q[g.c[ci].qt][0].d >> 3, sum, cnt);
-          for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) plane[(byl * 8 + r) * pitch + bx * 8 + c] = (int16_t)tmp[8 * r + c];
+          deringing_block(PlaneAcc{plane + (byl * 8) * pitch + bx * 8, pitch}, (int)qt->q[g.c[ci].qt][0].d >> 3, sum, cnt);
         }
         __syncwarp(0xFFu << (threadIdx.x & 24));          // the 8 lanes of this block
         d0 = rowp[0]; d1 = rowp[1]; d2 = rowp[2]; d3 = rowp[3]; d4 = rowp[4]; d5 = rowp[5]; d6 = rowp[6]; d7 = rowp[7];
@@ -361,7 +367,8 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
   bool gray = g.nc == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
   bool ycc = g.nc == 3 && g.cs_mode == 0 && g.in_comps == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax &&
              g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
-  if ((gray && g.hmax == 1 && g.vmax == 1) || ycc) {
+  static const bool force_generic = getenv("B200JPEG_GENERIC_FORWARD") != nullptr;   // A/B switch for debugging
+  if (!force_generic && ((gray && g.hmax == 1 && g.vmax == 1) || ycc)) {
     dim3 grid((g.W + 127) / 128, g.mcu_rows, n);
     if (gray) k_forward_tile<1, 1, 1><<<grid, 128, 0, s>>>(g, src, qt, dering);
     else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3><<<grid, 128, 0, s>>>(g, src, qt, dering);
@@ -896,13 +903,119 @@ __global__ void __launch_bounds__(64) k_trellis_dc(Geom g, const TrellisConsts *
     }
   }
 }
+// ---------------------------------------------------------------------
+// DC trellis, warp-cooperative version: 9 lanes per Viterbi chain (lane k =
+// candidate k), 3 chains per warp.  Back pointers and the per-block candidate
+// base live in shared memory, so the serial back-track (:1308-1327) chases
+// pointers at shared-memory latency.  Same arithmetic and tie-breaks as
+// k_trellis_dc (the one-thread-per-chain fallback for very wide images).
+// smem per chain: wib * 11 bytes (9 back pointers + int16 signed base).
+// ---------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_trellis_dc_warp(Geom g, const TrellisConsts *__restrict__ tc,
+                                                        const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
+                                                        const DcRec *__restrict__ rec, RecLayout rl, int max_wib)
+{
+  extern __shared__ unsigned char dsm[];
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
+  const CompGeom &c = g.c[ci];
+  __shared__ uint8_t dcsi[32];
+  {
+    const DevHuff *dc = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + c.dc_tbl;
+    if (threadIdx.x < 32) dcsi[threadIdx.x] = dc->size[threadIdx.x];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / 9, k = lane - grp * 9;                 // lanes 27..31: grp == 3, idle
+  const int chain_in_cta = warp * 3 + grp;
+  const int chains_per_cta = (blockDim.x >> 5) * 3;
+  const int imcu = blockIdx.x * chains_per_cta + chain_in_cta;
+  const int n_imcu = (c.hib + c.v - 1) / c.v;
+  const bool active = grp < 3 && imcu < n_imcu;
+  int16_t *qs = reinterpret_cast<int16_t *>(dsm) + (size_t)chain_in_cta * max_wib;
+  uint8_t *bt8 = dsm + (size_t)chains_per_cta * max_wib * 2 + (size_t)chain_in_cta * max_wib * 9;
+  const int q = tc->q8_zz[c.qt][0];
+  int ncand = (2 + 60 / (q >> 3)) | 1; if (ncand > 9) ncand = 9;
+  const int half = ncand / 2;
+  const int lim = 1 << tc->max_coef_bits;
+  const int gbase = grp * 9;
+  int last_dc = 0;
+  for (int br = 0; br < c.v; br++) {
+    int row = imcu * c.v + br;
+    bool rowok = active && row < c.hib;                        // uniform within a 9-lane group
+    size_t rbase = (size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)(rowok ? row : 0) * c.wib;
+    float acc = 0.f; int prevc = 0;
+    DcRec r = rec[rbase];
+    for (int bi = 0; bi < c.wib; bi++) {
+      DcRec rn = rec[rbase + min(bi + 1, c.wib - 1)];          // prefetch the next record
+      int raw = r.raw_dc, sign = raw >> 31, x = abs(raw);
+      int qval = (x + q / 2) / q;
+      int cd = qval - half + k;
+      if (cd >= lim) cd = lim - 1;
+      if (cd <= -lim) cd = -lim + 1;
+      int delta = cd * q - x;
+      float dist = (float)(delta * delta) * r.lambda_dc;
+      cd *= 1 + 2 * sign;
+      float best; int bl = 0;
+      if (bi == 0) {
+        int bits = nbits_of(abs(cd - last_dc));
+        best = (float)(bits + dcsi[bits]) + dist;
+      } else {
+        best = 0.f;
+#pragma unroll
+        for (int l = 0; l < 9; l++) {
+          int pc = __shfl_sync(0xffffffffu, prevc, gbase + l);
+          float pa = __shfl_sync(0xffffffffu, acc, gbase + l);
+          if (l < ncand) {
+            int bits = nbits_of(abs(cd - pc));
+            float cost = (float)(bits + dcsi[bits]) + dist + pa;
+            if (l == 0 || cost < best) { best = cost; bl = l; }
+          }
+        }
+      }
+      acc = best; prevc = cd;
+      if (rowok && k < ncand) bt8[(size_t)bi * 9 + k] = (uint8_t)bl;
+      if (rowok && k == 0) qs[bi] = (int16_t)(sign ? -qval - 1 : qval);     // sign folded in (one's complement keeps -0 distinct)
+      r = rn;
+    }
+    // first minimum over the candidates (:1309-1313)
+    int j = 0; float bj = __shfl_sync(0xffffffffu, acc, gbase);
+#pragma unroll
+    for (int i = 1; i < 9; i++) { float a = __shfl_sync(0xffffffffu, acc, gbase + i); if (i < ncand && a < bj) { bj = a; j = i; } }
+    __syncwarp();
+    if (rowok && k == 0) {
+      for (int bi = c.wib - 1; bi >= 0; bi--) {
+        int e = qs[bi]; int sg = e < 0; int qval = sg ? -e - 1 : e;
+        int cd = qval - half + j;
+        if (cd >= lim) cd = lim - 1;
+        if (cd <= -lim) cd = -lim + 1;
+        if (sg) cd = -cd;
+        c.coef[(((size_t)img * c.hpad + row) * c.wpad + bi) * 64] = (int16_t)cd;
+        if (bi == c.wib - 1) last_dc = cd;
+        j = bt8[(size_t)bi * 9 + j];
+      }
+    }
+    last_dc = __shfl_sync(0xffffffffu, last_dc, gbase < 27 ? gbase : 0);
+    __syncwarp();
+  }
+}
 void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                        const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int n, cudaStream_t s)
 {
-  int n_imcu = 0;
-  for (int ci = 0; ci < g.nc; ci++) n_imcu = max(n_imcu, (g.c[ci].hib + g.c[ci].v - 1) / g.c[ci].v);
-  dim3 grid((n_imcu + 63) / 64, n * g.nc);
-  k_trellis_dc<<<grid, 64, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, bt, rl);
+  int n_imcu = 0, max_wib = 0;
+  for (int ci = 0; ci < g.nc; ci++) { n_imcu = max(n_imcu, (g.c[ci].hib + g.c[ci].v - 1) / g.c[ci].v); max_wib = max(max_wib, g.c[ci].wib); }
+  // warp-cooperative kernel when a chain's back pointers fit in shared memory
+  int warps = 2;
+  size_t smem = (size_t)warps * 3 * max_wib * 11;
+  if (smem > 200 * 1024) { warps = 1; smem = (size_t)3 * max_wib * 11; }
+  if (smem <= 200 * 1024) {
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) { cudaFuncSetAttribute(k_trellis_dc_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = 200 * 1024; }
+    dim3 grid((n_imcu + warps * 3 - 1) / (warps * 3), n * g.nc);
+    k_trellis_dc_warp<<<grid, warps * 32, smem, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, max_wib);
+  } else {
+    dim3 grid((n_imcu + 63) / 64, n * g.nc);
+    k_trellis_dc<<<grid, 64, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, bt, rl);
+  }
   LAUNCHED();
 }
 
