@@ -76,7 +76,7 @@ struct b200jpeg_encoder {
   int n = 0;
   bool keep_plain = false;
   // device arenas
-  DevBuf d_src, d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_scan, d_tabs_trellis, d_tabs_fixed, d_rec, d_bt;
+  DevBuf d_src, d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_scan, d_tabs_trellis, d_tabs_fixed, d_rec, d_bt, d_perm;
   DevBuf d_blk_bits, d_blk_aux, d_blk_run, d_total_bits, d_status, d_out_pos, d_scan_size, d_bitbuf, d_out, d_qt, d_tc;
   size_t bitbuf_words_per_image = 0, out_cap_per_image = 0;
   double cap_factor = 0.25;
@@ -259,6 +259,7 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
   if ((rc = e->d_tabs_fixed.reserve(tabset))) return rc;
   if ((rc = e->d_rec.reserve((size_t)n * pl.sum_real_blocks * sizeof(DcRec)))) return rc;
   if ((rc = e->d_bt.reserve((size_t)n * pl.sum_real_blocks * 8))) return rc;
+  if ((rc = e->d_perm.reserve((size_t)n * pl.sum_real_blocks * 4))) return rc;
   if ((rc = e->d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
   if (pl.progressive) { if ((rc = e->d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = e->d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
   if ((rc = e->d_total_bits.reserve((size_t)n * 8))) return rc;
@@ -293,8 +294,10 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
   uint32_t *status = e->d_status.as<uint32_t>();
 
   // ---- pass 0 data path: colour/downsample/FDCT/quantize (compress_first_pass) ----
+  RecLayout rl; memset(&rl, 0, sizeof rl);
+  for (int ci = 0; ci < g.nc; ci++) { rl.comp_off[ci] = rl.per_image; rl.per_image += (long long)g.c[ci].wib * g.c[ci].hib; }
   tm.mark("forward");
-  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), pl.dering, n, s);
+  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), pl.dering, pl.trellis ? e->d_rec.as<DcRec>() : nullptr, rl, n, s);
   tm.mark("dummy");
   launch_dummy(g, n, s);
 
@@ -304,8 +307,6 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
   //      is ONE launch over all components of all images. ----
   if (pl.trellis) {
     if (e->keep_plain) for (int ci = 0; ci < g.nc; ci++) CU(cudaMemcpyAsync(e->d_plain[ci].p, e->d_coef[ci].p, pl.coef_bytes[ci] * n, cudaMemcpyDeviceToDevice, s));
-    RecLayout rl; memset(&rl, 0, sizeof rl);
-    for (int ci = 0; ci < g.nc; ci++) { rl.comp_off[ci] = rl.per_image; rl.per_image += (long long)g.c[ci].wib * g.c[ci].hib; }
     const size_t hist_bytes_t = hist_bytes * g.nc;
     DevHuff *tset = e->d_tabs_trellis.as<DevHuff>();                                       // [img*nc + ci][8]
     if (!pl.progressive) {
@@ -333,8 +334,10 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
         launch_gen_tables(e->d_hist.as<uint32_t>(), tset + (size_t)ci * HIST_SLOTS, tabset * g.nc, masks, n, s);
       }
     }
+    tm.mark("trellis_sort");
+    launch_sort_blocks(g, e->d_rec.as<DcRec>(), rl, e->d_perm.as<uint32_t>(), n, s);
     tm.mark("trellis_ac");
-    launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, e->d_rec.as<DcRec>(), rl, n, s);
+    launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, e->d_rec.as<DcRec>(), rl, e->d_perm.as<uint32_t>(), n, s);
     if (p->trellis_quant_dc) {
       tm.mark("trellis_dc");
       if (pl.progressive) launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, e->d_rec.as<DcRec>(), e->d_bt.as<unsigned long long>(), rl, n, s);
@@ -666,7 +669,7 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf *db[] = {&e->d_src, &e->d_hist, &e->d_tabs_scan, &e->d_tabs_trellis, &e->d_tabs_fixed, &e->d_rec, &e->d_bt, &e->d_blk_bits, &e->d_blk_aux, &e->d_blk_run,
+  DevBuf *db[] = {&e->d_src, &e->d_hist, &e->d_tabs_scan, &e->d_tabs_trellis, &e->d_tabs_fixed, &e->d_rec, &e->d_bt, &e->d_perm, &e->d_blk_bits, &e->d_blk_aux, &e->d_blk_run,
                   &e->d_total_bits, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_bitbuf, &e->d_out, &e->d_qt, &e->d_tc};
   for (DevBuf *b : db) b->release();
   for (int i = 0; i < 4; i++) { e->d_coef[i].release(); e->d_raw[i].release(); e->d_plain[i].release(); }

@@ -128,7 +128,8 @@ __device__ __forceinline__ unsigned quant_one(int x, QuantConst k, int dering)
 }
 
 __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restrict__ src,
-                                                 const QuantTables *__restrict__ qt, int dering)
+                                                 const QuantTables *__restrict__ qt, int dering,
+                                                 DcRec *__restrict__ rec, RecLayout rl)
 {
   const int ci = blockIdx.z % g.nc, img = blockIdx.z / g.nc;
   const CompGeom &c = g.c[ci];
@@ -184,6 +185,13 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
   for (int col = 0; col < 8; col++)
     fdct_1d<1>(ws[col], ws[8 + col], ws[16 + col], ws[24 + col], ws[32 + col], ws[40 + col], ws[48 + col], ws[56 + col]);
 
+  if (rec) {       // side record for the trellis: norm numerator in natural order (jcdctmgr.c:1026-1029), raw DC, #non-zero ACs
+    float norm = 0.0f; int nz = 0;
+#pragma unroll
+    for (int i = 1; i < 64; i++) { norm += (float)(ws[i] * ws[i]); nz += (quant_one(ws[i], qt->q[c.qt][i], dering) != 0u); }
+    DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)ws[0]; rr.nz = (uint8_t)nz; rr.pad = 0;
+    rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)by * c.wib + bx] = rr;
+  }
   // quantize (jcdctmgr.c:611-682 == sign(x)*floor((|x| + d/2)/d), d = 8Q) + deringing clamp (:761-770),
   // packed two int16 per 32-bit word in ZIGZAG order
   size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
@@ -216,7 +224,8 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
 // =====================================================================
 template <int HMAX, int VMAX, int NC>
 __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *__restrict__ src,
-                                                      const QuantTables *__restrict__ qt, int dering)
+                                                      const QuantTables *__restrict__ qt, int dering,
+                                                      DcRec *__restrict__ rec, RecLayout rl)
 {
   constexpr int TW = 128, TR = 8 * VMAX;
   constexpr int YBW = TW / 8, YB = YBW * VMAX;           // luma blocks in the tile
@@ -347,6 +356,25 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   }
   __syncthreads();
 
+  // ---- D2: trellis side record, one thread per block: serial fp32 sum of squares in NATURAL order ----
+  if (rec) {
+    for (int b = tid; b < NB; b += 128) {
+      int ci, row, col;
+      if (b < YB) { ci = 0; int byl = b / YBW; row = ty * VMAX + byl; col = tx * YBW + (b - byl * YBW); }
+      else { int cb = b - YB; int which = cb / CBW; ci = 1 + which; row = ty; col = tx * CBW + (cb - which * CBW); }
+      const CompGeom &c = g.c[ci];
+      if (row >= c.hib || col >= c.wib) continue;
+      const int16_t *r = sR + b * 64, *q = sQ + b * 64;
+      float norm = 0.0f; int nz = 0;
+#pragma unroll 9
+      for (int i = 1; i < 64; i++) { int v = r[c_izz[i]]; norm += (float)(v * v); }
+#pragma unroll 9
+      for (int k = 1; k < 64; k++) nz += (q[k] != 0);
+      DcRec rr; rr.lambda_dc = norm; rr.raw_dc = r[0]; rr.nz = (uint8_t)nz; rr.pad = 0;
+      rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * c.wib + col] = rr;
+    }
+  }
+
   // ---- E: whole blocks out, 16 bytes per thread-store ----
   for (int i = tid; i < NB * 8; i += 128) {
     int b = i >> 3, v = i & 7;
@@ -361,7 +389,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   }
 }
 
-void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, int n, cudaStream_t s)
+void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s)
 {
   // fast path: full-size first component, (for colour) two 1x1-sampled chroma components
   bool gray = g.nc == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
@@ -370,18 +398,18 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
   static const bool force_generic = getenv("B200JPEG_GENERIC_FORWARD") != nullptr;   // A/B switch for debugging
   if (!force_generic && ((gray && g.hmax == 1 && g.vmax == 1) || ycc)) {
     dim3 grid((g.W + 127) / 128, g.mcu_rows, n);
-    if (gray) k_forward_tile<1, 1, 1><<<grid, 128, 0, s>>>(g, src, qt, dering);
-    else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3><<<grid, 128, 0, s>>>(g, src, qt, dering);
-    else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3><<<grid, 128, 0, s>>>(g, src, qt, dering);
-    else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3><<<grid, 128, 0, s>>>(g, src, qt, dering);
-    else k_forward_tile<2, 2, 3><<<grid, 128, 0, s>>>(g, src, qt, dering);
+    if (gray) k_forward_tile<1, 1, 1><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+    else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+    else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+    else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+    else k_forward_tile<2, 2, 3><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
     LAUNCHED();
     return;
   }
   int mw = 0, mh = 0;
   for (int ci = 0; ci < g.nc; ci++) { mw = max(mw, g.c[ci].wib); mh = max(mh, g.c[ci].hib); }
   dim3 grid((mw + 127) / 128, mh, n * g.nc);
-  k_forward<<<grid, 128, 0, s>>>(g, src, qt, dering);
+  k_forward<<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
   LAUNCHED();
 }
 
@@ -670,75 +698,97 @@ void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s) { k_seed_
 //            (:1211-1222).
 // =====================================================================
 #define TRELLIS_THREADS 128
-__global__ void __launch_bounds__(TRELLIS_THREADS) k_trellis_ac(Geom g, const TrellisConsts *__restrict__ tc,
-                                                                const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
-                                                                DcRec *__restrict__ rec, RecLayout rl)
+
+// Order the real blocks of every (image, component) by decreasing number of
+// non-zero plain-quantized AC coefficients (counting sort on DcRec.nz), so that
+// the 32 blocks a warp of k_trellis_ac works on have similar trip counts.
+__global__ void __launch_bounds__(256) k_sort_blocks(Geom g, const DcRec *__restrict__ rec, RecLayout rl, uint32_t *__restrict__ perm)
 {
-  const int ci = blockIdx.z % g.nc, img = blockIdx.z / g.nc;
+  __shared__ unsigned cnt[64], start[64];
+  const int ci = blockIdx.x % g.nc, img = blockIdx.x / g.nc;
+  const CompGeom &c = g.c[ci];
+  const long long nblk = (long long)c.wib * c.hib;
+  const DcRec *r = rec + (size_t)img * rl.per_image + rl.comp_off[ci];
+  uint32_t *p = perm + (size_t)img * rl.per_image + rl.comp_off[ci];
+  if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) atomicAdd(&cnt[63 - min((int)r[b].nz, 63)], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned a = 0; for (int k = 0; k < 64; k++) { start[k] = a; a += cnt[k]; } }
+  __syncthreads();
+  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) { unsigned pos = atomicAdd(&start[63 - min((int)r[b].nz, 63)], 1u); p[pos] = (uint32_t)b; }
+}
+void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, int n, cudaStream_t s)
+{
+  k_sort_blocks<<<n * g.nc, 256, 0, s>>>(g, rec, rl, perm);
+  LAUNCHED();
+}
+
+__global__ void __launch_bounds__(TRELLIS_THREADS, 8) k_trellis_ac(Geom g, const TrellisConsts *__restrict__ tc,
+                                                                   const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
+                                                                   DcRec *__restrict__ rec, RecLayout rl, const uint32_t *__restrict__ perm)
+{
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
   const CompGeom &c = g.c[ci];
   __shared__ uint8_t acsi[256];
-  int by = blockIdx.y;
-  if (by >= c.hib || blockIdx.x * blockDim.x >= c.wib) return;
+  const long long nblk = (long long)c.wib * c.hib;
+  if ((long long)blockIdx.x * blockDim.x >= nblk) return;
   {
-    const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.z * tabs_set_stride) + (4 + c.ac_tbl);
+    const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + (4 + c.ac_tbl);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) acsi[i] = ac->size[i];
   }
   __syncthreads();
-  int bx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (bx >= c.wib) return;
-  size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
+  const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tix >= nblk) return;
+  const size_t rbase = (size_t)img * rl.per_image + rl.comp_off[ci];
+  const unsigned lin = perm[rbase + tix];
+  const int by = lin / c.wib, bx = lin - by * c.wib;
+  const size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
   const uint4 *r4 = reinterpret_cast<const uint4 *>(c.raw + blk * 64);
   uint4 *q4 = reinterpret_cast<uint4 *>(c.coef + blk * 64);
-  unsigned rw[32], qw[32];
-#pragma unroll
-  for (int v = 0; v < 8; v++) {
-    uint4 a = r4[v]; rw[4 * v] = a.x; rw[4 * v + 1] = a.y; rw[4 * v + 2] = a.z; rw[4 * v + 3] = a.w;
-    uint4 b = q4[v]; qw[4 * v] = b.x; qw[4 * v + 1] = b.y; qw[4 * v + 2] = b.z; qw[4 * v + 3] = b.w;
-  }
-#define RAWZ(k) ((int)(int16_t)((rw[(k) >> 1] >> (((k) & 1) * 16)) & 0xFFFF))
-#define QNTZ(k) ((int)(int16_t)((qw[(k) >> 1] >> (((k) & 1) * 16)) & 0xFFFF))
-  // norm over natural order i = 1..63  (:1026-1030)
-  float norm = 0.0f;
-  {
-    int nat[64];
-#define X(k, n) nat[n] = RAWZ(k);
-    ZZ_LIST
-#undef X
-#pragma unroll
-    for (int i = 1; i < 64; i++) norm += (float)(nat[i] * nat[i]);
-  }
-  norm = (float)((double)norm / 63.0);
+  // lambda from the block's norm (K1 left the natural-order sum of squares in rec.f)   :1026-1035
   float lambda;
-  if (tc->use_norm) lambda = (float)(tc->p1 / (tc->p2 + (double)norm));     // :1032-1035 (lambda_base == 1)
-  else lambda = tc->lambda_const;
+  {
+    DcRec rr = rec[rbase + lin];
+    float norm = (float)((double)rr.lambda_dc / 63.0);
+    if (tc->use_norm) lambda = (float)(tc->p1 / (tc->p2 + (double)norm));
+    else lambda = tc->lambda_const;
+    rec[rbase + lin].lambda_dc = lambda * tc->w_zz[c.qt][0];
+  }
   const float *wz = tc->w_zz[c.qt];
   const int *q8 = tc->q8_zz[c.qt];
-  {
-    DcRec rr; rr.lambda_dc = lambda * wz[0]; rr.raw_dc = (int16_t)RAWZ(0); rr.pad = 0;
-    rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)by * c.wib + bx] = rr;
-  }
 
-  // phase 1
+  // phase 1: zero-distortion prefix (zigzag order, serial fp32) + compact list of non-zero positions
   float e_azd_at[64], e_azd_before[64], e_acc[64];
   uint8_t e_pos[64], e_rs[64], e_k[64];
   short e_qv[64], e_x[64];
   int m = 0;
   float azd = 0.0f;
   const int maxq = (1 << tc->max_coef_bits) - 1;
+  int dc_q = 0;
+#pragma unroll 1
+  for (int v = 0; v < 8; v++) {
+    uint4 a = r4[v], b = q4[v];
+    unsigned aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-  for (int i = 1; i < 64; i++) {
-    int x = abs(RAWZ(i));
-    float before = azd;
-    azd = (float)(x * x) * lambda * wz[i] + azd;                               // :1134
-    int qv = abs(QNTZ(i));
-    if (qv != 0) {
-      e_pos[m] = (uint8_t)i; e_x[m] = (short)RAWZ(i); e_qv[m] = (short)min(qv, maxq); e_azd_at[m] = azd; e_azd_before[m] = before; m++;
+    for (int jj = 0; jj < 8; jj++) {
+      int i = 8 * v + jj;
+      int rawv = (int)(int16_t)((aw[jj >> 1] >> ((jj & 1) * 16)) & 0xFFFF);
+      int qntv = (int)(int16_t)((bw[jj >> 1] >> ((jj & 1) * 16)) & 0xFFFF);
+      if (i == 0) { dc_q = qntv; continue; }
+      int x = abs(rawv);
+      float before = azd;
+      azd = (float)(x * x) * lambda * wz[i] + azd;                               // :1134
+      int qv = abs(qntv);
+      if (qv != 0) {
+        e_pos[m] = (uint8_t)i; e_x[m] = (short)rawv; e_qv[m] = (short)min(qv, maxq); e_azd_at[m] = azd; e_azd_before[m] = before; m++;
+      }
     }
   }
   const float azd63 = azd;
   const int zrl_bits = acsi[0xF0];
 
-  // phase 2
+  // phase 2: best (predecessor, candidate) per listed position, strict '<' in (predecessor, candidate) order  :1157-1184
   for (int t = 0; t < m; t++) {
     int i = e_pos[t];
     int x = abs((int)e_x[t]);
@@ -771,7 +821,7 @@ __global__ void __launch_bounds__(TRELLIS_THREADS) k_trellis_ac(Geom g, const Tr
     e_acc[t] = best; e_rs[t] = (uint8_t)best_s; e_k[t] = (uint8_t)(best_k < 0 ? 255 : best_k);
   }
 
-  // phase 3
+  // phase 3: best end-of-block position (:1187-1207) and back-tracking (:1211-1222)
   int last = 0;                                  // 1-based entry index, 0 = none
   {
     float best_cost = azd63 + (float)acsi[0];
@@ -782,13 +832,9 @@ __global__ void __launch_bounds__(TRELLIS_THREADS) k_trellis_ac(Geom g, const Tr
     }
   }
   // output: zeros except the back-tracked chain; DC slot untouched here
-  unsigned ow[32];
+  q4[0] = make_uint4((unsigned)dc_q & 0xFFFFu, 0, 0, 0);
 #pragma unroll
-  for (int v = 0; v < 32; v++) ow[v] = 0;
-  ow[0] = qw[0] & 0xFFFFu;
-  uint4 *o4 = q4;
-#pragma unroll
-  for (int v = 0; v < 8; v++) o4[v] = make_uint4(ow[4 * v], ow[4 * v + 1], ow[4 * v + 2], ow[4 * v + 3]);
+  for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
   int16_t *o16 = c.coef + blk * 64;
   while (last != 0) {
     int t = last - 1;
@@ -799,17 +845,14 @@ __global__ void __launch_bounds__(TRELLIS_THREADS) k_trellis_ac(Geom g, const Tr
     last = e_rs[t];
   }
 }
-#undef RAWZ
-#undef QNTZ
-
 
 void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                       DcRec *rec, const RecLayout &rl, int n, cudaStream_t s)
+                       DcRec *rec, const RecLayout &rl, const uint32_t *perm, int n, cudaStream_t s)
 {
-  int mw = 0, mh = 0;
-  for (int ci = 0; ci < g.nc; ci++) { mw = max(mw, g.c[ci].wib); mh = max(mh, g.c[ci].hib); }
-  dim3 grid((mw + TRELLIS_THREADS - 1) / TRELLIS_THREADS, mh, n * g.nc);
-  k_trellis_ac<<<grid, TRELLIS_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl);
+  long long mb = 0;
+  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
+  dim3 grid((unsigned)((mb + TRELLIS_THREADS - 1) / TRELLIS_THREADS), n * g.nc);
+  k_trellis_ac<<<grid, TRELLIS_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, perm);
   LAUNCHED();
 }
 

@@ -73,8 +73,10 @@ struct DevHuff {
 };
 static_assert(sizeof(DevHuff) == 17 + 256 + 1 + 12 + 2 + 512 + 256, "DevHuff layout");
 
-// per-block record the AC trellis leaves for the DC trellis
-struct DcRec { float lambda_dc; int16_t raw_dc; int16_t pad; };
+// per real block side record: K1 writes {f = norm (jcdctmgr.c:1026-1030, before the /63),
+// raw_dc, nz = number of non-zero plain-quantized AC coefficients}; the AC trellis
+// replaces f by lambda_dc for the DC trellis.
+struct DcRec { float lambda_dc; int16_t raw_dc; uint8_t nz; uint8_t pad; };
 // where component ci's records start inside an image's record array
 struct RecLayout { long long per_image; long long comp_off[4]; };
 // which of the 8 table slots to (re)build for set i: m[i % period]
@@ -85,14 +87,15 @@ struct SlotMasks { uint32_t m[4]; int period; };
 
 // ---------------------------------------------------------------- launches (defined in kernels.cu)
 // status[img] bits: 2 = JERR_BAD_DCT_COEF / missing Huffman code, 4 = output buffer too small (host retries)
-void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, int n, cudaStream_t s);
+void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s);
+void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, int n, cudaStream_t s);
 void launch_dummy(const Geom &g, int n, cudaStream_t s);
 void launch_gather_comp(const Geom &g, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_gather_seq(const Geom &g, const ScanDesc &sd, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s);
 void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_set_stride, const SlotMasks &masks, int nsets, cudaStream_t s);
 void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                       DcRec *rec, const RecLayout &rl, int n, cudaStream_t s);
+                       DcRec *rec, const RecLayout &rl, const uint32_t *perm, int n, cudaStream_t s);
 void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                        const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int n, cudaStream_t s);
 void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int n, cudaStream_t s);
