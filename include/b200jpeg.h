@@ -177,6 +177,12 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *enc);
  * bracket the work with its own events. */
 int  b200jpeg_encoder_set_stream(b200jpeg_encoder *enc, void *cuda_stream);
 
+/* A batch is processed in chunks of images: the host->device staging of chunk
+ * k+1 and the read-back of chunk k-1 overlap the kernels of chunk k, and the
+ * intermediate HBM arenas are sized for one chunk.  0 = automatic (about 1.6 M
+ * 8x8 blocks per chunk, i.e. 8 images of 3840x2160 4:2:0). */
+int  b200jpeg_encoder_set_chunk_images(b200jpeg_encoder *enc, int images_per_chunk);
+
 /*
  * Encode a batch of `n_images` images that share one parameter set and one
  * geometry.  Replaces, per image, jpeg_start_compress (jcapistd.c:44-70) +
@@ -188,8 +194,8 @@ int  b200jpeg_encoder_set_stream(b200jpeg_encoder *enc, void *cuda_stream);
  * pixels_on_device : 0 = host memory (staged with cudaMemcpyAsync inside the
  *               call; pinned memory recommended), 1 = device pointer (HBM).
  * row_pitch   : bytes between rows;  image_stride: bytes between images.
- * The finished JPEG files stay in the encoder (device + pinned host mirror)
- * until the next encode call; read them with b200jpeg_get_output().
+ * The finished JPEG files stay in the encoder (pinned host memory) until the
+ * next encode call; read them with b200jpeg_get_output().
  */
 int  b200jpeg_encode_batch(b200jpeg_encoder *enc, const b200jpeg_params *p,
                            const void *pixels, int pixels_on_device,
@@ -214,7 +220,7 @@ unsigned long long b200jpeg_kernel_launches(const b200jpeg_encoder *enc);
 int  b200jpeg_last_stage_times(const b200jpeg_encoder *enc, const char **names, float *ms, int max);
 
 /* Debug/parity taps: copy intermediate device state of image `i` of the last
- * batch to host.  plane: 0 = quantized coefficients entering entropy coding
+ * batch to host (available for the images of the batch's LAST chunk only).  plane: 0 = quantized coefficients entering entropy coding
  * (after trellis, dummy blocks filled), 1 = raw DCT output (x8 scale),
  * 2 = plain-quantized coefficients (before trellis).  Blocks are returned in
  * the reference's layout: [height_in_blocks_padded][width_in_blocks_padded][64]

@@ -43,6 +43,10 @@ class Encoder:
         """Launch on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream)."""
         A.check(_lib.b200jpeg_encoder_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")
 
+    def set_chunk_images(self, n: int) -> None:
+        """Images per pipeline chunk (0 = automatic)."""
+        A.check(_lib.b200jpeg_encoder_set_chunk_images(self._h, n), "set_chunk_images")
+
     # -- batch API -------------------------------------------------------
     def encode_batch(self, p: Params, images: np.ndarray) -> List[bytes]:
         """images: (N, H, W, C) or (N, H, W) uint8 host array -> N JPEG files.

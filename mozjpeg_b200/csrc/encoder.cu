@@ -70,28 +70,49 @@ using namespace b200;
 
 struct b200jpeg_encoder {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;     // compute stream (caller-replaceable)
+  cudaStream_t s_in = nullptr;       // host->device staging of the pixels
+  cudaStream_t s_out = nullptr;      // device->host read-back of the entropy-coded bytes
   b200jpeg_params params;           // of the last batch
   Plan plan;
-  int n = 0;
+  int n = 0;                        // images of the last batch
+  int chunk = 0;                    // images per chunk of the last batch
+  int last_chunk_i0 = 0, last_chunk_n = 0;   // the chunk whose intermediates are still in the arenas
+  int chunk_images_override = 0;    // 0 = automatic
   bool keep_plain = false;
-  // device arenas
-  DevBuf d_src, d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_scan, d_tabs_trellis, d_tabs_fixed, d_rec, d_bt, d_perm;
-  DevBuf d_blk_bits, d_blk_aux, d_blk_run, d_total_bits, d_status, d_out_pos, d_scan_size, d_bitbuf, d_out, d_qt, d_tc;
+  // device arenas sized for ONE chunk
+  DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm;
+  DevBuf d_blk_bits, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
+  // device buffers sized for the WHOLE batch
+  DevBuf d_src, d_tabs_scan, d_tabs_fixed, d_status, d_out_pos, d_scan_size, d_out, d_qt, d_tc;
   size_t bitbuf_words_per_image = 0, out_cap_per_image = 0;
   double cap_factor = 0.25;
   // pinned host mirrors
-  PinBuf h_qt, h_tc, h_fixed, h_status, h_out_pos, h_scan_size, h_tabs, h_out, h_stage;
-  // results of the last batch
-  std::vector<std::vector<uint8_t>> files;
+  PinBuf h_qt, h_tc, h_fixed, h_status, h_out_pos, h_scan_size, h_tabs, h_stage;
+  // finished files: bump-allocated from pinned arenas, valid until the next encode call
+  std::vector<PinBuf> file_arenas; size_t arena_idx = 0, arena_off = 0;
+  std::vector<std::pair<uint8_t *, size_t>> files;
+  size_t last_file_bytes = 0;
   size_t last_scan_bytes = 0;
   unsigned long long launches_at_create = 0;
   // timing
   std::vector<cudaEvent_t> ev; std::vector<const char *> ev_names, stage_names; std::vector<float> stage_ms; std::vector<int> stage_calls;
+  std::vector<cudaEvent_t> ev_in, ev_done;      // per chunk: pixels staged / pipeline + metadata read-back queued
   bool own_stream = true;
   // streaming shim state
   int st_state = 0, st_next_row = 0;
   b200jpeg_params st_params;
+};
+
+// One chunk of a batch: images [i0, i0+n) and where their results go.
+struct ChunkIO {
+  int i0, n;
+  const uint8_t *src;               // first pixel of image i0 (device)
+  uint8_t *out;                     // [n][out_cap_per_image]
+  unsigned long long *out_pos;      // [n]
+  uint32_t *status;                 // [n]
+  uint32_t *scan_size;              // [nscans][n]
+  b200::DevHuff *tabs_scan;         // [n][nscans][8]
 };
 
 namespace b200 {
@@ -236,15 +257,15 @@ static uint32_t scan_slot_mask(const Plan &pl, const ScanDesc &sd)
   return m;
 }
 
-// The device pipeline for one batch.  src_dev: pixels already in HBM.
-static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
+// Buffers and constants of one batch of n_total images processed in chunks of `chunk`.
+static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_pixels, size_t src_bytes)
 {
-  Plan &pl = e->plan; const b200jpeg_params *p = &e->params; const int n = e->n; cudaStream_t s = e->stream;
+  Plan &pl = e->plan; const b200jpeg_params *p = &e->params; cudaStream_t s = e->stream;
   Geom &g = pl.g;
   const int nscans = (int)pl.scans.size();
   if (p->restart_interval || p->restart_in_rows) { set_error("restart intervals are not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
-
   int rc;
+  const int n = chunk;
   for (int ci = 0; ci < g.nc; ci++) {
     if ((rc = e->d_coef[ci].reserve(pl.coef_bytes[ci] * n))) return rc;
     if ((rc = e->d_raw[ci].reserve(pl.coef_bytes[ci] * n))) return rc;
@@ -254,24 +275,26 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
   const size_t hist_bytes = (size_t)n * HIST_SLOTS * HIST_BINS * 4;
   if ((rc = e->d_hist.reserve(hist_bytes * g.nc))) return rc;
   const size_t tabset = sizeof(DevHuff) * HIST_SLOTS;
-  if ((rc = e->d_tabs_scan.reserve(tabset * nscans * n))) return rc;
   if ((rc = e->d_tabs_trellis.reserve(tabset * 4 * n))) return rc;
-  if ((rc = e->d_tabs_fixed.reserve(tabset))) return rc;
   if ((rc = e->d_rec.reserve((size_t)n * pl.sum_real_blocks * sizeof(DcRec)))) return rc;
   if ((rc = e->d_bt.reserve((size_t)n * pl.sum_real_blocks * 8))) return rc;
   if ((rc = e->d_perm.reserve((size_t)n * pl.sum_real_blocks * 4))) return rc;
   if ((rc = e->d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
   if (pl.progressive) { if ((rc = e->d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = e->d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
   if ((rc = e->d_total_bits.reserve((size_t)n * 8))) return rc;
-  if ((rc = e->d_status.reserve((size_t)n * 4))) return rc;
-  if ((rc = e->d_out_pos.reserve((size_t)n * 8))) return rc;
-  if ((rc = e->d_scan_size.reserve((size_t)n * nscans * 4))) return rc;
   long long total_blocks = 0; for (int ci = 0; ci < g.nc; ci++) total_blocks += g.c[ci].blocks_per_image;
   size_t cap = (size_t)((double)total_blocks * 64 * e->cap_factor) + 65536;
   cap = (cap + 255) & ~(size_t)255;
   e->bitbuf_words_per_image = cap / 4; e->out_cap_per_image = cap + cap / 64 + 4096;
   if ((rc = e->d_bitbuf.reserve(cap * n))) return rc;
-  if ((rc = e->d_out.reserve(e->out_cap_per_image * n))) return rc;
+  // whole batch
+  if (host_pixels) { if ((rc = e->d_src.reserve(src_bytes))) return rc; }
+  if ((rc = e->d_tabs_scan.reserve(tabset * nscans * n_total))) return rc;
+  if ((rc = e->d_tabs_fixed.reserve(tabset))) return rc;
+  if ((rc = e->d_status.reserve((size_t)n_total * 4))) return rc;
+  if ((rc = e->d_out_pos.reserve((size_t)n_total * 8))) return rc;
+  if ((rc = e->d_scan_size.reserve((size_t)n_total * nscans * 4))) return rc;
+  if ((rc = e->d_out.reserve(e->out_cap_per_image * n_total))) return rc;
   if ((rc = e->d_qt.reserve(sizeof(QuantTables)))) return rc;
   if ((rc = e->d_tc.reserve(sizeof(TrellisConsts)))) return rc;
   if ((rc = e->h_qt.reserve(sizeof(QuantTables)))) return rc;
@@ -289,9 +312,20 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
   CU(cudaMemcpyAsync(e->d_qt.p, e->h_qt.p, sizeof(QuantTables), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(e->d_tc.p, e->h_tc.p, sizeof(TrellisConsts), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(e->d_tabs_fixed.p, e->h_fixed.p, tabset, cudaMemcpyHostToDevice, s));
-  CU(cudaMemsetAsync(e->d_status.p, 0, (size_t)n * 4, s));
-  CU(cudaMemsetAsync(e->d_out_pos.p, 0, (size_t)n * 8, s));
-  uint32_t *status = e->d_status.as<uint32_t>();
+  return B200JPEG_OK;
+}
+
+// The device pipeline for one chunk (pixels already in HBM): the pass plan of
+// jcmaster.c with every pass one launch over all images of the chunk.
+static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
+{
+  Plan &pl = e->plan; const b200jpeg_params *p = &e->params; const int n = io.n; cudaStream_t s = e->stream;
+  Geom &g = pl.g;
+  const int nscans = (int)pl.scans.size();
+  const size_t hist_bytes = (size_t)n * HIST_SLOTS * HIST_BINS * 4;
+  const size_t tabset = sizeof(DevHuff) * HIST_SLOTS;
+  const uint8_t *src_dev = io.src;
+  uint32_t *status = io.status;
 
   // ---- pass 0 data path: colour/downsample/FDCT/quantize (compress_first_pass) ----
   RecLayout rl; memset(&rl, 0, sizeof rl);
@@ -355,7 +389,7 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
     uint32_t *aux = e->d_blk_aux.as<uint32_t>(), *run_e = e->d_blk_run.as<uint32_t>();
     if (pl.progressive && sd.Ss != 0) { tm.mark("eobrun_runs"); launch_prog_prepare(g, sd, aux, run_e, n, s); }
     if (pl.optimize) {
-      DevHuff *tset = e->d_tabs_scan.as<DevHuff>() + (size_t)si * HIST_SLOTS;             // [img][scan][8]
+      DevHuff *tset = io.tabs_scan + (size_t)si * HIST_SLOTS;                              // [img][scan][8]
       tstride = tabset * nscans;
       if (!dc_refine) {                                                                    // jcmaster.c:650-662
         tm.mark("scan_stats");
@@ -377,11 +411,12 @@ static int run_pipeline(b200jpeg_encoder *e, const uint8_t *src_dev, Timer &tm)
     launch_encode(g, sd, tabs, tstride, pl.progressive, e->d_blk_bits.as<uint32_t>(), aux, run_e, e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, status, n, s);
     tm.mark("stuff");
     launch_stuff(e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, e->d_total_bits.as<unsigned long long>(),
-                 e->d_out.as<uint8_t>(), e->out_cap_per_image, e->out_cap_per_image, e->d_out_pos.as<unsigned long long>(),
-                 e->d_scan_size.as<uint32_t>() + (size_t)si * n, status, n, s);
+                 io.out, e->out_cap_per_image, e->out_cap_per_image, io.out_pos,
+                 io.scan_size + (size_t)si * n, status, n, s);
   }
   tm.mark("end");
   CU(cudaGetLastError());
+  e->last_chunk_i0 = io.i0; e->last_chunk_n = io.n;
   return B200JPEG_OK;
 }
 
@@ -518,61 +553,84 @@ static void write_scan_header(const b200jpeg_params *p, const ScanDesc &sd, TblS
   o.b(sd.Ss); o.b(sd.Se); o.b((sd.Ah << 4) + sd.Al);
 }
 
-static int collect_outputs(b200jpeg_encoder *e)
+// ---- finished files live in pinned arenas (bump allocation; steady state = one arena, no allocation) ----
+static void arena_reset(b200jpeg_encoder *e, size_t expect)
 {
-  Plan &pl = e->plan; const b200jpeg_params *p = &e->params; const int n = e->n; cudaStream_t s = e->stream;
+  size_t have = 0; for (PinBuf &b : e->file_arenas) have += b.cap;
+  if (e->file_arenas.size() != 1 || have < expect) {
+    size_t want = std::max(have, expect);
+    for (PinBuf &b : e->file_arenas) b.release();
+    e->file_arenas.clear();
+    e->file_arenas.emplace_back();
+    if (e->file_arenas[0].reserve(want)) e->file_arenas.clear();
+  }
+  e->arena_idx = 0; e->arena_off = 0;
+}
+static uint8_t *arena_alloc(b200jpeg_encoder *e, size_t size)
+{
+  size = (size + 63) & ~(size_t)63;
+  while (e->arena_idx < e->file_arenas.size()) {
+    PinBuf &b = e->file_arenas[e->arena_idx];
+    if (e->arena_off + size <= b.cap) { uint8_t *r = b.as<uint8_t>() + e->arena_off; e->arena_off += size; return r; }
+    e->arena_idx++; e->arena_off = 0;
+  }
+  e->file_arenas.emplace_back();
+  if (e->file_arenas.back().reserve(std::max(size, (size_t)64 << 20))) { e->file_arenas.pop_back(); return nullptr; }
+  e->arena_idx = e->file_arenas.size() - 1; e->arena_off = size;
+  return e->file_arenas.back().as<uint8_t>();
+}
+
+// Queue the read-back of chunk k's metadata (status, sizes, DHT payloads) behind its pipeline.
+static int queue_meta(b200jpeg_encoder *e, const ChunkIO &io, int k)
+{
+  Plan &pl = e->plan; cudaStream_t s = e->stream;
   const int nscans = (int)pl.scans.size();
-  int rc;
-  if ((rc = e->h_status.reserve((size_t)n * 4))) return rc;
-  if ((rc = e->h_out_pos.reserve((size_t)n * 8))) return rc;
-  if ((rc = e->h_scan_size.reserve((size_t)n * nscans * 4))) return rc;
-  CU(cudaMemcpyAsync(e->h_status.p, e->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(e->h_out_pos.p, e->d_out_pos.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(e->h_scan_size.p, e->d_scan_size.p, (size_t)n * nscans * 4, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  const uint32_t *st = e->h_status.as<uint32_t>();
+  CU(cudaMemcpyAsync(e->h_status.as<uint32_t>() + io.i0, io.status, (size_t)io.n * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(e->h_out_pos.as<unsigned long long>() + io.i0, io.out_pos, (size_t)io.n * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(e->h_scan_size.as<uint32_t>() + (size_t)io.i0 * nscans, io.scan_size, (size_t)io.n * nscans * 4, cudaMemcpyDeviceToHost, s));
+  if (pl.optimize) {
+    size_t ntab = (size_t)io.n * nscans * HIST_SLOTS;
+    CU(cudaMemcpy2DAsync(e->h_tabs.as<HostHuff>() + (size_t)io.i0 * nscans * HIST_SLOTS, sizeof(HostHuff), io.tabs_scan, sizeof(DevHuff), sizeof(HostHuff), ntab, cudaMemcpyDeviceToHost, s));
+  } else if (k == 0) {
+    CU(cudaMemcpy2DAsync(e->h_tabs.p, sizeof(HostHuff), e->d_tabs_fixed.p, sizeof(DevHuff), sizeof(HostHuff), HIST_SLOTS, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaEventRecord(e->ev_done[k], s));
+  return B200JPEG_OK;
+}
+
+// Chunk k's pipeline has finished: lay out its files in pinned memory, write the
+// markers (jcmarker.c) on the host and queue the copies of the entropy-coded
+// bytes straight into place.  Returns 1 if an image overflowed its output buffer.
+static int finish_chunk(b200jpeg_encoder *e, const ChunkIO &io, int k)
+{
+  Plan &pl = e->plan; const b200jpeg_params *p = &e->params;
+  const int nscans = (int)pl.scans.size();
+  CU(cudaEventSynchronize(e->ev_done[k]));
+  const uint32_t *st = e->h_status.as<uint32_t>() + io.i0;
   bool overflow = false;
-  for (int i = 0; i < n; i++) {
-    if (st[i] & 2u) { set_error("DCT coefficient out of range (image %d)", i); return B200JPEG_ERR_BAD_DCT_COEF; }
+  for (int i = 0; i < io.n; i++) {
+    if (st[i] & 2u) { set_error("DCT coefficient out of range (image %d)", io.i0 + i); return B200JPEG_ERR_BAD_DCT_COEF; }
     if (st[i] & 4u) overflow = true;
   }
-  if (overflow) return 1;          // caller grows the buffers and reruns
-  // Huffman tables of every scan (DHT payloads only: first 288 bytes of each DevHuff)
-  const size_t tabset = sizeof(DevHuff) * HIST_SLOTS;
-  size_t ntab = pl.optimize ? (size_t)n * nscans * HIST_SLOTS : HIST_SLOTS;
-  if ((rc = e->h_tabs.reserve(ntab * sizeof(HostHuff)))) return rc;
-  if (pl.optimize)
-    CU(cudaMemcpy2DAsync(e->h_tabs.p, sizeof(HostHuff), e->d_tabs_scan.p, sizeof(DevHuff), sizeof(HostHuff), ntab, cudaMemcpyDeviceToHost, s));
-  else
-    CU(cudaMemcpy2DAsync(e->h_tabs.p, sizeof(HostHuff), e->d_tabs_fixed.p, sizeof(DevHuff), sizeof(HostHuff), ntab, cudaMemcpyDeviceToHost, s));
-  (void)tabset;
-  const unsigned long long *pos = e->h_out_pos.as<unsigned long long>();
-  size_t total = 0; std::vector<size_t> off(n);
-  for (int i = 0; i < n; i++) { off[i] = total; total += (size_t)pos[i]; }
-  e->last_scan_bytes = total;
-  if ((rc = e->h_out.reserve(total + 16))) return rc;
-  for (int i = 0; i < n; i++)
-    if (pos[i]) CU(cudaMemcpyAsync(e->h_out.as<uint8_t>() + off[i], e->d_out.as<uint8_t>() + (size_t)i * e->out_cap_per_image, (size_t)pos[i], cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  // assemble the files (write_file_header / write_frame_header / write_scan_header / EOI)
-  e->files.resize(n);
+  if (overflow) return 1;
   const HostHuff *ht = e->h_tabs.as<HostHuff>();
-  const uint32_t *ss = e->h_scan_size.as<uint32_t>();
-  for (int i = 0; i < n; i++) {
-    std::vector<uint8_t> &f = e->files[i];
-    f.clear(); f.reserve((size_t)pos[i] + 2048);
-    Bytes o{f};
+  const uint32_t *ss = e->h_scan_size.as<uint32_t>() + (size_t)io.i0 * nscans;
+  const unsigned long long *pos = e->h_out_pos.as<unsigned long long>() + io.i0;
+  std::vector<uint8_t> hdr; std::vector<size_t> hdr_end(nscans);
+  for (int i = 0; i < io.n; i++) {
+    const int gi = io.i0 + i;
+    hdr.clear();
+    Bytes o{hdr};
     write_file_header(p, o);
     TblState ts;
     const HostHuff *fixed = pl.optimize ? nullptr : ht;
     for (int t = 0; t < 4; t++) { ts.dc[t] = fixed ? &fixed[t] : nullptr; ts.ac[t] = fixed ? &fixed[4 + t] : nullptr; ts.dc_sent[t] = ts.ac_sent[t] = false; }
     int last_ri = 0;
-    const uint8_t *data = e->h_out.as<uint8_t>() + off[i];
     for (int si = 0; si < nscans; si++) {
       const ScanDesc &sd = pl.scans[si];
       if (pl.optimize) {
         uint32_t m = scan_slot_mask(pl, sd);
-        const HostHuff *set = ht + ((size_t)i * nscans + si) * HIST_SLOTS;
+        const HostHuff *set = ht + ((size_t)gi * nscans + si) * HIST_SLOTS;
         for (int t = 0; t < 4; t++) {
           if (m & (1u << t)) { ts.dc[t] = &set[t]; ts.dc_sent[t] = false; }               // jpeg_gen_optimal_table clears sent_table (jchuff.c:1105)
           if (m & (1u << (4 + t))) { ts.ac[t] = &set[4 + t]; ts.ac_sent[t] = false; }
@@ -580,13 +638,39 @@ static int collect_outputs(b200jpeg_encoder *e)
       }
       if (si == 0) write_frame_header(p, pl.progressive, o);
       write_scan_header(p, sd, ts, last_ri, 0, o);
-      size_t sz = ss[(size_t)si * n + i];
-      f.insert(f.end(), data, data + sz);
-      data += sz;
+      hdr_end[si] = hdr.size();
     }
-    o.w(0xFFD9);
+    const size_t total = hdr.size() + (size_t)pos[i] + 2;
+    uint8_t *f = arena_alloc(e, total);
+    if (!f) return B200JPEG_ERR_CUDA;
+    const uint8_t *dsrc = io.out + (size_t)i * e->out_cap_per_image;
+    size_t w = 0, hprev = 0;
+    for (int si = 0; si < nscans; si++) {
+      memcpy(f + w, hdr.data() + hprev, hdr_end[si] - hprev); w += hdr_end[si] - hprev; hprev = hdr_end[si];
+      size_t sz = ss[(size_t)si * io.n + i];
+      if (sz) CU(cudaMemcpyAsync(f + w, dsrc, sz, cudaMemcpyDeviceToHost, e->s_out));
+      dsrc += sz; w += sz;
+    }
+    f[w++] = 0xFF; f[w++] = 0xD9;
+    e->files[gi] = std::make_pair(f, w);
+    e->last_scan_bytes += (size_t)pos[i];
+    e->last_file_bytes += w;
   }
   return B200JPEG_OK;
+}
+
+static int choose_chunk(const b200jpeg_encoder *e, const Plan &pl, int n_images, bool host_pixels)
+{
+  if (e->chunk_images_override > 0) return std::min(n_images, e->chunk_images_override);
+  long long per = 0; for (int ci = 0; ci < pl.g.nc; ci++) per += pl.g.c[ci].blocks_per_image;
+  // pixels already in HBM: nothing to overlap, so chunks only bound the arenas (64 images of 4K 4:2:0)
+  if (!host_pixels) return (int)std::min<long long>(n_images, std::max(1LL, 12800000LL / std::max(1LL, per)));
+  // about 1.6 M blocks (8 images of 3840x2160 4:2:0) per chunk: large enough to fill
+  // the 148 SMs several waves deep, small enough that staging the next chunk's
+  // pixels overlaps this chunk's kernels.
+  static const long long target = getenv("B200JPEG_CHUNK_BLOCKS") ? atoll(getenv("B200JPEG_CHUNK_BLOCKS")) : 1600000LL;
+  long long c = std::max(1LL, target / std::max(1LL, per));
+  return (int)std::min<long long>(n_images, c);
 }
 
 static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const void *pixels, int on_device,
@@ -600,37 +684,85 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   CU(cudaSetDevice(e->device));
   e->params = *p; e->n = n_images;
   if ((rc = build_plan(p, row_pitch, image_stride, e->plan))) return rc;
-  Timer tm{e};
-  const uint8_t *src_dev;
-  tm.mark("h2d");
-  if (on_device) src_dev = static_cast<const uint8_t *>(pixels);
-  else {
-    size_t bytes = image_stride * (size_t)(n_images - 1) + row_pitch * (size_t)(p->image_height - 1) + (size_t)p->image_width * p->input_components;
-    if ((rc = e->d_src.reserve(bytes))) return rc;
-    CU(cudaMemcpyAsync(e->d_src.p, pixels, bytes, cudaMemcpyHostToDevice, e->stream));
-    src_dev = e->d_src.as<uint8_t>();
+  Plan &pl = e->plan;
+  const int nscans = (int)pl.scans.size();
+  const int C = choose_chunk(e, pl, n_images, !on_device);
+  const int nchunks = (n_images + C - 1) / C;
+  e->chunk = C;
+  const size_t image_bytes = row_pitch * (size_t)(p->image_height - 1) + (size_t)p->image_width * p->input_components;
+  const size_t src_bytes = image_stride * (size_t)(n_images - 1) + image_bytes;
+  while ((int)e->ev_in.size() < nchunks) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->ev_in.push_back(ev); }
+  while ((int)e->ev_done.size() < nchunks) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->ev_done.push_back(ev); }
+  if (!device_only) {
+    if ((rc = e->h_status.reserve((size_t)n_images * 4))) return rc;
+    if ((rc = e->h_out_pos.reserve((size_t)n_images * 8))) return rc;
+    if ((rc = e->h_scan_size.reserve((size_t)n_images * nscans * 4))) return rc;
+    if ((rc = e->h_tabs.reserve((pl.optimize ? (size_t)n_images * nscans : 1) * HIST_SLOTS * sizeof(HostHuff)))) return rc;
   }
+  Timer tm{e};
   for (int attempt = 0; attempt < 6; attempt++) {
-    tm.idx = 1;
-    if ((rc = run_pipeline(e, src_dev, tm))) return rc;
+    tm.idx = 0;
+    if ((rc = prepare_batch(e, n_images, C, !on_device, src_bytes))) return rc;
+    CU(cudaMemsetAsync(e->d_status.p, 0, (size_t)n_images * 4, e->stream));
+    CU(cudaMemsetAsync(e->d_out_pos.p, 0, (size_t)n_images * 8, e->stream));
+    // stage every chunk's pixels up front on the copy stream; chunk k's kernels wait only for chunk k
+    const uint8_t *src_base = static_cast<const uint8_t *>(pixels);
+    if (!on_device) {
+      for (int k = 0; k < nchunks; k++) {
+        const int i0 = k * C, nk = std::min(C, n_images - i0);
+        const size_t off = (size_t)i0 * image_stride, bytes = image_stride * (size_t)(nk - 1) + image_bytes;
+        CU(cudaMemcpyAsync(e->d_src.as<uint8_t>() + off, static_cast<const uint8_t *>(pixels) + off, bytes, cudaMemcpyHostToDevice, e->s_in));
+        CU(cudaEventRecord(e->ev_in[k], e->s_in));
+      }
+      src_base = e->d_src.as<uint8_t>();
+    }
+    if (!device_only) {
+      e->files.assign(n_images, std::make_pair((uint8_t *)nullptr, (size_t)0));
+      size_t expect = e->last_file_bytes ? (size_t)((double)e->last_file_bytes / std::max(1, (int)e->files.size()) * 1.3 * n_images)
+                                         : (size_t)n_images * ((size_t)p->image_width * p->image_height * p->num_components / 6 + 65536);
+      e->last_scan_bytes = 0; e->last_file_bytes = 0;
+      arena_reset(e, expect + (size_t)n_images * 4096);
+    }
+    rc = B200JPEG_OK;
+    ChunkIO prev{}; bool have_prev = false;
+    for (int k = 0; k < nchunks && rc == B200JPEG_OK; k++) {
+      ChunkIO io;
+      io.i0 = k * C; io.n = std::min(C, n_images - io.i0);
+      io.src = src_base + (size_t)io.i0 * image_stride;
+      io.out = e->d_out.as<uint8_t>() + (size_t)io.i0 * e->out_cap_per_image;
+      io.out_pos = e->d_out_pos.as<unsigned long long>() + io.i0;
+      io.status = e->d_status.as<uint32_t>() + io.i0;
+      io.scan_size = e->d_scan_size.as<uint32_t>() + (size_t)io.i0 * nscans;
+      io.tabs_scan = e->d_tabs_scan.as<DevHuff>() + (size_t)io.i0 * nscans * HIST_SLOTS;
+      if (!on_device) { tm.mark("h2d_wait"); CU(cudaStreamWaitEvent(e->stream, e->ev_in[k], 0)); }
+      if ((rc = run_pipeline(e, io, tm))) break;
+      if (!device_only) {
+        if ((rc = queue_meta(e, io, k))) break;
+        if (have_prev) rc = finish_chunk(e, prev, k - 1);
+        prev = io; have_prev = true;
+      }
+    }
+    if (rc == B200JPEG_OK && !device_only && have_prev) rc = finish_chunk(e, prev, nchunks - 1);
+    if (rc < 0) { cudaStreamSynchronize(e->stream); cudaStreamSynchronize(e->s_in); cudaStreamSynchronize(e->s_out); return rc; }
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->s_in));
+    CU(cudaStreamSynchronize(e->s_out));
     if (device_only) {
-      CU(cudaStreamSynchronize(e->stream));
       // the overflow flag still matters for a meaningful timing run
       if ((rc = e->h_status.reserve((size_t)n_images * 4))) return rc;
       CU(cudaMemcpy(e->h_status.p, e->d_status.p, (size_t)n_images * 4, cudaMemcpyDeviceToHost));
       bool ovf = false; for (int i = 0; i < n_images; i++) if (e->h_status.as<uint32_t>()[i] & 4u) ovf = true;
-      if (!ovf) { rc = B200JPEG_OK; break; }
-      rc = 1;
-    } else rc = collect_outputs(e);
+      rc = ovf ? 1 : B200JPEG_OK;
+    }
     if (rc != 1) break;
     e->cap_factor *= 4.0;          // entropy-coded data did not fit: grow and rerun
   }
   if (rc == 1) { set_error("output does not fit even after growing buffers"); return B200JPEG_ERR_BUFFER; }
   if (rc) return rc;
-  // stage timings
-  // per-stage device times (CUDA events on the encoder's stream), summed by stage name
+  // per-stage device times (CUDA events on the encoder's stream), summed by stage name over the chunks
   e->stage_names.clear(); e->stage_ms.clear(); e->stage_calls.clear();
   for (size_t i = 0; i + 1 < tm.idx; i++) {
+    if (!strcmp(e->ev_names[i], "end")) continue;
     float ms = 0.f; cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]);
     size_t k = 0;
     for (; k < e->stage_names.size(); k++) if (!strcmp(e->stage_names[k], e->ev_names[i])) break;
@@ -656,10 +788,14 @@ int b200jpeg_encoder_create(b200jpeg_encoder **enc, int device)
   b200jpeg_encoder *o = new b200jpeg_encoder();
   o->device = device;
   cudaError_t e2 = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking);
+  if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&o->s_in, cudaStreamNonBlocking);
+  if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&o->s_out, cudaStreamNonBlocking);
   if (e2 != cudaSuccess) { set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e2)); delete o; return B200JPEG_ERR_CUDA; }
   o->launches_at_create = g_kernel_launches;
   const char *dbg = getenv("B200JPEG_KEEP_PLAIN");
   o->keep_plain = dbg && dbg[0] == '1';
+  const char *ch = getenv("B200JPEG_CHUNK_IMAGES");
+  if (ch) o->chunk_images_override = atoi(ch);
   *enc = o;
   return B200JPEG_OK;
 }
@@ -669,15 +805,29 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
+  if (e->s_in) cudaStreamSynchronize(e->s_in);
+  if (e->s_out) cudaStreamSynchronize(e->s_out);
   DevBuf *db[] = {&e->d_src, &e->d_hist, &e->d_tabs_scan, &e->d_tabs_trellis, &e->d_tabs_fixed, &e->d_rec, &e->d_bt, &e->d_perm, &e->d_blk_bits, &e->d_blk_aux, &e->d_blk_run,
                   &e->d_total_bits, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_bitbuf, &e->d_out, &e->d_qt, &e->d_tc};
   for (DevBuf *b : db) b->release();
   for (int i = 0; i < 4; i++) { e->d_coef[i].release(); e->d_raw[i].release(); e->d_plain[i].release(); }
-  PinBuf *pb[] = {&e->h_qt, &e->h_tc, &e->h_fixed, &e->h_status, &e->h_out_pos, &e->h_scan_size, &e->h_tabs, &e->h_out, &e->h_stage};
+  PinBuf *pb[] = {&e->h_qt, &e->h_tc, &e->h_fixed, &e->h_status, &e->h_out_pos, &e->h_scan_size, &e->h_tabs, &e->h_stage};
   for (PinBuf *b : pb) b->release();
+  for (PinBuf &b : e->file_arenas) b.release();
   for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->ev_in) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->ev_done) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->stream);
+  if (e->s_in) cudaStreamDestroy(e->s_in);
+  if (e->s_out) cudaStreamDestroy(e->s_out);
   delete e;
+}
+
+int b200jpeg_encoder_set_chunk_images(b200jpeg_encoder *e, int images_per_chunk)
+{
+  if (!e || images_per_chunk < 0) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  e->chunk_images_override = images_per_chunk;
+  return B200JPEG_OK;
 }
 
 int b200jpeg_encoder_set_stream(b200jpeg_encoder *e, void *cuda_stream)
@@ -705,8 +855,9 @@ int b200jpeg_encode_batch_device_only(b200jpeg_encoder *enc, const b200jpeg_para
 int b200jpeg_get_output(b200jpeg_encoder *e, int i, const uint8_t **data, size_t *size)
 {
   if (!e || i < 0 || i >= (int)e->files.size()) { set_error("no such output"); return B200JPEG_ERR_PARAM; }
-  if (data) *data = e->files[i].data();
-  if (size) *size = e->files[i].size();
+  if (!e->files[i].first) { set_error("no such output"); return B200JPEG_ERR_STATE; }
+  if (data) *data = e->files[i].first;
+  if (size) *size = e->files[i].second;
   return B200JPEG_OK;
 }
 size_t b200jpeg_last_scan_bytes(const b200jpeg_encoder *e) { return e ? e->last_scan_bytes : 0; }
@@ -723,6 +874,9 @@ long b200jpeg_debug_get_coefs(b200jpeg_encoder *e, int image, int component, int
                               int *width_in_blocks, int *height_in_blocks)
 {
   if (!e || image < 0 || image >= e->n || component < 0 || component >= e->plan.g.nc) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  // intermediates are kept for the LAST chunk of the batch only (the arenas are per chunk)
+  if (image < e->last_chunk_i0 || image >= e->last_chunk_i0 + e->last_chunk_n) { set_error("image %d is not in the last chunk [%d,%d) of the batch", image, e->last_chunk_i0, e->last_chunk_i0 + e->last_chunk_n); return B200JPEG_ERR_STATE; }
+  image -= e->last_chunk_i0;
   const CompGeom &c = e->plan.g.c[component];
   if (width_in_blocks) *width_in_blocks = c.wpad;
   if (height_in_blocks) *height_in_blocks = c.hpad;
@@ -748,7 +902,8 @@ int b200jpeg_debug_get_huff(b200jpeg_encoder *e, int image, int scan, int is_ac,
   if (scan < 0) {          // scan = -1-ci : the trellis-phase tables of component ci
     int ci = -1 - scan;
     if (ci >= e->plan.g.nc) { set_error("bad component"); return B200JPEG_ERR_PARAM; }
-    CU(cudaMemcpy(&h, e->d_tabs_trellis.as<DevHuff>() + ((size_t)image * e->plan.g.nc + ci) * HIST_SLOTS + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));
+    if (image < e->last_chunk_i0 || image >= e->last_chunk_i0 + e->last_chunk_n) { set_error("image %d is not in the last chunk of the batch", image); return B200JPEG_ERR_STATE; }
+    CU(cudaMemcpy(&h, e->d_tabs_trellis.as<DevHuff>() + ((size_t)(image - e->last_chunk_i0) * e->plan.g.nc + ci) * HIST_SLOTS + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));
   } else {
     if (scan >= nscans) { set_error("bad scan"); return B200JPEG_ERR_PARAM; }
     if (e->plan.optimize) CU(cudaMemcpy(&h, e->d_tabs_scan.as<DevHuff>() + ((size_t)image * nscans + scan) * HIST_SLOTS + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));

@@ -335,45 +335,65 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   }
   __syncthreads();
 
-  // ---- D: column pass + quantize; lane j owns column j; zigzag placement in the staging buffer ----
+  // ---- D: column pass + quantize; lane j owns column j; zigzag placement in the staging buffer.
+  //      With the trellis on, the same 8 lanes also produce the block's side record: the raw
+  //      coefficients go back to sW in natural order (each lane rewrites exactly the words it
+  //      read), lane r then owns ROW r and the serial fp32 sum of squares in NATURAL order
+  //      (jcdctmgr.c:1026-1029) is handed from lane to lane, 8 adds per hop. ----
   int16_t *sQ = reinterpret_cast<int16_t *>(sIO);              // [NB][64] quantized, then [NB][64] raw
   int16_t *sR = sQ + NB * 64;
+  static_assert(NB % 16 == 0, "whole warps walk the block list in step");
 #pragma unroll 1
   for (int b = tid >> 3; b < NB; b += 16) {
-    const int16_t *w = sW + b * 72 + j;
+    int16_t *w = sW + b * 72 + j;
     int d0 = w[0], d1 = w[8], d2 = w[16], d3 = w[24], d4 = w[32], d5 = w[40], d6 = w[48], d7 = w[56];
     fdct_1d<1>(d0, d1, d2, d3, d4, d5, d6, d7);
     const int ci = b < YB ? 0 : (1 + (b - YB) / CBW);
     const QuantConst *qc = qt->q[g.c[ci].qt];
     int dd[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
+    int nz = 0;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       int nat = 8 * r + j;
       int k = c_izz[nat];
-      sQ[b * 64 + k] = (int16_t)quant_one(dd[r], qc[nat], dering);
+      int16_t qv = (int16_t)quant_one(dd[r], qc[nat], dering);
+      sQ[b * 64 + k] = qv;
       sR[b * 64 + k] = (int16_t)dd[r];
+      nz += (qv != 0) && (nat != 0);
+    }
+    if (rec) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) w[8 * r] = (int16_t)dd[r];
+      __syncwarp();
+      const int4 rowv = *reinterpret_cast<const int4 *>(sW + b * 72 + 8 * j);
+      const int pw[4] = {rowv.x, rowv.y, rowv.z, rowv.w};
+      float sq[8];
+#pragma unroll
+      for (int cidx = 0; cidx < 8; cidx++) { int v = (int)(int16_t)((unsigned)pw[cidx >> 1] >> ((cidx & 1) * 16)); sq[cidx] = (float)(v * v); }
+      const int raw_dc = (int)(int16_t)((unsigned)pw[0] & 0xFFFFu);           // meaningful in lane 0
+      float norm = 0.0f;
+      const int gbase = (tid & 31) & ~7;
+#pragma unroll
+      for (int step = 0; step < 8; step++) {
+        float acc = norm;
+        if (step != 0) acc += sq[0];
+        acc += sq[1]; acc += sq[2]; acc += sq[3]; acc += sq[4]; acc += sq[5]; acc += sq[6]; acc += sq[7];
+        norm = __shfl_sync(0xffffffffu, j == step ? acc : norm, gbase + step);
+      }
+      nz += __shfl_xor_sync(0xffffffffu, nz, 1);
+      nz += __shfl_xor_sync(0xffffffffu, nz, 2);
+      nz += __shfl_xor_sync(0xffffffffu, nz, 4);
+      int row, col;
+      if (b < YB) { int byl = b / YBW; row = ty * VMAX + byl; col = tx * YBW + (b - byl * YBW); }
+      else { int cb = b - YB; int which = cb / CBW; row = ty; col = tx * CBW + (cb - which * CBW); }
+      const CompGeom &c = g.c[ci];
+      if (j == 0 && row < c.hib && col < c.wib) {
+        DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)raw_dc; rr.nz = (uint8_t)nz; rr.pad = 0;
+        rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * c.wib + col] = rr;
+      }
     }
   }
   __syncthreads();
-
-  // ---- D2: trellis side record, one thread per block: serial fp32 sum of squares in NATURAL order ----
-  if (rec) {
-    for (int b = tid; b < NB; b += 128) {
-      int ci, row, col;
-      if (b < YB) { ci = 0; int byl = b / YBW; row = ty * VMAX + byl; col = tx * YBW + (b - byl * YBW); }
-      else { int cb = b - YB; int which = cb / CBW; ci = 1 + which; row = ty; col = tx * CBW + (cb - which * CBW); }
-      const CompGeom &c = g.c[ci];
-      if (row >= c.hib || col >= c.wib) continue;
-      const int16_t *r = sR + b * 64, *q = sQ + b * 64;
-      float norm = 0.0f; int nz = 0;
-#pragma unroll 9
-      for (int i = 1; i < 64; i++) { int v = r[c_izz[i]]; norm += (float)(v * v); }
-#pragma unroll 9
-      for (int k = 1; k < 64; k++) nz += (q[k] != 0);
-      DcRec rr; rr.lambda_dc = norm; rr.raw_dc = r[0]; rr.nz = (uint8_t)nz; rr.pad = 0;
-      rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * c.wib + col] = rr;
-    }
-  }
 
   // ---- E: whole blocks out, 16 bytes per thread-store ----
   for (int i = tid; i < NB * 8; i += 128) {
