@@ -82,7 +82,7 @@ struct b200jpeg_encoder {
   bool keep_plain = false;
   // device arenas sized for ONE chunk
   DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm;
-  DevBuf d_blk_bits, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
+  DevBuf d_blk_bits, d_tile_bits, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
   // device buffers sized for the WHOLE batch
   DevBuf d_src, d_tabs_scan, d_tabs_fixed, d_status, d_out_pos, d_scan_size, d_out, d_qt, d_tc;
   size_t bitbuf_words_per_image = 0, out_cap_per_image = 0;
@@ -109,7 +109,7 @@ struct ChunkIO {
   int i0, n;
   const uint8_t *src;               // first pixel of image i0 (device)
   uint8_t *out;                     // [n][out_cap_per_image]
-  unsigned long long *out_pos;      // [n]
+  unsigned long long *out_pos;      // [nscans+1][n]: start of every scan's bytes inside out[img]; row nscans = total
   uint32_t *status;                 // [n]
   uint32_t *scan_size;              // [nscans][n]
   b200::DevHuff *tabs_scan;         // [n][nscans][8]
@@ -128,6 +128,7 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
   for (int ci = 0; ci < g.nc; ci++) { g.hmax = std::max(g.hmax, p->comp_info[ci].h_samp_factor); g.vmax = std::max(g.vmax, p->comp_info[ci].v_samp_factor); }
   g.mcus_per_row = div_up(g.W, g.hmax * 8); g.mcu_rows = div_up(g.H, g.vmax * 8);
   g.row_pitch = row_pitch; g.image_stride = image_stride;
+  g.max_coef_bits = p->data_precision + 2;
   if (p->in_color_space == B200JPEG_CS_RGB && p->jpeg_color_space == B200JPEG_CS_YCbCr) g.cs_mode = 0;
   else if (p->in_color_space == B200JPEG_CS_RGB && p->jpeg_color_space == B200JPEG_CS_GRAYSCALE) g.cs_mode = 1;
   else g.cs_mode = 2;
@@ -138,6 +139,7 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
     c.wib = div_up((long long)g.W * c.h, g.hmax * 8); c.hib = div_up((long long)g.H * c.v, g.vmax * 8);   // jcmaster.c:221-226
     c.wpad = g.mcus_per_row * c.h; c.hpad = g.mcu_rows * c.v;
     c.qt = ic.quant_tbl_no; c.dc_tbl = ic.dc_tbl_no; c.ac_tbl = ic.ac_tbl_no;
+    c.dc_q8 = 8 * (int)p->quant_tbl[c.qt][0];
     c.rows_avail = div_up(g.H, g.vmax) * c.v;
     c.blocks_per_image = (long long)c.wpad * c.hpad;
     pl.coef_bytes[ci] = (size_t)c.blocks_per_image * 128;
@@ -282,17 +284,19 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
   if ((rc = e->d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
   if (pl.progressive) { if ((rc = e->d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = e->d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
   if ((rc = e->d_total_bits.reserve((size_t)n * 8))) return rc;
+  if ((rc = e->d_tile_bits.reserve((size_t)n * ((pl.max_scan_blocks + 255) / 256) * 4))) return rc;
   long long total_blocks = 0; for (int ci = 0; ci < g.nc; ci++) total_blocks += g.c[ci].blocks_per_image;
   size_t cap = (size_t)((double)total_blocks * 64 * e->cap_factor) + 65536;
   cap = (cap + 255) & ~(size_t)255;
   e->bitbuf_words_per_image = cap / 4; e->out_cap_per_image = cap + cap / 64 + 4096;
   if ((rc = e->d_bitbuf.reserve(cap * n))) return rc;
+  if ((rc = e->d_ff_tile.reserve((size_t)n * stuff_tiles(e->bitbuf_words_per_image) * 4))) return rc;
   // whole batch
   if (host_pixels) { if ((rc = e->d_src.reserve(src_bytes))) return rc; }
   if ((rc = e->d_tabs_scan.reserve(tabset * nscans * n_total))) return rc;
   if ((rc = e->d_tabs_fixed.reserve(tabset))) return rc;
   if ((rc = e->d_status.reserve((size_t)n_total * 4))) return rc;
-  if ((rc = e->d_out_pos.reserve((size_t)n_total * 8))) return rc;
+  if ((rc = e->d_out_pos.reserve((size_t)n_total * (nscans + 1) * 8))) return rc;
   if ((rc = e->d_scan_size.reserve((size_t)n_total * nscans * 4))) return rc;
   if ((rc = e->d_out.reserve(e->out_cap_per_image * n_total))) return rc;
   if ((rc = e->d_qt.reserve(sizeof(QuantTables)))) return rc;
@@ -403,15 +407,14 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
       tabs = tset;
     } else { tabs = e->d_tabs_fixed.as<DevHuff>(); tstride = 0; }
     tm.mark("block_bits");
-    launch_block_bits(g, sd, tabs, tstride, pl.progressive, e->d_blk_bits.as<uint32_t>(), aux, run_e, status, n, s);
-    tm.mark("scan_offsets");
-    launch_scan_offsets(e->d_blk_bits.as<uint32_t>(), sd.nblocks, e->d_total_bits.as<unsigned long long>(), (size_t)e->bitbuf_words_per_image * 32, status, n, s);
+    launch_block_bits(g, sd, tabs, tstride, pl.progressive, e->d_blk_bits.as<uint32_t>(), e->d_tile_bits.as<uint32_t>(), aux, run_e, status, n, s);
     tm.mark("encode");
     CU(cudaMemsetAsync(e->d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
-    launch_encode(g, sd, tabs, tstride, pl.progressive, e->d_blk_bits.as<uint32_t>(), aux, run_e, e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, status, n, s);
+    launch_encode(g, sd, tabs, tstride, pl.progressive, e->d_blk_bits.as<uint32_t>(), e->d_tile_bits.as<uint32_t>(), aux, run_e,
+                  e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, e->d_total_bits.as<unsigned long long>(), status, n, s);
     tm.mark("stuff");
-    launch_stuff(e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, e->d_total_bits.as<unsigned long long>(),
-                 io.out, e->out_cap_per_image, e->out_cap_per_image, io.out_pos,
+    launch_stuff(e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, e->d_total_bits.as<unsigned long long>(), e->d_ff_tile.as<uint32_t>(),
+                 io.out, e->out_cap_per_image, e->out_cap_per_image, io.out_pos + (size_t)si * n, io.out_pos + (size_t)(si + 1) * n,
                  io.scan_size + (size_t)si * n, status, n, s);
   }
   tm.mark("end");
@@ -586,7 +589,7 @@ static int queue_meta(b200jpeg_encoder *e, const ChunkIO &io, int k)
   Plan &pl = e->plan; cudaStream_t s = e->stream;
   const int nscans = (int)pl.scans.size();
   CU(cudaMemcpyAsync(e->h_status.as<uint32_t>() + io.i0, io.status, (size_t)io.n * 4, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(e->h_out_pos.as<unsigned long long>() + io.i0, io.out_pos, (size_t)io.n * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(e->h_out_pos.as<unsigned long long>() + io.i0, io.out_pos + (size_t)nscans * io.n, (size_t)io.n * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(e->h_scan_size.as<uint32_t>() + (size_t)io.i0 * nscans, io.scan_size, (size_t)io.n * nscans * 4, cudaMemcpyDeviceToHost, s));
   if (pl.optimize) {
     size_t ntab = (size_t)io.n * nscans * HIST_SLOTS;
@@ -704,7 +707,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
     tm.idx = 0;
     if ((rc = prepare_batch(e, n_images, C, !on_device, src_bytes))) return rc;
     CU(cudaMemsetAsync(e->d_status.p, 0, (size_t)n_images * 4, e->stream));
-    CU(cudaMemsetAsync(e->d_out_pos.p, 0, (size_t)n_images * 8, e->stream));
+    CU(cudaMemsetAsync(e->d_out_pos.p, 0, (size_t)n_images * (nscans + 1) * 8, e->stream));
     // stage every chunk's pixels up front on the copy stream; chunk k's kernels wait only for chunk k
     const uint8_t *src_base = static_cast<const uint8_t *>(pixels);
     if (!on_device) {
@@ -730,7 +733,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
       io.i0 = k * C; io.n = std::min(C, n_images - io.i0);
       io.src = src_base + (size_t)io.i0 * image_stride;
       io.out = e->d_out.as<uint8_t>() + (size_t)io.i0 * e->out_cap_per_image;
-      io.out_pos = e->d_out_pos.as<unsigned long long>() + io.i0;
+      io.out_pos = e->d_out_pos.as<unsigned long long>() + (size_t)io.i0 * (nscans + 1);
       io.status = e->d_status.as<uint32_t>() + io.i0;
       io.scan_size = e->d_scan_size.as<uint32_t>() + (size_t)io.i0 * nscans;
       io.tabs_scan = e->d_tabs_scan.as<DevHuff>() + (size_t)io.i0 * nscans * HIST_SLOTS;
@@ -807,7 +810,7 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
   cudaStreamSynchronize(e->stream);
   if (e->s_in) cudaStreamSynchronize(e->s_in);
   if (e->s_out) cudaStreamSynchronize(e->s_out);
-  DevBuf *db[] = {&e->d_src, &e->d_hist, &e->d_tabs_scan, &e->d_tabs_trellis, &e->d_tabs_fixed, &e->d_rec, &e->d_bt, &e->d_perm, &e->d_blk_bits, &e->d_blk_aux, &e->d_blk_run,
+  DevBuf *db[] = {&e->d_src, &e->d_hist, &e->d_tabs_scan, &e->d_tabs_trellis, &e->d_tabs_fixed, &e->d_rec, &e->d_bt, &e->d_perm, &e->d_blk_bits, &e->d_tile_bits, &e->d_ff_tile, &e->d_blk_aux, &e->d_blk_run,
                   &e->d_total_bits, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_bitbuf, &e->d_out, &e->d_qt, &e->d_tc};
   for (DevBuf *b : db) b->release();
   for (int i = 0; i < 4; i++) { e->d_coef[i].release(); e->d_raw[i].release(); e->d_plain[i].release(); }

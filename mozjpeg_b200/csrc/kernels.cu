@@ -1,6 +1,7 @@
 // kernels.cu -- sm_100a kernels of the JPEG-encode hot path (see kernels.cuh).
 // Compile with: -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
 #include "kernels.cuh"
+#include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
 
@@ -186,10 +187,10 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
     fdct_1d<1>(ws[col], ws[8 + col], ws[16 + col], ws[24 + col], ws[32 + col], ws[40 + col], ws[48 + col], ws[56 + col]);
 
   if (rec) {       // side record for the trellis: norm numerator in natural order (jcdctmgr.c:1026-1029), raw DC, #non-zero ACs
-    float norm = 0.0f; int nz = 0;
+    float norm = 0.0f; unsigned long long mask = 0;
 #pragma unroll
-    for (int i = 1; i < 64; i++) { norm += (float)(ws[i] * ws[i]); nz += (quant_one(ws[i], qt->q[c.qt][i], dering) != 0u); }
-    DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)ws[0]; rr.nz = (uint8_t)nz; rr.pad = 0;
+    for (int i = 1; i < 64; i++) { norm += (float)(ws[i] * ws[i]); if (quant_one(ws[i], qt->q[c.qt][i], dering) != 0u) mask |= 1ull << c_izz[i]; }
+    DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)ws[0]; rr.nz = (uint8_t)__popcll(mask); rr.pad = 0; rr.nzmask = mask;
     rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)by * c.wib + bx] = rr;
   }
   // quantize (jcdctmgr.c:611-682 == sign(x)*floor((|x| + d/2)/d), d = 8Q) + deringing clamp (:761-770),
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
     const int ci = b < YB ? 0 : (1 + (b - YB) / CBW);
     const QuantConst *qc = qt->q[g.c[ci].qt];
     int dd[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
-    int nz = 0;
+    unsigned mlo = 0, mhi = 0;                                 // zigzag positions of this lane's non-zero AC values
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       int nat = 8 * r + j;
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
       int16_t qv = (int16_t)quant_one(dd[r], qc[nat], dering);
       sQ[b * 64 + k] = qv;
       sR[b * 64 + k] = (int16_t)dd[r];
-      nz += (qv != 0) && (nat != 0);
+      if (qv != 0 && nat != 0) { if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
     }
     if (rec) {
 #pragma unroll
@@ -380,15 +381,16 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
         acc += sq[1]; acc += sq[2]; acc += sq[3]; acc += sq[4]; acc += sq[5]; acc += sq[6]; acc += sq[7];
         norm = __shfl_sync(0xffffffffu, j == step ? acc : norm, gbase + step);
       }
-      nz += __shfl_xor_sync(0xffffffffu, nz, 1);
-      nz += __shfl_xor_sync(0xffffffffu, nz, 2);
-      nz += __shfl_xor_sync(0xffffffffu, nz, 4);
+      mlo |= __shfl_xor_sync(0xffffffffu, mlo, 1); mhi |= __shfl_xor_sync(0xffffffffu, mhi, 1);
+      mlo |= __shfl_xor_sync(0xffffffffu, mlo, 2); mhi |= __shfl_xor_sync(0xffffffffu, mhi, 2);
+      mlo |= __shfl_xor_sync(0xffffffffu, mlo, 4); mhi |= __shfl_xor_sync(0xffffffffu, mhi, 4);
       int row, col;
       if (b < YB) { int byl = b / YBW; row = ty * VMAX + byl; col = tx * YBW + (b - byl * YBW); }
       else { int cb = b - YB; int which = cb / CBW; row = ty; col = tx * CBW + (cb - which * CBW); }
       const CompGeom &c = g.c[ci];
       if (j == 0 && row < c.hib && col < c.wib) {
-        DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)raw_dc; rr.nz = (uint8_t)nz; rr.pad = 0;
+        DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)raw_dc; rr.nz = (uint8_t)(__popc(mlo) + __popc(mhi)); rr.pad = 0;
+        rr.nzmask = ((unsigned long long)mhi << 32) | mlo;
         rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * c.wib + col] = rr;
       }
     }
@@ -744,99 +746,130 @@ void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, ui
   LAUNCHED();
 }
 
+// Shared memory per CTA: the rate table of the CTA's (image, component)
+//   rate[k][run] = ehufsi[16*(run&15) + k+1] + (k+1) + (run>>4)*ehufsi[0xF0]   (:1163-1175)
+// as fp16 (exact: <= 74), +inf where the reference skips the combination
+// (missing code, or run >= 16 without a ZRL code) -- an infinite cost never
+// passes the strict '<'.
+// Local memory per thread (L1 resident) holds compact per-entry lists indexed by
+// the entry's rank among the block's non-zero positions, which K1 left as a bit
+// mask in the side record: position, accumulated zero distortion at / before the
+// position, accumulated cost, chosen predecessor and candidate.
+// The (predecessor, candidate) minimum of :1157-1184 is taken candidate by
+// candidate: for each candidate the first predecessor with the smallest cost,
+// then over candidates the smallest cost, ties to the earlier predecessor, then
+// to the earlier candidate -- the same pair the reference's scan order keeps.
 __global__ void __launch_bounds__(TRELLIS_THREADS, 8) k_trellis_ac(Geom g, const TrellisConsts *__restrict__ tc,
                                                                    const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
                                                                    DcRec *__restrict__ rec, RecLayout rl, const uint32_t *__restrict__ perm)
 {
   const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
   const CompGeom &c = g.c[ci];
+  __shared__ __half srate[10][64];
+  __shared__ float swz[64];
+  __shared__ int sq8[64];
   __shared__ uint8_t acsi[256];
   const long long nblk = (long long)c.wib * c.hib;
   if ((long long)blockIdx.x * blockDim.x >= nblk) return;
+  const int tid = threadIdx.x;
   {
     const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + (4 + c.ac_tbl);
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) acsi[i] = ac->size[i];
+    for (int i = tid; i < 256; i += TRELLIS_THREADS) acsi[i] = ac->size[i];
+    if (tid < 64) { swz[tid] = tc->w_zz[c.qt][tid]; sq8[tid] = tc->q8_zz[c.qt][tid]; }
   }
   __syncthreads();
-  const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int e = tid; e < 640; e += TRELLIS_THREADS) {
+    const int k = e >> 6, run = e & 63;
+    const int zrl = acsi[0xF0], cb = acsi[16 * (run & 15) + k + 1];
+    const bool skip = cb == 0 || ((run >> 4) && zrl == 0) || run == 63;
+    srate[k][run] = skip ? __ushort_as_half((unsigned short)0x7C00) : __int2half_rn(cb + (k + 1) + (run >> 4) * zrl);
+  }
+  __syncthreads();
+  const long long tix = (long long)blockIdx.x * blockDim.x + tid;
   if (tix >= nblk) return;
   const size_t rbase = (size_t)img * rl.per_image + rl.comp_off[ci];
   const unsigned lin = perm[rbase + tix];
   const int by = lin / c.wib, bx = lin - by * c.wib;
   const size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
-  const uint4 *r4 = reinterpret_cast<const uint4 *>(c.raw + blk * 64);
-  uint4 *q4 = reinterpret_cast<uint4 *>(c.coef + blk * 64);
+  const int16_t *raw16 = c.raw + blk * 64;
+  int16_t *o16 = c.coef + blk * 64;
   // lambda from the block's norm (K1 left the natural-order sum of squares in rec.f)   :1026-1035
-  float lambda;
+  float lambda; unsigned long long nzmask;
   {
     DcRec rr = rec[rbase + lin];
     float norm = (float)((double)rr.lambda_dc / 63.0);
     if (tc->use_norm) lambda = (float)(tc->p1 / (tc->p2 + (double)norm));
     else lambda = tc->lambda_const;
-    rec[rbase + lin].lambda_dc = lambda * tc->w_zz[c.qt][0];
+    rec[rbase + lin].lambda_dc = lambda * swz[0];
+    nzmask = rr.nzmask;
   }
-  const float *wz = tc->w_zz[c.qt];
-  const int *q8 = tc->q8_zz[c.qt];
-
-  // phase 1: zero-distortion prefix (zigzag order, serial fp32) + compact list of non-zero positions
-  float e_azd_at[64], e_azd_before[64], e_acc[64];
+  // compact lists, indexed by rank among the non-zero positions
   uint8_t e_pos[64], e_rs[64], e_k[64];
-  short e_qv[64], e_x[64];
-  int m = 0;
+  unsigned short e_qs[64];                         // plain-quantized magnitude (clamped) | sign of the raw value << 15
+  float e_at[64], e_before[64], e_acc[64];
+  // phase 1: accumulated zero distortion (zigzag order, serial fp32)   :1134
   float azd = 0.0f;
-  const int maxq = (1 << tc->max_coef_bits) - 1;
-  int dc_q = 0;
-#pragma unroll 1
-  for (int v = 0; v < 8; v++) {
-    uint4 a = r4[v], b = q4[v];
-    unsigned aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  int m = 0;
+  {
+    const uint4 *r4 = reinterpret_cast<const uint4 *>(raw16);
+    const unsigned mlo = (unsigned)nzmask, mhi = (unsigned)(nzmask >> 32);
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      int i = 8 * v + jj;
-      int rawv = (int)(int16_t)((aw[jj >> 1] >> ((jj & 1) * 16)) & 0xFFFF);
-      int qntv = (int)(int16_t)((bw[jj >> 1] >> ((jj & 1) * 16)) & 0xFFFF);
-      if (i == 0) { dc_q = qntv; continue; }
-      int x = abs(rawv);
-      float before = azd;
-      azd = (float)(x * x) * lambda * wz[i] + azd;                               // :1134
-      int qv = abs(qntv);
-      if (qv != 0) {
-        e_pos[m] = (uint8_t)i; e_x[m] = (short)rawv; e_qv[m] = (short)min(qv, maxq); e_azd_at[m] = azd; e_azd_before[m] = before; m++;
+    for (int v = 0; v < 8; v++) {
+      const uint4 a = r4[v];
+      const unsigned aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++) {
+        const int i = 8 * v + jj;
+        if (i == 0) continue;
+        const int rawv = (int)(int16_t)((aw[jj >> 1] >> ((jj & 1) * 16)) & 0xFFFF);
+        const int x = abs(rawv);
+        const float before = azd;
+        azd = (float)(x * x) * lambda * swz[i] + azd;
+        if ((i < 32 ? mlo >> i : mhi >> (i - 32)) & 1u) { e_pos[m] = (uint8_t)i; e_at[m] = azd; e_before[m] = before; e_qs[m] = (unsigned short)(rawv & 0xFFFF); m++; }
       }
     }
   }
   const float azd63 = azd;
-  const int zrl_bits = acsi[0xF0];
+  const int maxq = (1 << tc->max_coef_bits) - 1;
 
-  // phase 2: best (predecessor, candidate) per listed position, strict '<' in (predecessor, candidate) order  :1157-1184
+  // phase 2   :1121-1185.  The entry's plain-quantized value comes from global memory (L2 resident: K1 just wrote it);
+  // the next entry's value is requested one iteration ahead.
+  int nqnt = 0;
+  if (m > 0) nqnt = o16[e_pos[0]];
+#pragma unroll 1
   for (int t = 0; t < m; t++) {
-    int i = e_pos[t];
-    int x = abs((int)e_x[t]);
-    int q = q8[i], qv = e_qv[t];
-    int nc = nbits_of(qv);
-    float wl = wz[i];
+    const int i = e_pos[t];
+    const int rawv = (int)(short)e_qs[t], qntv = nqnt;
+    if (t + 1 < m) nqnt = o16[e_pos[t + 1]];
+    const int x = abs(rawv);
+    const int q = sq8[i];
+    const int qv = min(abs(qntv), maxq);
+    e_qs[t] = (unsigned short)(qv | ((rawv >> 31) & 0x8000));
+    const int nc = nbits_of(qv);
+    const float wl = swz[i];
+    const float Ai1 = e_before[t];
     float best = 1e38f; int best_s = 0, best_k = -1;
-    float before = e_azd_before[t];
-    float cand_dist[16];
+#pragma unroll 1
     for (int k = 0; k < nc; k++) {
-      int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
-      int delta = cand * q - x;
-      cand_dist[k] = (float)(delta * delta) * lambda * wl;                     // :1151
-    }
-    for (int s = -1; s < t; s++) {                                             // s = -1: "block start" (j = Ss-1)
-      int j = s < 0 ? 0 : e_pos[s];
-      int zero_run = i - 1 - j;
-      if ((zero_run >> 4) && zrl_bits == 0) continue;
-      int run_bits = (zero_run >> 4) * zrl_bits;
-      zero_run &= 15;
-      float tail = s < 0 ? (before - 0.0f) + 0.0f : (before - e_azd_at[s]) + e_acc[s];
-      for (int k = 0; k < nc; k++) {
-        int coef_bits = acsi[16 * zero_run + k + 1];
-        if (coef_bits == 0) continue;
-        float cost = (float)(coef_bits + (k + 1) + run_bits) + cand_dist[k];
-        cost += tail;
-        if (cost < best) { best = cost; best_s = s + 1; best_k = k; }
+      const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
+      const int delta = cand * q - x;
+      const float dist = (float)(delta * delta) * lambda * wl;                   // :1151
+      const __half *rk = &srate[k][i - 1];                                        // rk[-j] = rate for run i-1-j
+      // predecessor "block start" (j = Ss-1): run = i-1, zero tail
+      float kb = 1e38f; int ks = 0;
+      {
+        float cost = __half2float(rk[0]) + dist;
+        cost += (Ai1 - 0.0f) + 0.0f;
+        if (cost < kb) { kb = cost; ks = 0; }
       }
+#pragma unroll 2
+      for (int s2 = 0; s2 < t; s2++) {
+        const int j = e_pos[s2];
+        float cost = __half2float(rk[-j]) + dist;
+        cost += (Ai1 - e_at[s2]) + e_acc[s2];
+        if (cost < kb) { kb = cost; ks = s2 + 1; }
+      }
+      if (kb < best || (kb == best && ks < best_s)) { best = kb; best_s = ks; best_k = k; }
     }
     e_acc[t] = best; e_rs[t] = (uint8_t)best_s; e_k[t] = (uint8_t)(best_k < 0 ? 255 : best_k);
   }
@@ -844,24 +877,26 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, 8) k_trellis_ac(Geom g, const
   // phase 3: best end-of-block position (:1187-1207) and back-tracking (:1211-1222)
   int last = 0;                                  // 1-based entry index, 0 = none
   {
-    float best_cost = azd63 + (float)acsi[0];
+    const float eob = (float)acsi[0];
+    float best_cost = azd63 + eob;
     for (int t = 0; t < m; t++) {
-      float cst = e_acc[t] + azd63 - e_azd_at[t];
-      if (e_pos[t] < 63) cst += (float)acsi[0];
+      float cst = e_acc[t] + azd63 - e_at[t];
+      if (e_pos[t] < 63) cst += eob;
       if (cst < best_cost) { best_cost = cst; last = t + 1; }
     }
   }
+  const unsigned dc_q = (unsigned)(unsigned short)o16[0];
   // output: zeros except the back-tracked chain; DC slot untouched here
-  q4[0] = make_uint4((unsigned)dc_q & 0xFFFFu, 0, 0, 0);
+  uint4 *q4 = reinterpret_cast<uint4 *>(o16);
+  q4[0] = make_uint4(dc_q, 0, 0, 0);
 #pragma unroll
   for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
-  int16_t *o16 = c.coef + blk * 64;
   while (last != 0) {
-    int t = last - 1;
-    int i = e_pos[t], qv = e_qv[t], nc = nbits_of(qv), k = e_k[t];
-    int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
-    int sgn = ((int)e_x[t]) >> 31;
-    o16[i] = (int16_t)((cand ^ sgn) - sgn);
+    const int t = last - 1;
+    const int qs = e_qs[t], qv = qs & 0x7FFF, nc = nbits_of(qv), k = e_k[t];
+    const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
+    const int sgn = -(qs >> 15);
+    o16[e_pos[t]] = (int16_t)((cand ^ sgn) - sgn);
     last = e_rs[t];
   }
 }
@@ -1061,12 +1096,199 @@ __global__ void __launch_bounds__(64) k_trellis_dc_warp(Geom g, const TrellisCon
     __syncwarp();
   }
 }
+// ---------------------------------------------------------------------
+// DC trellis, latency-oriented version.  Layout as above (9 lanes per chain,
+// lane k = candidate k, 3 chains per warp) but:
+//   * the side records of the next 32 blocks are fetched by the whole warp
+//     (coalesced) while the current 32 are processed from shared memory;
+//   * everything that does not depend on the Viterbi state -- candidate values,
+//     distortions and the 9 rate terms (float)(bits + size[bits]) + dist of the
+//     step -- is computed ahead of the 9 shuffles that bring the predecessors'
+//     accumulated costs, so the state-dependent part of a step is 9 adds and a
+//     4-level first-minimum tree;
+//   * the serial back-track only chases one byte per block through shared
+//     memory; candidates are turned into coefficients by all 32 lanes afterwards.
+// Arithmetic, association order and tie-breaks are those of k_trellis_dc.
+// ---------------------------------------------------------------------
+#define DC2_WARPS 2
+struct DcDiv { unsigned mul[4]; int shift[4]; };
+// FLO: index of the most significant set bit, 0xFFFFFFFF for 0, so that
+// nbits(v) == bfind(v) + 1 (JPEG_NBITS) without the clz arithmetic.
+__device__ __forceinline__ int bfind_u32(unsigned v) { int r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+
+// FAST: 9 candidates and no clamping possible for any DC value (lim - 1 >= the
+// largest reachable candidate): the 81 candidate differences of a step collapse
+// to D0 - psgn*l, and no candidate needs masking.
+template <bool FAST>
+__global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const TrellisConsts *__restrict__ tc,
+                                                                 const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
+                                                                 const DcRec *__restrict__ rec, RecLayout rl, int max_wib, DcDiv dv)
+{
+  extern __shared__ __align__(16) unsigned char dsm[];
+  __shared__ float T[36];                                   // T[1 + bfind(|d|)] = (float)(bits + ehufsi[bits])
+  __shared__ DcRec stage[DC2_WARPS][3][32];
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
+  const CompGeom &c = g.c[ci];
+  {
+    const DevHuff *dc = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + c.dc_tbl;
+    if (threadIdx.x < 33) T[threadIdx.x] = (float)((int)threadIdx.x + (int)dc->size[threadIdx.x & 255]);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / 9, k = lane - grp * 9;                 // lanes 27..31: grp == 3 (help with loads only)
+  const int gsel = grp < 3 ? grp : 0;
+  const int gbase = gsel * 9;
+  const int n_imcu = (c.hib + c.v - 1) / c.v;
+  const int imcu0 = (blockIdx.x * DC2_WARPS + warp) * 3;        // first of this warp's three chains
+  const int wib = c.wib;
+  uint8_t *btw = dsm + (size_t)warp * 3 * max_wib * 9;          // [3][max_wib][9]
+  uint8_t *bt = btw + (size_t)gsel * max_wib * 9;
+  const int q = tc->q8_zz[c.qt][0];
+  int ncand = (2 + 60 / (q >> 3)) | 1; if (ncand > 9) ncand = 9;     // get_num_dc_trellis_candidates (:929-933)
+  const int half = ncand / 2;
+  const int lim = 1 << tc->max_coef_bits;
+  const float INF = __int_as_float(0x7f800000);
+  const size_t comp_rec = (size_t)img * rl.per_image + rl.comp_off[ci];
+  const int qhalf = q / 2;
+  const unsigned qmul = dv.mul[ci]; const int qshift = dv.shift[ci];
+  int last_dc = 0;                                                // per chain (uniform inside a 9-lane group)
+  for (int br = 0; br < c.v; br++) {
+    // rows of the three chains; a chain without this row idles on row 0 of the component
+    int rowg[3]; bool okg[3];
+#pragma unroll
+    for (int gg = 0; gg < 3; gg++) { int r = (imcu0 + gg) * c.v + br; okg[gg] = (imcu0 + gg) < n_imcu && r < c.hib; rowg[gg] = okg[gg] ? r : 0; }
+    const bool rowok = grp < 3 && okg[gsel];
+    DcRec nxt[3];
+#pragma unroll
+    for (int gg = 0; gg < 3; gg++) nxt[gg] = rec[comp_rec + (size_t)rowg[gg] * wib + min(lane, wib - 1)];
+    float acc = 0.f;
+    // previous block's candidate l is psgn * clamp(pbase + l); for the row's first block every
+    // predecessor is last_dc with zero accumulated cost (pstep = 0)
+    int pbase = last_dc, psgn = 1, pstep = 0;
+    uint8_t *btp = bt + k;
+    for (int bi0 = 0; bi0 < wib; bi0 += 32) {
+      __syncwarp();
+#pragma unroll
+      for (int gg = 0; gg < 3; gg++) stage[warp][gg][lane] = nxt[gg];
+      __syncwarp();
+      if (bi0 + 32 < wib) {
+#pragma unroll
+        for (int gg = 0; gg < 3; gg++) nxt[gg] = rec[comp_rec + (size_t)rowg[gg] * wib + min(bi0 + 32 + lane, wib - 1)];
+      }
+      const int nstep = min(32, wib - bi0);
+      const DcRec *sp = &stage[warp][gsel][0];
+#pragma unroll 1
+      for (int st = 0; st < nstep; st++) {
+        const DcRec r = sp[st];
+        const int raw = r.raw_dc, sign = raw >> 31, x = abs(raw);
+        const int qval = (int)(((unsigned long long)(unsigned)(x + qhalf) * qmul) >> qshift);       // (x + q/2) / q, exact
+        const int base = qval - half;
+        int cd = base + k;
+        if (!FAST) { if (cd >= lim) cd = lim - 1; if (cd <= -lim) cd = -lim + 1; }
+        const int delta = cd * q - x;
+        const float dist = (float)(delta * delta) * r.lambda_dc;
+        const int sgn = 1 + 2 * sign;                             // +1 / -1
+        cd *= sgn;
+        // rate + distortion against every predecessor candidate l (independent of the Viterbi state)
+        float rd[9];
+        if (FAST) {
+          const int D0 = cd - psgn * pbase, dstep = -psgn * pstep;
+#pragma unroll
+          for (int l = 0; l < 9; l++) rd[l] = T[1 + bfind_u32((unsigned)abs(D0 + dstep * l))] + dist;
+        } else {
+#pragma unroll
+          for (int l = 0; l < 9; l++) {
+            int v = pbase + pstep * l;
+            if (pstep) { if (v >= lim) v = lim - 1; if (v <= -lim) v = -lim + 1; }
+            rd[l] = T[1 + bfind_u32((unsigned)abs(cd - psgn * v))] + dist;
+          }
+        }
+        // state-dependent part: predecessors' accumulated costs, first minimum (strict '<', ascending l)
+        float cst[9];
+#pragma unroll
+        for (int l = 0; l < 9; l++) {
+          float pa = __shfl_sync(0xffffffffu, acc, gbase + l);
+          cst[l] = (FAST || l < ncand) ? rd[l] + pa : INF;
+        }
+        float c01 = cst[0]; int i01 = 0; if (cst[1] < c01) { c01 = cst[1]; i01 = 1; }
+        float c23 = cst[2]; int i23 = 2; if (cst[3] < c23) { c23 = cst[3]; i23 = 3; }
+        float c45 = cst[4]; int i45 = 4; if (cst[5] < c45) { c45 = cst[5]; i45 = 5; }
+        float c67 = cst[6]; int i67 = 6; if (cst[7] < c67) { c67 = cst[7]; i67 = 7; }
+        if (c23 < c01) { c01 = c23; i01 = i23; }
+        if (c67 < c45) { c45 = c67; i45 = i67; }
+        if (c45 < c01) { c01 = c45; i01 = i45; }
+        if (cst[8] < c01) { c01 = cst[8]; i01 = 8; }
+        acc = (FAST || k < ncand) ? c01 : INF;
+        if (rowok && (FAST || k < ncand)) *btp = (uint8_t)i01;
+        btp += 9;
+        pbase = base; psgn = sgn; pstep = 1;
+      }
+    }
+    // first minimum over the candidates (:1309-1313)
+    int j = 0; float bj = __shfl_sync(0xffffffffu, acc, gbase);
+#pragma unroll
+    for (int i = 1; i < 9; i++) { float a = __shfl_sync(0xffffffffu, acc, gbase + i); if (i < ncand && a < bj) { bj = a; j = i; } }
+    __syncwarp();
+    // serial back-track: chosen candidate of block bi goes to bt[bi][0]
+    if (rowok && k == 0) {
+#pragma unroll 4
+      for (int bi = wib - 1; bi >= 0; bi--) {
+        int jn = bt[(size_t)bi * 9 + j];
+        bt[(size_t)bi * 9] = (uint8_t)j;
+        j = jn;
+      }
+    }
+    __syncwarp();
+    // candidates -> coefficients, all lanes; the row's last value seeds the next row (jccoefct.c:418, :1320)
+#pragma unroll
+    for (int gg = 0; gg < 3; gg++) {
+      const uint8_t *btg = btw + (size_t)gg * max_wib * 9;
+      int lastv = 0;
+      for (int bi = lane; bi < wib && okg[gg]; bi += 32) {
+        DcRec r = rec[comp_rec + (size_t)rowg[gg] * wib + bi];
+        int raw = r.raw_dc, sign = raw >> 31, x = abs(raw);
+        int cdv = (int)(((unsigned long long)(unsigned)(x + qhalf) * qmul) >> qshift) - half + btg[(size_t)bi * 9];
+        if (cdv >= lim) cdv = lim - 1;
+        if (cdv <= -lim) cdv = -lim + 1;
+        if (sign) cdv = -cdv;
+        c.coef[(((size_t)img * c.hpad + rowg[gg]) * c.wpad + bi) * 64] = (int16_t)cdv;
+        if (bi == wib - 1) lastv = cdv;
+      }
+      lastv = __shfl_sync(0xffffffffu, lastv, (wib - 1) & 31);
+      if (grp == gg) last_dc = lastv;
+    }
+    __syncwarp();
+  }
+}
+
 void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                        const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int n, cudaStream_t s)
 {
   int n_imcu = 0, max_wib = 0;
   for (int ci = 0; ci < g.nc; ci++) { n_imcu = max(n_imcu, (g.c[ci].hib + g.c[ci].v - 1) / g.c[ci].v); max_wib = max(max_wib, g.c[ci].wib); }
-  // warp-cooperative kernel when a chain's back pointers fit in shared memory
+  // warp-cooperative kernel when the chains' back pointers fit in shared memory
+  static const bool use_v1 = getenv("B200JPEG_DC_V1") != nullptr;      // A/B switch
+  size_t smem2 = (size_t)DC2_WARPS * 3 * max_wib * 9;
+  if (!use_v1 && smem2 <= 200 * 1024) {
+    static size_t attr2 = 0;
+    if (smem2 > 40 * 1024 && smem2 > attr2) { cudaFuncSetAttribute(k_trellis_dc_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cudaFuncSetAttribute(k_trellis_dc_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr2 = 200 * 1024; }
+    dim3 grid((n_imcu + DC2_WARPS * 3 - 1) / (DC2_WARPS * 3), n * g.nc);
+    // the DC quantizer per component as an exact multiply-shift division (like make_quant_consts)
+    DcDiv dv; bool fast = true;
+    for (int ci = 0; ci < 4; ci++) { dv.mul[ci] = 0; dv.shift[ci] = 0; }
+    for (int ci = 0; ci < g.nc; ci++) {
+      const unsigned d = (unsigned)g.c[ci].dc_q8;
+      int l = 0; while ((1ull << l) < d) l++;
+      dv.shift[ci] = 18 + l;
+      dv.mul[ci] = (unsigned)(((1ull << dv.shift[ci]) + d - 1) / d);
+      int ncand = (2 + 60 / (int)(d >> 3)) | 1; if (ncand > 9) ncand = 9;
+      fast = fast && ncand == 9 && (int)((32768 + d / 2) / d) + 9 < (1 << g.max_coef_bits) - 1;
+    }
+    if (fast) k_trellis_dc_v2<true><<<grid, DC2_WARPS * 32, smem2, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, max_wib, dv);
+    else k_trellis_dc_v2<false><<<grid, DC2_WARPS * 32, smem2, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, max_wib, dv);
+    LAUNCHED();
+    return;
+  }
   int warps = 2;
   size_t smem = (size_t)warps * 3 * max_wib * 11;
   if (smem > 200 * 1024) { warps = 1; smem = (size_t)3 * max_wib * 11; }
@@ -1110,23 +1332,41 @@ struct CountSink {
   __device__ void ac(int sym, int nb, int) { int s = asz[sym]; if (!s) bad = 1; bits += s + nb; }
 };
 
+// sum of v over the CTA (256 threads), result valid in thread 0
+__device__ __forceinline__ unsigned cta_sum_256(unsigned v, unsigned *ws /* [8] shared */)
+{
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned r = 0;
+  if (threadIdx.x == 0) for (int i = 0; i < 8; i++) r += ws[i];
+  return r;
+}
+
+// One tile = the 256 blocks of one CTA; tile_bits[img][tile] = bits the tile emits.
 __global__ void __launch_bounds__(256) k_block_bits_seq(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
-                                                        uint32_t *__restrict__ blk_bits, uint32_t *__restrict__ status)
+                                                        uint32_t *__restrict__ blk_bits, uint32_t *__restrict__ tile_bits, uint32_t *__restrict__ status)
 {
   __shared__ ScanTables st;
+  __shared__ unsigned ws[8];
   int img = blockIdx.y;
   load_scan_tables(st, tabs, stride, img, g, sd, false);
   __syncthreads();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= sd.nblocks) return;
-  int sci, k; long long mcu;
-  const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
-  int last = prev_dc(g, sd, img, t, sci, mcu, k);
-  const CompGeom &c = g.c[sd.ci[sci]];
-  CountSink sink{st.size[c.dc_tbl], st.size[4 + c.ac_tbl], 0u, 0};
-  walk_seq_block(blk, last, sink);
-  if (sink.bad) atomicOr(&status[img], 2u);
-  blk_bits[(size_t)img * sd.nblocks + t] = sink.bits;
+  unsigned bits = 0;
+  if (t < sd.nblocks) {
+    int sci, k; long long mcu;
+    const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+    int last = prev_dc(g, sd, img, t, sci, mcu, k);
+    const CompGeom &c = g.c[sd.ci[sci]];
+    CountSink sink{st.size[c.dc_tbl], st.size[4 + c.ac_tbl], 0u, 0};
+    walk_seq_block(blk, last, sink);
+    if (sink.bad) atomicOr(&status[img], 2u);
+    bits = sink.bits;
+    blk_bits[(size_t)img * sd.nblocks + t] = bits;
+  }
+  unsigned tot = cta_sum_256(bits, ws);
+  if (threadIdx.x == 0) tile_bits[(size_t)img * gridDim.x + blockIdx.x] = tot;
 }
 
 struct BitSink {
@@ -1141,22 +1381,60 @@ struct BitSink {
   __device__ void finish() { if (nacc > 0) { unsigned w = (unsigned)(acc << (32 - nacc)); if (w) atomicOr(&buf[widx], w); } }
 };
 
+// Bit offset of this thread's block inside the scan: bits of the tiles before
+// this CTA's (tile_bits, summed here: a scan has a few hundred tiles) plus the
+// exclusive scan of blk_bits inside the CTA.  The last tile publishes the
+// scan's total and flags an output buffer that is too small.  Returns false if
+// the block must not be written.
+__device__ __forceinline__ bool block_bit_offset(const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
+                                                 long long nblocks, long long t, int img, size_t capacity_bits,
+                                                 unsigned long long *__restrict__ total_bits, uint32_t *__restrict__ status,
+                                                 unsigned long long &off)
+{
+  __shared__ unsigned long long red[8];
+  __shared__ unsigned wsum[8];
+  __shared__ unsigned long long base_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t *tb = tile_bits + (size_t)img * gridDim.x;
+  unsigned long long part = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += 256) part += tb[i];
+  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  unsigned v = t < nblocks ? blk_bits[(size_t)img * nblocks + t] : 0u, x = v;
+  for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 0) red[wid] = part;
+  if (lane == 31) wsum[wid] = x;
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned long long b = 0; for (int i = 0; i < 8; i++) b += red[i]; base_s = b; }
+  __syncthreads();
+  unsigned before = 0;
+  for (int i = 0; i < wid; i++) before += wsum[i];
+  off = base_s + before + (x - v);
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) {
+    unsigned long long tot = off + v;                      // threads past nblocks carry v = 0
+    total_bits[img] = tot;
+    if (tot + 64 > capacity_bits || tot >= (1ull << 32)) atomicOr(&status[img], 4u);
+  }
+  return t < nblocks && off + v + 64 <= capacity_bits;
+}
+
 __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
-                                                    const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ bitbuf,
-                                                    size_t bitbuf_stride_words, const uint32_t *__restrict__ status)
+                                                    const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
+                                                    uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
+                                                    unsigned long long *__restrict__ total_bits, uint32_t *__restrict__ status)
 {
   __shared__ ScanTables st;
   int img = blockIdx.y;
   load_scan_tables(st, tabs, stride, img, g, sd, true);
+  const unsigned flagged = status[img] & ~1u;      // an earlier stage flagged this image (overflow / bad coefficient)
   __syncthreads();
-  if (status[img] & ~1u) return;            // an earlier stage flagged this image (overflow / bad coefficient)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= sd.nblocks) return;
+  unsigned long long off;
+  bool ok = block_bit_offset(blk_bits, tile_bits, sd.nblocks, t, img, bitbuf_stride_words * 32, total_bits, status, off);
+  if (!ok || flagged) return;
   int sci, k; long long mcu;
   const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
   int last = prev_dc(g, sd, img, t, sci, mcu, k);
   const CompGeom &c = g.c[sd.ci[sci]];
-  unsigned off = blk_off[(size_t)img * sd.nblocks + t];
   BitSink sink;
   sink.buf = bitbuf + (size_t)img * bitbuf_stride_words; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
   sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
@@ -1164,106 +1442,109 @@ __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const D
   sink.finish();
 }
 
-// in-place exclusive scan of blk_bits[img][0..nblocks); one CTA per image
-__global__ void __launch_bounds__(1024) k_scan_offsets(uint32_t *__restrict__ blk_bits, long long nblocks,
-                                                       unsigned long long *__restrict__ total_bits,
-                                                       size_t capacity_bits, uint32_t *__restrict__ status)
-{
-  __shared__ unsigned long long warp_sums[32];
-  __shared__ unsigned long long carry_s;
-  int img = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t *a = blk_bits + (size_t)img * nblocks;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (long long base = 0; base < nblocks; base += 1024) {
-    long long i = base + threadIdx.x;
-    unsigned long long v = i < nblocks ? a[i] : 0, x = v;
-    for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) warp_sums[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-      unsigned long long s = warp_sums[lane], z = s;
-      for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
-      warp_sums[lane] = z - s;            // exclusive
-    }
-    __syncthreads();
-    unsigned long long carry = carry_s;
-    unsigned long long excl = carry + warp_sums[wid] + (x - v);
-    if (i < nblocks) a[i] = (uint32_t)excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = excl + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    unsigned long long tb = carry_s;
-    total_bits[img] = tb;
-    if (tb + 64 > capacity_bits || tb >= (1ull << 32)) atomicOr(&status[img], 4u);    // does not fit: host retries with a larger buffer
-  }
-}
-
 // byte stuffing (jchuff.c:386-435 emit byte / 0xFF00) + final 1-bit padding
-// (flush_bits: 7 one-bits, then drop the partial byte).  One CTA per image;
-// appends at out[img][out_pos[img]] and advances out_pos.
-__global__ void __launch_bounds__(1024) k_stuff(const uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
-                                                const unsigned long long *__restrict__ total_bits,
-                                                uint8_t *__restrict__ out, size_t out_stride, size_t out_capacity,
-                                                unsigned long long *__restrict__ out_pos, uint32_t *__restrict__ scan_size,
-                                                uint32_t *__restrict__ status)
+// (flush_bits: 7 one-bits, then drop the partial byte).  The unstuffed stream of
+// an image is cut into tiles of STUFF_TILE_WORDS 32-bit words, one CTA each:
+//   k_stuff_count : 0xFF bytes per tile;
+//   k_stuff_write : every CTA sums the counts of the tiles before it (a scan has
+//                   at most a few hundred tiles), scans inside the tile, and
+//                   writes its bytes at out[img][out_start[img] + ...]; the last
+//                   tile publishes the scan size and the next scan's start.
+#define STUFF_THREADS 256
+#define STUFF_TILE_WORDS (STUFF_THREADS * 4)
+__device__ __forceinline__ uint4 stuff_load(const uint32_t *__restrict__ src, unsigned long long nbytes, unsigned padbits,
+                                            unsigned long long w0, int &nb)
 {
-  __shared__ unsigned warp_sums[32];
-  __shared__ unsigned long long carry_s;
-  int img = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (status[img] & ~1u) { if (threadIdx.x == 0) *scan_size = 0, scan_size[img] = 0; return; }
-  const uint32_t *src = bitbuf + (size_t)img * bitbuf_stride_words;
-  unsigned long long bits = total_bits[img];
-  unsigned long long nbytes = (bits + 7) >> 3;
-  unsigned padbits = (unsigned)(nbytes * 8 - bits);           // low bits of the last byte to set to 1
-  unsigned long long nwords = (nbytes + 3) >> 2;
-  unsigned long long start = out_pos[img];
-  uint8_t *dst = out + (size_t)img * out_stride;
-  if (threadIdx.x == 0) carry_s = 0;
+  // 4 words = 16 stream bytes starting at word w0; nb = valid bytes among them; pad the last byte with 1-bits
+  uint4 q = make_uint4(0, 0, 0, 0);
+  nb = 0;
+  if (w0 * 4 < nbytes) {
+    unsigned long long rem = nbytes - w0 * 4;
+    nb = rem >= 16 ? 16 : (int)rem;
+    q = *reinterpret_cast<const uint4 *>(src + w0);
+    if (rem <= 16 && padbits) {
+      unsigned m = ((1u << padbits) - 1u) << (8 * (3 - ((nb - 1) & 3)));
+      int wi = (nb - 1) >> 2;
+      if (wi == 0) q.x |= m; else if (wi == 1) q.y |= m; else if (wi == 2) q.z |= m; else q.w |= m;
+    }
+  }
+  return q;
+}
+__device__ __forceinline__ unsigned count_ff16(uint4 q, int nb)
+{
+  unsigned w[4] = {q.x, q.y, q.z, q.w}; unsigned c = 0;
+#pragma unroll
+  for (int j = 0; j < 16; j++) c += (j < nb) && (((w[j >> 2] >> (24 - 8 * (j & 3))) & 0xFF) == 0xFF);
+  return c;
+}
+__global__ void __launch_bounds__(STUFF_THREADS) k_stuff_count(const uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
+                                                               const unsigned long long *__restrict__ total_bits,
+                                                               uint32_t *__restrict__ ff_tile, const uint32_t *__restrict__ status)
+{
+  __shared__ unsigned ws[8];
+  const int img = blockIdx.y;
+  if (status[img] & ~1u) return;
+  const unsigned long long bits = total_bits[img], nbytes = (bits + 7) >> 3;
+  const unsigned long long tile0 = (unsigned long long)blockIdx.x * STUFF_TILE_WORDS;
+  if (tile0 * 4 >= nbytes && blockIdx.x != 0) return;
+  const unsigned padbits = (unsigned)(nbytes * 8 - bits);
+  int nb;
+  uint4 q = stuff_load(bitbuf + (size_t)img * bitbuf_stride_words, nbytes, padbits, tile0 + threadIdx.x * 4, nb);
+  unsigned tot = cta_sum_256(count_ff16(q, nb), ws);
+  if (threadIdx.x == 0) ff_tile[(size_t)img * gridDim.x + blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(STUFF_THREADS) k_stuff_write(const uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
+                                                               const unsigned long long *__restrict__ total_bits,
+                                                               const uint32_t *__restrict__ ff_tile,
+                                                               uint8_t *__restrict__ out, size_t out_stride, size_t out_capacity,
+                                                               const unsigned long long *__restrict__ out_start, unsigned long long *__restrict__ out_next,
+                                                               uint32_t *__restrict__ scan_size, uint32_t *__restrict__ status)
+{
+  __shared__ unsigned red[8], wsum[8];
+  __shared__ unsigned base_s;
+  const int img = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned long long start = out_start[img];
+  if (status[img] & ~1u) { if (blockIdx.x == 0 && threadIdx.x == 0) { scan_size[img] = 0; out_next[img] = start; } return; }
+  const unsigned long long bits = total_bits[img], nbytes = (bits + 7) >> 3;
+  const unsigned long long tile0 = (unsigned long long)blockIdx.x * STUFF_TILE_WORDS;
+  if (tile0 * 4 >= nbytes && blockIdx.x != 0) return;
+  const unsigned padbits = (unsigned)(nbytes * 8 - bits);
+  unsigned part = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += STUFF_THREADS) part += ff_tile[(size_t)img * gridDim.x + i];
+  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  int nb;
+  uint4 q = stuff_load(bitbuf + (size_t)img * bitbuf_stride_words, nbytes, padbits, tile0 + threadIdx.x * 4, nb);
+  unsigned ff = count_ff16(q, nb), x = ff;
+  for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 0) red[wid] = part;
+  if (lane == 31) wsum[wid] = x;
   __syncthreads();
-  for (unsigned long long base = 0; base < nwords; base += 1024) {
-    unsigned long long wi = base + threadIdx.x;
-    unsigned w = 0; int nb = 0;
-    if (wi < nwords) {
-      w = src[wi];
-      unsigned long long rem = nbytes - wi * 4;
-      nb = rem >= 4 ? 4 : (int)rem;
-      if (wi == nwords - 1 && padbits) w |= ((1u << padbits) - 1u) << (8 * (4 - nb));
-    }
-    unsigned ff = 0;
-    for (int j = 0; j < nb; j++) ff += (((w >> (24 - 8 * j)) & 0xFF) == 0xFF);
-    unsigned x = ff;
-    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) warp_sums[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-      unsigned s = warp_sums[lane], z = s;
-      for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
-      warp_sums[lane] = z - s;
-    }
-    __syncthreads();
-    unsigned long long carry = carry_s;
-    unsigned long long ffbefore = carry + warp_sums[wid] + (x - ff);
-    if (nb) {
-      unsigned long long o = start + wi * 4 + ffbefore;
-      if (o + 8 <= out_capacity) {
-        for (int j = 0; j < nb; j++) {
-          unsigned b = (w >> (24 - 8 * j)) & 0xFF;
+  if (threadIdx.x == 0) { unsigned b = 0; for (int i = 0; i < 8; i++) b += red[i]; base_s = b; }
+  __syncthreads();
+  unsigned before = base_s;
+  for (int i = 0; i < wid; i++) before += wsum[i];
+  before += x - ff;
+  if (nb) {
+    unsigned long long o = start + (tile0 + threadIdx.x * 4) * 4 + before;
+    if (o + 32 <= out_capacity) {
+      uint8_t *dst = out + (size_t)img * out_stride;
+      unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        if (j < nb) {
+          unsigned b = (w[j >> 2] >> (24 - 8 * (j & 3))) & 0xFF;
           dst[o++] = (uint8_t)b;
           if (b == 0xFF) dst[o++] = 0;
         }
-      } else atomicOr(&status[img], 4u);
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = ffbefore + ff;
-    __syncthreads();
+      }
+    } else atomicOr(&status[img], 4u);
   }
-  if (threadIdx.x == 0) {
-    unsigned long long total = nbytes + carry_s;
+  // the thread holding the last stream byte (or thread 0 of tile 0 for an empty stream) publishes the totals
+  const unsigned long long myb0 = (tile0 + threadIdx.x * 4) * 4;
+  if ((nbytes == 0 && blockIdx.x == 0 && threadIdx.x == 0) || (nb && myb0 + nb == nbytes)) {
+    unsigned long long total = nbytes + before + ff;
     scan_size[img] = (uint32_t)total;
-    out_pos[img] = start + total;
+    out_next[img] = start + total;
   }
 }
 
@@ -1469,42 +1750,50 @@ __global__ void __launch_bounds__(256) k_gather_prog(Geom g, ScanDesc sd, const 
 
 __global__ void __launch_bounds__(256) k_block_bits_prog(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
                                                          const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
-                                                         uint32_t *__restrict__ blk_bits, uint32_t *__restrict__ status)
+                                                         uint32_t *__restrict__ blk_bits, uint32_t *__restrict__ tile_bits, uint32_t *__restrict__ status)
 {
   __shared__ ScanTables st;
+  __shared__ unsigned ws[8];
   int img = blockIdx.y;
   if (!(sd.Ss == 0 && sd.Ah != 0)) load_scan_tables(st, tabs, stride, img, g, sd, false);
   __syncthreads();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= sd.nblocks) return;
-  int sci, k; long long mcu;
-  const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
-  int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
-  const CompGeom &c = g.c[sd.ci[sci]];
-  CountSinkP sink{st.size[c.dc_tbl], st.size[4 + c.ac_tbl], 0u, 0};
-  unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
-  walk_prog_block(blk, sd, last, a, re, sink);
-  if (sink.bad) atomicOr(&status[img], 2u);
-  blk_bits[(size_t)img * sd.nblocks + t] = sink.bits;
+  unsigned bits = 0;
+  if (t < sd.nblocks) {
+    int sci, k; long long mcu;
+    const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+    int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
+    const CompGeom &c = g.c[sd.ci[sci]];
+    CountSinkP sink{st.size[c.dc_tbl], st.size[4 + c.ac_tbl], 0u, 0};
+    unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
+    walk_prog_block(blk, sd, last, a, re, sink);
+    if (sink.bad) atomicOr(&status[img], 2u);
+    bits = sink.bits;
+    blk_bits[(size_t)img * sd.nblocks + t] = bits;
+  }
+  unsigned tot = cta_sum_256(bits, ws);
+  if (threadIdx.x == 0) tile_bits[(size_t)img * gridDim.x + blockIdx.x] = tot;
 }
 
 __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
                                                      const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
-                                                     const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ bitbuf,
-                                                     size_t bitbuf_stride_words, const uint32_t *__restrict__ status)
+                                                     const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
+                                                     uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
+                                                     unsigned long long *__restrict__ total_bits, uint32_t *__restrict__ status)
 {
   __shared__ ScanTables st;
   int img = blockIdx.y;
   if (!(sd.Ss == 0 && sd.Ah != 0)) load_scan_tables(st, tabs, stride, img, g, sd, true);
+  const unsigned flagged = status[img] & ~1u;
   __syncthreads();
-  if (status[img] & ~1u) return;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= sd.nblocks) return;
+  unsigned long long off;
+  bool ok = block_bit_offset(blk_bits, tile_bits, sd.nblocks, t, img, bitbuf_stride_words * 32, total_bits, status, off);
+  if (!ok || flagged) return;
   int sci, k; long long mcu;
   const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
   int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
   const CompGeom &c = g.c[sd.ci[sci]];
-  unsigned off = blk_off[(size_t)img * sd.nblocks + t];
   BitSinkP sink;
   sink.buf = bitbuf + (size_t)img * bitbuf_stride_words; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
   sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
@@ -1527,34 +1816,30 @@ void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, 
 }
 
 void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, int progressive,
-                       uint32_t *blk_bits, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *status, int n, cudaStream_t s)
+                       uint32_t *blk_bits, uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  if (progressive) k_block_bits_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, status);
-  else k_block_bits_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, status);
-  LAUNCHED();
-}
-void launch_scan_offsets(uint32_t *blk_bits, long long nblocks, unsigned long long *total_bits, size_t capacity_bits,
-                         uint32_t *status, int n, cudaStream_t s)
-{
-  k_scan_offsets<<<n, 1024, 0, s>>>(blk_bits, nblocks, total_bits, capacity_bits, status);
+  if (progressive) k_block_bits_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, tile_bits, status);
+  else k_block_bits_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, tile_bits, status);
   LAUNCHED();
 }
 void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, int progressive,
-                   const uint32_t *blk_off, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *bitbuf, size_t bitbuf_stride_words,
-                   const uint32_t *status, int n, cudaStream_t s)
+                   const uint32_t *blk_bits, const uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e,
+                   uint32_t *bitbuf, size_t bitbuf_stride_words, unsigned long long *total_bits, uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_off, bitbuf, bitbuf_stride_words, status);
-  else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_off, bitbuf, bitbuf_stride_words, status);
+  if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, tile_bits, bitbuf, bitbuf_stride_words, total_bits, status);
+  else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, tile_bits, bitbuf, bitbuf_stride_words, total_bits, status);
   LAUNCHED();
 }
-void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_stride_words, const unsigned long long *total_bits,
-                  uint8_t *out, size_t out_stride, size_t out_capacity, unsigned long long *out_pos, uint32_t *scan_size,
-                  uint32_t *status, int n, cudaStream_t s)
+size_t stuff_tiles(size_t bitbuf_stride_words) { return (bitbuf_stride_words + STUFF_TILE_WORDS - 1) / STUFF_TILE_WORDS; }
+void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_stride_words, const unsigned long long *total_bits, uint32_t *ff_tile,
+                  uint8_t *out, size_t out_stride, size_t out_capacity, const unsigned long long *out_start, unsigned long long *out_next,
+                  uint32_t *scan_size, uint32_t *status, int n, cudaStream_t s)
 {
-  k_stuff<<<n, 1024, 0, s>>>(bitbuf, bitbuf_stride_words, total_bits, out, out_stride, out_capacity, out_pos, scan_size, status);
-  LAUNCHED();
+  dim3 grid((unsigned)stuff_tiles(bitbuf_stride_words), n);
+  k_stuff_count<<<grid, STUFF_THREADS, 0, s>>>(bitbuf, bitbuf_stride_words, total_bits, ff_tile, status); LAUNCHED();
+  k_stuff_write<<<grid, STUFF_THREADS, 0, s>>>(bitbuf, bitbuf_stride_words, total_bits, ff_tile, out, out_stride, out_capacity, out_start, out_next, scan_size, status); LAUNCHED();
 }
 
 }  // namespace b200

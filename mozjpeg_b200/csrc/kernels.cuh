@@ -25,6 +25,7 @@ struct CompGeom {
   int qt;              // quant table slot
   int dc_tbl, ac_tbl;  // Huffman table slots
   int rows_avail;      // downsampled rows holding real data (jcprepct.c:135-192)
+  int dc_q8;           // 8 * quantval[0] of the component's table
   long long blocks_per_image;   // wpad*hpad
   int16_t *coef, *raw;
 };
@@ -32,6 +33,7 @@ struct Geom {
   int W, H, nc, hmax, vmax;
   int mcus_per_row, mcu_rows;
   int in_comps;        // samples per input pixel
+  int max_coef_bits;   // data_precision + 2
   int cs_mode;         // 0: RGB->YCbCr  1: RGB->gray  2: pass-through
   size_t row_pitch, image_stride;
   CompGeom c[4];
@@ -74,9 +76,11 @@ struct DevHuff {
 static_assert(sizeof(DevHuff) == 17 + 256 + 1 + 12 + 2 + 512 + 256, "DevHuff layout");
 
 // per real block side record: K1 writes {f = norm (jcdctmgr.c:1026-1030, before the /63),
-// raw_dc, nz = number of non-zero plain-quantized AC coefficients}; the AC trellis
-// replaces f by lambda_dc for the DC trellis.
-struct DcRec { float lambda_dc; int16_t raw_dc; uint8_t nz; uint8_t pad; };
+// raw_dc, nz = number of non-zero plain-quantized AC coefficients, nzmask = their zigzag
+// positions (bit i = position i, bit 0 clear)}; the AC trellis replaces f by lambda_dc for
+// the DC trellis.
+struct DcRec { float lambda_dc; int16_t raw_dc; uint8_t nz; uint8_t pad; unsigned long long nzmask; };
+static_assert(sizeof(DcRec) == 16, "DcRec layout");
 // where component ci's records start inside an image's record array
 struct RecLayout { long long per_image; long long comp_off[4]; };
 // which of the 8 table slots to (re)build for set i: m[i % period]
@@ -101,15 +105,15 @@ void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *ta
 void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int n, cudaStream_t s);
 void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
-                       uint32_t *blk_bits, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *status, int n, cudaStream_t s);
-void launch_scan_offsets(uint32_t *blk_bits, long long nblocks, unsigned long long *total_bits, size_t capacity_bits,
-                         uint32_t *status, int n, cudaStream_t s);
+                       uint32_t *blk_bits, uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *status, int n, cudaStream_t s);
+// bit offsets are resolved inside the encode kernel (tile sums + in-CTA scan); it also publishes total_bits[img]
 void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
-                   const uint32_t *blk_off, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *bitbuf, size_t bitbuf_image_stride_words,
-                   const uint32_t *status, int n, cudaStream_t s);
-void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_image_stride_words, const unsigned long long *total_bits,
-                  uint8_t *out, size_t out_image_stride, size_t out_capacity, unsigned long long *out_pos, uint32_t *scan_size,
-                  uint32_t *status, int n, cudaStream_t s);
+                   const uint32_t *blk_bits, const uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e,
+                   uint32_t *bitbuf, size_t bitbuf_image_stride_words, unsigned long long *total_bits, uint32_t *status, int n, cudaStream_t s);
+size_t stuff_tiles(size_t bitbuf_image_stride_words);     // ff_tile entries per image
+void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_image_stride_words, const unsigned long long *total_bits, uint32_t *ff_tile,
+                  uint8_t *out, size_t out_image_stride, size_t out_capacity, const unsigned long long *out_start, unsigned long long *out_next,
+                  uint32_t *scan_size, uint32_t *status, int n, cudaStream_t s);
 
 extern unsigned long long g_kernel_launches;
 
