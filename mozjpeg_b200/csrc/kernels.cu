@@ -746,6 +746,87 @@ void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, ui
   LAUNCHED();
 }
 
+// Register fast path of the AC trellis for warps whose blocks all have at most
+// MM non-zero positions (blocks are sorted by that count, so this is the common
+// case): the compact lists are reloaded from local memory with STATIC indices
+// into registers, and the (entry, predecessor) loops are fully unrolled, so the
+// search touches no memory except the shared rate table.  Same arithmetic and
+// selection rule as the generic loop in k_trellis_ac.
+template <int MM>
+__device__ __forceinline__ void trellis_entries_regs(const int m, const uint8_t *e_pos, const unsigned short *e_qs, const float *e_at,
+                                                     const float *e_before, const int16_t *__restrict__ o16,
+                                                     const __half (*srate)[64], const float *swz, const int *sq8,
+                                                     const float lambda, const int maxq, const float azd63, const float eob)
+{
+  int r_pos[MM]; float r_at[MM], r_acc[MM];
+  int r_rs[MM], r_val[MM];
+#pragma unroll
+  for (int t = 0; t < MM; t++) { r_pos[t] = e_pos[t]; r_at[t] = e_at[t]; r_acc[t] = 0.f; r_rs[t] = 0; r_val[t] = 0; }
+  int nraw = (int)(short)e_qs[0], nqnt = m > 0 ? (int)o16[r_pos[0]] : 0; float nbefore = e_before[0];
+#pragma unroll
+  for (int t = 0; t < MM; t++) {
+    if (t < m) {
+      const int i = r_pos[t];
+      const int rawv = nraw, qntv = nqnt; const float Ai1 = nbefore;
+      if (t + 1 < MM) { nraw = (int)(short)e_qs[t + 1]; nbefore = e_before[t + 1]; if (t + 1 < m) nqnt = o16[r_pos[t + 1]]; }
+      const int x = abs(rawv);
+      const int q = sq8[i];
+      const int qv = min(abs(qntv), maxq);
+      const int nc = nbits_of(qv);
+      const float wl = swz[i];
+      float best = 1e38f; int best_s = 0, best_k = -1;
+#pragma unroll 1
+      for (int k = 0; k < nc; k++) {
+        const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
+        const int delta = cand * q - x;
+        const float dist = (float)(delta * delta) * lambda * wl;                   // :1151
+        const __half *rk = &srate[k][i - 1];                                        // rk[-j] = rate for run i-1-j
+        float kb = 1e38f; int ks = 0;
+        {
+          float cost = __half2float(rk[0]) + dist;
+          cost += (Ai1 - 0.0f) + 0.0f;
+          if (cost < kb) { kb = cost; ks = 0; }
+        }
+#pragma unroll
+        for (int s2 = 0; s2 < t; s2++) {
+          float cost = __half2float(rk[-r_pos[s2]]) + dist;
+          cost += (Ai1 - r_at[s2]) + r_acc[s2];
+          if (cost < kb) { kb = cost; ks = s2 + 1; }
+        }
+        if (kb < best || (kb == best && ks < best_s)) { best = kb; best_s = ks; best_k = k; }
+      }
+      r_acc[t] = best; r_rs[t] = best_s;
+      // the value this entry takes if it stays on the chain (:1179, :1143-1153)
+      const int nc1 = nc - 1;
+      const int cand = (best_k >= 0 && best_k < nc1) ? (2 << best_k) - 1 : qv;
+      const int sgn = rawv >> 31;
+      r_val[t] = (cand ^ sgn) - sgn;
+    }
+  }
+  // best end-of-block position (:1187-1207)
+  int last = 0;
+  float best_cost = azd63 + eob;
+#pragma unroll
+  for (int t = 0; t < MM; t++) {
+    if (t < m) {
+      float cst = r_acc[t] + azd63 - r_at[t];
+      if (r_pos[t] < 63) cst += eob;
+      if (cst < best_cost) { best_cost = cst; last = t + 1; }
+    }
+  }
+  // output: zeros except the back-tracked chain (:1211-1222); DC slot untouched here
+  int16_t *o = const_cast<int16_t *>(o16);
+  const unsigned dc_q = (unsigned)(unsigned short)o[0];
+  uint4 *q4 = reinterpret_cast<uint4 *>(o);
+  q4[0] = make_uint4(dc_q, 0, 0, 0);
+#pragma unroll
+  for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int t = MM - 1; t >= 0; t--) {
+    if (t + 1 == last) { o[r_pos[t]] = (int16_t)r_val[t]; last = r_rs[t]; }
+  }
+}
+
 // Shared memory per CTA: the rate table of the CTA's (image, component)
 //   rate[k][run] = ehufsi[16*(run&15) + k+1] + (k+1) + (run>>4)*ehufsi[0xF0]   (:1163-1175)
 // as fp16 (exact: <= 74), +inf where the reference skips the combination
@@ -759,7 +840,7 @@ void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, ui
 // candidate: for each candidate the first predecessor with the smallest cost,
 // then over candidates the smallest cost, ties to the earlier predecessor, then
 // to the earlier candidate -- the same pair the reference's scan order keeps.
-__global__ void __launch_bounds__(TRELLIS_THREADS, 8) k_trellis_ac(Geom g, const TrellisConsts *__restrict__ tc,
+__global__ void __launch_bounds__(TRELLIS_THREADS, 5) k_trellis_ac(Geom g, const TrellisConsts *__restrict__ tc,
                                                                    const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
                                                                    DcRec *__restrict__ rec, RecLayout rl, const uint32_t *__restrict__ perm)
 {
@@ -831,6 +912,15 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, 8) k_trellis_ac(Geom g, const
   }
   const float azd63 = azd;
   const int maxq = (1 << tc->max_coef_bits) - 1;
+
+  // warps whose blocks all have few non-zero positions take the register path
+  {
+    const int mmax = __reduce_max_sync(__activemask(), m);
+    if (mmax <= 16) {
+      trellis_entries_regs<16>(m, e_pos, e_qs, e_at, e_before, o16, srate, swz, sq8, lambda, maxq, azd63, (float)acsi[0]);
+      return;
+    }
+  }
 
   // phase 2   :1121-1185.  The entry's plain-quantized value comes from global memory (L2 resident: K1 just wrote it);
   // the next entry's value is requested one iteration ahead.
