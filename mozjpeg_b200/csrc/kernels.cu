@@ -753,22 +753,31 @@ void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, ui
 // search touches no memory except the shared rate table.  Same arithmetic and
 // selection rule as the generic loop in k_trellis_ac.
 template <int MM>
-__device__ __forceinline__ void trellis_entries_regs(const int m, const uint8_t *e_pos, const unsigned short *e_qs, const float *e_at,
-                                                     const float *e_before, const int16_t *__restrict__ o16,
+__device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long long nzmask, const float *A,
+                                                     const int16_t *__restrict__ raw16, const int16_t *__restrict__ o16,
                                                      const __half (*srate)[64], const float *swz, const int *sq8,
                                                      const float lambda, const int maxq, const float azd63, const float eob)
 {
   int r_pos[MM]; float r_at[MM], r_acc[MM];
   int r_rs[MM], r_val[MM];
+  {
+    unsigned lo = (unsigned)nzmask, hi = (unsigned)(nzmask >> 32);
 #pragma unroll
-  for (int t = 0; t < MM; t++) { r_pos[t] = e_pos[t]; r_at[t] = e_at[t]; r_acc[t] = 0.f; r_rs[t] = 0; r_val[t] = 0; }
-  int nraw = (int)(short)e_qs[0], nqnt = m > 0 ? (int)o16[r_pos[0]] : 0; float nbefore = e_before[0];
+    for (int t = 0; t < MM; t++) {
+      // next set bit, ascending (positions past the block's last non-zero read A[63], harmlessly)
+      int p = lo ? __ffs((int)lo) - 1 : (hi ? 31 + __ffs((int)hi) : 63);
+      if (lo) lo &= lo - 1; else hi &= hi - 1;
+      r_pos[t] = p; r_at[t] = A[p]; r_acc[t] = 0.f; r_rs[t] = 0; r_val[t] = 0;
+    }
+  }
+  int nraw = 0, nqnt = 0; float nbefore = 0.f;
+  if (m > 0) { nraw = raw16[r_pos[0]]; nqnt = o16[r_pos[0]]; nbefore = A[r_pos[0] - 1]; }
 #pragma unroll
   for (int t = 0; t < MM; t++) {
     if (t < m) {
       const int i = r_pos[t];
       const int rawv = nraw, qntv = nqnt; const float Ai1 = nbefore;
-      if (t + 1 < MM) { nraw = (int)(short)e_qs[t + 1]; nbefore = e_before[t + 1]; if (t + 1 < m) nqnt = o16[r_pos[t + 1]]; }
+      if (t + 1 < MM && t + 1 < m) { nraw = raw16[r_pos[t + 1]]; nqnt = o16[r_pos[t + 1]]; nbefore = A[r_pos[t + 1] - 1]; }
       const int x = abs(rawv);
       const int q = sq8[i];
       const int qv = min(abs(qntv), maxq);
@@ -884,16 +893,12 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, 5) k_trellis_ac(Geom g, const
     rec[rbase + lin].lambda_dc = lambda * swz[0];
     nzmask = rr.nzmask;
   }
-  // compact lists, indexed by rank among the non-zero positions
-  uint8_t e_pos[64], e_rs[64], e_k[64];
-  unsigned short e_qs[64];                         // plain-quantized magnitude (clamped) | sign of the raw value << 15
-  float e_at[64], e_before[64], e_acc[64];
-  // phase 1: accumulated zero distortion (zigzag order, serial fp32)   :1134
+  // phase 1: accumulated zero distortion (zigzag order, serial fp32), every position, to local memory   :1134
+  float A[64];
   float azd = 0.0f;
-  int m = 0;
+  A[0] = 0.0f;
   {
     const uint4 *r4 = reinterpret_cast<const uint4 *>(raw16);
-    const unsigned mlo = (unsigned)nzmask, mhi = (unsigned)(nzmask >> 32);
 #pragma unroll
     for (int v = 0; v < 8; v++) {
       const uint4 a = r4[v];
@@ -902,23 +907,34 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, 5) k_trellis_ac(Geom g, const
       for (int jj = 0; jj < 8; jj++) {
         const int i = 8 * v + jj;
         if (i == 0) continue;
-        const int rawv = (int)(int16_t)((aw[jj >> 1] >> ((jj & 1) * 16)) & 0xFFFF);
-        const int x = abs(rawv);
-        const float before = azd;
+        const int x = abs((int)(int16_t)((aw[jj >> 1] >> ((jj & 1) * 16)) & 0xFFFF));
         azd = (float)(x * x) * lambda * swz[i] + azd;
-        if ((i < 32 ? mlo >> i : mhi >> (i - 32)) & 1u) { e_pos[m] = (uint8_t)i; e_at[m] = azd; e_before[m] = before; e_qs[m] = (unsigned short)(rawv & 0xFFFF); m++; }
+        A[i] = azd;
       }
     }
   }
   const float azd63 = azd;
   const int maxq = (1 << tc->max_coef_bits) - 1;
+  const int m = __popcll(nzmask);
 
   // warps whose blocks all have few non-zero positions take the register path
   {
     const int mmax = __reduce_max_sync(__activemask(), m);
     if (mmax <= 16) {
-      trellis_entries_regs<16>(m, e_pos, e_qs, e_at, e_before, o16, srate, swz, sq8, lambda, maxq, azd63, (float)acsi[0]);
+      trellis_entries_regs<16>(m, nzmask, A, raw16, o16, srate, swz, sq8, lambda, maxq, azd63, (float)acsi[0]);
       return;
+    }
+  }
+
+  // generic path: compact lists, indexed by rank among the non-zero positions
+  uint8_t e_pos[64], e_rs[64], e_k[64];
+  unsigned short e_qs[64];                         // plain-quantized magnitude (clamped) | sign of the raw value << 15
+  float e_at[64], e_before[64], e_acc[64];
+  {
+    int r = 0;
+    for (unsigned long long mm = nzmask; mm; mm &= mm - 1) {
+      const int p = __ffsll((long long)mm) - 1;
+      e_pos[r] = (uint8_t)p; e_at[r] = A[p]; e_before[r] = A[p - 1]; e_qs[r] = (unsigned short)raw16[p]; r++;
     }
   }
 
