@@ -239,12 +239,17 @@ def main():
     ev0.record(stream)
     for _ in range(a.steps):
         step_resident()
-        for k, v in enc.stage_times().items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
     ev1.record(stream)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = enc.kernel_launches() - l0
+    # per-kernel times for the roofline: one extra, untimed pass with a single compute stream
+    # (in the timed region consecutive chunks overlap on two streams, so stage intervals overlap too)
+    enc.set_streams(1)
+    step_resident()
+    torch.cuda.synchronize()
+    stage_acc = {k: v * a.steps for k, v in enc.stage_times().items()}
+    enc.set_streams(2)
     clk = clocks.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:

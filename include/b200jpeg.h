@@ -182,6 +182,12 @@ int  b200jpeg_encoder_set_stream(b200jpeg_encoder *enc, void *cuda_stream);
  * intermediate HBM arenas are sized for one chunk.  0 = automatic (about 1.6 M
  * 8x8 blocks per chunk, i.e. 8 images of 3840x2160 4:2:0). */
 int  b200jpeg_encoder_set_chunk_images(b200jpeg_encoder *enc, int images_per_chunk);
+/* Consecutive chunks alternate between `n_streams` (1 or 2, default 2) compute
+ * streams, each with its own intermediate arenas, so that one chunk's
+ * latency-bound phases (serial Huffman table construction, trellis chains)
+ * overlap the other's bandwidth-bound ones.  With 1 stream the per-stage times
+ * of b200jpeg_last_stage_times() are those of kernels running alone. */
+int  b200jpeg_encoder_set_streams(b200jpeg_encoder *enc, int n_streams);
 
 /*
  * Encode a batch of `n_images` images that share one parameter set and one

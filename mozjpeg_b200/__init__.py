@@ -47,6 +47,10 @@ class Encoder:
         """Images per pipeline chunk (0 = automatic)."""
         A.check(_lib.b200jpeg_encoder_set_chunk_images(self._h, n), "set_chunk_images")
 
+    def set_streams(self, n: int) -> None:
+        """Compute streams consecutive chunks alternate between (1 or 2)."""
+        A.check(_lib.b200jpeg_encoder_set_streams(self._h, n), "set_streams")
+
     # -- batch API -------------------------------------------------------
     def encode_batch(self, p: Params, images: np.ndarray) -> List[bytes]:
         """images: (N, H, W, C) or (N, H, W) uint8 host array -> N JPEG files.

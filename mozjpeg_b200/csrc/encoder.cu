@@ -68,6 +68,18 @@ struct Plan {                // everything derived from b200jpeg_params
 
 using namespace b200;
 
+// intermediate HBM state of one chunk in flight
+struct Arena {
+  b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm;
+  b200::DevBuf d_blk_bits, d_tile_bits, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
+  b200::Geom g;                      // the plan's geometry with this arena's coefficient pointers
+  void release() {
+    b200::DevBuf *db[] = {&d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_blk_bits, &d_tile_bits, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
+    for (b200::DevBuf *b : db) b->release();
+    for (int i = 0; i < 4; i++) { d_coef[i].release(); d_raw[i].release(); d_plain[i].release(); }
+  }
+};
+
 struct b200jpeg_encoder {
   int device = 0;
   cudaStream_t stream = nullptr;     // compute stream (caller-replaceable)
@@ -77,12 +89,15 @@ struct b200jpeg_encoder {
   Plan plan;
   int n = 0;                        // images of the last batch
   int chunk = 0;                    // images per chunk of the last batch
-  int last_chunk_i0 = 0, last_chunk_n = 0;   // the chunk whose intermediates are still in the arenas
+  int last_chunk_i0 = 0, last_chunk_n = 0, last_chunk_slot = 0;   // the chunk whose intermediates are still in the arenas
   int chunk_images_override = 0;    // 0 = automatic
   bool keep_plain = false;
-  // device arenas sized for ONE chunk
-  DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm;
-  DevBuf d_blk_bits, d_tile_bits, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
+  // device arenas sized for ONE chunk; two of them so that consecutive chunks can run on two
+  // streams and fill each other's latency-bound phases (serial table construction, trellis chains)
+  Arena ar[2];
+  cudaStream_t sc[2] = {nullptr, nullptr};   // sc[0] aliases `stream`
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int n_streams = 2;
   // device buffers sized for the WHOLE batch
   DevBuf d_src, d_tabs_scan, d_tabs_fixed, d_status, d_out_pos, d_scan_size, d_out, d_qt, d_tc;
   size_t bitbuf_words_per_image = 0, out_cap_per_image = 0;
@@ -107,6 +122,7 @@ struct b200jpeg_encoder {
 // One chunk of a batch: images [i0, i0+n) and where their results go.
 struct ChunkIO {
   int i0, n;
+  int slot;                         // which arena / stream
   const uint8_t *src;               // first pixel of image i0 (device)
   uint8_t *out;                     // [n][out_cap_per_image]
   unsigned long long *out_pos;      // [nscans+1][n]: start of every scan's bytes inside out[img]; row nscans = total
@@ -237,10 +253,10 @@ static int make_fixed_table(const b200jpeg_huff_tbl &t, bool is_dc, DevHuff *out
 }
 
 struct Timer {
-  b200jpeg_encoder *e; size_t idx = 0;
+  b200jpeg_encoder *e; size_t idx = 0; cudaStream_t s = nullptr;
   void mark(const char *name) {
     if (idx >= e->ev.size()) { cudaEvent_t ev; cudaEventCreate(&ev); e->ev.push_back(ev); }
-    cudaEventRecord(e->ev[idx], e->stream);
+    cudaEventRecord(e->ev[idx], s ? s : e->stream);
     if (idx >= e->ev_names.size()) e->ev_names.push_back(name); else e->ev_names[idx] = name;
     idx++;
   }
@@ -260,7 +276,7 @@ static uint32_t scan_slot_mask(const Plan &pl, const ScanDesc &sd)
 }
 
 // Buffers and constants of one batch of n_total images processed in chunks of `chunk`.
-static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_pixels, size_t src_bytes)
+static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_pixels, size_t src_bytes, int n_arenas)
 {
   Plan &pl = e->plan; const b200jpeg_params *p = &e->params; cudaStream_t s = e->stream;
   Geom &g = pl.g;
@@ -268,29 +284,33 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
   if (p->restart_interval || p->restart_in_rows) { set_error("restart intervals are not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
   int rc;
   const int n = chunk;
-  for (int ci = 0; ci < g.nc; ci++) {
-    if ((rc = e->d_coef[ci].reserve(pl.coef_bytes[ci] * n))) return rc;
-    if ((rc = e->d_raw[ci].reserve(pl.coef_bytes[ci] * n))) return rc;
-    g.c[ci].coef = e->d_coef[ci].as<int16_t>(); g.c[ci].raw = e->d_raw[ci].as<int16_t>();
-    if (e->keep_plain && pl.trellis) { if ((rc = e->d_plain[ci].reserve(pl.coef_bytes[ci] * n))) return rc; }
-  }
-  const size_t hist_bytes = (size_t)n * HIST_SLOTS * HIST_BINS * 4;
-  if ((rc = e->d_hist.reserve(hist_bytes * g.nc))) return rc;
-  const size_t tabset = sizeof(DevHuff) * HIST_SLOTS;
-  if ((rc = e->d_tabs_trellis.reserve(tabset * 4 * n))) return rc;
-  if ((rc = e->d_rec.reserve((size_t)n * pl.sum_real_blocks * sizeof(DcRec)))) return rc;
-  if ((rc = e->d_bt.reserve((size_t)n * pl.sum_real_blocks * 8))) return rc;
-  if ((rc = e->d_perm.reserve((size_t)n * pl.sum_real_blocks * 4))) return rc;
-  if ((rc = e->d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
-  if (pl.progressive) { if ((rc = e->d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = e->d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
-  if ((rc = e->d_total_bits.reserve((size_t)n * 8))) return rc;
-  if ((rc = e->d_tile_bits.reserve((size_t)n * ((pl.max_scan_blocks + 255) / 256) * 4))) return rc;
   long long total_blocks = 0; for (int ci = 0; ci < g.nc; ci++) total_blocks += g.c[ci].blocks_per_image;
   size_t cap = (size_t)((double)total_blocks * 64 * e->cap_factor) + 65536;
   cap = (cap + 255) & ~(size_t)255;
   e->bitbuf_words_per_image = cap / 4; e->out_cap_per_image = cap + cap / 64 + 4096;
-  if ((rc = e->d_bitbuf.reserve(cap * n))) return rc;
-  if ((rc = e->d_ff_tile.reserve((size_t)n * stuff_tiles(e->bitbuf_words_per_image) * 4))) return rc;
+  const size_t hist_bytes = (size_t)n * HIST_SLOTS * HIST_BINS * 4;
+  const size_t tabset = sizeof(DevHuff) * HIST_SLOTS;
+  for (int ai = 0; ai < n_arenas; ai++) {
+    Arena &a = e->ar[ai];
+    a.g = g;
+    for (int ci = 0; ci < g.nc; ci++) {
+      if ((rc = a.d_coef[ci].reserve(pl.coef_bytes[ci] * n))) return rc;
+      if ((rc = a.d_raw[ci].reserve(pl.coef_bytes[ci] * n))) return rc;
+      a.g.c[ci].coef = a.d_coef[ci].as<int16_t>(); a.g.c[ci].raw = a.d_raw[ci].as<int16_t>();
+      if (e->keep_plain && pl.trellis) { if ((rc = a.d_plain[ci].reserve(pl.coef_bytes[ci] * n))) return rc; }
+    }
+    if ((rc = a.d_hist.reserve(hist_bytes * g.nc))) return rc;
+    if ((rc = a.d_tabs_trellis.reserve(tabset * 4 * n))) return rc;
+    if ((rc = a.d_rec.reserve((size_t)n * pl.sum_real_blocks * sizeof(DcRec)))) return rc;
+    if ((rc = a.d_bt.reserve((size_t)n * pl.sum_real_blocks * 8))) return rc;
+    if ((rc = a.d_perm.reserve((size_t)n * pl.sum_real_blocks * 4))) return rc;
+    if ((rc = a.d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
+    if (pl.progressive) { if ((rc = a.d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = a.d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
+    if ((rc = a.d_total_bits.reserve((size_t)n * 8))) return rc;
+    if ((rc = a.d_tile_bits.reserve((size_t)n * ((pl.max_scan_blocks + 255) / 256) * 4))) return rc;
+    if ((rc = a.d_bitbuf.reserve(cap * n))) return rc;
+    if ((rc = a.d_ff_tile.reserve((size_t)n * stuff_tiles(e->bitbuf_words_per_image) * 4))) return rc;
+  }
   // whole batch
   if (host_pixels) { if ((rc = e->d_src.reserve(src_bytes))) return rc; }
   if ((rc = e->d_tabs_scan.reserve(tabset * nscans * n_total))) return rc;
@@ -323,8 +343,10 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
 // jcmaster.c with every pass one launch over all images of the chunk.
 static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
 {
-  Plan &pl = e->plan; const b200jpeg_params *p = &e->params; const int n = io.n; cudaStream_t s = e->stream;
-  Geom &g = pl.g;
+  Plan &pl = e->plan; const b200jpeg_params *p = &e->params; const int n = io.n; cudaStream_t s = e->sc[io.slot];
+  Arena &A = e->ar[io.slot];
+  Geom &g = A.g;
+  tm.s = s;
   const int nscans = (int)pl.scans.size();
   const size_t hist_bytes = (size_t)n * HIST_SLOTS * HIST_BINS * 4;
   const size_t tabset = sizeof(DevHuff) * HIST_SLOTS;
@@ -335,7 +357,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   RecLayout rl; memset(&rl, 0, sizeof rl);
   for (int ci = 0; ci < g.nc; ci++) { rl.comp_off[ci] = rl.per_image; rl.per_image += (long long)g.c[ci].wib * g.c[ci].hib; }
   tm.mark("forward");
-  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), pl.dering, pl.trellis ? e->d_rec.as<DcRec>() : nullptr, rl, n, s);
+  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, n, s);
   tm.mark("dummy");
   launch_dummy(g, n, s);
 
@@ -344,17 +366,17 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   //      -> optimal tables -> quantize_trellis) are independent, so each step
   //      is ONE launch over all components of all images. ----
   if (pl.trellis) {
-    if (e->keep_plain) for (int ci = 0; ci < g.nc; ci++) CU(cudaMemcpyAsync(e->d_plain[ci].p, e->d_coef[ci].p, pl.coef_bytes[ci] * n, cudaMemcpyDeviceToDevice, s));
+    if (e->keep_plain) for (int ci = 0; ci < g.nc; ci++) CU(cudaMemcpyAsync(A.d_plain[ci].p, A.d_coef[ci].p, pl.coef_bytes[ci] * n, cudaMemcpyDeviceToDevice, s));
     const size_t hist_bytes_t = hist_bytes * g.nc;
-    DevHuff *tset = e->d_tabs_trellis.as<DevHuff>();                                       // [img*nc + ci][8]
+    DevHuff *tset = A.d_tabs_trellis.as<DevHuff>();                                       // [img*nc + ci][8]
     if (!pl.progressive) {
       tm.mark("trellis_stats");
-      CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes_t, s));
-      launch_gather_comp(g, e->d_hist.as<uint32_t>(), status, n, s);
+      CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes_t, s));
+      launch_gather_comp(g, A.d_hist.as<uint32_t>(), status, n, s);
       tm.mark("trellis_tables");
       SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = g.nc;
       for (int ci = 0; ci < g.nc; ci++) masks.m[ci] = (1u << g.c[ci].dc_tbl) | (1u << (4 + g.c[ci].ac_tbl));
-      launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tabset, masks, n * g.nc, s);
+      launch_gen_tables(A.d_hist.as<uint32_t>(), tset, tabset, masks, n * g.nc, s);
     } else {
       // jcphuff statistics with Ss=1..63, Al=0 (jcmaster.c:462-466), every AC symbol
       // pre-counted once (jcphuff.c:257-264); the DC table stays the supplied one.
@@ -363,23 +385,23 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
         ts.ncomps = 1; ts.ci[0] = ci; ts.Ss = 1; ts.Se = 63; ts.bim = 1; ts.k_count[0] = 1;
         ts.per_row = g.c[ci].wib; ts.rows = g.c[ci].hib; ts.nblocks = (long long)ts.per_row * ts.rows;
         tm.mark("trellis_stats");
-        CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes, s));
-        launch_seed_hist(e->d_hist.as<uint32_t>(), 4 + g.c[ci].ac_tbl, n, s);
-        launch_prog_prepare(g, ts, e->d_blk_aux.as<uint32_t>(), e->d_blk_run.as<uint32_t>(), n, s);
-        launch_gather_prog(g, ts, e->d_blk_aux.as<uint32_t>(), e->d_blk_run.as<uint32_t>(), e->d_hist.as<uint32_t>(), status, n, s);
+        CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
+        launch_seed_hist(A.d_hist.as<uint32_t>(), 4 + g.c[ci].ac_tbl, n, s);
+        launch_prog_prepare(g, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), n, s);
+        launch_gather_prog(g, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), A.d_hist.as<uint32_t>(), status, n, s);
         tm.mark("trellis_tables");
         SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = 1u << (4 + g.c[ci].ac_tbl);
-        launch_gen_tables(e->d_hist.as<uint32_t>(), tset + (size_t)ci * HIST_SLOTS, tabset * g.nc, masks, n, s);
+        launch_gen_tables(A.d_hist.as<uint32_t>(), tset + (size_t)ci * HIST_SLOTS, tabset * g.nc, masks, n, s);
       }
     }
     tm.mark("trellis_sort");
-    launch_sort_blocks(g, e->d_rec.as<DcRec>(), rl, e->d_perm.as<uint32_t>(), n, s);
+    launch_sort_blocks(g, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), n, s);
     tm.mark("trellis_ac");
-    launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, e->d_rec.as<DcRec>(), rl, e->d_perm.as<uint32_t>(), n, s);
+    launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), n, s);
     if (p->trellis_quant_dc) {
       tm.mark("trellis_dc");
-      if (pl.progressive) launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, e->d_rec.as<DcRec>(), e->d_bt.as<unsigned long long>(), rl, n, s);
-      else launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), tset, tabset, e->d_rec.as<DcRec>(), e->d_bt.as<unsigned long long>(), rl, n, s);
+      if (pl.progressive) launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rl, n, s);
+      else launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rl, n, s);
     }
     tm.mark("dummy");
     launch_dummy(g, n, s);
@@ -390,36 +412,36 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     const ScanDesc &sd = pl.scans[si];
     const DevHuff *tabs; size_t tstride;
     const bool dc_refine = pl.progressive && sd.Ss == 0 && sd.Ah != 0;
-    uint32_t *aux = e->d_blk_aux.as<uint32_t>(), *run_e = e->d_blk_run.as<uint32_t>();
+    uint32_t *aux = A.d_blk_aux.as<uint32_t>(), *run_e = A.d_blk_run.as<uint32_t>();
     if (pl.progressive && sd.Ss != 0) { tm.mark("eobrun_runs"); launch_prog_prepare(g, sd, aux, run_e, n, s); }
     if (pl.optimize) {
       DevHuff *tset = io.tabs_scan + (size_t)si * HIST_SLOTS;                              // [img][scan][8]
       tstride = tabset * nscans;
       if (!dc_refine) {                                                                    // jcmaster.c:650-662
         tm.mark("scan_stats");
-        CU(cudaMemsetAsync(e->d_hist.p, 0, hist_bytes, s));
-        if (pl.progressive) launch_gather_prog(g, sd, aux, run_e, e->d_hist.as<uint32_t>(), status, n, s);
-        else launch_gather_seq(g, sd, e->d_hist.as<uint32_t>(), status, n, s);
+        CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
+        if (pl.progressive) launch_gather_prog(g, sd, aux, run_e, A.d_hist.as<uint32_t>(), status, n, s);
+        else launch_gather_seq(g, sd, A.d_hist.as<uint32_t>(), status, n, s);
         tm.mark("scan_tables");
         SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = scan_slot_mask(pl, sd);
-        launch_gen_tables(e->d_hist.as<uint32_t>(), tset, tstride, masks, n, s);
+        launch_gen_tables(A.d_hist.as<uint32_t>(), tset, tstride, masks, n, s);
       }
       tabs = tset;
     } else { tabs = e->d_tabs_fixed.as<DevHuff>(); tstride = 0; }
     tm.mark("block_bits");
-    launch_block_bits(g, sd, tabs, tstride, pl.progressive, e->d_blk_bits.as<uint32_t>(), e->d_tile_bits.as<uint32_t>(), aux, run_e, status, n, s);
+    launch_block_bits(g, sd, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), aux, run_e, status, n, s);
     tm.mark("encode");
-    CU(cudaMemsetAsync(e->d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
-    launch_encode(g, sd, tabs, tstride, pl.progressive, e->d_blk_bits.as<uint32_t>(), e->d_tile_bits.as<uint32_t>(), aux, run_e,
-                  e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, e->d_total_bits.as<unsigned long long>(), status, n, s);
+    CU(cudaMemsetAsync(A.d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
+    launch_encode(g, sd, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), aux, run_e,
+                  A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_total_bits.as<unsigned long long>(), status, n, s);
     tm.mark("stuff");
-    launch_stuff(e->d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, e->d_total_bits.as<unsigned long long>(), e->d_ff_tile.as<uint32_t>(),
+    launch_stuff(A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_total_bits.as<unsigned long long>(), A.d_ff_tile.as<uint32_t>(),
                  io.out, e->out_cap_per_image, e->out_cap_per_image, io.out_pos + (size_t)si * n, io.out_pos + (size_t)(si + 1) * n,
                  io.scan_size + (size_t)si * n, status, n, s);
   }
   tm.mark("end");
   CU(cudaGetLastError());
-  e->last_chunk_i0 = io.i0; e->last_chunk_n = io.n;
+  e->last_chunk_i0 = io.i0; e->last_chunk_n = io.n; e->last_chunk_slot = io.slot;
   return B200JPEG_OK;
 }
 
@@ -586,7 +608,7 @@ static uint8_t *arena_alloc(b200jpeg_encoder *e, size_t size)
 // Queue the read-back of chunk k's metadata (status, sizes, DHT payloads) behind its pipeline.
 static int queue_meta(b200jpeg_encoder *e, const ChunkIO &io, int k)
 {
-  Plan &pl = e->plan; cudaStream_t s = e->stream;
+  Plan &pl = e->plan; cudaStream_t s = e->sc[io.slot];
   const int nscans = (int)pl.scans.size();
   CU(cudaMemcpyAsync(e->h_status.as<uint32_t>() + io.i0, io.status, (size_t)io.n * 4, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(e->h_out_pos.as<unsigned long long>() + io.i0, io.out_pos + (size_t)nscans * io.n, (size_t)io.n * 8, cudaMemcpyDeviceToHost, s));
@@ -703,11 +725,14 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
     if ((rc = e->h_tabs.reserve((pl.optimize ? (size_t)n_images * nscans : 1) * HIST_SLOTS * sizeof(HostHuff)))) return rc;
   }
   Timer tm{e};
+  const int nstreams = (nchunks > 1 && e->n_streams > 1) ? 2 : 1;
+  e->sc[0] = e->stream;
   for (int attempt = 0; attempt < 6; attempt++) {
     tm.idx = 0;
-    if ((rc = prepare_batch(e, n_images, C, !on_device, src_bytes))) return rc;
+    if ((rc = prepare_batch(e, n_images, C, !on_device, src_bytes, nstreams))) return rc;
     CU(cudaMemsetAsync(e->d_status.p, 0, (size_t)n_images * 4, e->stream));
     CU(cudaMemsetAsync(e->d_out_pos.p, 0, (size_t)n_images * (nscans + 1) * 8, e->stream));
+    if (nstreams > 1) { CU(cudaEventRecord(e->ev_fork, e->stream)); CU(cudaStreamWaitEvent(e->sc[1], e->ev_fork, 0)); }
     // stage every chunk's pixels up front on the copy stream; chunk k's kernels wait only for chunk k
     const uint8_t *src_base = static_cast<const uint8_t *>(pixels);
     if (!on_device) {
@@ -731,13 +756,14 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
     for (int k = 0; k < nchunks && rc == B200JPEG_OK; k++) {
       ChunkIO io;
       io.i0 = k * C; io.n = std::min(C, n_images - io.i0);
+      io.slot = k % nstreams;
       io.src = src_base + (size_t)io.i0 * image_stride;
       io.out = e->d_out.as<uint8_t>() + (size_t)io.i0 * e->out_cap_per_image;
       io.out_pos = e->d_out_pos.as<unsigned long long>() + (size_t)io.i0 * (nscans + 1);
       io.status = e->d_status.as<uint32_t>() + io.i0;
       io.scan_size = e->d_scan_size.as<uint32_t>() + (size_t)io.i0 * nscans;
       io.tabs_scan = e->d_tabs_scan.as<DevHuff>() + (size_t)io.i0 * nscans * HIST_SLOTS;
-      if (!on_device) { tm.mark("h2d_wait"); CU(cudaStreamWaitEvent(e->stream, e->ev_in[k], 0)); }
+      if (!on_device) { tm.s = e->sc[io.slot]; tm.mark("h2d_wait"); CU(cudaStreamWaitEvent(e->sc[io.slot], e->ev_in[k], 0)); }
       if ((rc = run_pipeline(e, io, tm))) break;
       if (!device_only) {
         if ((rc = queue_meta(e, io, k))) break;
@@ -746,6 +772,8 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
       }
     }
     if (rc == B200JPEG_OK && !device_only && have_prev) rc = finish_chunk(e, prev, nchunks - 1);
+    // the second stream joins the caller-visible one
+    if (nstreams > 1) { cudaEventRecord(e->ev_join, e->sc[1]); cudaStreamWaitEvent(e->stream, e->ev_join, 0); }
     if (rc < 0) { cudaStreamSynchronize(e->stream); cudaStreamSynchronize(e->s_in); cudaStreamSynchronize(e->s_out); return rc; }
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaStreamSynchronize(e->s_in));
@@ -765,7 +793,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   // per-stage device times (CUDA events on the encoder's stream), summed by stage name over the chunks
   e->stage_names.clear(); e->stage_ms.clear(); e->stage_calls.clear();
   for (size_t i = 0; i + 1 < tm.idx; i++) {
-    if (!strcmp(e->ev_names[i], "end")) continue;
+    if (!strcmp(e->ev_names[i], "end")) continue;           // (with two streams the intervals of concurrent chunks overlap)
     float ms = 0.f; cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]);
     size_t k = 0;
     for (; k < e->stage_names.size(); k++) if (!strcmp(e->stage_names[k], e->ev_names[i])) break;
@@ -793,12 +821,18 @@ int b200jpeg_encoder_create(b200jpeg_encoder **enc, int device)
   cudaError_t e2 = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking);
   if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&o->s_in, cudaStreamNonBlocking);
   if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&o->s_out, cudaStreamNonBlocking);
+  if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&o->sc[1], cudaStreamNonBlocking);
+  if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming);
+  if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming);
+  o->sc[0] = o->stream;
   if (e2 != cudaSuccess) { set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e2)); delete o; return B200JPEG_ERR_CUDA; }
   o->launches_at_create = g_kernel_launches;
   const char *dbg = getenv("B200JPEG_KEEP_PLAIN");
   o->keep_plain = dbg && dbg[0] == '1';
   const char *ch = getenv("B200JPEG_CHUNK_IMAGES");
   if (ch) o->chunk_images_override = atoi(ch);
+  const char *ns = getenv("B200JPEG_STREAMS");
+  if (ns) o->n_streams = atoi(ns) > 1 ? 2 : 1;
   *enc = o;
   return B200JPEG_OK;
 }
@@ -810,10 +844,10 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
   cudaStreamSynchronize(e->stream);
   if (e->s_in) cudaStreamSynchronize(e->s_in);
   if (e->s_out) cudaStreamSynchronize(e->s_out);
-  DevBuf *db[] = {&e->d_src, &e->d_hist, &e->d_tabs_scan, &e->d_tabs_trellis, &e->d_tabs_fixed, &e->d_rec, &e->d_bt, &e->d_perm, &e->d_blk_bits, &e->d_tile_bits, &e->d_ff_tile, &e->d_blk_aux, &e->d_blk_run,
-                  &e->d_total_bits, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_bitbuf, &e->d_out, &e->d_qt, &e->d_tc};
+  if (e->sc[1]) cudaStreamSynchronize(e->sc[1]);
+  DevBuf *db[] = {&e->d_src, &e->d_tabs_scan, &e->d_tabs_fixed, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_out, &e->d_qt, &e->d_tc};
   for (DevBuf *b : db) b->release();
-  for (int i = 0; i < 4; i++) { e->d_coef[i].release(); e->d_raw[i].release(); e->d_plain[i].release(); }
+  e->ar[0].release(); e->ar[1].release();
   PinBuf *pb[] = {&e->h_qt, &e->h_tc, &e->h_fixed, &e->h_status, &e->h_out_pos, &e->h_scan_size, &e->h_tabs, &e->h_stage};
   for (PinBuf *b : pb) b->release();
   for (PinBuf &b : e->file_arenas) b.release();
@@ -823,7 +857,17 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
   if (e->own_stream) cudaStreamDestroy(e->stream);
   if (e->s_in) cudaStreamDestroy(e->s_in);
   if (e->s_out) cudaStreamDestroy(e->s_out);
+  if (e->sc[1]) cudaStreamDestroy(e->sc[1]);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   delete e;
+}
+
+int b200jpeg_encoder_set_streams(b200jpeg_encoder *e, int n_streams)
+{
+  if (!e || n_streams < 1 || n_streams > 2) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  e->n_streams = n_streams;
+  return B200JPEG_OK;
 }
 
 int b200jpeg_encoder_set_chunk_images(b200jpeg_encoder *e, int images_per_chunk)
@@ -840,6 +884,7 @@ int b200jpeg_encoder_set_stream(b200jpeg_encoder *e, void *cuda_stream)
   CU(cudaStreamSynchronize(e->stream));
   if (e->own_stream) cudaStreamDestroy(e->stream);
   e->stream = static_cast<cudaStream_t>(cuda_stream);
+  e->sc[0] = e->stream;
   e->own_stream = false;
   return B200JPEG_OK;
 }
@@ -886,8 +931,9 @@ long b200jpeg_debug_get_coefs(b200jpeg_encoder *e, int image, int component, int
   size_t nb = (size_t)c.blocks_per_image;
   if (!dst) return (long)nb;
   if (dst_blocks < nb) { set_error("buffer too small"); return B200JPEG_ERR_BUFFER; }
-  DevBuf *src = plane == 0 ? &e->d_coef[component] : plane == 1 ? &e->d_raw[component] : &e->d_plain[component];
-  if (plane == 2 && !(e->keep_plain && e->plan.trellis)) src = &e->d_coef[component];
+  Arena &A = e->ar[e->last_chunk_slot];
+  DevBuf *src = plane == 0 ? &A.d_coef[component] : plane == 1 ? &A.d_raw[component] : &A.d_plain[component];
+  if (plane == 2 && !(e->keep_plain && e->plan.trellis)) src = &A.d_coef[component];
   if (!src->p) { set_error("plane not available"); return B200JPEG_ERR_STATE; }
   std::vector<int16_t> tmp(nb * 64);
   CU(cudaSetDevice(e->device));
@@ -906,7 +952,7 @@ int b200jpeg_debug_get_huff(b200jpeg_encoder *e, int image, int scan, int is_ac,
     int ci = -1 - scan;
     if (ci >= e->plan.g.nc) { set_error("bad component"); return B200JPEG_ERR_PARAM; }
     if (image < e->last_chunk_i0 || image >= e->last_chunk_i0 + e->last_chunk_n) { set_error("image %d is not in the last chunk of the batch", image); return B200JPEG_ERR_STATE; }
-    CU(cudaMemcpy(&h, e->d_tabs_trellis.as<DevHuff>() + ((size_t)(image - e->last_chunk_i0) * e->plan.g.nc + ci) * HIST_SLOTS + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&h, e->ar[e->last_chunk_slot].d_tabs_trellis.as<DevHuff>() + ((size_t)(image - e->last_chunk_i0) * e->plan.g.nc + ci) * HIST_SLOTS + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));
   } else {
     if (scan >= nscans) { set_error("bad scan"); return B200JPEG_ERR_PARAM; }
     if (e->plan.optimize) CU(cudaMemcpy(&h, e->d_tabs_scan.as<DevHuff>() + ((size_t)image * nscans + scan) * HIST_SLOTS + (is_ac ? 4 : 0) + tbl_no, sizeof h, cudaMemcpyDeviceToHost));
