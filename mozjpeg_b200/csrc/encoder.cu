@@ -211,6 +211,13 @@ static void make_quant_consts(const b200jpeg_params *p, QuantTables *qt)
       QuantConst &q = qt->q[t][i];
       q.mul = (uint32_t)m; q.shift = (uint16_t)k; q.bias = d / 2; q.d = d; q.pad = 0;
     }
+    // one shift for the whole table: L >= log2 of every divisor, mul2 = ceil(2^(18+L)/d) must fit 32 bits
+    unsigned dmax = 1, dmin = ~0u;
+    for (int i = 0; i < 64; i++) { unsigned d = 8u * p->quant_tbl[t][i]; dmax = std::max(dmax, d); dmin = std::min(dmin, d); }
+    int L = 0; while ((1ull << L) < dmax) L++;
+    qt->L[t] = L;
+    qt->fast[t] = (((1ull << (18 + L)) + dmin - 1) / dmin) < (1ull << 32) ? 1 : 0;
+    for (int i = 0; i < 64; i++) { unsigned d = qt->q[t][i].d; qt->q[t][i].mul2 = qt->fast[t] ? (uint32_t)(((1ull << (18 + L)) + d - 1) / d) : 0; }
   }
 }
 static void make_trellis_consts(const b200jpeg_params *p, TrellisConsts *tc)
@@ -357,7 +364,8 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   RecLayout rl; memset(&rl, 0, sizeof rl);
   for (int ci = 0; ci < g.nc; ci++) { rl.comp_off[ci] = rl.per_image; rl.per_image += (long long)g.c[ci].wib * g.c[ci].hib; }
   tm.mark("forward");
-  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, n, s);
+  int qfast = 1; for (int ci = 0; ci < g.nc; ci++) qfast &= e->h_qt.as<QuantTables>()->fast[g.c[ci].qt];
+  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), qfast, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, n, s);
   tm.mark("dummy");
   launch_dummy(g, n, s);
 

@@ -28,6 +28,9 @@ __constant__ uint8_t c_izz[64] = {
   X(32,35) X(33,42) X(34,49) X(35,56) X(36,57) X(37,50) X(38,43) X(39,36) X(40,29) X(41,22) X(42,15) X(43,23) X(44,30) X(45,37) X(46,44) X(47,51) \
   X(48,58) X(49,59) X(50,52) X(51,45) X(52,38) X(53,31) X(54,39) X(55,46) X(56,53) X(57,60) X(58,61) X(59,54) X(60,47) X(61,55) X(62,62) X(63,63)
 
+// natural index n (1..63) -> zigzag position, in natural order
+#define NAT_LIST Y(1,1) Y(2,5) Y(3,6) Y(4,14) Y(5,15) Y(6,27) Y(7,28) Y(8,2) Y(9,4) Y(10,7) Y(11,13) Y(12,16) Y(13,26) Y(14,29) Y(15,42) Y(16,3) Y(17,8) Y(18,12) Y(19,17) Y(20,25) Y(21,30) Y(22,41) Y(23,43) Y(24,9) Y(25,11) Y(26,18) Y(27,24) Y(28,31) Y(29,40) Y(30,44) Y(31,53) Y(32,10) Y(33,19) Y(34,23) Y(35,32) Y(36,39) Y(37,45) Y(38,52) Y(39,54) Y(40,20) Y(41,22) Y(42,33) Y(43,38) Y(44,46) Y(45,51) Y(46,55) Y(47,60) Y(48,21) Y(49,34) Y(50,37) Y(51,47) Y(52,50) Y(53,56) Y(54,59) Y(55,61) Y(56,35) Y(57,36) Y(58,48) Y(59,49) Y(60,57) Y(61,58) Y(62,62) Y(63,63)
+
 __device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(v); }   // v >= 0 ; JPEG_NBITS (jpeg_nbits.h)
 
 // =====================================================================
@@ -223,7 +226,42 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
 //   E. coalesced 16-byte stores of whole 128-byte blocks.
 // Same arithmetic as k_forward (the generic one-thread-per-block kernel).
 // =====================================================================
-template <int HMAX, int VMAX, int NC>
+// One row of 8 pixels of the strip (24 bytes for RGB, 8 for grey) in registers.
+struct Px8 { unsigned w[6]; };
+template <int IC>
+__device__ __forceinline__ Px8 load_px8(const uint8_t *__restrict__ base, size_t row_pitch, int iy, int x, int W, bool fast)
+{
+  Px8 r;
+  const uint8_t *row = base + (size_t)iy * row_pitch;
+  if (fast) {                                     // 8-byte aligned, fully inside the image
+    const uint2 *p = reinterpret_cast<const uint2 *>(row + (size_t)x * IC);
+    if (IC == 3) { uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2); r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y; r.w[4] = c.x; r.w[5] = c.y; }
+    else { uint2 a = __ldg(p); r.w[0] = a.x; r.w[1] = a.y; r.w[2] = r.w[3] = r.w[4] = r.w[5] = 0; }
+  } else {                                        // right edge / unaligned: bytes, columns clamped to W-1 (expand_right_edge)
+#pragma unroll
+    for (int i = 0; i < 6; i++) r.w[i] = 0;
+#pragma unroll
+    for (int b = 0; b < 8 * IC; b++) {
+      int px = b / IC, ch = b - px * IC;
+      int ix = min(x + px, W - 1);
+      r.w[b >> 2] |= (unsigned)row[(size_t)ix * IC + ch] << (8 * (b & 3));
+    }
+  }
+  return r;
+}
+template <int IC>
+__device__ __forceinline__ int px_byte(const Px8 &r, int px, int ch) { int b = px * IC + ch; return (int)((r.w[b >> 2] >> (8 * (b & 3))) & 0xFFu); }
+
+// exact floor((|x| + d/2) / d) * sign(x) with the per-table uniform shift (QuantTables.fast) or the general 64-bit form
+__device__ __forceinline__ int quant_fast(int x, uint2 k, int L, int dering)
+{
+  unsigned a14 = (unsigned)abs(x) * 16384u + k.y;            // (|x| + d/2) << 14   (< 2^32)
+  int q = (int)(__umulhi(a14, k.x) >> L);
+  if (dering) q = min(q, 1023);                              // (1 << (8 + 2)) - 1
+  return x < 0 ? -q : q;
+}
+
+template <int HMAX, int VMAX, int NC, bool QFAST>
 __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *__restrict__ src,
                                                       const QuantTables *__restrict__ qt, int dering,
                                                       DcRec *__restrict__ rec, RecLayout rl)
@@ -233,74 +271,87 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   constexpr int CW = TW / HMAX, CBW = CW / 8;            // chroma samples / blocks per tile row
   constexpr int NB = YB + (NC == 3 ? 2 * CBW : 0);
   constexpr int YP = TW + 8, CP = CW + 8;                // padded plane pitches (int16 elements)
+  constexpr int IC = NC == 3 ? 3 : 1;                    // bytes per input pixel on the fast path (grey from RGB: see below)
   __shared__ __align__(16) int16_t sY[TR * YP];
   __shared__ __align__(16) int16_t sC[NC == 3 ? 2 * 8 * CP : 8];
   __shared__ __align__(16) int16_t sW[NB * 72];
-  __shared__ __align__(16) unsigned char sIO[NB * 256];   // phase A: RGB strip; phases D/E: output staging
-  static_assert(NB * 256 >= TR * TW * 3, "staging buffer too small for the RGB strip");
+  __shared__ __align__(16) unsigned char sIO[NB * 256];   // phases D/E: output staging
+  __shared__ uint2 sQC[NC][64];                           // quantizer constants per component, natural order
+  __shared__ int sQL[NC];
 
   const int tid = threadIdx.x;
   const int tx = blockIdx.x, ty = blockIdx.y, img = blockIdx.z;
   const int x0 = tx * TW, y0 = ty * TR;
   const uint8_t *base = src + (size_t)img * g.image_stride;
-  const int ic = g.in_comps;
 
-  // ---- A: load the strip (rows clamped to H-1, columns clamped to W-1) ----
-  uint8_t *sRGB = sIO;
+  for (int i = tid; i < NC * 64; i += 128) { int ci = i >> 6, n = i & 63; const QuantConst &k = qt->q[g.c[ci].qt][n]; sQC[ci][n] = make_uint2(k.mul2, k.bias << 14); }
+  if (tid < NC) sQL[tid] = qt->L[g.c[tid].qt];
+
+  // ---- A+B: thread (row group rg, segment seg) converts VMAX rows x 8 pixels straight from global memory:
+  //      colour conversion (jccolext.c:30-75) + box downsampling (jcsample.c) into centred int16 planes ----
   {
-    const int rowbytes = TW * ic;
-    const bool full = (x0 + TW <= g.W) && ((g.row_pitch & 15) == 0) && ((((size_t)base) & 15) == 0) && (((size_t)x0 * ic & 15) == 0);
-    if (full) {
-      const int vec_per_row = rowbytes / 16;
-      for (int i = tid; i < TR * vec_per_row; i += 128) {
-        int r = i / vec_per_row, v = i - r * vec_per_row;
-        int iy = min(y0 + r, g.H - 1);
-        const uint4 *p = reinterpret_cast<const uint4 *>(base + (size_t)iy * g.row_pitch + (size_t)x0 * ic) + v;
-        reinterpret_cast<uint4 *>(sRGB + r * rowbytes)[v] = __ldg(p);
+    const int rg = tid >> 4, seg = tid & 15;
+    const int xs = x0 + seg * 8;
+    const bool grey_from_rgb = NC == 1 && g.cs_mode == 1;
+    const bool fast = (xs + 8 <= g.W) && ((g.row_pitch & 7) == 0) && ((((size_t)base) & 7) == 0) && !grey_from_rgb;
+    if (NC == 1 && grey_from_rgb) {
+      // RGB input, grayscale output: 3 bytes per pixel, luma only
+#pragma unroll
+      for (int rr = 0; rr < VMAX; rr++) {
+        const int iy = min(y0 + rg * VMAX + rr, g.H - 1);
+        const bool f3 = (xs + 8 <= g.W) && ((g.row_pitch & 7) == 0) && ((((size_t)base) & 7) == 0);
+        Px8 p = load_px8<3>(base, g.row_pitch, iy, xs, g.W, f3);
+        int16_t yv[8];
+#pragma unroll
+        for (int px = 0; px < 8; px++) yv[px] = (int16_t)(((19595 * px_byte<3>(p, px, 0) + 38470 * px_byte<3>(p, px, 1) + 7471 * px_byte<3>(p, px, 2) + 32768) >> 16) - 128);
+        *reinterpret_cast<uint4 *>(&sY[(rg * VMAX + rr) * YP + seg * 8]) = *reinterpret_cast<const uint4 *>(yv);
       }
     } else {
-      for (int i = tid; i < TR * rowbytes; i += 128) {
-        int r = i / rowbytes, b = i - r * rowbytes;
-        int px = b / ic, ch = b - px * ic;
-        int iy = min(y0 + r, g.H - 1), ix = min(x0 + px, g.W - 1);
-        sRGB[i] = base[(size_t)iy * g.row_pitch + (size_t)ix * ic + ch];
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- B: colour conversion + downsampling into centred int16 planes ----
-#pragma unroll 2
-  for (int i = tid; i < TR * TW; i += 128) {
-    int r = i / TW, x = i - r * TW;
-    const uint8_t *px = sRGB + (r * TW + x) * ic;
-    int yv = (g.cs_mode == 2) ? px[0] : (19595 * px[0] + 38470 * px[1] + 7471 * px[2] + 32768) >> 16;
-    sY[r * YP + x] = (int16_t)(yv - 128);
-  }
-  if (NC == 3) {
-    const CompGeom &cc = g.c[1];
-    // chroma rows past the last real row group replicate the last real chroma row (jcprepct.c:167-179)
-    const int last_real = cc.rows_avail - 1 - ty * 8;
-#pragma unroll 1
-    for (int i = tid; i < 8 * CW; i += 128) {
-      int cr = i / CW, cx = i - cr * CW;
-      int er = min(cr, last_real);
-      int sb = 0, sr = 0;
+      int sb[8 / HMAX], sr[8 / HMAX];
 #pragma unroll
-      for (int dv = 0; dv < VMAX; dv++)
+      for (int i = 0; i < 8 / HMAX; i++) { sb[i] = 0; sr[i] = 0; }
+      // chroma rows past the last real row group replicate the last real chroma row (jcprepct.c:167-179)
+      const int last_real = NC == 3 ? g.c[1].rows_avail - 1 - ty * 8 : 8;
+      const int er = min(rg, last_real);
 #pragma unroll
-        for (int du = 0; du < HMAX; du++) {
-          const uint8_t *px = sRGB + ((er * VMAX + dv) * TW + cx * HMAX + du) * 3;
-          int R = px[0], G = px[1], B = px[2];
-          sb += (-11059 * R - 21709 * G + 32768 * B + (128 << 16) + 32767) >> 16;
-          sr += (32768 * R - 27439 * G - 5329 * B + (128 << 16) + 32767) >> 16;
+      for (int rr = 0; rr < VMAX; rr++) {
+        const int iy = min(y0 + rg * VMAX + rr, g.H - 1);
+        Px8 p = load_px8<IC>(base, g.row_pitch, iy, xs, g.W, fast);
+        int16_t yv[8];
+#pragma unroll
+        for (int px = 0; px < 8; px++) {
+          if (NC == 1) yv[px] = (int16_t)(px_byte<1>(p, px, 0) - 128);
+          else {
+            const int R = px_byte<3>(p, px, 0), G = px_byte<3>(p, px, 1), B = px_byte<3>(p, px, 2);
+            yv[px] = (int16_t)(((19595 * R + 38470 * G + 7471 * B + 32768) >> 16) - 128);
+          }
         }
-      int xo = x0 / HMAX + cx;
-      if (HMAX == 2 && VMAX == 1) { sb = (sb + (xo & 1)) >> 1; sr = (sr + (xo & 1)) >> 1; }
-      else if (HMAX == 2 && VMAX == 2) { sb = (sb + 1 + (xo & 1)) >> 2; sr = (sr + 1 + (xo & 1)) >> 2; }
-      else if (HMAX * VMAX > 1) { sb = (sb + HMAX * VMAX / 2) / (HMAX * VMAX); sr = (sr + HMAX * VMAX / 2) / (HMAX * VMAX); }
-      sC[cr * CP + cx] = (int16_t)(sb - 128);
-      sC[8 * CP + cr * CP + cx] = (int16_t)(sr - 128);
+        *reinterpret_cast<uint4 *>(&sY[(rg * VMAX + rr) * YP + seg * 8]) = *reinterpret_cast<const uint4 *>(yv);
+        if (NC == 3) {
+          if (er != rg) p = load_px8<IC>(base, g.row_pitch, min(y0 + er * VMAX + rr, g.H - 1), xs, g.W, fast);
+#pragma unroll
+          for (int px = 0; px < 8; px++) {
+            const int R = px_byte<3>(p, px, 0), G = px_byte<3>(p, px, 1), B = px_byte<3>(p, px, 2);
+            sb[px / HMAX] += (-11059 * R - 21709 * G + 32768 * B + (128 << 16) + 32767) >> 16;
+            sr[px / HMAX] += (32768 * R - 27439 * G - 5329 * B + (128 << 16) + 32767) >> 16;
+          }
+        }
+      }
+      if (NC == 3) {
+        int16_t cbv[8 / HMAX], crv[8 / HMAX];
+#pragma unroll
+        for (int i = 0; i < 8 / HMAX; i++) {
+          const int xo = x0 / HMAX + seg * (8 / HMAX) + i;
+          int b = sb[i], r = sr[i];
+          if (HMAX == 2 && VMAX == 1) { b = (b + (xo & 1)) >> 1; r = (r + (xo & 1)) >> 1; }                      // jcsample.c:226-254
+          else if (HMAX == 2 && VMAX == 2) { b = (b + 1 + (xo & 1)) >> 2; r = (r + 1 + (xo & 1)) >> 2; }         // jcsample.c:263-295
+          else if (HMAX * VMAX > 1) { b = (b + HMAX * VMAX / 2) / (HMAX * VMAX); r = (r + HMAX * VMAX / 2) / (HMAX * VMAX); }   // jcsample.c:151-190
+          cbv[i] = (int16_t)(b - 128); crv[i] = (int16_t)(r - 128);
+        }
+        int16_t *cb = &sC[rg * CP + seg * (8 / HMAX)], *cr = &sC[8 * CP + rg * CP + seg * (8 / HMAX)];
+        if (HMAX == 1) { *reinterpret_cast<uint4 *>(cb) = *reinterpret_cast<const uint4 *>(cbv); *reinterpret_cast<uint4 *>(cr) = *reinterpret_cast<const uint4 *>(crv); }
+        else { *reinterpret_cast<uint2 *>(cb) = *reinterpret_cast<const uint2 *>(cbv); *reinterpret_cast<uint2 *>(cr) = *reinterpret_cast<const uint2 *>(crv); }
+      }
     }
   }
   __syncthreads();
@@ -313,7 +364,9 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
     if (b < YB) { plane = sY; pitch = YP; byl = b / YBW; bx = b - byl * YBW; }
     else { int cb = b - YB; int which = cb / CBW; plane = sC + which * 8 * CP; pitch = CP; byl = 0; bx = cb - which * CBW; }
     int16_t *rowp = plane + (byl * 8 + j) * pitch + bx * 8;
-    int d0 = rowp[0], d1 = rowp[1], d2 = rowp[2], d3 = rowp[3], d4 = rowp[4], d5 = rowp[5], d6 = rowp[6], d7 = rowp[7];
+    const uint4 rv = *reinterpret_cast<const uint4 *>(rowp);
+    int d0 = (int)(int16_t)(rv.x & 0xFFFF), d1 = (int)rv.x >> 16, d2 = (int)(int16_t)(rv.y & 0xFFFF), d3 = (int)rv.y >> 16;
+    int d4 = (int)(int16_t)(rv.z & 0xFFFF), d5 = (int)rv.z >> 16, d6 = (int)(int16_t)(rv.w & 0xFFFF), d7 = (int)rv.w >> 16;
     if (dering) {
       int sum = d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7;
       int cnt = (d0 >= 127) + (d1 >= 127) + (d2 >= 127) + (d3 >= 127) + (d4 >= 127) + (d5 >= 127) + (d6 >= 127) + (d7 >= 127);
@@ -330,48 +383,57 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
       }
     }
     fdct_1d<0>(d0, d1, d2, d3, d4, d5, d6, d7);
-    int16_t *w = sW + b * 72 + j * 8;
-    w[0] = (int16_t)d0; w[1] = (int16_t)d1; w[2] = (int16_t)d2; w[3] = (int16_t)d3;
-    w[4] = (int16_t)d4; w[5] = (int16_t)d5; w[6] = (int16_t)d6; w[7] = (int16_t)d7;
+    uint4 wv;
+    wv.x = ((unsigned)d0 & 0xFFFFu) | ((unsigned)d1 << 16); wv.y = ((unsigned)d2 & 0xFFFFu) | ((unsigned)d3 << 16);
+    wv.z = ((unsigned)d4 & 0xFFFFu) | ((unsigned)d5 << 16); wv.w = ((unsigned)d6 & 0xFFFFu) | ((unsigned)d7 << 16);
+    *reinterpret_cast<uint4 *>(sW + b * 72 + j * 8) = wv;
   }
   __syncthreads();
 
   // ---- D: column pass + quantize; lane j owns column j; zigzag placement in the staging buffer.
-  //      With the trellis on, the same 8 lanes also produce the block's side record: the raw
-  //      coefficients go back to sW in natural order (each lane rewrites exactly the words it
-  //      read), lane r then owns ROW r and the serial fp32 sum of squares in NATURAL order
-  //      (jcdctmgr.c:1026-1029) is handed from lane to lane, 8 adds per hop. ----
+  //      With the trellis on, the 8 lanes also OR together the zigzag positions of the block's
+  //      non-zero plain-quantized AC values for the side record (the trellis kernel finds its
+  //      entries from that mask). ----
   int16_t *sQ = reinterpret_cast<int16_t *>(sIO);              // [NB][64] quantized, then [NB][64] raw
   int16_t *sR = sQ + NB * 64;
   static_assert(NB % 16 == 0, "whole warps walk the block list in step");
+  // zigzag positions of this lane's 8 coefficients (natural index 8r + j)
+  int kz[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) kz[r] = c_izz[8 * r + j];
 #pragma unroll 1
   for (int b = tid >> 3; b < NB; b += 16) {
-    int16_t *w = sW + b * 72 + j;
+    const int16_t *w = sW + b * 72 + j;
     int d0 = w[0], d1 = w[8], d2 = w[16], d3 = w[24], d4 = w[32], d5 = w[40], d6 = w[48], d7 = w[56];
     fdct_1d<1>(d0, d1, d2, d3, d4, d5, d6, d7);
     const int ci = b < YB ? 0 : (1 + (b - YB) / CBW);
-    const QuantConst *qc = qt->q[g.c[ci].qt];
-    int dd[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
+    const int dd[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
+    const int L = sQL[NC == 1 ? 0 : ci];
     unsigned mlo = 0, mhi = 0;                                 // zigzag positions of this lane's non-zero AC values
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      int nat = 8 * r + j;
-      int k = c_izz[nat];
-      int16_t qv = (int16_t)quant_one(dd[r], qc[nat], dering);
-      sQ[b * 64 + k] = qv;
+      const int nat = 8 * r + j;
+      const int k = kz[r];
+      int qv;
+      if (QFAST) qv = quant_fast(dd[r], sQC[NC == 1 ? 0 : ci][nat], L, dering);
+      else qv = (int)(int16_t)quant_one(dd[r], qt->q[g.c[ci].qt][nat], dering);
+      sQ[b * 64 + k] = (int16_t)qv;
       sR[b * 64 + k] = (int16_t)dd[r];
       if (qv != 0 && nat != 0) { if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
     }
     if (rec) {
+      // the raw coefficients go back to sW in natural order (each lane rewrites exactly the words it
+      // read), lane r then owns ROW r and the serial fp32 sum of squares in NATURAL order
+      // (jcdctmgr.c:1026-1029) is handed from lane to lane, 8 adds per hop
+      int16_t *ww = sW + b * 72 + j;
 #pragma unroll
-      for (int r = 0; r < 8; r++) w[8 * r] = (int16_t)dd[r];
+      for (int r = 0; r < 8; r++) ww[8 * r] = (int16_t)dd[r];
       __syncwarp();
       const int4 rowv = *reinterpret_cast<const int4 *>(sW + b * 72 + 8 * j);
       const int pw[4] = {rowv.x, rowv.y, rowv.z, rowv.w};
       float sq[8];
 #pragma unroll
       for (int cidx = 0; cidx < 8; cidx++) { int v = (int)(int16_t)((unsigned)pw[cidx >> 1] >> ((cidx & 1) * 16)); sq[cidx] = (float)(v * v); }
-      const int raw_dc = (int)(int16_t)((unsigned)pw[0] & 0xFFFFu);           // meaningful in lane 0
       float norm = 0.0f;
       const int gbase = (tid & 31) & ~7;
 #pragma unroll
@@ -389,7 +451,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
       else { int cb = b - YB; int which = cb / CBW; row = ty; col = tx * CBW + (cb - which * CBW); }
       const CompGeom &c = g.c[ci];
       if (j == 0 && row < c.hib && col < c.wib) {
-        DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)raw_dc; rr.nz = (uint8_t)(__popc(mlo) + __popc(mhi)); rr.pad = 0;
+        DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)dd[0]; rr.nz = (uint8_t)(__popc(mlo) + __popc(mhi)); rr.pad = 0;
         rr.nzmask = ((unsigned long long)mhi << 32) | mlo;
         rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * c.wib + col] = rr;
       }
@@ -411,7 +473,17 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   }
 }
 
-void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s)
+template <bool QFAST>
+static void launch_forward_tile(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s, bool gray)
+{
+  dim3 grid((g.W + 127) / 128, g.mcu_rows, n);
+  if (gray) k_forward_tile<1, 1, 1, QFAST><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+  else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3, QFAST><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+  else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3, QFAST><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+  else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3, QFAST><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+  else k_forward_tile<2, 2, 3, QFAST><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+}
+void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s)
 {
   // fast path: full-size first component, (for colour) two 1x1-sampled chroma components
   bool gray = g.nc == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
@@ -419,12 +491,8 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
              g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
   static const bool force_generic = getenv("B200JPEG_GENERIC_FORWARD") != nullptr;   // A/B switch for debugging
   if (!force_generic && ((gray && g.hmax == 1 && g.vmax == 1) || ycc)) {
-    dim3 grid((g.W + 127) / 128, g.mcu_rows, n);
-    if (gray) k_forward_tile<1, 1, 1><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
-    else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
-    else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
-    else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
-    else k_forward_tile<2, 2, 3><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+    if (qfast) launch_forward_tile<true>(g, src, qt, dering, rec, rl, n, s, gray);
+    else launch_forward_tile<false>(g, src, qt, dering, rec, rl, n, s, gray);
     LAUNCHED();
     return;
   }

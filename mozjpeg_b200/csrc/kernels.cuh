@@ -51,8 +51,10 @@ struct ScanDesc {
 
 // quantizer constants per (table, natural index): exact floor((a + bias)/d)
 // by multiply-shift (d = 8*Q, a < 2^18), see encoder.cu make_quant_consts().
-struct QuantConst { uint32_t mul; uint16_t shift; uint16_t pad; uint32_t bias; uint32_t d; };
-struct QuantTables { QuantConst q[4][64]; };                 // natural order
+// general form: q = ((|x| + bias) * mul) >> shift (64-bit product);  fast form (QuantTables.fast[t]): one shift
+// L[t] for the whole table, q = umulhi((|x| + bias) << 14, mul2) >> L[t]  -- both exact for |x| + bias < 2^18.
+struct QuantConst { uint32_t mul; uint16_t shift; uint16_t pad; uint32_t bias; uint32_t d; uint32_t mul2; };
+struct QuantTables { QuantConst q[4][64]; int L[4]; int fast[4]; };                 // natural order
 struct TrellisConsts {
   float w_zz[4][64];      // (float)(1.0/(Q*Q)) per zigzag position   jcdctmgr.c:1017-1021
   int   q8_zz[4][64];     // 8*Q per zigzag position
@@ -91,7 +93,7 @@ struct SlotMasks { uint32_t m[4]; int period; };
 
 // ---------------------------------------------------------------- launches (defined in kernels.cu)
 // status[img] bits: 2 = JERR_BAD_DCT_COEF / missing Huffman code, 4 = output buffer too small (host retries)
-void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s);
+void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s);
 void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, int n, cudaStream_t s);
 void launch_dummy(const Geom &g, int n, cudaStream_t s);
 void launch_gather_comp(const Geom &g, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
