@@ -249,6 +249,7 @@ def main():
     step_resident()
     torch.cuda.synchronize()
     stage_acc = {k: v * a.steps for k, v in enc.stage_times().items()}
+    resident_chunk = enc.chunk_images()
     enc.set_streams(2)
     clk = clocks.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -280,7 +281,7 @@ def main():
         step_e2e_bytes = 0
 
     # ---- roofline of the dominant kernel (CUDA events inside the library, averaged over the timed steps) ----
-    stages = {k: v / a.steps for k, v in stage_acc.items() if k != "h2d"}
+    stages = {k: v / a.steps for k, v in stage_acc.items() if k not in ("h2d", "h2d_wait")}
     dom = max(stages, key=stages.get)
     peaks = {}
     try:
@@ -290,17 +291,22 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     out_bytes = enc.last_scan_bytes() / B if not a.no_e2e else 0.0
-    alg_bytes = B * (W * H * 3 + out_bytes)            # input bytes + JPEG bytes per image
-    achieved = alg_bytes / (stages[dom] / 1e3) / 1e9
+    # one launch of the dominant kernel covers one chunk of the batch; stage times are summed over the chunks,
+    # so bytes per launch / average launch duration == batch bytes / summed stage time
+    imgs_per_launch = resident_chunk
+    n_launch = (B + imgs_per_launch - 1) // imgs_per_launch
+    alg_bytes = imgs_per_launch * (W * H * 3 + out_bytes)            # input bytes + JPEG bytes per image
+    achieved = alg_bytes / (stages[dom] / n_launch / 1e3) / 1e9
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
         if prof.get("kernel") == dom:
-            traffic = prof.get("dram_bytes_per_launch")
+            traffic = prof.get("dram_bytes_per_image") * imgs_per_launch
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel_ms": stages[dom],
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": stages[dom] / n_launch, "launches_per_step": n_launch,
+                "images_per_launch": imgs_per_launch,
                 "algorithmic_bytes_per_launch": alg_bytes, "stage_ms": stages}
 
     # ---- the reference's CPU encoder on this box's host cores (rank 0, N=1 only; bounded sample) ----

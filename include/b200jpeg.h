@@ -182,6 +182,8 @@ int  b200jpeg_encoder_set_stream(b200jpeg_encoder *enc, void *cuda_stream);
  * intermediate HBM arenas are sized for one chunk.  0 = automatic (about 1.6 M
  * 8x8 blocks per chunk, i.e. 8 images of 3840x2160 4:2:0). */
 int  b200jpeg_encoder_set_chunk_images(b200jpeg_encoder *enc, int images_per_chunk);
+/* Images per chunk the last batch was processed with (= images per kernel launch). */
+int  b200jpeg_last_chunk_images(const b200jpeg_encoder *enc);
 /* Consecutive chunks alternate between `n_streams` (1 or 2, default 2) compute
  * streams, each with its own intermediate arenas, so that one chunk's
  * latency-bound phases (serial Huffman table construction, trellis chains)

@@ -47,6 +47,10 @@ class Encoder:
         """Images per pipeline chunk (0 = automatic)."""
         A.check(_lib.b200jpeg_encoder_set_chunk_images(self._h, n), "set_chunk_images")
 
+    def chunk_images(self) -> int:
+        """Images per chunk (= per kernel launch) of the last batch."""
+        return int(_lib.b200jpeg_last_chunk_images(self._h))
+
     def set_streams(self, n: int) -> None:
         """Compute streams consecutive chunks alternate between (1 or 2)."""
         A.check(_lib.b200jpeg_encoder_set_streams(self._h, n), "set_streams")

@@ -878,6 +878,8 @@ int b200jpeg_encoder_set_streams(b200jpeg_encoder *e, int n_streams)
   return B200JPEG_OK;
 }
 
+int b200jpeg_last_chunk_images(const b200jpeg_encoder *e) { return e ? e->chunk : 0; }
+
 int b200jpeg_encoder_set_chunk_images(b200jpeg_encoder *e, int images_per_chunk)
 {
   if (!e || images_per_chunk < 0) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
