@@ -59,7 +59,8 @@ static_assert(sizeof(HostHuff) == 288, "HostHuff");
 struct Plan {                // everything derived from b200jpeg_params
   Geom g;
   std::vector<ScanDesc> scans;
-  bool progressive = false, optimize = false, trellis = false, dering = false;
+  bool progressive = false, optimize = false, trellis = false, dering = false, restarts = false;
+  RestartSpec rs = {0, 0};
   size_t coef_bytes[4] = {0, 0, 0, 0};
   long long max_scan_blocks = 0, max_real_blocks = 0, sum_real_blocks = 0;
 };
@@ -71,10 +72,10 @@ using namespace b200;
 // intermediate HBM state of one chunk in flight
 struct Arena {
   b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm;
-  b200::DevBuf d_blk_bits, d_tile_bits, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
+  b200::DevBuf d_blk_bits, d_tile_bits, d_tile_base, d_seg_corr, d_mark, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
   b200::Geom g;                      // the plan's geometry with this arena's coefficient pointers
   void release() {
-    b200::DevBuf *db[] = {&d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_blk_bits, &d_tile_bits, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
+    b200::DevBuf *db[] = {&d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
     for (b200::DevBuf *b : db) b->release();
     for (int i = 0; i < 4; i++) { d_coef[i].release(); d_raw[i].release(); d_plain[i].release(); }
   }
@@ -186,6 +187,7 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
       sd.bim = k; sd.per_row = g.mcus_per_row; sd.rows = g.mcu_rows;
     }
     sd.nblocks = (long long)sd.per_row * sd.rows * sd.bim;
+    sd.ri = p->restart_in_rows > 0 ? (int)std::min((long long)p->restart_in_rows * sd.per_row, 65535LL) : p->restart_interval;   // jcmaster.c:594-599
     pl.max_scan_blocks = std::max(pl.max_scan_blocks, sd.nblocks);
     pl.scans.push_back(sd);
   }
@@ -193,6 +195,8 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
   pl.optimize = p->optimize_coding || pl.progressive;           // jcmaster.c:1091-1094
   pl.trellis = p->trellis_quant != 0;
   pl.dering = p->overshoot_deringing != 0;
+  pl.restarts = p->restart_interval != 0 || p->restart_in_rows > 0;
+  pl.rs.interval = p->restart_interval; pl.rs.in_rows = p->restart_in_rows;
   return B200JPEG_OK;
 }
 
@@ -288,7 +292,6 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
   Plan &pl = e->plan; const b200jpeg_params *p = &e->params; cudaStream_t s = e->stream;
   Geom &g = pl.g;
   const int nscans = (int)pl.scans.size();
-  if (p->restart_interval || p->restart_in_rows) { set_error("restart intervals are not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
   int rc;
   const int n = chunk;
   long long total_blocks = 0; for (int ci = 0; ci < g.nc; ci++) total_blocks += g.c[ci].blocks_per_image;
@@ -315,6 +318,11 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
     if (pl.progressive) { if ((rc = a.d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = a.d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
     if ((rc = a.d_total_bits.reserve((size_t)n * 8))) return rc;
     if ((rc = a.d_tile_bits.reserve((size_t)n * ((pl.max_scan_blocks + 255) / 256) * 4))) return rc;
+    if ((rc = a.d_tile_base.reserve((size_t)n * ((pl.max_scan_blocks + 255) / 256) * 8))) return rc;
+    if (pl.restarts) {
+      if ((rc = a.d_seg_corr.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;       // worst case: one block per segment
+      if ((rc = a.d_mark.reserve((size_t)n * (cap / 8 + 64)))) return rc;
+    }
     if ((rc = a.d_bitbuf.reserve(cap * n))) return rc;
     if ((rc = a.d_ff_tile.reserve((size_t)n * stuff_tiles(e->bitbuf_words_per_image) * 4))) return rc;
   }
@@ -380,7 +388,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     if (!pl.progressive) {
       tm.mark("trellis_stats");
       CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes_t, s));
-      launch_gather_comp(g, A.d_hist.as<uint32_t>(), status, n, s);
+      launch_gather_comp(g, pl.rs, A.d_hist.as<uint32_t>(), status, n, s);
       tm.mark("trellis_tables");
       SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = g.nc;
       for (int ci = 0; ci < g.nc; ci++) masks.m[ci] = (1u << g.c[ci].dc_tbl) | (1u << (4 + g.c[ci].ac_tbl));
@@ -392,6 +400,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
         ScanDesc ts; memset(&ts, 0, sizeof ts);
         ts.ncomps = 1; ts.ci[0] = ci; ts.Ss = 1; ts.Se = 63; ts.bim = 1; ts.k_count[0] = 1;
         ts.per_row = g.c[ci].wib; ts.rows = g.c[ci].hib; ts.nblocks = (long long)ts.per_row * ts.rows;
+        ts.ri = p->restart_in_rows > 0 ? (int)std::min((long long)p->restart_in_rows * ts.per_row, 65535LL) : p->restart_interval;
         tm.mark("trellis_stats");
         CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
         launch_seed_hist(A.d_hist.as<uint32_t>(), 4 + g.c[ci].ac_tbl, n, s);
@@ -438,14 +447,21 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     } else { tabs = e->d_tabs_fixed.as<DevHuff>(); tstride = 0; }
     tm.mark("block_bits");
     launch_block_bits(g, sd, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), aux, run_e, status, n, s);
+    tm.mark("scan_layout");
+    const size_t mark_words = (e->bitbuf_words_per_image * 4 / 8 + 64) / 4;
+    launch_scan_layout(sd, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
+                       A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, A.d_total_bits.as<unsigned long long>(),
+                       (size_t)e->bitbuf_words_per_image * 32, status, n, s);
     tm.mark("encode");
     CU(cudaMemsetAsync(A.d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
-    launch_encode(g, sd, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), aux, run_e,
-                  A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_total_bits.as<unsigned long long>(), status, n, s);
+    if (sd.ri) CU(cudaMemsetAsync(A.d_mark.p, 0, mark_words * 4 * n, s));
+    launch_encode(g, sd, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
+                  A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, aux, run_e,
+                  A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_mark.as<uint32_t>(), mark_words, status, n, s);
     tm.mark("stuff");
     launch_stuff(A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_total_bits.as<unsigned long long>(), A.d_ff_tile.as<uint32_t>(),
                  io.out, e->out_cap_per_image, e->out_cap_per_image, io.out_pos + (size_t)si * n, io.out_pos + (size_t)(si + 1) * n,
-                 io.scan_size + (size_t)si * n, status, n, s);
+                 io.scan_size + (size_t)si * n, status, sd.ri ? A.d_mark.as<uint32_t>() : nullptr, mark_words, n, s);
   }
   tm.mark("end");
   CU(cudaGetLastError());
@@ -670,7 +686,7 @@ static int finish_chunk(b200jpeg_encoder *e, const ChunkIO &io, int k)
         }
       }
       if (si == 0) write_frame_header(p, pl.progressive, o);
-      write_scan_header(p, sd, ts, last_ri, 0, o);
+      write_scan_header(p, sd, ts, last_ri, (unsigned)sd.ri, o);
       hdr_end[si] = hdr.size();
     }
     const size_t total = hdr.size() + (size_t)pos[i] + 2;

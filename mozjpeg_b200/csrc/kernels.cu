@@ -558,7 +558,7 @@ __device__ __forceinline__ int prev_dc(const Geom &g, const ScanDesc &sd, int im
 {
   long long tp;
   if (k > sd.k_first[sci]) tp = t - 1;
-  else if (mcu > 0) tp = t - sd.bim + sd.k_count[sci] - 1;
+  else if (mcu > 0 && !(sd.ri && mcu % sd.ri == 0)) tp = t - sd.bim + sd.k_count[sci] - 1;   // emit_restart resets last_dc_val (jchuff.c:681-683)
   else return 0;
   int s2, k2; long long m2;
   const int16_t *p = block_ptr(g, sd, img, tp, s2, m2, k2);
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, uint32_
 // Trellis-phase statistics: every component as its own non-interleaved scan
 // (jcmaster.c:443-467), all components of all images in one launch;
 // histogram set index = img*nc + ci.
-__global__ void __launch_bounds__(256) k_gather_comp(Geom g, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
+__global__ void __launch_bounds__(256) k_gather_comp(Geom g, RestartSpec rs, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
 {
   __shared__ unsigned sh[2 * HIST_BINS];
   const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
@@ -647,7 +647,8 @@ __global__ void __launch_bounds__(256) k_gather_comp(Geom g, uint32_t *__restric
     const int16_t *base = c.coef + (size_t)img * c.blocks_per_image * 64;
     const int16_t *blk = base + ((size_t)row * c.wpad + col) * 64;
     int last = 0;
-    if (t > 0) { int pr = col > 0 ? row : row - 1, pc = col > 0 ? col - 1 : c.wib - 1; last = base[((size_t)pr * c.wpad + pc) * 64]; }
+    const long long ri = rs.in_rows > 0 ? min((long long)rs.in_rows * c.wib, 65535LL) : rs.interval;      // per_scan_setup, jcmaster.c:594-599
+    if (t > 0 && !(ri && t % ri == 0)) { int pr = col > 0 ? row : row - 1, pc = col > 0 ? col - 1 : c.wib - 1; last = base[((size_t)pr * c.wpad + pc) * 64]; }
     HistSink sink{sh, sh + HIST_BINS, 0};
     walk_seq_block(blk, last, sink);
     if (sink.bad) atomicOr(&status[img], 2u);
@@ -659,12 +660,12 @@ __global__ void __launch_bounds__(256) k_gather_comp(Geom g, uint32_t *__restric
     if (sh[HIST_BINS + i]) atomicAdd(&gh[(4 + c.ac_tbl) * HIST_BINS + i], sh[HIST_BINS + i]);
   }
 }
-void launch_gather_comp(const Geom &g, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
+void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
 {
   long long mb = 0;
   for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
   dim3 grid((unsigned)((mb + 255) / 256), n * g.nc);
-  k_gather_comp<<<grid, 256, 0, s>>>(g, hist, status);
+  k_gather_comp<<<grid, 256, 0, s>>>(g, rs, hist, status);
   LAUNCHED();
 }
 
@@ -1517,7 +1518,23 @@ __device__ __forceinline__ unsigned cta_sum_256(unsigned v, unsigned *ws /* [8] 
   return r;
 }
 
-// One tile = the 256 blocks of one CTA; tile_bits[img][tile] = bits the tile emits.
+// exclusive prefix of v inside the CTA (256 threads) and the CTA total (valid in all threads)
+__device__ __forceinline__ unsigned cta_excl_scan_256(unsigned v, unsigned *ws /* [9] shared */, unsigned &total)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned x = v;
+  for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) ws[wid] = x;
+  __syncthreads();
+  unsigned before = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { unsigned w = ws[i]; if (i < wid) before += w; tot += w; }
+  total = tot;
+  return before + x - v;
+}
+
+// One tile = the 256 blocks of one CTA; tile_bits[img][tile] = bits the tile emits; blk_bits[img][t] = bits
+// the tile's blocks before t emit (exclusive prefix inside the tile).
 __global__ void __launch_bounds__(256) k_block_bits_seq(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
                                                         uint32_t *__restrict__ blk_bits, uint32_t *__restrict__ tile_bits, uint32_t *__restrict__ status)
 {
@@ -1537,9 +1554,10 @@ __global__ void __launch_bounds__(256) k_block_bits_seq(Geom g, ScanDesc sd, con
     walk_seq_block(blk, last, sink);
     if (sink.bad) atomicOr(&status[img], 2u);
     bits = sink.bits;
-    blk_bits[(size_t)img * sd.nblocks + t] = bits;
   }
-  unsigned tot = cta_sum_256(bits, ws);
+  unsigned tot;
+  const unsigned pre = cta_excl_scan_256(bits, ws, tot);
+  if (t < sd.nblocks) blk_bits[(size_t)img * sd.nblocks + t] = pre;
   if (threadIdx.x == 0) tile_bits[(size_t)img * gridDim.x + blockIdx.x] = tot;
 }
 
@@ -1555,56 +1573,96 @@ struct BitSink {
   __device__ void finish() { if (nacc > 0) { unsigned w = (unsigned)(acc << (32 - nacc)); if (w) atomicOr(&buf[widx], w); } }
 };
 
-// Bit offset of this thread's block inside the scan: bits of the tiles before
-// this CTA's (tile_bits, summed here: a scan has a few hundred tiles) plus the
-// exclusive scan of blk_bits inside the CTA.  The last tile publishes the
-// scan's total and flags an output buffer that is too small.  Returns false if
-// the block must not be written.
-__device__ __forceinline__ bool block_bit_offset(const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
-                                                 long long nblocks, long long t, int img, size_t capacity_bits,
-                                                 unsigned long long *__restrict__ total_bits, uint32_t *__restrict__ status,
-                                                 unsigned long long &off)
+// Scan layout, one CTA per image:
+//   tile_base[img][tile] = bits emitted before the tile (exclusive scan of tile_bits);
+//   with a restart interval (sd.ri MCUs), every segment but the last is padded to a byte boundary and
+//   followed by the 16 bits of its RSTn marker (emit_restart, jchuff.c:668-686): seg_corr[img][s] = padding +
+//   marker bits inserted before segment s;
+//   total_bits[img] = bits of the whole unstuffed scan; flags an output buffer that is too small.
+__device__ __forceinline__ unsigned long long bits_before(const unsigned long long *tb, const uint32_t *pre, long long nblocks, long long t, unsigned long long total)
 {
-  __shared__ unsigned long long red[8];
-  __shared__ unsigned wsum[8];
-  __shared__ unsigned long long base_s;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t *tb = tile_bits + (size_t)img * gridDim.x;
-  unsigned long long part = 0;
-  for (int i = threadIdx.x; i < (int)blockIdx.x; i += 256) part += tb[i];
-  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  unsigned v = t < nblocks ? blk_bits[(size_t)img * nblocks + t] : 0u, x = v;
-  for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-  if (lane == 0) red[wid] = part;
-  if (lane == 31) wsum[wid] = x;
+  return t < nblocks ? tb[t >> 8] + pre[t] : total;
+}
+__global__ void __launch_bounds__(256) k_scan_layout(ScanDesc sd, const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
+                                                     int ntiles, unsigned long long *__restrict__ tile_base, uint32_t *__restrict__ seg_corr,
+                                                     long long seg_stride, unsigned long long *__restrict__ total_bits,
+                                                     size_t capacity_bits, uint32_t *__restrict__ status)
+{
+  __shared__ unsigned ws[9];
+  __shared__ unsigned long long carry;
+  const int img = blockIdx.x;
+  const uint32_t *tbits = tile_bits + (size_t)img * ntiles;
+  unsigned long long *tb = tile_base + (size_t)img * ntiles;
+  if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  if (threadIdx.x == 0) { unsigned long long b = 0; for (int i = 0; i < 8; i++) b += red[i]; base_s = b; }
-  __syncthreads();
-  unsigned before = 0;
-  for (int i = 0; i < wid; i++) before += wsum[i];
-  off = base_s + before + (x - v);
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) {
-    unsigned long long tot = off + v;                      // threads past nblocks carry v = 0
-    total_bits[img] = tot;
-    if (tot + 64 > capacity_bits || tot >= (1ull << 32)) atomicOr(&status[img], 4u);
+  for (int base = 0; base < ntiles; base += 256) {
+    const int i = base + threadIdx.x;
+    unsigned v = i < ntiles ? tbits[i] : 0u, tot;
+    unsigned pre = cta_excl_scan_256(v, ws, tot);
+    if (i < ntiles) tb[i] = carry + pre;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
   }
-  return t < nblocks && off + v + 64 <= capacity_bits;
+  const unsigned long long total = carry;
+  unsigned long long grand = total;
+  if (sd.ri) {
+    const uint32_t *pre = blk_bits + (size_t)img * sd.nblocks;
+    uint32_t *sc = seg_corr + (size_t)img * seg_stride;
+    const long long seglen = (long long)sd.ri * sd.bim, nseg = (sd.nblocks + seglen - 1) / seglen;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < nseg; base += 256) {
+      const long long sgi = base + threadIdx.x;
+      unsigned pad = 0, tot;
+      if (sgi < nseg - 1) {
+        unsigned long long a = bits_before(tb, pre, sd.nblocks, (sgi + 1) * seglen, total) - bits_before(tb, pre, sd.nblocks, sgi * seglen, total);
+        pad = (unsigned)((8 - (a & 7)) & 7) + 16;
+      }
+      unsigned before = cta_excl_scan_256(pad, ws, tot);
+      if (sgi < nseg) sc[sgi] = (uint32_t)(carry + before);
+      __syncthreads();
+      if (threadIdx.x == 0) carry += tot;
+      __syncthreads();
+    }
+    grand = total + carry;
+  }
+  if (threadIdx.x == 0) {
+    total_bits[img] = grand;
+    if (grand + 64 > capacity_bits || grand >= (1ull << 32)) atomicOr(&status[img], 4u);    // does not fit: host retries with a larger buffer
+  }
+}
+
+// end of a restart segment (not the scan's last): 1-bits up to the byte boundary, then RSTn, whose 0xFF
+// must not be byte-stuffed: its position is recorded in the marker bitmap (one bit per unstuffed byte)
+__device__ __forceinline__ void emit_restart_marker(BitSink &sink, const ScanDesc &sd, long long t, uint32_t *__restrict__ mark)
+{
+  const long long seglen = (long long)sd.ri * sd.bim;
+  if ((t + 1) % seglen != 0 || t + 1 >= sd.nblocks) return;
+  const unsigned long long pos = sink.widx * 32ull + (unsigned)sink.nacc;
+  const int pad = (int)((8 - (pos & 7)) & 7);
+  if (pad) sink.put((1u << pad) - 1u, pad);
+  const unsigned long long byte = (pos + pad) >> 3;
+  sink.put(0xFFD0u + (unsigned)((t / seglen) & 7), 16);
+  atomicOr(&mark[byte >> 5], 1u << (byte & 31));
 }
 
 __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
-                                                    const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
+                                                    const uint32_t *__restrict__ blk_bits, const unsigned long long *__restrict__ tile_base,
+                                                    const uint32_t *__restrict__ seg_corr, long long seg_stride,
                                                     uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
-                                                    unsigned long long *__restrict__ total_bits, uint32_t *__restrict__ status)
+                                                    uint32_t *__restrict__ mark, size_t mark_stride_words, const uint32_t *__restrict__ status)
 {
   __shared__ ScanTables st;
   int img = blockIdx.y;
   load_scan_tables(st, tabs, stride, img, g, sd, true);
-  const unsigned flagged = status[img] & ~1u;      // an earlier stage flagged this image (overflow / bad coefficient)
   __syncthreads();
+  if (status[img] & ~1u) return;            // an earlier stage flagged this image (overflow / bad coefficient)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long off;
-  bool ok = block_bit_offset(blk_bits, tile_bits, sd.nblocks, t, img, bitbuf_stride_words * 32, total_bits, status, off);
-  if (!ok || flagged) return;
+  if (t >= sd.nblocks) return;
+  unsigned long long off = tile_base[(size_t)img * gridDim.x + blockIdx.x] + blk_bits[(size_t)img * sd.nblocks + t];
+  if (sd.ri) off += seg_corr[(size_t)img * seg_stride + t / ((long long)sd.ri * sd.bim)];
   int sci, k; long long mcu;
   const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
   int last = prev_dc(g, sd, img, t, sci, mcu, k);
@@ -1613,6 +1671,7 @@ __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const D
   sink.buf = bitbuf + (size_t)img * bitbuf_stride_words; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
   sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
   walk_seq_block(blk, last, sink);
+  if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
   sink.finish();
 }
 
@@ -1644,16 +1703,25 @@ __device__ __forceinline__ uint4 stuff_load(const uint32_t *__restrict__ src, un
   }
   return q;
 }
-__device__ __forceinline__ unsigned count_ff16(uint4 q, int nb)
+// 16 bits of the marker bitmap for the 16 stream bytes starting at word w0 (w0 % 4 == 0): bit j = byte j is the
+// 0xFF of a restart marker and must not be stuffed
+__device__ __forceinline__ unsigned marker_bits16(const uint32_t *__restrict__ mark, unsigned long long w0)
+{
+  if (!mark) return 0u;
+  const unsigned long long byte0 = w0 * 4;
+  return (mark[byte0 >> 5] >> (byte0 & 31)) & 0xFFFFu;
+}
+__device__ __forceinline__ unsigned count_ff16(uint4 q, int nb, unsigned mk)
 {
   unsigned w[4] = {q.x, q.y, q.z, q.w}; unsigned c = 0;
 #pragma unroll
-  for (int j = 0; j < 16; j++) c += (j < nb) && (((w[j >> 2] >> (24 - 8 * (j & 3))) & 0xFF) == 0xFF);
+  for (int j = 0; j < 16; j++) c += (j < nb) && (((w[j >> 2] >> (24 - 8 * (j & 3))) & 0xFF) == 0xFF) && !((mk >> j) & 1u);
   return c;
 }
 __global__ void __launch_bounds__(STUFF_THREADS) k_stuff_count(const uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
                                                                const unsigned long long *__restrict__ total_bits,
-                                                               uint32_t *__restrict__ ff_tile, const uint32_t *__restrict__ status)
+                                                               uint32_t *__restrict__ ff_tile, const uint32_t *__restrict__ status,
+                                                               const uint32_t *__restrict__ mark, size_t mark_stride_words)
 {
   __shared__ unsigned ws[8];
   const int img = blockIdx.y;
@@ -1664,7 +1732,8 @@ __global__ void __launch_bounds__(STUFF_THREADS) k_stuff_count(const uint32_t *_
   const unsigned padbits = (unsigned)(nbytes * 8 - bits);
   int nb;
   uint4 q = stuff_load(bitbuf + (size_t)img * bitbuf_stride_words, nbytes, padbits, tile0 + threadIdx.x * 4, nb);
-  unsigned tot = cta_sum_256(count_ff16(q, nb), ws);
+  const unsigned mk = marker_bits16(mark ? mark + (size_t)img * mark_stride_words : nullptr, tile0 + threadIdx.x * 4);
+  unsigned tot = cta_sum_256(count_ff16(q, nb, mk), ws);
   if (threadIdx.x == 0) ff_tile[(size_t)img * gridDim.x + blockIdx.x] = tot;
 }
 __global__ void __launch_bounds__(STUFF_THREADS) k_stuff_write(const uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
@@ -1672,7 +1741,8 @@ __global__ void __launch_bounds__(STUFF_THREADS) k_stuff_write(const uint32_t *_
                                                                const uint32_t *__restrict__ ff_tile,
                                                                uint8_t *__restrict__ out, size_t out_stride, size_t out_capacity,
                                                                const unsigned long long *__restrict__ out_start, unsigned long long *__restrict__ out_next,
-                                                               uint32_t *__restrict__ scan_size, uint32_t *__restrict__ status)
+                                                               uint32_t *__restrict__ scan_size, uint32_t *__restrict__ status,
+                                                               const uint32_t *__restrict__ mark, size_t mark_stride_words)
 {
   __shared__ unsigned red[8], wsum[8];
   __shared__ unsigned base_s;
@@ -1688,7 +1758,8 @@ __global__ void __launch_bounds__(STUFF_THREADS) k_stuff_write(const uint32_t *_
   for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   int nb;
   uint4 q = stuff_load(bitbuf + (size_t)img * bitbuf_stride_words, nbytes, padbits, tile0 + threadIdx.x * 4, nb);
-  unsigned ff = count_ff16(q, nb), x = ff;
+  const unsigned mk = marker_bits16(mark ? mark + (size_t)img * mark_stride_words : nullptr, tile0 + threadIdx.x * 4);
+  unsigned ff = count_ff16(q, nb, mk), x = ff;
   for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
   if (lane == 0) red[wid] = part;
   if (lane == 31) wsum[wid] = x;
@@ -1708,7 +1779,7 @@ __global__ void __launch_bounds__(STUFF_THREADS) k_stuff_write(const uint32_t *_
         if (j < nb) {
           unsigned b = (w[j >> 2] >> (24 - 8 * (j & 3))) & 0xFF;
           dst[o++] = (uint8_t)b;
-          if (b == 0xFF) dst[o++] = 0;
+          if (b == 0xFF && !((mk >> j) & 1u)) dst[o++] = 0;
         }
       }
     } else atomicOr(&status[img], 4u);
@@ -1786,11 +1857,16 @@ __global__ void __launch_bounds__(256) k_prog_runs(ScanDesc sd, const uint32_t *
   const uint32_t *a = aux + (size_t)img * sd.nblocks;
   uint32_t *re = run_e + (size_t)img * sd.nblocks;
   unsigned f = a[t];
-  if (!(f & AUX_BRK) && t != 0) return;
+  // a restart boundary flushes the pending run (emit_restart -> emit_eobrun, jcphuff.c:446), so a new run
+  // starts at the first block of every restart segment (AC scans: one block per MCU)
+  const long long seg = sd.ri;
+  if (!(f & AUX_BRK) && t != 0 && !(seg && t % seg == 0)) return;
   unsigned E = 0, B = 0; long long first = -1, j;
   if (f & AUX_BRK) { if (f & AUX_CONTRIB) { E = 1; B = f >> 2; first = t; } j = t + 1; }
-  else j = 0;
+  else j = t;
+  const long long j0 = j;
   for (; j < sd.nblocks; j++) {
+    if (seg && j % seg == 0 && !(j == j0 && j == t)) break;
     unsigned fj = a[j];
     if (fj & AUX_BRK) break;
     if (E == 0) first = j;
@@ -1876,7 +1952,7 @@ __device__ __forceinline__ int prev_dc_shifted(const Geom &g, const ScanDesc &sd
   if (sd.Ss != 0 || sd.Ah != 0) return 0;
   long long tp;
   if (k > sd.k_first[sci]) tp = t - 1;
-  else if (mcu > 0) tp = t - sd.bim + sd.k_count[sci] - 1;
+  else if (mcu > 0 && !(sd.ri && mcu % sd.ri == 0)) tp = t - sd.bim + sd.k_count[sci] - 1;   // jcphuff.c:455-457
   else return 0;
   int s2, k2; long long m2;
   const int16_t *p = block_ptr(g, sd, img, tp, s2, m2, k2);
@@ -1943,27 +2019,29 @@ __global__ void __launch_bounds__(256) k_block_bits_prog(Geom g, ScanDesc sd, co
     walk_prog_block(blk, sd, last, a, re, sink);
     if (sink.bad) atomicOr(&status[img], 2u);
     bits = sink.bits;
-    blk_bits[(size_t)img * sd.nblocks + t] = bits;
   }
-  unsigned tot = cta_sum_256(bits, ws);
+  unsigned tot;
+  const unsigned pre = cta_excl_scan_256(bits, ws, tot);
+  if (t < sd.nblocks) blk_bits[(size_t)img * sd.nblocks + t] = pre;
   if (threadIdx.x == 0) tile_bits[(size_t)img * gridDim.x + blockIdx.x] = tot;
 }
 
 __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
                                                      const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
-                                                     const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
+                                                     const uint32_t *__restrict__ blk_bits, const unsigned long long *__restrict__ tile_base,
+                                                     const uint32_t *__restrict__ seg_corr, long long seg_stride,
                                                      uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
-                                                     unsigned long long *__restrict__ total_bits, uint32_t *__restrict__ status)
+                                                     uint32_t *__restrict__ mark, size_t mark_stride_words, const uint32_t *__restrict__ status)
 {
   __shared__ ScanTables st;
   int img = blockIdx.y;
   if (!(sd.Ss == 0 && sd.Ah != 0)) load_scan_tables(st, tabs, stride, img, g, sd, true);
-  const unsigned flagged = status[img] & ~1u;
   __syncthreads();
+  if (status[img] & ~1u) return;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long off;
-  bool ok = block_bit_offset(blk_bits, tile_bits, sd.nblocks, t, img, bitbuf_stride_words * 32, total_bits, status, off);
-  if (!ok || flagged) return;
+  if (t >= sd.nblocks) return;
+  unsigned long long off = tile_base[(size_t)img * gridDim.x + blockIdx.x] + blk_bits[(size_t)img * sd.nblocks + t];
+  if (sd.ri) off += seg_corr[(size_t)img * seg_stride + t / ((long long)sd.ri * sd.bim)];
   int sci, k; long long mcu;
   const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
   int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
@@ -1973,6 +2051,7 @@ __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const 
   sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
   unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
   walk_prog_block(blk, sd, last, a, re, sink);
+  if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
   sink.finish();
 }
 
@@ -1997,23 +2076,32 @@ void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, s
   else k_block_bits_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, tile_bits, status);
   LAUNCHED();
 }
+void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint32_t *tile_bits, unsigned long long *tile_base,
+                        uint32_t *seg_corr, long long seg_stride, unsigned long long *total_bits, size_t capacity_bits,
+                        uint32_t *status, int n, cudaStream_t s)
+{
+  const int ntiles = (int)((sd.nblocks + 255) / 256);
+  k_scan_layout<<<n, 256, 0, s>>>(sd, blk_bits, tile_bits, ntiles, tile_base, seg_corr, seg_stride, total_bits, capacity_bits, status);
+  LAUNCHED();
+}
 void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, int progressive,
-                   const uint32_t *blk_bits, const uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e,
-                   uint32_t *bitbuf, size_t bitbuf_stride_words, unsigned long long *total_bits, uint32_t *status, int n, cudaStream_t s)
+                   const uint32_t *blk_bits, const unsigned long long *tile_base, const uint32_t *seg_corr, long long seg_stride,
+                   const uint32_t *blk_aux, const uint32_t *run_e,
+                   uint32_t *bitbuf, size_t bitbuf_stride_words, uint32_t *mark, size_t mark_stride_words, const uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, tile_bits, bitbuf, bitbuf_stride_words, total_bits, status);
-  else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, tile_bits, bitbuf, bitbuf_stride_words, total_bits, status);
+  if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
+  else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
   LAUNCHED();
 }
 size_t stuff_tiles(size_t bitbuf_stride_words) { return (bitbuf_stride_words + STUFF_TILE_WORDS - 1) / STUFF_TILE_WORDS; }
 void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_stride_words, const unsigned long long *total_bits, uint32_t *ff_tile,
                   uint8_t *out, size_t out_stride, size_t out_capacity, const unsigned long long *out_start, unsigned long long *out_next,
-                  uint32_t *scan_size, uint32_t *status, int n, cudaStream_t s)
+                  uint32_t *scan_size, uint32_t *status, const uint32_t *mark, size_t mark_stride_words, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)stuff_tiles(bitbuf_stride_words), n);
-  k_stuff_count<<<grid, STUFF_THREADS, 0, s>>>(bitbuf, bitbuf_stride_words, total_bits, ff_tile, status); LAUNCHED();
-  k_stuff_write<<<grid, STUFF_THREADS, 0, s>>>(bitbuf, bitbuf_stride_words, total_bits, ff_tile, out, out_stride, out_capacity, out_start, out_next, scan_size, status); LAUNCHED();
+  k_stuff_count<<<grid, STUFF_THREADS, 0, s>>>(bitbuf, bitbuf_stride_words, total_bits, ff_tile, status, mark, mark_stride_words); LAUNCHED();
+  k_stuff_write<<<grid, STUFF_THREADS, 0, s>>>(bitbuf, bitbuf_stride_words, total_bits, ff_tile, out, out_stride, out_capacity, out_start, out_next, scan_size, status, mark, mark_stride_words); LAUNCHED();
 }
 
 }  // namespace b200

@@ -29,6 +29,8 @@ struct CompGeom {
   long long blocks_per_image;   // wpad*hpad
   int16_t *coef, *raw;
 };
+// restart parameters as the caller gave them (cinfo->restart_interval / restart_in_rows)
+struct RestartSpec { int interval, in_rows; };
 struct Geom {
   int W, H, nc, hmax, vmax;
   int mcus_per_row, mcu_rows;
@@ -46,6 +48,7 @@ struct ScanDesc {
   int k_comp[10], k_y[10], k_x[10];
   int k_first[4], k_count[4];      // first k / number of blocks of scan-component i in the MCU
   int per_row, rows;               // MCUs per row / MCU rows of the scan (jcmaster.c:518-601)
+  int ri;                          // restart interval of the scan in MCUs, 0 = none (jcmaster.c:594-599)
   long long nblocks;               // per image
 };
 
@@ -96,7 +99,7 @@ struct SlotMasks { uint32_t m[4]; int period; };
 void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s);
 void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, int n, cudaStream_t s);
 void launch_dummy(const Geom &g, int n, cudaStream_t s);
-void launch_gather_comp(const Geom &g, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
+void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_gather_seq(const Geom &g, const ScanDesc &sd, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s);
 void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_set_stride, const SlotMasks &masks, int nsets, cudaStream_t s);
@@ -108,14 +111,19 @@ void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint3
 void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
                        uint32_t *blk_bits, uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *status, int n, cudaStream_t s);
-// bit offsets are resolved inside the encode kernel (tile sums + in-CTA scan); it also publishes total_bits[img]
+// tile_base[img][tile] / seg_corr[img][segment] / total_bits[img] from the tile sums (and the restart interval)
+void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint32_t *tile_bits, unsigned long long *tile_base,
+                        uint32_t *seg_corr, long long seg_stride, unsigned long long *total_bits, size_t capacity_bits,
+                        uint32_t *status, int n, cudaStream_t s);
+// mark: bitmap over the unstuffed bytes of each image (restart markers' 0xFF), only touched when sd.ri != 0
 void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
-                   const uint32_t *blk_bits, const uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e,
-                   uint32_t *bitbuf, size_t bitbuf_image_stride_words, unsigned long long *total_bits, uint32_t *status, int n, cudaStream_t s);
+                   const uint32_t *blk_bits, const unsigned long long *tile_base, const uint32_t *seg_corr, long long seg_stride,
+                   const uint32_t *blk_aux, const uint32_t *run_e,
+                   uint32_t *bitbuf, size_t bitbuf_image_stride_words, uint32_t *mark, size_t mark_stride_words, const uint32_t *status, int n, cudaStream_t s);
 size_t stuff_tiles(size_t bitbuf_image_stride_words);     // ff_tile entries per image
 void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_image_stride_words, const unsigned long long *total_bits, uint32_t *ff_tile,
                   uint8_t *out, size_t out_image_stride, size_t out_capacity, const unsigned long long *out_start, unsigned long long *out_next,
-                  uint32_t *scan_size, uint32_t *status, int n, cudaStream_t s);
+                  uint32_t *scan_size, uint32_t *status, const uint32_t *mark, size_t mark_stride_words, int n, cudaStream_t s);
 
 extern unsigned long long g_kernel_launches;
 

@@ -279,6 +279,7 @@ int b200jpeg_validate(const b200jpeg_params *p) {
     if (p->input_components != 3 || p->jpeg_color_space != B200JPEG_CS_YCbCr) { set_error("Unsupported color conversion request"); return B200JPEG_ERR_PARAM; }
   } else { set_error("Bogus input colorspace"); return B200JPEG_ERR_PARAM; }
   // things the reference can do that the device path cannot (yet)
+  if (p->restart_interval < 0 || p->restart_interval > 65535 || p->restart_in_rows < 0) { set_error("restart interval out of range"); return B200JPEG_ERR_PARAM; }
   if (p->dct_method != B200JPEG_DCT_ISLOW) { set_error("dct_method %d is not on the device path yet (only JDCT_ISLOW)", p->dct_method); return B200JPEG_ERR_UNSUPPORTED; }
   if (p->smoothing_factor) { set_error("input smoothing is not on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
   if (p->optimize_scans && p->num_scans != 0) { set_error("optimize_scans (scan search) is not on the device path yet; clear it (cjpeg -fastcrush) or drop the scan script (-baseline)"); return B200JPEG_ERR_UNSUPPORTED; }
