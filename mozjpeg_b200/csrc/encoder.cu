@@ -71,11 +71,11 @@ using namespace b200;
 
 // intermediate HBM state of one chunk in flight
 struct Arena {
-  b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm;
+  b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm, d_splits;
   b200::DevBuf d_blk_bits, d_tile_bits, d_tile_base, d_seg_corr, d_mark, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
   b200::Geom g;                      // the plan's geometry with this arena's coefficient pointers
   void release() {
-    b200::DevBuf *db[] = {&d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
+    b200::DevBuf *db[] = {&d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_splits, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
     for (b200::DevBuf *b : db) b->release();
     for (int i = 0; i < 4; i++) { d_coef[i].release(); d_raw[i].release(); d_plain[i].release(); }
   }
@@ -314,6 +314,7 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
     if ((rc = a.d_rec.reserve((size_t)n * pl.sum_real_blocks * sizeof(DcRec)))) return rc;
     if ((rc = a.d_bt.reserve((size_t)n * pl.sum_real_blocks * 8))) return rc;
     if ((rc = a.d_perm.reserve((size_t)n * pl.sum_real_blocks * 4))) return rc;
+    if ((rc = a.d_splits.reserve((size_t)n * 4 * 2 * 4))) return rc;
     if ((rc = a.d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
     if (pl.progressive) { if ((rc = a.d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = a.d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
     if ((rc = a.d_total_bits.reserve((size_t)n * 8))) return rc;
@@ -412,9 +413,9 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
       }
     }
     tm.mark("trellis_sort");
-    launch_sort_blocks(g, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), n, s);
+    launch_sort_blocks(g, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
     tm.mark("trellis_ac");
-    launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), n, s);
+    launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
     if (p->trellis_quant_dc) {
       tm.mark("trellis_dc");
       if (pl.progressive) launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rl, n, s);

@@ -793,7 +793,7 @@ void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s) { k_seed_
 // Order the real blocks of every (image, component) by decreasing number of
 // non-zero plain-quantized AC coefficients (counting sort on DcRec.nz), so that
 // the 32 blocks a warp of k_trellis_ac works on have similar trip counts.
-__global__ void __launch_bounds__(256) k_sort_blocks(Geom g, const DcRec *__restrict__ rec, RecLayout rl, uint32_t *__restrict__ perm)
+__global__ void __launch_bounds__(256) k_sort_blocks(Geom g, const DcRec *__restrict__ rec, RecLayout rl, uint32_t *__restrict__ perm, uint32_t *__restrict__ splits)
 {
   __shared__ unsigned cnt[64], start[64];
   const int ci = blockIdx.x % g.nc, img = blockIdx.x / g.nc;
@@ -805,13 +805,17 @@ __global__ void __launch_bounds__(256) k_sort_blocks(Geom g, const DcRec *__rest
   __syncthreads();
   for (long long b = threadIdx.x; b < nblk; b += blockDim.x) atomicAdd(&cnt[63 - min((int)r[b].nz, 63)], 1u);
   __syncthreads();
-  if (threadIdx.x == 0) { unsigned a = 0; for (int k = 0; k < 64; k++) { start[k] = a; a += cnt[k]; } }
+  if (threadIdx.x == 0) {
+    unsigned a = 0; for (int k = 0; k < 64; k++) { start[k] = a; a += cnt[k]; }
+    // sorted order = decreasing count: [0, splits[0]) have more than 32 non-zeros, [splits[0], splits[1]) 17..32, the rest <= 16
+    splits[2 * blockIdx.x] = start[63 - 32]; splits[2 * blockIdx.x + 1] = start[63 - 16];
+  }
   __syncthreads();
   for (long long b = threadIdx.x; b < nblk; b += blockDim.x) { unsigned pos = atomicAdd(&start[63 - min((int)r[b].nz, 63)], 1u); p[pos] = (uint32_t)b; }
 }
-void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, int n, cudaStream_t s)
+void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, uint32_t *splits, int n, cudaStream_t s)
 {
-  k_sort_blocks<<<n * g.nc, 256, 0, s>>>(g, rec, rl, perm);
+  k_sort_blocks<<<n * g.nc, 256, 0, s>>>(g, rec, rl, perm, splits);
   LAUNCHED();
 }
 
@@ -918,12 +922,23 @@ __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long 
 // candidate: for each candidate the first predecessor with the smallest cost,
 // then over candidates the smallest cost, ties to the earlier predecessor, then
 // to the earlier candidate -- the same pair the reference's scan order keeps.
-__global__ void __launch_bounds__(TRELLIS_THREADS, 5) k_trellis_ac(Geom g, const TrellisConsts *__restrict__ tc,
+// CLS selects the blocks by their number of non-zero positions m (class boundaries in sorted order from
+// k_sort_blocks).  CLS 1: 17 <= m <= 32, register path with 32 entries.  CLS 0: everything else -- warps
+// whose blocks all have m <= 16 take the 16-entry register path, the others (m > 32) the generic loops.
+template <int CLS>
+__global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_ac(Geom g, const TrellisConsts *__restrict__ tc,
                                                                    const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
-                                                                   DcRec *__restrict__ rec, RecLayout rl, const uint32_t *__restrict__ perm)
+                                                                   DcRec *__restrict__ rec, RecLayout rl, const uint32_t *__restrict__ perm,
+                                                                   const uint32_t *__restrict__ splits)
 {
   const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
   const CompGeom &c = g.c[ci];
+  {
+    // this CTA's slice of the sorted order against the class's range
+    const long long lo = splits[2 * blockIdx.y], hi = splits[2 * blockIdx.y + 1];      // [lo, hi) = the blocks with 17..32 non-zeros
+    const long long b0 = (long long)blockIdx.x * blockDim.x;
+    if (CLS == 1 ? (b0 >= hi || b0 + blockDim.x <= lo) : (b0 >= lo && b0 + blockDim.x <= hi)) return;
+  }
   __shared__ __half srate[10][64];
   __shared__ float swz[64];
   __shared__ int sq8[64];
@@ -956,11 +971,13 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, 5) k_trellis_ac(Geom g, const
   float lambda; unsigned long long nzmask;
   {
     DcRec rr = rec[rbase + lin];
+    nzmask = rr.nzmask;
+    const int mcls = __popcll(nzmask);
+    if ((CLS == 1) != (mcls > 16 && mcls <= 32)) return;      // the other class's block
     float norm = (float)((double)rr.lambda_dc / 63.0);
     if (tc->use_norm) lambda = (float)(tc->p1 / (tc->p2 + (double)norm));
     else lambda = tc->lambda_const;
     rec[rbase + lin].lambda_dc = lambda * swz[0];
-    nzmask = rr.nzmask;
   }
   // phase 1: accumulated zero distortion (zigzag order, serial fp32), every position, to local memory   :1134
   float A[64];
@@ -986,6 +1003,7 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, 5) k_trellis_ac(Geom g, const
   const int maxq = (1 << tc->max_coef_bits) - 1;
   const int m = __popcll(nzmask);
 
+  if (CLS == 1) { trellis_entries_regs<32>(m, nzmask, A, raw16, o16, srate, swz, sq8, lambda, maxq, azd63, (float)acsi[0]); return; }
   // warps whose blocks all have few non-zero positions take the register path
   {
     const int mmax = __reduce_max_sync(__activemask(), m);
@@ -1077,13 +1095,14 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, 5) k_trellis_ac(Geom g, const
 }
 
 void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                       DcRec *rec, const RecLayout &rl, const uint32_t *perm, int n, cudaStream_t s)
+                       DcRec *rec, const RecLayout &rl, const uint32_t *perm, const uint32_t *splits, int n, cudaStream_t s)
 {
   long long mb = 0;
   for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
   dim3 grid((unsigned)((mb + TRELLIS_THREADS - 1) / TRELLIS_THREADS), n * g.nc);
-  k_trellis_ac<<<grid, TRELLIS_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, perm);
-  LAUNCHED();
+  // largest blocks first (they sit at the front of the sorted order): the three classes touch disjoint blocks
+  k_trellis_ac<1><<<grid, TRELLIS_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, perm, splits); LAUNCHED();
+  k_trellis_ac<0><<<grid, TRELLIS_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, perm, splits); LAUNCHED();
 }
 
 // =====================================================================

@@ -97,14 +97,14 @@ struct SlotMasks { uint32_t m[4]; int period; };
 // ---------------------------------------------------------------- launches (defined in kernels.cu)
 // status[img] bits: 2 = JERR_BAD_DCT_COEF / missing Huffman code, 4 = output buffer too small (host retries)
 void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s);
-void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, int n, cudaStream_t s);
+void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, uint32_t *splits /* [n*nc][2] */, int n, cudaStream_t s);
 void launch_dummy(const Geom &g, int n, cudaStream_t s);
 void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_gather_seq(const Geom &g, const ScanDesc &sd, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s);
 void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_set_stride, const SlotMasks &masks, int nsets, cudaStream_t s);
 void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                       DcRec *rec, const RecLayout &rl, const uint32_t *perm, int n, cudaStream_t s);
+                       DcRec *rec, const RecLayout &rl, const uint32_t *perm, const uint32_t *splits, int n, cudaStream_t s);
 void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                        const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int n, cudaStream_t s);
 void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int n, cudaStream_t s);
