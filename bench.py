@@ -197,6 +197,9 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     sw = a.switches.split()
@@ -314,9 +317,10 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         threads = host_threads()
         imgs = [base[i] for i in range(min(4, a.distinct))]
-        v, kind, secs = cpu_reference_run(imgs, sw, threads, 1)
+        reps = 3
+        v, kind, secs = cpu_reference_run(imgs, sw, threads, reps)
         cpu = {"value": v, "unit": "MP/s", "cores": threads, "kind": kind,
-               "sample": f"{threads} images {W}x{H} (one per host thread, {secs:.1f} s wall), same switches"}
+               "sample": f"{threads * reps} images {W}x{H} ({reps} per host thread, {secs:.1f} s wall = {secs * threads:.0f} CPU-seconds), same switches"}
 
     if rank == 0:
         line = {"metric": "megapixels/sec encode (4K RGB q75 4:2:0)", "value": value, "unit": "MP/s", "n_gpus": world,
