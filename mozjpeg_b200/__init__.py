@@ -57,9 +57,10 @@ class Encoder:
 
     # -- batch API -------------------------------------------------------
     def encode_batch(self, p: Params, images: np.ndarray) -> List[bytes]:
-        """images: (N, H, W, C) or (N, H, W) uint8 host array -> N JPEG files.
+        """images: (N, H, W, C) or (N, H, W) host array -> N JPEG files (uint8, or uint16
+        holding 12-bit samples when p.data_precision == 12, like J12SAMPLE rows).
         Host->device staging and device->host read-back happen inside."""
-        a = np.ascontiguousarray(images, dtype=np.uint8)
+        a = np.ascontiguousarray(images, dtype=np.uint16 if p.data_precision == 12 else np.uint8)
         if a.ndim == 3 and p.input_components == 1:
             a = a[..., None]
         n, h, w, c = a.shape

@@ -98,6 +98,11 @@ def _parse(p: A.Params, argv: Sequence[str], for_real: bool) -> None:
             p.dc_scan_opt_mode = int(nextarg("dc-scan-opt"))
         elif _keymatch(a, "optimize", 1) or _keymatch(a, "optimise", 1):
             p.optimize_coding = 1
+        elif _keymatch(a, "precision", 3):
+            v = nextarg("precision")
+            if int(v) not in (8, 12):
+                raise UsageError("precision must be 8 or 12")
+            p.data_precision = int(v)
         elif _keymatch(a, "progressive", 1):
             simple_progressive = True
         elif _keymatch(a, "quality", 1):

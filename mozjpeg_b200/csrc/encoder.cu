@@ -192,7 +192,7 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
     pl.scans.push_back(sd);
   }
   pl.progressive = p->num_scans > 0 && (p->scan_info[0].Ss != 0 || p->scan_info[0].Se != 63);
-  pl.optimize = p->optimize_coding || pl.progressive;           // jcmaster.c:1091-1094
+  pl.optimize = p->optimize_coding || pl.progressive || p->data_precision == 12;   // jcmaster.c:1091-1094, :1102-1105
   pl.trellis = p->trellis_quant != 0;
   pl.dering = p->overshoot_deringing != 0;
   pl.restarts = p->restart_interval != 0 || p->restart_in_rows > 0;
@@ -374,7 +374,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   for (int ci = 0; ci < g.nc; ci++) { rl.comp_off[ci] = rl.per_image; rl.per_image += (long long)g.c[ci].wib * g.c[ci].hib; }
   tm.mark("forward");
   int qfast = 1; for (int ci = 0; ci < g.nc; ci++) qfast &= e->h_qt.as<QuantTables>()->fast[g.c[ci].qt];
-  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), qfast, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, n, s);
+  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), qfast, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, e->keep_plain ? 1 : 0, n, s);
   tm.mark("dummy");
   launch_dummy(g, n, s);
 
@@ -729,17 +729,25 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   if (!e || !p || !pixels || n_images <= 0) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
   int rc = b200jpeg_validate(p);
   if (rc) return rc;
-  if (row_pitch < (size_t)p->image_width * p->input_components) { set_error("row_pitch smaller than a row"); return B200JPEG_ERR_PARAM; }
-  if (n_images > 1 && image_stride < row_pitch * (size_t)(p->image_height - 1) + (size_t)p->image_width * p->input_components) { set_error("image_stride smaller than an image"); return B200JPEG_ERR_PARAM; }
+  const size_t sample_bytes = p->data_precision > 8 ? 2 : 1;                       // 12-bit samples are uint16 (J12SAMPLE)
+  const size_t row_bytes = (size_t)p->image_width * p->input_components * sample_bytes;
+  if (row_pitch < row_bytes) { set_error("row_pitch smaller than a row"); return B200JPEG_ERR_PARAM; }
+  if (n_images > 1 && image_stride < row_pitch * (size_t)(p->image_height - 1) + row_bytes) { set_error("image_stride smaller than an image"); return B200JPEG_ERR_PARAM; }
   CU(cudaSetDevice(e->device));
   e->params = *p; e->n = n_images;
   if ((rc = build_plan(p, row_pitch, image_stride, e->plan))) return rc;
   Plan &pl = e->plan;
+  if (p->data_precision == 12) {
+    const Geom &g = pl.g;
+    bool gray = g.nc == 1 && g.hmax == 1 && g.vmax == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
+    bool ycc = g.nc == 3 && g.cs_mode == 0 && g.in_comps == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax && g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
+    if (!gray && !ycc) { set_error("12-bit precision: only RGB->YCbCr 4:4:4/4:2:2/4:4:0/4:2:0 and grayscale layouts are on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
+  }
   const int nscans = (int)pl.scans.size();
   const int C = choose_chunk(e, pl, n_images, !on_device);
   const int nchunks = (n_images + C - 1) / C;
   e->chunk = C;
-  const size_t image_bytes = row_pitch * (size_t)(p->image_height - 1) + (size_t)p->image_width * p->input_components;
+  const size_t image_bytes = row_pitch * (size_t)(p->image_height - 1) + row_bytes;
   const size_t src_bytes = image_stride * (size_t)(n_images - 1) + image_bytes;
   while ((int)e->ev_in.size() < nchunks) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->ev_in.push_back(ev); }
   while ((int)e->ev_done.size() < nchunks) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->ev_done.push_back(ev); }
@@ -997,7 +1005,7 @@ int b200jpeg_start_compress(b200jpeg_encoder *e, const b200jpeg_params *p)
   if (e->st_state != 0) { set_error("Improper call to JPEG library in state %d", 100 + e->st_state); return B200JPEG_ERR_STATE; }   // JERR_BAD_STATE
   int rc = b200jpeg_validate(p);
   if (rc) return rc;
-  size_t bytes = (size_t)p->image_width * p->input_components * p->image_height;
+  size_t bytes = (size_t)p->image_width * p->input_components * p->image_height * (p->data_precision > 8 ? 2 : 1);
   if ((rc = e->h_stage.reserve(bytes))) return rc;
   e->st_params = *p; e->st_state = 1; e->st_next_row = 0;
   return B200JPEG_OK;
@@ -1006,7 +1014,7 @@ int b200jpeg_write_scanlines(b200jpeg_encoder *e, const uint8_t *const *scanline
 {
   if (!e || e->st_state != 1) { set_error("Improper call to JPEG library in state %d", e ? 100 + e->st_state : -1); return B200JPEG_ERR_STATE; }
   const b200jpeg_params &p = e->st_params;
-  size_t rowbytes = (size_t)p.image_width * p.input_components;
+  size_t rowbytes = (size_t)p.image_width * p.input_components * (p.data_precision > 8 ? 2 : 1);      // 12-bit rows are J12SAMPLE = short (jpeg12_write_scanlines)
   int left = p.image_height - e->st_next_row;            // extra rows are ignored (jcapistd.c:120-123)
   if (num_lines > left) num_lines = left;
   for (int i = 0; i < num_lines; i++) memcpy(e->h_stage.as<uint8_t>() + (size_t)(e->st_next_row + i) * rowbytes, scanlines[i], rowbytes);
@@ -1018,7 +1026,7 @@ int b200jpeg_finish_compress(b200jpeg_encoder *e, const uint8_t **jpeg, size_t *
   if (!e || e->st_state != 1) { set_error("Improper call to JPEG library in state %d", e ? 100 + e->st_state : -1); return B200JPEG_ERR_STATE; }
   const b200jpeg_params &p = e->st_params;
   if (e->st_next_row < p.image_height) { set_error("Application transferred too few scanlines"); return B200JPEG_ERR_STATE; }   // JERR_TOO_LITTLE_DATA
-  size_t rowbytes = (size_t)p.image_width * p.input_components;
+  size_t rowbytes = (size_t)p.image_width * p.input_components * (p.data_precision > 8 ? 2 : 1);
   e->st_state = 0;
   int rc = encode_common(e, &p, e->h_stage.p, 0, rowbytes, rowbytes * p.image_height, 1, false);
   if (rc) return rc;

@@ -50,15 +50,16 @@ __device__ __forceinline__ int load_component(const uint8_t *__restrict__ px, in
 }
 
 #define DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
-template <int PASS>
+// P1 = PASS1_BITS: 2 for 8-bit samples, 1 for 12-bit (jfdctint.c:80-86)
+template <int PASS, int P1 = 2>
 __device__ __forceinline__ void fdct_1d(int &d0, int &d1, int &d2, int &d3, int &d4, int &d5, int &d6, int &d7)
 {
   int t0 = d0 + d7, t7 = d0 - d7, t1 = d1 + d6, t6 = d1 - d6;
   int t2 = d2 + d5, t5 = d2 - d5, t3 = d3 + d4, t4 = d3 - d4;
   int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
-  constexpr int SH = PASS == 0 ? 13 - 2 : 13 + 2;
-  if (PASS == 0) { d0 = (t10 + t11) << 2; d4 = (t10 - t11) << 2; }
-  else { d0 = DESCALE(t10 + t11, 2); d4 = DESCALE(t10 - t11, 2); }
+  constexpr int SH = PASS == 0 ? 13 - P1 : 13 + P1;
+  if (PASS == 0) { d0 = (t10 + t11) << P1; d4 = (t10 - t11) << P1; }
+  else { d0 = DESCALE(t10 + t11, P1); d4 = DESCALE(t10 - t11, P1); }
   int z1 = (t12 + t13) * 4433;
   d2 = DESCALE(z1 + t13 * 6270, SH);
   d6 = DESCALE(z1 + t12 * (-15137), SH);
@@ -226,31 +227,46 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
 //   E. coalesced 16-byte stores of whole 128-byte blocks.
 // Same arithmetic as k_forward (the generic one-thread-per-block kernel).
 // =====================================================================
-// One row of 8 pixels of the strip (24 bytes for RGB, 8 for grey) in registers.
-struct Px8 { unsigned w[6]; };
-template <int IC>
+template <int PREC> struct WorkT { typedef int16_t type; };
+template <> struct WorkT<12> { typedef int type; };
+// One row of 8 pixels of the strip in registers: IC samples per pixel, SB bytes per sample
+// (8-bit: 24 bytes RGB / 8 grey; 12-bit in uint16: 48 / 16).
+struct Px8 { unsigned w[12]; };
+template <int IC, int SB>
 __device__ __forceinline__ Px8 load_px8(const uint8_t *__restrict__ base, size_t row_pitch, int iy, int x, int W, bool fast)
 {
   Px8 r;
   const uint8_t *row = base + (size_t)iy * row_pitch;
-  if (fast) {                                     // 8-byte aligned, fully inside the image
-    const uint2 *p = reinterpret_cast<const uint2 *>(row + (size_t)x * IC);
-    if (IC == 3) { uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2); r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y; r.w[4] = c.x; r.w[5] = c.y; }
-    else { uint2 a = __ldg(p); r.w[0] = a.x; r.w[1] = a.y; r.w[2] = r.w[3] = r.w[4] = r.w[5] = 0; }
+  constexpr int NBYTES = 8 * IC * SB;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.w[i] = 0;
+  if (fast) {                                     // aligned (8 bytes for 8-bit, 16 for 16-bit samples), fully inside the image
+    if (SB == 1) {
+      const uint2 *p = reinterpret_cast<const uint2 *>(row + (size_t)x * IC);
+#pragma unroll
+      for (int i = 0; i < NBYTES / 8; i++) { uint2 a = __ldg(p + i); r.w[2 * i] = a.x; r.w[2 * i + 1] = a.y; }
+    } else {
+      const uint4 *p = reinterpret_cast<const uint4 *>(row + (size_t)x * IC * 2);
+#pragma unroll
+      for (int i = 0; i < NBYTES / 16; i++) { uint4 a = __ldg(p + i); r.w[4 * i] = a.x; r.w[4 * i + 1] = a.y; r.w[4 * i + 2] = a.z; r.w[4 * i + 3] = a.w; }
+    }
   } else {                                        // right edge / unaligned: bytes, columns clamped to W-1 (expand_right_edge)
 #pragma unroll
-    for (int i = 0; i < 6; i++) r.w[i] = 0;
-#pragma unroll
-    for (int b = 0; b < 8 * IC; b++) {
-      int px = b / IC, ch = b - px * IC;
+    for (int b = 0; b < NBYTES; b++) {
+      int px = b / (IC * SB), rem = b - px * (IC * SB);
       int ix = min(x + px, W - 1);
-      r.w[b >> 2] |= (unsigned)row[(size_t)ix * IC + ch] << (8 * (b & 3));
+      r.w[b >> 2] |= (unsigned)row[(size_t)ix * IC * SB + rem] << (8 * (b & 3));
     }
   }
   return r;
 }
-template <int IC>
-__device__ __forceinline__ int px_byte(const Px8 &r, int px, int ch) { int b = px * IC + ch; return (int)((r.w[b >> 2] >> (8 * (b & 3))) & 0xFFu); }
+// sample `ch` of pixel `px`; 12-bit samples are masked like the reference's RANGE_LIMIT (jccolext.c:52-54)
+template <int IC, int SB>
+__device__ __forceinline__ int px_sample(const Px8 &r, int px, int ch)
+{
+  if (SB == 1) { int b = px * IC + ch; return (int)((r.w[b >> 2] >> (8 * (b & 3))) & 0xFFu); }
+  int h = px * IC + ch; return (int)((r.w[h >> 1] >> (16 * (h & 1))) & 0xFFFu);
+}
 
 // exact floor((|x| + d/2) / d) * sign(x) with the per-table uniform shift (QuantTables.fast) or the general 64-bit form
 __device__ __forceinline__ int quant_fast(int x, uint2 k, int L, int dering)
@@ -261,20 +277,24 @@ __device__ __forceinline__ int quant_fast(int x, uint2 k, int L, int dering)
   return x < 0 ? -q : q;
 }
 
-template <int HMAX, int VMAX, int NC, bool QFAST>
+template <int HMAX, int VMAX, int NC, bool QFAST, int PREC>
 __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *__restrict__ src,
                                                       const QuantTables *__restrict__ qt, int dering,
-                                                      DcRec *__restrict__ rec, RecLayout rl)
+                                                      DcRec *__restrict__ rec, RecLayout rl, int write_raw)
 {
   constexpr int TW = 128, TR = 8 * VMAX;
   constexpr int YBW = TW / 8, YB = YBW * VMAX;           // luma blocks in the tile
   constexpr int CW = TW / HMAX, CBW = CW / 8;            // chroma samples / blocks per tile row
   constexpr int NB = YB + (NC == 3 ? 2 * CBW : 0);
   constexpr int YP = TW + 8, CP = CW + 8;                // padded plane pitches (int16 elements)
-  constexpr int IC = NC == 3 ? 3 : 1;                    // bytes per input pixel on the fast path (grey from RGB: see below)
+  constexpr int IC = NC == 3 ? 3 : 1;                    // samples per input pixel on the fast path (grey from RGB: see below)
+  constexpr int SB = PREC == 8 ? 1 : 2;                  // bytes per sample (12-bit samples come as uint16)
+  constexpr int P1 = PREC == 8 ? 2 : 1;                  // PASS1_BITS
+  constexpr int CENTRE = 1 << (PREC - 1);
+  typedef typename WorkT<PREC>::type wtype;              // row-pass results: int16 holds them at 8 bits, not at 12
   __shared__ __align__(16) int16_t sY[TR * YP];
   __shared__ __align__(16) int16_t sC[NC == 3 ? 2 * 8 * CP : 8];
-  __shared__ __align__(16) int16_t sW[NB * 72];
+  __shared__ __align__(16) wtype sW[NB * 72];
   __shared__ __align__(16) unsigned char sIO[NB * 256];   // phases D/E: output staging
   __shared__ uint2 sQC[NC][64];                           // quantizer constants per component, natural order
   __shared__ int sQL[NC];
@@ -293,17 +313,18 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
     const int rg = tid >> 4, seg = tid & 15;
     const int xs = x0 + seg * 8;
     const bool grey_from_rgb = NC == 1 && g.cs_mode == 1;
-    const bool fast = (xs + 8 <= g.W) && ((g.row_pitch & 7) == 0) && ((((size_t)base) & 7) == 0) && !grey_from_rgb;
+    constexpr size_t AL = SB == 1 ? 7 : 15;
+    const bool fast = (xs + 8 <= g.W) && ((g.row_pitch & AL) == 0) && ((((size_t)base) & AL) == 0) && !grey_from_rgb;
     if (NC == 1 && grey_from_rgb) {
       // RGB input, grayscale output: 3 bytes per pixel, luma only
 #pragma unroll
       for (int rr = 0; rr < VMAX; rr++) {
         const int iy = min(y0 + rg * VMAX + rr, g.H - 1);
-        const bool f3 = (xs + 8 <= g.W) && ((g.row_pitch & 7) == 0) && ((((size_t)base) & 7) == 0);
-        Px8 p = load_px8<3>(base, g.row_pitch, iy, xs, g.W, f3);
+        const bool f3 = (xs + 8 <= g.W) && ((g.row_pitch & AL) == 0) && ((((size_t)base) & AL) == 0);
+        Px8 p = load_px8<3, SB>(base, g.row_pitch, iy, xs, g.W, f3);
         int16_t yv[8];
 #pragma unroll
-        for (int px = 0; px < 8; px++) yv[px] = (int16_t)(((19595 * px_byte<3>(p, px, 0) + 38470 * px_byte<3>(p, px, 1) + 7471 * px_byte<3>(p, px, 2) + 32768) >> 16) - 128);
+        for (int px = 0; px < 8; px++) yv[px] = (int16_t)(((19595 * px_sample<3, SB>(p, px, 0) + 38470 * px_sample<3, SB>(p, px, 1) + 7471 * px_sample<3, SB>(p, px, 2) + 32768) >> 16) - CENTRE);
         *reinterpret_cast<uint4 *>(&sY[(rg * VMAX + rr) * YP + seg * 8]) = *reinterpret_cast<const uint4 *>(yv);
       }
     } else {
@@ -316,24 +337,24 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
 #pragma unroll
       for (int rr = 0; rr < VMAX; rr++) {
         const int iy = min(y0 + rg * VMAX + rr, g.H - 1);
-        Px8 p = load_px8<IC>(base, g.row_pitch, iy, xs, g.W, fast);
+        Px8 p = load_px8<IC, SB>(base, g.row_pitch, iy, xs, g.W, fast);
         int16_t yv[8];
 #pragma unroll
         for (int px = 0; px < 8; px++) {
-          if (NC == 1) yv[px] = (int16_t)(px_byte<1>(p, px, 0) - 128);
+          if (NC == 1) yv[px] = (int16_t)(px_sample<1, SB>(p, px, 0) - CENTRE);
           else {
-            const int R = px_byte<3>(p, px, 0), G = px_byte<3>(p, px, 1), B = px_byte<3>(p, px, 2);
-            yv[px] = (int16_t)(((19595 * R + 38470 * G + 7471 * B + 32768) >> 16) - 128);
+            const int R = px_sample<3, SB>(p, px, 0), G = px_sample<3, SB>(p, px, 1), B = px_sample<3, SB>(p, px, 2);
+            yv[px] = (int16_t)(((19595 * R + 38470 * G + 7471 * B + 32768) >> 16) - CENTRE);
           }
         }
         *reinterpret_cast<uint4 *>(&sY[(rg * VMAX + rr) * YP + seg * 8]) = *reinterpret_cast<const uint4 *>(yv);
         if (NC == 3) {
-          if (er != rg) p = load_px8<IC>(base, g.row_pitch, min(y0 + er * VMAX + rr, g.H - 1), xs, g.W, fast);
+          if (er != rg) p = load_px8<IC, SB>(base, g.row_pitch, min(y0 + er * VMAX + rr, g.H - 1), xs, g.W, fast);
 #pragma unroll
           for (int px = 0; px < 8; px++) {
-            const int R = px_byte<3>(p, px, 0), G = px_byte<3>(p, px, 1), B = px_byte<3>(p, px, 2);
-            sb[px / HMAX] += (-11059 * R - 21709 * G + 32768 * B + (128 << 16) + 32767) >> 16;
-            sr[px / HMAX] += (32768 * R - 27439 * G - 5329 * B + (128 << 16) + 32767) >> 16;
+            const int R = px_sample<3, SB>(p, px, 0), G = px_sample<3, SB>(p, px, 1), B = px_sample<3, SB>(p, px, 2);
+            sb[px / HMAX] += (-11059 * R - 21709 * G + 32768 * B + (CENTRE << 16) + 32767) >> 16;
+            sr[px / HMAX] += (32768 * R - 27439 * G - 5329 * B + (CENTRE << 16) + 32767) >> 16;
           }
         }
       }
@@ -346,7 +367,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
           if (HMAX == 2 && VMAX == 1) { b = (b + (xo & 1)) >> 1; r = (r + (xo & 1)) >> 1; }                      // jcsample.c:226-254
           else if (HMAX == 2 && VMAX == 2) { b = (b + 1 + (xo & 1)) >> 2; r = (r + 1 + (xo & 1)) >> 2; }         // jcsample.c:263-295
           else if (HMAX * VMAX > 1) { b = (b + HMAX * VMAX / 2) / (HMAX * VMAX); r = (r + HMAX * VMAX / 2) / (HMAX * VMAX); }   // jcsample.c:151-190
-          cbv[i] = (int16_t)(b - 128); crv[i] = (int16_t)(r - 128);
+          cbv[i] = (int16_t)(b - CENTRE); crv[i] = (int16_t)(r - CENTRE);
         }
         int16_t *cb = &sC[rg * CP + seg * (8 / HMAX)], *cr = &sC[8 * CP + rg * CP + seg * (8 / HMAX)];
         if (HMAX == 1) { *reinterpret_cast<uint4 *>(cb) = *reinterpret_cast<const uint4 *>(cbv); *reinterpret_cast<uint4 *>(cr) = *reinterpret_cast<const uint4 *>(crv); }
@@ -382,11 +403,16 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
         d0 = rowp[0]; d1 = rowp[1]; d2 = rowp[2]; d3 = rowp[3]; d4 = rowp[4]; d5 = rowp[5]; d6 = rowp[6]; d7 = rowp[7];
       }
     }
-    fdct_1d<0>(d0, d1, d2, d3, d4, d5, d6, d7);
-    uint4 wv;
-    wv.x = ((unsigned)d0 & 0xFFFFu) | ((unsigned)d1 << 16); wv.y = ((unsigned)d2 & 0xFFFFu) | ((unsigned)d3 << 16);
-    wv.z = ((unsigned)d4 & 0xFFFFu) | ((unsigned)d5 << 16); wv.w = ((unsigned)d6 & 0xFFFFu) | ((unsigned)d7 << 16);
-    *reinterpret_cast<uint4 *>(sW + b * 72 + j * 8) = wv;
+    fdct_1d<0, P1>(d0, d1, d2, d3, d4, d5, d6, d7);
+    if (PREC == 8) {
+      uint4 wv;
+      wv.x = ((unsigned)d0 & 0xFFFFu) | ((unsigned)d1 << 16); wv.y = ((unsigned)d2 & 0xFFFFu) | ((unsigned)d3 << 16);
+      wv.z = ((unsigned)d4 & 0xFFFFu) | ((unsigned)d5 << 16); wv.w = ((unsigned)d6 & 0xFFFFu) | ((unsigned)d7 << 16);
+      *reinterpret_cast<uint4 *>(sW + b * 72 + j * 8) = wv;
+    } else {
+      wtype *w = sW + b * 72 + j * 8;
+      w[0] = (wtype)d0; w[1] = (wtype)d1; w[2] = (wtype)d2; w[3] = (wtype)d3; w[4] = (wtype)d4; w[5] = (wtype)d5; w[6] = (wtype)d6; w[7] = (wtype)d7;
+    }
   }
   __syncthreads();
 
@@ -403,9 +429,9 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   for (int r = 0; r < 8; r++) kz[r] = c_izz[8 * r + j];
 #pragma unroll 1
   for (int b = tid >> 3; b < NB; b += 16) {
-    const int16_t *w = sW + b * 72 + j;
+    const wtype *w = sW + b * 72 + j;
     int d0 = w[0], d1 = w[8], d2 = w[16], d3 = w[24], d4 = w[32], d5 = w[40], d6 = w[48], d7 = w[56];
-    fdct_1d<1>(d0, d1, d2, d3, d4, d5, d6, d7);
+    fdct_1d<1, P1>(d0, d1, d2, d3, d4, d5, d6, d7);
     const int ci = b < YB ? 0 : (1 + (b - YB) / CBW);
     const int dd[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
     const int L = sQL[NC == 1 ? 0 : ci];
@@ -421,15 +447,15 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
       sR[b * 64 + k] = (int16_t)dd[r];
       if (qv != 0 && nat != 0) { if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
     }
-    if (rec) {
+    if (PREC == 8 && rec) {
       // the raw coefficients go back to sW in natural order (each lane rewrites exactly the words it
       // read), lane r then owns ROW r and the serial fp32 sum of squares in NATURAL order
       // (jcdctmgr.c:1026-1029) is handed from lane to lane, 8 adds per hop
-      int16_t *ww = sW + b * 72 + j;
+      int16_t *ww = reinterpret_cast<int16_t *>(sW) + b * 72 + j;
 #pragma unroll
       for (int r = 0; r < 8; r++) ww[8 * r] = (int16_t)dd[r];
       __syncwarp();
-      const int4 rowv = *reinterpret_cast<const int4 *>(sW + b * 72 + 8 * j);
+      const int4 rowv = *reinterpret_cast<const int4 *>(reinterpret_cast<int16_t *>(sW) + b * 72 + 8 * j);
       const int pw[4] = {rowv.x, rowv.y, rowv.z, rowv.w};
       float sq[8];
 #pragma unroll
@@ -469,33 +495,38 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
     if (row >= c.hib || col >= c.wib) continue;
     size_t blk = ((size_t)img * c.hpad + row) * c.wpad + col;
     reinterpret_cast<uint4 *>(c.coef + blk * 64)[v] = reinterpret_cast<const uint4 *>(sQ + b * 64)[v];
-    reinterpret_cast<uint4 *>(c.raw + blk * 64)[v] = reinterpret_cast<const uint4 *>(sR + b * 64)[v];
+    if (write_raw) reinterpret_cast<uint4 *>(c.raw + blk * 64)[v] = reinterpret_cast<const uint4 *>(sR + b * 64)[v];   // only the trellis (and the debug tap) read the raw DCT
   }
 }
 
-template <bool QFAST>
-static void launch_forward_tile(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s, bool gray)
+template <bool QFAST, int PREC>
+static void launch_forward_tile(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s, bool gray, int write_raw)
 {
   dim3 grid((g.W + 127) / 128, g.mcu_rows, n);
-  if (gray) k_forward_tile<1, 1, 1, QFAST><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
-  else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3, QFAST><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
-  else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3, QFAST><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
-  else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3, QFAST><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
-  else k_forward_tile<2, 2, 3, QFAST><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+  if (gray) k_forward_tile<1, 1, 1, QFAST, PREC><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
+  else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3, QFAST, PREC><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
+  else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3, QFAST, PREC><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
+  else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3, QFAST, PREC><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
+  else k_forward_tile<2, 2, 3, QFAST, PREC><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
 }
-void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s)
+void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, int n, cudaStream_t s)
 {
+  const int write_raw = rec != nullptr || keep_raw;
   // fast path: full-size first component, (for colour) two 1x1-sampled chroma components
   bool gray = g.nc == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
   bool ycc = g.nc == 3 && g.cs_mode == 0 && g.in_comps == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax &&
              g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
   static const bool force_generic = getenv("B200JPEG_GENERIC_FORWARD") != nullptr;   // A/B switch for debugging
   if (!force_generic && ((gray && g.hmax == 1 && g.vmax == 1) || ycc)) {
-    if (qfast) launch_forward_tile<true>(g, src, qt, dering, rec, rl, n, s, gray);
-    else launch_forward_tile<false>(g, src, qt, dering, rec, rl, n, s, gray);
+    if (g.max_coef_bits == 14) {                       // 12-bit samples (uint16)
+      if (qfast) launch_forward_tile<true, 12>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
+      else launch_forward_tile<false, 12>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
+    } else if (qfast) launch_forward_tile<true, 8>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
+    else launch_forward_tile<false, 8>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
     LAUNCHED();
     return;
   }
+  if (g.max_coef_bits == 14) { fprintf(stderr, "libb200jpeg: 12-bit input needs one of the tiled layouts\n"); return; }   // refused earlier by the encoder
   int mw = 0, mh = 0;
   for (int ci = 0; ci < g.nc; ci++) { mw = max(mw, g.c[ci].wib); mh = max(mh, g.c[ci].hib); }
   dim3 grid((mw + 127) / 128, mh, n * g.nc);
@@ -604,9 +635,9 @@ __device__ __forceinline__ void walk_seq_block(const int16_t *__restrict__ blk, 
 // statistics pass (encode_mcu_gather, jchuff.c:886-915)
 // ---------------------------------------------------------------------
 struct HistSink {
-  unsigned *dc_hist, *ac_hist; int bad;
-  __device__ void dc(int nb, int) { if (nb > 11) bad = 1; atomicAdd(&dc_hist[nb], 1u); }
-  __device__ void ac(int sym, int nb, int) { if (nb > 10) bad = 1; atomicAdd(&ac_hist[sym], 1u); }
+  unsigned *dc_hist, *ac_hist; int bad; int maxbits;        // maxbits = data_precision + 2 (jchuff.c:819,836,865)
+  __device__ void dc(int nb, int) { if (nb > maxbits + 1) bad = 1; atomicAdd(&dc_hist[nb], 1u); }
+  __device__ void ac(int sym, int nb, int) { if (nb > maxbits) bad = 1; atomicAdd(&ac_hist[sym], 1u); }
 };
 
 __global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
@@ -621,7 +652,7 @@ __global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, uint32_
     const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
     int last = prev_dc(g, sd, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
-    HistSink sink{sh + c.dc_tbl * HIST_BINS, sh + (4 + c.ac_tbl) * HIST_BINS, 0};
+    HistSink sink{sh + c.dc_tbl * HIST_BINS, sh + (4 + c.ac_tbl) * HIST_BINS, 0, g.max_coef_bits};
     walk_seq_block(blk, last, sink);
     if (sink.bad) atomicOr(&status[img], 2u);          // JERR_BAD_DCT_COEF
   }
@@ -649,7 +680,7 @@ __global__ void __launch_bounds__(256) k_gather_comp(Geom g, RestartSpec rs, uin
     int last = 0;
     const long long ri = rs.in_rows > 0 ? min((long long)rs.in_rows * c.wib, 65535LL) : rs.interval;      // per_scan_setup, jcmaster.c:594-599
     if (t > 0 && !(ri && t % ri == 0)) { int pr = col > 0 ? row : row - 1, pc = col > 0 ? col - 1 : c.wib - 1; last = base[((size_t)pr * c.wpad + pc) * 64]; }
-    HistSink sink{sh, sh + HIST_BINS, 0};
+    HistSink sink{sh, sh + HIST_BINS, 0, g.max_coef_bits};
     walk_seq_block(blk, last, sink);
     if (sink.bad) atomicOr(&status[img], 2u);
   }
@@ -1979,8 +2010,8 @@ __device__ __forceinline__ int prev_dc_shifted(const Geom &g, const ScanDesc &sd
 }
 
 struct HistSinkP {
-  unsigned *dc_hist, *ac_hist; int bad;
-  __device__ void dc(int nb, int) { if (nb > 11) bad = 1; atomicAdd(&dc_hist[nb], 1u); }
+  unsigned *dc_hist, *ac_hist; int bad; int maxbits;
+  __device__ void dc(int nb, int) { if (nb > maxbits + 1) bad = 1; atomicAdd(&dc_hist[nb], 1u); }
   __device__ void ac(int sym, int nb, int) { if (nb > 14) bad = 1; atomicAdd(&ac_hist[sym], 1u); }
   __device__ void raw(unsigned, int) {}
 };
@@ -2007,7 +2038,7 @@ __global__ void __launch_bounds__(256) k_gather_prog(Geom g, ScanDesc sd, const 
     const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
     int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
-    HistSinkP sink{sh + c.dc_tbl * HIST_BINS, sh + (4 + c.ac_tbl) * HIST_BINS, 0};
+    HistSinkP sink{sh + c.dc_tbl * HIST_BINS, sh + (4 + c.ac_tbl) * HIST_BINS, 0, g.max_coef_bits};
     unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
     walk_prog_block(blk, sd, last, a, re, sink);
     if (sink.bad) atomicOr(&status[img], 2u);

@@ -252,7 +252,10 @@ int b200jpeg_validate(const b200jpeg_params *p) {
   // initial_setup (jcmaster.c:169-249)
   if (p->image_height <= 0 || p->image_width <= 0 || p->num_components <= 0 || p->input_components <= 0) { set_error("Empty input image"); return B200JPEG_ERR_PARAM; }
   if (p->image_height > 65500 || p->image_width > 65500) { set_error("Maximum supported image dimension is 65500 pixels"); return B200JPEG_ERR_PARAM; }
-  if (p->data_precision != 8) { set_error("data precision %d is not on the device path yet", p->data_precision); return p->data_precision == 12 ? B200JPEG_ERR_UNSUPPORTED : B200JPEG_ERR_PARAM; }
+  if (p->data_precision != 8 && p->data_precision != 12) { set_error("Unsupported JPEG data precision %d", p->data_precision); return B200JPEG_ERR_PARAM; }   // JERR_BAD_PRECISION
+  // 12-bit: the coefficient controller has no JBUF_REQUANT mode (jccoefct.c:132-138), so the reference cannot run the
+  // trellis passes ("Bogus buffer control mode"); its 12-bit deringing is unusable (jcdctmgr.c:419)
+  if (p->data_precision == 12 && (p->trellis_quant || p->overshoot_deringing)) { set_error("12-bit precision needs trellis quantization and overshoot deringing off (cjpeg -notrellis -noovershoot), as in the reference"); return B200JPEG_ERR_PARAM; }
   if (p->num_components > B200JPEG_MAX_COMPONENTS) { set_error("Too many color components: %d", p->num_components); return B200JPEG_ERR_PARAM; }
   int hmax = 1, vmax = 1;
   for (int ci = 0; ci < p->num_components; ci++) {
@@ -322,6 +325,7 @@ int b200jpeg_validate(const b200jpeg_params *p) {
     else { for (int ci = 0; ci < p->num_components; ci++) if (!sent[ci]) { set_error("Scan script does not transmit all data"); return B200JPEG_ERR_PARAM; } }
   }
   bool optimize = p->optimize_coding || progressive;
+  if (p->data_precision == 12) optimize = true;                     // jcmaster.c:1102-1105
   if (p->trellis_quant && !optimize) { set_error("trellis quantization without optimize_coding is not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
   if (!optimize) {
     for (int ci = 0; ci < p->num_components; ci++) {

@@ -22,3 +22,11 @@ def synth_image(seed: int, width: int, height: int) -> np.ndarray:
     out[y0 + rh // 3:y0 + rh // 3 + 1, x0:x0 + rw] = 0
     out[y0:y0 + rh, x0 + rw // 2:x0 + rw // 2 + 1] = 0
     return out
+
+
+def synth_image12(seed: int, width: int, height: int) -> np.ndarray:
+    """12-bit variant: the 8-bit generator x16 plus uniform{0..15},
+    uint16 samples in [0, 4095]."""
+    base = synth_image(seed, width, height).astype(np.uint16) * 16
+    rng = np.random.default_rng(seed + 7919)
+    return (base + rng.integers(0, 16, base.shape, dtype=np.uint16)).astype(np.uint16)

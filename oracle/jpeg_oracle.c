@@ -58,10 +58,23 @@ void orc_rgb_to_ycc(int r, int g, int b, int *y, int *cb, int *cr)
   *cb = (-11059 * r - 21709 * g + 32768 * b + (128 << 16) + 32767) >> 16;
   *cr = (32768 * r - 27439 * g - 5329 * b + (128 << 16) + 32767) >> 16;
 }
+/* the same tables at data precision P: CBCR_OFFSET = CENTERJSAMPLE << SCALEBITS (jccolor.c:70,235); the 12-bit
+ * instantiation masks its inputs with 0xFFF (RANGE_LIMIT, jccolext.c:52-54) */
+static void rgb_to_ycc_p(int r, int g, int b, int prec, int *y, int *cb, int *cr)
+{
+  const int centre = 1 << (prec - 1);
+  if (prec == 12) { r &= 0xFFF; g &= 0xFFF; b &= 0xFFF; }
+  *y  = (19595 * r + 38470 * g + 7471 * b + 32768) >> 16;
+  *cb = (-11059 * r - 21709 * g + 32768 * b + (centre << 16) + 32767) >> 16;
+  *cr = (32768 * r - 27439 * g - 5329 * b + (centre << 16) + 32767) >> 16;
+}
 
 /* jfdctint.c:142-286, 8-bit: CONST_BITS=13, PASS1_BITS=2 */
 #define DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
-static void fdct_1d(int *d, int stride, int pass)
+static void fdct_1d_p1(int *d, int stride, int pass, int p1);
+static void fdct_1d(int *d, int stride, int pass) { fdct_1d_p1(d, stride, pass, 2); }
+/* PASS1_BITS = 2 for 8-bit samples, 1 for 12-bit (jfdctint.c:80-86) */
+static void fdct_1d_p1(int *d, int stride, int pass, int p1)
 {
   int t0 = d[0] + d[7 * stride], t7 = d[0] - d[7 * stride];
   int t1 = d[stride] + d[6 * stride], t6 = d[stride] - d[6 * stride];
@@ -69,9 +82,9 @@ static void fdct_1d(int *d, int stride, int pass)
   int t3 = d[3 * stride] + d[4 * stride], t4 = d[3 * stride] - d[4 * stride];
   int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
   int z1, z2, z3, z4, z5;
-  int sh = pass == 0 ? 13 - 2 : 13 + 2;
-  if (pass == 0) { d[0] = (t10 + t11) << 2; d[4 * stride] = (t10 - t11) << 2; }
-  else { d[0] = DESCALE(t10 + t11, 2); d[4 * stride] = DESCALE(t10 - t11, 2); }
+  int sh = pass == 0 ? 13 - p1 : 13 + p1;
+  if (pass == 0) { d[0] = (t10 + t11) << p1; d[4 * stride] = (t10 - t11) << p1; }
+  else { d[0] = DESCALE(t10 + t11, p1); d[4 * stride] = DESCALE(t10 - t11, p1); }
   z1 = (t12 + t13) * 4433;
   d[2 * stride] = DESCALE(z1 + t13 * 6270, sh);
   d[6 * stride] = DESCALE(z1 + t12 * (-15137), sh);
@@ -90,6 +103,12 @@ void orc_fdct_islow(int *data)
   int i;
   for (i = 0; i < 8; i++) fdct_1d(data + 8 * i, 1, 0);   /* rows    */
   for (i = 0; i < 8; i++) fdct_1d(data + i, 8, 1);       /* columns */
+}
+static void fdct_islow_prec(int *data, int prec)          /* jpeg_fdct_islow / jpeg12_fdct_islow */
+{
+  int i, p1 = prec == 8 ? 2 : 1;
+  for (i = 0; i < 8; i++) fdct_1d_p1(data + 8 * i, 1, 0, p1);
+  for (i = 0; i < 8; i++) fdct_1d_p1(data + i, 8, 1, p1);
 }
 
 /* jcdctmgr.c:387-403 catmull_rom: all products/sums in fp32, left to right */
@@ -763,34 +782,38 @@ static void fill_dummy_blocks(enc_t *e, int ci)
     }
 }
 
+/* samples are uint8 (8-bit) or uint16 holding 12-bit values (J12SAMPLE, jmorecfg.h) */
 static int forward_all(enc_t *e, const uint8_t *pix, size_t pitch)
 {
   const b200jpeg_params *p = e->p;
+  const int prec = p->data_precision, centre = 1 << (prec - 1);
   int W = e->W, H = e->H, ci, x, y;
   /* full-resolution converted planes (jccolor.c) */
-  uint8_t *full[4] = {0, 0, 0, 0};
-  for (ci = 0; ci < e->nc; ci++) full[ci] = (uint8_t *)malloc((size_t)W * H);
+  uint16_t *full[4] = {0, 0, 0, 0};
+  for (ci = 0; ci < e->nc; ci++) full[ci] = (uint16_t *)malloc((size_t)W * H * 2);
+#define IN(xx, cc) (prec == 8 ? (int)row[p->input_components * (xx) + (cc)] : (int)((const uint16_t *)row)[p->input_components * (xx) + (cc)])
   for (y = 0; y < H; y++) {
     const uint8_t *row = pix + (size_t)y * pitch;
     for (x = 0; x < W; x++) {
       if (p->in_color_space == B200JPEG_CS_RGB && p->jpeg_color_space == B200JPEG_CS_YCbCr) {
-        int Y, Cb, Cr; orc_rgb_to_ycc(row[3 * x], row[3 * x + 1], row[3 * x + 2], &Y, &Cb, &Cr);
+        int Y, Cb, Cr; rgb_to_ycc_p(IN(x, 0), IN(x, 1), IN(x, 2), prec, &Y, &Cb, &Cr);
         full[0][(size_t)y * W + x] = Y; full[1][(size_t)y * W + x] = Cb; full[2][(size_t)y * W + x] = Cr;
       } else if (p->in_color_space == B200JPEG_CS_RGB && p->jpeg_color_space == B200JPEG_CS_GRAYSCALE) {
-        int Y, Cb, Cr; orc_rgb_to_ycc(row[3 * x], row[3 * x + 1], row[3 * x + 2], &Y, &Cb, &Cr);   /* jccolor.c rgb_gray_convert: same Y */
+        int Y, Cb, Cr; rgb_to_ycc_p(IN(x, 0), IN(x, 1), IN(x, 2), prec, &Y, &Cb, &Cr);   /* jccolor.c rgb_gray_convert: same Y */
         full[0][(size_t)y * W + x] = Y;
       } else {                                                                                     /* null_convert / grayscale_convert */
-        for (ci = 0; ci < e->nc; ci++) full[ci][(size_t)y * W + x] = row[p->input_components * x + ci];
+        for (ci = 0; ci < e->nc; ci++) full[ci][(size_t)y * W + x] = (uint16_t)IN(x, ci);
       }
     }
   }
+#undef IN
   for (ci = 0; ci < e->nc; ci++) {
     const b200jpeg_component_info *c = &p->comp_info[ci];
     int hx = e->hmax / c->h_samp_factor, vx = e->vmax / c->v_samp_factor;
     int ow = e->wib[ci] * 8, oh = e->hib[ci] * 8;
     int groups = (H + e->vmax - 1) / e->vmax;                /* row groups holding real data (jcprepct.c:135-192) */
     int rows_avail = groups * c->v_samp_factor;
-    uint8_t *plane = (uint8_t *)malloc((size_t)ow * oh);
+    uint16_t *plane = (uint16_t *)malloc((size_t)ow * oh * 2);
     int numpix = hx * vx, bx, by, i;
     for (y = 0; y < oh; y++) {
       int yy = y < rows_avail ? y : rows_avail - 1;          /* expand_bottom_edge on the downsampled rows */
@@ -805,19 +828,19 @@ static int forward_all(enc_t *e, const uint8_t *pix, size_t pitch)
         else if (hx == 2 && vx == 1) val = (sum + (x & 1)) >> 1;             /* jcsample.c:226-254 bias 0,1,.. */
         else if (hx == 2 && vx == 2) val = (sum + 1 + (x & 1)) >> 2;         /* jcsample.c:263-295 bias 1,2,.. */
         else val = (sum + numpix / 2) / numpix;                              /* jcsample.c:151-190 */
-        plane[(size_t)y * ow + x] = (uint8_t)val;
+        plane[(size_t)y * ow + x] = (uint16_t)val;
       }
     }
     /* forward_DCT on every real block (jcdctmgr.c:693-772) */
     for (by = 0; by < e->hib[ci]; by++) for (bx = 0; bx < e->wib[ci]; bx++) {
       int ws[64]; const uint16_t *q = p->quant_tbl[c->quant_tbl_no];
       int16_t *dq = e->coef[ci] + ((size_t)by * e->wpad[ci] + bx) * 64, *dr = e->raw[ci] + ((size_t)by * e->wpad[ci] + bx) * 64;
-      for (y = 0; y < 8; y++) for (x = 0; x < 8; x++) ws[8 * y + x] = plane[(size_t)(by * 8 + y) * ow + bx * 8 + x] - 128;   /* convsamp :576-604 */
+      for (y = 0; y < 8; y++) for (x = 0; x < 8; x++) ws[8 * y + x] = plane[(size_t)(by * 8 + y) * ow + bx * 8 + x] - centre;   /* convsamp :576-604 */
       if (p->overshoot_deringing) orc_deringing(ws, q[0]);
-      orc_fdct_islow(ws);
+      fdct_islow_prec(ws, prec);
       for (i = 0; i < 64; i++) {
-        int v = orc_quantize_coef(ws[i], q[i]);
-        dr[i] = (int16_t)ws[i];
+        int v = orc_quantize_coef(ws[i], q[i]);                /* 12-bit: the literal division of :646-678 is the same function */
+        dr[i] = (int16_t)ws[i];                                /* (12-bit raw values can exceed int16; only the trellis reads them and it is off) */
         if (p->overshoot_deringing) { int mx = (1 << (p->data_precision + 2)) - 1; if (v < -mx) v = -mx; if (v > mx) v = mx; }   /* :761-770 */
         dq[i] = (int16_t)v;
       }
@@ -860,7 +883,9 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
   *out = NULL; *outsize = 0;
   if (dbg) memset(dbg, 0, sizeof *dbg);
   e->p = p; e->nc = p->num_components; e->W = p->image_width; e->H = p->image_height;
-  if (p->data_precision != 8 || p->dct_method != B200JPEG_DCT_ISLOW || p->smoothing_factor || p->optimize_scans ||
+  /* 12-bit: no JBUF_REQUANT => no trellis (jccoefct.c:132-138); deringing is not usable at 12 bits (jcdctmgr.c:419) */
+  if (p->data_precision == 12 && (p->trellis_quant || p->overshoot_deringing)) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
+  if ((p->data_precision != 8 && p->data_precision != 12) || p->dct_method != B200JPEG_DCT_ISLOW || p->smoothing_factor || p->optimize_scans ||
       p->trellis_eob_opt || p->use_scans_in_trellis || p->trellis_q_opt || p->trellis_num_loops != 1 ||
       p->trellis_delta_dc_weight != 0.0f) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   e->hmax = e->vmax = 1;
@@ -887,7 +912,7 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
     e->progressive = 0;
   }
   {
-    int optimize = p->optimize_coding || e->progressive;                /* jcmaster.c:1091-1094 */
+    int optimize = p->optimize_coding || e->progressive || p->data_precision == 12;   /* jcmaster.c:1091-1094, :1102-1105 */
     if (p->trellis_quant && !optimize) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
 
     write_file_header(e);                                                /* jcinit.c:149 */

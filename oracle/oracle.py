@@ -73,9 +73,9 @@ class OracleResult:
 
 
 def oracle_encode(p: A.Params, pixels: np.ndarray, want_debug: bool = False) -> OracleResult:
-    """Run the C restatement on an (H, W, C) or (H, W) uint8 array."""
+    """Run the C restatement on an (H, W, C) or (H, W) uint8 array (uint16 for 12-bit precision)."""
     lib = orc()
-    pix = np.ascontiguousarray(pixels, dtype=np.uint8)
+    pix = np.ascontiguousarray(pixels, dtype=np.uint16 if p.data_precision == 12 else np.uint8)
     pitch = pix.strides[0]
     out = C.POINTER(C.c_uint8)()
     n = C.c_size_t(0)
@@ -177,6 +177,7 @@ def refcfg_from_switches(switches: Sequence[str], input_gray: bool = False) -> R
             if v[-1] in "bB": c.restart = int(v[:-1]); c.restart_blocks = 1
             else: c.restart = int(v)
         elif s == "-grayscale": c.grayscale = 1
+        elif s == "-precision": c.precision = int(next(it))
         elif s == "-quant-table": c.quant_table = int(next(it))
         elif s == "-lambda1": c.has_lambda1 = 1; c.lambda1 = float(next(it))
         elif s == "-lambda2": c.has_lambda2 = 1; c.lambda2 = float(next(it))
@@ -187,12 +188,12 @@ def refcfg_from_switches(switches: Sequence[str], input_gray: bool = False) -> R
 def ref_encode(pixels: np.ndarray, switches: Sequence[str]) -> bytes:
     """Encode with the UNMODIFIED reference (libjpeg API, cjpeg switch semantics)."""
     lib = ref()
-    pix = np.ascontiguousarray(pixels, dtype=np.uint8)
-    gray = pix.ndim == 2 or pix.shape[2] == 1
+    gray = pixels.ndim == 2 or pixels.shape[2] == 1
     cfg = refcfg_from_switches(switches, gray)
+    pix = np.ascontiguousarray(pixels, dtype=np.uint16 if cfg.precision == 12 else np.uint8)
     out = C.POINTER(C.c_uint8)(); n = C.c_ulong(0)
     err = C.create_string_buffer(256)
-    rc = lib.refshim_encode(pix.ctypes.data, pix.shape[1], pix.shape[0], pix.strides[0], C.byref(cfg), C.byref(out), C.byref(n), err, 256)
+    rc = lib.refshim_encode(pix.ctypes.data, pix.shape[1], pix.shape[0], pix.strides[0] // pix.itemsize, C.byref(cfg), C.byref(out), C.byref(n), err, 256)
     if rc != 0:
         raise RuntimeError("reference encode failed: " + err.value.decode())
     data = C.string_at(out, n.value)

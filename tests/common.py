@@ -18,7 +18,7 @@ def golden_cases():
 
 
 def case_id(c):
-    im = c["image"] if isinstance(c["image"], str) else "synth%dx%d" % (c["image"][1], c["image"][2])
+    im = c["image"] if isinstance(c["image"], str) else "synth%s%dx%d" % ("12b_" if len(c["image"]) > 3 else "", c["image"][1], c["image"][2])
     return im + ":" + "_".join(s.lstrip("-") for s in c["switches"])
 
 
@@ -34,8 +34,12 @@ def case_image(c):
             w, h, nc, data = mj.read_ppm(open(os.path.join(GOLD, "testorig.ppm"), "rb").read())
             _img_cache[key] = np.frombuffer(data, dtype=np.uint8).reshape(h, w, nc)
         else:
-            seed, w, h = c["image"]
-            _img_cache[key] = O.synth_image(seed, w, h)
+            seed, w, h = c["image"][:3]
+            if len(c["image"]) > 3:                      # [seed, w, h, 12]: 12-bit samples in uint16
+                from mozjpeg_b200.synth import synth_image12
+                _img_cache[key] = synth_image12(seed, w, h)
+            else:
+                _img_cache[key] = O.synth_image(seed, w, h)
     return _img_cache[key]
 
 

@@ -56,6 +56,17 @@ SWITCH_SETS = [
     ["-fastcrush", "-quality", "75", "-restart", "2"],
     ["-revert", "-restart", "3B"],
 ]
+# 12-bit precision (config 5 semantics and relatives): the reference can only run these with the trellis and the
+# deringing off; optimal Huffman tables are forced (jcmaster.c:1102-1105)
+SWITCH_SETS_12 = [
+    ["-precision", "12", "-sample", "1x1", "-quality", "75", "-notrellis", "-noovershoot", "-baseline"],      # config 5
+    ["-precision", "12", "-quality", "75", "-notrellis", "-noovershoot", "-baseline"],                           # 4:2:0
+    ["-precision", "12", "-quality", "90", "-notrellis", "-noovershoot", "-baseline", "-grayscale"],
+    ["-precision", "12", "-quality", "60", "-notrellis", "-noovershoot", "-fastcrush", "-sample", "2x1"],
+    ["-precision", "12", "-quality", "75", "-notrellis", "-noovershoot", "-fastcrush", "-restart", "1"],
+    ["-precision", "12", "-quality", "100", "-notrellis", "-noovershoot", "-baseline", "-sample", "1x2"],
+]
+SYNTH12 = [(21, 16, 16), (22, 33, 17), (23, 200, 136), (24, 640, 480), (25, 1, 1)]
 SYNTH = [(11, 16, 16), (12, 33, 17), (13, 200, 136), (14, 640, 480), (15, 1, 1), (16, 8, 8), (17, 1920, 1080)]
 
 
@@ -77,6 +88,12 @@ def main():
         for sw in sets:
             a = O.ref_encode(im, sw)
             cases.append({"image": [seed, sw_, sh_], "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
+    from mozjpeg_b200.synth import synth_image12
+    for (seed, sw_, sh_) in SYNTH12:
+        im = synth_image12(seed, sw_, sh_)
+        for sw in SWITCH_SETS_12:
+            a = O.ref_encode(im, sw)
+            cases.append({"image": [seed, sw_, sh_, 12], "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
     assert cases[0]["md5"] == "9a68f56bc76e466aa7e52f415d0f4a5f", "reference build does not reproduce MD5_JPEG_420_ISLOW"
     json.dump({"generator": "tools/make_golden.py", "reference": "mozilla/mozjpeg 5.0.0 (C path, WITH_SIMD=0), oracle/_ref", "cases": cases},
               open(os.path.join(GOLD, "golden.json"), "w"), indent=0)
