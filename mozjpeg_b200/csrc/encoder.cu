@@ -60,6 +60,9 @@ struct Plan {                // everything derived from b200jpeg_params
   Geom g;
   std::vector<ScanDesc> scans;
   bool progressive = false, optimize = false, trellis = false, dering = false, restarts = false;
+  // scan search (optimize_scans): the script of jpeg_search_progression (jcparam.c:733-852) and where its groups start
+  bool search = false; int n_luma = 0, luma_split0 = 0, chroma_split0 = 0, chroma_al0 = 0;
+  std::vector<int> order;        // scan ids in the order they are encoded; position in `order` = slot in out_pos
   RestartSpec rs = {0, 0};
   size_t coef_bytes[4] = {0, 0, 0, 0};
   long long max_scan_blocks = 0, max_real_blocks = 0, sum_real_blocks = 0;
@@ -71,11 +74,11 @@ using namespace b200;
 
 // intermediate HBM state of one chunk in flight
 struct Arena {
-  b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm, d_splits;
+  b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm, d_splits, d_best_al;
   b200::DevBuf d_blk_bits, d_tile_bits, d_tile_base, d_seg_corr, d_mark, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
   b200::Geom g;                      // the plan's geometry with this arena's coefficient pointers
   void release() {
-    b200::DevBuf *db[] = {&d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_splits, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
+    b200::DevBuf *db[] = {&d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_splits, &d_best_al, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
     for (b200::DevBuf *b : db) b->release();
     for (int i = 0; i < 4; i++) { d_coef[i].release(); d_raw[i].release(); d_plain[i].release(); }
   }
@@ -100,11 +103,11 @@ struct b200jpeg_encoder {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_streams = 2;
   // device buffers sized for the WHOLE batch
-  DevBuf d_src, d_tabs_scan, d_tabs_fixed, d_status, d_out_pos, d_scan_size, d_out, d_qt, d_tc;
+  DevBuf d_src, d_tabs_scan, d_tabs_fixed, d_status, d_out_pos, d_scan_size, d_out, d_qt, d_tc, d_best_al_all;
   size_t bitbuf_words_per_image = 0, out_cap_per_image = 0;
   double cap_factor = 0.25;
   // pinned host mirrors
-  PinBuf h_qt, h_tc, h_fixed, h_status, h_out_pos, h_scan_size, h_tabs, h_stage;
+  PinBuf h_qt, h_tc, h_fixed, h_status, h_out_pos, h_scan_size, h_tabs, h_stage, h_best_al;
   // finished files: bump-allocated from pinned arenas, valid until the next encode call
   std::vector<PinBuf> file_arenas; size_t arena_idx = 0, arena_off = 0;
   std::vector<std::pair<uint8_t *, size_t>> files;
@@ -130,6 +133,7 @@ struct ChunkIO {
   uint32_t *status;                 // [n]
   uint32_t *scan_size;              // [nscans][n]
   b200::DevHuff *tabs_scan;         // [n][nscans][8]
+  int *best_al;                     // [2][n] scan search: best luma / chroma Al per image
 };
 
 namespace b200 {
@@ -195,6 +199,30 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
   pl.optimize = p->optimize_coding || pl.progressive || p->data_precision == 12;   // jcmaster.c:1091-1094, :1102-1105
   pl.trellis = p->trellis_quant != 0;
   pl.dering = p->overshoot_deringing != 0;
+  pl.search = p->optimize_scans && p->num_scans > 0;
+  if (pl.search) {
+    // every candidate is buffered with its own scan header; a DRI marker opens it when its restart interval differs from
+    // the previously coded scan's (write_scan_header).  Scans that the search may skip share their neighbours' interval
+    // as long as Cb and Cr have the same geometry, so the flags do not depend on the search's course.
+    int last = 0;
+    for (size_t k = 0; k < pl.scans.size(); k++) { pl.scans[k].dri = pl.scans[k].ri != last; last = pl.scans[k].ri; }
+    if (pl.restarts && g.nc == 3 && (g.c[1].wib != g.c[2].wib || g.c[1].hib != g.c[2].hib)) { set_error("scan search with restart intervals needs equal Cb/Cr geometry"); return B200JPEG_ERR_UNSUPPORTED; }
+  }
+  pl.order.clear();
+  if (pl.search) {
+    // jpeg_search_progression constants: num_scans_luma_dc 1, Al_max_luma 3, 5 frequency splits; chroma: 3 DC scans, Al_max 2
+    pl.n_luma = 1 + (3 * 3 + 2) + (2 * 5 + 1);                  // 23
+    pl.luma_split0 = 1 + 3 * 3 + 2;                             // 12: first luma frequency-split scan (coded at the best luma Al)
+    pl.chroma_al0 = pl.n_luma + 3;                              // 26: first chroma Al-search scan
+    pl.chroma_split0 = pl.n_luma + 3 + (6 * 2 + 4);             // 42
+    const bool colour = nscans > pl.n_luma;
+    if (nscans != (colour ? 64 : 23)) { set_error("optimize_scans needs the script of jpeg_search_progression (%d scans given)", nscans); return B200JPEG_ERR_PARAM; }
+    // phase A: every scan whose parameters are fixed; phase B: the frequency-split scans, coded at the image's best Al
+    for (int si = 0; si < pl.luma_split0; si++) pl.order.push_back(si);
+    if (colour) for (int si = pl.n_luma; si < pl.chroma_split0; si++) pl.order.push_back(si);
+    for (int si = pl.luma_split0; si < pl.n_luma; si++) pl.order.push_back(si);
+    if (colour) for (int si = pl.chroma_split0; si < nscans; si++) pl.order.push_back(si);
+  } else for (int si = 0; si < nscans; si++) pl.order.push_back(si);
   pl.restarts = p->restart_interval != 0 || p->restart_in_rows > 0;
   pl.rs.interval = p->restart_interval; pl.rs.in_rows = p->restart_in_rows;
   return B200JPEG_OK;
@@ -297,7 +325,7 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
   long long total_blocks = 0; for (int ci = 0; ci < g.nc; ci++) total_blocks += g.c[ci].blocks_per_image;
   size_t cap = (size_t)((double)total_blocks * 64 * e->cap_factor) + 65536;
   cap = (cap + 255) & ~(size_t)255;
-  e->bitbuf_words_per_image = cap / 4; e->out_cap_per_image = cap + cap / 64 + 4096;
+  e->bitbuf_words_per_image = cap / 4; e->out_cap_per_image = (cap + cap / 64 + 4096) * (pl.search ? 6 : 1);   // scan search keeps all 64 candidate scans
   const size_t hist_bytes = (size_t)n * HIST_SLOTS * HIST_BINS * 4;
   const size_t tabset = sizeof(DevHuff) * HIST_SLOTS;
   for (int ai = 0; ai < n_arenas; ai++) {
@@ -315,6 +343,7 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
     if ((rc = a.d_bt.reserve((size_t)n * pl.sum_real_blocks * 8))) return rc;
     if ((rc = a.d_perm.reserve((size_t)n * pl.sum_real_blocks * 4))) return rc;
     if ((rc = a.d_splits.reserve((size_t)n * 4 * 2 * 4))) return rc;
+    if ((rc = a.d_best_al.reserve((size_t)n * 2 * 4))) return rc;
     if ((rc = a.d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
     if (pl.progressive) { if ((rc = a.d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = a.d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
     if ((rc = a.d_total_bits.reserve((size_t)n * 8))) return rc;
@@ -334,6 +363,7 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
   if ((rc = e->d_status.reserve((size_t)n_total * 4))) return rc;
   if ((rc = e->d_out_pos.reserve((size_t)n_total * (nscans + 1) * 8))) return rc;
   if ((rc = e->d_scan_size.reserve((size_t)n_total * nscans * 4))) return rc;
+  if ((rc = e->d_best_al_all.reserve((size_t)n_total * 2 * 4))) return rc;
   if ((rc = e->d_out.reserve(e->out_cap_per_image * n_total))) return rc;
   if ((rc = e->d_qt.reserve(sizeof(QuantTables)))) return rc;
   if ((rc = e->d_tc.reserve(sizeof(TrellisConsts)))) return rc;
@@ -425,9 +455,31 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     launch_dummy(g, n, s);
   }
 
-  // ---- scans: huff_opt_pass (statistics -> tables) + output_pass ----
-  for (int si = 0; si < nscans; si++) {
-    const ScanDesc &sd = pl.scans[si];
+  // ---- scans: huff_opt_pass (statistics -> tables) + output_pass.  With the scan search on, all 64 (23) candidate
+  //      scans are coded (the reference codes them one by one into memory buffers, jcmaster.c:668-674); the two
+  //      frequency-split groups are coded at each image's best Al, chosen on the device in between. ----
+  int *best_al = A.d_best_al.as<int>();                       // [2][n]: luma, chroma
+  for (size_t j = 0; j < pl.order.size(); j++) {
+    const int si = pl.order[j];
+    ScanDesc sd = pl.scans[si];
+    if (pl.search) {
+      const bool colour = nscans > pl.n_luma;
+      if (si == pl.luma_split0) {                               // all luma Al-search scans are done: pick the best Al per image
+        AlSearch as; memset(&as, 0, sizeof as);
+        as.first = 1; as.per_al = 3; as.nband = 2; as.al_max = 3; as.nscans_total = nscans;
+        for (int k = 0; k < pl.luma_split0 - 1; k++) as.sd[k] = pl.scans[1 + k];
+        tm.mark("select_al");
+        launch_select_al(g, as, io.tabs_scan, io.scan_size, n, best_al, s);
+        if (colour) {
+          AlSearch ac; memset(&ac, 0, sizeof ac);
+          ac.first = pl.chroma_al0; ac.per_al = 6; ac.nband = 4; ac.al_max = 2; ac.nscans_total = nscans;
+          for (int k = 0; k < pl.chroma_split0 - pl.chroma_al0; k++) ac.sd[k] = pl.scans[pl.chroma_al0 + k];
+          launch_select_al(g, ac, io.tabs_scan, io.scan_size, n, best_al + n, s);
+        }
+      }
+      if (si >= pl.luma_split0 && si < pl.n_luma) sd.al_img = best_al;            // jcmaster.c:477-482
+      if (si >= pl.chroma_split0) sd.al_img = best_al + n;                         // jcmaster.c:483-488
+    }
     const DevHuff *tabs; size_t tstride;
     const bool dc_refine = pl.progressive && sd.Ss == 0 && sd.Ah != 0;
     uint32_t *aux = A.d_blk_aux.as<uint32_t>(), *run_e = A.d_blk_run.as<uint32_t>();
@@ -461,9 +513,10 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
                   A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_mark.as<uint32_t>(), mark_words, status, n, s);
     tm.mark("stuff");
     launch_stuff(A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_total_bits.as<unsigned long long>(), A.d_ff_tile.as<uint32_t>(),
-                 io.out, e->out_cap_per_image, e->out_cap_per_image, io.out_pos + (size_t)si * n, io.out_pos + (size_t)(si + 1) * n,
+                 io.out, e->out_cap_per_image, e->out_cap_per_image, io.out_pos + j * n, io.out_pos + (j + 1) * n,
                  io.scan_size + (size_t)si * n, status, sd.ri ? A.d_mark.as<uint32_t>() : nullptr, mark_words, n, s);
   }
+  if (pl.search) CU(cudaMemcpyAsync(io.best_al, best_al, (size_t)n * 2 * sizeof(int), cudaMemcpyDeviceToDevice, s));   // kept per chunk for the host
   tm.mark("end");
   CU(cudaGetLastError());
   e->last_chunk_i0 = io.i0; e->last_chunk_n = io.n; e->last_chunk_slot = io.slot;
@@ -636,7 +689,8 @@ static int queue_meta(b200jpeg_encoder *e, const ChunkIO &io, int k)
   Plan &pl = e->plan; cudaStream_t s = e->sc[io.slot];
   const int nscans = (int)pl.scans.size();
   CU(cudaMemcpyAsync(e->h_status.as<uint32_t>() + io.i0, io.status, (size_t)io.n * 4, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(e->h_out_pos.as<unsigned long long>() + io.i0, io.out_pos + (size_t)nscans * io.n, (size_t)io.n * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(e->h_out_pos.as<unsigned long long>() + (size_t)io.i0 * (nscans + 1), io.out_pos, (size_t)io.n * (nscans + 1) * 8, cudaMemcpyDeviceToHost, s));
+  if (pl.search) CU(cudaMemcpyAsync(e->h_best_al.as<int>() + (size_t)io.i0 * 2, io.best_al, (size_t)io.n * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(e->h_scan_size.as<uint32_t>() + (size_t)io.i0 * nscans, io.scan_size, (size_t)io.n * nscans * 4, cudaMemcpyDeviceToHost, s));
   if (pl.optimize) {
     size_t ntab = (size_t)io.n * nscans * HIST_SLOTS;
@@ -646,6 +700,106 @@ static int queue_meta(b200jpeg_encoder *e, const ChunkIO &io, int k)
   }
   CU(cudaEventRecord(e->ev_done[k], s));
   return B200JPEG_OK;
+}
+
+// ---- scan search on the host: the decisions of select_scans (jcmaster.c:773-962) replayed on the sizes of the
+// candidate scans.  total[si] = DHT + SOS + entropy-coded bytes of scan si, i.e. what the reference has in
+// master->scan_size[si] (its memory destination receives write_scan_header too, jcmaster.c:668-681; scan 0 also holds
+// the frame header, but scan 0 never enters a comparison). ----
+static unsigned long scan_header_bytes(const Plan &pl, const ScanDesc &sd, const HostHuff *set)
+{
+  unsigned long dht = 0; unsigned seen = 0;
+  for (int i = 0; i < sd.ncomps; i++) {
+    const CompGeom &c = pl.g.c[sd.ci[i]];
+    if (sd.Ss == 0 && sd.Ah == 0 && !((seen >> c.dc_tbl) & 1u)) { seen |= 1u << c.dc_tbl; dht += 17 + huff_len(&set[c.dc_tbl]); }
+    if (sd.Se != 0 && !((seen >> (4 + c.ac_tbl)) & 1u)) { seen |= 1u << (4 + c.ac_tbl); dht += 17 + huff_len(&set[4 + c.ac_tbl]); }
+  }
+  if (dht) dht += 4;
+  return dht + (sd.dri ? 6 : 0) + (2 + 2 + 1 + 2 * sd.ncomps + 3);       // emit_dri: FFDD 0004 xxxx (jcmarker.c)
+}
+static void select_scans_host(const Plan &pl, const b200jpeg_params *p, int num_scans, const unsigned long *scan_size,
+                              std::vector<int> &copy, int &best_Al_luma_out, int &best_Al_chroma_out)
+{
+  const int num_scans_luma = pl.n_luma, num_scans_luma_dc = 1, Al_max_luma = 3, num_scans_chroma_dc = 3, Al_max_chroma = 2;
+  const int luma_freq_split_scan_start = num_scans_luma_dc + 3 * Al_max_luma + 2;
+  const int chroma_freq_split_scan_start = num_scans_luma + num_scans_chroma_dc + (6 * Al_max_chroma + 4);
+  unsigned long best_cost = 0;
+  int best_Al_luma = 0, best_Al_chroma = 0, best_freq_split_idx_luma = 0, best_freq_split_idx_chroma = 0;
+  bool interleave_chroma_dc = false;
+  copy.clear();
+  int scan_number = 0;
+  for (;;) {
+    const int next_scan_number = scan_number + 1;          // finish_pass_master: select_scans(cinfo, master->scan_number + 1)
+    int base_scan_idx = 0;
+    if (next_scan_number > 1 && next_scan_number <= luma_freq_split_scan_start) {
+      if ((next_scan_number - 1) % 3 == 2) {
+        int Al = (next_scan_number - 1) / 3;
+        unsigned long cost = scan_size[next_scan_number - 2] + scan_size[next_scan_number - 1];
+        for (int i = 0; i < Al; i++) cost += scan_size[3 + 3 * i];
+        if (Al == 0 || cost < best_cost) { best_cost = cost; best_Al_luma = Al; }
+        else scan_number = luma_freq_split_scan_start - 1;
+      }
+    } else if (next_scan_number > luma_freq_split_scan_start && next_scan_number <= num_scans_luma) {
+      if (next_scan_number == luma_freq_split_scan_start + 1) { best_freq_split_idx_luma = 0; best_cost = scan_size[next_scan_number - 1]; }
+      else if ((next_scan_number - luma_freq_split_scan_start) % 2 == 1) {
+        int idx = (next_scan_number - luma_freq_split_scan_start) >> 1;
+        unsigned long cost = scan_size[next_scan_number - 2] + scan_size[next_scan_number - 1];
+        if (cost < best_cost) { best_cost = cost; best_freq_split_idx_luma = idx; }
+        if ((idx == 2 && best_freq_split_idx_luma == 0) || (idx == 3 && best_freq_split_idx_luma != 2) || (idx == 4 && best_freq_split_idx_luma != 4))
+          scan_number = num_scans_luma - 1;
+      }
+    } else if (num_scans > num_scans_luma) {
+      if (next_scan_number == num_scans_luma + num_scans_chroma_dc) {
+        base_scan_idx = num_scans_luma;
+        interleave_chroma_dc = scan_size[base_scan_idx] <= scan_size[base_scan_idx + 1] + scan_size[base_scan_idx + 2];
+      } else if (next_scan_number > num_scans_luma + num_scans_chroma_dc && next_scan_number <= chroma_freq_split_scan_start) {
+        base_scan_idx = num_scans_luma + num_scans_chroma_dc;
+        if ((next_scan_number - base_scan_idx) % 6 == 4) {
+          int Al = (next_scan_number - base_scan_idx) / 6;
+          unsigned long cost = scan_size[next_scan_number - 4] + scan_size[next_scan_number - 3] + scan_size[next_scan_number - 2] + scan_size[next_scan_number - 1];
+          for (int i = 0; i < Al; i++) cost += scan_size[base_scan_idx + 4 + 6 * i] + scan_size[base_scan_idx + 5 + 6 * i];
+          if (Al == 0 || cost < best_cost) { best_cost = cost; best_Al_chroma = Al; }
+          else scan_number = chroma_freq_split_scan_start - 1;
+        }
+      } else if (next_scan_number > chroma_freq_split_scan_start && next_scan_number <= num_scans) {
+        if (next_scan_number == chroma_freq_split_scan_start + 2) {
+          best_freq_split_idx_chroma = 0;
+          best_cost = scan_size[next_scan_number - 2] + scan_size[next_scan_number - 1];
+        } else if ((next_scan_number - chroma_freq_split_scan_start) % 4 == 2) {
+          int idx = (next_scan_number - chroma_freq_split_scan_start) >> 2;
+          unsigned long cost = scan_size[next_scan_number - 4] + scan_size[next_scan_number - 3] + scan_size[next_scan_number - 2] + scan_size[next_scan_number - 1];
+          if (cost < best_cost) { best_cost = cost; best_freq_split_idx_chroma = idx; }
+          if ((idx == 2 && best_freq_split_idx_chroma == 0) || (idx == 3 && best_freq_split_idx_chroma != 2) || (idx == 4 && best_freq_split_idx_chroma != 4))
+            scan_number = num_scans - 1;
+        }
+      }
+    }
+    if (scan_number == num_scans - 1) {
+      const int min_Al = std::min(best_Al_luma, best_Al_chroma);
+      copy.push_back(0);
+      if (num_scans > num_scans_luma && p->dc_scan_opt_mode != 0) {
+        base_scan_idx = num_scans_luma;
+        if (interleave_chroma_dc && p->dc_scan_opt_mode != 1) copy.push_back(base_scan_idx);
+        else { copy.push_back(base_scan_idx + 1); copy.push_back(base_scan_idx + 2); }
+      }
+      if (best_freq_split_idx_luma == 0) copy.push_back(luma_freq_split_scan_start);
+      else { copy.push_back(luma_freq_split_scan_start + 2 * (best_freq_split_idx_luma - 1) + 1); copy.push_back(luma_freq_split_scan_start + 2 * (best_freq_split_idx_luma - 1) + 2); }
+      for (int Al = best_Al_luma - 1; Al >= min_Al; Al--) copy.push_back(3 + 3 * Al);
+      if (num_scans > num_scans_luma) {
+        if (best_freq_split_idx_chroma == 0) { copy.push_back(chroma_freq_split_scan_start); copy.push_back(chroma_freq_split_scan_start + 1); }
+        else for (int q = 2; q <= 5; q++) copy.push_back(chroma_freq_split_scan_start + 4 * (best_freq_split_idx_chroma - 1) + q);
+        base_scan_idx = num_scans_luma + num_scans_chroma_dc;
+        for (int Al = best_Al_chroma - 1; Al >= min_Al; Al--) { copy.push_back(base_scan_idx + 6 * Al + 4); copy.push_back(base_scan_idx + 6 * Al + 5); }
+      }
+      for (int Al = min_Al - 1; Al >= 0; Al--) {
+        copy.push_back(3 + 3 * Al);
+        if (num_scans > num_scans_luma) { copy.push_back(base_scan_idx + 6 * Al + 4); copy.push_back(base_scan_idx + 6 * Al + 5); }
+      }
+      break;
+    }
+    scan_number++;
+  }
+  best_Al_luma_out = best_Al_luma; best_Al_chroma_out = best_Al_chroma;
 }
 
 // Chunk k's pipeline has finished: lay out its files in pinned memory, write the
@@ -665,45 +819,69 @@ static int finish_chunk(b200jpeg_encoder *e, const ChunkIO &io, int k)
   if (overflow) return 1;
   const HostHuff *ht = e->h_tabs.as<HostHuff>();
   const uint32_t *ss = e->h_scan_size.as<uint32_t>() + (size_t)io.i0 * nscans;
-  const unsigned long long *pos = e->h_out_pos.as<unsigned long long>() + io.i0;
-  std::vector<uint8_t> hdr; std::vector<size_t> hdr_end(nscans);
+  const unsigned long long *pos = e->h_out_pos.as<unsigned long long>() + (size_t)io.i0 * (nscans + 1);    // [slot][n]
+  std::vector<int> slot_of(nscans);
+  for (size_t j = 0; j < pl.order.size(); j++) slot_of[pl.order[j]] = (int)j;
+  std::vector<uint8_t> hdr; std::vector<size_t> hdr_end;
+  std::vector<int> emit; std::vector<int> actual_al(nscans);
+  std::vector<unsigned long> total(nscans);
   for (int i = 0; i < io.n; i++) {
     const int gi = io.i0 + i;
-    hdr.clear();
+    const HostHuff *img_tabs = pl.optimize ? ht + (size_t)gi * nscans * HIST_SLOTS : nullptr;
+    // which scans go into the file, in which order, with which Al
+    emit.clear();
+    for (int si = 0; si < nscans; si++) actual_al[si] = pl.scans[si].Al;
+    if (pl.search) {
+      const int *dev_al = e->h_best_al.as<int>() + (size_t)io.i0 * 2;
+      int al_l = dev_al[i], al_c = nscans > pl.n_luma ? dev_al[io.n + i] : 0;
+      for (int si = pl.luma_split0; si < pl.n_luma; si++) actual_al[si] = al_l;
+      for (int si = pl.chroma_split0; si < nscans; si++) actual_al[si] = al_c;
+      for (int si = 0; si < nscans; si++) total[si] = scan_header_bytes(pl, pl.scans[si], img_tabs + (size_t)si * HIST_SLOTS) + ss[(size_t)si * io.n + i];
+      int hl = -1, hc = -1;
+      select_scans_host(pl, p, nscans, total.data(), emit, hl, hc);
+      if (hl != al_l || (nscans > pl.n_luma && hc != al_c)) { set_error("scan search: device and host disagree on the best Al (image %d: %d/%d vs %d/%d)", gi, al_l, al_c, hl, hc); return B200JPEG_ERR_CUDA; }
+    } else for (int si = 0; si < nscans; si++) emit.push_back(si);
+    hdr.clear(); hdr_end.assign(emit.size(), 0);
     Bytes o{hdr};
     write_file_header(p, o);
     TblState ts;
     const HostHuff *fixed = pl.optimize ? nullptr : ht;
     for (int t = 0; t < 4; t++) { ts.dc[t] = fixed ? &fixed[t] : nullptr; ts.ac[t] = fixed ? &fixed[4 + t] : nullptr; ts.dc_sent[t] = ts.ac_sent[t] = false; }
     int last_ri = 0;
-    for (int si = 0; si < nscans; si++) {
-      const ScanDesc &sd = pl.scans[si];
+    size_t scan_bytes = 0;
+    for (size_t k2 = 0; k2 < emit.size(); k2++) {
+      const int si = emit[k2];
+      ScanDesc sd = pl.scans[si];
+      sd.Al = actual_al[si];
       if (pl.optimize) {
         uint32_t m = scan_slot_mask(pl, sd);
-        const HostHuff *set = ht + ((size_t)gi * nscans + si) * HIST_SLOTS;
+        const HostHuff *set = img_tabs + (size_t)si * HIST_SLOTS;
         for (int t = 0; t < 4; t++) {
           if (m & (1u << t)) { ts.dc[t] = &set[t]; ts.dc_sent[t] = false; }               // jpeg_gen_optimal_table clears sent_table (jchuff.c:1105)
           if (m & (1u << (4 + t))) { ts.ac[t] = &set[4 + t]; ts.ac_sent[t] = false; }
         }
       }
-      if (si == 0) write_frame_header(p, pl.progressive, o);
+      if (k2 == 0) write_frame_header(p, pl.progressive, o);
+      if (pl.search) last_ri = sd.dri ? -1 : sd.ri;               // the candidate's header as it was buffered when it was coded
       write_scan_header(p, sd, ts, last_ri, (unsigned)sd.ri, o);
-      hdr_end[si] = hdr.size();
+      hdr_end[k2] = hdr.size();
+      scan_bytes += ss[(size_t)si * io.n + i];
     }
-    const size_t total = hdr.size() + (size_t)pos[i] + 2;
-    uint8_t *f = arena_alloc(e, total);
+    const size_t total_file = hdr.size() + scan_bytes + 2;
+    uint8_t *f = arena_alloc(e, total_file);
     if (!f) return B200JPEG_ERR_CUDA;
-    const uint8_t *dsrc = io.out + (size_t)i * e->out_cap_per_image;
+    const uint8_t *dimg = io.out + (size_t)i * e->out_cap_per_image;
     size_t w = 0, hprev = 0;
-    for (int si = 0; si < nscans; si++) {
-      memcpy(f + w, hdr.data() + hprev, hdr_end[si] - hprev); w += hdr_end[si] - hprev; hprev = hdr_end[si];
+    for (size_t k2 = 0; k2 < emit.size(); k2++) {
+      const int si = emit[k2];
+      memcpy(f + w, hdr.data() + hprev, hdr_end[k2] - hprev); w += hdr_end[k2] - hprev; hprev = hdr_end[k2];
       size_t sz = ss[(size_t)si * io.n + i];
-      if (sz) CU(cudaMemcpyAsync(f + w, dsrc, sz, cudaMemcpyDeviceToHost, e->s_out));
-      dsrc += sz; w += sz;
+      if (sz) CU(cudaMemcpyAsync(f + w, dimg + pos[(size_t)slot_of[si] * io.n + i], sz, cudaMemcpyDeviceToHost, e->s_out));
+      w += sz;
     }
     f[w++] = 0xFF; f[w++] = 0xD9;
     e->files[gi] = std::make_pair(f, w);
-    e->last_scan_bytes += (size_t)pos[i];
+    e->last_scan_bytes += scan_bytes;
     e->last_file_bytes += w;
   }
   return B200JPEG_OK;
@@ -753,7 +931,8 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   while ((int)e->ev_done.size() < nchunks) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->ev_done.push_back(ev); }
   if (!device_only) {
     if ((rc = e->h_status.reserve((size_t)n_images * 4))) return rc;
-    if ((rc = e->h_out_pos.reserve((size_t)n_images * 8))) return rc;
+    if ((rc = e->h_out_pos.reserve((size_t)n_images * (nscans + 1) * 8))) return rc;
+    if ((rc = e->h_best_al.reserve((size_t)n_images * 2 * 4))) return rc;
     if ((rc = e->h_scan_size.reserve((size_t)n_images * nscans * 4))) return rc;
     if ((rc = e->h_tabs.reserve((pl.optimize ? (size_t)n_images * nscans : 1) * HIST_SLOTS * sizeof(HostHuff)))) return rc;
   }
@@ -796,6 +975,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
       io.status = e->d_status.as<uint32_t>() + io.i0;
       io.scan_size = e->d_scan_size.as<uint32_t>() + (size_t)io.i0 * nscans;
       io.tabs_scan = e->d_tabs_scan.as<DevHuff>() + (size_t)io.i0 * nscans * HIST_SLOTS;
+      io.best_al = e->d_best_al_all.as<int>() + (size_t)io.i0 * 2;
       if (!on_device) { tm.s = e->sc[io.slot]; tm.mark("h2d_wait"); CU(cudaStreamWaitEvent(e->sc[io.slot], e->ev_in[k], 0)); }
       if ((rc = run_pipeline(e, io, tm))) break;
       if (!device_only) {
@@ -878,10 +1058,10 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
   if (e->s_in) cudaStreamSynchronize(e->s_in);
   if (e->s_out) cudaStreamSynchronize(e->s_out);
   if (e->sc[1]) cudaStreamSynchronize(e->sc[1]);
-  DevBuf *db[] = {&e->d_src, &e->d_tabs_scan, &e->d_tabs_fixed, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_out, &e->d_qt, &e->d_tc};
+  DevBuf *db[] = {&e->d_src, &e->d_tabs_scan, &e->d_tabs_fixed, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_out, &e->d_qt, &e->d_tc, &e->d_best_al_all};
   for (DevBuf *b : db) b->release();
   e->ar[0].release(); e->ar[1].release();
-  PinBuf *pb[] = {&e->h_qt, &e->h_tc, &e->h_fixed, &e->h_status, &e->h_out_pos, &e->h_scan_size, &e->h_tabs, &e->h_stage};
+  PinBuf *pb[] = {&e->h_qt, &e->h_tc, &e->h_fixed, &e->h_status, &e->h_out_pos, &e->h_scan_size, &e->h_tabs, &e->h_stage, &e->h_best_al};
   for (PinBuf *b : pb) b->release();
   for (PinBuf &b : e->file_arenas) b.release();
   for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);

@@ -1875,6 +1875,7 @@ __device__ __forceinline__ void load_block64(const int16_t *__restrict__ blk, in
 __global__ void __launch_bounds__(256) k_prog_flags(Geom g, ScanDesc sd, uint32_t *__restrict__ aux, uint32_t *__restrict__ run_e)
 {
   int img = blockIdx.y;
+  if (sd.al_img) sd.Al = sd.al_img[img];                 // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= sd.nblocks) return;
   int sci, k; long long mcu;
@@ -2030,6 +2031,7 @@ __global__ void __launch_bounds__(256) k_gather_prog(Geom g, ScanDesc sd, const 
 {
   __shared__ unsigned sh[HIST_SLOTS * HIST_BINS];
   int img = blockIdx.y;
+  if (sd.al_img) sd.Al = sd.al_img[img];                 // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
   for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2055,6 +2057,7 @@ __global__ void __launch_bounds__(256) k_block_bits_prog(Geom g, ScanDesc sd, co
   __shared__ ScanTables st;
   __shared__ unsigned ws[8];
   int img = blockIdx.y;
+  if (sd.al_img) sd.Al = sd.al_img[img];                 // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
   if (!(sd.Ss == 0 && sd.Ah != 0)) load_scan_tables(st, tabs, stride, img, g, sd, false);
   __syncthreads();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2085,6 +2088,7 @@ __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const 
 {
   __shared__ ScanTables st;
   int img = blockIdx.y;
+  if (sd.al_img) sd.Al = sd.al_img[img];                 // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
   if (!(sd.Ss == 0 && sd.Ah != 0)) load_scan_tables(st, tabs, stride, img, g, sd, true);
   __syncthreads();
   if (status[img] & ~1u) return;
@@ -2103,6 +2107,55 @@ __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const 
   walk_prog_block(blk, sd, last, a, re, sink);
   if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
   sink.finish();
+}
+
+
+// =====================================================================
+// scan search (optimize_scans), successive-approximation part of select_scans
+// (jcmaster.c:773-962): pick, per image, the point transform Al that minimises
+// the size of {band scans at Al} + {refinement scans below Al}, with the
+// reference's early stop at the first non-improvement.  A scan's size is what
+// the reference buffers for it: DHT + SOS + entropy-coded bytes.
+//   first      : index of the first Al-search scan of the group
+//   per_al     : scans per Al step (luma 3: refine, low band, high band; chroma 6)
+//   nband      : band scans per step (luma 2, chroma 4); nrefine = per_al - nband
+// =====================================================================
+__device__ __forceinline__ unsigned scan_total_bytes(const ScanDesc &sd, const Geom &g, const DevHuff *t /* this image's 8 slots for the scan */, unsigned entropy_bytes)
+{
+  unsigned dht = 0; unsigned seen = 0;
+  for (int i = 0; i < sd.ncomps; i++) {
+    const CompGeom &c = g.c[sd.ci[i]];
+    if (sd.Ss == 0 && sd.Ah == 0 && !((seen >> c.dc_tbl) & 1u)) { seen |= 1u << c.dc_tbl; dht += 17 + t[c.dc_tbl].nsym16; }
+    if (sd.Se != 0 && !((seen >> (4 + c.ac_tbl)) & 1u)) { seen |= 1u << (4 + c.ac_tbl); dht += 17 + t[4 + c.ac_tbl].nsym16; }
+  }
+  if (dht) dht += 4;                                   // one DHT marker holds all of the scan's tables (emit_multi_dht, jcmarker.c:293-401)
+  return dht + (sd.dri ? 6 : 0) + (2 + 2 + 1 + 2 * sd.ncomps + 3) + entropy_bytes;
+}
+__global__ void k_select_al(Geom g, AlSearch as, const DevHuff *__restrict__ tabs_scan, const uint32_t *__restrict__ scan_size, int n, int *__restrict__ best_al)
+{
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= n) return;
+  const DevHuff *timg = tabs_scan + (size_t)img * as.nscans_total * HIST_SLOTS;
+  auto size_of = [&](int si) -> unsigned long long {
+    return scan_total_bytes(as.sd[si - as.first], g, timg + (size_t)si * HIST_SLOTS, scan_size[(size_t)si * n + img]);
+  };
+  const int nref = as.per_al - as.nband;
+  unsigned long long best = 0; int best_Al = 0;
+  for (int Al = 0; Al <= as.al_max; Al++) {
+    // band scans at this Al: the group starts with the nband scans at Al = 0, then per step {refinements, bands at Al+1}
+    const int band0 = Al == 0 ? as.first : as.first + as.nband + (Al - 1) * as.per_al + nref;
+    unsigned long long cost = 0;
+    for (int b = 0; b < as.nband; b++) cost += size_of(band0 + b);
+    for (int i = 0; i < Al; i++) for (int r = 0; r < nref; r++) cost += size_of(as.first + as.nband + i * as.per_al + r);
+    if (Al == 0 || cost < best) { best = cost; best_Al = Al; }
+    else break;                                          // jcmaster.c:800-803 / :861-864
+  }
+  best_al[img] = best_Al;
+}
+void launch_select_al(const Geom &g, const AlSearch &as, const DevHuff *tabs_scan, const uint32_t *scan_size, int n, int *best_al, cudaStream_t s)
+{
+  k_select_al<<<(n + 63) / 64, 64, 0, s>>>(g, as, tabs_scan, scan_size, n, best_al);
+  LAUNCHED();
 }
 
 void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int n, cudaStream_t s)

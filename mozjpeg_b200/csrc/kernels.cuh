@@ -49,6 +49,8 @@ struct ScanDesc {
   int k_first[4], k_count[4];      // first k / number of blocks of scan-component i in the MCU
   int per_row, rows;               // MCUs per row / MCU rows of the scan (jcmaster.c:518-601)
   int ri;                          // restart interval of the scan in MCUs, 0 = none (jcmaster.c:594-599)
+  const int *al_img;               // scan search: per-image Al replacing .Al (device pointer), or nullptr
+  int dri;                         // scan search: this candidate's buffer starts with a DRI marker (its interval differs from the previous scan's)
   long long nblocks;               // per image
 };
 
@@ -125,6 +127,10 @@ size_t stuff_tiles(size_t bitbuf_image_stride_words);     // ff_tile entries per
 void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_image_stride_words, const unsigned long long *total_bits, uint32_t *ff_tile,
                   uint8_t *out, size_t out_image_stride, size_t out_capacity, const unsigned long long *out_start, unsigned long long *out_next,
                   uint32_t *scan_size, uint32_t *status, const uint32_t *mark, size_t mark_stride_words, int n, cudaStream_t s);
+
+// scan search: per-image best point transform of one Al-search group (see k_select_al)
+struct AlSearch { ScanDesc sd[24]; int first, per_al, nband, al_max, nscans_total; };
+void launch_select_al(const Geom &g, const AlSearch &as, const DevHuff *tabs_scan, const uint32_t *scan_size, int n, int *best_al, cudaStream_t s);
 
 extern unsigned long long g_kernel_launches;
 

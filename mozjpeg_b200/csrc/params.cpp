@@ -285,11 +285,15 @@ int b200jpeg_validate(const b200jpeg_params *p) {
   if (p->restart_interval < 0 || p->restart_interval > 65535 || p->restart_in_rows < 0) { set_error("restart interval out of range"); return B200JPEG_ERR_PARAM; }
   if (p->dct_method != B200JPEG_DCT_ISLOW) { set_error("dct_method %d is not on the device path yet (only JDCT_ISLOW)", p->dct_method); return B200JPEG_ERR_UNSUPPORTED; }
   if (p->smoothing_factor) { set_error("input smoothing is not on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
-  if (p->optimize_scans && p->num_scans != 0) { set_error("optimize_scans (scan search) is not on the device path yet; clear it (cjpeg -fastcrush) or drop the scan script (-baseline)"); return B200JPEG_ERR_UNSUPPORTED; }
   if (p->trellis_eob_opt || p->use_scans_in_trellis || p->trellis_q_opt || p->trellis_num_loops != 1 || p->trellis_delta_dc_weight != 0.0f) { set_error("non-default trellis option is not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
   // validate_script (jcmaster.c:252-436)
   bool progressive = false;
-  if (p->num_scans > 0) {
+  if (p->num_scans > 0 && p->optimize_scans) {
+    // "When we optimize scans, there is redundancy in the scan list and this function will fail.
+    //  Therefore skip all this checking" (jcmaster.c:285-291); the device path wants exactly the search script
+    progressive = true;
+    if (p->num_scans != (p->num_components == 1 ? 23 : 64) || (p->num_components != 1 && p->num_components != 3)) { set_error("optimize_scans needs the candidate script of jpeg_search_progression (jpeg_simple_progression with optimize_scans set)"); return B200JPEG_ERR_UNSUPPORTED; }
+  } else if (p->num_scans > 0) {
     if (p->num_scans > B200JPEG_MAX_SCANS) { set_error("Invalid scan script at entry 0"); return B200JPEG_ERR_PARAM; }
     const b200jpeg_scan_info *s = p->scan_info;
     if (s->Ss != 0 && s->Se == 0) { set_error("lossless scan script is out of scope"); return B200JPEG_ERR_UNSUPPORTED; }

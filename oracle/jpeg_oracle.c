@@ -885,7 +885,7 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
   e->p = p; e->nc = p->num_components; e->W = p->image_width; e->H = p->image_height;
   /* 12-bit: no JBUF_REQUANT => no trellis (jccoefct.c:132-138); deringing is not usable at 12 bits (jcdctmgr.c:419) */
   if (p->data_precision == 12 && (p->trellis_quant || p->overshoot_deringing)) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
-  if ((p->data_precision != 8 && p->data_precision != 12) || p->dct_method != B200JPEG_DCT_ISLOW || p->smoothing_factor || p->optimize_scans ||
+  if ((p->data_precision != 8 && p->data_precision != 12) || p->dct_method != B200JPEG_DCT_ISLOW || p->smoothing_factor ||
       p->trellis_eob_opt || p->use_scans_in_trellis || p->trellis_q_opt || p->trellis_num_loops != 1 ||
       p->trellis_delta_dc_weight != 0.0f) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   e->hmax = e->vmax = 1;
@@ -936,6 +936,113 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
     }
     if (dbg) for (ci = 0; ci < e->nc; ci++) { size_t n = (size_t)e->wpad[ci] * e->hpad[ci] * 64 * 2; dbg->final_[ci] = (int16_t *)malloc(n); memcpy(dbg->final_[ci], e->coef[ci], n); }
 
+    if (p->optimize_scans && p->num_scans > 0) {
+      /* scan search: finish_pass_master / select_scans / select_scan_parameters (jcmaster.c:443-515, 773-962, 968-1035)
+       * followed literally: every candidate scan the reference codes is coded into its own buffer (frame header
+       * included for scan 0, scan header for all: the memory destination is installed before write_scan_header,
+       * :668-681), select_scans() runs after each one and may jump ahead, and at the end the chosen buffers are
+       * copied out in the order of :911-957. */
+      const int num_scans_luma_dc = 1, Al_max_luma = 3, nsplits = 5, num_scans_chroma_dc = 3, Al_max_chroma = 2;
+      const int num_scans_luma = num_scans_luma_dc + (3 * Al_max_luma + 2) + (2 * nsplits + 1);
+      const int luma_freq_split_scan_start = num_scans_luma_dc + 3 * Al_max_luma + 2;
+      const int chroma_freq_split_scan_start = num_scans_luma + num_scans_chroma_dc + (6 * Al_max_chroma + 4);
+      bytebuf *sb = (bytebuf *)calloc((size_t)nscans, sizeof(bytebuf));
+      unsigned long best_cost = 0;
+      int best_Al_luma = 0, best_Al_chroma = 0, best_freq_split_idx_luma = 0, best_freq_split_idx_chroma = 0, interleave_chroma_dc = 0;
+      int scan_number = 0, done = 0, i;
+      bytebuf real_out = e->out;
+#define SZ(k) ((unsigned long)sb[k].n)
+#define COPY(k) do { size_t q_; for (q_ = 0; q_ < sb[k].n; q_++) bb_put(&e->out, sb[k].d[q_]); } while (0)
+      if (nscans != ((e->nc == 3) ? 64 : 23)) { free(sb); free(t); return B200JPEG_ERR_PARAM; }
+      while (!done && !e->err) {
+        scan_t sc = scans[scan_number]; int k, next_scan_number, base_scan_idx = 0; unsigned ri;
+        /* select_scan_parameters :477-488: the frequency-split scans are coded at the best Al found so far */
+        if (scan_number >= luma_freq_split_scan_start && scan_number < num_scans_luma) sc.Al = best_Al_luma;
+        if (scan_number >= chroma_freq_split_scan_start && scan_number < nscans) sc.Al = best_Al_chroma;
+        if (!(sc.Ss == 0 && sc.Ah != 0)) gather_scan(e, &sc, 0, t);
+        memset(&e->out, 0, sizeof e->out);
+        if (scan_number == 0) write_frame_header(e);
+        ri = p->restart_interval;
+        if (p->restart_in_rows > 0) { long nominal = (long)p->restart_in_rows * scan_mcus_per_row(e, &sc); ri = (unsigned)(nominal < 65535L ? nominal : 65535L); }
+        write_scan_header(e, &sc, ri);
+        memset(t, 0, sizeof *t); t->e = e; t->s = &sc; t->gather = 0; t->bw.o = &e->out;
+        for (k = 0; k < 4; k++) { orc_make_derived(&e->dc_tbl[k], 1, t->dco[k], t->dsi[k]); orc_make_derived(&e->ac_tbl[k], 0, t->aco[k], t->asi[k]); }
+        run_scan(t);
+        sb[scan_number] = e->out;
+        /* select_scans(cinfo, scan_number + 1) */
+        next_scan_number = scan_number + 1;
+        if (next_scan_number > 1 && next_scan_number <= luma_freq_split_scan_start) {
+          if ((next_scan_number - 1) % 3 == 2) {
+            int Al = (next_scan_number - 1) / 3; unsigned long cost = SZ(next_scan_number - 2) + SZ(next_scan_number - 1);
+            for (i = 0; i < Al; i++) cost += SZ(3 + 3 * i);
+            if (Al == 0 || cost < best_cost) { best_cost = cost; best_Al_luma = Al; }
+            else scan_number = luma_freq_split_scan_start - 1;
+          }
+        } else if (next_scan_number > luma_freq_split_scan_start && next_scan_number <= num_scans_luma) {
+          if (next_scan_number == luma_freq_split_scan_start + 1) { best_freq_split_idx_luma = 0; best_cost = SZ(next_scan_number - 1); }
+          else if ((next_scan_number - luma_freq_split_scan_start) % 2 == 1) {
+            int idx = (next_scan_number - luma_freq_split_scan_start) >> 1; unsigned long cost = SZ(next_scan_number - 2) + SZ(next_scan_number - 1);
+            if (cost < best_cost) { best_cost = cost; best_freq_split_idx_luma = idx; }
+            if ((idx == 2 && best_freq_split_idx_luma == 0) || (idx == 3 && best_freq_split_idx_luma != 2) || (idx == 4 && best_freq_split_idx_luma != 4))
+              scan_number = num_scans_luma - 1;
+          }
+        } else if (nscans > num_scans_luma) {
+          if (next_scan_number == num_scans_luma + num_scans_chroma_dc) {
+            base_scan_idx = num_scans_luma;
+            interleave_chroma_dc = SZ(base_scan_idx) <= SZ(base_scan_idx + 1) + SZ(base_scan_idx + 2);
+          } else if (next_scan_number > num_scans_luma + num_scans_chroma_dc && next_scan_number <= chroma_freq_split_scan_start) {
+            base_scan_idx = num_scans_luma + num_scans_chroma_dc;
+            if ((next_scan_number - base_scan_idx) % 6 == 4) {
+              int Al = (next_scan_number - base_scan_idx) / 6;
+              unsigned long cost = SZ(next_scan_number - 4) + SZ(next_scan_number - 3) + SZ(next_scan_number - 2) + SZ(next_scan_number - 1);
+              for (i = 0; i < Al; i++) { cost += SZ(base_scan_idx + 4 + 6 * i); cost += SZ(base_scan_idx + 5 + 6 * i); }
+              if (Al == 0 || cost < best_cost) { best_cost = cost; best_Al_chroma = Al; }
+              else scan_number = chroma_freq_split_scan_start - 1;
+            }
+          } else if (next_scan_number > chroma_freq_split_scan_start && next_scan_number <= nscans) {
+            if (next_scan_number == chroma_freq_split_scan_start + 2) { best_freq_split_idx_chroma = 0; best_cost = SZ(next_scan_number - 2) + SZ(next_scan_number - 1); }
+            else if ((next_scan_number - chroma_freq_split_scan_start) % 4 == 2) {
+              int idx = (next_scan_number - chroma_freq_split_scan_start) >> 2;
+              unsigned long cost = SZ(next_scan_number - 4) + SZ(next_scan_number - 3) + SZ(next_scan_number - 2) + SZ(next_scan_number - 1);
+              if (cost < best_cost) { best_cost = cost; best_freq_split_idx_chroma = idx; }
+              if ((idx == 2 && best_freq_split_idx_chroma == 0) || (idx == 3 && best_freq_split_idx_chroma != 2) || (idx == 4 && best_freq_split_idx_chroma != 4))
+                scan_number = nscans - 1;
+            }
+          }
+        }
+        if (scan_number == nscans - 1) {
+          int Al, min_Al = best_Al_luma < best_Al_chroma ? best_Al_luma : best_Al_chroma;
+          e->out = real_out;
+          COPY(0);
+          if (nscans > num_scans_luma && p->dc_scan_opt_mode != 0) {
+            base_scan_idx = num_scans_luma;
+            if (interleave_chroma_dc && p->dc_scan_opt_mode != 1) COPY(base_scan_idx);
+            else { COPY(base_scan_idx + 1); COPY(base_scan_idx + 2); }
+          }
+          if (best_freq_split_idx_luma == 0) COPY(luma_freq_split_scan_start);
+          else { COPY(luma_freq_split_scan_start + 2 * (best_freq_split_idx_luma - 1) + 1); COPY(luma_freq_split_scan_start + 2 * (best_freq_split_idx_luma - 1) + 2); }
+          for (Al = best_Al_luma - 1; Al >= min_Al; Al--) COPY(3 + 3 * Al);
+          if (nscans > num_scans_luma) {
+            if (best_freq_split_idx_chroma == 0) { COPY(chroma_freq_split_scan_start); COPY(chroma_freq_split_scan_start + 1); }
+            else { int q2; for (q2 = 2; q2 <= 5; q2++) COPY(chroma_freq_split_scan_start + 4 * (best_freq_split_idx_chroma - 1) + q2); }
+            base_scan_idx = num_scans_luma + num_scans_chroma_dc;
+            for (Al = best_Al_chroma - 1; Al >= min_Al; Al--) { COPY(base_scan_idx + 6 * Al + 4); COPY(base_scan_idx + 6 * Al + 5); }
+          }
+          for (Al = min_Al - 1; Al >= 0; Al--) {
+            COPY(3 + 3 * Al);
+            if (nscans > num_scans_luma) { COPY(base_scan_idx + 6 * Al + 4); COPY(base_scan_idx + 6 * Al + 5); }
+          }
+          real_out = e->out;
+          done = 1;
+        }
+        scan_number++;
+      }
+      e->out = real_out;
+      for (i = 0; i < nscans; i++) free(sb[i].d);
+      free(sb);
+#undef SZ
+#undef COPY
+    } else
     for (si = 0; si < nscans && !e->err; si++) {
       const scan_t *s = &scans[si]; size_t before; int k;
       unsigned ri;

@@ -35,7 +35,8 @@ def _golden(switches):
 
 
 DEVICE_SETS = [["-baseline", "-quality", "75"], ["-quality", "75", "-fastcrush"], ["-revert", "-dct", "int"],
-               ["-baseline", "-notrellis", "-quality", "75"], ["-revert", "-optimize", "-grayscale"]]
+               ["-baseline", "-notrellis", "-quality", "75"], ["-revert", "-optimize", "-grayscale"],
+               ["-quality", "75"]]                      # the library default: 64-candidate scan search
 
 
 @need_files
@@ -56,12 +57,12 @@ def test_reference_cjpeg_runs_on_the_device(sw, tmp_path):
 @need_files
 @pytest.mark.gpu
 def test_unsupported_parameters_fall_through_to_the_reference(tmp_path):
-    """Scan search (the library default) is not on the device path: the shim must hand the image to
-    the reference's own implementation, and say so."""
-    r, data = _run(["-quality", "75"], {}, tmp_path)
+    """Input smoothing is not on the device path: the shim must hand the image to the reference's own
+    implementation, and say so."""
+    r, data = _run(["-quality", "75", "-smooth", "10"], {}, tmp_path)
     assert r.returncode == 0, r.stderr
     assert "reference path" in r.stderr
-    plain = subprocess.run([CJPEG, "-quality", "75", PPM], capture_output=True, timeout=300)
+    plain = subprocess.run([CJPEG, "-quality", "75", "-smooth", "10", PPM], capture_output=True, timeout=300)
     assert data == plain.stdout
 
 

@@ -55,6 +55,19 @@ SWITCH_SETS = [
     ["-baseline", "-quality", "75", "-restart", "1"],
     ["-fastcrush", "-quality", "75", "-restart", "2"],
     ["-revert", "-restart", "3B"],
+    # the library default: 64-scan (23 for gray) search, jcparam.c:733-852 + jcmaster.c:773-962
+    ["-quality", "75"],
+    ["-quality", "90"],
+    ["-quality", "50", "-sample", "2x2"],
+    ["-grayscale", "-quality", "75"],
+    ["-quality", "75", "-restart", "1"],
+    ["-quality", "85", "-notrellis"],
+]
+# through the reference's cjpeg binary only (our refshim driver does not parse these switches)
+CJPEG_ONLY = [
+    ["-quality", "75", "-dc-scan-opt", "2"],
+    ["-quality", "60", "-dc-scan-opt", "1"],
+    ["-quality", "85", "-dc-scan-opt", "0"],
 ]
 # 12-bit precision (config 5 semantics and relatives): the reference can only run these with the trellis and the
 # deringing off; optimal Huffman tables are forced (jcmaster.c:1102-1105)
@@ -82,9 +95,12 @@ def main():
         b = O.ref_encode(img, sw)                  # our driver around the reference library
         assert a == b, ("refshim disagrees with cjpeg", sw)
         cases.append({"image": "testorig", "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
+    for sw in CJPEG_ONLY:
+        a = O.ref_cjpeg(ppm, sw)
+        cases.append({"image": "testorig", "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
     for (seed, sw_, sh_) in SYNTH:
         im = O.synth_image(seed, sw_, sh_)
-        sets = SWITCH_SETS if sw_ * sh_ <= 640 * 480 else [s for s in SWITCH_SETS if s in (["-revert", "-dct", "int"], ["-baseline", "-quality", "75", "-sample", "2x2"], ["-fastcrush", "-quality", "75", "-sample", "2x2"], ["-baseline", "-quality", "90", "-sample", "2x2"])]
+        sets = SWITCH_SETS if sw_ * sh_ <= 640 * 480 else [s for s in SWITCH_SETS if s in (["-revert", "-dct", "int"], ["-baseline", "-quality", "75", "-sample", "2x2"], ["-fastcrush", "-quality", "75", "-sample", "2x2"], ["-baseline", "-quality", "90", "-sample", "2x2"], ["-quality", "75"])]
         for sw in sets:
             a = O.ref_encode(im, sw)
             cases.append({"image": [seed, sw_, sh_], "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
