@@ -435,7 +435,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
         tm.mark("trellis_stats");
         CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
         launch_seed_hist(A.d_hist.as<uint32_t>(), 4 + g.c[ci].ac_tbl, n, s);
-        launch_prog_prepare(g, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), n, s);
+        launch_prog_prepare(g, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), A.d_tile_bits.as<int>(), A.d_tile_base.as<int>(), n, s);
         launch_gather_prog(g, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), A.d_hist.as<uint32_t>(), status, n, s);
         tm.mark("trellis_tables");
         SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = 1u << (4 + g.c[ci].ac_tbl);
@@ -483,7 +483,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     const DevHuff *tabs; size_t tstride;
     const bool dc_refine = pl.progressive && sd.Ss == 0 && sd.Ah != 0;
     uint32_t *aux = A.d_blk_aux.as<uint32_t>(), *run_e = A.d_blk_run.as<uint32_t>();
-    if (pl.progressive && sd.Ss != 0) { tm.mark("eobrun_runs"); launch_prog_prepare(g, sd, aux, run_e, n, s); }
+    if (pl.progressive && sd.Ss != 0) { tm.mark("eobrun_runs"); launch_prog_prepare(g, sd, aux, run_e, A.d_tile_bits.as<int>(), A.d_tile_base.as<int>(), n, s); }
     if (pl.optimize) {
       DevHuff *tset = io.tabs_scan + (size_t)si * HIST_SLOTS;                              // [img][scan][8]
       tstride = tabset * nscans;

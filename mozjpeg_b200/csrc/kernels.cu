@@ -1872,32 +1872,121 @@ __device__ __forceinline__ void load_block64(const int16_t *__restrict__ blk, in
   }
 }
 
-__global__ void __launch_bounds__(256) k_prog_flags(Geom g, ScanDesc sd, uint32_t *__restrict__ aux, uint32_t *__restrict__ run_e)
+// A block is a run BOUNDARY if it breaks the pending EOBRUN (AUX_BRK), or opens the scan or a restart segment.
+// tile_last / tile_first[img][tile]: largest / smallest boundary index inside the tile (-1 / INT_MAX if none).
+__global__ void __launch_bounds__(256) k_prog_flags(Geom g, ScanDesc sd, uint32_t *__restrict__ aux, uint32_t *__restrict__ run_e,
+                                                    int *__restrict__ tile_last, int *__restrict__ tile_first)
 {
+  __shared__ int smax[8], smin[8];
   int img = blockIdx.y;
   if (sd.al_img) sd.Al = sd.al_img[img];                 // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= sd.nblocks) return;
-  int sci, k; long long mcu;
-  const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
-  int v[64];
-  load_block64(blk, v);
-  unsigned brk = 0, contrib, tail = 0;
-  if (sd.Ah == 0) {
-    int lastnz = 0;
+  int bmax = -1, bmin = 0x7fffffff;
+  if (t < sd.nblocks) {
+    int sci, k; long long mcu;
+    const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+    int v[64];
+    load_block64(blk, v);
+    unsigned brk = 0, contrib, tail = 0;
+    if (sd.Ah == 0) {
+      int lastnz = 0;
 #pragma unroll
-    for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && (abs(v[i]) >> sd.Al) != 0) { brk = 1; lastnz = i; }
-    contrib = (lastnz != sd.Se);
-  } else {
-    int lastone = 0;
+      for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && (abs(v[i]) >> sd.Al) != 0) { brk = 1; lastnz = i; }
+      contrib = (lastnz != sd.Se);
+    } else {
+      int lastone = 0;
 #pragma unroll
-    for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && (abs(v[i]) >> sd.Al) == 1) { brk = 1; lastone = i; }
+      for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && (abs(v[i]) >> sd.Al) == 1) { brk = 1; lastone = i; }
 #pragma unroll
-    for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && i > lastone && (abs(v[i]) >> sd.Al) > 1) tail++;
-    contrib = (lastone != sd.Se);
+      for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && i > lastone && (abs(v[i]) >> sd.Al) > 1) tail++;
+      contrib = (lastone != sd.Se);
+    }
+    aux[(size_t)img * sd.nblocks + t] = brk | (contrib << 1) | (tail << 2);
+    run_e[(size_t)img * sd.nblocks + t] = 0;
+    if (brk || t == 0 || (sd.ri && t % sd.ri == 0)) bmax = bmin = (int)t;
   }
-  aux[(size_t)img * sd.nblocks + t] = brk | (contrib << 1) | (tail << 2);
-  run_e[(size_t)img * sd.nblocks + t] = 0;
+  for (int o = 16; o; o >>= 1) { bmax = max(bmax, __shfl_xor_sync(0xffffffffu, bmax, o)); bmin = min(bmin, __shfl_xor_sync(0xffffffffu, bmin, o)); }
+  if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = bmax; smin[threadIdx.x >> 5] = bmin; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) { bmax = max(bmax, smax[i]); bmin = min(bmin, smin[i]); }
+    tile_last[(size_t)img * gridDim.x + blockIdx.x] = bmax; tile_first[(size_t)img * gridDim.x + blockIdx.x] = bmin;
+  }
+}
+// per image: tile_last -> running maximum over the tiles up to and including each tile; tile_first -> running
+// minimum over the tiles from each tile to the end
+__global__ void __launch_bounds__(256) k_prog_tile_scan(int ntiles, int *__restrict__ tile_last, int *__restrict__ tile_first)
+{
+  int *tl = tile_last + (size_t)blockIdx.x * ntiles, *tf = tile_first + (size_t)blockIdx.x * ntiles;
+  __shared__ int carry, wsm[8];
+  if (threadIdx.x == 0) carry = -1;
+  __syncthreads();
+  for (int base = 0; base < ntiles; base += 256) {
+    int i = base + threadIdx.x, v = i < ntiles ? tl[i] : -1;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o) v = max(v, y); }
+    if ((threadIdx.x & 31) == 31) wsm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int pre = carry;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) pre = max(pre, wsm[w]);
+    v = max(v, pre);
+    if (i < ntiles) tl[i] = v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry = v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) carry = 0x7fffffff;
+  __syncthreads();
+  for (int base = 0; base < ntiles; base += 256) {             // from the last tile backwards
+    int i = ntiles - 1 - (base + threadIdx.x), v = i >= 0 ? tf[i] : 0x7fffffff;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o) v = min(v, y); }
+    if ((threadIdx.x & 31) == 31) wsm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int pre = carry;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) pre = min(pre, wsm[w]);
+    v = min(v, pre);
+    if (i >= 0) tf[i] = v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry = v;
+    __syncthreads();
+  }
+}
+// EOBRUN values of a FIRST scan (Ah == 0: no correction bits, so a run is only cut every 0x7FFF blocks,
+// jcphuff.c:727-729): every member of a run knows the run's start (last boundary at or before it) and end (next
+// boundary after it); the first block of each sub-run of 0x7FFF members owns the sub-run's EOBRUN symbol.
+__global__ void __launch_bounds__(256) k_prog_runs_first(ScanDesc sd, const uint32_t *__restrict__ aux, uint32_t *__restrict__ run_e,
+                                                         const int *__restrict__ tile_last, const int *__restrict__ tile_first)
+{
+  __shared__ int sprev[8], snext[8];
+  const int img = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t *a = aux + (size_t)img * sd.nblocks;
+  unsigned f = 0; bool boundary = false;
+  if (t < sd.nblocks) { f = a[t]; boundary = (f & AUX_BRK) || t == 0 || (sd.ri && t % sd.ri == 0); }
+  // last boundary at or before t inside the tile / first boundary after t inside the tile
+  int pv = boundary ? (int)t : -1;
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, pv, o); if (lane >= o) pv = max(pv, y); }
+  int nv = boundary ? (int)t : 0x7fffffff;
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_down_sync(0xffffffffu, nv, o); if (lane + o < 32) nv = min(nv, y); }
+  int nstrict = __shfl_down_sync(0xffffffffu, nv, 1); if (lane == 31) nstrict = 0x7fffffff;
+  if (lane == 31) sprev[wid] = pv;
+  if (lane == 0) snext[wid] = nv;
+  __syncthreads();
+  for (int w = 0; w < wid; w++) pv = max(pv, sprev[w]);
+  for (int w = wid + 1; w < 8; w++) nstrict = min(nstrict, snext[w]);
+  if (t >= sd.nblocks) return;
+  const int *tl = tile_last + (size_t)img * gridDim.x, *tf = tile_first + (size_t)img * gridDim.x;
+  if (pv < 0) pv = tl[blockIdx.x - 1];                               // block 0 is a boundary, so tile 0 always has one
+  if (nstrict == 0x7fffffff && blockIdx.x + 1 < gridDim.x) nstrict = tf[blockIdx.x + 1];
+  const long long nb = nstrict == 0x7fffffff ? sd.nblocks : (long long)nstrict;
+  const long long b = pv;
+  const unsigned fb = (b == t) ? f : a[b];
+  const bool b_brk = fb & AUX_BRK;
+  const long long cb = b_brk ? ((fb & AUX_CONTRIB) ? 1 : 0) : 0;
+  // members of the run: the boundary itself unless it is a breaker that does not end in an EOB, then every block up to nb
+  const long long first_member = b_brk ? (cb ? b : b + 1) : b;
+  if (t < first_member) return;
+  const long long off = t - first_member, total = nb - first_member;
+  if (off % 0x7FFF == 0) run_e[(size_t)img * sd.nblocks + t] = (uint32_t)min(0x7FFFLL, total - off);
 }
 
 __global__ void __launch_bounds__(256) k_prog_runs(ScanDesc sd, const uint32_t *__restrict__ aux, uint32_t *__restrict__ run_e)
@@ -2158,12 +2247,15 @@ void launch_select_al(const Geom &g, const AlSearch &as, const DevHuff *tabs_sca
   LAUNCHED();
 }
 
-void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int n, cudaStream_t s)
+void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int *tile_last, int *tile_first, int n, cudaStream_t s)
 {
   if (sd.Ss == 0) return;
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  k_prog_flags<<<grid, 256, 0, s>>>(g, sd, aux, run_e); LAUNCHED();
-  k_prog_runs<<<grid, 256, 0, s>>>(sd, aux, run_e); LAUNCHED();
+  k_prog_flags<<<grid, 256, 0, s>>>(g, sd, aux, run_e, tile_last, tile_first); LAUNCHED();
+  if (sd.Ah == 0) {
+    k_prog_tile_scan<<<n, 256, 0, s>>>((int)grid.x, tile_last, tile_first); LAUNCHED();
+    k_prog_runs_first<<<grid, 256, 0, s>>>(sd, aux, run_e, tile_last, tile_first); LAUNCHED();
+  } else { k_prog_runs<<<grid, 256, 0, s>>>(sd, aux, run_e); LAUNCHED(); }
 }
 void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
 {
