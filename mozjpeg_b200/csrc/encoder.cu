@@ -250,6 +250,8 @@ static void make_quant_consts(const b200jpeg_params *p, QuantTables *qt)
     qt->L[t] = L;
     qt->fast[t] = (((1ull << (18 + L)) + dmin - 1) / dmin) < (1ull << 32) ? 1 : 0;
     for (int i = 0; i < 64; i++) { unsigned d = qt->q[t][i].d; qt->q[t][i].mul2 = qt->fast[t] ? (uint32_t)(((1ull << (18 + L)) + d - 1) / d) : 0; }
+    static const double aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0, 0.785694958, 0.541196100, 0.275899379};
+    for (int i = 0; i < 64; i++) qt->fdiv[t][i] = (float)(1.0 / (((double)p->quant_tbl[t][i] * aan[i / 8] * aan[i % 8] * 8.0)));       // jcdctmgr.c:371-374
   }
 }
 static void make_trellis_consts(const b200jpeg_params *p, TrellisConsts *tc)
@@ -261,7 +263,15 @@ static void make_trellis_consts(const b200jpeg_params *p, TrellisConsts *tc)
       int q = p->quant_tbl[t][kZigzag[k]];
       tc->w_zz[t][k] = (float)(1.0 / (q * q));                       // jcdctmgr.c:1020 (double divide, float store)
       tc->q8_zz[t][k] = 8 * q;
+
     }
+  }
+  for (int t = 0; t < 4; t++) {
+    if (!p->quant_tbl_present[t]) continue;
+    unsigned dmax = 1; for (int k = 0; k < 64; k++) dmax = std::max(dmax, 8u * p->quant_tbl[t][k]);
+    int L = 0; while ((1ull << L) < dmax) L++;
+    tc->qL[t] = L;
+    for (int k = 0; k < 64; k++) { unsigned d = 8u * p->quant_tbl[t][kZigzag[k]]; tc->qmul_zz[t][k] = (unsigned)std::min<unsigned long long>(((1ull << (18 + L)) + d - 1) / d, 0xFFFFFFFFull); }
   }
   tc->use_norm = p->lambda_log_scale2 > 0.0f;
   tc->p1 = pow(2.0, (double)p->lambda_log_scale1);
@@ -373,6 +383,11 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
 
   make_quant_consts(p, e->h_qt.as<QuantTables>());
   make_trellis_consts(p, e->h_tc.as<TrellisConsts>());
+  if (pl.trellis) for (int t = 0; t < 4; t++) {
+    if (!p->quant_tbl_present[t]) continue;
+    unsigned dmin = ~0u; for (int k = 0; k < 64; k++) dmin = std::min(dmin, 8u * p->quant_tbl[t][k]);
+    if ((((1ull << (18 + e->h_tc.as<TrellisConsts>()->qL[t])) + dmin - 1) / dmin) >= (1ull << 32)) { set_error("trellis quantization: quantization table %d mixes values too far apart for the device divider", t); return B200JPEG_ERR_UNSUPPORTED; }
+  }
   {
     DevHuff *f = e->h_fixed.as<DevHuff>();
     for (int t = 0; t < 4; t++) {
@@ -404,7 +419,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   for (int ci = 0; ci < g.nc; ci++) { rl.comp_off[ci] = rl.per_image; rl.per_image += (long long)g.c[ci].wib * g.c[ci].hib; }
   tm.mark("forward");
   int qfast = 1; for (int ci = 0; ci < g.nc; ci++) qfast &= e->h_qt.as<QuantTables>()->fast[g.c[ci].qt];
-  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), qfast, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, e->keep_plain ? 1 : 0, n, s);
+  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), qfast, p->dct_method, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, e->keep_plain ? 1 : 0, n, s);
   tm.mark("dummy");
   launch_dummy(g, n, s);
 
@@ -915,11 +930,11 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   e->params = *p; e->n = n_images;
   if ((rc = build_plan(p, row_pitch, image_stride, e->plan))) return rc;
   Plan &pl = e->plan;
-  if (p->data_precision == 12) {
+  if (p->data_precision == 12 || p->dct_method == B200JPEG_DCT_FLOAT) {
     const Geom &g = pl.g;
     bool gray = g.nc == 1 && g.hmax == 1 && g.vmax == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
     bool ycc = g.nc == 3 && g.cs_mode == 0 && g.in_comps == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax && g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
-    if (!gray && !ycc) { set_error("12-bit precision: only RGB->YCbCr 4:4:4/4:2:2/4:4:0/4:2:0 and grayscale layouts are on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
+    if (!gray && !ycc) { set_error("12-bit precision / float DCT: only RGB->YCbCr 4:4:4/4:2:2/4:4:0/4:2:0 and grayscale layouts are on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
   }
   const int nscans = (int)pl.scans.size();
   const int C = choose_chunk(e, pl, n_images, !on_device);

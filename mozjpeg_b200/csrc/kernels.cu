@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
 // =====================================================================
 template <int PREC> struct WorkT { typedef int16_t type; };
 template <> struct WorkT<12> { typedef int type; };
+template <> struct WorkT<32> { typedef float type; };
 // One row of 8 pixels of the strip in registers: IC samples per pixel, SB bytes per sample
 // (8-bit: 24 bytes RGB / 8 grey; 12-bit in uint16: 48 / 16).
 struct Px8 { unsigned w[12]; };
@@ -277,7 +278,54 @@ __device__ __forceinline__ int quant_fast(int x, uint2 k, int L, int dering)
   return x < 0 ? -q : q;
 }
 
-template <int HMAX, int VMAX, int NC, bool QFAST, int PREC>
+// ---- JDCT_FLOAT (jfdctflt.c:59-167, AA&N): one 1-D pass, fp32, no contraction ----
+__device__ __forceinline__ void fdct_float_1d(float &d0, float &d1, float &d2, float &d3, float &d4, float &d5, float &d6, float &d7)
+{
+  float tmp0 = d0 + d7, tmp7 = d0 - d7, tmp1 = d1 + d6, tmp6 = d1 - d6;
+  float tmp2 = d2 + d5, tmp5 = d2 - d5, tmp3 = d3 + d4, tmp4 = d3 - d4;
+  float tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  d0 = tmp10 + tmp11; d4 = tmp10 - tmp11;
+  float z1 = (tmp12 + tmp13) * 0.707106781f;
+  d2 = tmp13 + z1; d6 = tmp13 - z1;
+  tmp10 = tmp4 + tmp5; tmp11 = tmp5 + tmp6; tmp12 = tmp6 + tmp7;
+  float z5 = (tmp10 - tmp12) * 0.382683433f;
+  float z2 = 0.541196100f * tmp10 + z5;
+  float z4 = 1.306562965f * tmp12 + z5;
+  float z3 = tmp11 * 0.707106781f;
+  float z11 = tmp7 + z3, z13 = tmp7 - z3;
+  d5 = z13 + z2; d3 = z13 - z2; d1 = z11 + z4; d7 = z11 - z4;
+}
+// float_preprocess_deringing (jcdctmgr.c:503-575) on 64 floats in natural order; catmull_rom takes DCTELEM (int)
+// values, so the float slopes are truncated on the way in
+__device__ __forceinline__ void deringing_block_float(float *data, int q0, float sum, int cnt)
+{
+  const float maxsample = 127.0f; const int size = 64;
+  const int a = min(31, 2 * q0); const float bq = (maxsample * size - sum) / (float)cnt;
+  const float maxovershoot = maxsample + ((float)a < bq ? (float)a : bq);
+  int n = 0;
+  do {
+    if (data[c_zz[n]] < maxsample) { n++; continue; }
+    int start = n;
+    while (++n < size && data[c_zz[n]] >= maxsample) {}
+    int end = n;
+    float f1 = data[c_zz[start >= 1 ? start - 1 : 0]], f2 = data[c_zz[start >= 2 ? start - 2 : 0]];
+    float l1 = data[c_zz[end < size - 1 ? end : size - 1]], l2 = data[c_zz[end < size - 2 ? end + 1 : size - 1]];
+    float fslope = fmaxf(f1 - f2, maxsample - f1), lslope = fmaxf(l1 - l2, maxsample - l1);
+    if (start == 0) fslope = lslope;
+    if (end == size) lslope = fslope;
+    int length = end - start;
+    float step = 1.f / (float)(length + 1), position = step;
+    for (int i = start; i < end; i++, position += step) {
+      float tmp = catmull_rom((int)(maxsample - fslope), 127, 127, (int)(maxsample - lslope), position, length);
+      data[c_zz[i]] = tmp < maxovershoot ? tmp : maxovershoot;
+    }
+    n++;
+  } while (n < size);
+}
+__constant__ double c_aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0, 0.785694958, 0.541196100, 0.275899379};
+
+// DCTM: 0 = JDCT_ISLOW, 2 = JDCT_FLOAT (8-bit only)
+template <int HMAX, int VMAX, int NC, bool QFAST, int PREC, int DCTM>
 __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *__restrict__ src,
                                                       const QuantTables *__restrict__ qt, int dering,
                                                       DcRec *__restrict__ rec, RecLayout rl, int write_raw)
@@ -291,7 +339,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   constexpr int SB = PREC == 8 ? 1 : 2;                  // bytes per sample (12-bit samples come as uint16)
   constexpr int P1 = PREC == 8 ? 2 : 1;                  // PASS1_BITS
   constexpr int CENTRE = 1 << (PREC - 1);
-  typedef typename WorkT<PREC>::type wtype;              // row-pass results: int16 holds them at 8 bits, not at 12
+  typedef typename WorkT<DCTM == 2 ? 32 : PREC>::type wtype;   // row-pass results: int16 holds them at 8 bits, int32 at 12, float for JDCT_FLOAT
   __shared__ __align__(16) int16_t sY[TR * YP];
   __shared__ __align__(16) int16_t sC[NC == 3 ? 2 * 8 * CP : 8];
   __shared__ __align__(16) wtype sW[NB * 72];
@@ -388,6 +436,31 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
     const uint4 rv = *reinterpret_cast<const uint4 *>(rowp);
     int d0 = (int)(int16_t)(rv.x & 0xFFFF), d1 = (int)rv.x >> 16, d2 = (int)(int16_t)(rv.y & 0xFFFF), d3 = (int)rv.y >> 16;
     int d4 = (int)(int16_t)(rv.z & 0xFFFF), d5 = (int)rv.z >> 16, d6 = (int)(int16_t)(rv.w & 0xFFFF), d7 = (int)rv.w >> 16;
+    if (DCTM == 2) {
+      // convsamp_float -> (float deringing) -> row pass of jpeg_fdct_float; the block's 64 floats sit in sW in natural order
+      float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2, f3 = (float)d3, f4 = (float)d4, f5 = (float)d5, f6 = (float)d6, f7 = (float)d7;
+      float *w = reinterpret_cast<float *>(sW) + b * 72 + j * 8;
+      if (dering) {
+        int sum = d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7;          // integer-valued floats add exactly, so the int sum is the float sum
+        int cnt = (d0 >= 127) + (d1 >= 127) + (d2 >= 127) + (d3 >= 127) + (d4 >= 127) + (d5 >= 127) + (d6 >= 127) + (d7 >= 127);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1); cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2); cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4); cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+        if (cnt != 0 && cnt != 64) {
+          w[0] = f0; w[1] = f1; w[2] = f2; w[3] = f3; w[4] = f4; w[5] = f5; w[6] = f6; w[7] = f7;
+          __syncwarp(0xFFu << (threadIdx.x & 24));
+          if (j == 0) {
+            const int ci = b < YB ? 0 : (1 + (b - YB) / CBW);
+            deringing_block_float(reinterpret_cast<float *>(sW) + b * 72, (int)qt->q[g.c[ci].qt][0].d >> 3, (float)sum, cnt);
+          }
+          __syncwarp(0xFFu << (threadIdx.x & 24));
+          f0 = w[0]; f1 = w[1]; f2 = w[2]; f3 = w[3]; f4 = w[4]; f5 = w[5]; f6 = w[6]; f7 = w[7];
+        }
+      }
+      fdct_float_1d(f0, f1, f2, f3, f4, f5, f6, f7);
+      w[0] = f0; w[1] = f1; w[2] = f2; w[3] = f3; w[4] = f4; w[5] = f5; w[6] = f6; w[7] = f7;
+      continue;
+    }
     if (dering) {
       int sum = d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7;
       int cnt = (d0 >= 127) + (d1 >= 127) + (d2 >= 127) + (d3 >= 127) + (d4 >= 127) + (d5 >= 127) + (d6 >= 127) + (d7 >= 127);
@@ -404,14 +477,15 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
       }
     }
     fdct_1d<0, P1>(d0, d1, d2, d3, d4, d5, d6, d7);
-    if (PREC == 8) {
+    if (DCTM == 2) {
+    } else if (PREC == 8) {
       uint4 wv;
       wv.x = ((unsigned)d0 & 0xFFFFu) | ((unsigned)d1 << 16); wv.y = ((unsigned)d2 & 0xFFFFu) | ((unsigned)d3 << 16);
       wv.z = ((unsigned)d4 & 0xFFFFu) | ((unsigned)d5 << 16); wv.w = ((unsigned)d6 & 0xFFFFu) | ((unsigned)d7 << 16);
-      *reinterpret_cast<uint4 *>(sW + b * 72 + j * 8) = wv;
+      *reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(sW) + b * 72 + j * 8) = wv;
     } else {
-      wtype *w = sW + b * 72 + j * 8;
-      w[0] = (wtype)d0; w[1] = (wtype)d1; w[2] = (wtype)d2; w[3] = (wtype)d3; w[4] = (wtype)d4; w[5] = (wtype)d5; w[6] = (wtype)d6; w[7] = (wtype)d7;
+      int *w = reinterpret_cast<int *>(sW) + b * 72 + j * 8;
+      w[0] = d0; w[1] = d1; w[2] = d2; w[3] = d3; w[4] = d4; w[5] = d5; w[6] = d6; w[7] = d7;
     }
   }
   __syncthreads();
@@ -430,10 +504,34 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
 #pragma unroll 1
   for (int b = tid >> 3; b < NB; b += 16) {
     const wtype *w = sW + b * 72 + j;
-    int d0 = w[0], d1 = w[8], d2 = w[16], d3 = w[24], d4 = w[32], d5 = w[40], d6 = w[48], d7 = w[56];
-    fdct_1d<1, P1>(d0, d1, d2, d3, d4, d5, d6, d7);
     const int ci = b < YB ? 0 : (1 + (b - YB) / CBW);
-    const int dd[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
+    int dd[8], qf[8];                                             // raw coefficients (integers) of this lane's column / float-path quantized values
+    if (DCTM == 2) {
+      float f0 = w[0], f1 = w[8], f2 = w[16], f3 = w[24], f4 = w[32], f5 = w[40], f6 = w[48], f7 = w[56];
+      fdct_float_1d(f0, f1, f2, f3, f4, f5, f6, f7);
+      const float ff[8] = {f0, f1, f2, f3, f4, f5, f6, f7};
+      const float *fd = qt->fdiv[g.c[ci].qt];
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        // forward_DCT_float :860-874 (coefficients for the trellis, as integers; the divisions are in double) ...
+        dd[r] = 0;
+        if (write_raw) {
+          float v = ff[r];
+          v = (float)((double)v / c_aan[j]);                      // i % 8 = column
+          v = (float)((double)v / c_aan[r]);                      // i / 8 = row
+          dd[r] = (v >= 0.0f) ? (int)((double)v + 0.5) : (int)((double)v - 0.5);
+        }
+        // ... and quantize_float :808-827
+        const float temp = ff[r] * fd[8 * r + j];
+        int q = (int)(int16_t)(__float2int_rz(temp + 16384.5f) - 16384);
+        if (dering) q = max(-1023, min(1023, q));
+        qf[r] = q;
+      }
+    } else {
+      int d0 = w[0], d1 = w[8], d2 = w[16], d3 = w[24], d4 = w[32], d5 = w[40], d6 = w[48], d7 = w[56];
+      fdct_1d<1, P1>(d0, d1, d2, d3, d4, d5, d6, d7);
+      dd[0] = d0; dd[1] = d1; dd[2] = d2; dd[3] = d3; dd[4] = d4; dd[5] = d5; dd[6] = d6; dd[7] = d7;
+    }
     const int L = sQL[NC == 1 ? 0 : ci];
     unsigned mlo = 0, mhi = 0;                                 // zigzag positions of this lane's non-zero AC values
 #pragma unroll
@@ -441,21 +539,28 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
       const int nat = 8 * r + j;
       const int k = kz[r];
       int qv;
-      if (QFAST) qv = quant_fast(dd[r], sQC[NC == 1 ? 0 : ci][nat], L, dering);
+      if (DCTM == 2) qv = qf[r];
+      else if (QFAST) qv = quant_fast(dd[r], sQC[NC == 1 ? 0 : ci][nat], L, dering);
       else qv = (int)(int16_t)quant_one(dd[r], qt->q[g.c[ci].qt][nat], dering);
       sQ[b * 64 + k] = (int16_t)qv;
       sR[b * 64 + k] = (int16_t)dd[r];
-      if (qv != 0 && nat != 0) { if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
+      // the trellis derives its entries from the RAW coefficient (qval = (|x| + q/2) / q, jcdctmgr.c:1136); with the
+      // integer DCT that is the plain-quantized value, with the float DCT it can differ from quantize_float's result
+      bool nzv = qv != 0;
+      if (DCTM == 2 && rec) { const int dq = (int)qt->q[g.c[ci].qt][nat].d; nzv = abs(dd[r]) >= dq - dq / 2; }
+      if (nzv && nat != 0) { if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
     }
     if (PREC == 8 && rec) {
       // the raw coefficients go back to sW in natural order (each lane rewrites exactly the words it
       // read), lane r then owns ROW r and the serial fp32 sum of squares in NATURAL order
       // (jcdctmgr.c:1026-1029) is handed from lane to lane, 8 adds per hop
-      int16_t *ww = reinterpret_cast<int16_t *>(sW) + b * 72 + j;
+      if (DCTM == 2) __syncwarp();                             // every lane has read its float column before the int16 view reuses the words
+      int16_t *blk16 = reinterpret_cast<int16_t *>(sW + b * 72);     // the block's own words (also when sW holds floats)
+      int16_t *ww = blk16 + j;
 #pragma unroll
       for (int r = 0; r < 8; r++) ww[8 * r] = (int16_t)dd[r];
       __syncwarp();
-      const int4 rowv = *reinterpret_cast<const int4 *>(reinterpret_cast<int16_t *>(sW) + b * 72 + 8 * j);
+      const int4 rowv = *reinterpret_cast<const int4 *>(blk16 + 8 * j);
       const int pw[4] = {rowv.x, rowv.y, rowv.z, rowv.w};
       float sq[8];
 #pragma unroll
@@ -499,17 +604,17 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   }
 }
 
-template <bool QFAST, int PREC>
+template <bool QFAST, int PREC, int DCTM>
 static void launch_forward_tile(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s, bool gray, int write_raw)
 {
   dim3 grid((g.W + 127) / 128, g.mcu_rows, n);
-  if (gray) k_forward_tile<1, 1, 1, QFAST, PREC><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
-  else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3, QFAST, PREC><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
-  else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3, QFAST, PREC><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
-  else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3, QFAST, PREC><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
-  else k_forward_tile<2, 2, 3, QFAST, PREC><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
+  if (gray) k_forward_tile<1, 1, 1, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
+  else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
+  else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
+  else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
+  else k_forward_tile<2, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
 }
-void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, int n, cudaStream_t s)
+void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dct_method, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, int n, cudaStream_t s)
 {
   const int write_raw = rec != nullptr || keep_raw;
   // fast path: full-size first component, (for colour) two 1x1-sampled chroma components
@@ -519,10 +624,11 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
   static const bool force_generic = getenv("B200JPEG_GENERIC_FORWARD") != nullptr;   // A/B switch for debugging
   if (!force_generic && ((gray && g.hmax == 1 && g.vmax == 1) || ycc)) {
     if (g.max_coef_bits == 14) {                       // 12-bit samples (uint16)
-      if (qfast) launch_forward_tile<true, 12>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
-      else launch_forward_tile<false, 12>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
-    } else if (qfast) launch_forward_tile<true, 8>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
-    else launch_forward_tile<false, 8>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
+      if (qfast) launch_forward_tile<true, 12, 0>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
+      else launch_forward_tile<false, 12, 0>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
+    } else if (dct_method == 2) launch_forward_tile<true, 8, 2>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
+    else if (qfast) launch_forward_tile<true, 8, 0>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
+    else launch_forward_tile<false, 8, 0>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
     LAUNCHED();
     return;
   }
@@ -859,8 +965,8 @@ void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, ui
 template <int MM>
 __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long long nzmask, const float *A,
                                                      const int16_t *__restrict__ raw16, const int16_t *__restrict__ o16,
-                                                     const __half (*srate)[64], const float *swz, const int *sq8,
-                                                     const float lambda, const int maxq, const float azd63, const float eob)
+                                                     const __half (*srate)[64], const float *swz, const int *sq8, const unsigned *sqdiv, const int qL,
+                                                     const float lambda, const int maxq, const float azd63, const float eob, const unsigned dc_q)
 {
   int r_pos[MM]; float r_at[MM], r_acc[MM];
   int r_rs[MM], r_val[MM];
@@ -874,17 +980,17 @@ __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long 
       r_pos[t] = p; r_at[t] = A[p]; r_acc[t] = 0.f; r_rs[t] = 0; r_val[t] = 0;
     }
   }
-  int nraw = 0, nqnt = 0; float nbefore = 0.f;
-  if (m > 0) { nraw = raw16[r_pos[0]]; nqnt = o16[r_pos[0]]; nbefore = A[r_pos[0] - 1]; }
+  int nraw = 0; float nbefore = 0.f;
+  if (m > 0) { nraw = raw16[r_pos[0]]; nbefore = A[r_pos[0] - 1]; }
 #pragma unroll
   for (int t = 0; t < MM; t++) {
     if (t < m) {
       const int i = r_pos[t];
-      const int rawv = nraw, qntv = nqnt; const float Ai1 = nbefore;
-      if (t + 1 < MM && t + 1 < m) { nraw = raw16[r_pos[t + 1]]; nqnt = o16[r_pos[t + 1]]; nbefore = A[r_pos[t + 1] - 1]; }
+      const int rawv = nraw; const float Ai1 = nbefore;
+      if (t + 1 < MM && t + 1 < m) { nraw = raw16[r_pos[t + 1]]; nbefore = A[r_pos[t + 1] - 1]; }
       const int x = abs(rawv);
       const int q = sq8[i];
-      const int qv = min(abs(qntv), maxq);
+      const int qv = min((int)(__umulhi((unsigned)(x + (q >> 1)) << 14, sqdiv[i]) >> qL), maxq);      // :1136-1144
       const int nc = nbits_of(qv);
       const float wl = swz[i];
       float best = 1e38f; int best_s = 0, best_k = -1;
@@ -929,7 +1035,6 @@ __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long 
   }
   // output: zeros except the back-tracked chain (:1211-1222); DC slot untouched here
   int16_t *o = const_cast<int16_t *>(o16);
-  const unsigned dc_q = (unsigned)(unsigned short)o[0];
   uint4 *q4 = reinterpret_cast<uint4 *>(o);
   q4[0] = make_uint4(dc_q, 0, 0, 0);
 #pragma unroll
@@ -973,6 +1078,8 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
   __shared__ __half srate[10][64];
   __shared__ float swz[64];
   __shared__ int sq8[64];
+  __shared__ unsigned sqdiv[64];              // exact (|x| + q/2) / q: umulhi((|x| + q/2) << 14, sqdiv[i]) >> qL  (table-uniform shift, like quant_fast)
+  __shared__ int sqL;
   __shared__ uint8_t acsi[256];
   const long long nblk = (long long)c.wib * c.hib;
   if ((long long)blockIdx.x * blockDim.x >= nblk) return;
@@ -980,7 +1087,8 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
   {
     const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + (4 + c.ac_tbl);
     for (int i = tid; i < 256; i += TRELLIS_THREADS) acsi[i] = ac->size[i];
-    if (tid < 64) { swz[tid] = tc->w_zz[c.qt][tid]; sq8[tid] = tc->q8_zz[c.qt][tid]; }
+    if (tid < 64) { swz[tid] = tc->w_zz[c.qt][tid]; sq8[tid] = tc->q8_zz[c.qt][tid]; sqdiv[tid] = tc->qmul_zz[c.qt][tid]; }
+    if (tid == 0) sqL = tc->qL[c.qt];
   }
   __syncthreads();
   for (int e = tid; e < 640; e += TRELLIS_THREADS) {
@@ -998,6 +1106,11 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
   const size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
   const int16_t *raw16 = c.raw + blk * 64;
   int16_t *o16 = c.coef + blk * 64;
+  // the block's coefficient line is rewritten at the end (16-byte and 2-byte stores): have it in L2 by then, or every
+  // partial-sector store turns into a read-modify-write against DRAM
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 16)); asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 32));
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 48));
+  const unsigned dc_q = (unsigned)(unsigned short)o16[0];      // the DC value survives the rewrite: fetched now, needed only at the end
   // lambda from the block's norm (K1 left the natural-order sum of squares in rec.f)   :1026-1035
   float lambda; unsigned long long nzmask;
   {
@@ -1033,13 +1146,14 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
   const float azd63 = azd;
   const int maxq = (1 << tc->max_coef_bits) - 1;
   const int m = __popcll(nzmask);
+  const int qL = sqL;
 
-  if (CLS == 1) { trellis_entries_regs<32>(m, nzmask, A, raw16, o16, srate, swz, sq8, lambda, maxq, azd63, (float)acsi[0]); return; }
+  if (CLS == 1) { trellis_entries_regs<32>(m, nzmask, A, raw16, o16, srate, swz, sq8, sqdiv, qL, lambda, maxq, azd63, (float)acsi[0], dc_q); return; }
   // warps whose blocks all have few non-zero positions take the register path
   {
     const int mmax = __reduce_max_sync(__activemask(), m);
     if (mmax <= 16) {
-      trellis_entries_regs<16>(m, nzmask, A, raw16, o16, srate, swz, sq8, lambda, maxq, azd63, (float)acsi[0]);
+      trellis_entries_regs<16>(m, nzmask, A, raw16, o16, srate, swz, sq8, sqdiv, qL, lambda, maxq, azd63, (float)acsi[0], dc_q);
       return;
     }
   }
@@ -1058,16 +1172,13 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
 
   // phase 2   :1121-1185.  The entry's plain-quantized value comes from global memory (L2 resident: K1 just wrote it);
   // the next entry's value is requested one iteration ahead.
-  int nqnt = 0;
-  if (m > 0) nqnt = o16[e_pos[0]];
 #pragma unroll 1
   for (int t = 0; t < m; t++) {
     const int i = e_pos[t];
-    const int rawv = (int)(short)e_qs[t], qntv = nqnt;
-    if (t + 1 < m) nqnt = o16[e_pos[t + 1]];
+    const int rawv = (int)(short)e_qs[t];
     const int x = abs(rawv);
     const int q = sq8[i];
-    const int qv = min(abs(qntv), maxq);
+    const int qv = min((int)(__umulhi((unsigned)(x + (q >> 1)) << 14, sqdiv[i]) >> qL), maxq);      // :1136-1144
     e_qs[t] = (unsigned short)(qv | ((rawv >> 31) & 0x8000));
     const int nc = nbits_of(qv);
     const float wl = swz[i];
@@ -1109,7 +1220,6 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
       if (cst < best_cost) { best_cost = cst; last = t + 1; }
     }
   }
-  const unsigned dc_q = (unsigned)(unsigned short)o16[0];
   // output: zeros except the back-tracked chain; DC slot untouched here
   uint4 *q4 = reinterpret_cast<uint4 *>(o16);
   q4[0] = make_uint4(dc_q, 0, 0, 0);

@@ -59,10 +59,11 @@ struct ScanDesc {
 // general form: q = ((|x| + bias) * mul) >> shift (64-bit product);  fast form (QuantTables.fast[t]): one shift
 // L[t] for the whole table, q = umulhi((|x| + bias) << 14, mul2) >> L[t]  -- both exact for |x| + bias < 2^18.
 struct QuantConst { uint32_t mul; uint16_t shift; uint16_t pad; uint32_t bias; uint32_t d; uint32_t mul2; };
-struct QuantTables { QuantConst q[4][64]; int L[4]; int fast[4]; };                 // natural order
+struct QuantTables { QuantConst q[4][64]; int L[4]; int fast[4]; float fdiv[4][64]; };   // fdiv: JDCT_FLOAT divisors (jcdctmgr.c:355-379)                 // natural order
 struct TrellisConsts {
   float w_zz[4][64];      // (float)(1.0/(Q*Q)) per zigzag position   jcdctmgr.c:1017-1021
   int   q8_zz[4][64];     // 8*Q per zigzag position
+  unsigned qmul_zz[4][64]; int qL[4];          // exact a / q8 for a < 2^18: umulhi(a << 14, qmul_zz) >> qL (one shift per table)
   double p1, p2;          // pow(2, lambda_log_scale1), pow(2, lambda_log_scale2)
   float lambda_const;     // used when lambda_log_scale2 <= 0
   int   use_norm;         // lambda_log_scale2 > 0
@@ -99,7 +100,7 @@ struct SlotMasks { uint32_t m[4]; int period; };
 // ---------------------------------------------------------------- launches (defined in kernels.cu)
 // status[img] bits: 2 = JERR_BAD_DCT_COEF / missing Huffman code, 4 = output buffer too small (host retries)
 // the raw DCT plane is written only when the trellis (rec != nullptr) or the debug tap (keep_raw) will read it
-void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, int n, cudaStream_t s);
+void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dct_method /* J_DCT_METHOD */, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, int n, cudaStream_t s);
 void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, uint32_t *splits /* [n*nc][2] */, int n, cudaStream_t s);
 void launch_dummy(const Geom &g, int n, cudaStream_t s);
 void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);

@@ -171,6 +171,94 @@ int orc_quantize_coef(int x, int q)
 }
 
 /* ------------------------------------------------------------------ */
+/* JDCT_FLOAT path: convsamp_float / float_preprocess_deringing / jpeg_fdct_float / quantize_float and the raw
+ * coefficients forward_DCT_float saves for the trellis (jcdctmgr.c:500-575, 777-902; jfdctflt.c:59-167).
+ * Built with -ffp-contract=off, every operation in fp32 unless the reference promotes it.                          */
+static const double aanscalefactor[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0, 0.785694958, 0.541196100, 0.275899379};
+
+static void fdct_float_1d(float *d, int stride)
+{
+  float tmp0 = d[0] + d[7 * stride], tmp7 = d[0] - d[7 * stride];
+  float tmp1 = d[stride] + d[6 * stride], tmp6 = d[stride] - d[6 * stride];
+  float tmp2 = d[2 * stride] + d[5 * stride], tmp5 = d[2 * stride] - d[5 * stride];
+  float tmp3 = d[3 * stride] + d[4 * stride], tmp4 = d[3 * stride] - d[4 * stride];
+  float tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  float z1, z2, z3, z4, z5, z11, z13;
+  d[0] = tmp10 + tmp11; d[4 * stride] = tmp10 - tmp11;
+  z1 = (tmp12 + tmp13) * ((float)0.707106781);
+  d[2 * stride] = tmp13 + z1; d[6 * stride] = tmp13 - z1;
+  tmp10 = tmp4 + tmp5; tmp11 = tmp5 + tmp6; tmp12 = tmp6 + tmp7;
+  z5 = (tmp10 - tmp12) * ((float)0.382683433);
+  z2 = ((float)0.541196100) * tmp10 + z5;
+  z4 = ((float)1.306562965) * tmp12 + z5;
+  z3 = tmp11 * ((float)0.707106781);
+  z11 = tmp7 + z3; z13 = tmp7 - z3;
+  d[5 * stride] = z13 + z2; d[3 * stride] = z13 - z2; d[stride] = z11 + z4; d[7 * stride] = z11 - z4;
+}
+static void fdct_float(float *data)
+{
+  int i;
+  for (i = 0; i < 8; i++) fdct_float_1d(data + 8 * i, 1);
+  for (i = 0; i < 8; i++) fdct_float_1d(data + i, 8);
+}
+/* jcdctmgr.c:503-575; catmull_rom takes DCTELEM (int) values, so the float slopes are truncated on the way in */
+static void deringing_float(float *data, int q0)
+{
+  const float maxsample = 255 - 128; const int size = 64;
+  float sum = 0; int cnt = 0, i, n; float maxovershoot;
+  for (i = 0; i < size; i++) { sum += data[i]; if (data[i] >= maxsample) cnt++; }
+  if (!cnt || cnt == size) return;
+  {
+    int a = 31 < 2 * q0 ? 31 : 2 * q0; float b = (maxsample * size - sum) / cnt;
+    maxovershoot = maxsample + ((float)a < b ? (float)a : b);
+  }
+  n = 0;
+  do {
+    int start, end, length; float f1, f2, l1, l2, fslope, lslope, step, position;
+    if (data[zz[n]] < maxsample) { n++; continue; }
+    start = n;
+    while (++n < size && data[zz[n]] >= maxsample) {}
+    end = n;
+    f1 = data[zz[start >= 1 ? start - 1 : 0]]; f2 = data[zz[start >= 2 ? start - 2 : 0]];
+    l1 = data[zz[end < size - 1 ? end : size - 1]]; l2 = data[zz[end < size - 2 ? end + 1 : size - 1]];
+    fslope = (f1 - f2) > (maxsample - f1) ? (f1 - f2) : (maxsample - f1);
+    lslope = (l1 - l2) > (maxsample - l1) ? (l1 - l2) : (maxsample - l1);
+    if (start == 0) fslope = lslope;
+    if (end == size) lslope = fslope;
+    length = end - start;
+    step = 1.f / (float)(length + 1);
+    position = step;
+    for (i = start; i < end; i++, position += step) {
+      float tmp = catmull_rom((int)(maxsample - fslope), (int)maxsample, (int)maxsample, (int)(maxsample - lslope), position, length);
+      data[zz[i]] = tmp < maxovershoot ? tmp : maxovershoot;
+    }
+    n++;
+  } while (n < size);
+}
+/* one block: samples (already centred ints) -> quantized + raw coefficients, natural order */
+static void forward_block_float(const b200jpeg_params *p, const int *centred, const uint16_t *q, int16_t *dq, int16_t *dr)
+{
+  float ws[64]; int i;
+  for (i = 0; i < 64; i++) ws[i] = (float)centred[i];
+  if (p->overshoot_deringing) deringing_float(ws, q[0]);
+  fdct_float(ws);
+  for (i = 0; i < 64; i++) {                                  /* :860-874: raw coefficients for the trellis, as integers */
+    float v = ws[i]; int x;
+    v /= aanscalefactor[i % 8];
+    v /= aanscalefactor[i / 8];
+    x = (v >= 0.0) ? (int)(v + 0.5) : (int)(v - 0.5);
+    dr[i] = (int16_t)x;
+  }
+  for (i = 0; i < 64; i++) {                                  /* quantize_float :808-827 with the divisors of :355-379 */
+    float div = (float)(1.0 / (((double)q[i] * aanscalefactor[i / 8] * aanscalefactor[i % 8] * 8.0)));
+    float temp = ws[i] * div;
+    int v = (int16_t)((int)(temp + (float)16384.5) - 16384);
+    if (p->overshoot_deringing) { int mx = (1 << (p->data_precision + 2)) - 1; if (v < -mx) v = -mx; if (v > mx) v = mx; }
+    dq[i] = (int16_t)v;
+  }
+}
+
+/* ------------------------------------------------------------------ */
 /* Huffman table machinery                                              */
 /* ------------------------------------------------------------------ */
 
@@ -836,6 +924,7 @@ static int forward_all(enc_t *e, const uint8_t *pix, size_t pitch)
       int ws[64]; const uint16_t *q = p->quant_tbl[c->quant_tbl_no];
       int16_t *dq = e->coef[ci] + ((size_t)by * e->wpad[ci] + bx) * 64, *dr = e->raw[ci] + ((size_t)by * e->wpad[ci] + bx) * 64;
       for (y = 0; y < 8; y++) for (x = 0; x < 8; x++) ws[8 * y + x] = plane[(size_t)(by * 8 + y) * ow + bx * 8 + x] - centre;   /* convsamp :576-604 */
+      if (p->dct_method == B200JPEG_DCT_FLOAT) { forward_block_float(p, ws, q, dq, dr); continue; }
       if (p->overshoot_deringing) orc_deringing(ws, q[0]);
       fdct_islow_prec(ws, prec);
       for (i = 0; i < 64; i++) {
@@ -885,7 +974,7 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
   e->p = p; e->nc = p->num_components; e->W = p->image_width; e->H = p->image_height;
   /* 12-bit: no JBUF_REQUANT => no trellis (jccoefct.c:132-138); deringing is not usable at 12 bits (jcdctmgr.c:419) */
   if (p->data_precision == 12 && (p->trellis_quant || p->overshoot_deringing)) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
-  if ((p->data_precision != 8 && p->data_precision != 12) || p->dct_method != B200JPEG_DCT_ISLOW || p->smoothing_factor ||
+  if ((p->data_precision != 8 && p->data_precision != 12) || (p->dct_method != B200JPEG_DCT_ISLOW && !(p->dct_method == B200JPEG_DCT_FLOAT && p->data_precision == 8)) || p->smoothing_factor ||
       p->trellis_eob_opt || p->use_scans_in_trellis || p->trellis_q_opt || p->trellis_num_loops != 1 ||
       p->trellis_delta_dc_weight != 0.0f) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   e->hmax = e->vmax = 1;

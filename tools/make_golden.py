@@ -62,9 +62,17 @@ SWITCH_SETS = [
     ["-grayscale", "-quality", "75"],
     ["-quality", "75", "-restart", "1"],
     ["-quality", "85", "-notrellis"],
+    # JDCT_FLOAT (jfdctflt.c; this reference build is the "no-fp-contract" flavour of CMakeLists.txt:965-1024)
+    ["-dct", "float", "-baseline", "-quality", "75"],
+    ["-dct", "float", "-quality", "75", "-fastcrush"],
+    ["-dct", "float", "-baseline", "-notrellis", "-quality", "90", "-sample", "1x1"],
+    ["-dct", "float", "-baseline", "-quality", "50", "-grayscale"],
+    ["-dct", "float", "-quality", "75"],
 ]
 # through the reference's cjpeg binary only (our refshim driver does not parse these switches)
 CJPEG_ONLY = [
+    ["-revert", "-dct", "float"],
+    ["-revert", "-dct", "float", "-optimize", "-progressive"],
     ["-quality", "75", "-dc-scan-opt", "2"],
     ["-quality", "60", "-dc-scan-opt", "1"],
     ["-quality", "85", "-dc-scan-opt", "0"],
