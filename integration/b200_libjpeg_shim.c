@@ -16,8 +16,8 @@
  * binary, in tests/test_libjpeg_shim.py) produces its files on the GPU.
  *
  * Parameter sets the device path does not cover (B200JPEG_ERR_UNSUPPORTED from
- * b200jpeg_start_compress: scan search, arithmetic coding, 12-bit, raw data,
- * ...) and hosts without a CUDA device fall through to the reference's
+ * b200jpeg_start_compress: JDCT_IFAST, smoothing, arithmetic coding, raw data,
+ * 12-bit through this 8-bit entry point, ...) and hosts without a CUDA device fall through to the reference's
  * implementation of the same three functions (dlsym RTLD_NEXT): that is the
  * REFERENCE running, not a CPU path of this library.  B200_SHIM_VERBOSE=1
  * reports on stderr which path an image took; B200_SHIM_REQUIRE=1 turns a
