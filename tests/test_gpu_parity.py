@@ -199,3 +199,33 @@ def test_chunked_pipeline_matches_oracle(built, sw, chunk):
         enc.close()
     for i in range(len(imgs)):
         assert out[i] == O.oracle_encode(p, imgs[i]).jpeg, f"image {i}, chunk {chunk}"
+
+
+def test_very_wide_image_takes_the_fallback_dc_trellis(encoder):
+    """A row of 3750 blocks does not fit the warp-cooperative DC trellis's shared-memory back pointers:
+    the launch falls back to the older kernels, which must give the same bytes."""
+    import mozjpeg_b200 as mj
+    from oracle import oracle as O
+    w, h = 30000, 16
+    img = O.synth_image(77, w, h)
+    sw = ["-baseline", "-quality", "75", "-sample", "1x1"]
+    p = mj.params_from_switches(sw, w, h)
+    assert encoder.encode_batch(p, img[None])[0] == O.oracle_encode(p, img).jpeg
+
+
+def test_incompressible_input_grows_the_output_buffers(built):
+    """Noise at quality 100 needs more than the initial 2 bits per coefficient: the pipeline flags the
+    overflow on the device, the host grows the buffers and reruns; the result must still be exact."""
+    import mozjpeg_b200 as mj
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (3, 128, 192, 3), dtype=np.uint8)
+    sw = ["-baseline", "-notrellis", "-quality", "100", "-sample", "1x1"]
+    p = mj.params_from_switches(sw, 192, 128)
+    enc = mj.Encoder(0)
+    try:
+        out = enc.encode_batch(p, img)
+    finally:
+        enc.close()
+    for i in range(3):
+        assert out[i] == O.oracle_encode(p, img[i]).jpeg
