@@ -250,6 +250,20 @@ static void make_quant_consts(const b200jpeg_params *p, QuantTables *qt)
     qt->L[t] = L;
     qt->fast[t] = (((1ull << (18 + L)) + dmin - 1) / dmin) < (1ull << 32) ? 1 : 0;
     for (int i = 0; i < 64; i++) { unsigned d = qt->q[t][i].d; qt->q[t][i].mul2 = qt->fast[t] ? (uint32_t)(((1ull << (18 + L)) + d - 1) / d) : 0; }
+    static const short aanscales[64] = {16384, 22725, 21407, 19266, 16384, 12873, 8867, 4520, 22725, 31521, 29692, 26722, 22725, 17855, 12299, 6270,
+      21407, 29692, 27969, 25172, 21407, 16819, 11585, 5906, 19266, 26722, 25172, 22654, 19266, 15137, 10426, 5315,
+      16384, 22725, 21407, 19266, 16384, 12873, 8867, 4520, 12873, 17855, 16819, 15137, 12873, 10114, 6967, 3552,
+      8867, 12299, 11585, 10426, 8867, 6967, 4799, 2446, 4520, 6270, 5906, 5315, 4520, 3552, 2446, 1247};
+    for (int i = 0; i < 64; i++) {                                 // jcdctmgr.c:290-339 + compute_reciprocal :181-230
+      unsigned divisor = (unsigned)(unsigned short)(((long)p->quant_tbl[t][i] * aanscales[i] + (1L << 10)) >> 11);
+      IfastConst &k = qt->ifast[t][i]; k.pad = 0;
+      if (divisor == 1) { k.recip = 1; k.corr = 0; k.shift = -32; continue; }
+      int b = 0; for (unsigned v = divisor; v; v >>= 1) b++; b -= 1;
+      int r = 32 + b;
+      unsigned long long fq = (1ULL << r) / divisor, fr = (1ULL << r) % divisor; unsigned c = divisor / 2;
+      if (fr == 0) { fq >>= 1; r--; } else if (fr <= (divisor / 2U)) c++; else fq++;
+      k.recip = (unsigned)fq; k.corr = c; k.shift = r - 32;
+    }
     static const double aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0, 0.785694958, 0.541196100, 0.275899379};
     for (int i = 0; i < 64; i++) qt->fdiv[t][i] = (float)(1.0 / (((double)p->quant_tbl[t][i] * aan[i / 8] * aan[i % 8] * 8.0)));       // jcdctmgr.c:371-374
   }
@@ -930,11 +944,11 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   e->params = *p; e->n = n_images;
   if ((rc = build_plan(p, row_pitch, image_stride, e->plan))) return rc;
   Plan &pl = e->plan;
-  if (p->data_precision == 12 || p->dct_method == B200JPEG_DCT_FLOAT) {
+  if (p->data_precision == 12 || p->dct_method != B200JPEG_DCT_ISLOW) {
     const Geom &g = pl.g;
     bool gray = g.nc == 1 && g.hmax == 1 && g.vmax == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
     bool ycc = g.nc == 3 && g.cs_mode == 0 && g.in_comps == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax && g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
-    if (!gray && !ycc) { set_error("12-bit precision / float DCT: only RGB->YCbCr 4:4:4/4:2:2/4:4:0/4:2:0 and grayscale layouts are on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
+    if (!gray && !ycc) { set_error("12-bit precision / fast and float DCT: only RGB->YCbCr 4:4:4/4:2:2/4:4:0/4:2:0 and grayscale layouts are on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
   }
   const int nscans = (int)pl.scans.size();
   const int C = choose_chunk(e, pl, n_images, !on_device);

@@ -278,6 +278,33 @@ __device__ __forceinline__ int quant_fast(int x, uint2 k, int L, int dering)
   return x < 0 ? -q : q;
 }
 
+// ---- JDCT_IFAST (jfdctfst.c:113-224): MULTIPLY = (v * c) >> 8, no rounding ----
+__device__ __forceinline__ void fdct_ifast_1d(int &d0, int &d1, int &d2, int &d3, int &d4, int &d5, int &d6, int &d7)
+{
+  int tmp0 = d0 + d7, tmp7 = d0 - d7, tmp1 = d1 + d6, tmp6 = d1 - d6;
+  int tmp2 = d2 + d5, tmp5 = d2 - d5, tmp3 = d3 + d4, tmp4 = d3 - d4;
+  int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  d0 = tmp10 + tmp11; d4 = tmp10 - tmp11;
+  int z1 = ((tmp12 + tmp13) * 181) >> 8;
+  d2 = tmp13 + z1; d6 = tmp13 - z1;
+  tmp10 = tmp4 + tmp5; tmp11 = tmp5 + tmp6; tmp12 = tmp6 + tmp7;
+  int z5 = ((tmp10 - tmp12) * 98) >> 8;
+  int z2 = ((tmp10 * 139) >> 8) + z5;
+  int z4 = ((tmp12 * 334) >> 8) + z5;
+  int z3 = (tmp11 * 181) >> 8;
+  int z11 = tmp7 + z3, z13 = tmp7 - z3;
+  d5 = z13 + z2; d3 = z13 - z2; d1 = z11 + z4; d7 = z11 - z4;
+}
+__constant__ short c_aanscales[64] = {
+  16384, 22725, 21407, 19266, 16384, 12873,  8867,  4520,
+  22725, 31521, 29692, 26722, 22725, 17855, 12299,  6270,
+  21407, 29692, 27969, 25172, 21407, 16819, 11585,  5906,
+  19266, 26722, 25172, 22654, 19266, 15137, 10426,  5315,
+  16384, 22725, 21407, 19266, 16384, 12873,  8867,  4520,
+  12873, 17855, 16819, 15137, 12873, 10114,  6967,  3552,
+   8867, 12299, 11585, 10426,  8867,  6967,  4799,  2446,
+   4520,  6270,  5906,  5315,  4520,  3552,  2446,  1247};
+
 // ---- JDCT_FLOAT (jfdctflt.c:59-167, AA&N): one 1-D pass, fp32, no contraction ----
 __device__ __forceinline__ void fdct_float_1d(float &d0, float &d1, float &d2, float &d3, float &d4, float &d5, float &d6, float &d7)
 {
@@ -324,7 +351,7 @@ __device__ __forceinline__ void deringing_block_float(float *data, int q0, float
 }
 __constant__ double c_aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0, 0.785694958, 0.541196100, 0.275899379};
 
-// DCTM: 0 = JDCT_ISLOW, 2 = JDCT_FLOAT (8-bit only)
+// DCTM: 0 = JDCT_ISLOW, 1 = JDCT_IFAST, 2 = JDCT_FLOAT (1 and 2: 8-bit only)
 template <int HMAX, int VMAX, int NC, bool QFAST, int PREC, int DCTM>
 __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *__restrict__ src,
                                                       const QuantTables *__restrict__ qt, int dering,
@@ -476,7 +503,8 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
         d0 = rowp[0]; d1 = rowp[1]; d2 = rowp[2]; d3 = rowp[3]; d4 = rowp[4]; d5 = rowp[5]; d6 = rowp[6]; d7 = rowp[7];
       }
     }
-    fdct_1d<0, P1>(d0, d1, d2, d3, d4, d5, d6, d7);
+    if (DCTM == 1) fdct_ifast_1d(d0, d1, d2, d3, d4, d5, d6, d7);
+    else fdct_1d<0, P1>(d0, d1, d2, d3, d4, d5, d6, d7);
     if (DCTM == 2) {
     } else if (PREC == 8) {
       uint4 wv;
@@ -527,6 +555,25 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
         if (dering) q = max(-1023, min(1023, q));
         qf[r] = q;
       }
+    } else if (DCTM == 1) {
+      int d0 = w[0], d1 = w[8], d2 = w[16], d3 = w[24], d4 = w[32], d5 = w[40], d6 = w[48], d7 = w[56];
+      fdct_ifast_1d(d0, d1, d2, d3, d4, d5, d6, d7);
+      const int ws8[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
+      const IfastConst *ic = qt->ifast[g.c[ci].qt];
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const int nat = 8 * r + j;
+        // raw coefficient for the trellis, rescaled as forward_DCT does (jcdctmgr.c:729-746) ...
+        dd[r] = 0;
+        if (write_raw) { const int x = ws8[r], sc = c_aanscales[nat]; dd[r] = (x >= 0) ? (x * 32768 + sc) / (2 * sc) : (x * 32768 - sc) / (2 * sc); }
+        // ... and the reciprocal quantizer of :611-645 with the scaled divisor's constants (compute_reciprocal :181-230)
+        const IfastConst k = ic[nat];
+        const int a = abs(ws8[r]);
+        int q = (int)(int16_t)(int)(((unsigned long long)(unsigned)(a + (int)k.corr) * k.recip) >> (k.shift + 32));
+        if (ws8[r] < 0) q = (int)(int16_t)(-q);
+        if (dering) q = max(-1023, min(1023, q));
+        qf[r] = q;
+      }
     } else {
       int d0 = w[0], d1 = w[8], d2 = w[16], d3 = w[24], d4 = w[32], d5 = w[40], d6 = w[48], d7 = w[56];
       fdct_1d<1, P1>(d0, d1, d2, d3, d4, d5, d6, d7);
@@ -539,7 +586,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
       const int nat = 8 * r + j;
       const int k = kz[r];
       int qv;
-      if (DCTM == 2) qv = qf[r];
+      if (DCTM != 0) qv = qf[r];
       else if (QFAST) qv = quant_fast(dd[r], sQC[NC == 1 ? 0 : ci][nat], L, dering);
       else qv = (int)(int16_t)quant_one(dd[r], qt->q[g.c[ci].qt][nat], dering);
       sQ[b * 64 + k] = (int16_t)qv;
@@ -547,7 +594,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
       // the trellis derives its entries from the RAW coefficient (qval = (|x| + q/2) / q, jcdctmgr.c:1136); with the
       // integer DCT that is the plain-quantized value, with the float DCT it can differ from quantize_float's result
       bool nzv = qv != 0;
-      if (DCTM == 2 && rec) { const int dq = (int)qt->q[g.c[ci].qt][nat].d; nzv = abs(dd[r]) >= dq - dq / 2; }
+      if (DCTM != 0 && rec) { const int dq = (int)qt->q[g.c[ci].qt][nat].d; nzv = abs(dd[r]) >= dq - dq / 2; }
       if (nzv && nat != 0) { if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
     }
     if (PREC == 8 && rec) {
@@ -627,6 +674,7 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
       if (qfast) launch_forward_tile<true, 12, 0>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
       else launch_forward_tile<false, 12, 0>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
     } else if (dct_method == 2) launch_forward_tile<true, 8, 2>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
+    else if (dct_method == 1) launch_forward_tile<true, 8, 1>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
     else if (qfast) launch_forward_tile<true, 8, 0>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
     else launch_forward_tile<false, 8, 0>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
     LAUNCHED();

@@ -259,6 +259,76 @@ static void forward_block_float(const b200jpeg_params *p, const int *centred, co
 }
 
 /* ------------------------------------------------------------------ */
+/* JDCT_IFAST path (8-bit, C code without SIMD): jpeg_fdct_ifast (jfdctfst.c:113-224), its scaled divisors
+ * with the reciprocal quantizer (jcdctmgr.c:181-230, 290-339, 611-645) and the raw coefficients
+ * forward_DCT rescales for the trellis (jcdctmgr.c:729-752).                                                    */
+static const short aanscales_ifast[64] = {
+  16384, 22725, 21407, 19266, 16384, 12873,  8867,  4520,
+  22725, 31521, 29692, 26722, 22725, 17855, 12299,  6270,
+  21407, 29692, 27969, 25172, 21407, 16819, 11585,  5906,
+  19266, 26722, 25172, 22654, 19266, 15137, 10426,  5315,
+  16384, 22725, 21407, 19266, 16384, 12873,  8867,  4520,
+  12873, 17855, 16819, 15137, 12873, 10114,  6967,  3552,
+   8867, 12299, 11585, 10426,  8867,  6967,  4799,  2446,
+   4520,  6270,  5906,  5315,  4520,  3552,  2446,  1247
+};
+#define IFMUL(v, c) ((int)(((v) * (c)) >> 8))          /* MULTIPLY with CONST_BITS 8, DESCALE = plain right shift */
+static void fdct_ifast_1d(int *d, int stride)
+{
+  int tmp0 = d[0] + d[7 * stride], tmp7 = d[0] - d[7 * stride];
+  int tmp1 = d[stride] + d[6 * stride], tmp6 = d[stride] - d[6 * stride];
+  int tmp2 = d[2 * stride] + d[5 * stride], tmp5 = d[2 * stride] - d[5 * stride];
+  int tmp3 = d[3 * stride] + d[4 * stride], tmp4 = d[3 * stride] - d[4 * stride];
+  int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  int z1, z2, z3, z4, z5, z11, z13;
+  d[0] = tmp10 + tmp11; d[4 * stride] = tmp10 - tmp11;
+  z1 = IFMUL(tmp12 + tmp13, 181);
+  d[2 * stride] = tmp13 + z1; d[6 * stride] = tmp13 - z1;
+  tmp10 = tmp4 + tmp5; tmp11 = tmp5 + tmp6; tmp12 = tmp6 + tmp7;
+  z5 = IFMUL(tmp10 - tmp12, 98);
+  z2 = IFMUL(tmp10, 139) + z5;
+  z4 = IFMUL(tmp12, 334) + z5;
+  z3 = IFMUL(tmp11, 181);
+  z11 = tmp7 + z3; z13 = tmp7 - z3;
+  d[5 * stride] = z13 + z2; d[3 * stride] = z13 - z2; d[stride] = z11 + z4; d[7 * stride] = z11 - z4;
+}
+/* compute_reciprocal (jcdctmgr.c:181-230) with DCTELEM = int */
+void orc_ifast_reciprocal(unsigned q, int natural_index, unsigned *recip, unsigned *corr, int *shift)
+{
+  unsigned divisor = (unsigned)(unsigned short)(((long)q * aanscales_ifast[natural_index] + (1L << 10)) >> 11);   /* DESCALE(.., CONST_BITS-3), passed as UINT16 */
+  unsigned long long fq, fr; unsigned c; int b = 0, r;
+  if (divisor == 1) { *recip = 1; *corr = 0; *shift = -32; return; }
+  { unsigned v = divisor; while (v) { b++; v >>= 1; } b -= 1; }      /* flss(divisor) - 1 */
+  r = 32 + b;
+  fq = (1ULL << r) / divisor; fr = (1ULL << r) % divisor;
+  c = divisor / 2;
+  if (fr == 0) { fq >>= 1; r--; } else if (fr <= (divisor / 2U)) c++; else fq++;
+  *recip = (unsigned)fq; *corr = c; *shift = r - 32;
+}
+static void forward_block_ifast(const b200jpeg_params *p, int *ws, const uint16_t *q, int16_t *dq, int16_t *dr)
+{
+  int i;
+  if (p->overshoot_deringing) orc_deringing(ws, q[0]);
+  for (i = 0; i < 8; i++) fdct_ifast_1d(ws + 8 * i, 1);
+  for (i = 0; i < 8; i++) fdct_ifast_1d(ws + i, 8);
+  for (i = 0; i < 64; i++) {                                   /* :729-746 */
+    int x = ws[i], sc = aanscales_ifast[i];
+    x = (x >= 0) ? (x * 32768 + sc) / (2 * sc) : (x * 32768 - sc) / (2 * sc);
+    dr[i] = (int16_t)x;
+  }
+  for (i = 0; i < 64; i++) {                                   /* quantize :611-645 */
+    unsigned recip, corr; int shift, temp = ws[i], v;
+    unsigned long long product;
+    orc_ifast_reciprocal(q[i], i, &recip, &corr, &shift);
+    if (temp < 0) { temp = -temp; product = (unsigned long long)(temp + corr) * recip; product >>= shift + 32; v = -(int)product; }
+    else { product = (unsigned long long)(temp + corr) * recip; product >>= shift + 32; v = (int)product; }
+    v = (int16_t)v;
+    if (p->overshoot_deringing) { int mx = (1 << (p->data_precision + 2)) - 1; if (v < -mx) v = -mx; if (v > mx) v = mx; }
+    dq[i] = (int16_t)v;
+  }
+}
+
+/* ------------------------------------------------------------------ */
 /* Huffman table machinery                                              */
 /* ------------------------------------------------------------------ */
 
@@ -925,6 +995,7 @@ static int forward_all(enc_t *e, const uint8_t *pix, size_t pitch)
       int16_t *dq = e->coef[ci] + ((size_t)by * e->wpad[ci] + bx) * 64, *dr = e->raw[ci] + ((size_t)by * e->wpad[ci] + bx) * 64;
       for (y = 0; y < 8; y++) for (x = 0; x < 8; x++) ws[8 * y + x] = plane[(size_t)(by * 8 + y) * ow + bx * 8 + x] - centre;   /* convsamp :576-604 */
       if (p->dct_method == B200JPEG_DCT_FLOAT) { forward_block_float(p, ws, q, dq, dr); continue; }
+      if (p->dct_method == B200JPEG_DCT_IFAST) { forward_block_ifast(p, ws, q, dq, dr); continue; }
       if (p->overshoot_deringing) orc_deringing(ws, q[0]);
       fdct_islow_prec(ws, prec);
       for (i = 0; i < 64; i++) {
@@ -974,7 +1045,7 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
   e->p = p; e->nc = p->num_components; e->W = p->image_width; e->H = p->image_height;
   /* 12-bit: no JBUF_REQUANT => no trellis (jccoefct.c:132-138); deringing is not usable at 12 bits (jcdctmgr.c:419) */
   if (p->data_precision == 12 && (p->trellis_quant || p->overshoot_deringing)) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
-  if ((p->data_precision != 8 && p->data_precision != 12) || (p->dct_method != B200JPEG_DCT_ISLOW && !(p->dct_method == B200JPEG_DCT_FLOAT && p->data_precision == 8)) || p->smoothing_factor ||
+  if ((p->data_precision != 8 && p->data_precision != 12) || (p->dct_method != B200JPEG_DCT_ISLOW && p->data_precision != 8) || p->smoothing_factor ||
       p->trellis_eob_opt || p->use_scans_in_trellis || p->trellis_q_opt || p->trellis_num_loops != 1 ||
       p->trellis_delta_dc_weight != 0.0f) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   e->hmax = e->vmax = 1;

@@ -93,6 +93,8 @@ def test_validation_errors(built):
     q = p.copy(); q.dct_method = A.DCT_FLOAT
     assert lib.b200jpeg_validate(C.byref(q)) == 0                      # float DCT is on the device path (8-bit)
     q = p.copy(); q.dct_method = A.DCT_IFAST
+    assert lib.b200jpeg_validate(C.byref(q)) == 0
+    q = p.copy(); q.smoothing_factor = 10
     assert lib.b200jpeg_validate(C.byref(q)) == A.ERR_UNSUPPORTED
     q = p.copy(); q.num_scans = 1; q.scan_info[0].comps_in_scan = 1; q.scan_info[0].Ss = 0; q.scan_info[0].Se = 63
     assert lib.b200jpeg_validate(C.byref(q)) == A.ERR_PARAM and b"transmit" in lib.b200jpeg_last_error()   # JERR_MISSING_DATA

@@ -68,11 +68,18 @@ SWITCH_SETS = [
     ["-dct", "float", "-baseline", "-notrellis", "-quality", "90", "-sample", "1x1"],
     ["-dct", "float", "-baseline", "-quality", "50", "-grayscale"],
     ["-dct", "float", "-quality", "75"],
+    # JDCT_IFAST (jfdctfst.c, scaled divisors + reciprocal quantizer)
+    ["-dct", "fast", "-baseline", "-quality", "75"],
+    ["-dct", "fast", "-fastcrush", "-quality", "40"],
+    ["-dct", "fast", "-baseline", "-notrellis", "-quality", "95", "-sample", "1x1"],
+    ["-dct", "fast", "-baseline", "-quality", "100", "-grayscale"],
+    ["-dct", "fast", "-quality", "75"],
 ]
 # through the reference's cjpeg binary only (our refshim driver does not parse these switches)
 CJPEG_ONLY = [
     ["-revert", "-dct", "float"],
     ["-revert", "-dct", "float", "-optimize", "-progressive"],
+    ["-revert", "-dct", "fast"],
     ["-quality", "75", "-dc-scan-opt", "2"],
     ["-quality", "60", "-dc-scan-opt", "1"],
     ["-quality", "85", "-dc-scan-opt", "0"],
