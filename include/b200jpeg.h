@@ -209,6 +209,17 @@ int  b200jpeg_encode_batch(b200jpeg_encoder *enc, const b200jpeg_params *p,
                            const void *pixels, int pixels_on_device,
                            size_t row_pitch, size_t image_stride, int n_images);
 
+/*
+ * Raw-data variant: replaces jpeg_write_raw_data (jcapistd.c:145-195; the entry point under tj3CompressFromYUV*):
+ * the caller supplies already converted and downsampled component planes, 8-bit samples.  planes[ci] points at
+ * image 0's plane of component ci, which must hold at least height_in_blocks*8 rows of width_in_blocks*8 samples
+ * (the library does no edge expansion on this path, exactly like the reference); row_pitch[ci] / image_stride[ci]
+ * in bytes.  in_color_space / input_components of the parameter block are ignored.
+ */
+int  b200jpeg_encode_batch_raw(b200jpeg_encoder *enc, const b200jpeg_params *p,
+                               const uint8_t *const *planes, int planes_on_device,
+                               const size_t *row_pitch, const size_t *image_stride, int n_images);
+
 /* Same, but stops after the entropy-coded bytes are in HBM: no device->host
  * copy, no host-side file assembly.  Used to time the device pipeline alone. */
 int  b200jpeg_encode_batch_device_only(b200jpeg_encoder *enc, const b200jpeg_params *p,

@@ -69,6 +69,17 @@ class Encoder:
         A.check(_lib.b200jpeg_encode_batch(self._h, C.byref(p), a.ctypes.data, 0, a.strides[1], a.strides[0], n), "encode_batch")
         return [self.get_output(i) for i in range(n)]
 
+    def encode_batch_raw(self, p: Params, planes: Sequence[np.ndarray]) -> List[bytes]:
+        """Raw-data input (jpeg_write_raw_data): planes[ci] is an (N, rows, cols) uint8 array holding
+        the converted, downsampled samples of component ci (at least hib*8 x wib*8 per image)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in planes]
+        n = arrs[0].shape[0]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        pitch = (C.c_size_t * len(arrs))(*[a.strides[1] for a in arrs])
+        stride = (C.c_size_t * len(arrs))(*[a.strides[0] for a in arrs])
+        A.check(_lib.b200jpeg_encode_batch_raw(self._h, C.byref(p), ptrs, 0, pitch, stride, n), "encode_batch_raw")
+        return [self.get_output(i) for i in range(n)]
+
     def encode_batch_ptr(self, p: Params, ptr: int, on_device: bool, row_pitch: int, image_stride: int, n: int,
                          device_only: bool = False) -> None:
         """Raw-pointer form (device tensors, pinned host buffers)."""

@@ -128,6 +128,7 @@ struct ChunkIO {
   int i0, n;
   int slot;                         // which arena / stream
   const uint8_t *src;               // first pixel of image i0 (device)
+  const uint8_t *plane[4];          // raw-data input: image i0's component planes (device)
   uint8_t *out;                     // [n][out_cap_per_image]
   unsigned long long *out_pos;      // [nscans+1][n]: start of every scan's bytes inside out[img]; row nscans = total
   uint32_t *status;                 // [n]
@@ -426,6 +427,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   const size_t hist_bytes = (size_t)n * HIST_SLOTS * HIST_BINS * 4;
   const size_t tabset = sizeof(DevHuff) * HIST_SLOTS;
   const uint8_t *src_dev = io.src;
+  for (int ci = 0; ci < 4; ci++) g.plane[ci] = io.plane[ci];
   uint32_t *status = io.status;
 
   // ---- pass 0 data path: colour/downsample/FDCT/quantize (compress_first_pass) ----
@@ -930,21 +932,43 @@ static int choose_chunk(const b200jpeg_encoder *e, const Plan &pl, int n_images,
   return (int)std::min<long long>(n_images, c);
 }
 
+// raw-data input (jpeg_write_raw_data): one plane per component instead of interleaved pixels
+struct RawDesc { const uint8_t *plane[4]; size_t pitch[4], stride[4]; };
+
 static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const void *pixels, int on_device,
-                         size_t row_pitch, size_t image_stride, int n_images, bool device_only)
+                         size_t row_pitch, size_t image_stride, int n_images, bool device_only, const RawDesc *raw = nullptr)
 {
-  if (!e || !p || !pixels || n_images <= 0) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  if (!e || !p || (!pixels && !raw) || n_images <= 0) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
   int rc = b200jpeg_validate(p);
   if (rc) return rc;
   const size_t sample_bytes = p->data_precision > 8 ? 2 : 1;                       // 12-bit samples are uint16 (J12SAMPLE)
   const size_t row_bytes = (size_t)p->image_width * p->input_components * sample_bytes;
-  if (row_pitch < row_bytes) { set_error("row_pitch smaller than a row"); return B200JPEG_ERR_PARAM; }
-  if (n_images > 1 && image_stride < row_pitch * (size_t)(p->image_height - 1) + row_bytes) { set_error("image_stride smaller than an image"); return B200JPEG_ERR_PARAM; }
+  if (!raw) {
+    if (row_pitch < row_bytes) { set_error("row_pitch smaller than a row"); return B200JPEG_ERR_PARAM; }
+    if (n_images > 1 && image_stride < row_pitch * (size_t)(p->image_height - 1) + row_bytes) { set_error("image_stride smaller than an image"); return B200JPEG_ERR_PARAM; }
+  }
   CU(cudaSetDevice(e->device));
   e->params = *p; e->n = n_images;
   if ((rc = build_plan(p, row_pitch, image_stride, e->plan))) return rc;
   Plan &pl = e->plan;
-  if (p->data_precision == 12 || p->dct_method != B200JPEG_DCT_ISLOW) {
+  size_t raw_plane_bytes[4] = {0, 0, 0, 0}, raw_total[4] = {0, 0, 0, 0}, raw_off[4] = {0, 0, 0, 0}, raw_sum = 0;
+  if (raw) {
+    Geom &g = pl.g;
+    if (p->data_precision != 8) { set_error("raw-data input is 8-bit only on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
+    bool gray = g.nc == 1 && g.hmax == 1 && g.vmax == 1;
+    bool ycc = g.nc == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax && g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
+    if (!gray && !ycc) { set_error("raw-data input: only 4:4:4/4:2:2/4:4:0/4:2:0 and single-component layouts are on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
+    g.raw_in = 1;
+    for (int ci = 0; ci < g.nc; ci++) {
+      const size_t rows = (size_t)g.c[ci].hib * 8, cols = (size_t)g.c[ci].wib * 8;      // what compress_first_pass reads (jccoefct.c:262-353)
+      if (!raw->plane[ci] || raw->pitch[ci] < cols || (n_images > 1 && raw->stride[ci] < raw->pitch[ci] * (rows - 1) + cols)) { set_error("raw-data plane %d: bad pointer, pitch or stride (needs %zu rows of %zu samples)", ci, rows, cols); return B200JPEG_ERR_PARAM; }
+      raw_plane_bytes[ci] = raw->pitch[ci] * (rows - 1) + cols;
+      raw_total[ci] = raw->stride[ci] * (size_t)(n_images - 1) + raw_plane_bytes[ci];
+      raw_off[ci] = raw_sum; raw_sum += (raw_total[ci] + 255) & ~(size_t)255;
+      g.plane_pitch[ci] = raw->pitch[ci]; g.plane_stride[ci] = raw->stride[ci];
+    }
+  }
+  if (!raw && (p->data_precision == 12 || p->dct_method != B200JPEG_DCT_ISLOW)) {
     const Geom &g = pl.g;
     bool gray = g.nc == 1 && g.hmax == 1 && g.vmax == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
     bool ycc = g.nc == 3 && g.cs_mode == 0 && g.in_comps == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax && g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
@@ -955,7 +979,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   const int nchunks = (n_images + C - 1) / C;
   e->chunk = C;
   const size_t image_bytes = row_pitch * (size_t)(p->image_height - 1) + row_bytes;
-  const size_t src_bytes = image_stride * (size_t)(n_images - 1) + image_bytes;
+  const size_t src_bytes = raw ? raw_sum : image_stride * (size_t)(n_images - 1) + image_bytes;
   while ((int)e->ev_in.size() < nchunks) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->ev_in.push_back(ev); }
   while ((int)e->ev_done.size() < nchunks) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->ev_done.push_back(ev); }
   if (!device_only) {
@@ -976,11 +1000,20 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
     if (nstreams > 1) { CU(cudaEventRecord(e->ev_fork, e->stream)); CU(cudaStreamWaitEvent(e->sc[1], e->ev_fork, 0)); }
     // stage every chunk's pixels up front on the copy stream; chunk k's kernels wait only for chunk k
     const uint8_t *src_base = static_cast<const uint8_t *>(pixels);
+    const uint8_t *plane_base[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (raw) for (int ci = 0; ci < pl.g.nc; ci++) plane_base[ci] = on_device ? raw->plane[ci] : e->d_src.as<uint8_t>() + raw_off[ci];
     if (!on_device) {
       for (int k = 0; k < nchunks; k++) {
         const int i0 = k * C, nk = std::min(C, n_images - i0);
-        const size_t off = (size_t)i0 * image_stride, bytes = image_stride * (size_t)(nk - 1) + image_bytes;
-        CU(cudaMemcpyAsync(e->d_src.as<uint8_t>() + off, static_cast<const uint8_t *>(pixels) + off, bytes, cudaMemcpyHostToDevice, e->s_in));
+        if (raw) {
+          for (int ci = 0; ci < pl.g.nc; ci++) {
+            const size_t off = (size_t)i0 * raw->stride[ci], bytes = raw->stride[ci] * (size_t)(nk - 1) + raw_plane_bytes[ci];
+            CU(cudaMemcpyAsync(e->d_src.as<uint8_t>() + raw_off[ci] + off, raw->plane[ci] + off, bytes, cudaMemcpyHostToDevice, e->s_in));
+          }
+        } else {
+          const size_t off = (size_t)i0 * image_stride, bytes = image_stride * (size_t)(nk - 1) + image_bytes;
+          CU(cudaMemcpyAsync(e->d_src.as<uint8_t>() + off, static_cast<const uint8_t *>(pixels) + off, bytes, cudaMemcpyHostToDevice, e->s_in));
+        }
         CU(cudaEventRecord(e->ev_in[k], e->s_in));
       }
       src_base = e->d_src.as<uint8_t>();
@@ -998,7 +1031,8 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
       ChunkIO io;
       io.i0 = k * C; io.n = std::min(C, n_images - io.i0);
       io.slot = k % nstreams;
-      io.src = src_base + (size_t)io.i0 * image_stride;
+      io.src = raw ? nullptr : src_base + (size_t)io.i0 * image_stride;
+      for (int ci = 0; ci < 4; ci++) io.plane[ci] = raw && plane_base[ci] ? plane_base[ci] + (size_t)io.i0 * raw->stride[ci] : nullptr;
       io.out = e->d_out.as<uint8_t>() + (size_t)io.i0 * e->out_cap_per_image;
       io.out_pos = e->d_out_pos.as<unsigned long long>() + (size_t)io.i0 * (nscans + 1);
       io.status = e->d_status.as<uint32_t>() + io.i0;
@@ -1142,6 +1176,15 @@ int b200jpeg_encode_batch_device_only(b200jpeg_encoder *enc, const b200jpeg_para
                                       size_t row_pitch, size_t image_stride, int n_images)
 {
   return encode_common(enc, p, pixels_device, 1, row_pitch, image_stride, n_images, true);
+}
+
+int b200jpeg_encode_batch_raw(b200jpeg_encoder *enc, const b200jpeg_params *p, const uint8_t *const *planes, int planes_on_device,
+                              const size_t *row_pitch, const size_t *image_stride, int n_images)
+{
+  if (!enc || !p || !planes || !row_pitch || !image_stride) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  RawDesc rd; memset(&rd, 0, sizeof rd);
+  for (int ci = 0; ci < p->num_components && ci < 4; ci++) { rd.plane[ci] = planes[ci]; rd.pitch[ci] = row_pitch[ci]; rd.stride[ci] = image_stride[ci]; }
+  return encode_common(enc, p, nullptr, planes_on_device, 0, 0, n_images, false, &rd);
 }
 
 int b200jpeg_get_output(b200jpeg_encoder *e, int i, const uint8_t **data, size_t *size)

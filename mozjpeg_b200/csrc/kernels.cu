@@ -387,6 +387,38 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   {
     const int rg = tid >> 4, seg = tid & 15;
     const int xs = x0 + seg * 8;
+    if (PREC == 8 && g.raw_in) {
+      // raw-data input: the planes are already converted and downsampled; only centre them (convsamp).  Samples past
+      // the component's last real block are never used (those blocks are skipped on output), so they read as 0.
+#pragma unroll
+      for (int rr = 0; rr < VMAX; rr++) {
+        const int row = y0 + rg * VMAX + rr;
+        const CompGeom &c0 = g.c[0];
+        int16_t yv[8];
+#pragma unroll
+        for (int px = 0; px < 8; px++) {
+          const int x = xs + px;
+          yv[px] = (row < c0.hib * 8 && x < c0.wib * 8) ? (int16_t)((int)g.plane[0][(size_t)img * g.plane_stride[0] + (size_t)row * g.plane_pitch[0] + x] - 128) : (int16_t)0;
+        }
+        *reinterpret_cast<uint4 *>(&sY[(rg * VMAX + rr) * YP + seg * 8]) = *reinterpret_cast<const uint4 *>(yv);
+      }
+      if (NC == 3) {
+        const int row = ty * 8 + rg;
+#pragma unroll
+        for (int cc = 1; cc <= 2; cc++) {
+          const CompGeom &c1 = g.c[cc];
+          int16_t cv[8 / HMAX];
+#pragma unroll
+          for (int i = 0; i < 8 / HMAX; i++) {
+            const int x = x0 / HMAX + seg * (8 / HMAX) + i;
+            cv[i] = (row < c1.hib * 8 && x < c1.wib * 8) ? (int16_t)((int)g.plane[cc][(size_t)img * g.plane_stride[cc] + (size_t)row * g.plane_pitch[cc] + x] - 128) : (int16_t)0;
+          }
+          int16_t *dst = &sC[(cc - 1) * 8 * CP + rg * CP + seg * (8 / HMAX)];
+          if (HMAX == 1) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(cv);
+          else *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(cv);
+        }
+      }
+    } else {
     const bool grey_from_rgb = NC == 1 && g.cs_mode == 1;
     constexpr size_t AL = SB == 1 ? 7 : 15;
     const bool fast = (xs + 8 <= g.W) && ((g.row_pitch & AL) == 0) && ((((size_t)base) & AL) == 0) && !grey_from_rgb;
@@ -448,6 +480,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
         if (HMAX == 1) { *reinterpret_cast<uint4 *>(cb) = *reinterpret_cast<const uint4 *>(cbv); *reinterpret_cast<uint4 *>(cr) = *reinterpret_cast<const uint4 *>(crv); }
         else { *reinterpret_cast<uint2 *>(cb) = *reinterpret_cast<const uint2 *>(cbv); *reinterpret_cast<uint2 *>(cr) = *reinterpret_cast<const uint2 *>(crv); }
       }
+    }
     }
   }
   __syncthreads();
@@ -665,8 +698,8 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
 {
   const int write_raw = rec != nullptr || keep_raw;
   // fast path: full-size first component, (for colour) two 1x1-sampled chroma components
-  bool gray = g.nc == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
-  bool ycc = g.nc == 3 && g.cs_mode == 0 && g.in_comps == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax &&
+  bool gray = g.nc == 1 && (g.raw_in || g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
+  bool ycc = g.nc == 3 && (g.raw_in || (g.cs_mode == 0 && g.in_comps == 3)) && g.c[0].h == g.hmax && g.c[0].v == g.vmax &&
              g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
   static const bool force_generic = getenv("B200JPEG_GENERIC_FORWARD") != nullptr;   // A/B switch for debugging
   if (!force_generic && ((gray && g.hmax == 1 && g.vmax == 1) || ycc)) {

@@ -38,6 +38,10 @@ struct Geom {
   int max_coef_bits;   // data_precision + 2
   int cs_mode;         // 0: RGB->YCbCr  1: RGB->gray  2: pass-through
   size_t row_pitch, image_stride;
+  // raw-data input (jpeg_write_raw_data, jcapistd.c:145-195): downsampled component planes instead of pixels;
+  // plane ci holds at least hib*8 rows of wib*8 samples
+  int raw_in;
+  const uint8_t *plane[4]; size_t plane_pitch[4], plane_stride[4];
   CompGeom c[4];
 };
 

@@ -30,3 +30,19 @@ def synth_image12(seed: int, width: int, height: int) -> np.ndarray:
     base = synth_image(seed, width, height).astype(np.uint16) * 16
     rng = np.random.default_rng(seed + 7919)
     return (base + rng.integers(0, 16, base.shape, dtype=np.uint16)).astype(np.uint16)
+
+
+def synth_planes(p, seed: int):
+    """Raw-data test input (jpeg_write_raw_data): one (hib*8, wib*8) uint8 plane per component of the
+    parameter block p, smooth field + noise, already 'downsampled'."""
+    rng = np.random.default_rng(seed)
+    nc = p.num_components
+    hmax = max(p.comp_info[i].h_samp_factor for i in range(nc)); vmax = max(p.comp_info[i].v_samp_factor for i in range(nc))
+    out = []
+    for ci in range(nc):
+        h = p.comp_info[ci].h_samp_factor; v = p.comp_info[ci].v_samp_factor
+        wib = -(-p.image_width * h // (hmax * 8)); hib = -(-p.image_height * v // (vmax * 8))
+        yy, xx = np.mgrid[0:hib * 8, 0:wib * 8]
+        a = 128 + 90 * np.sin(xx / (7 + 3 * ci)) * np.cos(yy / (9 + 2 * ci)) + rng.normal(0, 10, (hib * 8, wib * 8))
+        out.append(np.clip(a, 0, 255).astype(np.uint8))
+    return out

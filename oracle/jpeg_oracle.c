@@ -543,6 +543,7 @@ typedef struct {
   int dc_sent[4], ac_sent[4], qt_sent[4];
   int progressive;
   int last_restart_interval;
+  const uint8_t *const *raw_planes; const size_t *raw_pitch;
   bytebuf out;
   int err;
 } enc_t;
@@ -943,12 +944,14 @@ static void fill_dummy_blocks(enc_t *e, int ci)
 /* samples are uint8 (8-bit) or uint16 holding 12-bit values (J12SAMPLE, jmorecfg.h) */
 static int forward_all(enc_t *e, const uint8_t *pix, size_t pitch)
 {
+  const uint8_t *const *rawp = e->raw_planes; const size_t *rawpitch = e->raw_pitch;     /* jpeg_write_raw_data input, or NULL */
   const b200jpeg_params *p = e->p;
   const int prec = p->data_precision, centre = 1 << (prec - 1);
   int W = e->W, H = e->H, ci, x, y;
   /* full-resolution converted planes (jccolor.c) */
   uint16_t *full[4] = {0, 0, 0, 0};
   for (ci = 0; ci < e->nc; ci++) full[ci] = (uint16_t *)malloc((size_t)W * H * 2);
+  if (rawp) goto planes_ready;                       /* raw data: no colour conversion, no downsampling, no edge expansion */
 #define IN(xx, cc) (prec == 8 ? (int)row[p->input_components * (xx) + (cc)] : (int)((const uint16_t *)row)[p->input_components * (xx) + (cc)])
   for (y = 0; y < H; y++) {
     const uint8_t *row = pix + (size_t)y * pitch;
@@ -965,6 +968,7 @@ static int forward_all(enc_t *e, const uint8_t *pix, size_t pitch)
     }
   }
 #undef IN
+planes_ready:
   for (ci = 0; ci < e->nc; ci++) {
     const b200jpeg_component_info *c = &p->comp_info[ci];
     int hx = e->hmax / c->h_samp_factor, vx = e->vmax / c->v_samp_factor;
@@ -973,6 +977,9 @@ static int forward_all(enc_t *e, const uint8_t *pix, size_t pitch)
     int rows_avail = groups * c->v_samp_factor;
     uint16_t *plane = (uint16_t *)malloc((size_t)ow * oh * 2);
     int numpix = hx * vx, bx, by, i;
+    if (rawp) {                                       /* compress_first_pass reads hib*8 rows of wib*8 samples straight from the caller's planes */
+      for (y = 0; y < oh; y++) for (x = 0; x < ow; x++) plane[(size_t)y * ow + x] = rawp[ci][(size_t)y * rawpitch[ci] + x];
+    } else
     for (y = 0; y < oh; y++) {
       int yy = y < rows_avail ? y : rows_avail - 1;          /* expand_bottom_edge on the downsampled rows */
       int g = yy / c->v_samp_factor, s = yy % c->v_samp_factor;
@@ -1034,6 +1041,19 @@ static void trellis_component(enc_t *e, int ci)
 void orc_free(void *p) { free(p); }
 void orc_debug_free(orc_debug *d) { int i; for (i = 0; i < 4; i++) { free(d->plain[i]); free(d->raw[i]); free(d->final_[i]); } memset(d, 0, sizeof *d); }
 
+static const uint8_t *const *g_raw_planes; static const size_t *g_raw_pitch;   /* set by orc_encode_raw around its call of orc_encode (test infrastructure: single-threaded) */
+int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch,
+               uint8_t **out, size_t *outsize, orc_debug *dbg);
+/* jpeg_write_raw_data (jcapistd.c:145-195): component planes instead of pixels */
+int orc_encode_raw(const b200jpeg_params *p, const uint8_t *const *planes, const size_t *pitch, uint8_t **out, size_t *outsize)
+{
+  int rc;
+  if (p->data_precision != 8) return B200JPEG_ERR_UNSUPPORTED;
+  g_raw_planes = planes; g_raw_pitch = pitch;
+  rc = orc_encode(p, planes[0], pitch[0], out, outsize, NULL);
+  g_raw_planes = NULL; g_raw_pitch = NULL;
+  return rc;
+}
 int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch,
                uint8_t **out, size_t *outsize, orc_debug *dbg)
 {
@@ -1043,6 +1063,7 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
   *out = NULL; *outsize = 0;
   if (dbg) memset(dbg, 0, sizeof *dbg);
   e->p = p; e->nc = p->num_components; e->W = p->image_width; e->H = p->image_height;
+  e->raw_planes = g_raw_planes; e->raw_pitch = g_raw_pitch;
   /* 12-bit: no JBUF_REQUANT => no trellis (jccoefct.c:132-138); deringing is not usable at 12 bits (jcdctmgr.c:419) */
   if (p->data_precision == 12 && (p->trellis_quant || p->overshoot_deringing)) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   if ((p->data_precision != 8 && p->data_precision != 12) || (p->dct_method != B200JPEG_DCT_ISLOW && p->data_precision != 8) || p->smoothing_factor ||

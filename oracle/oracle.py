@@ -201,6 +201,47 @@ def ref_encode(pixels: np.ndarray, switches: Sequence[str]) -> bytes:
     return data
 
 
+def _plane_args(planes):
+    arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in planes]
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    return arrs, ptrs
+
+
+def oracle_encode_raw(p: A.Params, planes) -> bytes:
+    """C restatement on raw-data input: planes[ci] = (hib*8, wib*8) uint8 (jpeg_write_raw_data semantics)."""
+    lib = orc()
+    lib.orc_encode_raw.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
+    lib.orc_encode_raw.restype = C.c_int
+    arrs, ptrs = _plane_args(planes)
+    pitch = (C.c_size_t * len(arrs))(*[a.strides[0] for a in arrs])
+    out = C.POINTER(C.c_uint8)(); n = C.c_size_t(0)
+    rc = lib.orc_encode_raw(C.byref(p), ptrs, pitch, C.byref(out), C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"oracle raw encode failed: {rc}")
+    data = C.string_at(out, n.value)
+    lib.orc_free(out)
+    return data
+
+
+def ref_encode_raw(planes, width: int, height: int, switches: Sequence[str]) -> bytes:
+    """The UNMODIFIED reference through jpeg_write_raw_data."""
+    lib = ref()
+    lib.refshim_encode_raw.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_ulong), C.c_char_p, C.c_int]
+    lib.refshim_encode_raw.restype = C.c_int
+    arrs, ptrs = _plane_args(planes)
+    pitch = (C.c_int * len(arrs))(*[a.strides[0] for a in arrs])
+    cfg = refcfg_from_switches(switches, len(arrs) == 1)
+    out = C.POINTER(C.c_uint8)(); n = C.c_ulong(0)
+    err = C.create_string_buffer(256)
+    rc = lib.refshim_encode_raw(ptrs, pitch, width, height, len(arrs), C.byref(cfg), C.byref(out), C.byref(n), err, 256)
+    if rc != 0:
+        raise RuntimeError("reference raw encode failed: " + err.value.decode())
+    data = C.string_at(out, n.value)
+    lib.refshim_free(out)
+    return data
+
+
 def ref_read_coefs(jpeg: bytes) -> Dict[str, object]:
     """jpeg_read_coefficients via the reference decoder: per-component
     [hib][wib][64] int16 (natural order) + quant tables."""

@@ -182,6 +182,46 @@ int refshim_encode(const void *pixels, int width, int height, int pitch_samples,
   return 0;
 }
 
+/* The same through jpeg_write_raw_data: planes[ci] = hib*8 rows of wib*8 samples (pitch in samples). */
+int refshim_encode_raw(const unsigned char *const *planes, const int *pitch, int width, int height, int ncomp,
+                       const refshim_cfg *cfg, unsigned char **out, unsigned long *outsize, char *errbuf, int errlen)
+{
+  struct jpeg_compress_struct cinfo;
+  struct my_err jerr;
+  int fb = 0, sp = 0, ci;
+  *out = NULL; *outsize = 0;
+  cinfo.err = jpeg_std_error(&jerr.pub);
+  jerr.pub.error_exit = my_exit;
+  if (setjmp(jerr.jb)) { (*cinfo.err->format_message)((j_common_ptr)&cinfo, jerr.msg); snprintf(errbuf, errlen, "%s", jerr.msg); jpeg_destroy_compress(&cinfo); return 1; }
+  jpeg_create_compress(&cinfo);
+  cinfo.in_color_space = ncomp == 1 ? JCS_GRAYSCALE : JCS_YCbCr;      /* raw data: the planes are already in the JPEG colour space */
+  cinfo.input_components = ncomp;
+  jpeg_set_defaults(&cinfo);
+  apply_switches(&cinfo, cfg, 0, &fb, &sp);
+  cinfo.image_width = width; cinfo.image_height = height;
+  jpeg_default_colorspace(&cinfo);
+  apply_switches(&cinfo, cfg, 1, &fb, &sp);
+  cinfo.raw_data_in = TRUE;
+  jpeg_mem_dest(&cinfo, out, outsize);
+  jpeg_start_compress(&cinfo, TRUE);
+  {
+    JSAMPROW rows[3][32]; JSAMPARRAY data[3];
+    int lines = cinfo.max_v_samp_factor * DCTSIZE;
+    for (ci = 0; ci < ncomp; ci++) data[ci] = rows[ci];
+    while (cinfo.next_scanline < cinfo.image_height) {
+      int imcu = cinfo.next_scanline / lines, r;
+      for (ci = 0; ci < ncomp; ci++) {
+        int v = cinfo.comp_info[ci].v_samp_factor, hrows = (int)cinfo.comp_info[ci].height_in_blocks * DCTSIZE;
+        for (r = 0; r < v * DCTSIZE; r++) { int y = imcu * v * DCTSIZE + r; if (y > hrows - 1) y = hrows - 1; rows[ci][r] = (JSAMPROW)(planes[ci] + (size_t)y * pitch[ci]); }
+      }
+      jpeg_write_raw_data(&cinfo, data, lines);
+    }
+  }
+  jpeg_finish_compress(&cinfo);
+  jpeg_destroy_compress(&cinfo);
+  return 0;
+}
+
 void refshim_free(void *p) { free(p); }
 
 /*

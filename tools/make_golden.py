@@ -125,6 +125,17 @@ def main():
         for sw in SWITCH_SETS_12:
             a = O.ref_encode(im, sw)
             cases.append({"image": [seed, sw_, sh_, 12], "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
+    # raw-data input (jpeg_write_raw_data): separate fixture, the inputs are component planes
+    from mozjpeg_b200.synth import synth_planes
+    raw_cases = []
+    for (seed, w_, h_) in [(31, 33, 17), (32, 200, 136), (33, 227, 149), (34, 640, 480)]:
+        for sw in (["-baseline", "-quality", "75"], ["-quality", "75"], ["-baseline", "-quality", "85", "-sample", "1x1"],
+                   ["-fastcrush", "-quality", "60", "-sample", "2x1"], ["-baseline", "-quality", "75", "-grayscale"],
+                   ["-baseline", "-notrellis", "-quality", "90", "-sample", "1x2", "-dct", "float"]):
+            pp = cjpeg.params_from_switches(sw, w_, h_, 1 if "-grayscale" in sw else 3)
+            a = O.ref_encode_raw(synth_planes(pp, seed), w_, h_, sw)
+            raw_cases.append({"seed": seed, "width": w_, "height": h_, "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
+    json.dump({"generator": "tools/make_golden.py", "cases": raw_cases}, open(os.path.join(GOLD, "raw_golden.json"), "w"), indent=0)
     assert cases[0]["md5"] == "9a68f56bc76e466aa7e52f415d0f4a5f", "reference build does not reproduce MD5_JPEG_420_ISLOW"
     json.dump({"generator": "tools/make_golden.py", "reference": "mozilla/mozjpeg 5.0.0 (C path, WITH_SIMD=0), oracle/_ref", "cases": cases},
               open(os.path.join(GOLD, "golden.json"), "w"), indent=0)
