@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   __shared__ __align__(16) wtype sW[NB * 72];
   __shared__ __align__(16) unsigned char sIO[NB * 256];   // phases D/E: output staging
   __shared__ uint2 sQC[NC][64];                           // quantizer constants per component, natural order
+  __shared__ uint2 sMask[NB];                             // per block: zigzag positions of its non-zero AC values
   __shared__ int sQL[NC];
 
   const int tid = threadIdx.x;
@@ -631,44 +632,49 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
       if (nzv && nat != 0) { if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
     }
     if (PREC == 8 && rec) {
-      // the raw coefficients go back to sW in natural order (each lane rewrites exactly the words it
-      // read), lane r then owns ROW r and the serial fp32 sum of squares in NATURAL order
-      // (jcdctmgr.c:1026-1029) is handed from lane to lane, 8 adds per hop
+      // the raw coefficients go back to sW in natural order (each lane rewrites exactly the words it read) for
+      // phase D2; the 8 lanes OR their non-zero masks together
       if (DCTM == 2) __syncwarp();                             // every lane has read its float column before the int16 view reuses the words
       int16_t *blk16 = reinterpret_cast<int16_t *>(sW + b * 72);     // the block's own words (also when sW holds floats)
       int16_t *ww = blk16 + j;
 #pragma unroll
       for (int r = 0; r < 8; r++) ww[8 * r] = (int16_t)dd[r];
-      __syncwarp();
-      const int4 rowv = *reinterpret_cast<const int4 *>(blk16 + 8 * j);
-      const int pw[4] = {rowv.x, rowv.y, rowv.z, rowv.w};
-      float sq[8];
-#pragma unroll
-      for (int cidx = 0; cidx < 8; cidx++) { int v = (int)(int16_t)((unsigned)pw[cidx >> 1] >> ((cidx & 1) * 16)); sq[cidx] = (float)(v * v); }
-      float norm = 0.0f;
-      const int gbase = (tid & 31) & ~7;
-#pragma unroll
-      for (int step = 0; step < 8; step++) {
-        float acc = norm;
-        if (step != 0) acc += sq[0];
-        acc += sq[1]; acc += sq[2]; acc += sq[3]; acc += sq[4]; acc += sq[5]; acc += sq[6]; acc += sq[7];
-        norm = __shfl_sync(0xffffffffu, j == step ? acc : norm, gbase + step);
-      }
       mlo |= __shfl_xor_sync(0xffffffffu, mlo, 1); mhi |= __shfl_xor_sync(0xffffffffu, mhi, 1);
       mlo |= __shfl_xor_sync(0xffffffffu, mlo, 2); mhi |= __shfl_xor_sync(0xffffffffu, mhi, 2);
       mlo |= __shfl_xor_sync(0xffffffffu, mlo, 4); mhi |= __shfl_xor_sync(0xffffffffu, mhi, 4);
-      int row, col;
-      if (b < YB) { int byl = b / YBW; row = ty * VMAX + byl; col = tx * YBW + (b - byl * YBW); }
-      else { int cb = b - YB; int which = cb / CBW; row = ty; col = tx * CBW + (cb - which * CBW); }
-      const CompGeom &c = g.c[ci];
-      if (j == 0 && row < c.hib && col < c.wib) {
-        DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)dd[0]; rr.nz = (uint8_t)(__popc(mlo) + __popc(mhi)); rr.pad = 0;
-        rr.nzmask = ((unsigned long long)mhi << 32) | mlo;
-        rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * c.wib + col] = rr;
-      }
+      if (j == 0) sMask[b] = make_uint2(mlo, mhi);
     }
   }
   __syncthreads();
+
+  // ---- D2: trellis side records, one thread per block: the serial fp32 sum of squares in NATURAL order
+  //      (jcdctmgr.c:1026-1029) over the block's rows (16-byte shared loads; the 144-byte block stride keeps
+  //      them conflict-free), the raw DC and the non-zero mask ----
+  if (PREC == 8 && rec) {
+    for (int b = tid; b < NB; b += 128) {
+      int ci, row, col;
+      if (b < YB) { ci = 0; int byl = b / YBW; row = ty * VMAX + byl; col = tx * YBW + (b - byl * YBW); }
+      else { int cb = b - YB; int which = cb / CBW; ci = 1 + which; row = ty; col = tx * CBW + (cb - which * CBW); }
+      const CompGeom &c = g.c[ci];
+      if (row >= c.hib || col >= c.wib) continue;
+      const int4 *rows = reinterpret_cast<const int4 *>(reinterpret_cast<const int16_t *>(sW + b * 72));
+      float norm = 0.0f; int raw_dc = 0;
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const int4 rv = rows[r];
+        const int pw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+        for (int cidx = 0; cidx < 8; cidx++) {
+          const int v = (int)(int16_t)((unsigned)pw[cidx >> 1] >> ((cidx & 1) * 16));
+          if (r == 0 && cidx == 0) raw_dc = v; else norm += (float)(v * v);
+        }
+      }
+      const uint2 mk = sMask[b];
+      DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)raw_dc; rr.nz = (uint8_t)(__popc(mk.x) + __popc(mk.y)); rr.pad = 0;
+      rr.nzmask = ((unsigned long long)mk.y << 32) | mk.x;
+      rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * c.wib + col] = rr;
+    }
+  }
 
   // ---- E: whole blocks out, 16 bytes per thread-store ----
   for (int i = tid; i < NB * 8; i += 128) {
