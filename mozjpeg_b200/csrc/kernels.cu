@@ -1563,8 +1563,10 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
   const int n_imcu = (c.hib + c.v - 1) / c.v;
   const int imcu0 = (blockIdx.x * DC2_WARPS + warp) * 3;        // first of this warp's three chains
   const int wib = c.wib;
-  uint8_t *btw = dsm + (size_t)warp * 3 * max_wib * 9;          // [3][max_wib][9]
-  uint8_t *bt = btw + (size_t)gsel * max_wib * 9;
+  // back pointers: 9 nibbles per block packed into 5 bytes (candidates 2i, 2i+1 in byte i; byte 4 = candidate 8 in the
+  // low nibble, and after the back-track the block's chosen candidate in the high nibble)
+  uint8_t *btw = dsm + (size_t)warp * 3 * max_wib * 5;          // [3][max_wib][5]
+  uint8_t *bt = btw + (size_t)gsel * max_wib * 5;
   const int q = tc->q8_zz[c.qt][0];
   int ncand = (2 + 60 / (q >> 3)) | 1; if (ncand > 9) ncand = 9;     // get_num_dc_trellis_candidates (:929-933)
   const int half = ncand / 2;
@@ -1587,7 +1589,7 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
     // previous block's candidate l is psgn * clamp(pbase + l); for the row's first block every
     // predecessor is last_dc with zero accumulated cost (pstep = 0)
     int pbase = last_dc, psgn = 1, pstep = 0;
-    uint8_t *btp = bt + k;
+    uint8_t *btp = bt + (k >> 1);
     for (int bi0 = 0; bi0 < wib; bi0 += 32) {
       __syncwarp();
 #pragma unroll
@@ -1641,8 +1643,12 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
         if (c45 < c01) { c01 = c45; i01 = i45; }
         if (cst[8] < c01) { c01 = cst[8]; i01 = 8; }
         acc = (FAST || k < ncand) ? c01 : INF;
-        if (rowok && (FAST || k < ncand)) *btp = (uint8_t)i01;
-        btp += 9;
+        {
+          const int hi = __shfl_down_sync(0xffffffffu, i01, 1);          // candidate k+1's pointer (lane k+1 of the same chain for even k < 8)
+          const int nib = (FAST || k < ncand) ? i01 : 0, nibhi = (k < 8 && (FAST || k + 1 < ncand)) ? hi : 0;
+          if (rowok && !(k & 1)) *btp = (uint8_t)(nib | (nibhi << 4));
+        }
+        btp += 5;
         pbase = base; psgn = sgn; pstep = 1;
       }
     }
@@ -1655,8 +1661,10 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
     if (rowok && k == 0) {
 #pragma unroll 4
       for (int bi = wib - 1; bi >= 0; bi--) {
-        int jn = bt[(size_t)bi * 9 + j];
-        bt[(size_t)bi * 9] = (uint8_t)j;
+        uint8_t *bb = bt + (size_t)bi * 5;
+        const int byte = bb[j >> 1];
+        const int jn = (j & 1) ? (byte >> 4) : (byte & 15);
+        bb[4] = (uint8_t)((bb[4] & 15) | (j << 4));
         j = jn;
       }
     }
@@ -1664,12 +1672,12 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
     // candidates -> coefficients, all lanes; the row's last value seeds the next row (jccoefct.c:418, :1320)
 #pragma unroll
     for (int gg = 0; gg < 3; gg++) {
-      const uint8_t *btg = btw + (size_t)gg * max_wib * 9;
+      const uint8_t *btg = btw + (size_t)gg * max_wib * 5;
       int lastv = 0;
       for (int bi = lane; bi < wib && okg[gg]; bi += 32) {
         DcRec r = rec[comp_rec + (size_t)rowg[gg] * wib + bi];
         int raw = r.raw_dc, sign = raw >> 31, x = abs(raw);
-        int cdv = (int)(((unsigned long long)(unsigned)(x + qhalf) * qmul) >> qshift) - half + btg[(size_t)bi * 9];
+        int cdv = (int)(((unsigned long long)(unsigned)(x + qhalf) * qmul) >> qshift) - half + (btg[(size_t)bi * 5 + 4] >> 4);
         if (cdv >= lim) cdv = lim - 1;
         if (cdv <= -lim) cdv = -lim + 1;
         if (sign) cdv = -cdv;
@@ -1690,7 +1698,7 @@ void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *ta
   for (int ci = 0; ci < g.nc; ci++) { n_imcu = max(n_imcu, (g.c[ci].hib + g.c[ci].v - 1) / g.c[ci].v); max_wib = max(max_wib, g.c[ci].wib); }
   // warp-cooperative kernel when the chains' back pointers fit in shared memory
   static const bool use_v1 = getenv("B200JPEG_DC_V1") != nullptr;      // A/B switch
-  size_t smem2 = (size_t)DC2_WARPS * 3 * max_wib * 9;
+  size_t smem2 = (size_t)DC2_WARPS * 3 * max_wib * 5;
   if (!use_v1 && smem2 <= 200 * 1024) {
     static size_t attr2 = 0;
     if (smem2 > 40 * 1024 && smem2 > attr2) { cudaFuncSetAttribute(k_trellis_dc_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cudaFuncSetAttribute(k_trellis_dc_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr2 = 200 * 1024; }
