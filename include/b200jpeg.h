@@ -99,7 +99,7 @@ typedef struct {
   int dct_method;
   int restart_interval;                   /* MCUs; 0 = none */
   int restart_in_rows;
-  int smoothing_factor;                   /* must be 0 */
+  int smoothing_factor;                   /* 0..100 (jcsample.c:298-455; ignored for raw-data input) */
   int write_JFIF_header;
   int JFIF_major_version, JFIF_minor_version;
   int density_unit, X_density, Y_density;
@@ -119,7 +119,7 @@ typedef struct {
   int quant_tbl_master_idx;               /* JINT_BASE_QUANT_TBL_IDX */
   int dc_scan_opt_mode;
   float lambda_log_scale1, lambda_log_scale2;
-  float trellis_delta_dc_weight;          /* must be 0 */
+  float trellis_delta_dc_weight;          /* cjpeg -trellis-dc-ver-weight (jcdctmgr.c:1069-1086) */
   /* cjpeg keeps these outside cinfo (rdswitch.c:509): per-slot linear scale factors */
   int q_scale_factor[B200JPEG_NUM_QUANT_TBLS];
 } b200jpeg_params;

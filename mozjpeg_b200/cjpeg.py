@@ -133,6 +133,8 @@ def _parse(p: A.Params, argv: Sequence[str], for_real: bool) -> None:
             p.trellis_quant_dc = 0
         elif _keymatch(a, "notrellis", 1):
             p.trellis_quant = 0
+        elif _keymatch(a, "trellis-dc-ver-weight", 11):          # cjpeg.c:667-672
+            p.trellis_delta_dc_weight = float(nextarg("trellis-dc-ver-weight"))
         elif _keymatch(a, "trellis-dc", 9):
             p.trellis_quant_dc = 1
         elif _keymatch(a, "tune-psnr", 6):

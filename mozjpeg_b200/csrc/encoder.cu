@@ -60,6 +60,7 @@ struct Plan {                // everything derived from b200jpeg_params
   Geom g;
   std::vector<ScanDesc> scans;
   bool progressive = false, optimize = false, trellis = false, dering = false, restarts = false;
+  int smooth = 0;                // smoothing_factor: colour conversion + (smoothing) downsampling run as a pre-pass into planes
   // scan search (optimize_scans): the script of jpeg_search_progression (jcparam.c:733-852) and where its groups start
   bool search = false; int n_luma = 0, luma_split0 = 0, chroma_split0 = 0, chroma_al0 = 0;
   std::vector<int> order;        // scan ids in the order they are encoded; position in `order` = slot in out_pos
@@ -74,11 +75,12 @@ using namespace b200;
 
 // intermediate HBM state of one chunk in flight
 struct Arena {
+  b200::DevBuf d_planes;             // input smoothing: the pre-pass's component planes
   b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm, d_splits, d_best_al;
   b200::DevBuf d_blk_bits, d_tile_bits, d_tile_base, d_seg_corr, d_mark, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
   b200::Geom g;                      // the plan's geometry with this arena's coefficient pointers
   void release() {
-    b200::DevBuf *db[] = {&d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_splits, &d_best_al, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
+    b200::DevBuf *db[] = {&d_planes, &d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_splits, &d_best_al, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
     for (b200::DevBuf *b : db) b->release();
     for (int i = 0; i < 4; i++) { d_coef[i].release(); d_raw[i].release(); d_plain[i].release(); }
   }
@@ -200,6 +202,7 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
   pl.optimize = p->optimize_coding || pl.progressive || p->data_precision == 12;   // jcmaster.c:1091-1094, :1102-1105
   pl.trellis = p->trellis_quant != 0;
   pl.dering = p->overshoot_deringing != 0;
+  pl.smooth = p->smoothing_factor;
   pl.search = p->optimize_scans && p->num_scans > 0;
   if (pl.search) {
     // every candidate is buffered with its own scan header; a DRI marker opens it when its restart interval differs from
@@ -289,6 +292,7 @@ static void make_trellis_consts(const b200jpeg_params *p, TrellisConsts *tc)
     for (int k = 0; k < 64; k++) { unsigned d = 8u * p->quant_tbl[t][kZigzag[k]]; tc->qmul_zz[t][k] = (unsigned)std::min<unsigned long long>(((1ull << (18 + L)) + d - 1) / d, 0xFFFFFFFFull); }
   }
   tc->use_norm = p->lambda_log_scale2 > 0.0f;
+  tc->delta_dc_weight = p->trellis_delta_dc_weight;
   tc->p1 = pow(2.0, (double)p->lambda_log_scale1);
   tc->p2 = pow(2.0, (double)p->lambda_log_scale2);
   tc->lambda_const = (float)(pow(2.0, (double)p->lambda_log_scale1 - 12.0) * 1.0f);
@@ -339,6 +343,14 @@ static uint32_t scan_slot_mask(const Plan &pl, const ScanDesc &sd)
   return m;
 }
 
+// bytes per image of the smoothing pre-pass's planes (hib*8 rows of wib*8 samples per component, 256-byte aligned each)
+static size_t smooth_plane_bytes(const Geom &g)
+{
+  const size_t sb = g.max_coef_bits == 14 ? 2 : 1; size_t t = 0;
+  for (int ci = 0; ci < g.nc; ci++) t += ((size_t)g.c[ci].wib * 8 * sb * g.c[ci].hib * 8 + 255) & ~(size_t)255;
+  return t;
+}
+
 // Buffers and constants of one batch of n_total images processed in chunks of `chunk`.
 static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_pixels, size_t src_bytes, int n_arenas)
 {
@@ -362,6 +374,7 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
       a.g.c[ci].coef = a.d_coef[ci].as<int16_t>(); a.g.c[ci].raw = a.d_raw[ci].as<int16_t>();
       if (e->keep_plain && pl.trellis) { if ((rc = a.d_plain[ci].reserve(pl.coef_bytes[ci] * n))) return rc; }
     }
+    if (pl.smooth && !g.raw_in) { if ((rc = a.d_planes.reserve(smooth_plane_bytes(g) * n))) return rc; }
     if ((rc = a.d_hist.reserve(hist_bytes * g.nc))) return rc;
     if ((rc = a.d_tabs_trellis.reserve(tabset * 4 * n))) return rc;
     if ((rc = a.d_rec.reserve((size_t)n * pl.sum_real_blocks * sizeof(DcRec)))) return rc;
@@ -435,7 +448,22 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   for (int ci = 0; ci < g.nc; ci++) { rl.comp_off[ci] = rl.per_image; rl.per_image += (long long)g.c[ci].wib * g.c[ci].hib; }
   tm.mark("forward");
   int qfast = 1; for (int ci = 0; ci < g.nc; ci++) qfast &= e->h_qt.as<QuantTables>()->fast[g.c[ci].qt];
-  launch_forward(g, src_dev, e->d_qt.as<QuantTables>(), qfast, p->dct_method, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, e->keep_plain ? 1 : 0, n, s);
+  Geom gf = g;
+  if (pl.smooth && !g.raw_in) {
+    // input smoothing: conversion + context-mode downsampling as a pre-pass; the forward kernel then reads planes
+    tm.mark("smooth_planes");
+    const size_t sb = g.max_coef_bits == 14 ? 2 : 1;
+    PlanesOut po; memset(&po, 0, sizeof po); size_t off = 0;
+    for (int ci = 0; ci < g.nc; ci++) {
+      po.pitch[ci] = (size_t)g.c[ci].wib * 8 * sb; po.stride[ci] = (po.pitch[ci] * g.c[ci].hib * 8 + 255) & ~(size_t)255;
+      po.p[ci] = A.d_planes.as<uint8_t>() + off; off += po.stride[ci] * n;
+      gf.plane[ci] = po.p[ci]; gf.plane_pitch[ci] = po.pitch[ci]; gf.plane_stride[ci] = po.stride[ci];
+    }
+    launch_prep_planes(g, src_dev, pl.smooth, po, n, s);
+    gf.raw_in = 1;
+    tm.mark("forward");
+  }
+  launch_forward(gf, src_dev, e->d_qt.as<QuantTables>(), qfast, p->dct_method, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, e->keep_plain ? 1 : 0, n, s);
   tm.mark("dummy");
   launch_dummy(g, n, s);
 
@@ -479,8 +507,8 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
     if (p->trellis_quant_dc) {
       tm.mark("trellis_dc");
-      if (pl.progressive) launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rl, n, s);
-      else launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rl, n, s);
+      if (pl.progressive) launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rl, p->trellis_delta_dc_weight > 0.0f, n, s);
+      else launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rl, p->trellis_delta_dc_weight > 0.0f, n, s);
     }
     tm.mark("dummy");
     launch_dummy(g, n, s);
@@ -957,7 +985,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
     if (p->data_precision != 8) { set_error("raw-data input is 8-bit only on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
     bool gray = g.nc == 1 && g.hmax == 1 && g.vmax == 1;
     bool ycc = g.nc == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax && g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
-    if (!gray && !ycc) { set_error("raw-data input: only 4:4:4/4:2:2/4:4:0/4:2:0 and single-component layouts are on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
+    if (!gray && !ycc && p->dct_method != B200JPEG_DCT_ISLOW) { set_error("raw-data input with the fast or float DCT: only 4:4:4/4:2:2/4:4:0/4:2:0 and single-component layouts are on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
     g.raw_in = 1;
     for (int ci = 0; ci < g.nc; ci++) {
       const size_t rows = (size_t)g.c[ci].hib * 8, cols = (size_t)g.c[ci].wib * 8;      // what compress_first_pass reads (jccoefct.c:262-353)

@@ -153,6 +153,10 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
 #pragma unroll
     for (int x = 0; x < 8; x++) {
       int xo = bx * 8 + x;
+      if (g.raw_in) {                                     // component planes (raw-data input / the smoothing pre-pass): only centre them
+        ws[8 * y + x] = (int)g.plane[ci][(size_t)img * g.plane_stride[ci] + (size_t)yo * g.plane_pitch[ci] + xo] - 128;
+        continue;
+      }
       int sum = 0;
       for (int dv = 0; dv < c.vx; dv++) {
         int iy = min(iy0 + dv, g.H - 1);                  // bottom row replication inside the row group
@@ -388,9 +392,14 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   {
     const int rg = tid >> 4, seg = tid & 15;
     const int xs = x0 + seg * 8;
-    if (PREC == 8 && g.raw_in) {
+    if (g.raw_in) {
       // raw-data input: the planes are already converted and downsampled; only centre them (convsamp).  Samples past
       // the component's last real block are never used (those blocks are skipped on output), so they read as 0.
+      // Plane pitches and strides are in bytes; 12-bit planes (the smoothing pre-pass makes them) hold uint16 samples.
+      auto sample = [&](int cc, int row, int x) -> int {
+        const uint8_t *q = g.plane[cc] + (size_t)img * g.plane_stride[cc] + (size_t)row * g.plane_pitch[cc] + (size_t)x * SB;
+        return SB == 1 ? (int)*q : (int)*reinterpret_cast<const uint16_t *>(q);
+      };
 #pragma unroll
       for (int rr = 0; rr < VMAX; rr++) {
         const int row = y0 + rg * VMAX + rr;
@@ -399,7 +408,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
 #pragma unroll
         for (int px = 0; px < 8; px++) {
           const int x = xs + px;
-          yv[px] = (row < c0.hib * 8 && x < c0.wib * 8) ? (int16_t)((int)g.plane[0][(size_t)img * g.plane_stride[0] + (size_t)row * g.plane_pitch[0] + x] - 128) : (int16_t)0;
+          yv[px] = (row < c0.hib * 8 && x < c0.wib * 8) ? (int16_t)(sample(0, row, x) - CENTRE) : (int16_t)0;
         }
         *reinterpret_cast<uint4 *>(&sY[(rg * VMAX + rr) * YP + seg * 8]) = *reinterpret_cast<const uint4 *>(yv);
       }
@@ -412,7 +421,7 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
 #pragma unroll
           for (int i = 0; i < 8 / HMAX; i++) {
             const int x = x0 / HMAX + seg * (8 / HMAX) + i;
-            cv[i] = (row < c1.hib * 8 && x < c1.wib * 8) ? (int16_t)((int)g.plane[cc][(size_t)img * g.plane_stride[cc] + (size_t)row * g.plane_pitch[cc] + x] - 128) : (int16_t)0;
+            cv[i] = (row < c1.hib * 8 && x < c1.wib * 8) ? (int16_t)(sample(cc, row, x) - CENTRE) : (int16_t)0;
           }
           int16_t *dst = &sC[(cc - 1) * 8 * CP + rg * CP + seg * (8 / HMAX)];
           if (HMAX == 1) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(cv);
@@ -700,6 +709,69 @@ static void launch_forward_tile(const Geom &g, const uint8_t *src, const QuantTa
   else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
   else k_forward_tile<2, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
 }
+// =====================================================================
+// Input smoothing (cinfo->smoothing_factor, cjpeg -smooth N).  The smoothing downsamplers (jcsample.c:298-455) read a
+// row and a column of context around every sample, and the pre-processing controller then runs in context mode
+// (pre_process_context, jcprepct.c:201-262), which also changes how rows past the image bottom come about: every
+// output row is downsampled from input rows clamped to the last one (not replicated after downsampling).  That case
+// runs as its own pre-pass: colour conversion + the methods jinit_downsampler picks (jcsample.c:463-545) into component
+// planes of hib*8 x wib*8 samples, which the forward kernel then takes like raw-data input.
+//   full-size component : fullsize_smooth_downsample  (member*(65536 - 512 SF) + 8 neighbours * 64 SF)
+//   2h x 2v             : h2v2_smooth_downsample      (4 members * (16384 - 80 SF) + (2 * 8 edge + 4 corner neighbours) * 16 SF)
+//   anything else       : the plain box filters (h2v1 bias 0,1,..; int_downsample rounded mean) - no smoothing there
+// Edge columns: the reference's first/last-column special cases equal clamping the column index to [0, W-1].
+// =====================================================================
+template <int SB>
+__global__ void __launch_bounds__(128) k_prep_planes(Geom g, const uint8_t *__restrict__ src, int sf, PlanesOut out)
+{
+  const int ci = blockIdx.z % g.nc, img = blockIdx.z / g.nc;
+  const CompGeom &c = g.c[ci];
+  const int xo = blockIdx.x * blockDim.x + threadIdx.x, yo = blockIdx.y;
+  if (xo >= c.wib * 8 || yo >= c.hib * 8) return;
+  const uint8_t *base = src + (size_t)img * g.image_stride;
+  const int comp = g.cs_mode == 1 ? 0 : ci;
+  constexpr int CENTRE = SB == 1 ? 128 : 2048;
+  auto at = [&](int y, int x) -> int {
+    y = max(0, min(y, g.H - 1)); x = max(0, min(x, g.W - 1));
+    const uint8_t *px = base + (size_t)y * g.row_pitch + (size_t)x * g.in_comps * SB;
+    auto smp = [&](int k) -> int { return SB == 1 ? (int)px[k] : (int)(reinterpret_cast<const uint16_t *>(px)[k] & 0xFFF); };
+    if (g.cs_mode == 2) return smp(comp);
+    const int r = smp(0), gg = smp(1), b = smp(2);
+    if (comp == 0) return (19595 * r + 38470 * gg + 7471 * b + 32768) >> 16;
+    if (comp == 1) return (-11059 * r - 21709 * gg + 32768 * b + (CENTRE << 16) + 32767) >> 16;
+    return (32768 * r - 27439 * gg - 5329 * b + (CENTRE << 16) + 32767) >> 16;
+  };
+  int val;
+  if (c.hx == 1 && c.vx == 1) {
+    const int member = at(yo, xo);
+    int neigh = -member;
+    for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) neigh += at(yo + dy, xo + dx);
+    val = (member * (65536 - sf * 512) + neigh * (sf * 64) + 32768) >> 16;
+  } else if (c.hx == 2 && c.vx == 2) {
+    const int y = 2 * yo, x = 2 * xo;
+    const int member = at(y, x) + at(y, x + 1) + at(y + 1, x) + at(y + 1, x + 1);
+    int edge = at(y - 1, x) + at(y - 1, x + 1) + at(y + 2, x) + at(y + 2, x + 1) + at(y, x - 1) + at(y, x + 2) + at(y + 1, x - 1) + at(y + 1, x + 2);
+    const int corner = at(y - 1, x - 1) + at(y - 1, x + 2) + at(y + 2, x - 1) + at(y + 2, x + 2);
+    val = (member * (16384 - sf * 80) + (2 * edge + corner) * (sf * 16) + 32768) >> 16;
+  } else {
+    int sum = 0;
+    for (int dv = 0; dv < c.vx; dv++) for (int du = 0; du < c.hx; du++) sum += at(yo * c.vx + dv, xo * c.hx + du);
+    if (c.hx == 2 && c.vx == 1) val = (sum + (xo & 1)) >> 1;
+    else { const int np = c.hx * c.vx; val = (sum + np / 2) / np; }
+  }
+  uint8_t *dst = out.p[ci] + (size_t)img * out.stride[ci] + (size_t)yo * out.pitch[ci] + (size_t)xo * SB;
+  if (SB == 1) *dst = (uint8_t)val; else *reinterpret_cast<uint16_t *>(dst) = (uint16_t)val;
+}
+void launch_prep_planes(const Geom &g, const uint8_t *src, int smoothing_factor, const PlanesOut &out, int n, cudaStream_t s)
+{
+  int mw = 0, mh = 0;
+  for (int ci = 0; ci < g.nc; ci++) { mw = max(mw, g.c[ci].wib * 8); mh = max(mh, g.c[ci].hib * 8); }
+  dim3 grid((mw + 127) / 128, mh, n * g.nc);
+  if (g.max_coef_bits == 14) k_prep_planes<2><<<grid, 128, 0, s>>>(g, src, smoothing_factor, out);
+  else k_prep_planes<1><<<grid, 128, 0, s>>>(g, src, smoothing_factor, out);
+  LAUNCHED();
+}
+
 void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dct_method, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, int n, cudaStream_t s)
 {
   const int write_raw = rec != nullptr || keep_raw;
@@ -1371,6 +1443,11 @@ __global__ void __launch_bounds__(64) k_trellis_dc(Geom g, const TrellisConsts *
       DcRec r = rec[rbase + bi];
       int raw = r.raw_dc, sign = raw >> 31, x = abs(raw);
       int qval = (x + q / 2) / q;
+      // trellis_delta_dc_weight: the block above inside the same iMCU row (lastblockrow, jccoefct.c:420) - its raw DC and
+      // the value this thread's back-track of the previous block row left in the coefficient plane
+      const bool vert = br > 0 && tc->delta_dc_weight > 0.0f;
+      int above_raw = 0, above_fin = 0;
+      if (vert) { above_raw = rec[rbase - c.wib + bi].raw_dc; above_fin = c.coef[(((size_t)img * c.hpad + row - 1) * c.wpad + bi) * 64]; }
       float nacc[9]; int cand[9];
       unsigned long long w = 0;
 #pragma unroll
@@ -1384,6 +1461,11 @@ __global__ void __launch_bounds__(64) k_trellis_dc(Geom g, const TrellisConsts *
           float dist = (float)(delta * delta) * r.lambda_dc;
           cd *= 1 + 2 * sign;
           cand[k] = cd;
+          if (vert) {                                               // difference of vertical gradients (:1069-1086)
+            const int d2 = (above_raw - raw) - (above_fin * q - cd * q);
+            const float vd = (float)(d2 * d2) * r.lambda_dc;
+            dist += tc->delta_dc_weight * (vd - dist);
+          }
           if (bi == 0) {
             int bits = nbits_of(abs(cd - last_dc));
             nacc[k] = (float)(bits + dcsi[bits]) + dist;
@@ -1692,10 +1774,18 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
 }
 
 void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                       const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int n, cudaStream_t s)
+                       const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int vertical, int n, cudaStream_t s)
 {
   int n_imcu = 0, max_wib = 0;
   for (int ci = 0; ci < g.nc; ci++) { n_imcu = max(n_imcu, (g.c[ci].hib + g.c[ci].v - 1) / g.c[ci].v); max_wib = max(max_wib, g.c[ci].wib); }
+  if (vertical) {
+    // trellis_delta_dc_weight > 0 (cjpeg -trellis-dc-ver-weight): the candidates' distortion reads the finished block
+    // row above; only the one-thread-per-chain kernel carries that term (a non-default tuning option)
+    dim3 grid((n_imcu + 63) / 64, n * g.nc);
+    k_trellis_dc<<<grid, 64, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, bt, rl);
+    LAUNCHED();
+    return;
+  }
   // warp-cooperative kernel when the chains' back pointers fit in shared memory
   static const bool use_v1 = getenv("B200JPEG_DC_V1") != nullptr;      // A/B switch
   size_t smem2 = (size_t)DC2_WARPS * 3 * max_wib * 5;

@@ -39,11 +39,14 @@ struct Geom {
   int cs_mode;         // 0: RGB->YCbCr  1: RGB->gray  2: pass-through
   size_t row_pitch, image_stride;
   // raw-data input (jpeg_write_raw_data, jcapistd.c:145-195): downsampled component planes instead of pixels;
-  // plane ci holds at least hib*8 rows of wib*8 samples
+  // plane ci holds at least hib*8 rows of wib*8 samples; pitch and stride in bytes
   int raw_in;
   const uint8_t *plane[4]; size_t plane_pitch[4], plane_stride[4];
   CompGeom c[4];
 };
+
+// component planes written by the input-smoothing pre-pass (pitch, stride in bytes)
+struct PlanesOut { uint8_t *p[4]; size_t pitch[4], stride[4]; };
 
 struct ScanDesc {
   int ncomps, ci[4];
@@ -72,6 +75,7 @@ struct TrellisConsts {
   unsigned qmul_zz[4][64]; int qL[4];          // exact a / q8 for a < 2^18: umulhi(a << 14, qmul_zz) >> qL (one shift per table)
   double p1, p2;          // pow(2, lambda_log_scale1), pow(2, lambda_log_scale2)
   float lambda_const;     // used when lambda_log_scale2 <= 0
+  float delta_dc_weight;  // trellis_delta_dc_weight (jcdctmgr.c:1069-1086)
   int   use_norm;         // lambda_log_scale2 > 0
   int   max_coef_bits;    // data_precision + 2
   int   dc_trellis;       // trellis_quant_dc
@@ -106,6 +110,7 @@ struct SlotMasks { uint32_t m[4]; int period; };
 // ---------------------------------------------------------------- launches (defined in kernels.cu)
 // status[img] bits: 2 = JERR_BAD_DCT_COEF / missing Huffman code, 4 = output buffer too small (host retries)
 // the raw DCT plane is written only when the trellis (rec != nullptr) or the debug tap (keep_raw) will read it
+void launch_prep_planes(const Geom &g, const uint8_t *src, int smoothing_factor, const PlanesOut &out, int n, cudaStream_t s);
 void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dct_method /* J_DCT_METHOD */, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, int n, cudaStream_t s);
 void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, uint32_t *splits /* [n*nc][2] */, int n, cudaStream_t s);
 void launch_dummy(const Geom &g, int n, cudaStream_t s);
@@ -116,7 +121,7 @@ void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_set_stri
 void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                        DcRec *rec, const RecLayout &rl, const uint32_t *perm, const uint32_t *splits, int n, cudaStream_t s);
 void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                       const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int n, cudaStream_t s);
+                       const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int vertical, int n, cudaStream_t s);
 // tile_last / tile_first: int [n][ceil(nblocks/256)] scratch
 void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int *tile_last, int *tile_first, int n, cudaStream_t s);
 void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);

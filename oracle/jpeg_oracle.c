@@ -403,11 +403,13 @@ int orc_make_derived(const b200jpeg_huff_tbl *t, int is_dc, unsigned *ehufco, un
 
 /* ------------------------------------------------------------------ */
 /* quantize_trellis  (jcdctmgr.c:936-1330), default option set:         */
-/* trellis_eob_opt=0, trellis_q_opt=0, delta_dc_weight=0, mode==1.       */
+/* trellis_eob_opt=0, trellis_q_opt=0, mode==1; coef_above / src_above  */
+/* = the block row above inside the same iMCU row (or NULL), read only  */
+/* when trellis_delta_dc_weight > 0 (:1069-1086).                        */
 /* ------------------------------------------------------------------ */
 void orc_trellis_row(const b200jpeg_params *p, const unsigned char *dcsi, const unsigned char *acsi,
                      int16_t *coef_blocks, const int16_t *src, int num_blocks,
-                     const uint16_t *qtbl, int16_t *last_dc_val)
+                     const uint16_t *qtbl, int16_t *last_dc_val, const int16_t *coef_above, const int16_t *src_above)
 {
   float azd[64], acc[64], lambda_table[64];
   int run_start[64];
@@ -452,6 +454,13 @@ void orc_trellis_row(const b200jpeg_params *p, const unsigned char *dcsi, const 
         dist = delta * delta * lambda_dc;
         cand *= 1 + 2 * sign;
         cand_dc[k][bi] = (int16_t)cand;
+        if (coef_above && src_above && p->trellis_delta_dc_weight > 0.0) {       /* difference of vertical gradients :1069-1086 */
+          int dc_above_orig = src_above[64 * bi], dc_above_recon = coef_above[64 * bi] * q, dc_orig = s[0], dc_recon = cand * q;
+          float vertical_dist;
+          delta = (dc_above_orig - dc_orig) - (dc_above_recon - dc_recon);
+          vertical_dist = delta * delta * lambda_dc;
+          dist += p->trellis_delta_dc_weight * (vertical_dist - dist);
+        }
         if (bi == 0) {
           dc_delta = abs(cand - *last_dc_val);
           bits = nbits_of(dc_delta);
@@ -979,6 +988,34 @@ planes_ready:
     int numpix = hx * vx, bx, by, i;
     if (rawp) {                                       /* compress_first_pass reads hib*8 rows of wib*8 samples straight from the caller's planes */
       for (y = 0; y < oh; y++) for (x = 0; x < ow; x++) plane[(size_t)y * ow + x] = rawp[ci][(size_t)y * rawpitch[ci] + x];
+    } else if (p->smoothing_factor) {
+      /* Input smoothing (jcsample.c:298-455).  Some component always takes a smoothing method (the full-size one), so
+       * the downsampler asks for context rows (jcsample.c:482,517) and the pre-processing controller runs
+       * pre_process_context (jcprepct.c:201-262): the first row is replicated upwards (:226-234), rows past the bottom
+       * are replicas of the last INPUT row (:246-252) and every output row - padding included - is downsampled from
+       * them.  expand_right_edge + the first/last-column special cases equal clamping the column to [0, W-1]. */
+      const long SF = p->smoothing_factor;
+#define AT(yy_, xx_) ((long)full[ci][(size_t)((yy_) < 0 ? 0 : (yy_) > H - 1 ? H - 1 : (yy_)) * W + ((xx_) < 0 ? 0 : (xx_) > W - 1 ? W - 1 : (xx_))])
+      for (y = 0; y < oh; y++) for (x = 0; x < ow; x++) {
+        long val;
+        if (hx == 1 && vx == 1) {                                            /* fullsize_smooth_downsample :405-455 */
+          long member = AT(y, x), neigh = -member; int dy, dx;
+          for (dy = -1; dy <= 1; dy++) for (dx = -1; dx <= 1; dx++) neigh += AT(y + dy, x + dx);
+          val = (member * (65536L - SF * 512L) + neigh * (SF * 64) + 32768) >> 16;
+        } else if (hx == 2 && vx == 2) {                                     /* h2v2_smooth_downsample :306-397 */
+          int Y = 2 * y, X = 2 * x;
+          long member = AT(Y, X) + AT(Y, X + 1) + AT(Y + 1, X) + AT(Y + 1, X + 1);
+          long edge = AT(Y - 1, X) + AT(Y - 1, X + 1) + AT(Y + 2, X) + AT(Y + 2, X + 1) + AT(Y, X - 1) + AT(Y, X + 2) + AT(Y + 1, X - 1) + AT(Y + 1, X + 2);
+          long corner = AT(Y - 1, X - 1) + AT(Y - 1, X + 2) + AT(Y + 2, X - 1) + AT(Y + 2, X + 2);
+          val = (member * (16384 - SF * 80) + (2 * edge + corner) * (SF * 16) + 32768) >> 16;
+        } else {                                                             /* no smoothing variant: h2v1 / int_downsample */
+          long sum = 0; int u, v;
+          for (v = 0; v < vx; v++) for (u = 0; u < hx; u++) sum += AT(y * vx + v, x * hx + u);
+          if (hx == 2 && vx == 1) val = (sum + (x & 1)) >> 1; else val = (sum + numpix / 2) / numpix;
+        }
+        plane[(size_t)y * ow + x] = (uint16_t)val;
+      }
+#undef AT
     } else
     for (y = 0; y < oh; y++) {
       int yy = y < rows_avail ? y : rows_avail - 1;          /* expand_bottom_edge on the downsampled rows */
@@ -1031,7 +1068,9 @@ static void trellis_component(enc_t *e, int ci)
     int16_t lastDC = 0;
     for (br = 0; br < v && imcu * v + br < e->hib[ci]; br++) {
       size_t off = (size_t)(imcu * v + br) * e->wpad[ci] * 64;
-      orc_trellis_row(p, dcsi, acsi, e->coef[ci] + off, e->raw[ci] + off, e->wib[ci], p->quant_tbl[c->quant_tbl_no], &lastDC);
+      size_t up = off - (size_t)e->wpad[ci] * 64;                 /* lastblockrow = buffer[block_row-1] only inside the iMCU row (jccoefct.c:420) */
+      orc_trellis_row(p, dcsi, acsi, e->coef[ci] + off, e->raw[ci] + off, e->wib[ci], p->quant_tbl[c->quant_tbl_no], &lastDC,
+                      br > 0 ? e->coef[ci] + up : NULL, br > 0 ? e->raw[ci] + up : NULL);
     }
   }
   fill_dummy_blocks(e, ci);
@@ -1066,9 +1105,8 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
   e->raw_planes = g_raw_planes; e->raw_pitch = g_raw_pitch;
   /* 12-bit: no JBUF_REQUANT => no trellis (jccoefct.c:132-138); deringing is not usable at 12 bits (jcdctmgr.c:419) */
   if (p->data_precision == 12 && (p->trellis_quant || p->overshoot_deringing)) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
-  if ((p->data_precision != 8 && p->data_precision != 12) || (p->dct_method != B200JPEG_DCT_ISLOW && p->data_precision != 8) || p->smoothing_factor ||
-      p->trellis_eob_opt || p->use_scans_in_trellis || p->trellis_q_opt || p->trellis_num_loops != 1 ||
-      p->trellis_delta_dc_weight != 0.0f) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
+  if ((p->data_precision != 8 && p->data_precision != 12) || (p->dct_method != B200JPEG_DCT_ISLOW && p->data_precision != 8) ||
+      p->trellis_eob_opt || p->use_scans_in_trellis || p->trellis_q_opt || p->trellis_num_loops != 1) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   e->hmax = e->vmax = 1;
   for (ci = 0; ci < e->nc; ci++) { if (p->comp_info[ci].h_samp_factor > e->hmax) e->hmax = p->comp_info[ci].h_samp_factor; if (p->comp_info[ci].v_samp_factor > e->vmax) e->vmax = p->comp_info[ci].v_samp_factor; }
   e->mcus_per_row = (e->W + e->hmax * 8 - 1) / (e->hmax * 8); e->mcu_rows = (e->H + e->vmax * 8 - 1) / (e->vmax * 8);

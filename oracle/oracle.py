@@ -189,7 +189,10 @@ def ref_encode(pixels: np.ndarray, switches: Sequence[str]) -> bytes:
     """Encode with the UNMODIFIED reference (libjpeg API, cjpeg switch semantics)."""
     lib = ref()
     gray = pixels.ndim == 2 or pixels.shape[2] == 1
-    cfg = refcfg_from_switches(switches, gray)
+    try:
+        cfg = refcfg_from_switches(switches, gray)
+    except ValueError:
+        return _ref_cjpeg_pixels(pixels, switches)      # a switch only the reference's own cjpeg parses (8-bit input)
     pix = np.ascontiguousarray(pixels, dtype=np.uint16 if cfg.precision == 12 else np.uint8)
     out = C.POINTER(C.c_uint8)(); n = C.c_ulong(0)
     err = C.create_string_buffer(256)
@@ -258,6 +261,16 @@ def ref_read_coefs(jpeg: bytes) -> Dict[str, object]:
     if rc != 0:
         raise RuntimeError("reference decode failed")
     return {"coefs": arrs, "qt": np.array(qt, dtype=np.uint16).reshape(4, 64)[:nc.value]}
+
+
+def _ref_cjpeg_pixels(pixels: np.ndarray, switches: Sequence[str]) -> bytes:
+    """The reference's cjpeg binary on an in-memory 8-bit image (written out as a PGM/PPM first)."""
+    import tempfile
+    pix = np.ascontiguousarray(pixels, dtype=np.uint8)
+    gray = pix.ndim == 2 or pix.shape[2] == 1
+    with tempfile.NamedTemporaryFile(suffix=".pgm" if gray else ".ppm") as f:
+        f.write(b"%s\n%d %d\n255\n" % (b"P5" if gray else b"P6", pix.shape[1], pix.shape[0])); f.write(pix.tobytes()); f.flush()
+        return ref_cjpeg(f.name, switches)
 
 
 def ref_cjpeg(ppm_path: str, switches: Sequence[str]) -> bytes:

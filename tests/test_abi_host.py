@@ -95,6 +95,10 @@ def test_validation_errors(built):
     q = p.copy(); q.dct_method = A.DCT_IFAST
     assert lib.b200jpeg_validate(C.byref(q)) == 0
     q = p.copy(); q.smoothing_factor = 10
+    assert lib.b200jpeg_validate(C.byref(q)) == 0                      # input smoothing is on the device path
+    q = p.copy(); q.smoothing_factor = 101
+    assert lib.b200jpeg_validate(C.byref(q)) == A.ERR_PARAM
+    q = p.copy(); q.trellis_q_opt = 1
     assert lib.b200jpeg_validate(C.byref(q)) == A.ERR_UNSUPPORTED
     q = p.copy(); q.num_scans = 1; q.scan_info[0].comps_in_scan = 1; q.scan_info[0].Ss = 0; q.scan_info[0].Se = 63
     assert lib.b200jpeg_validate(C.byref(q)) == A.ERR_PARAM and b"transmit" in lib.b200jpeg_last_error()   # JERR_MISSING_DATA

@@ -93,6 +93,39 @@ def test_ragged_shapes_vs_oracle(encoder):
             assert encoder.encode_batch(p, img[None])[0] == O.oracle_encode(p, img).jpeg, (w, h, sw)
 
 
+def test_input_smoothing_vs_oracle(encoder):
+    """cjpeg -smooth N (jcsample.c:298-455 + the context-row mode of jcprepct.c): ragged sizes, every sampler family,
+    the three DCTs and 12-bit samples; the 8-bit cases of the oracle are pinned to the reference in golden.json."""
+    import mozjpeg_b200 as mj
+    from mozjpeg_b200.synth import synth_image12
+    from oracle import oracle as O
+    rng = np.random.default_rng(9)
+    sws = [["-baseline", "-quality", "75", "-smooth", "30"], ["-revert", "-smooth", "100", "-sample", "1x1"], ["-quality", "70", "-smooth", "12"],
+           ["-baseline", "-quality", "80", "-smooth", "50", "-sample", "2x1"], ["-revert", "-smooth", "20", "-sample", "3x2"],
+           ["-baseline", "-grayscale", "-smooth", "15", "-quality", "60"], ["-dct", "fast", "-baseline", "-quality", "75", "-smooth", "40"],
+           ["-dct", "float", "-fastcrush", "-quality", "75", "-smooth", "8", "-sample", "1x2"], ["-fastcrush", "-smooth", "5", "-sample", "2x2,1x1,2x2"]]
+    for (w, h) in [(1, 1), (1, 40), (40, 1), (7, 9), (17, 15), (31, 33), (65, 63), (200, 136), (517, 260)]:
+        img = O.synth_image(int(rng.integers(1 << 30)), w, h)
+        for sw in sws:
+            p = mj.params_from_switches(sw, w, h)
+            assert encoder.encode_batch(p, img[None])[0] == O.oracle_encode(p, img).jpeg, (w, h, sw)
+    for (w, h) in [(33, 17), (200, 136)]:
+        img = synth_image12(int(rng.integers(1 << 30)), w, h)
+        for sw in (["-precision", "12", "-quality", "75", "-notrellis", "-noovershoot", "-baseline", "-smooth", "25"],
+                   ["-precision", "12", "-quality", "85", "-notrellis", "-noovershoot", "-fastcrush", "-smooth", "60", "-sample", "1x1"]):
+            p = mj.params_from_switches(sw, w, h)
+            assert encoder.encode_batch(p, img[None])[0] == O.oracle_encode(p, img).jpeg, (w, h, sw)
+    # a batch through the chunked pipeline
+    imgs = np.stack([O.synth_image(100 + i, 200, 136) for i in range(5)])
+    p = mj.params_from_switches(sws[0], 200, 136)
+    encoder.set_chunk_images(2)
+    try:
+        got = encoder.encode_batch(p, imgs)
+    finally:
+        encoder.set_chunk_images(0)
+    assert got == [O.oracle_encode(p, im).jpeg for im in imgs]
+
+
 def test_extreme_content(encoder):
     """All-white (deringing 'completely flat' exit), all-black, random noise at q100, saturated checkerboard."""
     import mozjpeg_b200 as mj

@@ -36,7 +36,8 @@ def _golden(switches):
 
 DEVICE_SETS = [["-baseline", "-quality", "75"], ["-quality", "75", "-fastcrush"], ["-revert", "-dct", "int"],
                ["-baseline", "-notrellis", "-quality", "75"], ["-revert", "-optimize", "-grayscale"],
-               ["-quality", "75"]]                      # the library default: 64-candidate scan search
+               ["-quality", "75"],                      # the library default: 64-candidate scan search
+               ["-baseline", "-quality", "75", "-smooth", "30"]]
 
 
 @need_files
@@ -57,12 +58,12 @@ def test_reference_cjpeg_runs_on_the_device(sw, tmp_path):
 @need_files
 @pytest.mark.gpu
 def test_unsupported_parameters_fall_through_to_the_reference(tmp_path):
-    """Input smoothing is not on the device path: the shim must hand the image to the reference's own
-    implementation, and say so."""
-    r, data = _run(["-quality", "75", "-smooth", "10"], {}, tmp_path)
+    """Arithmetic coding is not on the device path: the shim must hand the image to the
+    reference's own implementation, and say so."""
+    r, data = _run(["-quality", "75", "-arithmetic"], {}, tmp_path)
     assert r.returncode == 0, r.stderr
     assert "reference path" in r.stderr
-    plain = subprocess.run([CJPEG, "-quality", "75", "-smooth", "10", PPM], capture_output=True, timeout=300)
+    plain = subprocess.run([CJPEG, "-quality", "75", "-arithmetic", PPM], capture_output=True, timeout=300)
     assert data == plain.stdout
 
 

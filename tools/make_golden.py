@@ -75,6 +75,27 @@ SWITCH_SETS = [
     ["-dct", "fast", "-baseline", "-quality", "100", "-grayscale"],
     ["-dct", "fast", "-quality", "75"],
 ]
+# input smoothing (jcsample.c:298-455, context-row mode of jcprepct.c) and sampling layouts that go through
+# int_downsample (jcsample.c:151-190); the refshim driver hands these to the reference's cjpeg binary
+SWITCH_SETS_EXTRA = [
+    ["-revert", "-smooth", "10"],
+    ["-baseline", "-quality", "75", "-smooth", "30"],
+    ["-quality", "75", "-smooth", "100", "-sample", "1x1"],
+    ["-baseline", "-quality", "80", "-smooth", "50", "-sample", "2x1"],
+    ["-revert", "-smooth", "20", "-sample", "3x2"],
+    ["-baseline", "-grayscale", "-smooth", "15", "-quality", "60"],
+    ["-fastcrush", "-smooth", "5", "-sample", "2x2,1x1,2x2"],
+    ["-dct", "float", "-baseline", "-quality", "75", "-smooth", "40"],
+    # vertical-gradient weight in the DC trellis (jcdctmgr.c:1069-1086): acts on components with v_samp_factor > 1
+    ["-baseline", "-quality", "75", "-trellis-dc-ver-weight", "1.0"],
+    ["-quality", "85", "-trellis-dc-ver-weight", "0.5", "-sample", "2x2"],
+    ["-fastcrush", "-quality", "60", "-trellis-dc-ver-weight", "2.5", "-sample", "1x2"],
+    ["-revert", "-sample", "3x2"],
+    ["-baseline", "-quality", "75", "-sample", "4x2"],
+    ["-quality", "75", "-sample", "3x1"],
+    ["-baseline", "-quality", "80", "-sample", "2x2,1x1,2x2"],
+    ["-baseline", "-sample", "4x1,1x1,2x1", "-quality", "60"],
+]
 # through the reference's cjpeg binary only (our refshim driver does not parse these switches)
 CJPEG_ONLY = [
     ["-revert", "-dct", "float"],
@@ -98,14 +119,24 @@ SYNTH12 = [(21, 16, 16), (22, 33, 17), (23, 200, 136), (24, 640, 480), (25, 1, 1
 SYNTH = [(11, 16, 16), (12, 33, 17), (13, 200, 136), (14, 640, 480), (15, 1, 1), (16, 8, 8), (17, 1920, 1080)]
 
 
+def _key(image, sw):
+    return json.dumps([image, sw])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    # cases already recorded are kept as they are unless --force is given (a full regeneration takes a while)
+    have = {}
+    if "--force" not in sys.argv and os.path.exists(os.path.join(GOLD, "golden.json")):
+        for c in json.load(open(os.path.join(GOLD, "golden.json")))["cases"]:
+            have[_key(c["image"], c["switches"])] = c
     shutil.copyfile(os.path.join(REF, "testimages", "testorig.ppm"), os.path.join(GOLD, "testorig.ppm"))
     cases = []
     ppm = os.path.join(GOLD, "testorig.ppm")
     w, h, nc, data = cjpeg.read_ppm(open(ppm, "rb").read())
     img = np.frombuffer(data, dtype=np.uint8).reshape(h, w, nc)
     for sw in SWITCH_SETS:
+        if _key("testorig", sw) in have: cases.append(have[_key("testorig", sw)]); continue
         a = O.ref_cjpeg(ppm, sw)                   # the reference's own cjpeg binary
         b = O.ref_encode(img, sw)                  # our driver around the reference library
         assert a == b, ("refshim disagrees with cjpeg", sw)
@@ -113,16 +144,21 @@ def main():
     for sw in CJPEG_ONLY:
         a = O.ref_cjpeg(ppm, sw)
         cases.append({"image": "testorig", "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
+    for sw in SWITCH_SETS_EXTRA:
+        a = O.ref_cjpeg(ppm, sw)
+        cases.append({"image": "testorig", "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
     for (seed, sw_, sh_) in SYNTH:
         im = O.synth_image(seed, sw_, sh_)
-        sets = SWITCH_SETS if sw_ * sh_ <= 640 * 480 else [s for s in SWITCH_SETS if s in (["-revert", "-dct", "int"], ["-baseline", "-quality", "75", "-sample", "2x2"], ["-fastcrush", "-quality", "75", "-sample", "2x2"], ["-baseline", "-quality", "90", "-sample", "2x2"], ["-quality", "75"])]
+        sets = SWITCH_SETS + SWITCH_SETS_EXTRA if sw_ * sh_ <= 640 * 480 else [s for s in SWITCH_SETS if s in (["-revert", "-dct", "int"], ["-baseline", "-quality", "75", "-sample", "2x2"], ["-fastcrush", "-quality", "75", "-sample", "2x2"], ["-baseline", "-quality", "90", "-sample", "2x2"], ["-quality", "75"])]
         for sw in sets:
+            if _key([seed, sw_, sh_], sw) in have: cases.append(have[_key([seed, sw_, sh_], sw)]); continue
             a = O.ref_encode(im, sw)
             cases.append({"image": [seed, sw_, sh_], "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
     from mozjpeg_b200.synth import synth_image12
     for (seed, sw_, sh_) in SYNTH12:
         im = synth_image12(seed, sw_, sh_)
         for sw in SWITCH_SETS_12:
+            if _key([seed, sw_, sh_, 12], sw) in have: cases.append(have[_key([seed, sw_, sh_, 12], sw)]); continue
             a = O.ref_encode(im, sw)
             cases.append({"image": [seed, sw_, sh_, 12], "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
     # raw-data input (jpeg_write_raw_data): separate fixture, the inputs are component planes
@@ -131,7 +167,8 @@ def main():
     for (seed, w_, h_) in [(31, 33, 17), (32, 200, 136), (33, 227, 149), (34, 640, 480)]:
         for sw in (["-baseline", "-quality", "75"], ["-quality", "75"], ["-baseline", "-quality", "85", "-sample", "1x1"],
                    ["-fastcrush", "-quality", "60", "-sample", "2x1"], ["-baseline", "-quality", "75", "-grayscale"],
-                   ["-baseline", "-notrellis", "-quality", "90", "-sample", "1x2", "-dct", "float"]):
+                   ["-baseline", "-notrellis", "-quality", "90", "-sample", "1x2", "-dct", "float"],
+                   ["-baseline", "-quality", "75", "-sample", "4x2"], ["-fastcrush", "-quality", "70", "-sample", "2x2,1x1,2x2"]):
             pp = cjpeg.params_from_switches(sw, w_, h_, 1 if "-grayscale" in sw else 3)
             a = O.ref_encode_raw(synth_planes(pp, seed), w_, h_, sw)
             raw_cases.append({"seed": seed, "width": w_, "height": h_, "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
