@@ -220,6 +220,20 @@ int  b200jpeg_encode_batch_raw(b200jpeg_encoder *enc, const b200jpeg_params *p,
                                const uint8_t *const *planes, int planes_on_device,
                                const size_t *row_pitch, const size_t *image_stride, int n_images);
 
+/*
+ * Coefficient-domain variant: replaces jpeg_write_coefficients + jpeg_finish_compress (jctrans.c:39-66, the encode
+ * half of jpegtran): the caller supplies already QUANTIZED DCT coefficients and the path runs only its entropy-coding
+ * stages (optimal tables, sequential / progressive scans, scan search, restarts).  planes[ci] points at image 0's
+ * blocks of component ci in the libjpeg JBLOCK layout (64 int16 per block, natural order), height_in_blocks rows of
+ * width_in_blocks blocks; row_pitch_blocks[ci] / image_stride_blocks[ci] in blocks.  Dummy blocks are generated like
+ * compress_output does (jctrans.c:352-362).  The parameter block is what jpeg_copy_critical_parameters (jctrans.c:
+ * 76-166) plus the caller's changes would hold: trellis_quant must be 0; in_color_space / input_components,
+ * dct_method, smoothing and deringing have no meaning here.
+ */
+int  b200jpeg_encode_batch_coefs(b200jpeg_encoder *enc, const b200jpeg_params *p,
+                                 const int16_t *const *planes, int planes_on_device,
+                                 const size_t *row_pitch_blocks, const size_t *image_stride_blocks, int n_images);
+
 /* Same, but stops after the entropy-coded bytes are in HBM: no device->host
  * copy, no host-side file assembly.  Used to time the device pipeline alone. */
 int  b200jpeg_encode_batch_device_only(b200jpeg_encoder *enc, const b200jpeg_params *p,

@@ -80,6 +80,17 @@ class Encoder:
         A.check(_lib.b200jpeg_encode_batch_raw(self._h, C.byref(p), ptrs, 0, pitch, stride, n), "encode_batch_raw")
         return [self.get_output(i) for i in range(n)]
 
+    def encode_batch_coefs(self, p: Params, planes: Sequence[np.ndarray]) -> List[bytes]:
+        """Coefficient-domain input (jpeg_write_coefficients): planes[ci] is an (N, hib, wib, 64) int16 array of
+        quantized coefficients in natural order (libjpeg JBLOCKs)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.int16) for a in planes]
+        n = arrs[0].shape[0]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        pitch = (C.c_size_t * len(arrs))(*[a.strides[1] // 128 for a in arrs])
+        stride = (C.c_size_t * len(arrs))(*[a.strides[0] // 128 for a in arrs])
+        A.check(_lib.b200jpeg_encode_batch_coefs(self._h, C.byref(p), ptrs, 0, pitch, stride, n), "encode_batch_coefs")
+        return [self.get_output(i) for i in range(n)]
+
     def encode_batch_ptr(self, p: Params, ptr: int, on_device: bool, row_pitch: int, image_stride: int, n: int,
                          device_only: bool = False) -> None:
         """Raw-pointer form (device tensors, pinned host buffers)."""

@@ -449,6 +449,9 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   tm.mark("forward");
   int qfast = 1; for (int ci = 0; ci < g.nc; ci++) qfast &= e->h_qt.as<QuantTables>()->fast[g.c[ci].qt];
   Geom gf = g;
+  if (g.raw_in == 2) {
+    launch_import_coefs(g, n, s);
+  } else {
   if (pl.smooth && !g.raw_in) {
     // input smoothing: conversion + context-mode downsampling as a pre-pass; the forward kernel then reads planes
     tm.mark("smooth_planes");
@@ -464,6 +467,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     tm.mark("forward");
   }
   launch_forward(gf, src_dev, e->d_qt.as<QuantTables>(), qfast, p->dct_method, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, e->keep_plain ? 1 : 0, n, s);
+  }
   tm.mark("dummy");
   launch_dummy(g, n, s);
 
@@ -961,7 +965,7 @@ static int choose_chunk(const b200jpeg_encoder *e, const Plan &pl, int n_images,
 }
 
 // raw-data input (jpeg_write_raw_data): one plane per component instead of interleaved pixels
-struct RawDesc { const uint8_t *plane[4]; size_t pitch[4], stride[4]; };
+struct RawDesc { const uint8_t *plane[4]; size_t pitch[4], stride[4]; bool coefs; };   // pitch, stride in bytes; coefs: planes hold JBLOCK rows
 
 static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const void *pixels, int on_device,
                          size_t row_pitch, size_t image_stride, int n_images, bool device_only, const RawDesc *raw = nullptr)
@@ -980,7 +984,20 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   if ((rc = build_plan(p, row_pitch, image_stride, e->plan))) return rc;
   Plan &pl = e->plan;
   size_t raw_plane_bytes[4] = {0, 0, 0, 0}, raw_total[4] = {0, 0, 0, 0}, raw_off[4] = {0, 0, 0, 0}, raw_sum = 0;
-  if (raw) {
+  if (raw && raw->coefs) {
+    // jpeg_write_coefficients: no forward stage, no trellis (jpeg_copy_critical_parameters turns it off, jctrans.c:103)
+    Geom &g = pl.g;
+    if (p->trellis_quant) { set_error("coefficient input: trellis quantization needs the unquantized coefficients (trellis_quant must be 0, as jpeg_copy_critical_parameters sets it)"); return B200JPEG_ERR_PARAM; }
+    g.raw_in = 2;
+    for (int ci = 0; ci < g.nc; ci++) {
+      const size_t rows = (size_t)g.c[ci].hib, cols = (size_t)g.c[ci].wib * 128;
+      if (!raw->plane[ci] || raw->pitch[ci] < cols || (n_images > 1 && raw->stride[ci] < raw->pitch[ci] * (rows - 1) + cols)) { set_error("coefficient plane %d: bad pointer, pitch or stride (needs %zu rows of %zu blocks)", ci, rows, cols / 128); return B200JPEG_ERR_PARAM; }
+      raw_plane_bytes[ci] = raw->pitch[ci] * (rows - 1) + cols;
+      raw_total[ci] = raw->stride[ci] * (size_t)(n_images - 1) + raw_plane_bytes[ci];
+      raw_off[ci] = raw_sum; raw_sum += (raw_total[ci] + 255) & ~(size_t)255;
+      g.plane_pitch[ci] = raw->pitch[ci]; g.plane_stride[ci] = raw->stride[ci];
+    }
+  } else if (raw) {
     Geom &g = pl.g;
     if (p->data_precision != 8) { set_error("raw-data input is 8-bit only on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
     bool gray = g.nc == 1 && g.hmax == 1 && g.vmax == 1;
@@ -1212,6 +1229,17 @@ int b200jpeg_encode_batch_raw(b200jpeg_encoder *enc, const b200jpeg_params *p, c
   if (!enc || !p || !planes || !row_pitch || !image_stride) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
   RawDesc rd; memset(&rd, 0, sizeof rd);
   for (int ci = 0; ci < p->num_components && ci < 4; ci++) { rd.plane[ci] = planes[ci]; rd.pitch[ci] = row_pitch[ci]; rd.stride[ci] = image_stride[ci]; }
+  return encode_common(enc, p, nullptr, planes_on_device, 0, 0, n_images, false, &rd);
+}
+
+int b200jpeg_encode_batch_coefs(b200jpeg_encoder *enc, const b200jpeg_params *p, const int16_t *const *planes, int planes_on_device,
+                                const size_t *row_pitch_blocks, const size_t *image_stride_blocks, int n_images)
+{
+  if (!enc || !p || !planes || !row_pitch_blocks || !image_stride_blocks) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  RawDesc rd; memset(&rd, 0, sizeof rd); rd.coefs = true;
+  for (int ci = 0; ci < p->num_components && ci < 4; ci++) {
+    rd.plane[ci] = reinterpret_cast<const uint8_t *>(planes[ci]); rd.pitch[ci] = row_pitch_blocks[ci] * 128; rd.stride[ci] = image_stride_blocks[ci] * 128;
+  }
   return encode_common(enc, p, nullptr, planes_on_device, 0, 0, n_images, false, &rd);
 }
 

@@ -800,6 +800,33 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
 }
 
 // =====================================================================
+// Coefficient-domain input (jpeg_write_coefficients, jctrans.c:39-66 / compress_output :303-378): the caller's
+// blocks are libjpeg JBLOCKs (natural order, width_in_blocks x height_in_blocks per component); they go into the
+// padded zigzag-order planes every later stage reads.  Dummy blocks are made by k_dummy as on the pixel path: the
+// transcoder's rule (DC of the previous block of the MCU, jctrans.c:352-362) gives the same values.
+// =====================================================================
+__global__ void __launch_bounds__(256) k_import_coefs(Geom g)
+{
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
+  const CompGeom &c = g.c[ci];
+  const long long nblk = (long long)c.wib * c.hib;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (block, zigzag position)
+  if (t >= nblk * 64) return;
+  const long long b = t >> 6; const int k = (int)(t & 63);
+  const int row = (int)(b / c.wib), col = (int)(b - (long long)row * c.wib);
+  const int16_t *src = reinterpret_cast<const int16_t *>(g.plane[ci] + (size_t)img * g.plane_stride[ci] + (size_t)row * g.plane_pitch[ci]) + (size_t)col * 64;
+  c.coef[(((size_t)img * c.hpad + row) * c.wpad + col) * 64 + k] = src[c_zz[k]];
+}
+void launch_import_coefs(const Geom &g, int n, cudaStream_t s)
+{
+  long long mb = 0;
+  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
+  dim3 grid((unsigned)((mb * 64 + 255) / 256), n * g.nc);
+  k_import_coefs<<<grid, 256, 0, s>>>(g);
+  LAUNCHED();
+}
+
+// =====================================================================
 // dummy blocks (jccoefct.c:312-345 == :443-476): AC = 0; right-edge dummies
 // take the DC of the last real block of the row, bottom dummy rows take, per
 // MCU, the DC of the last block of that MCU in the row above.

@@ -40,7 +40,7 @@ struct Geom {
   size_t row_pitch, image_stride;
   // raw-data input (jpeg_write_raw_data, jcapistd.c:145-195): downsampled component planes instead of pixels;
   // plane ci holds at least hib*8 rows of wib*8 samples; pitch and stride in bytes
-  int raw_in;
+  int raw_in;          // 1: sample planes; 2: quantized coefficient blocks (jpeg_write_coefficients), natural order
   const uint8_t *plane[4]; size_t plane_pitch[4], plane_stride[4];
   CompGeom c[4];
 };
@@ -111,6 +111,7 @@ struct SlotMasks { uint32_t m[4]; int period; };
 // status[img] bits: 2 = JERR_BAD_DCT_COEF / missing Huffman code, 4 = output buffer too small (host retries)
 // the raw DCT plane is written only when the trellis (rec != nullptr) or the debug tap (keep_raw) will read it
 void launch_prep_planes(const Geom &g, const uint8_t *src, int smoothing_factor, const PlanesOut &out, int n, cudaStream_t s);
+void launch_import_coefs(const Geom &g, int n, cudaStream_t s);     // raw_in == 2: planes hold JBLOCK rows
 void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dct_method /* J_DCT_METHOD */, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, int n, cudaStream_t s);
 void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, uint32_t *splits /* [n*nc][2] */, int n, cudaStream_t s);
 void launch_dummy(const Geom &g, int n, cudaStream_t s);

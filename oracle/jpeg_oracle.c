@@ -1081,8 +1081,21 @@ void orc_free(void *p) { free(p); }
 void orc_debug_free(orc_debug *d) { int i; for (i = 0; i < 4; i++) { free(d->plain[i]); free(d->raw[i]); free(d->final_[i]); } memset(d, 0, sizeof *d); }
 
 static const uint8_t *const *g_raw_planes; static const size_t *g_raw_pitch;   /* set by orc_encode_raw around its call of orc_encode (test infrastructure: single-threaded) */
+static const int16_t *const *g_coef_planes; static const size_t *g_coef_pitch;  /* likewise, set by orc_encode_coefs */
 int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch,
                uint8_t **out, size_t *outsize, orc_debug *dbg);
+/* jpeg_write_coefficients (jctrans.c:39-66): quantized coefficients in, entropy coding only.  planes[ci] = hib rows of
+ * wib JBLOCKs (natural order), pitch_blocks[ci] blocks per row.  Dummy blocks as compress_output makes them
+ * (jctrans.c:352-362: AC 0, DC of the previous block of the MCU) - the same values fill_dummy_blocks produces. */
+int orc_encode_coefs(const b200jpeg_params *p, const int16_t *const *planes, const size_t *pitch_blocks, uint8_t **out, size_t *outsize)
+{
+  int rc;
+  if (p->trellis_quant) return B200JPEG_ERR_PARAM;        /* jpeg_copy_critical_parameters turns it off (jctrans.c:103) */
+  g_coef_planes = planes; g_coef_pitch = pitch_blocks;
+  rc = orc_encode(p, (const uint8_t *)planes[0], 0, out, outsize, NULL);
+  g_coef_planes = NULL; g_coef_pitch = NULL;
+  return rc;
+}
 /* jpeg_write_raw_data (jcapistd.c:145-195): component planes instead of pixels */
 int orc_encode_raw(const b200jpeg_params *p, const uint8_t *const *planes, const size_t *pitch, uint8_t **out, size_t *outsize)
 {
@@ -1135,6 +1148,14 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
     if (p->trellis_quant && !optimize) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
 
     write_file_header(e);                                                /* jcinit.c:149 */
+    if (g_coef_planes) {                                                 /* transcoding: no pass 0, the arrays are given */
+      for (ci = 0; ci < e->nc; ci++) {
+        int by;
+        for (by = 0; by < e->hib[ci]; by++)
+          memcpy(e->coef[ci] + (size_t)by * e->wpad[ci] * 64, g_coef_planes[ci] + (size_t)by * g_coef_pitch[ci] * 64, (size_t)e->wib[ci] * 128);
+        fill_dummy_blocks(e, ci);
+      }
+    } else
     forward_all(e, pixels, row_pitch);                                   /* pass 0 data path */
     if (dbg) { dbg->ncomp = e->nc; for (ci = 0; ci < e->nc; ci++) { size_t n = (size_t)e->wpad[ci] * e->hpad[ci] * 64 * 2;
         dbg->wib[ci] = e->wib[ci]; dbg->hib[ci] = e->hib[ci]; dbg->wpad[ci] = e->wpad[ci]; dbg->hpad[ci] = e->hpad[ci];

@@ -15,6 +15,7 @@
 
 #ifdef __cplusplus
 extern "C" {
+int orc_encode_coefs(const b200jpeg_params *p, const int16_t *const *planes, const size_t *pitch_blocks, uint8_t **out, size_t *outsize);
 int orc_encode_raw(const b200jpeg_params *p, const uint8_t *const *planes, const size_t *pitch, uint8_t **out, size_t *outsize);
 #endif
 

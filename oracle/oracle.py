@@ -283,3 +283,29 @@ def ref_cjpeg(ppm_path: str, switches: Sequence[str]) -> bytes:
 
 
 from mozjpeg_b200.synth import synth_image  # noqa: E402,F401  (input generator shared with bench.py)
+
+
+def oracle_encode_coefs(p: A.Params, planes) -> bytes:
+    """C restatement on coefficient input: planes[ci] = (hib, wib, 64) int16, natural order (jpeg_write_coefficients)."""
+    lib = orc()
+    lib.orc_encode_coefs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
+    lib.orc_encode_coefs.restype = C.c_int
+    arrs = [np.ascontiguousarray(a, dtype=np.int16) for a in planes]
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    pitch = (C.c_size_t * len(arrs))(*[a.strides[0] // 128 for a in arrs])
+    out = C.POINTER(C.c_uint8)(); n = C.c_size_t(0)
+    rc = lib.orc_encode_coefs(C.byref(p), ptrs, pitch, C.byref(out), C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"oracle coefficient encode failed: {rc}")
+    data = C.string_at(out, n.value)
+    lib.orc_free(out)
+    return data
+
+
+def ref_jpegtran(jpeg: bytes, switches: Sequence[str]) -> bytes:
+    """The reference's own jpegtran binary (oracle/_ref/jpegtran) on an in-memory file."""
+    exe = os.path.join(REF_DIR, "jpegtran")
+    r = subprocess.run([exe, *switches], input=jpeg, capture_output=True)
+    if r.returncode != 0:
+        raise RuntimeError("jpegtran failed: " + r.stderr.decode())
+    return r.stdout
