@@ -3,11 +3,14 @@
  * interposition library for the libjpeg API (JPEG_LIB_VERSION 62).
  *
  * Loaded in front of the reference's libjpeg (LD_PRELOAD, or linked before it),
- * it takes over the three calls that bracket the encode hot path,
+ * it takes over the calls that bracket the encode hot path,
  *
- *     jpeg_start_compress   (jcapistd.c:44-70)
- *     jpeg_write_scanlines  (jcapistd.c:90-135)
- *     jpeg_finish_compress  (jcapimin.c:176-229)
+ *     jpeg_start_compress      (jcapistd.c:44-70)
+ *     jpeg_write_scanlines     (jcapistd.c:90-135)
+ *     jpeg_write_raw_data      (jcapistd.c:145-195; under tj3CompressFromYUV*)
+ *     jpeg_write_coefficients  (jctrans.c:39-66; the encode half of jpegtran)
+ *     jpeg_finish_compress     (jcapimin.c:176-229)
+ *     jpeg_write_marker        (jcapimin.c:232-261; segments are spliced in after the file header)
  *
  * and runs the image through the C-ABI of include/b200jpeg.h (sm_100a kernels).
  * Everything else -- jpeg_create_compress, jpeg_set_defaults, jpeg_set_quality,
@@ -41,7 +44,13 @@
 #include "b200jpeg.h"
 
 #define MAX_ACTIVE 16
-static struct { j_compress_ptr cinfo; b200jpeg_encoder *enc; } g_active[MAX_ACTIVE];
+static struct {
+  j_compress_ptr cinfo; b200jpeg_encoder *enc;
+  jvirt_barray_ptr *coef_arrays; b200jpeg_params params;     /* jpeg_write_coefficients objects: read at finish time */
+  int raw; uint8_t *plane[4]; size_t plane_pitch[4], plane_rows[4];   /* jpeg_write_raw_data objects: the component planes so far */
+  unsigned char *extra; size_t extra_len, extra_cap;         /* jpeg_write_marker segments, in call order */
+  size_t header_len;                                         /* SOI + JFIF APP0 + Adobe APP14 (write_file_header, jcmarker.c:649-663) */
+} g_active[MAX_ACTIVE];
 static b200jpeg_encoder *g_idle_enc;          /* encoders are reused: creating one costs a CUDA context */
 static int g_no_device;
 
@@ -69,7 +78,19 @@ static int find_active(j_compress_ptr cinfo)
 static void release_slot(int i)
 {
   if (g_idle_enc) b200jpeg_encoder_destroy(g_active[i].enc); else g_idle_enc = g_active[i].enc;
-  g_active[i].cinfo = NULL; g_active[i].enc = NULL;
+  free(g_active[i].extra);
+  for (int k = 0; k < 4; k++) free(g_active[i].plane[k]);
+  memset(&g_active[i], 0, sizeof g_active[i]);
+}
+
+/* width_in_blocks / height_in_blocks as initial_setup computes them (jcmaster.c:215-236); the reference's master
+ * control is not run on objects that take the device path, so they are derived here */
+static void comp_blocks(j_compress_ptr cinfo, int ci, JDIMENSION *wib, JDIMENSION *hib)
+{
+  int hmax = 1, vmax = 1;
+  for (int k = 0; k < cinfo->num_components; k++) { if (cinfo->comp_info[k].h_samp_factor > hmax) hmax = cinfo->comp_info[k].h_samp_factor; if (cinfo->comp_info[k].v_samp_factor > vmax) vmax = cinfo->comp_info[k].v_samp_factor; }
+  *wib = (JDIMENSION)(((long)cinfo->image_width * cinfo->comp_info[ci].h_samp_factor + hmax * DCTSIZE - 1) / (hmax * DCTSIZE));
+  *hib = (JDIMENSION)(((long)cinfo->image_height * cinfo->comp_info[ci].v_samp_factor + vmax * DCTSIZE - 1) / (vmax * DCTSIZE));
 }
 
 /* the encoder-relevant state of the reference's object -> b200jpeg_params.  Returns 0 if the
@@ -79,7 +100,7 @@ static int fill_params(j_compress_ptr cinfo, boolean write_all_tables, b200jpeg_
   int i, ci;
   memset(p, 0, sizeof(*p));
   if (!write_all_tables) return 0;                       /* abbreviated datastreams: reference only */
-  if (cinfo->data_precision != 8 || cinfo->arith_code || cinfo->raw_data_in || cinfo->master->lossless) return 0;
+  if (cinfo->data_precision != 8 || cinfo->arith_code || cinfo->master->lossless) return 0;
   if (cinfo->num_components > B200JPEG_MAX_COMPONENTS || cinfo->num_scans > B200JPEG_MAX_SCANS) return 0;
   switch (cinfo->in_color_space) {
   case JCS_GRAYSCALE: p->in_color_space = B200JPEG_CS_GRAYSCALE; break;
@@ -163,7 +184,8 @@ jpeg_start_compress(j_compress_ptr cinfo, boolean write_all_tables)
   }
   if (!why && !g_idle_enc) why = b200jpeg_last_error();
   if (!why) {
-    int rc = b200jpeg_start_compress(g_idle_enc, &p);
+    /* raw-data objects (jpeg_write_raw_data) collect their planes on the host and encode at finish time */
+    int rc = cinfo->raw_data_in ? b200jpeg_validate(&p) : b200jpeg_start_compress(g_idle_enc, &p);
     if (rc != B200JPEG_OK) why = b200jpeg_last_error();
   }
   if (why) {
@@ -172,12 +194,53 @@ jpeg_start_compress(j_compress_ptr cinfo, boolean write_all_tables)
     real(cinfo, write_all_tables);
     return;
   }
-  if (verbose()) fprintf(stderr, "b200 shim: device path (%ux%u, %d scans)\n", cinfo->image_width, cinfo->image_height, p.num_scans);
+  if (verbose()) fprintf(stderr, "b200 shim: device path (%s%ux%u, %d scans)\n", cinfo->raw_data_in ? "raw data, " : "", cinfo->image_width, cinfo->image_height, p.num_scans);
+  memset(&g_active[slot], 0, sizeof g_active[slot]);
   g_active[slot].cinfo = cinfo; g_active[slot].enc = g_idle_enc; g_idle_enc = NULL;
+  g_active[slot].header_len = 2 + (p.write_JFIF_header ? 18 : 0) + (p.write_Adobe_marker ? 16 : 0);
+  if (cinfo->raw_data_in) {
+    g_active[slot].raw = 1; g_active[slot].params = p;
+    for (int ci = 0; ci < cinfo->num_components; ci++) {
+      JDIMENSION wib, hib; comp_blocks(cinfo, ci, &wib, &hib);
+      g_active[slot].plane_pitch[ci] = (size_t)wib * DCTSIZE; g_active[slot].plane_rows[ci] = (size_t)hib * DCTSIZE;
+      g_active[slot].plane[ci] = (uint8_t *)calloc(g_active[slot].plane_pitch[ci], g_active[slot].plane_rows[ci]);
+      if (!g_active[slot].plane[ci]) { release_slot(slot); ERREXIT1(cinfo, JERR_OUT_OF_MEMORY, 0); }
+    }
+  }
   jpeg_suppress_tables(cinfo, FALSE);                               /* jcapistd.c:50-51 (write_all_tables is TRUE here) */
   (*cinfo->err->reset_error_mgr) ((j_common_ptr)cinfo);
   cinfo->next_scanline = 0;
-  cinfo->global_state = CSTATE_SCANNING;
+  cinfo->global_state = cinfo->raw_data_in ? CSTATE_RAW_OK : CSTATE_SCANNING;
+}
+
+/* jpeg_write_raw_data (jcapistd.c:145-195): one iMCU row of already converted, downsampled component rows per call;
+ * compress_first_pass (jccoefct.c:262-353) reads v_samp_factor*8 rows of width_in_blocks*8 samples of every component */
+typedef JDIMENSION (*rawdata_fn)(j_compress_ptr, JSAMPIMAGE, JDIMENSION);
+GLOBAL(JDIMENSION)
+jpeg_write_raw_data(j_compress_ptr cinfo, JSAMPIMAGE data, JDIMENSION num_lines)
+{
+  static rawdata_fn real;
+  int slot = find_active(cinfo);
+  if (slot < 0) { if (!real) real = (rawdata_fn)next_sym("jpeg_write_raw_data"); return real(cinfo, data, num_lines); }
+  if (cinfo->global_state != CSTATE_RAW_OK || !g_active[slot].raw) ERREXIT1(cinfo, JERR_BAD_STATE, cinfo->global_state);
+  if (cinfo->next_scanline >= cinfo->image_height) { WARNMS(cinfo, JWRN_TOO_MUCH_DATA); return 0; }
+  if (cinfo->progress != NULL) {
+    cinfo->progress->pass_counter = (long)cinfo->next_scanline;
+    cinfo->progress->pass_limit = (long)cinfo->image_height;
+    (*cinfo->progress->progress_monitor) ((j_common_ptr)cinfo);
+  }
+  int vmax = 1;
+  for (int k = 0; k < cinfo->num_components; k++) if (cinfo->comp_info[k].v_samp_factor > vmax) vmax = cinfo->comp_info[k].v_samp_factor;
+  const JDIMENSION lines_per_iMCU_row = (JDIMENSION)(vmax * DCTSIZE);
+  if (num_lines < lines_per_iMCU_row) ERREXIT(cinfo, JERR_BUFFER_SIZE);
+  const size_t imcu = cinfo->next_scanline / lines_per_iMCU_row;
+  for (int ci = 0; ci < cinfo->num_components; ci++) {
+    const size_t rows = (size_t)cinfo->comp_info[ci].v_samp_factor * DCTSIZE, r0 = imcu * rows;
+    for (size_t r = 0; r < rows && r0 + r < g_active[slot].plane_rows[ci]; r++)
+      memcpy(g_active[slot].plane[ci] + (r0 + r) * g_active[slot].plane_pitch[ci], data[ci][r], g_active[slot].plane_pitch[ci]);
+  }
+  cinfo->next_scanline += lines_per_iMCU_row;
+  return lines_per_iMCU_row;
 }
 
 GLOBAL(JDIMENSION)
@@ -199,32 +262,74 @@ jpeg_write_scanlines(j_compress_ptr cinfo, JSAMPARRAY scanlines, JDIMENSION num_
   return (JDIMENSION)took;
 }
 
+/* hand the finished datastream to the application's destination manager (jpeglib.h:897-904) */
+static void push_bytes(j_compress_ptr cinfo, int slot, const uint8_t *src, size_t n)
+{
+  size_t off = 0;
+  while (off < n) {
+    size_t k = n - off < cinfo->dest->free_in_buffer ? n - off : cinfo->dest->free_in_buffer;
+    memcpy(cinfo->dest->next_output_byte, src + off, k);
+    cinfo->dest->next_output_byte += k; cinfo->dest->free_in_buffer -= k; off += k;
+    if (cinfo->dest->free_in_buffer == 0) {
+      if (!(*cinfo->dest->empty_output_buffer) (cinfo)) { release_slot(slot); ERREXIT(cinfo, JERR_CANT_SUSPEND); }
+    }
+  }
+}
+
+/* the caller's coefficient arrays -> one contiguous plane per component -> b200jpeg_encode_batch_coefs */
+static int encode_coef_arrays(j_compress_ptr cinfo, int slot)
+{
+  b200jpeg_params *p = &g_active[slot].params;
+  const int16_t *planes[4] = {NULL, NULL, NULL, NULL}; size_t pitch[4] = {0, 0, 0, 0}, stride[4] = {0, 0, 0, 0};
+  int16_t *buf[4] = {NULL, NULL, NULL, NULL};
+  int rc = B200JPEG_OK;
+  for (int ci = 0; ci < cinfo->num_components; ci++) {
+    JDIMENSION wib, hib; comp_blocks(cinfo, ci, &wib, &hib);
+    buf[ci] = (int16_t *)malloc((size_t)wib * hib * DCTSIZE2 * sizeof(int16_t));
+    if (!buf[ci]) { rc = B200JPEG_ERR_BUFFER; break; }
+    for (JDIMENSION r = 0; r < hib; r++) {
+      JBLOCKARRAY rows = (*cinfo->mem->access_virt_barray) ((j_common_ptr)cinfo, g_active[slot].coef_arrays[ci], r, 1, FALSE);
+      memcpy(buf[ci] + (size_t)r * wib * DCTSIZE2, rows[0], (size_t)wib * DCTSIZE2 * sizeof(JCOEF));
+    }
+    planes[ci] = buf[ci]; pitch[ci] = wib; stride[ci] = (size_t)wib * hib;
+  }
+  if (rc == B200JPEG_OK) rc = b200jpeg_encode_batch_coefs(g_active[slot].enc, p, planes, 0, pitch, stride, 1);
+  for (int ci = 0; ci < 4; ci++) free(buf[ci]);
+  return rc;
+}
+
 GLOBAL(void)
 jpeg_finish_compress(j_compress_ptr cinfo)
 {
   static finish_fn real;
   int slot = find_active(cinfo);
   if (slot < 0) { if (!real) real = (finish_fn)next_sym("jpeg_finish_compress"); real(cinfo); return; }
-  if (cinfo->next_scanline < cinfo->image_height) { release_slot(slot); ERREXIT(cinfo, JERR_TOO_LITTLE_DATA); }   /* jcapimin.c:183-184 */
-  const uint8_t *jpg; size_t n, off = 0;
+  const int from_coefs = g_active[slot].coef_arrays != NULL;
+  if (!from_coefs && cinfo->next_scanline < cinfo->image_height) { release_slot(slot); ERREXIT(cinfo, JERR_TOO_LITTLE_DATA); }   /* jcapimin.c:183-184 */
+  const uint8_t *jpg; size_t n;
   b200jpeg_encoder *enc = g_active[slot].enc;
-  int rc = b200jpeg_finish_compress(enc, &jpg, &n);                  /* all device work happens here, on the caller's thread */
+  int rc;                                                            /* all device work happens here, on the caller's thread */
+  if (from_coefs) { rc = encode_coef_arrays(cinfo, slot); if (rc == B200JPEG_OK) rc = b200jpeg_get_output(enc, 0, &jpg, &n); }
+  else if (g_active[slot].raw) {
+    size_t stride[4];
+    for (int ci = 0; ci < 4; ci++) stride[ci] = g_active[slot].plane_pitch[ci] * g_active[slot].plane_rows[ci];
+    rc = b200jpeg_encode_batch_raw(enc, &g_active[slot].params, (const uint8_t *const *)g_active[slot].plane, 0, g_active[slot].plane_pitch, stride, 1);
+    if (rc == B200JPEG_OK) rc = b200jpeg_get_output(enc, 0, &jpg, &n);
+  }
+  else rc = b200jpeg_finish_compress(enc, &jpg, &n);
   if (rc != B200JPEG_OK) {
     release_slot(slot);
     fprintf(stderr, "b200 shim: %s\n", b200jpeg_last_error());
     if (rc == B200JPEG_ERR_BAD_DCT_COEF) ERREXIT(cinfo, JERR_BAD_DCT_COEF);
     ERREXIT(cinfo, JERR_NOTIMPL);
   }
-  /* hand the finished datastream to the application's destination manager (jpeglib.h:897-904) */
-  (*cinfo->dest->init_destination) (cinfo);
-  while (off < n) {
-    size_t k = n - off < cinfo->dest->free_in_buffer ? n - off : cinfo->dest->free_in_buffer;
-    memcpy(cinfo->dest->next_output_byte, jpg + off, k);
-    cinfo->dest->next_output_byte += k; cinfo->dest->free_in_buffer -= k; off += k;
-    if (cinfo->dest->free_in_buffer == 0 && off < n) {
-      if (!(*cinfo->dest->empty_output_buffer) (cinfo)) { release_slot(slot); ERREXIT(cinfo, JERR_CANT_SUSPEND); }
-    }
-  }
+  if (!from_coefs) (*cinfo->dest->init_destination) (cinfo);         /* jpeg_write_coefficients did it already (jctrans.c:57) */
+  /* the file header, the application's own marker segments (written right behind it, like the reference's marker
+   * writer would have), then the rest */
+  size_t hl = g_active[slot].header_len < n ? g_active[slot].header_len : n;
+  push_bytes(cinfo, slot, jpg, hl);
+  if (g_active[slot].extra_len) push_bytes(cinfo, slot, g_active[slot].extra, g_active[slot].extra_len);
+  push_bytes(cinfo, slot, jpg + hl, n - hl);
   (*cinfo->dest->term_destination) (cinfo);
   /* tables are now "sent" (jcmarker.c sets sent_table as it writes them) */
   for (int i = 0; i < NUM_QUANT_TBLS; i++) if (cinfo->quant_tbl_ptrs[i]) cinfo->quant_tbl_ptrs[i]->sent_table = TRUE;
@@ -236,13 +341,57 @@ jpeg_finish_compress(j_compress_ptr cinfo)
   jpeg_abort((j_common_ptr)cinfo);                                   /* back to CSTATE_START (jcapimin.c:227) */
 }
 
+/* jpeg_write_coefficients (jctrans.c:39-66): the arrays may still be empty here (jpegtran fills them afterwards,
+ * jtransform_execute_transformation), so they are only remembered; jpeg_finish_compress reads and encodes them. */
+typedef void (*wrcoef_fn)(j_compress_ptr, jvirt_barray_ptr *);
+GLOBAL(void)
+jpeg_write_coefficients(j_compress_ptr cinfo, jvirt_barray_ptr *coef_arrays)
+{
+  static wrcoef_fn real;
+  if (!real) real = (wrcoef_fn)next_sym("jpeg_write_coefficients");
+  b200jpeg_params p;
+  const char *why = NULL;
+  int slot = -1;
+  if (cinfo->global_state != CSTATE_START || cinfo->master->lossless) { real(cinfo, coef_arrays); return; }   /* the reference raises the error */
+  if (getenv("MOZ_B200_FORCE_CPU")) why = "MOZ_B200_FORCE_CPU is set";
+  if (cinfo->master->num_scans_luma == 0) cinfo->master->optimize_scans = FALSE;        /* jctrans.c:49-50 */
+  if (!why && !fill_params(cinfo, TRUE, &p)) why = "parameter set outside b200jpeg_params";
+  if (!why && p.trellis_quant) why = "trellis quantization requested on coefficient input";
+  if (!why && b200jpeg_validate(&p) != B200JPEG_OK) why = b200jpeg_last_error();
+  if (!why) {
+    for (int i = 0; i < MAX_ACTIVE && slot < 0; i++) if (!g_active[i].cinfo) slot = i;
+    if (slot < 0) why = "too many concurrent compressors";
+  }
+  if (!why && !g_idle_enc && !g_no_device) {
+    if (b200jpeg_encoder_create(&g_idle_enc, 0) != B200JPEG_OK) { g_no_device = 1; g_idle_enc = NULL; }
+  }
+  if (!why && !g_idle_enc) why = b200jpeg_last_error();
+  if (why) {
+    if (verbose()) fprintf(stderr, "b200 shim: reference path (%s)\n", why);
+    if (required()) { fprintf(stderr, "b200 shim: B200_SHIM_REQUIRE=1 and the device path was not taken: %s\n", why); ERREXIT(cinfo, JERR_NOTIMPL); }
+    real(cinfo, coef_arrays);
+    return;
+  }
+  if (verbose()) fprintf(stderr, "b200 shim: device path (coefficients, %ux%u, %d scans)\n", cinfo->image_width, cinfo->image_height, p.num_scans);
+  memset(&g_active[slot], 0, sizeof g_active[slot]);
+  g_active[slot].cinfo = cinfo; g_active[slot].enc = g_idle_enc; g_idle_enc = NULL;
+  g_active[slot].coef_arrays = coef_arrays; g_active[slot].params = p;
+  g_active[slot].header_len = 2 + (p.write_JFIF_header ? 18 : 0) + (p.write_Adobe_marker ? 16 : 0);
+  jpeg_suppress_tables(cinfo, FALSE);                                /* jctrans.c:54 */
+  (*cinfo->err->reset_error_mgr) ((j_common_ptr)cinfo);
+  (*cinfo->dest->init_destination) (cinfo);
+  (*cinfo->mem->realize_virt_arrays) ((j_common_ptr)cinfo);          /* arrays requested from this object's pool (jctrans.c:211) */
+  cinfo->next_scanline = 0;                                          /* so jpeg_write_marker works (jctrans.c:63) */
+  cinfo->global_state = CSTATE_WRCOEFS;
+}
+
 /* an application that gives up mid-image */
 GLOBAL(void)
 jpeg_abort_compress(j_compress_ptr cinfo)
 {
   static abort_fn real;
   int slot = find_active(cinfo);
-  if (slot >= 0) { const uint8_t *j; size_t n; (void)j; (void)n; b200jpeg_encoder_destroy(g_active[slot].enc); g_active[slot].cinfo = NULL; g_active[slot].enc = NULL; }
+  if (slot >= 0) { b200jpeg_encoder_destroy(g_active[slot].enc); free(g_active[slot].extra); for (int k = 0; k < 4; k++) free(g_active[slot].plane[k]); memset(&g_active[slot], 0, sizeof g_active[slot]); }
   if (!real) real = (abort_fn)next_sym("jpeg_abort_compress");
   real(cinfo);
 }
@@ -251,18 +400,69 @@ jpeg_destroy_compress(j_compress_ptr cinfo)
 {
   static abort_fn real;
   int slot = find_active(cinfo);
-  if (slot >= 0) { b200jpeg_encoder_destroy(g_active[slot].enc); g_active[slot].cinfo = NULL; g_active[slot].enc = NULL; }
+  if (slot >= 0) { b200jpeg_encoder_destroy(g_active[slot].enc); free(g_active[slot].extra); for (int k = 0; k < 4; k++) free(g_active[slot].plane[k]); memset(&g_active[slot], 0, sizeof g_active[slot]); }
   if (!real) real = (abort_fn)next_sym("jpeg_destroy_compress");
   real(cinfo);
 }
 
-/* markers between start_compress and the first scanline would go through the reference's marker
- * writer, which the device path never initialises: refuse loudly instead of crashing */
+/* Marker segments an application writes between jpeg_start_compress / jpeg_write_coefficients and the first
+ * data (jpeg_write_marker, jpeg_write_m_header + jpeg_write_m_byte, jcapimin.c:232-290): the reference's marker writer
+ * would put them right behind the file header; the device path keeps them and splices them in at the same place. */
+static void extra_put(int slot, j_compress_ptr cinfo, const unsigned char *d, size_t n)
+{
+  if (g_active[slot].extra_len + n > g_active[slot].extra_cap) {
+    size_t cap = g_active[slot].extra_cap ? g_active[slot].extra_cap * 2 : 4096;
+    while (cap < g_active[slot].extra_len + n) cap *= 2;
+    unsigned char *q = (unsigned char *)realloc(g_active[slot].extra, cap);
+    if (!q) ERREXIT1(cinfo, JERR_OUT_OF_MEMORY, 0);
+    g_active[slot].extra = q; g_active[slot].extra_cap = cap;
+  }
+  memcpy(g_active[slot].extra + g_active[slot].extra_len, d, n); g_active[slot].extra_len += n;
+}
+static void marker_state_check(j_compress_ptr cinfo)
+{
+  if (cinfo->next_scanline != 0 || (cinfo->global_state != CSTATE_SCANNING && cinfo->global_state != CSTATE_RAW_OK && cinfo->global_state != CSTATE_WRCOEFS))
+    ERREXIT1(cinfo, JERR_BAD_STATE, cinfo->global_state);
+}
 GLOBAL(void)
 jpeg_write_marker(j_compress_ptr cinfo, int marker, const JOCTET *dataptr, unsigned int datalen)
 {
   static marker_fn real;
-  if (find_active(cinfo) >= 0) { fprintf(stderr, "b200 shim: jpeg_write_marker is not supported on the device path\n"); ERREXIT(cinfo, JERR_NOTIMPL); }
+  int slot = find_active(cinfo);
+  if (slot >= 0) {
+    marker_state_check(cinfo);
+    if (datalen > 65533u) ERREXIT(cinfo, JERR_BAD_LENGTH);           /* write_marker_header, jcmarker.c:609-619 */
+    unsigned char h[4] = {0xFF, (unsigned char)marker, (unsigned char)((datalen + 2) >> 8), (unsigned char)((datalen + 2) & 0xFF)};
+    extra_put(slot, cinfo, h, 4);
+    extra_put(slot, cinfo, dataptr, datalen);
+    return;
+  }
   if (!real) real = (marker_fn)next_sym("jpeg_write_marker");
   real(cinfo, marker, dataptr, datalen);
+}
+typedef void (*mheader_fn)(j_compress_ptr, int, unsigned int);
+typedef void (*mbyte_fn)(j_compress_ptr, int);
+GLOBAL(void)
+jpeg_write_m_header(j_compress_ptr cinfo, int marker, unsigned int datalen)
+{
+  static mheader_fn real;
+  int slot = find_active(cinfo);
+  if (slot >= 0) {
+    marker_state_check(cinfo);
+    if (datalen > 65533u) ERREXIT(cinfo, JERR_BAD_LENGTH);
+    unsigned char h[4] = {0xFF, (unsigned char)marker, (unsigned char)((datalen + 2) >> 8), (unsigned char)((datalen + 2) & 0xFF)};
+    extra_put(slot, cinfo, h, 4);
+    return;
+  }
+  if (!real) real = (mheader_fn)next_sym("jpeg_write_m_header");
+  real(cinfo, marker, datalen);
+}
+GLOBAL(void)
+jpeg_write_m_byte(j_compress_ptr cinfo, int val)
+{
+  static mbyte_fn real;
+  int slot = find_active(cinfo);
+  if (slot >= 0) { unsigned char b = (unsigned char)val; extra_put(slot, cinfo, &b, 1); return; }
+  if (!real) real = (mbyte_fn)next_sym("jpeg_write_m_byte");
+  real(cinfo, val);
 }

@@ -78,3 +78,78 @@ def test_shim_without_gpu_is_transparent(tmp_path):
     assert data == plain.stdout
     r2, _ = _run(["-baseline", "-quality", "75"], {"MOZ_B200_FORCE_CPU": "1", "B200_SHIM_REQUIRE": "1"}, tmp_path)
     assert r2.returncode != 0
+
+
+JPEGTRAN = os.path.join(ROOT, "oracle", "_ref", "jpegtran")
+need_tran = pytest.mark.skipif(not (os.path.exists(SHIM) and os.path.exists(CJPEG) and os.path.exists(JPEGTRAN)),
+                               reason="shim / reference cjpeg / jpegtran not built (needs /root/reference at build time)")
+
+
+def _tran(switches, src, env_extra):
+    env = dict(os.environ, LD_PRELOAD=SHIM, B200_SHIM_VERBOSE="1", **env_extra)
+    return subprocess.run([JPEGTRAN, *switches], input=src, env=env, capture_output=True, timeout=300)
+
+
+@need_tran
+@pytest.mark.gpu
+@pytest.mark.parametrize("tsw", [[], ["-progressive"], ["-revert", "-optimize"], ["-fastcrush", "-restart", "2"], ["-revert"]],
+                         ids=lambda s: "_".join(x.lstrip("-") for x in s) or "default")
+@pytest.mark.parametrize("esw", [["-revert"], ["-quality", "85", "-sample", "1x1"]], ids=lambda s: "_".join(x.lstrip("-") for x in s))
+def test_reference_jpegtran_encodes_on_the_device(esw, tsw):
+    """jpeg_read_coefficients stays the reference's; jpeg_write_coefficients + jpeg_finish_compress run on the GPU."""
+    src = subprocess.run([CJPEG, *esw, PPM], capture_output=True, timeout=300).stdout
+    r = _tran(tsw, src, {"B200_SHIM_REQUIRE": "1"})
+    assert r.returncode == 0, r.stderr
+    assert b"device path (coefficients" in r.stderr, r.stderr
+    plain = subprocess.run([JPEGTRAN, *tsw], input=src, capture_output=True, timeout=300)
+    assert plain.returncode == 0 and r.stdout == plain.stdout
+
+
+@need_tran
+@pytest.mark.gpu
+def test_application_markers_are_spliced_in_behind_the_file_header(tmp_path):
+    """jpeg_write_icc_profile (jpeg_write_m_header / jpeg_write_m_byte) on the pixel path, jcopy_markers_execute
+    (jpeg_write_marker) on the coefficient path."""
+    icc = tmp_path / "fake.icc"
+    icc.write_bytes(bytes(range(256)) * 300)                     # two APP2 chunks' worth is not needed; one 76 KB profile = 2 chunks
+    sw = ["-quality", "75", "-icc", str(icc)]
+    r, data = _run(sw, {"B200_SHIM_REQUIRE": "1"}, tmp_path)
+    assert r.returncode == 0, r.stderr
+    plain = subprocess.run([CJPEG, *sw, PPM], capture_output=True, timeout=300)
+    assert plain.returncode == 0 and data == plain.stdout and b"ICC_PROFILE" in data
+    t = _tran(["-copy", "all", "-progressive"], data, {"B200_SHIM_REQUIRE": "1"})
+    assert t.returncode == 0, t.stderr
+    plain_t = subprocess.run([JPEGTRAN, "-copy", "all", "-progressive"], input=data, capture_output=True, timeout=300)
+    assert plain_t.returncode == 0 and t.stdout == plain_t.stdout and b"ICC_PROFILE" in t.stdout
+
+
+TJBENCH = os.path.join(ROOT, "oracle", "_ref", "tjbench")
+need_tj = pytest.mark.skipif(not (os.path.exists(SHIM) and os.path.exists(TJBENCH)),
+                             reason="shim / reference tjbench not built (needs /root/reference at build time)")
+
+
+@need_tj
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts", [["-subsamp", "420"], ["-subsamp", "444", "-optimize"], ["-subsamp", "422", "-progressive"],
+                                  ["-subsamp", "gray"], ["-subsamp", "420", "-restart", "1"],
+                                  ["-subsamp", "420", "-yuv"], ["-subsamp", "422", "-yuv", "-optimize"]], ids=lambda s: "_".join(x.lstrip("-") for x in s))
+def test_turbojpeg_api_runs_on_the_device(opts, tmp_path):
+    """The TurboJPEG API (tj3Compress8, turbojpeg.c:1268-1340) sits on the libjpeg API exactly as in the reference
+    (turbojpeg-mp.c:104-125); with the reference's turbojpeg.c linked dynamically against libjpeg (oracle/Makefile) the
+    shim is underneath it, and the reference's own tjbench writes the same files as without the shim.  -yuv goes through
+    tj3EncodeYUV8 (CPU colour conversion, the reference's) + tj3CompressFromYUVPlanes8 -> jpeg_write_raw_data."""
+    import shutil
+    outs = []
+    for name, env_extra in (("dev", {"LD_PRELOAD": SHIM, "B200_SHIM_REQUIRE": "1", "B200_SHIM_VERBOSE": "1"}), ("ref", {})):
+        d = tmp_path / name
+        d.mkdir()
+        shutil.copyfile(PPM, d / "img.ppm")
+        r = subprocess.run([TJBENCH, "img.ppm", "75", "-rgb", "-quiet", "-benchtime", "0.01", "-warmup", "0", "-componly", *opts],
+                           cwd=d, env=dict(os.environ, **env_extra), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr + r.stdout
+        if name == "dev":
+            assert "device path" in r.stderr, r.stderr
+        jpgs = sorted(f for f in os.listdir(d) if f.endswith(".jpg"))
+        assert len(jpgs) == 1, os.listdir(d)
+        outs.append((d / jpgs[0]).read_bytes())
+    assert outs[0] == outs[1] and len(outs[0]) > 100
