@@ -54,11 +54,110 @@ def _set_sample_factors(p: A.Params, arg: str) -> None:
         p.comp_info[ci].v_samp_factor = v
 
 
+def _text_integers(text: str):
+    """rdswitch.c:37-77 read_text_integer over a whole file: ('int', value) / ('sep', char) tokens; '#' starts a
+    comment that runs to the end of the line and reads as a newline."""
+    out = []
+    i, n = 0, len(text)
+    while i < n:
+        ch = text[i]
+        if ch == "#":
+            while i < n and text[i] != "\n":
+                i += 1
+            continue
+        if ch.isdigit():
+            j = i
+            while j < n and text[j].isdigit():
+                j += 1
+            out.append(("int", int(text[i:j])))
+            i = j
+            continue
+        if not ch.isspace():
+            out.append(("sep", ch))
+        i += 1
+    return out
+
+
+def _read_quant_tables(p: A.Params, filename: str, force_baseline: bool) -> None:
+    """rdswitch.c:83-146: up to NUM_QUANT_TBLS tables of 64 decimal values, each scaled by its slot's q_scale_factor."""
+    lib = A.load()
+    toks = _text_integers(open(filename).read())
+    if any(k != "int" for k, _ in toks):
+        raise UsageError(f"Non-numeric data in file {filename}")
+    vals = [v for _, v in toks]
+    if len(vals) % 64:
+        raise UsageError(f"Invalid table data in file {filename}")
+    if len(vals) // 64 > A.NUM_QUANT_TBLS:
+        raise UsageError(f"Too many tables in file {filename}")
+    for t in range(len(vals) // 64):
+        tbl = (C.c_uint * 64)(*vals[64 * t:64 * t + 64])
+        A.check(lib.b200jpeg_add_quant_table(C.byref(p), t, tbl, p.q_scale_factor[t], int(force_baseline)), "add_quant_table")
+
+
+def _set_quant_slots(p: A.Params, arg: str) -> None:
+    """rdswitch.c:576-612: N[,N,...], the last value replicated over the remaining components."""
+    parts = arg.split(",") if arg else []
+    val = 0
+    for ci in range(A.MAX_COMPONENTS):
+        if ci < len(parts):
+            try:
+                val = int(parts[ci])
+            except ValueError:
+                raise UsageError("can't set quant slots")
+            if not 0 <= val < A.NUM_QUANT_TBLS:
+                raise UsageError(f"JPEG quantization tables are numbered 0..{A.NUM_QUANT_TBLS - 1}")
+        p.comp_info[ci].quant_tbl_no = val
+
+
+def _read_scan_script(p: A.Params, filename: str) -> None:
+    """rdswitch.c:174-270: entries 'c0 [c1 ..] [: Ss Se Ah Al] ;' - any punctuation other than ':' and ';' is a
+    separator.  Validation is left to the library, like jcmaster.c does for the reference."""
+    toks = _text_integers(open(filename).read())
+    scans = []
+    cur: List[int] = []
+    prog: List[int] = []
+    in_prog = False
+
+    def close():
+        nonlocal cur, prog, in_prog
+        if not cur:
+            raise UsageError(f"Invalid scan entry format in file {filename}")
+        if in_prog and len(prog) != 4:
+            raise UsageError(f"Invalid scan entry format in file {filename}")
+        if len(cur) > 4:
+            raise UsageError(f"Too many components in one scan in file {filename}")
+        scans.append((cur, prog if in_prog else [0, 63, 0, 0]))
+        cur, prog, in_prog = [], [], False
+
+    for kind, v in toks:
+        if kind == "int":
+            (prog if in_prog else cur).append(v)
+        elif v == ":":
+            if in_prog or not cur:
+                raise UsageError(f"Invalid scan entry format in file {filename}")
+            in_prog = True
+        elif v == ";":
+            close()
+    if cur or in_prog:
+        close()                                               # the last entry may end at EOF
+    if len(scans) > 64:
+        raise UsageError(f"Too many scans defined in file {filename}")
+    if scans:
+        p.num_scans = len(scans)
+        for i, (comps, pr) in enumerate(scans):
+            si = p.scan_info[i]
+            si.comps_in_scan = len(comps)
+            for k in range(4):
+                si.component_index[k] = comps[k] if k < len(comps) else 0
+            si.Ss, si.Se, si.Ah, si.Al = pr
+        p.optimize_scans = 0                                  # rdswitch.c:262-263
+
+
 def _parse(p: A.Params, argv: Sequence[str], for_real: bool) -> None:
     lib = A.load()
     force_baseline = False
     simple_progressive = p.num_scans != 0          # cjpeg.c:343
-    qualityarg = samplearg = None
+    qualityarg = samplearg = qtablefile = qslotsarg = scansarg = None
     i = 0
     n = len(argv)
 
@@ -107,6 +206,12 @@ def _parse(p: A.Params, argv: Sequence[str], for_real: bool) -> None:
             simple_progressive = True
         elif _keymatch(a, "quality", 1):
             qualityarg = nextarg("quality")
+        elif _keymatch(a, "qslots", 2):
+            qslotsarg = nextarg("qslots")
+        elif _keymatch(a, "qtables", 2):
+            qtablefile = nextarg("qtables")
+        elif _keymatch(a, "scans", 2):
+            scansarg = nextarg("scans")
         elif _keymatch(a, "quant-table", 7):
             v = int(nextarg("quant-table"))
             if not 0 <= v <= 8:
@@ -171,10 +276,16 @@ def _parse(p: A.Params, argv: Sequence[str], for_real: bool) -> None:
                 _set_sample_factors(p, "1x1")
             elif val >= 80:
                 _set_sample_factors(p, "2x1")
+        if qtablefile is not None:
+            _read_quant_tables(p, qtablefile, force_baseline)
+        if qslotsarg is not None:
+            _set_quant_slots(p, qslotsarg)
         if samplearg is not None:
             _set_sample_factors(p, samplearg)
         if simple_progressive:
             A.check(lib.b200jpeg_simple_progression(C.byref(p)), "simple_progression")
+        if scansarg is not None:
+            _read_scan_script(p, scansarg)
 
 
 def params_from_switches(switches: Sequence[str], width: int, height: int,

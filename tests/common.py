@@ -13,13 +13,17 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 
 def golden_cases():
+    """Switch arguments written "@GOLD/name" in the fixture are files next to it (quantization tables, scan scripts)."""
     with open(os.path.join(GOLD, "golden.json")) as f:
-        return json.load(f)["cases"]
+        cases = json.load(f)["cases"]
+    for c in cases:
+        c["switches"] = [os.path.join(GOLD, s[6:]) if s.startswith("@GOLD/") else s for s in c["switches"]]
+    return cases
 
 
 def case_id(c):
     im = c["image"] if isinstance(c["image"], str) else "synth%s%dx%d" % ("12b_" if len(c["image"]) > 3 else "", c["image"][1], c["image"][2])
-    return im + ":" + "_".join(s.lstrip("-") for s in c["switches"])
+    return im + ":" + "_".join(os.path.basename(s).lstrip("-") for s in c["switches"])
 
 
 _img_cache = {}

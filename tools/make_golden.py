@@ -96,6 +96,19 @@ SWITCH_SETS_EXTRA = [
     ["-baseline", "-quality", "80", "-sample", "2x2,1x1,2x2"],
     ["-baseline", "-sample", "4x1,1x1,2x1", "-quality", "60"],
 ]
+# switches that name files (rdswitch.c read_quant_tables / set_quant_slots / read_scan_script); "@GOLD/" = tests/golden/
+SWITCH_SETS_FILES = [
+    ["-qtables", "@GOLD/qtables_a.txt", "-quality", "75"],
+    ["-qtables", "@GOLD/qtables_a.txt", "-baseline"],
+    ["-quality", "60,90", "-qtables", "@GOLD/qtables_a.txt", "-qslots", "1,0,0"],
+    ["-quality", "70,80", "-qslots", "1,0,1"],
+    ["-scans", "@GOLD/scans_a.txt", "-quality", "75"],                       # successive approximation, band splits
+    ["-scans", "@GOLD/scans_b.txt", "-quality", "80"],                       # sequential, two scans
+    ["-scans", "@GOLD/scans_c.txt"],
+    ["-revert", "-scans", "@GOLD/scans_a.txt"],
+    ["-revert", "-scans", "@GOLD/scans_b.txt", "-optimize"],
+    ["-scans", "@GOLD/scans_c.txt", "-restart", "1", "-sample", "2x1"],
+]
 # through the reference's cjpeg binary only (our refshim driver does not parse these switches)
 CJPEG_ONLY = [
     ["-revert", "-dct", "float"],
@@ -147,6 +160,15 @@ def main():
     for sw in SWITCH_SETS_EXTRA:
         a = O.ref_cjpeg(ppm, sw)
         cases.append({"image": "testorig", "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
+    expand = lambda sw: [os.path.join(GOLD, x[6:]) if x.startswith("@GOLD/") else x for x in sw]
+    for sw in SWITCH_SETS_FILES:
+        a = O.ref_cjpeg(ppm, expand(sw))
+        cases.append({"image": "testorig", "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
+    for (seed, sw_, sh_) in SYNTH[:4]:
+        im = O.synth_image(seed, sw_, sh_)
+        for sw in SWITCH_SETS_FILES:
+            a = O.ref_encode(im, expand(sw))
+            cases.append({"image": [seed, sw_, sh_], "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
     for (seed, sw_, sh_) in SYNTH:
         im = O.synth_image(seed, sw_, sh_)
         sets = SWITCH_SETS + SWITCH_SETS_EXTRA if sw_ * sh_ <= 640 * 480 else [s for s in SWITCH_SETS if s in (["-revert", "-dct", "int"], ["-baseline", "-quality", "75", "-sample", "2x2"], ["-fastcrush", "-quality", "75", "-sample", "2x2"], ["-baseline", "-quality", "90", "-sample", "2x2"], ["-quality", "75"])]
