@@ -92,11 +92,13 @@ def _tran(switches, src, env_extra):
 
 @need_tran
 @pytest.mark.gpu
-@pytest.mark.parametrize("tsw", [[], ["-progressive"], ["-revert", "-optimize"], ["-fastcrush", "-restart", "2"], ["-revert"]],
+@pytest.mark.parametrize("tsw", [[], ["-progressive"], ["-revert", "-optimize"], ["-fastcrush", "-restart", "2"], ["-revert"],
+                                 ["-rotate", "90"], ["-flip", "horizontal", "-progressive"], ["-grayscale", "-optimize"], ["-crop", "100x80+16+16"]],
                          ids=lambda s: "_".join(x.lstrip("-") for x in s) or "default")
 @pytest.mark.parametrize("esw", [["-revert"], ["-quality", "85", "-sample", "1x1"]], ids=lambda s: "_".join(x.lstrip("-") for x in s))
 def test_reference_jpegtran_encodes_on_the_device(esw, tsw):
-    """jpeg_read_coefficients stays the reference's; jpeg_write_coefficients + jpeg_finish_compress run on the GPU."""
+    """jpeg_read_coefficients (and the lossless transforms, which fill the output arrays only after
+    jpeg_write_coefficients) stay the reference's; jpeg_write_coefficients + jpeg_finish_compress run on the GPU."""
     src = subprocess.run([CJPEG, *esw, PPM], capture_output=True, timeout=300).stdout
     r = _tran(tsw, src, {"B200_SHIM_REQUIRE": "1"})
     assert r.returncode == 0, r.stderr
