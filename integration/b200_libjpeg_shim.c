@@ -93,6 +93,28 @@ static void comp_blocks(j_compress_ptr cinfo, int ci, JDIMENSION *wib, JDIMENSIO
   *hib = (JDIMENSION)(((long)cinfo->image_height * cinfo->comp_info[ci].v_samp_factor + vmax * DCTSIZE - 1) / (vmax * DCTSIZE));
 }
 
+/* The derived fields initial_setup (jcmaster.c:209-257) leaves in the object: applications read them after
+ * jpeg_start_compress / jpeg_write_coefficients (jpegtran's transforms loop over comp_info[].width_in_blocks and use
+ * max_h_samp_factor, jtransform_execute_transformation), so the device path fills them in too. */
+static void derive_geometry(j_compress_ptr cinfo)
+{
+  cinfo->max_h_samp_factor = 1; cinfo->max_v_samp_factor = 1;
+  for (int ci = 0; ci < cinfo->num_components; ci++) {
+    if (cinfo->comp_info[ci].h_samp_factor > cinfo->max_h_samp_factor) cinfo->max_h_samp_factor = cinfo->comp_info[ci].h_samp_factor;
+    if (cinfo->comp_info[ci].v_samp_factor > cinfo->max_v_samp_factor) cinfo->max_v_samp_factor = cinfo->comp_info[ci].v_samp_factor;
+  }
+  for (int ci = 0; ci < cinfo->num_components; ci++) {
+    jpeg_component_info *c = &cinfo->comp_info[ci];
+    c->component_index = ci;
+    c->DCT_scaled_size = DCTSIZE;
+    comp_blocks(cinfo, ci, &c->width_in_blocks, &c->height_in_blocks);
+    c->downsampled_width = (JDIMENSION)(((long)cinfo->image_width * c->h_samp_factor + cinfo->max_h_samp_factor - 1) / cinfo->max_h_samp_factor);
+    c->downsampled_height = (JDIMENSION)(((long)cinfo->image_height * c->v_samp_factor + cinfo->max_v_samp_factor - 1) / cinfo->max_v_samp_factor);
+    c->component_needed = TRUE;
+  }
+  cinfo->total_iMCU_rows = (JDIMENSION)(((long)cinfo->image_height + cinfo->max_v_samp_factor * DCTSIZE - 1) / (cinfo->max_v_samp_factor * DCTSIZE));
+}
+
 /* the encoder-relevant state of the reference's object -> b200jpeg_params.  Returns 0 if the
  * object uses something the parameter block cannot express (then the reference encodes it). */
 static int fill_params(j_compress_ptr cinfo, boolean write_all_tables, b200jpeg_params *p)
@@ -207,6 +229,7 @@ jpeg_start_compress(j_compress_ptr cinfo, boolean write_all_tables)
       if (!g_active[slot].plane[ci]) { release_slot(slot); ERREXIT1(cinfo, JERR_OUT_OF_MEMORY, 0); }
     }
   }
+  derive_geometry(cinfo);
   jpeg_suppress_tables(cinfo, FALSE);                               /* jcapistd.c:50-51 (write_all_tables is TRUE here) */
   (*cinfo->err->reset_error_mgr) ((j_common_ptr)cinfo);
   cinfo->next_scanline = 0;
@@ -377,6 +400,7 @@ jpeg_write_coefficients(j_compress_ptr cinfo, jvirt_barray_ptr *coef_arrays)
   g_active[slot].cinfo = cinfo; g_active[slot].enc = g_idle_enc; g_idle_enc = NULL;
   g_active[slot].coef_arrays = coef_arrays; g_active[slot].params = p;
   g_active[slot].header_len = 2 + (p.write_JFIF_header ? 18 : 0) + (p.write_Adobe_marker ? 16 : 0);
+  derive_geometry(cinfo);
   jpeg_suppress_tables(cinfo, FALSE);                                /* jctrans.c:54 */
   (*cinfo->err->reset_error_mgr) ((j_common_ptr)cinfo);
   (*cinfo->dest->init_destination) (cinfo);

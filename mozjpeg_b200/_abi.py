@@ -12,6 +12,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200jpeg.so")
+if os.environ.get("B200JPEG_LIB_VARIANT"):            # development aid (tools/build_variant.sh): A/B builds of the kernels
+    LIB_PATH = os.path.join(_HERE, "variants", "libb200jpeg_%s.so" % os.environ["B200JPEG_LIB_VARIANT"])
 
 MAX_COMPONENTS = 4
 NUM_QUANT_TBLS = 4

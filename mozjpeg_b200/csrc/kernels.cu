@@ -22,6 +22,12 @@ __constant__ uint8_t c_izz[64] = {
    3,  8, 12, 17, 25, 30, 41, 43,  9, 11, 18, 24, 31, 40, 44, 53,
   10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60,
   21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+// the same table by column: byte r of c_izz_col[j] = zigzag position of natural index 8r + j (one 8-byte load per lane
+// instead of eight byte loads at lane-dependent constant addresses, which the constant cache serialises)
+__constant__ unsigned long long c_izz_col[8] = {0x2315140a09030200ull, 0x242216130b080401ull, 0x30252117120c0705ull, 0x312f262018110d06ull, 0x39322e271f19100eull, 0x3a38332d281e1a0full, 0x3e3b37342c291d1bull, 0x3f3d3c36352b2a1cull};
+#ifndef FWD_KZ_PACKED
+#define FWD_KZ_PACKED 0
+#endif
 #define ZZ_LIST \
   X(0,0) X(1,1) X(2,8) X(3,16) X(4,9) X(5,2) X(6,3) X(7,10) X(8,17) X(9,24) X(10,32) X(11,25) X(12,18) X(13,11) X(14,4) X(15,5) \
   X(16,12) X(17,19) X(18,26) X(19,33) X(20,40) X(21,48) X(22,41) X(23,34) X(24,27) X(25,20) X(26,13) X(27,6) X(28,7) X(29,14) X(30,21) X(31,28) \
@@ -356,8 +362,11 @@ __device__ __forceinline__ void deringing_block_float(float *data, int q0, float
 __constant__ double c_aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0, 0.785694958, 0.541196100, 0.275899379};
 
 // DCTM: 0 = JDCT_ISLOW, 1 = JDCT_IFAST, 2 = JDCT_FLOAT (1 and 2: 8-bit only)
+#ifndef FWD_MIN_CTAS
+#define FWD_MIN_CTAS 6
+#endif
 template <int HMAX, int VMAX, int NC, bool QFAST, int PREC, int DCTM>
-__global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *__restrict__ src,
+__global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, const uint8_t *__restrict__ src,
                                                       const QuantTables *__restrict__ qt, int dering,
                                                       DcRec *__restrict__ rec, RecLayout rl, int write_raw)
 {
@@ -571,7 +580,13 @@ __global__ void __launch_bounds__(128, 6) k_forward_tile(Geom g, const uint8_t *
   // zigzag positions of this lane's 8 coefficients (natural index 8r + j)
   int kz[8];
 #pragma unroll
-  for (int r = 0; r < 8; r++) kz[r] = c_izz[8 * r + j];
+  for (int r = 0; r < 8; r++) {
+#if FWD_KZ_PACKED
+    kz[r] = (int)((c_izz_col[j] >> (8 * r)) & 63);
+#else
+    kz[r] = c_izz[8 * r + j];
+#endif
+  }
 #pragma unroll 1
   for (int b = tid >> 3; b < NB; b += 16) {
     const wtype *w = sW + b * 72 + j;
@@ -1112,11 +1127,36 @@ void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s) { k_seed_
 //            (:1211-1222).
 // =====================================================================
 #define TRELLIS_THREADS 128
+// The zero-distortion prefix A[0..63] of a thread's block: TRELLIS_SMEM_A keeps it in shared memory (element i of
+// thread tid at sA[i * TRELLIS_THREADS + tid]: conflict-free for any per-thread index) instead of local memory
+#ifndef TRELLIS_SMEM_A
+#define TRELLIS_SMEM_A 0
+#endif
+#if TRELLIS_SMEM_A
+#define AX(i) ((i) * TRELLIS_THREADS)
+#else
+#define AX(i) (i)
+#endif
+// rate table element type: fp16 (half the shared memory) or fp32 (no conversion in the inner loop)
+#ifndef TRELLIS_RATE_F32
+#define TRELLIS_RATE_F32 0
+#endif
+#if TRELLIS_RATE_F32
+typedef float rate_t;
+#define RATE_F(x) (x)
+#else
+typedef __half rate_t;
+#define RATE_F(x) __half2float(x)
+#endif
 
 // Order the real blocks of every (image, component) by decreasing number of
 // non-zero plain-quantized AC coefficients (counting sort on DcRec.nz), so that
 // the 32 blocks a warp of k_trellis_ac works on have similar trip counts.
-__global__ void __launch_bounds__(256) k_sort_blocks(Geom g, const DcRec *__restrict__ rec, RecLayout rl, uint32_t *__restrict__ perm, uint32_t *__restrict__ splits)
+#ifndef SORT_AGG
+#define SORT_AGG 0
+#endif
+#define SORT_THREADS (SORT_AGG ? 1024 : 256)
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_blocks(Geom g, const DcRec *__restrict__ rec, RecLayout rl, uint32_t *__restrict__ perm, uint32_t *__restrict__ splits)
 {
   __shared__ unsigned cnt[64], start[64];
   const int ci = blockIdx.x % g.nc, img = blockIdx.x / g.nc;
@@ -1126,7 +1166,17 @@ __global__ void __launch_bounds__(256) k_sort_blocks(Geom g, const DcRec *__rest
   uint32_t *p = perm + (size_t)img * rl.per_image + rl.comp_off[ci];
   if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
   __syncthreads();
+#if SORT_AGG
+  // neighbouring blocks mostly fall into the same few bins: one shared-memory atomic per (warp, bin) instead of per block
+  const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) {
+    const unsigned bin = 63 - min((int)r[b].nz, 63);
+    const unsigned peers = __match_any_sync(__activemask(), bin);
+    if ((peers & lt) == 0) atomicAdd(&cnt[bin], (unsigned)__popc(peers));
+  }
+#else
   for (long long b = threadIdx.x; b < nblk; b += blockDim.x) atomicAdd(&cnt[63 - min((int)r[b].nz, 63)], 1u);
+#endif
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned a = 0; for (int k = 0; k < 64; k++) { start[k] = a; a += cnt[k]; }
@@ -1134,11 +1184,23 @@ __global__ void __launch_bounds__(256) k_sort_blocks(Geom g, const DcRec *__rest
     splits[2 * blockIdx.x] = start[63 - 32]; splits[2 * blockIdx.x + 1] = start[63 - 16];
   }
   __syncthreads();
+#if SORT_AGG
+  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) {
+    const unsigned bin = 63 - min((int)r[b].nz, 63);
+    const unsigned peers = __match_any_sync(__activemask(), bin);
+    const int leader = __ffs((int)peers) - 1;
+    unsigned base = 0;
+    if ((int)lane == leader) base = atomicAdd(&start[bin], (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    p[base + __popc(peers & lt)] = (uint32_t)b;
+  }
+#else
   for (long long b = threadIdx.x; b < nblk; b += blockDim.x) { unsigned pos = atomicAdd(&start[63 - min((int)r[b].nz, 63)], 1u); p[pos] = (uint32_t)b; }
+#endif
 }
 void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, uint32_t *splits, int n, cudaStream_t s)
 {
-  k_sort_blocks<<<n * g.nc, 256, 0, s>>>(g, rec, rl, perm, splits);
+  k_sort_blocks<<<n * g.nc, SORT_THREADS, 0, s>>>(g, rec, rl, perm, splits);
   LAUNCHED();
 }
 
@@ -1151,7 +1213,7 @@ void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, ui
 template <int MM>
 __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long long nzmask, const float *A,
                                                      const int16_t *__restrict__ raw16, const int16_t *__restrict__ o16,
-                                                     const __half (*srate)[64], const float *swz, const int *sq8, const unsigned *sqdiv, const int qL,
+                                                     const rate_t (*srate)[64], const float *swz, const int *sq8, const unsigned *sqdiv, const int qL,
                                                      const float lambda, const int maxq, const float azd63, const float eob, const unsigned dc_q)
 {
   int r_pos[MM]; float r_at[MM], r_acc[MM];
@@ -1163,17 +1225,17 @@ __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long 
       // next set bit, ascending (positions past the block's last non-zero read A[63], harmlessly)
       int p = lo ? __ffs((int)lo) - 1 : (hi ? 31 + __ffs((int)hi) : 63);
       if (lo) lo &= lo - 1; else hi &= hi - 1;
-      r_pos[t] = p; r_at[t] = A[p]; r_acc[t] = 0.f; r_rs[t] = 0; r_val[t] = 0;
+      r_pos[t] = p; r_at[t] = A[AX(p)]; r_acc[t] = 0.f; r_rs[t] = 0; r_val[t] = 0;
     }
   }
   int nraw = 0; float nbefore = 0.f;
-  if (m > 0) { nraw = raw16[r_pos[0]]; nbefore = A[r_pos[0] - 1]; }
+  if (m > 0) { nraw = raw16[r_pos[0]]; nbefore = A[AX(r_pos[0] - 1)]; }
 #pragma unroll
   for (int t = 0; t < MM; t++) {
     if (t < m) {
       const int i = r_pos[t];
       const int rawv = nraw; const float Ai1 = nbefore;
-      if (t + 1 < MM && t + 1 < m) { nraw = raw16[r_pos[t + 1]]; nbefore = A[r_pos[t + 1] - 1]; }
+      if (t + 1 < MM && t + 1 < m) { nraw = raw16[r_pos[t + 1]]; nbefore = A[AX(r_pos[t + 1] - 1)]; }
       const int x = abs(rawv);
       const int q = sq8[i];
       const int qv = min((int)(__umulhi((unsigned)(x + (q >> 1)) << 14, sqdiv[i]) >> qL), maxq);      // :1136-1144
@@ -1185,16 +1247,16 @@ __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long 
         const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
         const int delta = cand * q - x;
         const float dist = (float)(delta * delta) * lambda * wl;                   // :1151
-        const __half *rk = &srate[k][i - 1];                                        // rk[-j] = rate for run i-1-j
+        const rate_t *rk = &srate[k][i - 1];                                        // rk[-j] = rate for run i-1-j
         float kb = 1e38f; int ks = 0;
         {
-          float cost = __half2float(rk[0]) + dist;
+          float cost = RATE_F(rk[0]) + dist;
           cost += (Ai1 - 0.0f) + 0.0f;
           if (cost < kb) { kb = cost; ks = 0; }
         }
 #pragma unroll
         for (int s2 = 0; s2 < t; s2++) {
-          float cost = __half2float(rk[-r_pos[s2]]) + dist;
+          float cost = RATE_F(rk[-r_pos[s2]]) + dist;
           cost += (Ai1 - r_at[s2]) + r_acc[s2];
           if (cost < kb) { kb = cost; ks = s2 + 1; }
         }
@@ -1261,7 +1323,7 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
     const long long b0 = (long long)blockIdx.x * blockDim.x;
     if (CLS == 1 ? (b0 >= hi || b0 + blockDim.x <= lo) : (b0 >= lo && b0 + blockDim.x <= hi)) return;
   }
-  __shared__ __half srate[10][64];
+  __shared__ rate_t srate[10][64];
   __shared__ float swz[64];
   __shared__ int sq8[64];
   __shared__ unsigned sqdiv[64];              // exact (|x| + q/2) / q: umulhi((|x| + q/2) << 14, sqdiv[i]) >> qL  (table-uniform shift, like quant_fast)
@@ -1281,7 +1343,11 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
     const int k = e >> 6, run = e & 63;
     const int zrl = acsi[0xF0], cb = acsi[16 * (run & 15) + k + 1];
     const bool skip = cb == 0 || ((run >> 4) && zrl == 0) || run == 63;
+#if TRELLIS_RATE_F32
+    srate[k][run] = skip ? __int_as_float(0x7F800000) : (float)(cb + (k + 1) + (run >> 4) * zrl);
+#else
     srate[k][run] = skip ? __ushort_as_half((unsigned short)0x7C00) : __int2half_rn(cb + (k + 1) + (run >> 4) * zrl);
+#endif
   }
   __syncthreads();
   const long long tix = (long long)blockIdx.x * blockDim.x + tid;
@@ -1310,9 +1376,14 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
     rec[rbase + lin].lambda_dc = lambda * swz[0];
   }
   // phase 1: accumulated zero distortion (zigzag order, serial fp32), every position, to local memory   :1134
+#if TRELLIS_SMEM_A
+  __shared__ float sA[64 * TRELLIS_THREADS];
+  float *A = sA + tid;
+#else
   float A[64];
+#endif
   float azd = 0.0f;
-  A[0] = 0.0f;
+  A[AX(0)] = 0.0f;
   {
     const uint4 *r4 = reinterpret_cast<const uint4 *>(raw16);
 #pragma unroll
@@ -1325,7 +1396,7 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
         if (i == 0) continue;
         const int x = abs((int)(int16_t)((aw[jj >> 1] >> ((jj & 1) * 16)) & 0xFFFF));
         azd = (float)(x * x) * lambda * swz[i] + azd;
-        A[i] = azd;
+        A[AX(i)] = azd;
       }
     }
   }
@@ -1352,7 +1423,7 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
     int r = 0;
     for (unsigned long long mm = nzmask; mm; mm &= mm - 1) {
       const int p = __ffsll((long long)mm) - 1;
-      e_pos[r] = (uint8_t)p; e_at[r] = A[p]; e_before[r] = A[p - 1]; e_qs[r] = (unsigned short)raw16[p]; r++;
+      e_pos[r] = (uint8_t)p; e_at[r] = A[AX(p)]; e_before[r] = A[AX(p - 1)]; e_qs[r] = (unsigned short)raw16[p]; r++;
     }
   }
 
@@ -1375,18 +1446,18 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_a
       const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
       const int delta = cand * q - x;
       const float dist = (float)(delta * delta) * lambda * wl;                   // :1151
-      const __half *rk = &srate[k][i - 1];                                        // rk[-j] = rate for run i-1-j
+      const rate_t *rk = &srate[k][i - 1];                                        // rk[-j] = rate for run i-1-j
       // predecessor "block start" (j = Ss-1): run = i-1, zero tail
       float kb = 1e38f; int ks = 0;
       {
-        float cost = __half2float(rk[0]) + dist;
+        float cost = RATE_F(rk[0]) + dist;
         cost += (Ai1 - 0.0f) + 0.0f;
         if (cost < kb) { kb = cost; ks = 0; }
       }
 #pragma unroll 2
       for (int s2 = 0; s2 < t; s2++) {
         const int j = e_pos[s2];
-        float cost = __half2float(rk[-j]) + dist;
+        float cost = RATE_F(rk[-j]) + dist;
         cost += (Ai1 - e_at[s2]) + e_acc[s2];
         if (cost < kb) { kb = cost; ks = s2 + 1; }
       }
@@ -2020,8 +2091,13 @@ __device__ __forceinline__ void emit_restart_marker(BitSink &sink, const ScanDes
   atomicOr(&mark[byte >> 5], 1u << (byte & 31));
 }
 
+#ifndef ENC_SMEM
+#define ENC_SMEM 0
+#endif
+#define ENC_SMEM_WORDS 4096          // 16 KB: a tile of 256 blocks whose bits fit is assembled in shared memory
 __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
-                                                    const uint32_t *__restrict__ blk_bits, const unsigned long long *__restrict__ tile_base,
+                                                    const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
+                                                    const unsigned long long *__restrict__ tile_base,
                                                     const uint32_t *__restrict__ seg_corr, long long seg_stride,
                                                     uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
                                                     uint32_t *__restrict__ mark, size_t mark_stride_words, const uint32_t *__restrict__ status)
@@ -2032,19 +2108,48 @@ __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const D
   __syncthreads();
   if (status[img] & ~1u) return;            // an earlier stage flagged this image (overflow / bad coefficient)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= sd.nblocks) return;
-  unsigned long long off = tile_base[(size_t)img * gridDim.x + blockIdx.x] + blk_bits[(size_t)img * sd.nblocks + t];
-  if (sd.ri) off += seg_corr[(size_t)img * seg_stride + t / ((long long)sd.ri * sd.bim)];
-  int sci, k; long long mcu;
-  const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
-  int last = prev_dc(g, sd, img, t, sci, mcu, k);
-  const CompGeom &c = g.c[sd.ci[sci]];
-  BitSink sink;
-  sink.buf = bitbuf + (size_t)img * bitbuf_stride_words; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
-  sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
-  walk_seq_block(blk, last, sink);
-  if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
-  sink.finish();
+  const unsigned long long tb = tile_base[(size_t)img * gridDim.x + blockIdx.x];
+  uint32_t *gbuf = bitbuf + (size_t)img * bitbuf_stride_words;
+#if ENC_SMEM
+  // Without restart intervals the tile's 256 blocks emit one contiguous bit range [tb, tb + tile_bits): it is put
+  // together with shared-memory atomics and written out word by word (plain stores; only the two words shared with
+  // the neighbouring tiles go through a global atomic).  Tiles whose bits do not fit take the direct path below.
+  __shared__ uint32_t sbits[ENC_SMEM_WORDS];
+  const unsigned tbits = tile_bits[(size_t)img * gridDim.x + blockIdx.x];
+  const unsigned long long word0 = tb >> 5;
+  const unsigned nwords = (unsigned)(((tb & 31) + tbits + 31) >> 5);
+  const bool staged = !sd.ri && nwords <= ENC_SMEM_WORDS;
+  if (staged) {
+    for (unsigned w = threadIdx.x; w < nwords; w += 256) sbits[w] = 0;
+    __syncthreads();
+  }
+#else
+  const bool staged = false; const unsigned long long word0 = 0; uint32_t *sbits = nullptr; const unsigned nwords = 0;
+#endif
+  if (t < sd.nblocks) {
+    unsigned long long off = tb + blk_bits[(size_t)img * sd.nblocks + t];
+    if (sd.ri) off += seg_corr[(size_t)img * seg_stride + t / ((long long)sd.ri * sd.bim)];
+    int sci, k; long long mcu;
+    const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+    int last = prev_dc(g, sd, img, t, sci, mcu, k);
+    const CompGeom &c = g.c[sd.ci[sci]];
+    BitSink sink;
+    sink.buf = staged ? sbits : gbuf; sink.widx = (off >> 5) - (staged ? word0 : 0ull); sink.acc = 0; sink.nacc = (int)(off & 31);
+    sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
+    walk_seq_block(blk, last, sink);
+    if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
+    sink.finish();
+  }
+#if ENC_SMEM
+  if (staged) {
+    __syncthreads();
+    for (unsigned w = threadIdx.x; w < nwords; w += 256) {
+      const uint32_t v = sbits[w];
+      if (!v) continue;                                   // the stream buffer starts out zeroed
+      if (w == 0 || w == nwords - 1) atomicOr(&gbuf[word0 + w], v); else gbuf[word0 + w] = v;
+    }
+  }
+#endif
 }
 
 // byte stuffing (jchuff.c:386-435 emit byte / 0xFF00) + final 1-bit padding
@@ -2602,13 +2707,13 @@ void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint
   LAUNCHED();
 }
 void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, int progressive,
-                   const uint32_t *blk_bits, const unsigned long long *tile_base, const uint32_t *seg_corr, long long seg_stride,
+                   const uint32_t *blk_bits, const uint32_t *tile_bits, const unsigned long long *tile_base, const uint32_t *seg_corr, long long seg_stride,
                    const uint32_t *blk_aux, const uint32_t *run_e,
                    uint32_t *bitbuf, size_t bitbuf_stride_words, uint32_t *mark, size_t mark_stride_words, const uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
   if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
-  else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
+  else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
   LAUNCHED();
 }
 size_t stuff_tiles(size_t bitbuf_stride_words) { return (bitbuf_stride_words + STUFF_TILE_WORDS - 1) / STUFF_TILE_WORDS; }
