@@ -6,7 +6,7 @@
  * it takes over the calls that bracket the encode hot path,
  *
  *     jpeg_start_compress      (jcapistd.c:44-70)
- *     jpeg_write_scanlines     (jcapistd.c:90-135)
+ *     jpeg_write_scanlines     (jcapistd.c:90-135; jpeg12_write_scanlines for 12-bit samples)
  *     jpeg_write_raw_data      (jcapistd.c:145-195; under tj3CompressFromYUV*)
  *     jpeg_write_coefficients  (jctrans.c:39-66; the encode half of jpegtran)
  *     jpeg_finish_compress     (jcapimin.c:176-229)
@@ -19,8 +19,8 @@
  * binary, in tests/test_libjpeg_shim.py) produces its files on the GPU.
  *
  * Parameter sets the device path does not cover (B200JPEG_ERR_UNSUPPORTED from
- * b200jpeg_start_compress: JDCT_IFAST, smoothing, arithmetic coding, raw data,
- * 12-bit through this 8-bit entry point, ...) and hosts without a CUDA device fall through to the reference's
+ * b200jpeg_start_compress: arithmetic coding, lossless, the optional trellis modes, abbreviated
+ * datastreams, ...) and hosts without a CUDA device fall through to the reference's
  * implementation of the same three functions (dlsym RTLD_NEXT): that is the
  * REFERENCE running, not a CPU path of this library.  B200_SHIM_VERBOSE=1
  * reports on stderr which path an image took; B200_SHIM_REQUIRE=1 turns a
@@ -122,7 +122,8 @@ static int fill_params(j_compress_ptr cinfo, boolean write_all_tables, b200jpeg_
   int i, ci;
   memset(p, 0, sizeof(*p));
   if (!write_all_tables) return 0;                       /* abbreviated datastreams: reference only */
-  if (cinfo->data_precision != 8 || cinfo->arith_code || cinfo->master->lossless) return 0;
+  if ((cinfo->data_precision != 8 && cinfo->data_precision != 12) || cinfo->arith_code || cinfo->master->lossless) return 0;
+  if (cinfo->data_precision == 12 && cinfo->raw_data_in) return 0;   /* jpeg12_write_raw_data: reference only */
   if (cinfo->num_components > B200JPEG_MAX_COMPONENTS || cinfo->num_scans > B200JPEG_MAX_SCANS) return 0;
   switch (cinfo->in_color_space) {
   case JCS_GRAYSCALE: p->in_color_space = B200JPEG_CS_GRAYSCALE; break;
@@ -266,12 +267,9 @@ jpeg_write_raw_data(j_compress_ptr cinfo, JSAMPIMAGE data, JDIMENSION num_lines)
   return lines_per_iMCU_row;
 }
 
-GLOBAL(JDIMENSION)
-jpeg_write_scanlines(j_compress_ptr cinfo, JSAMPARRAY scanlines, JDIMENSION num_lines)
+static JDIMENSION device_write_scanlines(j_compress_ptr cinfo, int slot, const uint8_t *const *rows, JDIMENSION num_lines, int precision)
 {
-  static write_fn real;
-  int slot = find_active(cinfo);
-  if (slot < 0) { if (!real) real = (write_fn)next_sym("jpeg_write_scanlines"); return real(cinfo, scanlines, num_lines); }
+  if (cinfo->data_precision != precision) ERREXIT1(cinfo, JERR_BAD_PRECISION, cinfo->data_precision);   /* jcapistd.c:97-98 */
   if (cinfo->global_state != CSTATE_SCANNING) ERREXIT1(cinfo, JERR_BAD_STATE, cinfo->global_state);
   if (cinfo->next_scanline >= cinfo->image_height) WARNMS(cinfo, JWRN_TOO_MUCH_DATA);   /* jcapistd.c:103-104 */
   if (cinfo->progress != NULL) {                                                         /* jcapistd.c:107-111 */
@@ -279,10 +277,30 @@ jpeg_write_scanlines(j_compress_ptr cinfo, JSAMPARRAY scanlines, JDIMENSION num_
     cinfo->progress->pass_limit = (long)cinfo->image_height;
     (*cinfo->progress->progress_monitor) ((j_common_ptr)cinfo);
   }
-  int took = b200jpeg_write_scanlines(g_active[slot].enc, (const uint8_t *const *)scanlines, (int)num_lines);
+  int took = b200jpeg_write_scanlines(g_active[slot].enc, rows, (int)num_lines);
   if (took < 0) ERREXIT1(cinfo, JERR_BAD_STATE, cinfo->global_state);
   cinfo->next_scanline += (JDIMENSION)took;
   return (JDIMENSION)took;
+}
+
+GLOBAL(JDIMENSION)
+jpeg_write_scanlines(j_compress_ptr cinfo, JSAMPARRAY scanlines, JDIMENSION num_lines)
+{
+  static write_fn real;
+  int slot = find_active(cinfo);
+  if (slot < 0) { if (!real) real = (write_fn)next_sym("jpeg_write_scanlines"); return real(cinfo, scanlines, num_lines); }
+  return device_write_scanlines(cinfo, slot, (const uint8_t *const *)scanlines, num_lines, 8);
+}
+
+/* 12-bit samples (J12SAMPLE = short): same entry point, rows of uint16 (jcapistd.c compiled with BITS_IN_JSAMPLE 12) */
+typedef JDIMENSION (*write12_fn)(j_compress_ptr, J12SAMPARRAY, JDIMENSION);
+GLOBAL(JDIMENSION)
+jpeg12_write_scanlines(j_compress_ptr cinfo, J12SAMPARRAY scanlines, JDIMENSION num_lines)
+{
+  static write12_fn real;
+  int slot = find_active(cinfo);
+  if (slot < 0) { if (!real) real = (write12_fn)next_sym("jpeg12_write_scanlines"); return real(cinfo, scanlines, num_lines); }
+  return device_write_scanlines(cinfo, slot, (const uint8_t *const *)scanlines, num_lines, 12);
 }
 
 /* hand the finished datastream to the application's destination manager (jpeglib.h:897-904) */

@@ -2597,7 +2597,8 @@ __global__ void __launch_bounds__(256) k_block_bits_prog(Geom g, ScanDesc sd, co
 
 __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
                                                      const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
-                                                     const uint32_t *__restrict__ blk_bits, const unsigned long long *__restrict__ tile_base,
+                                                     const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
+                                                     const unsigned long long *__restrict__ tile_base,
                                                      const uint32_t *__restrict__ seg_corr, long long seg_stride,
                                                      uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
                                                      uint32_t *__restrict__ mark, size_t mark_stride_words, const uint32_t *__restrict__ status)
@@ -2609,20 +2610,47 @@ __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const 
   __syncthreads();
   if (status[img] & ~1u) return;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= sd.nblocks) return;
-  unsigned long long off = tile_base[(size_t)img * gridDim.x + blockIdx.x] + blk_bits[(size_t)img * sd.nblocks + t];
-  if (sd.ri) off += seg_corr[(size_t)img * seg_stride + t / ((long long)sd.ri * sd.bim)];
-  int sci, k; long long mcu;
-  const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
-  int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
-  const CompGeom &c = g.c[sd.ci[sci]];
-  BitSinkP sink;
-  sink.buf = bitbuf + (size_t)img * bitbuf_stride_words; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
-  sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
-  unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
-  walk_prog_block(blk, sd, last, a, re, sink);
-  if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
-  sink.finish();
+  const unsigned long long tb = tile_base[(size_t)img * gridDim.x + blockIdx.x];
+  uint32_t *gbuf = bitbuf + (size_t)img * bitbuf_stride_words;
+#if ENC_SMEM
+  // same staging as k_encode_seq: the tile's contiguous bit range is assembled in shared memory
+  __shared__ uint32_t sbits[ENC_SMEM_WORDS];
+  const unsigned tbits = tile_bits[(size_t)img * gridDim.x + blockIdx.x];
+  const unsigned long long word0 = tb >> 5;
+  const unsigned nwords = (unsigned)(((tb & 31) + tbits + 31) >> 5);
+  const bool staged = !sd.ri && nwords <= ENC_SMEM_WORDS;
+  if (staged) {
+    for (unsigned w = threadIdx.x; w < nwords; w += 256) sbits[w] = 0;
+    __syncthreads();
+  }
+#else
+  const bool staged = false; const unsigned long long word0 = 0; uint32_t *sbits = nullptr; const unsigned nwords = 0;
+#endif
+  if (t < sd.nblocks) {
+    unsigned long long off = tb + blk_bits[(size_t)img * sd.nblocks + t];
+    if (sd.ri) off += seg_corr[(size_t)img * seg_stride + t / ((long long)sd.ri * sd.bim)];
+    int sci, k; long long mcu;
+    const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+    int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
+    const CompGeom &c = g.c[sd.ci[sci]];
+    BitSinkP sink;
+    sink.buf = staged ? sbits : gbuf; sink.widx = (off >> 5) - (staged ? word0 : 0ull); sink.acc = 0; sink.nacc = (int)(off & 31);
+    sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
+    unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
+    walk_prog_block(blk, sd, last, a, re, sink);
+    if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
+    sink.finish();
+  }
+#if ENC_SMEM
+  if (staged) {
+    __syncthreads();
+    for (unsigned w = threadIdx.x; w < nwords; w += 256) {
+      const uint32_t v = sbits[w];
+      if (!v) continue;
+      if (w == 0 || w == nwords - 1) atomicOr(&gbuf[word0 + w], v); else gbuf[word0 + w] = v;
+    }
+  }
+#endif
 }
 
 
@@ -2712,7 +2740,7 @@ void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_
                    uint32_t *bitbuf, size_t bitbuf_stride_words, uint32_t *mark, size_t mark_stride_words, const uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
+  if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
   else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
   LAUNCHED();
 }

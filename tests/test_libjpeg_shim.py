@@ -155,3 +155,23 @@ def test_turbojpeg_api_runs_on_the_device(opts, tmp_path):
         assert len(jpgs) == 1, os.listdir(d)
         outs.append((d / jpgs[0]).read_bytes())
     assert outs[0] == outs[1] and len(outs[0]) > 100
+
+
+@need_files
+@pytest.mark.gpu
+@pytest.mark.parametrize("sw", [["-precision", "12", "-quality", "75", "-notrellis", "-noovershoot", "-baseline"],
+                                ["-precision", "12", "-quality", "85", "-notrellis", "-noovershoot", "-fastcrush", "-sample", "1x1"]],
+                         ids=lambda s: "_".join(x.lstrip("-") for x in s))
+def test_reference_cjpeg_12bit_runs_on_the_device(sw, tmp_path):
+    """12-bit samples reach the library through jpeg12_write_scanlines (rows of J12SAMPLE = short)."""
+    from mozjpeg_b200.synth import synth_image12
+    im = synth_image12(5, 200, 136)
+    ppm = tmp_path / "in12.ppm"
+    ppm.write_bytes(b"P6\n200 136\n4095\n" + im.astype(">u2").tobytes())
+    out = tmp_path / "o.jpg"
+    env = dict(os.environ, LD_PRELOAD=SHIM, B200_SHIM_VERBOSE="1", B200_SHIM_REQUIRE="1")
+    r = subprocess.run([CJPEG, *sw, "-outfile", str(out), str(ppm)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "device path" in r.stderr, r.stderr
+    plain = subprocess.run([CJPEG, *sw, str(ppm)], capture_output=True, timeout=300)
+    assert plain.returncode == 0 and out.read_bytes() == plain.stdout
