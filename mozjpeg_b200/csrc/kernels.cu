@@ -362,6 +362,9 @@ __device__ __forceinline__ void deringing_block_float(float *data, int q0, float
 __constant__ double c_aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0, 0.785694958, 0.541196100, 0.275899379};
 
 // DCTM: 0 = JDCT_ISLOW, 1 = JDCT_IFAST, 2 = JDCT_FLOAT (1 and 2: 8-bit only)
+#ifndef FWD_MASK_SQ
+#define FWD_MASK_SQ 0
+#endif
 #ifndef FWD_MIN_CTAS
 #define FWD_MIN_CTAS 6
 #endif
@@ -651,9 +654,11 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
       sR[b * 64 + k] = (int16_t)dd[r];
       // the trellis derives its entries from the RAW coefficient (qval = (|x| + q/2) / q, jcdctmgr.c:1136); with the
       // integer DCT that is the plain-quantized value, with the float DCT it can differ from quantize_float's result
-      bool nzv = qv != 0;
-      if (DCTM != 0 && rec) { const int dq = (int)qt->q[g.c[ci].qt][nat].d; nzv = abs(dd[r]) >= dq - dq / 2; }
-      if (nzv && nat != 0) { if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
+      if (!(FWD_MASK_SQ && DCTM == 0)) {
+        bool nzv = qv != 0;
+        if (DCTM != 0 && rec) { const int dq = (int)qt->q[g.c[ci].qt][nat].d; nzv = abs(dd[r]) >= dq - dq / 2; }
+        if (nzv && nat != 0) { if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
+      }
     }
     if (PREC == 8 && rec) {
       // the raw coefficients go back to sW in natural order (each lane rewrites exactly the words it read) for
@@ -663,10 +668,27 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
       int16_t *ww = blk16 + j;
 #pragma unroll
       for (int r = 0; r < 8; r++) ww[8 * r] = (int16_t)dd[r];
+      if (FWD_MASK_SQ && DCTM == 0) {
+        // integer DCT: the mask is "which of the block's 64 staged (zigzag-ordered) values are non-zero"; lane j tests
+        // the 8 values at positions 8j..8j+7 (two per 32-bit word) and stores its byte of the 64-bit mask
+        __syncwarp();
+        const uint4 zq = *reinterpret_cast<const uint4 *>(sQ + b * 64 + 8 * j);
+        const unsigned zw[4] = {zq.x, zq.y, zq.z, zq.w};
+        unsigned m8 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const unsigned nz = (((zw[i] & 0x7FFF7FFFu) + 0x7FFF7FFFu) | zw[i]) & 0x80008000u;   // bit 15 / 31: low / high half non-zero
+          const unsigned t2 = nz >> 15;
+          m8 |= ((t2 | (t2 >> 15)) & 3u) << (2 * i);
+        }
+        if (j == 0) m8 &= ~1u;                                   // position 0 is the DC value
+        reinterpret_cast<uint8_t *>(&sMask[b])[j] = (uint8_t)m8;
+      } else {
       mlo |= __shfl_xor_sync(0xffffffffu, mlo, 1); mhi |= __shfl_xor_sync(0xffffffffu, mhi, 1);
       mlo |= __shfl_xor_sync(0xffffffffu, mlo, 2); mhi |= __shfl_xor_sync(0xffffffffu, mhi, 2);
       mlo |= __shfl_xor_sync(0xffffffffu, mlo, 4); mhi |= __shfl_xor_sync(0xffffffffu, mhi, 4);
       if (j == 0) sMask[b] = make_uint2(mlo, mhi);
+      }
     }
   }
   __syncthreads();
@@ -941,10 +963,24 @@ __device__ __forceinline__ void walk_seq_block(const int16_t *__restrict__ blk, 
 // ---------------------------------------------------------------------
 // statistics pass (encode_mcu_gather, jchuff.c:886-915)
 // ---------------------------------------------------------------------
+#ifndef HIST_AGG
+#define HIST_AGG 0
+#endif
+// shared-memory histogram increment; HIST_AGG: the lanes of a warp that hit the same counter send one atomic
+__device__ __forceinline__ void hist_inc(unsigned *addr)
+{
+#if HIST_AGG
+  const unsigned peers = __match_any_sync(__activemask(), (unsigned)(size_t)addr);
+  const unsigned lane = threadIdx.x & 31;
+  if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(addr, (unsigned)__popc(peers));
+#else
+  atomicAdd(addr, 1u);
+#endif
+}
 struct HistSink {
   unsigned *dc_hist, *ac_hist; int bad; int maxbits;        // maxbits = data_precision + 2 (jchuff.c:819,836,865)
-  __device__ void dc(int nb, int) { if (nb > maxbits + 1) bad = 1; atomicAdd(&dc_hist[nb], 1u); }
-  __device__ void ac(int sym, int nb, int) { if (nb > maxbits) bad = 1; atomicAdd(&ac_hist[sym], 1u); }
+  __device__ void dc(int nb, int) { if (nb > maxbits + 1) bad = 1; hist_inc(&dc_hist[nb]); }
+  __device__ void ac(int sym, int nb, int) { if (nb > maxbits) bad = 1; hist_inc(&ac_hist[sym]); }
 };
 
 __global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
@@ -1127,6 +1163,12 @@ void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s) { k_seed_
 //            (:1211-1222).
 // =====================================================================
 #define TRELLIS_THREADS 128
+#ifndef TRELLIS_ILP4
+#define TRELLIS_ILP4 0
+#endif
+#ifndef TRELLIS_MIN_CTAS
+#define TRELLIS_MIN_CTAS 5           // register cap of the common class: 5 CTAs x 128 threads -> 96 registers
+#endif
 // The zero-distortion prefix A[0..63] of a thread's block: TRELLIS_SMEM_A keeps it in shared memory (element i of
 // thread tid at sA[i * TRELLIS_THREADS + tid]: conflict-free for any per-thread index) instead of local memory
 #ifndef TRELLIS_SMEM_A
@@ -1254,12 +1296,32 @@ __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long 
           cost += (Ai1 - 0.0f) + 0.0f;
           if (cost < kb) { kb = cost; ks = 0; }
         }
+#if TRELLIS_ILP4
+        // predecessors four at a time: the four costs are independent (loads and adds overlap), then a first-minimum
+        // tree (a later element wins only if strictly smaller) - the same (value, index) the sequential scan keeps
+#pragma unroll
+        for (int s0 = 0; s0 < t; s0 += 4) {
+          float cc[4]; 
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            cc[u] = 1e38f;
+            if (s0 + u < t) { cc[u] = RATE_F(rk[-r_pos[s0 + u]]) + dist; cc[u] += (Ai1 - r_at[s0 + u]) + r_acc[s0 + u]; }
+          }
+          float m01 = cc[0]; int i01 = 0; if (s0 + 1 < t && cc[1] < m01) { m01 = cc[1]; i01 = 1; }
+          if (s0 + 2 < t) {
+            float m23 = cc[2]; int i23 = 2; if (s0 + 3 < t && cc[3] < m23) { m23 = cc[3]; i23 = 3; }
+            if (m23 < m01) { m01 = m23; i01 = i23; }
+          }
+          if (m01 < kb) { kb = m01; ks = s0 + i01 + 1; }
+        }
+#else
 #pragma unroll
         for (int s2 = 0; s2 < t; s2++) {
           float cost = RATE_F(rk[-r_pos[s2]]) + dist;
           cost += (Ai1 - r_at[s2]) + r_acc[s2];
           if (cost < kb) { kb = cost; ks = s2 + 1; }
         }
+#endif
         if (kb < best || (kb == best && ks < best_s)) { best = kb; best_s = ks; best_k = k; }
       }
       r_acc[t] = best; r_rs[t] = best_s;
@@ -1310,7 +1372,7 @@ __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long 
 // k_sort_blocks).  CLS 1: 17 <= m <= 32, register path with 32 entries.  CLS 0: everything else -- warps
 // whose blocks all have m <= 16 take the 16-entry register path, the others (m > 32) the generic loops.
 template <int CLS>
-__global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : 5) k_trellis_ac(Geom g, const TrellisConsts *__restrict__ tc,
+__global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : TRELLIS_MIN_CTAS) k_trellis_ac(Geom g, const TrellisConsts *__restrict__ tc,
                                                                    const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
                                                                    DcRec *__restrict__ rec, RecLayout rl, const uint32_t *__restrict__ perm,
                                                                    const uint32_t *__restrict__ splits)
