@@ -331,3 +331,51 @@ def read_ppm(data: bytes) -> Tuple[int, int, int, bytes]:
         raise ValueError("only binary 8-bit PGM/PPM supported")
     nc = 3 if magic == b"P6" else 1
     return w, h, nc, data[pos:pos + w * h * nc]
+
+
+def main(argv: Sequence[str] = None) -> int:
+    """``python -m mozjpeg_b200.cjpeg [switches] [-outfile name] file.ppm [more.ppm ...]`` - cjpeg's command line on
+    the device path.  Several input files of one size are encoded as one batch (outputs: <input>.jpg)."""
+    import sys
+    import numpy as np
+    from . import Encoder
+    args = list(sys.argv[1:] if argv is None else argv)
+    outfile = None
+    switches: List[str] = []
+    files: List[str] = []
+    takes_arg = ("dct", "lambda1", "lambda2", "dc-scan-opt", "precision", "quality", "qslots", "qtables", "scans", "quant-table",
+                 "restart", "sample", "smooth", "trellis-dc-ver-weight")
+    i = 0
+    while i < len(args):
+        a = args[i]
+        if a.startswith("-") and len(a) > 1:
+            if _keymatch(a[1:], "outfile", 4):
+                outfile = args[i + 1]; i += 2; continue
+            switches.append(a)
+            if any(_keymatch(a[1:], k, 2 if k not in ("quality", "restart") else 1) for k in takes_arg) and not _keymatch(a[1:], "quant-baseline", 7):
+                switches.append(args[i + 1]); i += 1
+        else:
+            files.append(a)
+        i += 1
+    if not files:
+        print("usage: python -m mozjpeg_b200.cjpeg [switches] [-outfile name] file.ppm [more.ppm ...]", file=sys.stderr)
+        return 2
+    imgs = []
+    for f in files:
+        w, h, nc, data = read_ppm(open(f, "rb").read())
+        imgs.append(np.frombuffer(data, dtype=np.uint8).reshape(h, w, nc))
+    if len({im.shape for im in imgs}) != 1:
+        print("all input files of one call must have the same size", file=sys.stderr)
+        return 2
+    h, w, nc = imgs[0].shape
+    p = params_from_switches(switches, w, h, nc)
+    out = Encoder(0).encode_batch(p, np.stack(imgs))
+    for f, jpg in zip(files, out):
+        name = outfile if (outfile and len(files) == 1) else f.rsplit(".", 1)[0] + ".jpg"
+        with open(name, "wb") as fo:
+            fo.write(jpg)
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

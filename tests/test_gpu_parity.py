@@ -262,3 +262,25 @@ def test_incompressible_input_grows_the_output_buffers(built):
         enc.close()
     for i in range(3):
         assert out[i] == O.oracle_encode(p, img[i]).jpeg
+
+
+@pytest.mark.gpu
+def test_command_line_front_end(tmp_path):
+    """python -m mozjpeg_b200.cjpeg: cjpeg's command line on the device path, one file and a batch of files."""
+    import shutil
+    import subprocess
+    import sys
+    from common import GOLD, ROOT
+    sw = ["-quality", "75"]
+    want = next(c for c in CASES if c["image"] == "testorig" and c["switches"] == sw)
+    out = tmp_path / "o.jpg"
+    r = subprocess.run([sys.executable, "-m", "mozjpeg_b200.cjpeg", *sw, "-outfile", str(out), os.path.join(GOLD, "testorig.ppm")],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert md5(out.read_bytes()) == want["md5"]
+    for i in range(3):
+        shutil.copyfile(os.path.join(GOLD, "testorig.ppm"), tmp_path / f"in{i}.ppm")
+    r = subprocess.run([sys.executable, "-m", "mozjpeg_b200.cjpeg", *sw, *[str(tmp_path / f"in{i}.ppm") for i in range(3)]],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert all(md5((tmp_path / f"in{i}.jpg").read_bytes()) == want["md5"] for i in range(3))
