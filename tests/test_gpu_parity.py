@@ -9,6 +9,7 @@ the reference's bytes.
   recorded 1920x1080 md5s.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
