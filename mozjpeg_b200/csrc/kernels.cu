@@ -960,6 +960,49 @@ __device__ __forceinline__ void walk_seq_block(const int16_t *__restrict__ blk, 
   if (r > 0) sink.ac(0, 0, 0);
 }
 
+#ifndef SEQ_SPARSE_ENC
+#define SEQ_SPARSE_ENC 0
+#endif
+// Zigzag positions of a scan-order block's non-zero AC coefficients, from the side records (the AC trellis leaves the
+// final ones there); dummy blocks have none.
+__device__ __forceinline__ unsigned long long block_nzmask(const Geom &g, const ScanDesc &sd, const DcRec *__restrict__ rec, const RecLayout &rl,
+                                                           int img, int sci, long long mcu, int k)
+{
+  const int ci = sd.ci[sci];
+  const CompGeom &c = g.c[ci];
+  const long long mrow = mcu / sd.per_row; const int mcol = (int)(mcu - mrow * sd.per_row);
+  const int mh = sd.ncomps == 1 ? 1 : c.v, mw = sd.ncomps == 1 ? 1 : c.h;
+  const long long row = mrow * mh + sd.k_y[k]; const int col = mcol * mw + sd.k_x[k];
+  return (row < c.hib && col < c.wib) ? rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * c.wib + col].nzmask : 0ull;
+}
+// walk_seq_block for a block whose non-zero positions are known: touches only those coefficients
+template <class Sink>
+__device__ __forceinline__ void walk_seq_sparse(const int16_t *__restrict__ blk, unsigned long long mask, int last_dc, Sink &sink)
+{
+  if (mask & 0xFFFF0000ull) asm volatile("prefetch.global.L1 [%0];" :: "l"(blk + 16));
+  if (mask & 0xFFFF00000000ull) asm volatile("prefetch.global.L1 [%0];" :: "l"(blk + 32));
+  if (mask >> 48) asm volatile("prefetch.global.L1 [%0];" :: "l"(blk + 48));
+  {
+    int temp = (int)blk[0] - last_dc, temp2 = temp;
+    if (temp < 0) { temp = -temp; temp2--; }
+    sink.dc(nbits_of(temp), temp2);
+  }
+  int prev = 0;
+  while (mask) {
+    const int pos = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
+    const int val = blk[pos];
+    if (val == 0) continue;                              // a superset mask is fine
+    int r = pos - prev - 1; prev = pos;
+    while (r > 15) { sink.ac(0xF0, 0, 0); r -= 16; }
+    int temp = val, temp2 = val;
+    if (temp < 0) { temp = -temp; temp2--; }
+    const int nb = nbits_of(temp);
+    sink.ac((r << 4) + nb, nb, temp2);
+  }
+  if (prev != 63) sink.ac(0, 0, 0);
+}
+
 // ---------------------------------------------------------------------
 // statistics pass (encode_mcu_gather, jchuff.c:886-915)
 // ---------------------------------------------------------------------
@@ -1256,7 +1299,7 @@ template <int MM>
 __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long long nzmask, const float *A,
                                                      const int16_t *__restrict__ raw16, const int16_t *__restrict__ o16,
                                                      const rate_t (*srate)[64], const float *swz, const int *sq8, const unsigned *sqdiv, const int qL,
-                                                     const float lambda, const int maxq, const float azd63, const float eob, const unsigned dc_q)
+                                                     const float lambda, const int maxq, const float azd63, const float eob, const unsigned dc_q, unsigned long long &final_mask)
 {
   int r_pos[MM]; float r_at[MM], r_acc[MM];
   int r_rs[MM], r_val[MM];
@@ -1349,10 +1392,12 @@ __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long 
   q4[0] = make_uint4(dc_q, 0, 0, 0);
 #pragma unroll
   for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
+  unsigned long long fm = 0;
 #pragma unroll
   for (int t = MM - 1; t >= 0; t--) {
-    if (t + 1 == last) { o[r_pos[t]] = (int16_t)r_val[t]; last = r_rs[t]; }
+    if (t + 1 == last) { o[r_pos[t]] = (int16_t)r_val[t]; if (SEQ_SPARSE_ENC && r_val[t]) fm |= 1ull << r_pos[t]; last = r_rs[t]; }
   }
+  final_mask = fm;
 }
 
 // Shared memory per CTA: the rate table of the CTA's (image, component)
@@ -1430,7 +1475,7 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : TRELLIS_MIN_CT
   {
     DcRec rr = rec[rbase + lin];
     nzmask = rr.nzmask;
-    const int mcls = __popcll(nzmask);
+    const int mcls = rr.nz;                                   // K1's count (the mask itself is replaced by the final one below)
     if ((CLS == 1) != (mcls > 16 && mcls <= 32)) return;      // the other class's block
     float norm = (float)((double)rr.lambda_dc / 63.0);
     if (tc->use_norm) lambda = (float)(tc->p1 / (tc->p2 + (double)norm));
@@ -1466,13 +1511,15 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : TRELLIS_MIN_CT
   const int maxq = (1 << tc->max_coef_bits) - 1;
   const int m = __popcll(nzmask);
   const int qL = sqL;
+  unsigned long long fmask = 0;                  // SEQ_SPARSE_ENC: positions that stay non-zero, for the sequential bit packer
 
-  if (CLS == 1) { trellis_entries_regs<32>(m, nzmask, A, raw16, o16, srate, swz, sq8, sqdiv, qL, lambda, maxq, azd63, (float)acsi[0], dc_q); return; }
+  if (CLS == 1) { trellis_entries_regs<32>(m, nzmask, A, raw16, o16, srate, swz, sq8, sqdiv, qL, lambda, maxq, azd63, (float)acsi[0], dc_q, fmask); if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fmask; return; }
   // warps whose blocks all have few non-zero positions take the register path
   {
     const int mmax = __reduce_max_sync(__activemask(), m);
     if (mmax <= 16) {
-      trellis_entries_regs<16>(m, nzmask, A, raw16, o16, srate, swz, sq8, sqdiv, qL, lambda, maxq, azd63, (float)acsi[0], dc_q);
+      trellis_entries_regs<16>(m, nzmask, A, raw16, o16, srate, swz, sq8, sqdiv, qL, lambda, maxq, azd63, (float)acsi[0], dc_q, fmask);
+      if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fmask;
       return;
     }
   }
@@ -1549,9 +1596,12 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : TRELLIS_MIN_CT
     const int qs = e_qs[t], qv = qs & 0x7FFF, nc = nbits_of(qv), k = e_k[t];
     const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
     const int sgn = -(qs >> 15);
-    o16[e_pos[t]] = (int16_t)((cand ^ sgn) - sgn);
+    const int outv = (cand ^ sgn) - sgn;
+    o16[e_pos[t]] = (int16_t)outv;
+    if (SEQ_SPARSE_ENC && outv) fmask |= 1ull << e_pos[t];
     last = e_rs[t];
   }
+  if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fmask;
 }
 
 void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
@@ -2157,7 +2207,7 @@ __device__ __forceinline__ void emit_restart_marker(BitSink &sink, const ScanDes
 #define ENC_SMEM 0
 #endif
 #define ENC_SMEM_WORDS 4096          // 16 KB: a tile of 256 blocks whose bits fit is assembled in shared memory
-__global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
+__global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ rec, RecLayout rl, const DevHuff *__restrict__ tabs, size_t stride,
                                                     const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
                                                     const unsigned long long *__restrict__ tile_base,
                                                     const uint32_t *__restrict__ seg_corr, long long seg_stride,
@@ -2198,7 +2248,8 @@ __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const D
     BitSink sink;
     sink.buf = staged ? sbits : gbuf; sink.widx = (off >> 5) - (staged ? word0 : 0ull); sink.acc = 0; sink.nacc = (int)(off & 31);
     sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
-    walk_seq_block(blk, last, sink);
+    if (SEQ_SPARSE_ENC && rec) walk_seq_sparse(blk, block_nzmask(g, sd, rec, rl, img, sci, mcu, k), last, sink);
+    else walk_seq_block(blk, last, sink);
     if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
     sink.finish();
   }
@@ -2796,14 +2847,14 @@ void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint
   k_scan_layout<<<n, 256, 0, s>>>(sd, blk_bits, tile_bits, ntiles, tile_base, seg_corr, seg_stride, total_bits, capacity_bits, status);
   LAUNCHED();
 }
-void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, int progressive,
+void launch_encode(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t stride, int progressive,
                    const uint32_t *blk_bits, const uint32_t *tile_bits, const unsigned long long *tile_base, const uint32_t *seg_corr, long long seg_stride,
                    const uint32_t *blk_aux, const uint32_t *run_e,
                    uint32_t *bitbuf, size_t bitbuf_stride_words, uint32_t *mark, size_t mark_stride_words, const uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
   if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
-  else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
+  else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, rl, tabs, stride, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
   LAUNCHED();
 }
 size_t stuff_tiles(size_t bitbuf_stride_words) { return (bitbuf_stride_words + STUFF_TILE_WORDS - 1) / STUFF_TILE_WORDS; }

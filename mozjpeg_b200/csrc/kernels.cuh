@@ -133,7 +133,8 @@ void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint
                         uint32_t *seg_corr, long long seg_stride, unsigned long long *total_bits, size_t capacity_bits,
                         uint32_t *status, int n, cudaStream_t s);
 // mark: bitmap over the unstuffed bytes of each image (restart markers' 0xFF), only touched when sd.ri != 0
-void launch_encode(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
+// nz_rec: the side records holding every block's final non-zero positions (trellis on, sequential scans), or nullptr
+void launch_encode(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
                    const uint32_t *blk_bits, const uint32_t *tile_bits, const unsigned long long *tile_base, const uint32_t *seg_corr, long long seg_stride,
                    const uint32_t *blk_aux, const uint32_t *run_e,
                    uint32_t *bitbuf, size_t bitbuf_image_stride_words, uint32_t *mark, size_t mark_stride_words, const uint32_t *status, int n, cudaStream_t s);
