@@ -960,6 +960,36 @@ __device__ __forceinline__ void walk_seq_block(const int16_t *__restrict__ blk, 
   if (r > 0) sink.ac(0, 0, 0);
 }
 
+// walk_seq_block on a block already held in registers (eight 16-byte quarters, zigzag order)
+template <class Sink>
+__device__ __forceinline__ void walk_seq_regs(const uint4 (&b4)[8], int last_dc, Sink &sink)
+{
+  int r = 0;
+#pragma unroll
+  for (int v = 0; v < 8; v++) {
+    const unsigned w[4] = {b4[v].x, b4[v].y, b4[v].z, b4[v].w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      int val = (int)(int16_t)((w[j >> 1] >> ((j & 1) * 16)) & 0xFFFF);
+      if (v == 0 && j == 0) {
+        int temp = val - last_dc, temp2 = temp;
+        if (temp < 0) { temp = -temp; temp2--; }
+        sink.dc(nbits_of(temp), temp2);
+      } else if (val == 0) {
+        r++;
+      } else {
+        while (r > 15) { sink.ac(0xF0, 0, 0); r -= 16; }
+        int temp = val, temp2 = val;
+        if (temp < 0) { temp = -temp; temp2--; }
+        int nb = nbits_of(temp);
+        sink.ac((r << 4) + nb, nb, temp2);
+        r = 0;
+      }
+    }
+  }
+  if (r > 0) sink.ac(0, 0, 0);
+}
+
 #ifndef SEQ_SPARSE_ENC
 #define SEQ_SPARSE_ENC 0
 #endif
@@ -2263,6 +2293,111 @@ __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const D
     }
   }
 #endif
+}
+
+// ---------------------------------------------------------------------
+// Sequential scans without restart intervals, single pass (SEQ_FUSED): bits per block, the prefix over the whole image
+// and the bit packing in ONE kernel, so the coefficient blocks are read from memory once instead of twice.  A tile
+// (256 blocks, taken in ticket order so that a tile only ever waits for tiles that have already started) counts its
+// bits with the block held in registers, publishes its total, finds its base with a decoupled look-back over the
+// tiles before it (state word: 2-bit flag | 62-bit value, written with one 64-bit store), then packs the same
+// registers.  Replaces k_block_bits_seq + k_scan_layout + k_encode_seq for those scans; same bit stream.
+// ---------------------------------------------------------------------
+#ifndef SEQ_FUSED
+#define SEQ_FUSED 0
+#endif
+int seq_fused_enabled() { return SEQ_FUSED; }
+__global__ void __launch_bounds__(256) k_encode_seq_fused(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
+                                                          unsigned long long *__restrict__ tile_state, unsigned *__restrict__ ticket,
+                                                          uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
+                                                          unsigned long long *__restrict__ total_bits, size_t capacity_bits, uint32_t *__restrict__ status)
+{
+  __shared__ ScanTables st;
+  __shared__ unsigned ws[9];
+  __shared__ unsigned s_tile;
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t sbits[ENC_SMEM_WORDS];
+  const int img = blockIdx.y, ntiles = gridDim.x;
+  load_scan_tables(st, tabs, stride, img, g, sd, true);
+  if (threadIdx.x == 0) s_tile = atomicAdd(&ticket[img], 1u);
+  __syncthreads();
+  const unsigned tile = s_tile;
+  const long long t = (long long)tile * 256 + threadIdx.x;
+  uint4 q[8];
+  int last = 0; int dct = 0, act = 0;
+  unsigned bits = 0;
+  if (t < sd.nblocks) {
+    int sci, k; long long mcu;
+    const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(blk);
+#pragma unroll
+    for (int v = 0; v < 8; v++) q[v] = b4[v];
+    last = prev_dc(g, sd, img, t, sci, mcu, k);
+    const CompGeom &c = g.c[sd.ci[sci]];
+    dct = c.dc_tbl; act = 4 + c.ac_tbl;
+    CountSink cs{st.size[dct], st.size[act], 0u, 0};
+    walk_seq_regs(q, last, cs);
+    if (cs.bad) atomicOr(&status[img], 2u);
+    bits = cs.bits;
+  }
+  unsigned tot;
+  const unsigned pre = cta_excl_scan_256(bits, ws, tot);
+  if (threadIdx.x == 0) {
+    volatile unsigned long long *ts = tile_state + (size_t)img * ntiles;
+    const unsigned long long VMASK = (1ull << 62) - 1;
+    unsigned long long base = 0;
+    if (tile == 0) ts[0] = (2ull << 62) | tot;
+    else {
+      ts[tile] = (1ull << 62) | tot;                      // this tile's own total, for the tiles behind it
+      for (int p = (int)tile - 1; ; p--) {
+        unsigned long long v;
+        do { v = ts[p]; } while ((v >> 62) == 0);
+        base += v & VMASK;
+        if ((v >> 62) == 2) break;                         // p's entry already includes everything before it
+      }
+      ts[tile] = (2ull << 62) | (base + tot);
+    }
+    s_base = base;
+    if (tile == (unsigned)ntiles - 1) {
+      const unsigned long long grand = base + tot;
+      total_bits[img] = grand;
+      if (grand + 64 > capacity_bits || grand >= (1ull << 32)) atomicOr(&status[img], 4u);    // does not fit: host retries with a larger buffer
+    }
+  }
+  __syncthreads();
+  const unsigned long long tb = s_base;
+  if (tb + tot + 64 > capacity_bits) return;              // past the buffer: the last tile flags the image
+  uint32_t *gbuf = bitbuf + (size_t)img * bitbuf_stride_words;
+  const unsigned long long word0 = tb >> 5;
+  const unsigned nwords = (unsigned)(((tb & 31) + tot + 31) >> 5);
+  const bool staged = nwords <= ENC_SMEM_WORDS;
+  if (staged) {
+    for (unsigned w = threadIdx.x; w < nwords; w += 256) sbits[w] = 0;
+    __syncthreads();
+  }
+  if (t < sd.nblocks) {
+    const unsigned long long off = tb + pre;
+    BitSink sink;
+    sink.buf = staged ? sbits : gbuf; sink.widx = (off >> 5) - (staged ? word0 : 0ull); sink.acc = 0; sink.nacc = (int)(off & 31);
+    sink.dco = st.code[dct]; sink.aco = st.code[act]; sink.dsz = st.size[dct]; sink.asz = st.size[act];
+    walk_seq_regs(q, last, sink);
+    sink.finish();
+  }
+  if (staged) {
+    __syncthreads();
+    for (unsigned w = threadIdx.x; w < nwords; w += 256) {
+      const uint32_t v = sbits[w];
+      if (!v) continue;
+      if (w == 0 || w == nwords - 1) atomicOr(&gbuf[word0 + w], v); else gbuf[word0 + w] = v;
+    }
+  }
+}
+void launch_encode_seq_fused(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, unsigned long long *tile_state, unsigned *ticket,
+                             uint32_t *bitbuf, size_t bitbuf_stride_words, unsigned long long *total_bits, size_t capacity_bits, uint32_t *status, int n, cudaStream_t s)
+{
+  dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
+  k_encode_seq_fused<<<grid, 256, 0, s>>>(g, sd, tabs, stride, tile_state, ticket, bitbuf, bitbuf_stride_words, total_bits, capacity_bits, status);
+  LAUNCHED();
 }
 
 // byte stuffing (jchuff.c:386-435 emit byte / 0xFF00) + final 1-bit padding
