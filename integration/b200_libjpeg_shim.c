@@ -397,6 +397,12 @@ jpeg_write_coefficients(j_compress_ptr cinfo, jvirt_barray_ptr *coef_arrays)
   if (getenv("MOZ_B200_FORCE_CPU")) why = "MOZ_B200_FORCE_CPU is set";
   if (cinfo->master->num_scans_luma == 0) cinfo->master->optimize_scans = FALSE;        /* jctrans.c:49-50 */
   if (!why && !fill_params(cinfo, TRUE, &p)) why = "parameter set outside b200jpeg_params";
+  if (!why) {
+    /* no pixels on this path: the input colour space of the object (whatever jpeg_copy_critical_parameters and the
+     * application left there, e.g. YCbCr after jpegtran -grayscale) has no meaning, as in transencode_master_selection
+     * (jctrans.c:181-184) */
+    p.in_color_space = p.jpeg_color_space; p.input_components = p.num_components;
+  }
   if (!why && p.trellis_quant) why = "trellis quantization requested on coefficient input";
   if (!why && b200jpeg_validate(&p) != B200JPEG_OK) why = b200jpeg_last_error();
   if (!why) {

@@ -26,7 +26,7 @@ __constant__ uint8_t c_izz[64] = {
 // instead of eight byte loads at lane-dependent constant addresses, which the constant cache serialises)
 __constant__ unsigned long long c_izz_col[8] = {0x2315140a09030200ull, 0x242216130b080401ull, 0x30252117120c0705ull, 0x312f262018110d06ull, 0x39322e271f19100eull, 0x3a38332d281e1a0full, 0x3e3b37342c291d1bull, 0x3f3d3c36352b2a1cull};
 #ifndef FWD_KZ_PACKED
-#define FWD_KZ_PACKED 0
+#define FWD_KZ_PACKED 1
 #endif
 #define ZZ_LIST \
   X(0,0) X(1,1) X(2,8) X(3,16) X(4,9) X(5,2) X(6,3) X(7,10) X(8,17) X(9,24) X(10,32) X(11,25) X(12,18) X(13,11) X(14,4) X(15,5) \
@@ -363,7 +363,7 @@ __constant__ double c_aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0,
 
 // DCTM: 0 = JDCT_ISLOW, 1 = JDCT_IFAST, 2 = JDCT_FLOAT (1 and 2: 8-bit only)
 #ifndef FWD_MASK_SQ
-#define FWD_MASK_SQ 0
+#define FWD_MASK_SQ 1
 #endif
 #ifndef FWD_MIN_CTAS
 #define FWD_MIN_CTAS 6
@@ -991,7 +991,7 @@ __device__ __forceinline__ void walk_seq_regs(const uint4 (&b4)[8], int last_dc,
 }
 
 #ifndef SEQ_SPARSE_ENC
-#define SEQ_SPARSE_ENC 0
+#define SEQ_SPARSE_ENC 1
 #endif
 // Zigzag positions of a scan-order block's non-zero AC coefficients, from the side records (the AC trellis leaves the
 // final ones there); dummy blocks have none.
@@ -1240,12 +1240,12 @@ void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s) { k_seed_
 #define TRELLIS_ILP4 0
 #endif
 #ifndef TRELLIS_MIN_CTAS
-#define TRELLIS_MIN_CTAS 5           // register cap of the common class: 5 CTAs x 128 threads -> 96 registers
+#define TRELLIS_MIN_CTAS 4           // register cap of the common class: 4 CTAs x 128 threads -> 128 registers (5 -> 96: slower, measured)
 #endif
 // The zero-distortion prefix A[0..63] of a thread's block: TRELLIS_SMEM_A keeps it in shared memory (element i of
 // thread tid at sA[i * TRELLIS_THREADS + tid]: conflict-free for any per-thread index) instead of local memory
 #ifndef TRELLIS_SMEM_A
-#define TRELLIS_SMEM_A 0
+#define TRELLIS_SMEM_A 1
 #endif
 #if TRELLIS_SMEM_A
 #define AX(i) ((i) * TRELLIS_THREADS)
@@ -1254,7 +1254,7 @@ void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s) { k_seed_
 #endif
 // rate table element type: fp16 (half the shared memory) or fp32 (no conversion in the inner loop)
 #ifndef TRELLIS_RATE_F32
-#define TRELLIS_RATE_F32 0
+#define TRELLIS_RATE_F32 1
 #endif
 #if TRELLIS_RATE_F32
 typedef float rate_t;
