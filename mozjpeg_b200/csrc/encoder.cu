@@ -562,17 +562,6 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
       tabs = tset;
     } else { tabs = e->d_tabs_fixed.as<DevHuff>(); tstride = 0; }
     const size_t mark_words = (e->bitbuf_words_per_image * 4 / 8 + 64) / 4;
-    if (!pl.progressive && !sd.ri && seq_fused_enabled()) {
-      // single pass: bit counts, image-wide prefix (decoupled look-back) and bit packing in one kernel
-      tm.mark("encode");
-      const size_t ntiles = (size_t)((sd.nblocks + 255) / 256);
-      CU(cudaMemsetAsync(A.d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
-      CU(cudaMemsetAsync(A.d_tile_base.p, 0, ntiles * 8 * n, s));
-      CU(cudaMemsetAsync(A.d_tile_bits.p, 0, (size_t)n * 4, s));
-      launch_encode_seq_fused(g, sd, tabs, tstride, A.d_tile_base.as<unsigned long long>(), A.d_tile_bits.as<unsigned>(),
-                              A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_total_bits.as<unsigned long long>(),
-                              (size_t)e->bitbuf_words_per_image * 32, status, n, s);
-    } else {
     tm.mark("block_bits");
     launch_block_bits(g, sd, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), aux, run_e, status, n, s);
     tm.mark("scan_layout");
@@ -585,7 +574,6 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     launch_encode(g, sd, (pl.trellis && !pl.progressive) ? A.d_rec.as<DcRec>() : nullptr, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
                   A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, aux, run_e,
                   A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_mark.as<uint32_t>(), mark_words, status, n, s);
-    }
     tm.mark("stuff");
     launch_stuff(A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_total_bits.as<unsigned long long>(), A.d_ff_tile.as<uint32_t>(),
                  io.out, e->out_cap_per_image, e->out_cap_per_image, io.out_pos + j * n, io.out_pos + (j + 1) * n,

@@ -960,36 +960,6 @@ __device__ __forceinline__ void walk_seq_block(const int16_t *__restrict__ blk, 
   if (r > 0) sink.ac(0, 0, 0);
 }
 
-// walk_seq_block on a block already held in registers (eight 16-byte quarters, zigzag order)
-template <class Sink>
-__device__ __forceinline__ void walk_seq_regs(const uint4 (&b4)[8], int last_dc, Sink &sink)
-{
-  int r = 0;
-#pragma unroll
-  for (int v = 0; v < 8; v++) {
-    const unsigned w[4] = {b4[v].x, b4[v].y, b4[v].z, b4[v].w};
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      int val = (int)(int16_t)((w[j >> 1] >> ((j & 1) * 16)) & 0xFFFF);
-      if (v == 0 && j == 0) {
-        int temp = val - last_dc, temp2 = temp;
-        if (temp < 0) { temp = -temp; temp2--; }
-        sink.dc(nbits_of(temp), temp2);
-      } else if (val == 0) {
-        r++;
-      } else {
-        while (r > 15) { sink.ac(0xF0, 0, 0); r -= 16; }
-        int temp = val, temp2 = val;
-        if (temp < 0) { temp = -temp; temp2--; }
-        int nb = nbits_of(temp);
-        sink.ac((r << 4) + nb, nb, temp2);
-        r = 0;
-      }
-    }
-  }
-  if (r > 0) sink.ac(0, 0, 0);
-}
-
 #ifndef SEQ_SPARSE_ENC
 #define SEQ_SPARSE_ENC 1
 #endif
@@ -1036,19 +1006,10 @@ __device__ __forceinline__ void walk_seq_sparse(const int16_t *__restrict__ blk,
 // ---------------------------------------------------------------------
 // statistics pass (encode_mcu_gather, jchuff.c:886-915)
 // ---------------------------------------------------------------------
-#ifndef HIST_AGG
-#define HIST_AGG 0
-#endif
-// shared-memory histogram increment; HIST_AGG: the lanes of a warp that hit the same counter send one atomic
+// shared-memory histogram increment (warp-aggregating the atomics per counter was measured slower)
 __device__ __forceinline__ void hist_inc(unsigned *addr)
 {
-#if HIST_AGG
-  const unsigned peers = __match_any_sync(__activemask(), (unsigned)(size_t)addr);
-  const unsigned lane = threadIdx.x & 31;
-  if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(addr, (unsigned)__popc(peers));
-#else
   atomicAdd(addr, 1u);
-#endif
 }
 struct HistSink {
   unsigned *dc_hist, *ac_hist; int bad; int maxbits;        // maxbits = data_precision + 2 (jchuff.c:819,836,865)
@@ -1236,9 +1197,6 @@ void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s) { k_seed_
 //            (:1211-1222).
 // =====================================================================
 #define TRELLIS_THREADS 128
-#ifndef TRELLIS_ILP4
-#define TRELLIS_ILP4 0
-#endif
 #ifndef TRELLIS_MIN_CTAS
 #define TRELLIS_MIN_CTAS 4           // register cap of the common class: 4 CTAs x 128 threads -> 128 registers (5 -> 96: slower, measured)
 #endif
@@ -1267,11 +1225,7 @@ typedef __half rate_t;
 // Order the real blocks of every (image, component) by decreasing number of
 // non-zero plain-quantized AC coefficients (counting sort on DcRec.nz), so that
 // the 32 blocks a warp of k_trellis_ac works on have similar trip counts.
-#ifndef SORT_AGG
-#define SORT_AGG 0
-#endif
-#define SORT_THREADS (SORT_AGG ? 1024 : 256)
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_blocks(Geom g, const DcRec *__restrict__ rec, RecLayout rl, uint32_t *__restrict__ perm, uint32_t *__restrict__ splits)
+__global__ void __launch_bounds__(256) k_sort_blocks(Geom g, const DcRec *__restrict__ rec, RecLayout rl, uint32_t *__restrict__ perm, uint32_t *__restrict__ splits)
 {
   __shared__ unsigned cnt[64], start[64];
   const int ci = blockIdx.x % g.nc, img = blockIdx.x / g.nc;
@@ -1281,17 +1235,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_blocks(Geom g, const DcRe
   uint32_t *p = perm + (size_t)img * rl.per_image + rl.comp_off[ci];
   if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
   __syncthreads();
-#if SORT_AGG
-  // neighbouring blocks mostly fall into the same few bins: one shared-memory atomic per (warp, bin) instead of per block
-  const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
-  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) {
-    const unsigned bin = 63 - min((int)r[b].nz, 63);
-    const unsigned peers = __match_any_sync(__activemask(), bin);
-    if ((peers & lt) == 0) atomicAdd(&cnt[bin], (unsigned)__popc(peers));
-  }
-#else
   for (long long b = threadIdx.x; b < nblk; b += blockDim.x) atomicAdd(&cnt[63 - min((int)r[b].nz, 63)], 1u);
-#endif
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned a = 0; for (int k = 0; k < 64; k++) { start[k] = a; a += cnt[k]; }
@@ -1299,23 +1243,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_blocks(Geom g, const DcRe
     splits[2 * blockIdx.x] = start[63 - 32]; splits[2 * blockIdx.x + 1] = start[63 - 16];
   }
   __syncthreads();
-#if SORT_AGG
-  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) {
-    const unsigned bin = 63 - min((int)r[b].nz, 63);
-    const unsigned peers = __match_any_sync(__activemask(), bin);
-    const int leader = __ffs((int)peers) - 1;
-    unsigned base = 0;
-    if ((int)lane == leader) base = atomicAdd(&start[bin], (unsigned)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    p[base + __popc(peers & lt)] = (uint32_t)b;
-  }
-#else
   for (long long b = threadIdx.x; b < nblk; b += blockDim.x) { unsigned pos = atomicAdd(&start[63 - min((int)r[b].nz, 63)], 1u); p[pos] = (uint32_t)b; }
-#endif
 }
 void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, uint32_t *splits, int n, cudaStream_t s)
 {
-  k_sort_blocks<<<n * g.nc, SORT_THREADS, 0, s>>>(g, rec, rl, perm, splits);
+  k_sort_blocks<<<n * g.nc, 256, 0, s>>>(g, rec, rl, perm, splits);
   LAUNCHED();
 }
 
@@ -1369,32 +1301,12 @@ __device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long 
           cost += (Ai1 - 0.0f) + 0.0f;
           if (cost < kb) { kb = cost; ks = 0; }
         }
-#if TRELLIS_ILP4
-        // predecessors four at a time: the four costs are independent (loads and adds overlap), then a first-minimum
-        // tree (a later element wins only if strictly smaller) - the same (value, index) the sequential scan keeps
-#pragma unroll
-        for (int s0 = 0; s0 < t; s0 += 4) {
-          float cc[4]; 
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            cc[u] = 1e38f;
-            if (s0 + u < t) { cc[u] = RATE_F(rk[-r_pos[s0 + u]]) + dist; cc[u] += (Ai1 - r_at[s0 + u]) + r_acc[s0 + u]; }
-          }
-          float m01 = cc[0]; int i01 = 0; if (s0 + 1 < t && cc[1] < m01) { m01 = cc[1]; i01 = 1; }
-          if (s0 + 2 < t) {
-            float m23 = cc[2]; int i23 = 2; if (s0 + 3 < t && cc[3] < m23) { m23 = cc[3]; i23 = 3; }
-            if (m23 < m01) { m01 = m23; i01 = i23; }
-          }
-          if (m01 < kb) { kb = m01; ks = s0 + i01 + 1; }
-        }
-#else
 #pragma unroll
         for (int s2 = 0; s2 < t; s2++) {
           float cost = RATE_F(rk[-r_pos[s2]]) + dist;
           cost += (Ai1 - r_at[s2]) + r_acc[s2];
           if (cost < kb) { kb = cost; ks = s2 + 1; }
         }
-#endif
         if (kb < best || (kb == best && ks < best_s)) { best = kb; best_s = ks; best_k = k; }
       }
       r_acc[t] = best; r_rs[t] = best_s;
@@ -2233,12 +2145,8 @@ __device__ __forceinline__ void emit_restart_marker(BitSink &sink, const ScanDes
   atomicOr(&mark[byte >> 5], 1u << (byte & 31));
 }
 
-#ifndef ENC_SMEM
-#define ENC_SMEM 0
-#endif
-#define ENC_SMEM_WORDS 4096          // 16 KB: a tile of 256 blocks whose bits fit is assembled in shared memory
 __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ rec, RecLayout rl, const DevHuff *__restrict__ tabs, size_t stride,
-                                                    const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
+                                                    const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits /* per-tile totals: not read here */,
                                                     const unsigned long long *__restrict__ tile_base,
                                                     const uint32_t *__restrict__ seg_corr, long long seg_stride,
                                                     uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
@@ -2252,22 +2160,6 @@ __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const D
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long tb = tile_base[(size_t)img * gridDim.x + blockIdx.x];
   uint32_t *gbuf = bitbuf + (size_t)img * bitbuf_stride_words;
-#if ENC_SMEM
-  // Without restart intervals the tile's 256 blocks emit one contiguous bit range [tb, tb + tile_bits): it is put
-  // together with shared-memory atomics and written out word by word (plain stores; only the two words shared with
-  // the neighbouring tiles go through a global atomic).  Tiles whose bits do not fit take the direct path below.
-  __shared__ uint32_t sbits[ENC_SMEM_WORDS];
-  const unsigned tbits = tile_bits[(size_t)img * gridDim.x + blockIdx.x];
-  const unsigned long long word0 = tb >> 5;
-  const unsigned nwords = (unsigned)(((tb & 31) + tbits + 31) >> 5);
-  const bool staged = !sd.ri && nwords <= ENC_SMEM_WORDS;
-  if (staged) {
-    for (unsigned w = threadIdx.x; w < nwords; w += 256) sbits[w] = 0;
-    __syncthreads();
-  }
-#else
-  const bool staged = false; const unsigned long long word0 = 0; uint32_t *sbits = nullptr; const unsigned nwords = 0;
-#endif
   if (t < sd.nblocks) {
     unsigned long long off = tb + blk_bits[(size_t)img * sd.nblocks + t];
     if (sd.ri) off += seg_corr[(size_t)img * seg_stride + t / ((long long)sd.ri * sd.bim)];
@@ -2276,128 +2168,13 @@ __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const D
     int last = prev_dc(g, sd, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
     BitSink sink;
-    sink.buf = staged ? sbits : gbuf; sink.widx = (off >> 5) - (staged ? word0 : 0ull); sink.acc = 0; sink.nacc = (int)(off & 31);
+    sink.buf = gbuf; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
     sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
     if (SEQ_SPARSE_ENC && rec) walk_seq_sparse(blk, block_nzmask(g, sd, rec, rl, img, sci, mcu, k), last, sink);
     else walk_seq_block(blk, last, sink);
     if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
     sink.finish();
   }
-#if ENC_SMEM
-  if (staged) {
-    __syncthreads();
-    for (unsigned w = threadIdx.x; w < nwords; w += 256) {
-      const uint32_t v = sbits[w];
-      if (!v) continue;                                   // the stream buffer starts out zeroed
-      if (w == 0 || w == nwords - 1) atomicOr(&gbuf[word0 + w], v); else gbuf[word0 + w] = v;
-    }
-  }
-#endif
-}
-
-// ---------------------------------------------------------------------
-// Sequential scans without restart intervals, single pass (SEQ_FUSED): bits per block, the prefix over the whole image
-// and the bit packing in ONE kernel, so the coefficient blocks are read from memory once instead of twice.  A tile
-// (256 blocks, taken in ticket order so that a tile only ever waits for tiles that have already started) counts its
-// bits with the block held in registers, publishes its total, finds its base with a decoupled look-back over the
-// tiles before it (state word: 2-bit flag | 62-bit value, written with one 64-bit store), then packs the same
-// registers.  Replaces k_block_bits_seq + k_scan_layout + k_encode_seq for those scans; same bit stream.
-// ---------------------------------------------------------------------
-#ifndef SEQ_FUSED
-#define SEQ_FUSED 0
-#endif
-int seq_fused_enabled() { return SEQ_FUSED; }
-__global__ void __launch_bounds__(256) k_encode_seq_fused(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
-                                                          unsigned long long *__restrict__ tile_state, unsigned *__restrict__ ticket,
-                                                          uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
-                                                          unsigned long long *__restrict__ total_bits, size_t capacity_bits, uint32_t *__restrict__ status)
-{
-  __shared__ ScanTables st;
-  __shared__ unsigned ws[9];
-  __shared__ unsigned s_tile;
-  __shared__ unsigned long long s_base;
-  __shared__ uint32_t sbits[ENC_SMEM_WORDS];
-  const int img = blockIdx.y, ntiles = gridDim.x;
-  load_scan_tables(st, tabs, stride, img, g, sd, true);
-  if (threadIdx.x == 0) s_tile = atomicAdd(&ticket[img], 1u);
-  __syncthreads();
-  const unsigned tile = s_tile;
-  const long long t = (long long)tile * 256 + threadIdx.x;
-  uint4 q[8];
-  int last = 0; int dct = 0, act = 0;
-  unsigned bits = 0;
-  if (t < sd.nblocks) {
-    int sci, k; long long mcu;
-    const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
-    const uint4 *b4 = reinterpret_cast<const uint4 *>(blk);
-#pragma unroll
-    for (int v = 0; v < 8; v++) q[v] = b4[v];
-    last = prev_dc(g, sd, img, t, sci, mcu, k);
-    const CompGeom &c = g.c[sd.ci[sci]];
-    dct = c.dc_tbl; act = 4 + c.ac_tbl;
-    CountSink cs{st.size[dct], st.size[act], 0u, 0};
-    walk_seq_regs(q, last, cs);
-    if (cs.bad) atomicOr(&status[img], 2u);
-    bits = cs.bits;
-  }
-  unsigned tot;
-  const unsigned pre = cta_excl_scan_256(bits, ws, tot);
-  if (threadIdx.x == 0) {
-    volatile unsigned long long *ts = tile_state + (size_t)img * ntiles;
-    const unsigned long long VMASK = (1ull << 62) - 1;
-    unsigned long long base = 0;
-    if (tile == 0) ts[0] = (2ull << 62) | tot;
-    else {
-      ts[tile] = (1ull << 62) | tot;                      // this tile's own total, for the tiles behind it
-      for (int p = (int)tile - 1; ; p--) {
-        unsigned long long v;
-        do { v = ts[p]; } while ((v >> 62) == 0);
-        base += v & VMASK;
-        if ((v >> 62) == 2) break;                         // p's entry already includes everything before it
-      }
-      ts[tile] = (2ull << 62) | (base + tot);
-    }
-    s_base = base;
-    if (tile == (unsigned)ntiles - 1) {
-      const unsigned long long grand = base + tot;
-      total_bits[img] = grand;
-      if (grand + 64 > capacity_bits || grand >= (1ull << 32)) atomicOr(&status[img], 4u);    // does not fit: host retries with a larger buffer
-    }
-  }
-  __syncthreads();
-  const unsigned long long tb = s_base;
-  if (tb + tot + 64 > capacity_bits) return;              // past the buffer: the last tile flags the image
-  uint32_t *gbuf = bitbuf + (size_t)img * bitbuf_stride_words;
-  const unsigned long long word0 = tb >> 5;
-  const unsigned nwords = (unsigned)(((tb & 31) + tot + 31) >> 5);
-  const bool staged = nwords <= ENC_SMEM_WORDS;
-  if (staged) {
-    for (unsigned w = threadIdx.x; w < nwords; w += 256) sbits[w] = 0;
-    __syncthreads();
-  }
-  if (t < sd.nblocks) {
-    const unsigned long long off = tb + pre;
-    BitSink sink;
-    sink.buf = staged ? sbits : gbuf; sink.widx = (off >> 5) - (staged ? word0 : 0ull); sink.acc = 0; sink.nacc = (int)(off & 31);
-    sink.dco = st.code[dct]; sink.aco = st.code[act]; sink.dsz = st.size[dct]; sink.asz = st.size[act];
-    walk_seq_regs(q, last, sink);
-    sink.finish();
-  }
-  if (staged) {
-    __syncthreads();
-    for (unsigned w = threadIdx.x; w < nwords; w += 256) {
-      const uint32_t v = sbits[w];
-      if (!v) continue;
-      if (w == 0 || w == nwords - 1) atomicOr(&gbuf[word0 + w], v); else gbuf[word0 + w] = v;
-    }
-  }
-}
-void launch_encode_seq_fused(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, unsigned long long *tile_state, unsigned *ticket,
-                             uint32_t *bitbuf, size_t bitbuf_stride_words, unsigned long long *total_bits, size_t capacity_bits, uint32_t *status, int n, cudaStream_t s)
-{
-  dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  k_encode_seq_fused<<<grid, 256, 0, s>>>(g, sd, tabs, stride, tile_state, ticket, bitbuf, bitbuf_stride_words, total_bits, capacity_bits, status);
-  LAUNCHED();
 }
 
 // byte stuffing (jchuff.c:386-435 emit byte / 0xFF00) + final 1-bit padding
@@ -2845,7 +2622,7 @@ __global__ void __launch_bounds__(256) k_block_bits_prog(Geom g, ScanDesc sd, co
 
 __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
                                                      const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
-                                                     const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits,
+                                                     const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits /* per-tile totals: not read here */,
                                                      const unsigned long long *__restrict__ tile_base,
                                                      const uint32_t *__restrict__ seg_corr, long long seg_stride,
                                                      uint32_t *__restrict__ bitbuf, size_t bitbuf_stride_words,
@@ -2860,20 +2637,6 @@ __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const 
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long tb = tile_base[(size_t)img * gridDim.x + blockIdx.x];
   uint32_t *gbuf = bitbuf + (size_t)img * bitbuf_stride_words;
-#if ENC_SMEM
-  // same staging as k_encode_seq: the tile's contiguous bit range is assembled in shared memory
-  __shared__ uint32_t sbits[ENC_SMEM_WORDS];
-  const unsigned tbits = tile_bits[(size_t)img * gridDim.x + blockIdx.x];
-  const unsigned long long word0 = tb >> 5;
-  const unsigned nwords = (unsigned)(((tb & 31) + tbits + 31) >> 5);
-  const bool staged = !sd.ri && nwords <= ENC_SMEM_WORDS;
-  if (staged) {
-    for (unsigned w = threadIdx.x; w < nwords; w += 256) sbits[w] = 0;
-    __syncthreads();
-  }
-#else
-  const bool staged = false; const unsigned long long word0 = 0; uint32_t *sbits = nullptr; const unsigned nwords = 0;
-#endif
   if (t < sd.nblocks) {
     unsigned long long off = tb + blk_bits[(size_t)img * sd.nblocks + t];
     if (sd.ri) off += seg_corr[(size_t)img * seg_stride + t / ((long long)sd.ri * sd.bim)];
@@ -2882,23 +2645,13 @@ __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const 
     int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
     BitSinkP sink;
-    sink.buf = staged ? sbits : gbuf; sink.widx = (off >> 5) - (staged ? word0 : 0ull); sink.acc = 0; sink.nacc = (int)(off & 31);
+    sink.buf = gbuf; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
     sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
     unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
     walk_prog_block(blk, sd, last, a, re, sink);
     if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
     sink.finish();
   }
-#if ENC_SMEM
-  if (staged) {
-    __syncthreads();
-    for (unsigned w = threadIdx.x; w < nwords; w += 256) {
-      const uint32_t v = sbits[w];
-      if (!v) continue;
-      if (w == 0 || w == nwords - 1) atomicOr(&gbuf[word0 + w], v); else gbuf[word0 + w] = v;
-    }
-  }
-#endif
 }
 
 

@@ -138,11 +138,6 @@ void launch_encode(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const
                    const uint32_t *blk_bits, const uint32_t *tile_bits, const unsigned long long *tile_base, const uint32_t *seg_corr, long long seg_stride,
                    const uint32_t *blk_aux, const uint32_t *run_e,
                    uint32_t *bitbuf, size_t bitbuf_image_stride_words, uint32_t *mark, size_t mark_stride_words, const uint32_t *status, int n, cudaStream_t s);
-// single-pass variant of block_bits + scan_layout + encode for sequential scans without restart intervals (SEQ_FUSED
-// build switch); tile_state [n][tiles] and ticket [n] must be zeroed
-int seq_fused_enabled();
-void launch_encode_seq_fused(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, unsigned long long *tile_state, unsigned *ticket,
-                             uint32_t *bitbuf, size_t bitbuf_image_stride_words, unsigned long long *total_bits, size_t capacity_bits, uint32_t *status, int n, cudaStream_t s);
 size_t stuff_tiles(size_t bitbuf_image_stride_words);     // ff_tile entries per image
 void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_image_stride_words, const unsigned long long *total_bits, uint32_t *ff_tile,
                   uint8_t *out, size_t out_image_stride, size_t out_capacity, const unsigned long long *out_start, unsigned long long *out_next,
