@@ -409,15 +409,16 @@ int orc_make_derived(const b200jpeg_huff_tbl *t, int is_dc, unsigned *ehufco, un
 /* ------------------------------------------------------------------ */
 void orc_trellis_row(const b200jpeg_params *p, const unsigned char *dcsi, const unsigned char *acsi,
                      int16_t *coef_blocks, const int16_t *src, int num_blocks,
-                     const uint16_t *qtbl, int16_t *last_dc_val, const int16_t *coef_above, const int16_t *src_above)
+                     const uint16_t *qtbl, int16_t *last_dc_val, const int16_t *coef_above, const int16_t *src_above, int Ss, int Se)
 {
   float azd[64], acc[64], lambda_table[64];
   int run_start[64];
   const int max_coef_bits = p->data_precision + 2;
-  const int Ss = 1, Se = 63;
   int ncand_dc = (2 + 60 / qtbl[0]) | 1;
   float *acc_dc[9]; int *bt_dc[9]; int16_t *cand_dc[9];
   int bi, i, j, k, l;
+  if (Ss == 0) Ss = 1;                                                           /* :975-980 */
+  if (Se < Ss) return;
   if (ncand_dc > 9) ncand_dc = 9;
   for (i = 0; i < 9; i++) { acc_dc[i] = NULL; bt_dc[i] = NULL; cand_dc[i] = NULL; }
   if (p->trellis_quant_dc)
@@ -1057,7 +1058,7 @@ planes_ready:
 }
 
 /* compress_trellis_pass over the whole image for one component (jccoefct.c:356-486) */
-static void trellis_component(enc_t *e, int ci)
+static void trellis_component(enc_t *e, int ci, int Ss, int Se)
 {
   const b200jpeg_params *p = e->p; const b200jpeg_component_info *c = &p->comp_info[ci];
   unsigned co[256]; unsigned char dcsi[256], acsi[256];
@@ -1070,7 +1071,7 @@ static void trellis_component(enc_t *e, int ci)
       size_t off = (size_t)(imcu * v + br) * e->wpad[ci] * 64;
       size_t up = off - (size_t)e->wpad[ci] * 64;                 /* lastblockrow = buffer[block_row-1] only inside the iMCU row (jccoefct.c:420) */
       orc_trellis_row(p, dcsi, acsi, e->coef[ci] + off, e->raw[ci] + off, e->wib[ci], p->quant_tbl[c->quant_tbl_no], &lastDC,
-                      br > 0 ? e->coef[ci] + up : NULL, br > 0 ? e->raw[ci] + up : NULL);
+                      br > 0 ? e->coef[ci] + up : NULL, br > 0 ? e->raw[ci] + up : NULL, Ss, Se);
     }
   }
   fill_dummy_blocks(e, ci);
@@ -1119,7 +1120,7 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
   /* 12-bit: no JBUF_REQUANT => no trellis (jccoefct.c:132-138); deringing is not usable at 12 bits (jcdctmgr.c:419) */
   if (p->data_precision == 12 && (p->trellis_quant || p->overshoot_deringing)) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   if ((p->data_precision != 8 && p->data_precision != 12) || (p->dct_method != B200JPEG_DCT_ISLOW && p->data_precision != 8) ||
-      p->trellis_eob_opt || p->use_scans_in_trellis || p->trellis_q_opt || p->trellis_num_loops != 1) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
+      p->trellis_eob_opt || p->trellis_q_opt || p->trellis_num_loops != 1) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   e->hmax = e->vmax = 1;
   for (ci = 0; ci < e->nc; ci++) { if (p->comp_info[ci].h_samp_factor > e->hmax) e->hmax = p->comp_info[ci].h_samp_factor; if (p->comp_info[ci].v_samp_factor > e->vmax) e->vmax = p->comp_info[ci].v_samp_factor; }
   e->mcus_per_row = (e->W + e->hmax * 8 - 1) / (e->hmax * 8); e->mcu_rows = (e->H + e->vmax * 8 - 1) / (e->vmax * 8);
@@ -1167,11 +1168,21 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
        * tables, requantize.  The re-gather the reference does inside the
        * trellis pass only produces tables that are overwritten before use. */
       for (ci = 0; ci < e->nc; ci++) {
-        scan_t ts; ts.ncomps = 1; ts.ci[0] = ci; ts.Ss = 1; ts.Se = 63; ts.Ah = ts.Al = 0;
-        if (!e->progressive) ts.Ss = 0;   /* jchuff ignores Ss/Se: DC+AC statistics */
-        gather_scan(e, &ts, 1, t);
-        if (dbg) { dbg->trellis_dc[ci] = e->dc_tbl[p->comp_info[ci].dc_tbl_no]; dbg->trellis_ac[ci] = e->ac_tbl[p->comp_info[ci].ac_tbl_no]; }
-        trellis_component(e, ci);
+        /* use_scans_in_trellis: the component's AC band is split at trellis_freq_split and each half gets its own
+         * statistics -> tables -> quantize_trellis pair of passes (select_scan_parameters, jcmaster.c:451-467) */
+        const int nband = p->use_scans_in_trellis ? 2 : 1; int band;
+        for (band = 0; band < nband; band++) {
+          scan_t ts; ts.ncomps = 1; ts.ci[0] = ci; ts.Ah = ts.Al = 0;
+          ts.Ss = (nband == 2 && band == 1) ? p->trellis_freq_split + 1 : 1;
+          ts.Se = (nband == 2 && band == 0) ? p->trellis_freq_split : 63;
+          {
+            scan_t gs = ts;
+            if (!e->progressive) gs.Ss = 0;   /* jchuff ignores Ss/Se: DC+AC statistics over the whole block */
+            gather_scan(e, &gs, 1, t);
+          }
+          if (dbg) { dbg->trellis_dc[ci] = e->dc_tbl[p->comp_info[ci].dc_tbl_no]; dbg->trellis_ac[ci] = e->ac_tbl[p->comp_info[ci].ac_tbl_no]; }
+          trellis_component(e, ci, ts.Ss, ts.Se);
+        }
       }
     }
     if (dbg) for (ci = 0; ci < e->nc; ci++) { size_t n = (size_t)e->wpad[ci] * e->hpad[ci] * 64 * 2; dbg->final_[ci] = (int16_t *)malloc(n); memcpy(dbg->final_[ci], e->coef[ci], n); }

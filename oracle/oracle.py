@@ -120,6 +120,8 @@ class RefCfg(C.Structure):
         ("restart", C.c_int), ("restart_blocks", C.c_int), ("grayscale", C.c_int), ("quant_table", C.c_int),
         ("precision", C.c_int), ("has_lambda1", C.c_int), ("has_lambda2", C.c_int),
         ("lambda1", C.c_float), ("lambda2", C.c_float), ("tjapi", C.c_int), ("input_gray", C.c_int),
+        ("ext_use_scans_in_trellis", C.c_int), ("ext_trellis_freq_split", C.c_int), ("ext_trellis_eob_opt", C.c_int),
+        ("ext_trellis_q_opt", C.c_int), ("ext_trellis_num_loops", C.c_int),
     ]
 
 
@@ -154,6 +156,7 @@ def refcfg_from_switches(switches: Sequence[str], input_gray: bool = False) -> R
     the shim applies them in a fixed order, so tests pass them that way too)."""
     c = RefCfg()
     c.trellis_dc = -1; c.dct = -1; c.quant_table = -1; c.precision = 8
+    c.ext_use_scans_in_trellis = c.ext_trellis_freq_split = c.ext_trellis_eob_opt = c.ext_trellis_q_opt = c.ext_trellis_num_loops = -1
     c.input_gray = int(input_gray)
     it = iter(switches)
     for s in it:
@@ -185,14 +188,19 @@ def refcfg_from_switches(switches: Sequence[str], input_gray: bool = False) -> R
     return c
 
 
-def ref_encode(pixels: np.ndarray, switches: Sequence[str]) -> bytes:
-    """Encode with the UNMODIFIED reference (libjpeg API, cjpeg switch semantics)."""
+def ref_encode(pixels: np.ndarray, switches: Sequence[str], ext: Optional[dict] = None) -> bytes:
+    """Encode with the UNMODIFIED reference (libjpeg API, cjpeg switch semantics).  ext: extension parameters cjpeg has
+    no switch for, e.g. {"use_scans_in_trellis": 1, "trellis_freq_split": 8} (set through jpeg_c_set_*_param)."""
     lib = ref()
     gray = pixels.ndim == 2 or pixels.shape[2] == 1
     try:
         cfg = refcfg_from_switches(switches, gray)
     except ValueError:
+        if ext:
+            raise
         return _ref_cjpeg_pixels(pixels, switches)      # a switch only the reference's own cjpeg parses (8-bit input)
+    for k, v in (ext or {}).items():
+        setattr(cfg, "ext_" + k, int(v))
     pix = np.ascontiguousarray(pixels, dtype=np.uint16 if cfg.precision == 12 else np.uint8)
     out = C.POINTER(C.c_uint8)(); n = C.c_ulong(0)
     err = C.create_string_buffer(256)

@@ -42,6 +42,8 @@ typedef struct {
                           (turbojpeg.c:330-397): JCP_FASTEST, quality,
                           subsampling from samp_h/v[0], optimize/progressive */
   int input_gray;      /* input buffer is 1 component grayscale */
+  /* extension parameters cjpeg has no switch for (jpeg_c_set_*_param, jcext.c); -1 = leave the default */
+  int ext_use_scans_in_trellis, ext_trellis_freq_split, ext_trellis_eob_opt, ext_trellis_q_opt, ext_trellis_num_loops;
 } refshim_cfg;
 
 struct my_err { struct jpeg_error_mgr pub; jmp_buf jb; char msg[JMSG_LENGTH_MAX]; };
@@ -70,6 +72,11 @@ static void apply_switches(j_compress_ptr cinfo, const refshim_cfg *cfg, int for
   else if (cfg->dct == 2) cinfo->dct_method = JDCT_FLOAT;
   if (cfg->fastcrush) jpeg_c_set_bool_param(cinfo, JBOOLEAN_OPTIMIZE_SCANS, FALSE);
   if (cfg->grayscale) jpeg_set_colorspace(cinfo, JCS_GRAYSCALE);
+  if (cfg->ext_use_scans_in_trellis >= 0) jpeg_c_set_bool_param(cinfo, JBOOLEAN_USE_SCANS_IN_TRELLIS, cfg->ext_use_scans_in_trellis);
+  if (cfg->ext_trellis_freq_split >= 0) jpeg_c_set_int_param(cinfo, JINT_TRELLIS_FREQ_SPLIT, cfg->ext_trellis_freq_split);
+  if (cfg->ext_trellis_eob_opt >= 0) jpeg_c_set_bool_param(cinfo, JBOOLEAN_TRELLIS_EOB_OPT, cfg->ext_trellis_eob_opt);
+  if (cfg->ext_trellis_q_opt >= 0) jpeg_c_set_bool_param(cinfo, JBOOLEAN_TRELLIS_Q_OPT, cfg->ext_trellis_q_opt);
+  if (cfg->ext_trellis_num_loops >= 0) jpeg_c_set_int_param(cinfo, JINT_TRELLIS_NUM_LOOPS, cfg->ext_trellis_num_loops);
   if (cfg->has_lambda1) jpeg_c_set_float_param(cinfo, JFLOAT_LAMBDA_LOG_SCALE1, cfg->lambda1);
   if (cfg->has_lambda2) jpeg_c_set_float_param(cinfo, JFLOAT_LAMBDA_LOG_SCALE2, cfg->lambda2);
   if (cfg->optimize) cinfo->optimize_coding = TRUE;
