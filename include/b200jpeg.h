@@ -111,11 +111,11 @@ typedef struct {
   int trellis_quant_dc;
   int trellis_eob_opt;                    /* must be 0 */
   int use_lambda_weight_tbl;              /* no effect in the reference (jcdctmgr.c:971,1017) */
-  int use_scans_in_trellis;               /* must be 0 */
+  int use_scans_in_trellis;               /* trellis in two AC bands split at trellis_freq_split (jcmaster.c:451-467) */
   int trellis_q_opt;                      /* must be 0 */
   int overshoot_deringing;
   int trellis_freq_split;
-  int trellis_num_loops;                  /* must be 1 */
+  int trellis_num_loops;                  /* 1..16 rounds of statistics + trellis per component (jcmaster.c:453-465) */
   int quant_tbl_master_idx;               /* JINT_BASE_QUANT_TBL_IDX */
   int dc_scan_opt_mode;
   float lambda_log_scale1, lambda_log_scale2;

@@ -479,6 +479,16 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     if (e->keep_plain) for (int ci = 0; ci < g.nc; ci++) CU(cudaMemcpyAsync(A.d_plain[ci].p, A.d_coef[ci].p, pl.coef_bytes[ci] * n, cudaMemcpyDeviceToDevice, s));
     const size_t hist_bytes_t = hist_bytes * g.nc;
     DevHuff *tset = A.d_tabs_trellis.as<DevHuff>();                                       // [img*nc + ci][8]
+    // use_scans_in_trellis (jcmaster.c:451-467): two statistics -> tables -> quantize_trellis rounds per component, on
+    // the zigzag bands 1..trellis_freq_split and the rest; otherwise one round on 1..63
+    const int nband = p->use_scans_in_trellis ? 2 : 1;
+    // trellis_num_loops > 1 repeats the rounds (jcmaster.c:453-465); later rounds start from the requantized
+    // coefficients, which the band kernel honours (it reads the values a block has on entry), so it serves those too
+    const bool generic_rounds = nband == 2 || p->trellis_num_loops > 1;
+    for (int loop = 0; loop < p->trellis_num_loops; loop++)
+    for (int band = 0; band < nband; band++) {
+    const int bSs = (nband == 2 && band == 1) ? p->trellis_freq_split + 1 : 1;
+    const int bSe = (nband == 2 && band == 0) ? p->trellis_freq_split : 63;
     if (!pl.progressive) {
       tm.mark("trellis_stats");
       CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes_t, s));
@@ -488,11 +498,11 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
       for (int ci = 0; ci < g.nc; ci++) masks.m[ci] = (1u << g.c[ci].dc_tbl) | (1u << (4 + g.c[ci].ac_tbl));
       launch_gen_tables(A.d_hist.as<uint32_t>(), tset, tabset, masks, n * g.nc, s);
     } else {
-      // jcphuff statistics with Ss=1..63, Al=0 (jcmaster.c:462-466), every AC symbol
+      // jcphuff statistics with Ss=1..63 (or the band), Al=0 (jcmaster.c:462-466), every AC symbol
       // pre-counted once (jcphuff.c:257-264); the DC table stays the supplied one.
       for (int ci = 0; ci < g.nc; ci++) {
         ScanDesc ts; memset(&ts, 0, sizeof ts);
-        ts.ncomps = 1; ts.ci[0] = ci; ts.Ss = 1; ts.Se = 63; ts.bim = 1; ts.k_count[0] = 1;
+        ts.ncomps = 1; ts.ci[0] = ci; ts.Ss = bSs; ts.Se = bSe; ts.bim = 1; ts.k_count[0] = 1;
         ts.per_row = g.c[ci].wib; ts.rows = g.c[ci].hib; ts.nblocks = (long long)ts.per_row * ts.rows;
         ts.ri = p->restart_in_rows > 0 ? (int)std::min((long long)p->restart_in_rows * ts.per_row, 65535LL) : p->restart_interval;
         tm.mark("trellis_stats");
@@ -505,14 +515,20 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
         launch_gen_tables(A.d_hist.as<uint32_t>(), tset + (size_t)ci * HIST_SLOTS, tabset * g.nc, masks, n, s);
       }
     }
-    tm.mark("trellis_sort");
-    launch_sort_blocks(g, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
-    tm.mark("trellis_ac");
-    launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
+    if (!generic_rounds) {
+      tm.mark("trellis_sort");
+      launch_sort_blocks(g, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
+      tm.mark("trellis_ac");
+      launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
+    } else {
+      tm.mark("trellis_ac");
+      launch_trellis_ac_band(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, bSs, bSe, n, s);
+    }
     if (p->trellis_quant_dc) {
       tm.mark("trellis_dc");
       if (pl.progressive) launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rl, p->trellis_delta_dc_weight > 0.0f, n, s);
       else launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rl, p->trellis_delta_dc_weight > 0.0f, n, s);
+    }
     }
     tm.mark("dummy");
     launch_dummy(g, n, s);

@@ -1546,6 +1546,112 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : TRELLIS_MIN_CT
   if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fmask;
 }
 
+// ---------------------------------------------------------------------
+// Optional trellis mode use_scans_in_trellis (jcmaster.c:451-467): the AC coefficients of a component are requantized
+// in two passes, zigzag positions 1..trellis_freq_split and the rest, each with Huffman tables gathered just before
+// it.  quantize_trellis then works on the band [Ss, Se] only (jcdctmgr.c:975-980, :1121-1222): zero distortion and
+// runs start at position Ss-1, the end-of-block choice is made at Se, and coefficients outside the band are left
+// alone.  One thread per block, the reference's (predecessor, candidate) loop order kept literally; an API-only
+// option, so this kernel is written for exactness, not speed.  Also (re)writes lambda_dc for the DC trellis that
+// follows each pass, from the natural-order norm recomputed here (:1026-1035).
+// ---------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_trellis_ac_band(Geom g, const TrellisConsts *__restrict__ tc,
+                                                         const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
+                                                         DcRec *__restrict__ rec, RecLayout rl, int Ss, int Se)
+{
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
+  const CompGeom &c = g.c[ci];
+  __shared__ float swz[64];
+  __shared__ int sq8[64];
+  __shared__ uint8_t acsi[256];
+  const long long nblk = (long long)c.wib * c.hib;
+  if ((long long)blockIdx.x * blockDim.x >= nblk) return;
+  {
+    const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + (4 + c.ac_tbl);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) acsi[i] = ac->size[i];
+    if (threadIdx.x < 64) { swz[threadIdx.x] = tc->w_zz[c.qt][threadIdx.x]; sq8[threadIdx.x] = tc->q8_zz[c.qt][threadIdx.x]; }
+  }
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nblk) return;
+  const int by = (int)(t / c.wib), bx = (int)(t - (long long)by * c.wib);
+  const size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
+  const int16_t *raw16 = c.raw + blk * 64;
+  int16_t *o16 = c.coef + blk * 64;
+  const size_t ridx = (size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)t;
+  float lambda;
+  {
+    float nsum = 0.0f;
+    for (int nat = 1; nat < 64; nat++) { const int v = raw16[c_izz[nat]]; nsum += (float)(v * v); }
+    const float norm = (float)((double)nsum / 63.0);
+    if (tc->use_norm) lambda = (float)(tc->p1 / (tc->p2 + (double)norm));
+    else lambda = tc->lambda_const;
+    rec[ridx].lambda_dc = lambda * swz[0];
+  }
+  const int maxq = (1 << tc->max_coef_bits) - 1;
+  float azd[64], acc[64];
+  int16_t cur[64];
+  uint8_t rs[64];
+  for (int i = Ss; i <= Se; i++) cur[i] = o16[i];
+  azd[Ss - 1] = 0.0f; acc[Ss - 1] = 0.0f; cur[Ss - 1] = 0; rs[Ss - 1] = 0;
+  const int zrl = acsi[0xF0];
+  for (int i = Ss; i <= Se; i++) {
+    const int rawv = raw16[i], sign = rawv >> 31, x = abs(rawv), q = sq8[i];
+    azd[i] = (float)(x * x) * lambda * swz[i] + azd[i - 1];
+    rs[i] = 0;
+    int qval = (x + q / 2) / q;
+    if (qval == 0) { cur[i] = 0; acc[i] = 1e38f; continue; }
+    if (qval > maxq) qval = maxq;
+    const int nc = nbits_of(qval);
+    acc[i] = 1e38f;
+    for (int j = Ss - 1; j < i; j++) {
+      if (j != Ss - 1 && cur[j] == 0) continue;
+      int zero_run = i - 1 - j;
+      if ((zero_run >> 4) && zrl == 0) continue;
+      const int run_bits = (zero_run >> 4) * zrl;
+      zero_run &= 15;
+      for (int k = 0; k < nc; k++) {
+        const int cand = (k < nc - 1) ? (2 << k) - 1 : qval;
+        const int coef_bits = acsi[16 * zero_run + k + 1];
+        if (coef_bits == 0) continue;
+        const int delta = cand * q - x;
+        const float dist = (float)(delta * delta) * lambda * swz[i];
+        float cost = (float)(coef_bits + (k + 1) + run_bits) + dist;
+        cost += (azd[i - 1] - azd[j]) + acc[j];
+        if (cost < acc[i]) { cur[i] = (int16_t)((cand ^ sign) - sign); acc[i] = cost; rs[i] = (uint8_t)j; }
+      }
+    }
+  }
+  int last = Ss - 1;
+  float best = azd[Se] + (float)acsi[0];
+  for (int i = Ss; i <= Se; i++) {
+    if (cur[i] != 0) {
+      float cst = acc[i] + azd[Se] - azd[i];
+      if (i < Se) cst += (float)acsi[0];
+      if (cst < best) { best = cst; last = i; }
+    }
+  }
+  for (int i = Se; i >= Ss; ) {
+    while (i > last) { cur[i] = 0; i--; }
+    if (i < Ss) break;
+    last = rs[i];
+    i--;
+  }
+  unsigned long long bits = 0;
+  for (int i = Ss; i <= Se; i++) { o16[i] = cur[i]; if (cur[i]) bits |= 1ull << i; }
+  const unsigned long long bandmask = ((Se >= 63 ? ~0ull : ((1ull << (Se + 1)) - 1ull))) & ~((1ull << Ss) - 1ull);
+  rec[ridx].nzmask = (rec[ridx].nzmask & ~bandmask) | bits;
+}
+void launch_trellis_ac_band(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
+                            DcRec *rec, const RecLayout &rl, int Ss, int Se, int n, cudaStream_t s)
+{
+  long long mb = 0;
+  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
+  dim3 grid((unsigned)((mb + 127) / 128), n * g.nc);
+  k_trellis_ac_band<<<grid, 128, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, Ss, Se);
+  LAUNCHED();
+}
+
 void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                        DcRec *rec, const RecLayout &rl, const uint32_t *perm, const uint32_t *splits, int n, cudaStream_t s)
 {

@@ -286,7 +286,8 @@ int b200jpeg_validate(const b200jpeg_params *p) {
   if (p->dct_method < B200JPEG_DCT_ISLOW || p->dct_method > B200JPEG_DCT_FLOAT) { set_error("unknown dct_method %d", p->dct_method); return B200JPEG_ERR_PARAM; }
   if (p->dct_method != B200JPEG_DCT_ISLOW && p->data_precision != 8) { set_error("dct_method %d at %d bits is not on the device path (JDCT_IFAST / JDCT_FLOAT: 8 bits only)", p->dct_method, p->data_precision); return B200JPEG_ERR_UNSUPPORTED; }
   if (p->smoothing_factor < 0 || p->smoothing_factor > 100) { set_error("smoothing_factor %d out of range 0..100", p->smoothing_factor); return B200JPEG_ERR_PARAM; }
-  if (p->trellis_eob_opt || p->use_scans_in_trellis || p->trellis_q_opt || p->trellis_num_loops != 1) { set_error("non-default trellis option is not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
+  if (p->trellis_quant && p->use_scans_in_trellis && (p->trellis_freq_split < 1 || p->trellis_freq_split > 62)) { set_error("trellis_freq_split %d: the device path takes 1..62 with use_scans_in_trellis", p->trellis_freq_split); return B200JPEG_ERR_UNSUPPORTED; }
+  if (p->trellis_eob_opt || p->trellis_q_opt || p->trellis_num_loops < 1 || p->trellis_num_loops > 16) { set_error("non-default trellis option is not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
   // validate_script (jcmaster.c:252-436)
   bool progressive = false;
   if (p->num_scans > 0 && p->optimize_scans) {
@@ -349,7 +350,8 @@ int b200jpeg_total_passes(const b200jpeg_params *p) {
   int num_scans = p->num_scans > 0 ? p->num_scans : 1;
   int total = optimize ? num_scans * 2 : num_scans;
   if (p->trellis_quant) {
-    int base = optimize ? 2 * p->num_components * p->trellis_num_loops : p->num_components * p->trellis_num_loops + 1;
+    const int per = p->use_scans_in_trellis ? 2 : 1;                      // jcmaster.c:1128-1139
+    int base = optimize ? 2 * per * p->num_components * p->trellis_num_loops : per * p->num_components * p->trellis_num_loops + 1;
     total += base;
   }
   return total;

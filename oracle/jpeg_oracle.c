@@ -409,7 +409,7 @@ int orc_make_derived(const b200jpeg_huff_tbl *t, int is_dc, unsigned *ehufco, un
 /* ------------------------------------------------------------------ */
 void orc_trellis_row(const b200jpeg_params *p, const unsigned char *dcsi, const unsigned char *acsi,
                      int16_t *coef_blocks, const int16_t *src, int num_blocks,
-                     const uint16_t *qtbl, int16_t *last_dc_val, const int16_t *coef_above, const int16_t *src_above, int Ss, int Se)
+                     const uint16_t *qtbl, int16_t *last_dc_val, const int16_t *coef_above, const int16_t *src_above, int Ss, int Se, double *norm_src, double *norm_coef)
 {
   float azd[64], acc[64], lambda_table[64];
   int run_start[64];
@@ -417,8 +417,14 @@ void orc_trellis_row(const b200jpeg_params *p, const unsigned char *dcsi, const 
   int ncand_dc = (2 + 60 / qtbl[0]) | 1;
   float *acc_dc[9]; int *bt_dc[9]; int16_t *cand_dc[9];
   int bi, i, j, k, l;
+  float *eo_zero = NULL, *eo_cost = NULL; int *eo_start = NULL, *eo_req = NULL;
   if (Ss == 0) Ss = 1;                                                           /* :975-980 */
   if (Se < Ss) return;
+  if (p->trellis_eob_opt) {                                                      /* :981-996 */
+    eo_zero = (float *)malloc((num_blocks + 1) * sizeof(float)); eo_cost = (float *)malloc((num_blocks + 1) * sizeof(float));
+    eo_start = (int *)malloc(num_blocks * sizeof(int)); eo_req = (int *)malloc((num_blocks + 1) * sizeof(int));
+    eo_zero[0] = 0; eo_cost[0] = 0; eo_req[0] = 0;
+  }
   if (ncand_dc > 9) ncand_dc = 9;
   for (i = 0; i < 9; i++) { acc_dc[i] = NULL; bt_dc[i] = NULL; cand_dc[i] = NULL; }
   if (p->trellis_quant_dc)
@@ -432,7 +438,7 @@ void orc_trellis_row(const b200jpeg_params *p, const unsigned char *dcsi, const 
   for (bi = 0; bi < num_blocks; bi++) {
     const int16_t *s = src + 64 * bi;
     int16_t *c = coef_blocks + 64 * bi;
-    float norm = 0.0, lambda, lambda_dc, cost, best_cost;
+    float norm = 0.0, lambda, lambda_dc, cost, best_cost, cost_all_zeros, best_cost_skip; int has_eob;
     int last_coeff_idx;
     for (i = 1; i < 64; i++) norm += s[i] * s[i];                               /* :1026-1029 natural order */
     norm /= 63.0;
@@ -515,20 +521,78 @@ void orc_trellis_row(const b200jpeg_params *p, const unsigned char *dcsi, const 
 
     last_coeff_idx = Ss - 1;                                                     /* :1187-1207 */
     best_cost = azd[Se] + acsi[0];
+    cost_all_zeros = azd[Se]; best_cost_skip = cost_all_zeros;
     for (i = Ss; i <= Se; i++) {
       int z = zz[i];
       if (c[z] != 0) {
         float cst = acc[i] + azd[Se] - azd[i];
+        float cst_wo_eob = cst;
         if (i < Se) cst += acsi[0];
-        if (cst < best_cost) { best_cost = cst; last_coeff_idx = i; }
+        if (cst < best_cost) { best_cost = cst; last_coeff_idx = i; best_cost_skip = cst_wo_eob; }
       }
     }
+    has_eob = (last_coeff_idx < Se) + (last_coeff_idx == Ss - 1);                /* 2 = the band is all zero in this block */
     i = Se;                                                                      /* :1211-1222 */
     while (i >= Ss) {
       while (i > last_coeff_idx) { c[zz[i]] = 0; i--; }
       last_coeff_idx = run_start[i];
       i--;
     }
+    if (p->trellis_eob_opt) {
+      /* trellis_eob_opt (:1224-1256): a second, block-level dynamic program over the row - which runs of all-zero
+       * blocks to code as one EOBRUN.  eo_zero[b] = zero-distortion cost of blanking blocks 0..b-1; eo_cost[b] = best
+       * cost of the row up to block b-1 given that block b-1 stays non-zero; the EOBRUN symbol for a run of r blocks
+       * costs len(16*nbits(r)) + nbits(r). */
+      eo_zero[bi + 1] = eo_zero[bi];
+      eo_zero[bi + 1] += cost_all_zeros;
+      eo_req[bi + 1] = has_eob;
+      best_cost = 1e38;
+      if (has_eob != 2) {
+        for (i = 0; i <= bi; i++) {
+          int zero_block_run, nb; float cst;
+          if (eo_req[i] == 2) continue;
+          cst = best_cost_skip;
+          cst += eo_zero[bi];
+          cst -= eo_zero[i];
+          cst += eo_cost[i];
+          zero_block_run = bi - i + eo_req[i];
+          nb = nbits_of(zero_block_run);
+          cst += acsi[16 * nb] + nb;
+          if (cst < best_cost) { eo_start[bi] = i; best_cost = cst; eo_cost[bi + 1] = cst; }
+        }
+      }
+    }
+  }
+
+  if (p->trellis_eob_opt) {                                                      /* :1258-1297 */
+    int last_block = num_blocks;
+    float best = 1e38;
+    for (i = 0; i <= num_blocks; i++) {
+      int zero_block_run, nb; float cst = 0.0;
+      if (eo_req[i] == 2) continue;
+      cst += eo_zero[num_blocks];
+      cst -= eo_zero[i];
+      zero_block_run = num_blocks - i + eo_req[i];
+      nb = nbits_of(zero_block_run);
+      cst += acsi[16 * nb] + nb;
+      if (cst < best) { best = cst; last_block = i; }
+    }
+    last_block--;
+    bi = num_blocks - 1;
+    while (bi >= 0) {
+      while (bi > last_block) { for (j = Ss; j <= Se; j++) coef_blocks[64 * bi + zz[j]] = 0; bi--; }
+      last_block = eo_start[bi] - 1;
+      bi--;
+    }
+    free(eo_zero); free(eo_cost); free(eo_start); free(eo_req);
+  }
+
+  if (p->trellis_q_opt && norm_src && norm_coef) {                               /* :1299-1306, natural order, before the DC back-track */
+    for (bi = 0; bi < num_blocks; bi++)
+      for (i = 1; i < 64; i++) {
+        norm_src[i] += src[64 * bi + i] * coef_blocks[64 * bi + i];
+        norm_coef[i] += 8 * coef_blocks[64 * bi + i] * coef_blocks[64 * bi + i];
+      }
   }
 
   if (p->trellis_quant_dc) {                                                     /* :1308-1327 */
@@ -1058,7 +1122,7 @@ planes_ready:
 }
 
 /* compress_trellis_pass over the whole image for one component (jccoefct.c:356-486) */
-static void trellis_component(enc_t *e, int ci, int Ss, int Se)
+static void trellis_component(enc_t *e, int ci, int Ss, int Se, double (*norm_src)[64], double (*norm_coef)[64])
 {
   const b200jpeg_params *p = e->p; const b200jpeg_component_info *c = &p->comp_info[ci];
   unsigned co[256]; unsigned char dcsi[256], acsi[256];
@@ -1071,7 +1135,8 @@ static void trellis_component(enc_t *e, int ci, int Ss, int Se)
       size_t off = (size_t)(imcu * v + br) * e->wpad[ci] * 64;
       size_t up = off - (size_t)e->wpad[ci] * 64;                 /* lastblockrow = buffer[block_row-1] only inside the iMCU row (jccoefct.c:420) */
       orc_trellis_row(p, dcsi, acsi, e->coef[ci] + off, e->raw[ci] + off, e->wib[ci], p->quant_tbl[c->quant_tbl_no], &lastDC,
-                      br > 0 ? e->coef[ci] + up : NULL, br > 0 ? e->raw[ci] + up : NULL, Ss, Se);
+                      br > 0 ? e->coef[ci] + up : NULL, br > 0 ? e->raw[ci] + up : NULL, Ss, Se,
+                      norm_src ? norm_src[c->quant_tbl_no] : NULL, norm_coef ? norm_coef[c->quant_tbl_no] : NULL);
     }
   }
   fill_dummy_blocks(e, ci);
@@ -1115,12 +1180,14 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
   memset(e, 0, sizeof *e);
   *out = NULL; *outsize = 0;
   if (dbg) memset(dbg, 0, sizeof *dbg);
+  static b200jpeg_params P;                                /* mutable copy: trellis_q_opt rewrites the quantization tables (test infrastructure: single-threaded) */
+  P = *p; p = &P;
   e->p = p; e->nc = p->num_components; e->W = p->image_width; e->H = p->image_height;
   e->raw_planes = g_raw_planes; e->raw_pitch = g_raw_pitch;
   /* 12-bit: no JBUF_REQUANT => no trellis (jccoefct.c:132-138); deringing is not usable at 12 bits (jcdctmgr.c:419) */
   if (p->data_precision == 12 && (p->trellis_quant || p->overshoot_deringing)) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   if ((p->data_precision != 8 && p->data_precision != 12) || (p->dct_method != B200JPEG_DCT_ISLOW && p->data_precision != 8) ||
-      p->trellis_eob_opt || p->trellis_q_opt || p->trellis_num_loops != 1) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
+      p->trellis_num_loops < 1) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   e->hmax = e->vmax = 1;
   for (ci = 0; ci < e->nc; ci++) { if (p->comp_info[ci].h_samp_factor > e->hmax) e->hmax = p->comp_info[ci].h_samp_factor; if (p->comp_info[ci].v_samp_factor > e->vmax) e->vmax = p->comp_info[ci].v_samp_factor; }
   e->mcus_per_row = (e->W + e->hmax * 8 - 1) / (e->hmax * 8); e->mcu_rows = (e->H + e->vmax * 8 - 1) / (e->vmax * 8);
@@ -1167,11 +1234,17 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
        * gather on the plain-quantized coefs (Ss=1..63 for jcphuff), build
        * tables, requantize.  The re-gather the reference does inside the
        * trellis pass only produces tables that are overwritten before use. */
+      double norm_src[4][64], norm_coef[4][64]; int pass_number = 0;
+      memset(norm_src, 0, sizeof norm_src); memset(norm_coef, 0, sizeof norm_coef);
       for (ci = 0; ci < e->nc; ci++) {
         /* use_scans_in_trellis: the component's AC band is split at trellis_freq_split and each half gets its own
          * statistics -> tables -> quantize_trellis pair of passes (select_scan_parameters, jcmaster.c:451-467) */
-        const int nband = p->use_scans_in_trellis ? 2 : 1; int band;
+        const int nband = p->use_scans_in_trellis ? 2 : 1; int band, loop;
+        /* trellis_num_loops: the component's rounds are simply repeated (pass -> component = pass / (2 or 4 * loops),
+         * jcmaster.c:453-465): later rounds gather on the already requantized coefficients */
+        for (loop = 0; loop < p->trellis_num_loops; loop++)
         for (band = 0; band < nband; band++) {
+          const int group = e->nc * (nband == 2 ? 4 : 2);     /* passes between two table updates (jcmaster.c:687-698,1014-1030) */
           scan_t ts; ts.ncomps = 1; ts.ci[0] = ci; ts.Ah = ts.Al = 0;
           ts.Ss = (nband == 2 && band == 1) ? p->trellis_freq_split + 1 : 1;
           ts.Se = (nband == 2 && band == 0) ? p->trellis_freq_split : 63;
@@ -1181,7 +1254,20 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
             gather_scan(e, &gs, 1, t);
           }
           if (dbg) { dbg->trellis_dc[ci] = e->dc_tbl[p->comp_info[ci].dc_tbl_no]; dbg->trellis_ac[ci] = e->ac_tbl[p->comp_info[ci].ac_tbl_no]; }
-          trellis_component(e, ci, ts.Ss, ts.Se);
+          pass_number++;                                       /* the statistics pass */
+          if (p->trellis_q_opt && pass_number % group == 1) memset(norm_src, 0, sizeof norm_src), memset(norm_coef, 0, sizeof norm_coef);
+          trellis_component(e, ci, ts.Ss, ts.Se, norm_src, norm_coef);
+          if (p->trellis_q_opt && (pass_number + 1) % group == 0) {
+            /* trellis_q_opt: every table entry becomes the least-squares dequantizer of what the trellis kept */
+            int ti, jj;
+            for (ti = 0; ti < 4; ti++) for (jj = 1; jj < 64; jj++) if (norm_coef[ti][jj] != 0.0) {
+              int q = (int)(norm_src[ti][jj] / norm_coef[ti][jj] + 0.5);
+              if (q > 254) q = 254;
+              if (q < 1) q = 1;
+              P.quant_tbl[ti][jj] = (uint16_t)q;
+            }
+          }
+          pass_number++;                                       /* the trellis pass */
         }
       }
     }

@@ -52,7 +52,7 @@ int  orc_make_derived(const b200jpeg_huff_tbl *t, int is_dc, unsigned *ehufco, u
 /* quantize_trellis on one block row (jcdctmgr.c:936-1330), natural-order blocks */
 void orc_trellis_row(const b200jpeg_params *p, const unsigned char *dcsi, const unsigned char *acsi,
                      int16_t *coef_blocks, const int16_t *src, int num_blocks,
-                     const uint16_t *qtbl, int16_t *last_dc_val, const int16_t *coef_above, const int16_t *src_above, int Ss, int Se);
+                     const uint16_t *qtbl, int16_t *last_dc_val, const int16_t *coef_above, const int16_t *src_above, int Ss, int Se, double *norm_src, double *norm_coef);
 
 #ifdef __cplusplus
 }
