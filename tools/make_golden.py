@@ -90,6 +90,11 @@ SWITCH_SETS_EXTRA = [
     ["-baseline", "-quality", "75", "-trellis-dc-ver-weight", "1.0"],
     ["-quality", "85", "-trellis-dc-ver-weight", "0.5", "-sample", "2x2"],
     ["-fastcrush", "-quality", "60", "-trellis-dc-ver-weight", "2.5", "-sample", "1x2"],
+    # cjpeg's tuning presets (cjpeg.c:678-704): base table index + lambda scales; -tune-psnr has lambda_log_scale2 = 0,
+    # i.e. the constant-lambda branch of quantize_trellis (jcdctmgr.c:1031-1035)
+    ["-tune-psnr"], ["-tune-ssim"], ["-tune-ms-ssim"], ["-tune-hvs-psnr"],
+    ["-tune-psnr", "-quality", "85", "-baseline"],
+    ["-baseline", "-lambda1", "10.5", "-lambda2", "0", "-quality", "70"],
     ["-revert", "-sample", "3x2"],
     ["-baseline", "-quality", "75", "-sample", "4x2"],
     ["-quality", "75", "-sample", "3x1"],
