@@ -113,3 +113,17 @@ def test_no_cpu_fallback(built):
     with pytest.raises(mj.B200JpegError) as ei:
         mj.Encoder(0)
     assert ei.value.code == -3
+
+
+def test_shim_exports_the_interposed_entry_points(built):
+    """The libjpeg interposition library defines exactly the calls INTEGRATION.md says it takes over."""
+    import subprocess
+    shim = os.path.join(ROOT, "integration", "_build", "libjpeg_b200shim.so")
+    if not os.path.exists(shim):
+        pytest.skip("shim not built (needs the reference's headers at build time)")
+    out = subprocess.check_output(["nm", "-D", "--defined-only", shim], text=True)
+    have = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    want = {"jpeg_start_compress", "jpeg_write_scanlines", "jpeg12_write_scanlines", "jpeg_write_raw_data", "jpeg_write_coefficients",
+            "jpeg_finish_compress", "jpeg_abort_compress", "jpeg_destroy_compress", "jpeg_write_marker", "jpeg_write_m_header", "jpeg_write_m_byte"}
+    assert want <= have, want - have
+    assert not {s for s in have if s.startswith("jpeg") and s not in want}, "an undocumented libjpeg symbol is interposed"
