@@ -1,6 +1,6 @@
 #!/bin/bash
 # Development aid, runs on the GPU box: stage times of the default pipeline for the main library and each variant named.
-#   tools/ab.sh old a r   (variants from tools/build_variant.sh)
+#   tools/ab.sh v1 v2   (variants built by tools/build_variant.sh v1 -DSOME_SWITCH=1 ...)
 for V in "" "$@"; do
   B200JPEG_LIB_VARIANT=$V B200JPEG_CHUNK_IMAGES=64 B200JPEG_STREAMS=1 timeout 150 python bench.py --batch 64 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_${V:-main}.json 2> gpurun_out/ab_${V:-main}.err
   python - "$V" <<'PY'
