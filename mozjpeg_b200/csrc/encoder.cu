@@ -1256,7 +1256,11 @@ int b200jpeg_encode_batch_coefs(b200jpeg_encoder *enc, const b200jpeg_params *p,
   for (int ci = 0; ci < p->num_components && ci < 4; ci++) {
     rd.plane[ci] = reinterpret_cast<const uint8_t *>(planes[ci]); rd.pitch[ci] = row_pitch_blocks[ci] * 128; rd.stride[ci] = image_stride_blocks[ci] * 128;
   }
-  return encode_common(enc, p, nullptr, planes_on_device, 0, 0, n_images, false, &rd);
+  // the switches of the forward stage have no meaning on this path (and must not trip its 12-bit rules: jpegtran's
+  // object still carries the profile's overshoot_deringing = TRUE)
+  b200jpeg_params q = *p;
+  q.overshoot_deringing = 0; q.smoothing_factor = 0; q.dct_method = B200JPEG_DCT_ISLOW;
+  return encode_common(enc, &q, nullptr, planes_on_device, 0, 0, n_images, false, &rd);
 }
 
 int b200jpeg_get_output(b200jpeg_encoder *e, int i, const uint8_t **data, size_t *size)

@@ -1185,7 +1185,7 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
   e->p = p; e->nc = p->num_components; e->W = p->image_width; e->H = p->image_height;
   e->raw_planes = g_raw_planes; e->raw_pitch = g_raw_pitch;
   /* 12-bit: no JBUF_REQUANT => no trellis (jccoefct.c:132-138); deringing is not usable at 12 bits (jcdctmgr.c:419) */
-  if (p->data_precision == 12 && (p->trellis_quant || p->overshoot_deringing)) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
+  if (p->data_precision == 12 && !g_coef_planes && (p->trellis_quant || p->overshoot_deringing)) { free(t); return B200JPEG_ERR_UNSUPPORTED; }   /* (no forward stage when transcoding) */
   if ((p->data_precision != 8 && p->data_precision != 12) || (p->dct_method != B200JPEG_DCT_ISLOW && p->data_precision != 8) ||
       p->trellis_num_loops < 1) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   e->hmax = e->vmax = 1;

@@ -90,3 +90,30 @@ def test_device_transcode_batch_and_roundtrip(encoder):
     # round trip: same parameters as the encode, minus the trellis (its result is already in the coefficients)
     q = penc.copy(); q.trellis_quant = 0
     assert encoder.encode_batch_coefs(q, stacked) == srcs
+
+
+def test_oracle_transcode_live_against_reference_odd_sources(built):
+    """Sources the recorded cases do not have: 16-bit quantization tables, an RGB-colourspace file, restart markers in
+    the source, 12-bit precision - straight against the reference's jpegtran where oracle/_ref is available."""
+    from mozjpeg_b200 import jpegtran as T, _abi as A
+    from mozjpeg_b200.synth import synth_image12
+    from oracle import oracle as O
+    if not (O.ref_available() and os.path.exists(os.path.join(O.REF_DIR, "jpegtran"))):
+        pytest.skip("oracle/_ref not built")
+    im = O.synth_image(3, 120, 72)
+    srcs = []
+    for esw in (["-revert", "-quality", "3"], ["-quality", "12", "-sample", "2x2"], ["-revert", "-rgb"], ["-revert", "-progressive", "-restart", "1"]):
+        try:
+            srcs.append(O.ref_encode(im, esw))
+        except ValueError:
+            srcs.append(O._ref_cjpeg_pixels(im, esw))
+    srcs.append(O.ref_encode(synth_image12(4, 120, 72), ["-precision", "12", "-quality", "75", "-notrellis", "-noovershoot", "-baseline"]))
+    for src in srcs:
+        planes = O.ref_read_coefs(src)["coefs"]
+        info = T.parse_header(src)
+        for tsw in ([], ["-revert"], ["-progressive"], ["-revert", "-optimize"]):
+            p, prefer_smallest = T.params_for_transcode(info, tsw)
+            out = O.oracle_encode_coefs(p, planes)
+            if prefer_smallest and p.compress_profile == A.PROFILE_MAX_COMPRESSION and len(src) < len(out):
+                out = src
+            assert out == O.ref_jpegtran(src, tsw), (info.data_precision, tsw)
