@@ -12,6 +12,7 @@ from the source file's header and sequences the same API calls,
 
     jpeg_create_compress ; parse_switches(for_real=FALSE)        jpegtran.c:545-556
     jpeg_copy_critical_parameters                                jpegtran.c:700
+    jtransform_adjust_parameters (1x1 sampling for gray sources) jpegtran.c:706
     parse_switches(for_real=TRUE)                                jpegtran.c:737
     jpeg_write_coefficients ; jpeg_finish_compress               jpegtran.c:750-765
     keep the input if it is smaller (prefer_smallest)            jpegtran.c:772-775
@@ -198,6 +199,9 @@ def params_for_transcode(src: SourceInfo, switches: Sequence[str]) -> Tuple[A.Pa
     p0.compress_profile = A.PROFILE_MAX_COMPRESSION
     _parse(p0, list(switches), False)
     p = _copy_critical_parameters(src, p0.compress_profile)
+    if src.num_components == 1:                       # jtransform_adjust_parameters (transupp.c:2072-2079): a single-component
+        p.comp_info[0].h_samp_factor = 1              # source always leaves with 1x1 sampling, with or without -grayscale
+        p.comp_info[0].v_samp_factor = 1
     prefer_smallest = _parse(p, list(switches), True)
     if p.num_scans == 0:                              # jpeg_write_coefficients has no such step; kept for symmetry with
         p.optimize_scans = 0                          # jpeg_start_compress (a sequential file has nothing to search)
