@@ -122,6 +122,7 @@ class RefCfg(C.Structure):
         ("lambda1", C.c_float), ("lambda2", C.c_float), ("tjapi", C.c_int), ("input_gray", C.c_int),
         ("ext_use_scans_in_trellis", C.c_int), ("ext_trellis_freq_split", C.c_int), ("ext_trellis_eob_opt", C.c_int),
         ("ext_trellis_q_opt", C.c_int), ("ext_trellis_num_loops", C.c_int),
+        ("has_dc_ver_weight", C.c_int), ("dc_ver_weight", C.c_float),
     ]
 
 
@@ -182,6 +183,7 @@ def refcfg_from_switches(switches: Sequence[str], input_gray: bool = False) -> R
         elif s == "-grayscale": c.grayscale = 1
         elif s == "-precision": c.precision = int(next(it))
         elif s == "-quant-table": c.quant_table = int(next(it))
+        elif s == "-trellis-dc-ver-weight": c.has_dc_ver_weight = 1; c.dc_ver_weight = float(next(it))
         elif s == "-lambda1": c.has_lambda1 = 1; c.lambda1 = float(next(it))
         elif s == "-lambda2": c.has_lambda2 = 1; c.lambda2 = float(next(it))
         else: raise ValueError(f"refshim: unsupported switch {s}")

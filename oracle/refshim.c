@@ -44,6 +44,7 @@ typedef struct {
   int input_gray;      /* input buffer is 1 component grayscale */
   /* extension parameters cjpeg has no switch for (jpeg_c_set_*_param, jcext.c); -1 = leave the default */
   int ext_use_scans_in_trellis, ext_trellis_freq_split, ext_trellis_eob_opt, ext_trellis_q_opt, ext_trellis_num_loops;
+  int has_dc_ver_weight; float dc_ver_weight;   /* -trellis-dc-ver-weight W (cjpeg.c:667-672) */
 } refshim_cfg;
 
 struct my_err { struct jpeg_error_mgr pub; jmp_buf jb; char msg[JMSG_LENGTH_MAX]; };
@@ -77,6 +78,7 @@ static void apply_switches(j_compress_ptr cinfo, const refshim_cfg *cfg, int for
   if (cfg->ext_trellis_eob_opt >= 0) jpeg_c_set_bool_param(cinfo, JBOOLEAN_TRELLIS_EOB_OPT, cfg->ext_trellis_eob_opt);
   if (cfg->ext_trellis_q_opt >= 0) jpeg_c_set_bool_param(cinfo, JBOOLEAN_TRELLIS_Q_OPT, cfg->ext_trellis_q_opt);
   if (cfg->ext_trellis_num_loops >= 0) jpeg_c_set_int_param(cinfo, JINT_TRELLIS_NUM_LOOPS, cfg->ext_trellis_num_loops);
+  if (cfg->has_dc_ver_weight) jpeg_c_set_float_param(cinfo, JFLOAT_TRELLIS_DELTA_DC_WEIGHT, cfg->dc_ver_weight);
   if (cfg->has_lambda1) jpeg_c_set_float_param(cinfo, JFLOAT_LAMBDA_LOG_SCALE1, cfg->lambda1);
   if (cfg->has_lambda2) jpeg_c_set_float_param(cinfo, JFLOAT_LAMBDA_LOG_SCALE2, cfg->lambda2);
   if (cfg->optimize) cinfo->optimize_coding = TRUE;
