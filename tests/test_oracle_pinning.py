@@ -6,6 +6,8 @@
 * live, byte for byte, against oracle/_ref when it is built (container and GPU
   box both carry it; skipped otherwise).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -72,3 +74,16 @@ def test_stage_oracles_vs_reference_internals(built):
         O.orc().orc_fdct_islow(a.ctypes.data_as(C.POINTER(C.c_int)))
         O.ref().refshim_fdct_islow(b.ctypes.data_as(C.POINTER(C.c_int)))
         assert (a == b).all()
+
+
+def test_random_switch_sets_live_against_reference_cjpeg(built):
+    """tools/fuzz_vs_reference.py, a short run: random cjpeg switch sets (profiles, quality, sampling, restarts, DCT,
+    smoothing, tuning presets, lambda, DC weight) on random small images - reference binary vs mirror + oracle."""
+    import subprocess
+    import sys
+    from common import ROOT
+    from oracle import oracle as O
+    if not (O.ref_available() and os.path.exists(os.path.join(O.REF_DIR, "cjpeg"))):
+        pytest.skip("oracle/_ref not built")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_vs_reference.py"), "2024", "60"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-500:]
