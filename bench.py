@@ -180,6 +180,27 @@ def run_reference_arm(a, rank, world):
     print(json.dumps(line))
 
 
+def rank_seeds(rank: int, distinct: int):
+    """Synthetic-image seeds of one rank: the batch shards by rank, every rank encodes images of its own."""
+    return [1000 * (rank + 1) + i for i in range(distinct)]
+
+
+def max_over_ranks(value: float, world: int, device) -> float:
+    """The contract's timing rule: a multi-rank number is the MAX over ranks (one all-reduce at the end; the data path
+    itself has no collective).  `device` is where the process group lives (cuda:<local> for NCCL, cpu for gloo)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_mp_per_step(world: int, batch: int, width: int, height: int) -> float:
+    """Megapixels one step encodes over ALL ranks (weak scaling: every rank has its own full batch)."""
+    return world * batch * width * height / 1e6
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -207,7 +228,7 @@ def main():
     p = mj.params_from_switches(sw, W, H)
 
     # ---- synthetic inputs: `distinct` images per rank, tiled to B (6.4 GB at the default size >> 126 MB L2)
-    base = np.stack([synth_image(1000 * (rank + 1) + i, W, H) for i in range(a.distinct)])
+    base = np.stack([synth_image(seed, W, H) for seed in rank_seeds(rank, a.distinct)])
     host = torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True)
     hb = torch.from_numpy(base)
     for i in range(B):
@@ -255,11 +276,8 @@ def main():
     resident_chunk = enc.chunk_images()
     enc.set_streams(2)
     clk = clocks.stop()
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    mp_per_step = world * B * W * H / 1e6
+    ms_total = max_over_ranks(ms_total, world, dev)
+    mp_per_step = whole_job_mp_per_step(world, B, W, H)
     value = mp_per_step * a.steps / (ms_total / 1e3)
 
     # ---- end to end through the public API: host pixels in, JPEG files out ----
@@ -274,10 +292,7 @@ def main():
         ev1.record(stream)
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3     # includes host-side file assembly, which events do not see
-        t = torch.tensor([wall_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        e2e_ms = max_over_ranks(wall_ms, world, dev)
         e2e = {"value": mp_per_step * a.steps / (e2e_ms / 1e3), "unit": "MP/s", "h2d_bytes_per_step": B * W * H * 3,
                "d2h_bytes_per_step": int(jpeg_bytes), "ms_per_step": e2e_ms / a.steps, "timer": "host wall clock around the API calls, max over ranks"}
     else:
