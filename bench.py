@@ -34,25 +34,55 @@ if ROOT not in sys.path:
 import numpy as np
 
 
+# BASELINE.json configs[1..4] (configs[0] is the reference's own CPU-runnable case, a parity test) + the library default
+WORKLOADS = {
+    "cfg2": dict(batch=256, width=3840, height=2160, switches="-baseline -quality 75 -sample 2x2", scaling="weak",
+                 label="BASELINE.json configs[1]: batch of 256 synthetic 3840x2160 RGB, q75 4:2:0, trellis on, baseline"),
+    "cfg3": dict(batch=128, width=3840, height=2160, switches="-fastcrush -quality 75 -sample 2x2", scaling="weak",
+                 label="BASELINE.json configs[2]: 4K batch, progressive (jcphuff), 9-scan jpgcrush script of jpeg_simple_progression"),
+    "cfg4": dict(batch=1024, width=1920, height=1080, switches="-baseline -quality 75 -sample 2x2", scaling="strong", sweep=(50, 75, 90),
+                 label="BASELINE.json configs[3]: 1024-image 1920x1080 batch sharded over the GPUs, q50/75/90 sweep (value = q75)"),
+    "cfg5": dict(batch=64, width=3840, height=2160, switches="-precision 12 -sample 1x1 -quality 75 -notrellis -noovershoot -baseline", scaling="weak",
+                 label="BASELINE.json configs[4]: 12-bit 4:4:4 3840x2160 (jfdctint 12-bit; the reference has no trellis at 12 bits)"),
+    "default": dict(batch=32, width=3840, height=2160, switches="-quality 75 -sample 2x2", scaling="weak",
+                    label="library default profile (progressive + 64-candidate scan search), 4K q75 4:2:0"),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--width", type=int, default=3840)
-    ap.add_argument("--height", type=int, default=2160)
-    ap.add_argument("--switches", default="-baseline -quality 75 -sample 2x2",
-                    help="cjpeg switch set naming the profile (config 2 of BASELINE.json)")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="BASELINE.json configuration (cfg2 = configs[1], the headline)")
+    ap.add_argument("--batch", type=int, default=None, help="images per step (per GPU for weak scaling, whole job for cfg4)")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--switches", default=None, help="cjpeg switch set naming the profile")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic images tiled to fill the batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-parity-gate", action="store_true", help="development only: skip the untimed byte comparison with the reference")
+    a = ap.parse_args()
+    w = WORKLOADS[a.workload]
+    a.custom = any(v is not None for v in (a.batch, a.width, a.height, a.switches))
+    for k in ("batch", "width", "height", "switches"):
+        if getattr(a, k) is None:
+            setattr(a, k, w[k])
+    a.scaling = w["scaling"]; a.sweep = w.get("sweep"); a.label = w["label"]
+    a.precision = 12 if "-precision 12" in a.switches else 8
+    return a
 
 
 def workload_name(a):
-    return f"batch of {a.batch} synthetic {a.width}x{a.height} RGB, cjpeg {a.switches} (BASELINE.json configs[1] shape)"
+    if a.custom:
+        return f"batch of {a.batch} synthetic {a.width}x{a.height} {'12-bit ' if a.precision == 12 else ''}RGB, cjpeg {a.switches} (variation of {a.workload})"
+    return f"{a.label} (cjpeg {a.switches})"
+
+
+def metric_name(a):
+    return "megapixels/sec encode (4K RGB q75 4:2:0)" if a.workload == "cfg2" else f"megapixels/sec encode ({a.workload}: {a.width}x{a.height}, cjpeg {a.switches})"
 
 
 # ---------------------------------------------------------------------------
@@ -105,21 +135,21 @@ class ClockSampler:
 # the reference's CPU encoder on the host cores (oracle/_ref via refshim)
 # ---------------------------------------------------------------------------
 def cpu_reference_run(images, switches, threads, reps):
-    """Encode len(images)*reps... each thread encodes `reps` images with the
-    UNMODIFIED reference library (ctypes releases the GIL).  Returns
-    (MP/s, kind, seconds)."""
+    """Each thread encodes `reps` images with the UNMODIFIED reference library
+    (oracle/_ref; ctypes releases the GIL).  Returns (MP/s, kind, seconds).
+    Never touches the product package: with the reference library absent the
+    oracle port stands in (kind "port")."""
     from oracle import oracle as O
-    import mozjpeg_b200 as mj
     use_ref = O.ref_available()
     h, w = images[0].shape[:2]
     if use_ref:
         O.ref()
         fn = lambda im: O.ref_encode(im, switches)
     else:
+        import mozjpeg_b200 as mj                     # parameter parsing only (cjpeg switch semantics)
         p = mj.params_from_switches(switches, w, h)
         O.orc()
         fn = lambda im: O.oracle_encode(p, im).jpeg
-    fn(images[0][:64, :64].copy()) if False else None
     done = [0] * threads
 
     def work(t):
@@ -152,15 +182,18 @@ def host_threads():
 
 
 def run_reference_arm(a, rank, world):
-    """--impl reference: the reference's own CPU implementation, all host threads."""
+    """--impl reference: the reference's own CPU implementation (oracle/_ref, C path: this image has no NASM), all the
+    host threads the container may use, on the same workload.  Each step is a bounded sample (one image per host thread)
+    so that K+W steps end within minutes.  The process never imports the product package."""
     if rank != 0:
         return
-    from mozjpeg_b200.synth import synth_image
+    os.environ["B200JPEG_ORACLE_STANDALONE"] = "1"
+    from oracle import oracle as O
     sw = a.switches.split()
     threads = host_threads()
-    imgs = [synth_image(1000 + i, a.width, a.height) for i in range(min(a.distinct, 4))]
+    gen = O.synth_image12 if a.precision == 12 else O.synth_image
+    imgs = [gen(1000 + i, a.width, a.height) for i in range(min(a.distinct, 8))]
     per = a.width * a.height / 1e6
-    # size the step so K+W steps end within a few minutes: 1 image per thread per step
     reps = 1
     for _ in range(a.warmup):
         cpu_reference_run(imgs, sw, threads, reps)
@@ -169,15 +202,39 @@ def run_reference_arm(a, rank, world):
         _, kind, _ = cpu_reference_run(imgs, sw, threads, reps)
     dt = time.perf_counter() - t0
     val = a.steps * threads * reps * per / dt
-    sample = f"{threads * reps} images {a.width}x{a.height} per step, one per host thread"
-    line = {"impl": "reference", "metric": "megapixels/sec encode (4K RGB q75 4:2:0)", "value": val, "unit": "MP/s",
+    sample = f"{threads * reps} images {a.width}x{a.height} per step (one per host thread, {len(imgs)} distinct), a bounded sample of the batch of {a.batch}"
+    line = {"impl": "reference", "metric": metric_name(a), "value": val, "unit": "MP/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/fp32 (CPU)", "data": "synthetic",
+            "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "int32 DCT / fp32 trellis costs (CPU, C path without SIMD)", "data": "synthetic",
             "config": {"workload": workload_name(a), "sample_per_step": sample},
             "cpu_baseline": {"value": val, "unit": "MP/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def bind_to_gpu_numa_node(local: int):
+    """Run this rank's host thread (and so its pinned allocations, by first touch) on the NUMA node the GPU hangs off:
+    on the 8-GPU boxes GPU0-3 / GPU4-7 sit on different sockets and staging across the socket link costs ~10 % of
+    the end-to-end rate.  Best effort; returns a note for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return f"numa node {node}: no allowed cpu"
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node} ({len(allowed)} cpus)"
+    except Exception as e:                             # containers without sysfs access: leave the affinity alone
+        return f"not bound ({type(e).__name__})"
 
 
 def rank_seeds(rank: int, distinct: int):
@@ -201,44 +258,39 @@ def whole_job_mp_per_step(world: int, batch: int, width: int, height: int) -> fl
     return world * batch * width * height / 1e6
 
 
-def main():
-    a = parse()
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if a.impl == "reference":
-        run_reference_arm(a, rank, world)
-        return
+def parity_gate(outputs, images, switches, who):
+    """Untimed: the bytes the timed call produced for a few images must be the reference's bytes for the same pixels
+    and switches (oracle/_ref when it is there, else the oracle port).  A mismatch voids the run."""
+    from oracle import oracle as O
+    use_ref = O.ref_available()
+    if not use_ref:
+        import mozjpeg_b200 as mj
+    res = [None] * len(images)
 
-    import torch
-    import torch.distributed as dist
+    def one(k):
+        im = images[k]
+        if use_ref:
+            res[k] = O.ref_encode(im, switches)
+        else:
+            res[k] = O.oracle_encode(mj.params_from_switches(switches, im.shape[1], im.shape[0]), im).jpeg
+    ths = [threading.Thread(target=one, args=(k,)) for k in range(len(images))]
+    for t in ths: t.start()
+    for t in ths: t.join()
+    bad = [k for k in range(len(images)) if res[k] != outputs[k]]
+    if bad:
+        raise SystemExit(f"bench.py: PARITY GATE FAILED ({who}): output of image(s) {bad} differs from the reference's bytes "
+                         f"({[len(outputs[k]) for k in bad]} vs {[len(res[k]) for k in bad]} bytes); no number is reported")
+    return {"checked_images": len(images), "against": "oracle/_ref (unmodified reference)" if use_ref else "oracle port", "identical": True}
+
+
+def measure(a, sw, enc, host, devbuf, base, rank, world, local, dev, stream, dist, torch):
+    """One configuration (switch set) on the already staged batch: resident value, e2e, stage times, parity gate."""
     import mozjpeg_b200 as mj
-    from mozjpeg_b200.synth import synth_image
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    sw = a.switches.split()
-    W, H, B = a.width, a.height, a.batch
+    W, H = a.width, a.height
+    B = host.shape[0]
     p = mj.params_from_switches(sw, W, H)
-
-    # ---- synthetic inputs: `distinct` images per rank, tiled to B (6.4 GB at the default size >> 126 MB L2)
-    base = np.stack([synth_image(seed, W, H) for seed in rank_seeds(rank, a.distinct)])
-    host = torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True)
-    hb = torch.from_numpy(base)
-    for i in range(B):
-        host[i].copy_(hb[i % a.distinct])
-    devbuf = host.to(dev, non_blocking=False)
-    row_pitch, image_stride = W * 3, W * H * 3
-
-    enc = mj.Encoder(local)
-    stream = torch.cuda.current_stream()
-    enc.set_stream(stream.cuda_stream)
+    sb = 2 if a.precision == 12 else 1
+    row_pitch, image_stride = W * 3 * sb, W * H * 3 * sb
 
     def step_resident():
         enc.encode_batch_ptr(p, devbuf.data_ptr(), True, row_pitch, image_stride, B, device_only=True)
@@ -259,7 +311,6 @@ def main():
     clocks = ClockSampler(local); clocks.start()
     l0 = enc.kernel_launches()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-    stage_acc = {}
     ev0.record(stream)
     for _ in range(a.steps):
         step_resident()
@@ -272,34 +323,104 @@ def main():
     enc.set_streams(1)
     step_resident()
     torch.cuda.synchronize()
-    stage_acc = {k: v * a.steps for k, v in enc.stage_times().items()}
-    resident_chunk = enc.chunk_images()
+    stages = {k: v for k, v in enc.stage_times().items() if k not in ("h2d", "h2d_wait")}
+    chunk = enc.chunk_images()
     enc.set_streams(2)
     clk = clocks.stop()
     ms_total = max_over_ranks(ms_total, world, dev)
-    mp_per_step = whole_job_mp_per_step(world, B, W, H)
-    value = mp_per_step * a.steps / (ms_total / 1e3)
 
     # ---- end to end through the public API: host pixels in, JPEG files out ----
-    e2e = None
+    e2e_ms = None; jpeg_bytes = 0
     if not a.no_e2e:
         jpeg_bytes = step_e2e()                       # warm (pinned output buffers get allocated)
         barrier()
         t0 = time.perf_counter()
-        ev0.record(stream)
         for _ in range(a.steps):
             jpeg_bytes = step_e2e()
-        ev1.record(stream)
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3     # includes host-side file assembly, which events do not see
         e2e_ms = max_over_ranks(wall_ms, world, dev)
-        e2e = {"value": mp_per_step * a.steps / (e2e_ms / 1e3), "unit": "MP/s", "h2d_bytes_per_step": B * W * H * 3,
-               "d2h_bytes_per_step": int(jpeg_bytes), "ms_per_step": e2e_ms / a.steps, "timer": "host wall clock around the API calls, max over ranks"}
     else:
-        step_e2e_bytes = 0
+        step_e2e()                                     # the parity gate needs files
+        jpeg_bytes = sum(enc.output_size(i) for i in range(B))
 
-    # ---- roofline of the dominant kernel (CUDA events inside the library, averaged over the timed steps) ----
-    stages = {k: v / a.steps for k, v in stage_acc.items() if k not in ("h2d", "h2d_wait")}
+    # ---- parity gate (untimed): first and last image of this rank's batch against the reference ----
+    gate = None
+    if not a.no_parity_gate:
+        idx = sorted({0, B - 1})
+        gate = parity_gate([enc.get_output(i) for i in idx], [base[i % len(base)] for i in idx], sw, f"rank {rank}, {' '.join(sw)}")
+    return {"ms_total": ms_total, "launches": launches, "stages": stages, "chunk": chunk, "clk": clk, "e2e_ms": e2e_ms,
+            "jpeg_bytes": jpeg_bytes, "gate": gate, "B": B}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference_arm(a, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mozjpeg_b200 as mj
+    from mozjpeg_b200.synth import synth_image, synth_image12
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)                # before the pinned buffers are allocated (first touch)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    W, H = a.width, a.height
+    # weak scaling: every rank encodes its own full batch; strong (cfg4): the batch is split over the ranks
+    B = a.batch if a.scaling == "weak" else (a.batch + world - 1) // world
+    global_images = B * world
+
+    # ---- synthetic inputs: `distinct` images per rank, tiled to B (inputs >> 126 MB L2)
+    gen = synth_image12 if a.precision == 12 else synth_image
+    cache = os.environ.get("B200JPEG_BENCH_CACHE")           # development aid: reuse the synthetic images between A/B runs
+    cpath = os.path.join(cache, f"synth_{W}x{H}_{a.precision}_{a.distinct}_{rank}.npy") if cache else None
+    if cpath and os.path.exists(cpath):
+        base = np.load(cpath)
+    else:
+        base = np.stack([gen(seed, W, H) for seed in rank_seeds(rank, a.distinct)])
+        if cpath:
+            np.save(cpath, base)
+    host = torch.empty((B, H, W, 3), dtype=torch.int16 if a.precision == 12 else torch.uint8, pin_memory=True)   # 12-bit samples: 16-bit words
+    hb = torch.from_numpy(base.view(np.int16) if a.precision == 12 else base)
+    for i in range(B):
+        host[i].copy_(hb[i % a.distinct])
+    devbuf = host.to(dev, non_blocking=False)
+    in_bytes = W * H * 3 * (2 if a.precision == 12 else 1)
+
+    enc = mj.Encoder(local)
+    stream = torch.cuda.current_stream()
+    enc.set_stream(stream.cuda_stream)
+
+    runs = {}
+    if a.sweep and not a.custom:
+        for q in a.sweep:
+            sw = a.switches.replace("-quality 75", f"-quality {q}").split()
+            runs[q] = measure(a, sw, enc, host, devbuf, base, rank, world, local, dev, stream, dist, torch)
+        r = runs[75]
+    else:
+        r = measure(a, a.switches.split(), enc, host, devbuf, base, rank, world, local, dev, stream, dist, torch)
+
+    mp_per_step = global_images * W * H / 1e6
+    value = mp_per_step * a.steps / (r["ms_total"] / 1e3)
+    e2e = None
+    if r["e2e_ms"] is not None:
+        e2e = {"value": mp_per_step * a.steps / (r["e2e_ms"] / 1e3), "unit": "MP/s", "h2d_bytes_per_step": B * in_bytes,
+               "d2h_bytes_per_step": int(r["jpeg_bytes"]), "ms_per_step": r["e2e_ms"] / a.steps,
+               "timer": "host wall clock around the API calls, max over ranks", "bytes_are": "per rank"}
+
+    # ---- roofline of the dominant kernel (CUDA events inside the library; one single-stream pass over the batch) ----
+    stages = r["stages"]
     dom = max(stages, key=stages.get)
     peaks = {}
     try:
@@ -308,42 +429,53 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    out_bytes = enc.last_scan_bytes() / B if not a.no_e2e else 0.0
-    # one launch of the dominant kernel covers one chunk of the batch; stage times are summed over the chunks,
-    # so bytes per launch / average launch duration == batch bytes / summed stage time
-    imgs_per_launch = resident_chunk
-    n_launch = (B + imgs_per_launch - 1) // imgs_per_launch
-    alg_bytes = imgs_per_launch * (W * H * 3 + out_bytes)            # input bytes + JPEG bytes per image
-    achieved = alg_bytes / (stages[dom] / n_launch / 1e3) / 1e9
-    traffic = None
+    out_bytes = r["jpeg_bytes"] / B
+    # the dominant stage is launched once per chunk of the batch; its stage time is the sum over the chunks, so
+    # (algorithmic bytes of the whole batch) / (summed time) is the mean over launches of bytes-per-launch / duration
+    chunk = r["chunk"]
+    per_launch = [min(chunk, B - i) for i in range(0, B, chunk)]
+    alg_per_image = in_bytes + out_bytes                               # input bytes + JPEG bytes per image
+    achieved = B * alg_per_image / (stages[dom] / 1e3) / 1e9
+    pipeline = B * alg_per_image / (sum(stages.values()) / 1e3) / 1e9
+    traffic = None; traffic_src = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
-        if prof.get("kernel") == dom:
-            traffic = prof.get("dram_bytes_per_image") * imgs_per_launch
+        if prof.get("kernel") == dom and a.workload == "cfg2":
+            traffic = prof.get("dram_bytes_per_image") * max(per_launch); traffic_src = prof.get("source")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel_ms": stages[dom] / n_launch, "launches_per_step": n_launch,
-                "images_per_launch": imgs_per_launch,
-                "algorithmic_bytes_per_launch": alg_bytes, "stage_ms": stages}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": stages[dom] / len(per_launch),
+                "launches_per_step": len(per_launch), "images_per_launch": per_launch,
+                "algorithmic_bytes_per_image": alg_per_image, "algorithmic_bytes_per_launch": max(per_launch) * alg_per_image,
+                "pipeline_achieved": pipeline, "pipeline_frac": pipeline / peak, "stage_ms": stages}
 
     # ---- the reference's CPU encoder on this box's host cores (rank 0, N=1 only; bounded sample) ----
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         threads = host_threads()
         imgs = [base[i] for i in range(min(4, a.distinct))]
-        reps = 3
-        v, kind, secs = cpu_reference_run(imgs, sw, threads, reps)
+        reps = 3 if W * H > 4e6 else 8
+        v, kind, secs = cpu_reference_run(imgs, a.switches.split(), threads, reps)
         cpu = {"value": v, "unit": "MP/s", "cores": threads, "kind": kind,
+               "simd": "none (C path: no NASM in this image; the trellis, 62 % of the reference's time, has no SIMD version)",
                "sample": f"{threads * reps} images {W}x{H} ({reps} per host thread, {secs:.1f} s wall = {secs * threads:.0f} CPU-seconds), same switches"}
 
     if rank == 0:
-        line = {"metric": "megapixels/sec encode (4K RGB q75 4:2:0)", "value": value, "unit": "MP/s", "n_gpus": world,
-                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8 in / int32 DCT / fp32 trellis costs / u8 out", "data": "synthetic",
-                "config": {"workload": workload_name(a), "images_per_gpu": B, "global_images": B * world,
-                           "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2" % (B * W * H * 3 / 1e9), "parallelism": f"images sharded over {world} GPU(s), no data-path collective"},
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        cfg = {"workload": workload_name(a), "images_per_gpu": B, "global_images": global_images,
+               "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2" % (B * in_bytes / 1e9),
+               "parallelism": f"images sharded over {world} GPU(s), no data-path collective", "host_affinity": numa,
+               "parity_gate": r["gate"]}
+        if runs:
+            cfg["sweep"] = {f"q{q}": {"value": mp_per_step * a.steps / (x["ms_total"] / 1e3),
+                                      "e2e": (mp_per_step * a.steps / (x["e2e_ms"] / 1e3)) if x["e2e_ms"] else None,
+                                      "ms_per_step": x["ms_total"] / a.steps, "parity_gate": x["gate"],
+                                      "stage_ms": x["stages"]} for q, x in runs.items()}
+        line = {"metric": metric_name(a), "value": value, "unit": "MP/s", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_total"] / a.steps, "higher_is_better": True,
+                "scaling": a.scaling, "vs_baseline": None,
+                "dtype": ("u16 (12-bit) in / int32 DCT / u8 out" if a.precision == 12 else "u8 in / int32 DCT / fp32 trellis costs / u8 out"), "data": "synthetic",
+                "config": cfg, "clocks": r["clk"], "e2e": e2e, "gpu_launches": int(r["launches"]), "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

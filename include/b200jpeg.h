@@ -34,8 +34,18 @@ extern "C" {
 #define B200JPEG_DCTSIZE2       64
 
 /* J_COLOR_SPACE subset (jpeglib.h:243-266), same numeric values. */
-enum { B200JPEG_CS_UNKNOWN = 0, B200JPEG_CS_GRAYSCALE = 1, B200JPEG_CS_RGB = 2, B200JPEG_CS_YCbCr = 3 };
-/* J_DCT_METHOD (jpeglib.h:275-279). Only ISLOW is on the device path so far. */
+enum { B200JPEG_CS_UNKNOWN = 0, B200JPEG_CS_GRAYSCALE = 1, B200JPEG_CS_RGB = 2, B200JPEG_CS_YCbCr = 3,
+       /* input pixel orders of the RGB family (in_color_space only; jccolor.c:253-291 dispatches them into jccolext.c:30-75):
+        * 3 samples per pixel for EXT_RGB / EXT_BGR, 4 for the others (the filler / alpha sample is ignored) */
+       B200JPEG_CS_EXT_RGB = 6, B200JPEG_CS_EXT_RGBX = 7, B200JPEG_CS_EXT_BGR = 8, B200JPEG_CS_EXT_BGRX = 9,
+       B200JPEG_CS_EXT_XBGR = 10, B200JPEG_CS_EXT_XRGB = 11, B200JPEG_CS_EXT_RGBA = 12, B200JPEG_CS_EXT_BGRA = 13,
+       B200JPEG_CS_EXT_ABGR = 14, B200JPEG_CS_EXT_ARGB = 15 };
+/* RGB-family test and layout of an in_color_space value: samples per pixel, index of the first colour sample, blue-first */
+#define B200JPEG_CS_IS_RGB(cs) ((cs) == B200JPEG_CS_RGB || ((cs) >= B200JPEG_CS_EXT_RGB && (cs) <= B200JPEG_CS_EXT_ARGB))
+#define B200JPEG_CS_PIXELSIZE(cs) (((cs) == B200JPEG_CS_RGB || (cs) == B200JPEG_CS_EXT_RGB || (cs) == B200JPEG_CS_EXT_BGR) ? 3 : 4)
+#define B200JPEG_CS_FIRST(cs) (((cs) == B200JPEG_CS_EXT_XBGR || (cs) == B200JPEG_CS_EXT_XRGB || (cs) == B200JPEG_CS_EXT_ABGR || (cs) == B200JPEG_CS_EXT_ARGB) ? 1 : 0)
+#define B200JPEG_CS_BLUE_FIRST(cs) ((cs) == B200JPEG_CS_EXT_BGR || (cs) == B200JPEG_CS_EXT_BGRX || (cs) == B200JPEG_CS_EXT_XBGR || (cs) == B200JPEG_CS_EXT_BGRA || (cs) == B200JPEG_CS_EXT_ABGR)
+/* J_DCT_METHOD (jpeglib.h:275-279); all three are on the device path (IFAST / FLOAT at 8 bits). */
 enum { B200JPEG_DCT_ISLOW = 0, B200JPEG_DCT_IFAST = 1, B200JPEG_DCT_FLOAT = 2 };
 /* JINT_COMPRESS_PROFILE values (jpeglib.h:349-352). */
 enum { B200JPEG_PROFILE_MAX_COMPRESSION = 0x5D083AAD, B200JPEG_PROFILE_FASTEST = 0x2AEA5CB4 };

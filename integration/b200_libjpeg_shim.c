@@ -33,6 +33,7 @@
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -50,9 +51,14 @@ static struct {
   int raw; uint8_t *plane[4]; size_t plane_pitch[4], plane_rows[4];   /* jpeg_write_raw_data objects: the component planes so far */
   unsigned char *extra; size_t extra_len, extra_cap;         /* jpeg_write_marker segments, in call order */
   size_t header_len;                                         /* SOI + JFIF APP0 + Adobe APP14 (write_file_header, jcmarker.c:649-663) */
+  int total_passes;                                          /* what jinit_c_master_control would have counted (jcmaster.c:1114-1139) */
 } g_active[MAX_ACTIVE];
 static b200jpeg_encoder *g_idle_enc;          /* encoders are reused: creating one costs a CUDA context */
 static int g_no_device;
+/* libjpeg lets different threads work on different objects (libjpeg.txt, "Multiple-thread usage"): the slot table and
+ * the spare encoder are shared, so every access to them is under this lock; a slot's contents belong to the thread
+ * that owns the object. */
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 
 static int verbose(void) { const char *v = getenv("B200_SHIM_VERBOSE"); return v && v[0] == '1'; }
 static int required(void) { const char *v = getenv("B200_SHIM_REQUIRE"); return v && v[0] == '1'; }
@@ -72,15 +78,53 @@ static void *next_sym(const char *name)
 
 static int find_active(j_compress_ptr cinfo)
 {
-  for (int i = 0; i < MAX_ACTIVE; i++) if (g_active[i].cinfo == cinfo) return i;
-  return -1;
+  int r = -1;
+  pthread_mutex_lock(&g_lock);
+  for (int i = 0; i < MAX_ACTIVE; i++) if (g_active[i].cinfo == cinfo) { r = i; break; }
+  pthread_mutex_unlock(&g_lock);
+  return r;
 }
-static void release_slot(int i)
+/* reusable: the encoder is between images (a finished one); anything else (errors, abandoned objects) destroys it,
+ * because its streaming state cannot be reset from outside */
+static void release_slot_ex(int i, int reusable)
 {
-  if (g_idle_enc) b200jpeg_encoder_destroy(g_active[i].enc); else g_idle_enc = g_active[i].enc;
+  b200jpeg_encoder *enc = g_active[i].enc, *kill = NULL;
   free(g_active[i].extra);
   for (int k = 0; k < 4; k++) free(g_active[i].plane[k]);
+  pthread_mutex_lock(&g_lock);
+  if (reusable && !g_idle_enc) g_idle_enc = enc; else kill = enc;
   memset(&g_active[i], 0, sizeof g_active[i]);
+  pthread_mutex_unlock(&g_lock);
+  if (kill) b200jpeg_encoder_destroy(kill);
+}
+static void release_slot(int i) { release_slot_ex(i, 0); }
+/* a free slot and an encoder for `cinfo` (a stale slot of the same object is dropped first); -1 and *why set when
+ * there is none */
+static int claim_slot(j_compress_ptr cinfo, const char **why)
+{
+  int stale = find_active(cinfo);
+  if (stale >= 0) release_slot(stale);
+  int slot = -1;
+  b200jpeg_encoder *enc = NULL;
+  pthread_mutex_lock(&g_lock);
+  for (int i = 0; i < MAX_ACTIVE && slot < 0; i++) if (!g_active[i].cinfo) slot = i;
+  if (slot >= 0) {
+    enc = g_idle_enc; g_idle_enc = NULL;
+    memset(&g_active[slot], 0, sizeof g_active[slot]);
+    g_active[slot].cinfo = cinfo;                        /* reserved from here on */
+  }
+  const int no_device = g_no_device;
+  pthread_mutex_unlock(&g_lock);
+  if (slot < 0) { *why = "too many concurrent compressors"; return -1; }
+  if (!enc && !no_device) {
+    if (b200jpeg_encoder_create(&enc, 0) != B200JPEG_OK) { enc = NULL; pthread_mutex_lock(&g_lock); g_no_device = 1; pthread_mutex_unlock(&g_lock); }
+  }
+  if (!enc) {
+    pthread_mutex_lock(&g_lock); memset(&g_active[slot], 0, sizeof g_active[slot]); pthread_mutex_unlock(&g_lock);
+    *why = b200jpeg_last_error(); return -1;
+  }
+  g_active[slot].enc = enc;
+  return slot;
 }
 
 /* width_in_blocks / height_in_blocks as initial_setup computes them (jcmaster.c:215-236); the reference's master
@@ -129,6 +173,10 @@ static int fill_params(j_compress_ptr cinfo, boolean write_all_tables, b200jpeg_
   case JCS_GRAYSCALE: p->in_color_space = B200JPEG_CS_GRAYSCALE; break;
   case JCS_RGB: case JCS_EXT_RGB: p->in_color_space = B200JPEG_CS_RGB; break;
   case JCS_YCbCr: p->in_color_space = B200JPEG_CS_YCbCr; break;
+  /* the other pixel orders of the RGB family (jccolor.c:253-291): same numeric values as J_COLOR_SPACE */
+  case JCS_EXT_RGBX: case JCS_EXT_BGR: case JCS_EXT_BGRX: case JCS_EXT_XBGR: case JCS_EXT_XRGB:
+  case JCS_EXT_RGBA: case JCS_EXT_BGRA: case JCS_EXT_ABGR: case JCS_EXT_ARGB:
+    p->in_color_space = (int)cinfo->in_color_space; break;
   default: return 0;
   }
   switch (cinfo->jpeg_color_space) {
@@ -198,18 +246,11 @@ jpeg_start_compress(j_compress_ptr cinfo, boolean write_all_tables)
   if (cinfo->master->num_scans_luma == 0 || cinfo->scan_info == NULL || cinfo->num_scans == 0)
     cinfo->master->optimize_scans = FALSE;
   if (!why && !fill_params(cinfo, write_all_tables, &p)) why = "parameter set outside b200jpeg_params";
-  if (!why) {
-    for (int i = 0; i < MAX_ACTIVE && slot < 0; i++) if (!g_active[i].cinfo) slot = i;
-    if (slot < 0) why = "too many concurrent compressors";
-  }
-  if (!why && !g_idle_enc && !g_no_device) {
-    if (b200jpeg_encoder_create(&g_idle_enc, 0) != B200JPEG_OK) { g_no_device = 1; g_idle_enc = NULL; }
-  }
-  if (!why && !g_idle_enc) why = b200jpeg_last_error();
-  if (!why) {
+  if (!why && b200jpeg_validate(&p) != B200JPEG_OK) why = b200jpeg_last_error();
+  if (!why) slot = claim_slot(cinfo, &why);
+  if (!why && !cinfo->raw_data_in) {
     /* raw-data objects (jpeg_write_raw_data) collect their planes on the host and encode at finish time */
-    int rc = cinfo->raw_data_in ? b200jpeg_validate(&p) : b200jpeg_start_compress(g_idle_enc, &p);
-    if (rc != B200JPEG_OK) why = b200jpeg_last_error();
+    if (b200jpeg_start_compress(g_active[slot].enc, &p) != B200JPEG_OK) { why = b200jpeg_last_error(); release_slot(slot); slot = -1; }
   }
   if (why) {
     if (verbose()) fprintf(stderr, "b200 shim: reference path (%s)\n", why);
@@ -218,9 +259,9 @@ jpeg_start_compress(j_compress_ptr cinfo, boolean write_all_tables)
     return;
   }
   if (verbose()) fprintf(stderr, "b200 shim: device path (%s%ux%u, %d scans)\n", cinfo->raw_data_in ? "raw data, " : "", cinfo->image_width, cinfo->image_height, p.num_scans);
-  memset(&g_active[slot], 0, sizeof g_active[slot]);
-  g_active[slot].cinfo = cinfo; g_active[slot].enc = g_idle_enc; g_idle_enc = NULL;
   g_active[slot].header_len = 2 + (p.write_JFIF_header ? 18 : 0) + (p.write_Adobe_marker ? 16 : 0);
+  g_active[slot].total_passes = b200jpeg_total_passes(&p);
+  if (cinfo->progress != NULL) { cinfo->progress->completed_passes = 0; cinfo->progress->total_passes = g_active[slot].total_passes; }   /* prepare_for_pass, jcmaster.c:711-714 */
   if (cinfo->raw_data_in) {
     g_active[slot].raw = 1; g_active[slot].params = p;
     for (int ci = 0; ci < cinfo->num_components; ci++) {
@@ -364,6 +405,17 @@ jpeg_finish_compress(j_compress_ptr cinfo)
     if (rc == B200JPEG_ERR_BAD_DCT_COEF) ERREXIT(cinfo, JERR_BAD_DCT_COEF);
     ERREXIT(cinfo, JERR_NOTIMPL);
   }
+  /* the remaining passes ran inside the one device call; the application's monitor hears about each of them, on this
+   * thread, with the counters the reference's loop would show at the end of the pass (jcapimin.c:193-215,
+   * jcmaster.c:711-714) */
+  if (cinfo->progress != NULL) {
+    const int tp = g_active[slot].total_passes;
+    for (int pass = from_coefs ? 0 : 1; pass < tp; pass++) {
+      cinfo->progress->completed_passes = pass; cinfo->progress->total_passes = tp;
+      cinfo->progress->pass_counter = (long)cinfo->total_iMCU_rows; cinfo->progress->pass_limit = (long)cinfo->total_iMCU_rows;
+      (*cinfo->progress->progress_monitor) ((j_common_ptr)cinfo);
+    }
+  }
   if (!from_coefs) (*cinfo->dest->init_destination) (cinfo);         /* jpeg_write_coefficients did it already (jctrans.c:57) */
   /* the file header, the application's own marker segments (written right behind it, like the reference's marker
    * writer would have), then the rest */
@@ -378,7 +430,7 @@ jpeg_finish_compress(j_compress_ptr cinfo)
     if (cinfo->dc_huff_tbl_ptrs[i]) cinfo->dc_huff_tbl_ptrs[i]->sent_table = TRUE;
     if (cinfo->ac_huff_tbl_ptrs[i]) cinfo->ac_huff_tbl_ptrs[i]->sent_table = TRUE;
   }
-  release_slot(slot);
+  release_slot_ex(slot, 1);
   jpeg_abort((j_common_ptr)cinfo);                                   /* back to CSTATE_START (jcapimin.c:227) */
 }
 
@@ -405,14 +457,7 @@ jpeg_write_coefficients(j_compress_ptr cinfo, jvirt_barray_ptr *coef_arrays)
   }
   if (!why && p.trellis_quant) why = "trellis quantization requested on coefficient input";
   if (!why && b200jpeg_validate(&p) != B200JPEG_OK) why = b200jpeg_last_error();
-  if (!why) {
-    for (int i = 0; i < MAX_ACTIVE && slot < 0; i++) if (!g_active[i].cinfo) slot = i;
-    if (slot < 0) why = "too many concurrent compressors";
-  }
-  if (!why && !g_idle_enc && !g_no_device) {
-    if (b200jpeg_encoder_create(&g_idle_enc, 0) != B200JPEG_OK) { g_no_device = 1; g_idle_enc = NULL; }
-  }
-  if (!why && !g_idle_enc) why = b200jpeg_last_error();
+  if (!why) slot = claim_slot(cinfo, &why);
   if (why) {
     if (verbose()) fprintf(stderr, "b200 shim: reference path (%s)\n", why);
     if (required()) { fprintf(stderr, "b200 shim: B200_SHIM_REQUIRE=1 and the device path was not taken: %s\n", why); ERREXIT(cinfo, JERR_NOTIMPL); }
@@ -420,9 +465,9 @@ jpeg_write_coefficients(j_compress_ptr cinfo, jvirt_barray_ptr *coef_arrays)
     return;
   }
   if (verbose()) fprintf(stderr, "b200 shim: device path (coefficients, %ux%u, %d scans)\n", cinfo->image_width, cinfo->image_height, p.num_scans);
-  memset(&g_active[slot], 0, sizeof g_active[slot]);
-  g_active[slot].cinfo = cinfo; g_active[slot].enc = g_idle_enc; g_idle_enc = NULL;
   g_active[slot].coef_arrays = coef_arrays; g_active[slot].params = p;
+  g_active[slot].total_passes = b200jpeg_total_passes(&p);
+  if (cinfo->progress != NULL) { cinfo->progress->completed_passes = 0; cinfo->progress->total_passes = g_active[slot].total_passes; }
   g_active[slot].header_len = 2 + (p.write_JFIF_header ? 18 : 0) + (p.write_Adobe_marker ? 16 : 0);
   derive_geometry(cinfo);
   jpeg_suppress_tables(cinfo, FALSE);                                /* jctrans.c:54 */
@@ -433,13 +478,18 @@ jpeg_write_coefficients(j_compress_ptr cinfo, jvirt_barray_ptr *coef_arrays)
   cinfo->global_state = CSTATE_WRCOEFS;
 }
 
-/* an application that gives up mid-image */
+/* an application that gives up mid-image: through the compress-specific entry points or the generic ones
+ * (jpeg_abort / jpeg_destroy, jcomapi.c:29-98, which jpeg_abort_compress / jpeg_destroy_compress forward to) */
+static void drop_object(void *cinfo)
+{
+  int slot = find_active((j_compress_ptr)cinfo);
+  if (slot >= 0) release_slot(slot);
+}
 GLOBAL(void)
 jpeg_abort_compress(j_compress_ptr cinfo)
 {
   static abort_fn real;
-  int slot = find_active(cinfo);
-  if (slot >= 0) { b200jpeg_encoder_destroy(g_active[slot].enc); free(g_active[slot].extra); for (int k = 0; k < 4; k++) free(g_active[slot].plane[k]); memset(&g_active[slot], 0, sizeof g_active[slot]); }
+  drop_object(cinfo);
   if (!real) real = (abort_fn)next_sym("jpeg_abort_compress");
   real(cinfo);
 }
@@ -447,9 +497,25 @@ GLOBAL(void)
 jpeg_destroy_compress(j_compress_ptr cinfo)
 {
   static abort_fn real;
-  int slot = find_active(cinfo);
-  if (slot >= 0) { b200jpeg_encoder_destroy(g_active[slot].enc); free(g_active[slot].extra); for (int k = 0; k < 4; k++) free(g_active[slot].plane[k]); memset(&g_active[slot], 0, sizeof g_active[slot]); }
+  drop_object(cinfo);
   if (!real) real = (abort_fn)next_sym("jpeg_destroy_compress");
+  real(cinfo);
+}
+typedef void (*common_fn)(j_common_ptr);
+GLOBAL(void)
+jpeg_abort(j_common_ptr cinfo)
+{
+  static common_fn real;
+  if (!cinfo->is_decompressor) drop_object(cinfo);
+  if (!real) real = (common_fn)next_sym("jpeg_abort");
+  real(cinfo);
+}
+GLOBAL(void)
+jpeg_destroy(j_common_ptr cinfo)
+{
+  static common_fn real;
+  if (!cinfo->is_decompressor) drop_object(cinfo);
+  if (!real) real = (common_fn)next_sym("jpeg_destroy");
   real(cinfo);
 }
 

@@ -76,11 +76,11 @@ using namespace b200;
 // intermediate HBM state of one chunk in flight
 struct Arena {
   b200::DevBuf d_planes;             // input smoothing: the pre-pass's component planes
-  b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm, d_splits, d_best_al;
+  b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm, d_srec, d_splits, d_best_al;
   b200::DevBuf d_blk_bits, d_tile_bits, d_tile_base, d_seg_corr, d_mark, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
   b200::Geom g;                      // the plan's geometry with this arena's coefficient pointers
   void release() {
-    b200::DevBuf *db[] = {&d_planes, &d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_splits, &d_best_al, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
+    b200::DevBuf *db[] = {&d_planes, &d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_srec, &d_splits, &d_best_al, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
     for (b200::DevBuf *b : db) b->release();
     for (int i = 0; i < 4; i++) { d_coef[i].release(); d_raw[i].release(); d_plain[i].release(); }
   }
@@ -107,7 +107,8 @@ struct b200jpeg_encoder {
   // device buffers sized for the WHOLE batch
   DevBuf d_src, d_tabs_scan, d_tabs_fixed, d_status, d_out_pos, d_scan_size, d_out, d_qt, d_tc, d_best_al_all;
   size_t bitbuf_words_per_image = 0, out_cap_per_image = 0;
-  double cap_factor = 0.25;
+  double cap_factor = 0.25;      // entropy-coded bytes the buffers hold per coefficient; grows on overflow, falls back after calm batches
+  int calm_batches = 0;
   // pinned host mirrors
   PinBuf h_qt, h_tc, h_fixed, h_status, h_out_pos, h_scan_size, h_tabs, h_stage, h_best_al;
   // finished files: bump-allocated from pinned arenas, valid until the next encode call
@@ -153,9 +154,12 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
   g.mcus_per_row = div_up(g.W, g.hmax * 8); g.mcu_rows = div_up(g.H, g.vmax * 8);
   g.row_pitch = row_pitch; g.image_stride = image_stride;
   g.max_coef_bits = p->data_precision + 2;
-  if (p->in_color_space == B200JPEG_CS_RGB && p->jpeg_color_space == B200JPEG_CS_YCbCr) g.cs_mode = 0;
-  else if (p->in_color_space == B200JPEG_CS_RGB && p->jpeg_color_space == B200JPEG_CS_GRAYSCALE) g.cs_mode = 1;
+  const bool rgb_in = B200JPEG_CS_IS_RGB(p->in_color_space);
+  if (rgb_in && p->jpeg_color_space == B200JPEG_CS_YCbCr) g.cs_mode = 0;
+  else if (rgb_in && p->jpeg_color_space == B200JPEG_CS_GRAYSCALE) g.cs_mode = 1;
   else g.cs_mode = 2;
+  g.px_first = rgb_in ? B200JPEG_CS_FIRST(p->in_color_space) : 0;             // jccolor.c:253-291 (JCS_EXT_* pixel orders)
+  g.px_swap = rgb_in ? B200JPEG_CS_BLUE_FIRST(p->in_color_space) : 0;
   pl.max_real_blocks = 0; pl.sum_real_blocks = 0;
   for (int ci = 0; ci < g.nc; ci++) {
     CompGeom &c = g.c[ci]; const b200jpeg_component_info &ic = p->comp_info[ci];
@@ -204,6 +208,8 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
   pl.dering = p->overshoot_deringing != 0;
   pl.smooth = p->smoothing_factor;
   pl.search = p->optimize_scans && p->num_scans > 0;
+  pl.restarts = p->restart_interval != 0 || p->restart_in_rows > 0;       // before the search guard below reads it
+  pl.rs.interval = p->restart_interval; pl.rs.in_rows = p->restart_in_rows;
   if (pl.search) {
     // every candidate is buffered with its own scan header; a DRI marker opens it when its restart interval differs from
     // the previously coded scan's (write_scan_header).  Scans that the search may skip share their neighbours' interval
@@ -227,8 +233,6 @@ static int build_plan(const b200jpeg_params *p, size_t row_pitch, size_t image_s
     for (int si = pl.luma_split0; si < pl.n_luma; si++) pl.order.push_back(si);
     if (colour) for (int si = pl.chroma_split0; si < nscans; si++) pl.order.push_back(si);
   } else for (int si = 0; si < nscans; si++) pl.order.push_back(si);
-  pl.restarts = p->restart_interval != 0 || p->restart_in_rows > 0;
-  pl.rs.interval = p->restart_interval; pl.rs.in_rows = p->restart_in_rows;
   return B200JPEG_OK;
 }
 
@@ -380,7 +384,8 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
     if ((rc = a.d_rec.reserve((size_t)n * pl.sum_real_blocks * sizeof(DcRec)))) return rc;
     if ((rc = a.d_bt.reserve((size_t)n * pl.sum_real_blocks * 8))) return rc;
     if ((rc = a.d_perm.reserve((size_t)n * pl.sum_real_blocks * 4))) return rc;
-    if ((rc = a.d_splits.reserve((size_t)n * 4 * 2 * 4))) return rc;
+    if ((rc = a.d_srec.reserve((size_t)n * pl.sum_real_blocks * 16))) return rc;
+    if ((rc = a.d_splits.reserve((size_t)n * 4 * 4 * 4))) return rc;
     if ((rc = a.d_best_al.reserve((size_t)n * 2 * 4))) return rc;
     if ((rc = a.d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
     if (pl.progressive) { if ((rc = a.d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = a.d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
@@ -516,10 +521,16 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
       }
     }
     if (!generic_rounds) {
+      static const bool trellis_v1 = getenv("B200JPEG_TRELLIS_V1") != nullptr;       // A/B aid: the first-generation kernels
+      if (trellis_v1) {
       tm.mark("trellis_sort");
       launch_sort_blocks(g, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
       tm.mark("trellis_ac");
       launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
+      } else {
+      tm.mark("trellis_ac");
+      launch_trellis_ac2(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, A.d_srec.p, A.d_splits.as<uint32_t>(), n, s);
+      }
     } else {
       tm.mark("trellis_ac");
       launch_trellis_ac_band(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, bSs, bSe, n, s);
@@ -796,89 +807,78 @@ static unsigned long scan_header_bytes(const Plan &pl, const ScanDesc &sd, const
   if (dht) dht += 4;
   return dht + (sd.dri ? 6 : 0) + (2 + 2 + 1 + 2 * sd.ncomps + 3);       // emit_dri: FFDD 0004 xxxx (jcmarker.c)
 }
+// The layout of jpeg_search_progression's script (jcparam.c:733-852) as three kinds of groups per component set:
+//   * an Al ladder: `nband` band scans coded at Al = 0, then per step a: `nrefine` refinement scans (Ah = a, Al = a-1)
+//     followed by the `nband` band scans at Al = a;
+//   * a split menu: the unsplit candidate (`width` scans) followed by 5 two-band candidates (2*width scans each, at
+//     the split points 2, 8, 5, 12, 18 in that order).
+// select_scans (jcmaster.c:773-962) walks them with the early exits below; every candidate is coded here, so only
+// its DECISIONS are replayed, on the candidates' sizes.
+struct AlLadder { int base, nband, nrefine, al_max;
+  int refine(int a, int r) const { return base + nband + (nband + nrefine) * a + r; }            // refinement r of step a+1
+  int band(int a, int b) const { return a == 0 ? base + b : refine(a - 1, nrefine) + b; } };
+struct SplitMenu { int first, width;
+  int scan(int idx, int w) const { return idx == 0 ? first + w : first + width + 2 * width * (idx - 1) + w; }
+  int count(int idx) const { return idx == 0 ? width : 2 * width; } };
+
+// cheapest point transform: total bytes of the bands at Al = a plus the refinement scans that restore the dropped bits;
+// the search stops at the first step that does not improve (jcmaster.c:792-812, :879-903)
+static int pick_al(const unsigned long *size, const AlLadder &L)
+{
+  unsigned long best = 0; int best_a = 0;
+  for (int a = 0; a <= L.al_max; a++) {
+    unsigned long cost = 0;
+    for (int b = 0; b < L.nband; b++) cost += size[L.band(a, b)];
+    for (int i = 0; i < a; i++) for (int r = 0; r < L.nrefine; r++) cost += size[L.refine(i, r)];
+    if (a > 0 && cost >= best) break;
+    best = cost; best_a = a;
+  }
+  return best_a;
+}
+// cheapest frequency split; candidates are visited in script order and the walk ends once the trend is settled:
+// after the second split point if nothing beat "unsplit", after the third unless the second won, after the fourth
+// unless it won itself (jcmaster.c:814-858, :905-941)
+static int pick_split(const unsigned long *size, const SplitMenu &M)
+{
+  unsigned long best = 0; int best_idx = 0;
+  for (int idx = 0; idx <= 5; idx++) {
+    unsigned long cost = 0;
+    for (int w = 0; w < M.count(idx); w++) cost += size[M.scan(idx, w)];
+    if (idx == 0 || cost < best) { best = cost; best_idx = idx; }
+    if ((idx == 2 && best_idx == 0) || (idx == 3 && best_idx != 2) || (idx == 4 && best_idx != 4)) break;
+  }
+  return best_idx;
+}
 static void select_scans_host(const Plan &pl, const b200jpeg_params *p, int num_scans, const unsigned long *scan_size,
                               std::vector<int> &copy, int &best_Al_luma_out, int &best_Al_chroma_out)
 {
-  const int num_scans_luma = pl.n_luma, num_scans_luma_dc = 1, Al_max_luma = 3, num_scans_chroma_dc = 3, Al_max_chroma = 2;
-  const int luma_freq_split_scan_start = num_scans_luma_dc + 3 * Al_max_luma + 2;
-  const int chroma_freq_split_scan_start = num_scans_luma + num_scans_chroma_dc + (6 * Al_max_chroma + 4);
-  unsigned long best_cost = 0;
-  int best_Al_luma = 0, best_Al_chroma = 0, best_freq_split_idx_luma = 0, best_freq_split_idx_chroma = 0;
-  bool interleave_chroma_dc = false;
+  const bool colour = num_scans > pl.n_luma;
+  const AlLadder luma_al{1, 2, 1, 3}, chroma_al{pl.n_luma + 3, 4, 2, 2};
+  const SplitMenu luma_split{pl.luma_split0, 1}, chroma_split{pl.chroma_split0, 2};
+  const int al_y = pick_al(scan_size, luma_al), split_y = pick_split(scan_size, luma_split);
+  const int al_c = colour ? pick_al(scan_size, chroma_al) : 0, split_c = colour ? pick_split(scan_size, chroma_split) : 0;
+  // one interleaved chroma DC scan unless the two separate ones are smaller (jcmaster.c:871-877)
+  const bool joint_dc = colour && scan_size[pl.n_luma] <= scan_size[pl.n_luma + 1] + scan_size[pl.n_luma + 2];
+  // output order (jcmaster.c:943-1007... copy_buffer calls): DC, chroma DC, luma bands, the refinements only luma needs,
+  // chroma bands, the refinements only chroma needs, then the shared refinement steps from coarse to fine
   copy.clear();
-  int scan_number = 0;
-  for (;;) {
-    const int next_scan_number = scan_number + 1;          // finish_pass_master: select_scans(cinfo, master->scan_number + 1)
-    int base_scan_idx = 0;
-    if (next_scan_number > 1 && next_scan_number <= luma_freq_split_scan_start) {
-      if ((next_scan_number - 1) % 3 == 2) {
-        int Al = (next_scan_number - 1) / 3;
-        unsigned long cost = scan_size[next_scan_number - 2] + scan_size[next_scan_number - 1];
-        for (int i = 0; i < Al; i++) cost += scan_size[3 + 3 * i];
-        if (Al == 0 || cost < best_cost) { best_cost = cost; best_Al_luma = Al; }
-        else scan_number = luma_freq_split_scan_start - 1;
-      }
-    } else if (next_scan_number > luma_freq_split_scan_start && next_scan_number <= num_scans_luma) {
-      if (next_scan_number == luma_freq_split_scan_start + 1) { best_freq_split_idx_luma = 0; best_cost = scan_size[next_scan_number - 1]; }
-      else if ((next_scan_number - luma_freq_split_scan_start) % 2 == 1) {
-        int idx = (next_scan_number - luma_freq_split_scan_start) >> 1;
-        unsigned long cost = scan_size[next_scan_number - 2] + scan_size[next_scan_number - 1];
-        if (cost < best_cost) { best_cost = cost; best_freq_split_idx_luma = idx; }
-        if ((idx == 2 && best_freq_split_idx_luma == 0) || (idx == 3 && best_freq_split_idx_luma != 2) || (idx == 4 && best_freq_split_idx_luma != 4))
-          scan_number = num_scans_luma - 1;
-      }
-    } else if (num_scans > num_scans_luma) {
-      if (next_scan_number == num_scans_luma + num_scans_chroma_dc) {
-        base_scan_idx = num_scans_luma;
-        interleave_chroma_dc = scan_size[base_scan_idx] <= scan_size[base_scan_idx + 1] + scan_size[base_scan_idx + 2];
-      } else if (next_scan_number > num_scans_luma + num_scans_chroma_dc && next_scan_number <= chroma_freq_split_scan_start) {
-        base_scan_idx = num_scans_luma + num_scans_chroma_dc;
-        if ((next_scan_number - base_scan_idx) % 6 == 4) {
-          int Al = (next_scan_number - base_scan_idx) / 6;
-          unsigned long cost = scan_size[next_scan_number - 4] + scan_size[next_scan_number - 3] + scan_size[next_scan_number - 2] + scan_size[next_scan_number - 1];
-          for (int i = 0; i < Al; i++) cost += scan_size[base_scan_idx + 4 + 6 * i] + scan_size[base_scan_idx + 5 + 6 * i];
-          if (Al == 0 || cost < best_cost) { best_cost = cost; best_Al_chroma = Al; }
-          else scan_number = chroma_freq_split_scan_start - 1;
-        }
-      } else if (next_scan_number > chroma_freq_split_scan_start && next_scan_number <= num_scans) {
-        if (next_scan_number == chroma_freq_split_scan_start + 2) {
-          best_freq_split_idx_chroma = 0;
-          best_cost = scan_size[next_scan_number - 2] + scan_size[next_scan_number - 1];
-        } else if ((next_scan_number - chroma_freq_split_scan_start) % 4 == 2) {
-          int idx = (next_scan_number - chroma_freq_split_scan_start) >> 2;
-          unsigned long cost = scan_size[next_scan_number - 4] + scan_size[next_scan_number - 3] + scan_size[next_scan_number - 2] + scan_size[next_scan_number - 1];
-          if (cost < best_cost) { best_cost = cost; best_freq_split_idx_chroma = idx; }
-          if ((idx == 2 && best_freq_split_idx_chroma == 0) || (idx == 3 && best_freq_split_idx_chroma != 2) || (idx == 4 && best_freq_split_idx_chroma != 4))
-            scan_number = num_scans - 1;
-        }
-      }
-    }
-    if (scan_number == num_scans - 1) {
-      const int min_Al = std::min(best_Al_luma, best_Al_chroma);
-      copy.push_back(0);
-      if (num_scans > num_scans_luma && p->dc_scan_opt_mode != 0) {
-        base_scan_idx = num_scans_luma;
-        if (interleave_chroma_dc && p->dc_scan_opt_mode != 1) copy.push_back(base_scan_idx);
-        else { copy.push_back(base_scan_idx + 1); copy.push_back(base_scan_idx + 2); }
-      }
-      if (best_freq_split_idx_luma == 0) copy.push_back(luma_freq_split_scan_start);
-      else { copy.push_back(luma_freq_split_scan_start + 2 * (best_freq_split_idx_luma - 1) + 1); copy.push_back(luma_freq_split_scan_start + 2 * (best_freq_split_idx_luma - 1) + 2); }
-      for (int Al = best_Al_luma - 1; Al >= min_Al; Al--) copy.push_back(3 + 3 * Al);
-      if (num_scans > num_scans_luma) {
-        if (best_freq_split_idx_chroma == 0) { copy.push_back(chroma_freq_split_scan_start); copy.push_back(chroma_freq_split_scan_start + 1); }
-        else for (int q = 2; q <= 5; q++) copy.push_back(chroma_freq_split_scan_start + 4 * (best_freq_split_idx_chroma - 1) + q);
-        base_scan_idx = num_scans_luma + num_scans_chroma_dc;
-        for (int Al = best_Al_chroma - 1; Al >= min_Al; Al--) { copy.push_back(base_scan_idx + 6 * Al + 4); copy.push_back(base_scan_idx + 6 * Al + 5); }
-      }
-      for (int Al = min_Al - 1; Al >= 0; Al--) {
-        copy.push_back(3 + 3 * Al);
-        if (num_scans > num_scans_luma) { copy.push_back(base_scan_idx + 6 * Al + 4); copy.push_back(base_scan_idx + 6 * Al + 5); }
-      }
-      break;
-    }
-    scan_number++;
+  copy.push_back(0);
+  if (colour && p->dc_scan_opt_mode != 0) {
+    if (joint_dc && p->dc_scan_opt_mode != 1) copy.push_back(pl.n_luma);
+    else { copy.push_back(pl.n_luma + 1); copy.push_back(pl.n_luma + 2); }
   }
-  best_Al_luma_out = best_Al_luma; best_Al_chroma_out = best_Al_chroma;
+  const int al_shared = std::min(al_y, al_c);
+  for (int w = 0; w < luma_split.count(split_y); w++) copy.push_back(luma_split.scan(split_y, w));
+  for (int a = al_y - 1; a >= al_shared; a--) copy.push_back(luma_al.refine(a, 0));
+  if (colour) {
+    for (int w = 0; w < chroma_split.count(split_c); w++) copy.push_back(chroma_split.scan(split_c, w));
+    for (int a = al_c - 1; a >= al_shared; a--) for (int r = 0; r < 2; r++) copy.push_back(chroma_al.refine(a, r));
+  }
+  for (int a = al_shared - 1; a >= 0; a--) {
+    copy.push_back(luma_al.refine(a, 0));
+    if (colour) for (int r = 0; r < 2; r++) copy.push_back(chroma_al.refine(a, r));
+  }
+  best_Al_luma_out = al_y; best_Al_chroma_out = al_c;
 }
 
 // Chunk k's pipeline has finished: lay out its files in pinned memory, write the
@@ -968,16 +968,18 @@ static int finish_chunk(b200jpeg_encoder *e, const ChunkIO &io, int k)
 
 static int choose_chunk(const b200jpeg_encoder *e, const Plan &pl, int n_images, bool host_pixels)
 {
-  if (e->chunk_images_override > 0) return std::min(n_images, e->chunk_images_override);
+  // several kernels put (image, component) or the image index into gridDim.y / gridDim.z (limit 65535)
+  const int grid_cap = 65535 / std::max(1, pl.g.nc);
+  if (e->chunk_images_override > 0) return std::min(std::min(n_images, e->chunk_images_override), grid_cap);
   long long per = 0; for (int ci = 0; ci < pl.g.nc; ci++) per += pl.g.c[ci].blocks_per_image;
   // pixels already in HBM: nothing to overlap, so chunks only bound the arenas (64 images of 4K 4:2:0)
-  if (!host_pixels) return (int)std::min<long long>(n_images, std::max(1LL, 12800000LL / std::max(1LL, per)));
+  if (!host_pixels) return (int)std::min<long long>(std::min(n_images, grid_cap), std::max(1LL, 12800000LL / std::max(1LL, per)));
   // about 1.6 M blocks (8 images of 3840x2160 4:2:0) per chunk: large enough to fill
   // the 148 SMs several waves deep, small enough that staging the next chunk's
   // pixels overlaps this chunk's kernels.
   static const long long target = getenv("B200JPEG_CHUNK_BLOCKS") ? atoll(getenv("B200JPEG_CHUNK_BLOCKS")) : 1600000LL;
   long long c = std::max(1LL, target / std::max(1LL, per));
-  return (int)std::min<long long>(n_images, c);
+  return (int)std::min<long long>(std::min(n_images, grid_cap), c);
 }
 
 // raw-data input (jpeg_write_raw_data): one plane per component instead of interleaved pixels
@@ -1032,7 +1034,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   if (!raw && (p->data_precision == 12 || p->dct_method != B200JPEG_DCT_ISLOW)) {
     const Geom &g = pl.g;
     bool gray = g.nc == 1 && g.hmax == 1 && g.vmax == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
-    bool ycc = g.nc == 3 && g.cs_mode == 0 && g.in_comps == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax && g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
+    bool ycc = g.nc == 3 && g.cs_mode == 0 && (g.in_comps == 3 || g.in_comps == 4) && g.c[0].h == g.hmax && g.c[0].v == g.vmax && g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
     if (!gray && !ycc) { set_error("12-bit precision / fast and float DCT: only RGB->YCbCr 4:4:4/4:2:2/4:4:0/4:2:0 and grayscale layouts are on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
   }
   const int nscans = (int)pl.scans.size();
@@ -1053,6 +1055,8 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   Timer tm{e};
   const int nstreams = (nchunks > 1 && e->n_streams > 1) ? 2 : 1;
   e->sc[0] = e->stream;
+  if (e->calm_batches >= 2) e->cap_factor = 0.25;          // one incompressible batch does not enlarge the buffers for good
+  bool grew = false;
   for (int attempt = 0; attempt < 6; attempt++) {
     tm.idx = 0;
     if ((rc = prepare_batch(e, n_images, C, !on_device, src_bytes, nstreams))) return rc;
@@ -1124,7 +1128,9 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
     }
     if (rc != 1) break;
     e->cap_factor *= 4.0;          // entropy-coded data did not fit: grow and rerun
+    grew = true;
   }
+  e->calm_batches = grew ? 0 : e->calm_batches + 1;
   if (rc == 1) { set_error("output does not fit even after growing buffers"); return B200JPEG_ERR_BUFFER; }
   if (rc) return rc;
   // per-stage device times (CUDA events on the encoder's stream), summed by stage name over the chunks

@@ -46,10 +46,12 @@ __device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(v); }   // v 
 //     jcprepct.c:135-192 (edge rules), jcdctmgr.c:416-498,576-604,611-682,
 //     693-772, jfdctint.c:142-286.
 // =====================================================================
-__device__ __forceinline__ int load_component(const uint8_t *__restrict__ px, int cs_mode, int comp)
+// first / swap: where the three colour samples sit inside an RGB-family pixel (jccolor.c:253-291, the JCS_EXT_* orders):
+// they start at sample `first` and are stored blue-first when `swap` is set; other inputs have first = swap = 0
+__device__ __forceinline__ int load_component(const uint8_t *__restrict__ px, int cs_mode, int comp, int first, int swap)
 {
-  if (cs_mode == 2) return px[comp];
-  int r = px[0], g = px[1], b = px[2];
+  if (cs_mode == 2) return px[first + (swap ? 2 - comp : comp)];
+  int r = px[first + (swap ? 2 : 0)], g = px[first + 1], b = px[first + (swap ? 0 : 2)];
   if (comp == 0) return (19595 * r + 38470 * g + 7471 * b + 32768) >> 16;
   if (comp == 1) return (-11059 * r - 21709 * g + 32768 * b + (128 << 16) + 32767) >> 16;
   return (32768 * r - 27439 * g - 5329 * b + (128 << 16) + 32767) >> 16;
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
         const uint8_t *row = base + (size_t)iy * g.row_pitch;
         for (int du = 0; du < c.hx; du++) {
           int ix = min(xo * c.hx + du, g.W - 1);          // expand_right_edge (jcsample.c:98-116)
-          sum += load_component(row + (size_t)ix * g.in_comps, g.cs_mode, comp);
+          sum += load_component(row + (size_t)ix * g.in_comps, g.cs_mode, comp, g.px_first, g.px_swap);
         }
       }
       int val;
@@ -243,14 +245,50 @@ template <> struct WorkT<32> { typedef float type; };
 // One row of 8 pixels of the strip in registers: IC samples per pixel, SB bytes per sample
 // (8-bit: 24 bytes RGB / 8 grey; 12-bit in uint16: 48 / 16).
 struct Px8 { unsigned w[12]; };
+// px4: the pixels in memory have 4 samples (JCS_EXT_RGBX/BGRX/XBGR/XRGB and the alpha orders); the three colour samples
+// start at sample `first` (0 or 1) and are packed to the 3-sample register layout on the way in
 template <int IC, int SB>
-__device__ __forceinline__ Px8 load_px8(const uint8_t *__restrict__ base, size_t row_pitch, int iy, int x, int W, bool fast)
+__device__ __forceinline__ Px8 load_px8(const uint8_t *__restrict__ base, size_t row_pitch, int iy, int x, int W, bool fast, bool px4 = false, int first = 0)
 {
   Px8 r;
   const uint8_t *row = base + (size_t)iy * row_pitch;
   constexpr int NBYTES = 8 * IC * SB;
 #pragma unroll
   for (int i = 0; i < 12; i++) r.w[i] = 0;
+  if (fast && IC == 3 && px4) {
+    // 8 pixels x 4 samples, aligned: drop the filler sample (byte permutes; a 16-bit sample is two bytes)
+    unsigned q[16];
+    if (SB == 1) {
+      const uint4 *p = reinterpret_cast<const uint4 *>(row + (size_t)x * 4);
+      const uint4 a = __ldg(p), b = __ldg(p + 1);
+      q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+      if (first) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) q[i] >>= 8;                    // colour samples into bytes 0..2
+      }
+#pragma unroll
+      for (int g4 = 0; g4 < 2; g4++) {                             // 4 pixels (12 bytes) per group
+        const unsigned p0 = q[4 * g4], p1 = q[4 * g4 + 1], p2 = q[4 * g4 + 2], p3 = q[4 * g4 + 3];
+        r.w[3 * g4] = __byte_perm(p0, p1, 0x4210);
+        r.w[3 * g4 + 1] = __byte_perm(p1, p2, 0x5421);
+        r.w[3 * g4 + 2] = __byte_perm(p2, p3, 0x6542);
+      }
+    } else {
+      const uint4 *p = reinterpret_cast<const uint4 *>(row + (size_t)x * 8);
+#pragma unroll
+      for (int i = 0; i < 4; i++) { const uint4 a = __ldg(p + i); q[4 * i] = a.x; q[4 * i + 1] = a.y; q[4 * i + 2] = a.z; q[4 * i + 3] = a.w; }
+      // pixel k = words 2k, 2k+1 (4 halfwords); output halfword h = 3k + c <- pixel k, halfword first + c
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const unsigned lo = q[2 * k], hi = q[2 * k + 1];
+        const unsigned c0 = first ? (lo >> 16) : (lo & 0xFFFFu), c1 = first ? (hi & 0xFFFFu) : (lo >> 16), c2 = first ? (hi >> 16) : (hi & 0xFFFFu);
+        const unsigned cc[3] = {c0, c1, c2};
+#pragma unroll
+        for (int c = 0; c < 3; c++) { const int h = 3 * k + c; r.w[h >> 1] |= cc[c] << (16 * (h & 1)); }
+      }
+    }
+    return r;
+  }
   if (fast) {                                     // aligned (8 bytes for 8-bit, 16 for 16-bit samples), fully inside the image
     if (SB == 1) {
       const uint2 *p = reinterpret_cast<const uint2 *>(row + (size_t)x * IC);
@@ -262,11 +300,12 @@ __device__ __forceinline__ Px8 load_px8(const uint8_t *__restrict__ base, size_t
       for (int i = 0; i < NBYTES / 16; i++) { uint4 a = __ldg(p + i); r.w[4 * i] = a.x; r.w[4 * i + 1] = a.y; r.w[4 * i + 2] = a.z; r.w[4 * i + 3] = a.w; }
     }
   } else {                                        // right edge / unaligned: bytes, columns clamped to W-1 (expand_right_edge)
+    const int pxb = (IC == 3 && px4 ? 4 : IC) * SB, off = (IC == 3 && px4 ? first : 0) * SB;
 #pragma unroll
     for (int b = 0; b < NBYTES; b++) {
       int px = b / (IC * SB), rem = b - px * (IC * SB);
       int ix = min(x + px, W - 1);
-      r.w[b >> 2] |= (unsigned)row[(size_t)ix * IC * SB + rem] << (8 * (b & 3));
+      r.w[b >> 2] |= (unsigned)row[(size_t)ix * pxb + off + rem] << (8 * (b & 3));
     }
   }
   return r;
@@ -442,7 +481,9 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
       }
     } else {
     const bool grey_from_rgb = NC == 1 && g.cs_mode == 1;
-    constexpr size_t AL = SB == 1 ? 7 : 15;
+    const bool px4 = g.in_comps == 4 && (NC == 3 || grey_from_rgb);       // 4-sample RGB-family pixels
+    const int pfirst = g.px_first; const bool pswap = g.px_swap != 0;
+    const size_t AL = px4 ? 15 : (SB == 1 ? 7 : 15);
     const bool fast = (xs + 8 <= g.W) && ((g.row_pitch & AL) == 0) && ((((size_t)base) & AL) == 0) && !grey_from_rgb;
     if (NC == 1 && grey_from_rgb) {
       // RGB input, grayscale output: 3 bytes per pixel, luma only
@@ -450,10 +491,13 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
       for (int rr = 0; rr < VMAX; rr++) {
         const int iy = min(y0 + rg * VMAX + rr, g.H - 1);
         const bool f3 = (xs + 8 <= g.W) && ((g.row_pitch & AL) == 0) && ((((size_t)base) & AL) == 0);
-        Px8 p = load_px8<3, SB>(base, g.row_pitch, iy, xs, g.W, f3);
+        Px8 p = load_px8<3, SB>(base, g.row_pitch, iy, xs, g.W, f3, px4, pfirst);
         int16_t yv[8];
 #pragma unroll
-        for (int px = 0; px < 8; px++) yv[px] = (int16_t)(((19595 * px_sample<3, SB>(p, px, 0) + 38470 * px_sample<3, SB>(p, px, 1) + 7471 * px_sample<3, SB>(p, px, 2) + 32768) >> 16) - CENTRE);
+        for (int px = 0; px < 8; px++) {
+          const int s0 = px_sample<3, SB>(p, px, 0), s2 = px_sample<3, SB>(p, px, 2);
+          yv[px] = (int16_t)(((19595 * (pswap ? s2 : s0) + 38470 * px_sample<3, SB>(p, px, 1) + 7471 * (pswap ? s0 : s2) + 32768) >> 16) - CENTRE);
+        }
         *reinterpret_cast<uint4 *>(&sY[(rg * VMAX + rr) * YP + seg * 8]) = *reinterpret_cast<const uint4 *>(yv);
       }
     } else {
@@ -466,22 +510,24 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
 #pragma unroll
       for (int rr = 0; rr < VMAX; rr++) {
         const int iy = min(y0 + rg * VMAX + rr, g.H - 1);
-        Px8 p = load_px8<IC, SB>(base, g.row_pitch, iy, xs, g.W, fast);
+        Px8 p = load_px8<IC, SB>(base, g.row_pitch, iy, xs, g.W, fast, px4, pfirst);
         int16_t yv[8];
 #pragma unroll
         for (int px = 0; px < 8; px++) {
           if (NC == 1) yv[px] = (int16_t)(px_sample<1, SB>(p, px, 0) - CENTRE);
           else {
-            const int R = px_sample<3, SB>(p, px, 0), G = px_sample<3, SB>(p, px, 1), B = px_sample<3, SB>(p, px, 2);
+            const int S0 = px_sample<3, SB>(p, px, 0), G = px_sample<3, SB>(p, px, 1), S2 = px_sample<3, SB>(p, px, 2);
+            const int R = pswap ? S2 : S0, B = pswap ? S0 : S2;
             yv[px] = (int16_t)(((19595 * R + 38470 * G + 7471 * B + 32768) >> 16) - CENTRE);
           }
         }
         *reinterpret_cast<uint4 *>(&sY[(rg * VMAX + rr) * YP + seg * 8]) = *reinterpret_cast<const uint4 *>(yv);
         if (NC == 3) {
-          if (er != rg) p = load_px8<IC, SB>(base, g.row_pitch, min(y0 + er * VMAX + rr, g.H - 1), xs, g.W, fast);
+          if (er != rg) p = load_px8<IC, SB>(base, g.row_pitch, min(y0 + er * VMAX + rr, g.H - 1), xs, g.W, fast, px4, pfirst);
 #pragma unroll
           for (int px = 0; px < 8; px++) {
-            const int R = px_sample<3, SB>(p, px, 0), G = px_sample<3, SB>(p, px, 1), B = px_sample<3, SB>(p, px, 2);
+            const int S0 = px_sample<3, SB>(p, px, 0), G = px_sample<3, SB>(p, px, 1), S2 = px_sample<3, SB>(p, px, 2);
+            const int R = pswap ? S2 : S0, B = pswap ? S0 : S2;
             sb[px / HMAX] += (-11059 * R - 21709 * G + 32768 * B + (CENTRE << 16) + 32767) >> 16;
             sr[px / HMAX] += (32768 * R - 27439 * G - 5329 * B + (CENTRE << 16) + 32767) >> 16;
           }
@@ -772,8 +818,9 @@ __global__ void __launch_bounds__(128) k_prep_planes(Geom g, const uint8_t *__re
     y = max(0, min(y, g.H - 1)); x = max(0, min(x, g.W - 1));
     const uint8_t *px = base + (size_t)y * g.row_pitch + (size_t)x * g.in_comps * SB;
     auto smp = [&](int k) -> int { return SB == 1 ? (int)px[k] : (int)(reinterpret_cast<const uint16_t *>(px)[k] & 0xFFF); };
-    if (g.cs_mode == 2) return smp(comp);
-    const int r = smp(0), gg = smp(1), b = smp(2);
+    const int f0 = g.px_first, sw = g.px_swap;
+    if (g.cs_mode == 2) return smp(f0 + (sw ? 2 - comp : comp));
+    const int r = smp(f0 + (sw ? 2 : 0)), gg = smp(f0 + 1), b = smp(f0 + (sw ? 0 : 2));
     if (comp == 0) return (19595 * r + 38470 * gg + 7471 * b + 32768) >> 16;
     if (comp == 1) return (-11059 * r - 21709 * gg + 32768 * b + (CENTRE << 16) + 32767) >> 16;
     return (32768 * r - 27439 * gg - 5329 * b + (CENTRE << 16) + 32767) >> 16;
@@ -814,7 +861,7 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
   const int write_raw = rec != nullptr || keep_raw;
   // fast path: full-size first component, (for colour) two 1x1-sampled chroma components
   bool gray = g.nc == 1 && (g.raw_in || g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
-  bool ycc = g.nc == 3 && (g.raw_in || (g.cs_mode == 0 && g.in_comps == 3)) && g.c[0].h == g.hmax && g.c[0].v == g.vmax &&
+  bool ycc = g.nc == 3 && (g.raw_in || (g.cs_mode == 0 && (g.in_comps == 3 || g.in_comps == 4))) && g.c[0].h == g.hmax && g.c[0].v == g.vmax &&
              g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
   static const bool force_generic = getenv("B200JPEG_GENERIC_FORWARD") != nullptr;   // A/B switch for debugging
   if (!force_generic && ((gray && g.hmax == 1 && g.vmax == 1) || ycc)) {
@@ -1650,6 +1697,392 @@ void launch_trellis_ac_band(const Geom &g, const TrellisConsts *tc, const DevHuf
   dim3 grid((unsigned)((mb + 127) / 128), n * g.nc);
   k_trellis_ac_band<<<grid, 128, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, Ss, Se);
   LAUNCHED();
+}
+
+// =====================================================================
+// AC trellis, second generation (same arithmetic as k_trellis_ac, jcdctmgr.c:1121-1222).
+//  * k_sort_blocks2 emits sorted RECORDS {norm, block index, non-zero mask} and four class boundaries per
+//    (image, component): blocks with more than 32 / 17..32 / 9..16 / at most 8 non-zero plain-quantized AC values;
+//  * one kernel instantiation per class (MM = capacity of the register-resident predecessor lists), launched over a
+//    small grid whose CTAs build the rate table once and then loop over the 128-block chunks of their class;
+//  * phase 1 converts the raw coefficients without I2F (exponent trick; fx*fx rounds like (float)(x*x)) and in packed
+//    fp32x2 operations (sm_100 add/mul.f32x2), the serial prefix sum stays a scalar chain in the reference's order;
+//  * per entry, T[s] = (A[i-1] - A[p_s]) + acc[s] is formed once and shared by all candidates (it does not depend on the
+//    candidate); candidates 0..2 are unrolled (immediate rate-table offsets), further ones loop;
+//  * per entry state is one packed word {4*position, chosen predecessor, chosen value}.
+// =====================================================================
+struct SRec { float norm; uint32_t lin; unsigned long long nzmask; };
+static_assert(sizeof(SRec) == 16, "SRec layout");
+
+__global__ void __launch_bounds__(256) k_sort_blocks2(Geom g, const DcRec *__restrict__ rec, RecLayout rl, SRec *__restrict__ srec, uint32_t *__restrict__ splits)
+{
+  __shared__ unsigned cnt[64], start[64];
+  const int ci = blockIdx.x % g.nc, img = blockIdx.x / g.nc;
+  const CompGeom &c = g.c[ci];
+  const long long nblk = (long long)c.wib * c.hib;
+  const DcRec *r = rec + (size_t)img * rl.per_image + rl.comp_off[ci];
+  SRec *p = srec + (size_t)img * rl.per_image + rl.comp_off[ci];
+  if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) atomicAdd(&cnt[63 - min((int)r[b].nz, 63)], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned a = 0; for (int k = 0; k < 64; k++) { start[k] = a; a += cnt[k]; }
+    // decreasing count: [0, s0) more than 32 non-zeros, [s0, s1) 17..32, [s1, s2) 9..16, [s2, nblk) at most 8
+    splits[4 * blockIdx.x] = start[63 - 32]; splits[4 * blockIdx.x + 1] = start[63 - 16]; splits[4 * blockIdx.x + 2] = start[63 - 8];
+    splits[4 * blockIdx.x + 3] = (uint32_t)nblk;
+  }
+  __syncthreads();
+  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) {
+    const uint4 q = reinterpret_cast<const uint4 *>(r)[b];        // {norm, raw_dc | nz << 16, mask lo, mask hi}
+    const int nz = (int)((q.y >> 16) & 0xFF);
+    const unsigned pos = atomicAdd(&start[63 - min(nz, 63)], 1u);
+    reinterpret_cast<uint4 *>(p)[pos] = make_uint4(q.x, (unsigned)b, q.z, q.w);
+  }
+}
+
+#ifndef T2_PACKED
+#define T2_PACKED 1
+#endif
+#ifndef T2_PREFETCH_OUT
+#define T2_PREFETCH_OUT 1
+#endif
+#ifndef T2_KSTATIC
+#define T2_KSTATIC 3
+#endif
+#ifndef T2_CTAS8
+#define T2_CTAS8 6
+#endif
+#ifndef T2_CTAS16
+#define T2_CTAS16 5
+#endif
+#define T2_THREADS 128
+#define T2A(i) ((i) * T2_THREADS)
+// exact int -> float for 0 <= v < 2^23 without the conversion unit
+__device__ __forceinline__ float u2f_exact(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
+
+template <int MM>
+__device__ __forceinline__ void trellis2_regs(const int m, unsigned long long nzmask, const float *__restrict__ A /* sA + tid */,
+                                              const int16_t *__restrict__ raw16, int16_t *__restrict__ o16,
+                                              const float *__restrict__ srate /* [10][64] */, const uint4 *__restrict__ sEnt, const int qL,
+                                              const float lambda, const int maxq, const float azd63, const float eob, const unsigned dc_q,
+                                              unsigned long long &final_mask)
+{
+  float nat[MM], acc[MM];            // -A[p_s], accumulated cost of entry s
+  unsigned ew[MM];                   // 4*p_s | chosen predecessor (1-based entry, 0 = block start) << 8 | chosen value << 16
+#pragma unroll
+  for (int t = 0; t < MM; t++) { nat[t] = 0.f; acc[t] = 0.f; ew[t] = 0u; }
+  unsigned lo = (unsigned)nzmask, hi = (unsigned)(nzmask >> 32);
+  int p_next = lo ? __ffs((int)lo) - 1 : (hi ? 31 + __ffs((int)hi) : 63);
+  if (lo) lo &= lo - 1; else hi &= hi - 1;
+  int raw_next = raw16[p_next];
+  const char *srate_b = reinterpret_cast<const char *>(srate);
+#pragma unroll
+  for (int t = 0; t < MM; t++) {
+    if (t < m) {
+      const int i = p_next, rawv = raw_next;
+      if (t + 1 < MM) {
+        p_next = lo ? __ffs((int)lo) - 1 : (hi ? 31 + __ffs((int)hi) : 63);
+        if (lo) lo &= lo - 1; else hi &= hi - 1;
+        raw_next = raw16[p_next];
+      }
+      const uint4 en = sEnt[i];                               // {8*Q, reciprocal, weight bits, -}
+      const float Ai1 = A[T2A(i - 1)], Ai = A[T2A(i)];
+      const int x = abs(rawv), q = (int)en.x;
+      const float wl = __uint_as_float(en.z);
+      const int qv = min((int)(__umulhi((unsigned)(x + (q >> 1)) << 14, en.y) >> qL), maxq);      // :1136-1144
+      const int nc = nbits_of(qv);
+      const char *rb = srate_b + (i - 1) * 4;                  // rate of run i-1-j at rb[-4j] (+256 per candidate)
+      // candidate-independent part of the cost per predecessor (:1176)
+      float T[MM + 1]; int ra[MM + 1];
+      T[0] = Ai1; ra[0] = 0;
+#if T2_PACKED
+#pragma unroll
+      for (int s = 0; s + 1 < t; s += 2) {
+        const float2 d = __fadd2_rn(__fadd2_rn(make_float2(Ai1, Ai1), make_float2(nat[s], nat[s + 1])), make_float2(acc[s], acc[s + 1]));
+        T[s + 1] = d.x; T[s + 2] = d.y;
+      }
+      if (t & 1) T[t] = (Ai1 + nat[t - 1]) + acc[t - 1];
+#else
+#pragma unroll
+      for (int s = 0; s < t; s++) T[s + 1] = (Ai1 + nat[s]) + acc[s];
+#endif
+#pragma unroll
+      for (int s = 0; s < t; s++) ra[s + 1] = -(int)(ew[s] & 0xFFu);
+      float best = 1e38f; int best_s = 0, best_k = -1;
+      auto eval_k = [&](const int k) {
+        const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
+        const int delta = cand * q - x;
+        const float fd = u2f_exact((unsigned)abs(delta));
+        const float dist = (fd * fd) * lambda * wl;                                // :1151
+        const char *rk = rb + k * 256;
+        float kb = 1e38f; int ks = 0;
+#if T2_PACKED
+        const float2 d2 = make_float2(dist, dist);
+#pragma unroll
+        for (int s = 0; s + 1 <= t; s += 2) {
+          const float2 r2 = make_float2(*reinterpret_cast<const float *>(rk + ra[s]), *reinterpret_cast<const float *>(rk + ra[s + 1]));
+          const float2 c2 = __fadd2_rn(__fadd2_rn(r2, d2), make_float2(T[s], T[s + 1]));
+          if (c2.x < kb) { kb = c2.x; ks = s; }
+          if (c2.y < kb) { kb = c2.y; ks = s + 1; }
+        }
+        if (!(t & 1)) {
+          const float cost = (*reinterpret_cast<const float *>(rk + ra[t]) + dist) + T[t];
+          if (cost < kb) { kb = cost; ks = t; }
+        }
+#else
+#pragma unroll
+        for (int s = 0; s <= t; s++) {
+          const float cost = (*reinterpret_cast<const float *>(rk + ra[s]) + dist) + T[s];
+          if (cost < kb) { kb = cost; ks = s; }
+        }
+#endif
+        if (kb < best || (kb == best && ks < best_s)) { best = kb; best_s = ks; best_k = k; }
+      };
+      // candidates 0..KS-1 unrolled (immediate table offsets), the rest in a loop; the 32-entry class keeps its code small
+      constexpr int KS = MM <= 16 ? T2_KSTATIC : 1;
+      eval_k(0);
+      if (KS > 1 && nc > 1) eval_k(1);
+      if (KS > 2 && nc > 2) eval_k(2);
+#pragma unroll 1
+      for (int k = KS; k < nc; k++) eval_k(k);
+      // the value this entry takes if it stays on the chain (:1179, :1143-1153)
+      const int cand = (best_k >= 0 && best_k < nc - 1) ? (2 << best_k) - 1 : qv;
+      const int sgn = rawv >> 31;
+      const int val = (cand ^ sgn) - sgn;
+      acc[t] = best; nat[t] = -Ai;
+      ew[t] = (unsigned)(i << 2) | ((unsigned)best_s << 8) | ((unsigned)val << 16);
+    }
+  }
+  // best end-of-block position (:1187-1207)
+  int last = 0;
+  float best_cost = azd63 + eob;
+#pragma unroll
+  for (int t = 0; t < MM; t++) {
+    if (t < m) {
+      float cst = (acc[t] + azd63) + nat[t];
+      if ((ew[t] & 0xFFu) < 63u * 4u) cst += eob;
+      if (cst < best_cost) { best_cost = cst; last = t + 1; }
+    }
+  }
+  // output: zeros except the back-tracked chain (:1211-1222)
+  uint4 *q4 = reinterpret_cast<uint4 *>(o16);
+  q4[0] = make_uint4(dc_q, 0, 0, 0);
+#pragma unroll
+  for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
+  unsigned long long fm = 0;
+#pragma unroll
+  for (int t = MM - 1; t >= 0; t--) {
+    if (t + 1 == last) {
+      const int pos = (int)((ew[t] & 0xFFu) >> 2); const int val = (int)ew[t] >> 16;
+      o16[pos] = (int16_t)val; if (val) fm |= 1ull << pos;
+      last = (int)((ew[t] >> 8) & 0xFFu);
+    }
+  }
+  final_mask = fm;
+}
+
+// m > 32: the same search over compact lists in local memory (rare at photographic quality settings)
+__device__ __noinline__ void trellis2_generic(const int m, unsigned long long nzmask, const float *__restrict__ A,
+                                              const int16_t *__restrict__ raw16, int16_t *__restrict__ o16,
+                                              const float *__restrict__ srate, const uint4 *__restrict__ sEnt, const int qL,
+                                              const float lambda, const int maxq, const float azd63, const float eob, const unsigned dc_q,
+                                              unsigned long long &final_mask)
+{
+  uint8_t e_pos[64], e_rs[64], e_k[64];
+  unsigned short e_qs[64];                         // plain-quantized magnitude (clamped) | sign of the raw value << 15
+  float e_at[64], e_before[64], e_acc[64];
+  {
+    int r = 0;
+    for (unsigned long long mm = nzmask; mm; mm &= mm - 1) {
+      const int p = __ffsll((long long)mm) - 1;
+      e_pos[r] = (uint8_t)p; e_at[r] = A[T2A(p)]; e_before[r] = A[T2A(p - 1)]; e_qs[r] = (unsigned short)raw16[p]; r++;
+    }
+  }
+#pragma unroll 1
+  for (int t = 0; t < m; t++) {
+    const int i = e_pos[t];
+    const int rawv = (int)(short)e_qs[t];
+    const int x = abs(rawv);
+    const uint4 en = sEnt[i];
+    const int q = (int)en.x;
+    const int qv = min((int)(__umulhi((unsigned)(x + (q >> 1)) << 14, en.y) >> qL), maxq);
+    e_qs[t] = (unsigned short)(qv | ((rawv >> 31) & 0x8000));
+    const int nc = nbits_of(qv);
+    const float wl = __uint_as_float(en.z);
+    const float Ai1 = e_before[t];
+    float best = 1e38f; int best_s = 0, best_k = -1;
+#pragma unroll 1
+    for (int k = 0; k < nc; k++) {
+      const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
+      const int delta = cand * q - x;
+      const float dist = (float)(delta * delta) * lambda * wl;
+      const float *rk = srate + k * 64 + (i - 1);
+      float kb = 1e38f; int ks = 0;
+      {
+        float cost = rk[0] + dist;
+        cost += (Ai1 - 0.0f) + 0.0f;
+        if (cost < kb) { kb = cost; ks = 0; }
+      }
+#pragma unroll 2
+      for (int s2 = 0; s2 < t; s2++) {
+        float cost = rk[-(int)e_pos[s2]] + dist;
+        cost += (Ai1 - e_at[s2]) + e_acc[s2];
+        if (cost < kb) { kb = cost; ks = s2 + 1; }
+      }
+      if (kb < best || (kb == best && ks < best_s)) { best = kb; best_s = ks; best_k = k; }
+    }
+    e_acc[t] = best; e_rs[t] = (uint8_t)best_s; e_k[t] = (uint8_t)(best_k < 0 ? 255 : best_k);
+  }
+  int last = 0;
+  {
+    float best_cost = azd63 + eob;
+    for (int t = 0; t < m; t++) {
+      float cst = e_acc[t] + azd63 - e_at[t];
+      if (e_pos[t] < 63) cst += eob;
+      if (cst < best_cost) { best_cost = cst; last = t + 1; }
+    }
+  }
+  uint4 *q4 = reinterpret_cast<uint4 *>(o16);
+  q4[0] = make_uint4(dc_q, 0, 0, 0);
+#pragma unroll
+  for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
+  unsigned long long fm = 0;
+  while (last != 0) {
+    const int t = last - 1;
+    const int qs = e_qs[t], qv = qs & 0x7FFF, nc = nbits_of(qv), k = e_k[t];
+    const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
+    const int sgn = -(qs >> 15);
+    const int outv = (cand ^ sgn) - sgn;
+    o16[e_pos[t]] = (int16_t)outv;
+    if (outv) fm |= 1ull << e_pos[t];
+    last = e_rs[t];
+  }
+  final_mask = fm;
+}
+
+// MM: 8 / 16 / 32 = register-resident lists of that capacity, 64 = generic (more than 32 entries)
+template <int MM>
+__global__ void __launch_bounds__(T2_THREADS, MM == 8 ? T2_CTAS8 : MM == 16 ? T2_CTAS16 : MM == 32 ? 3 : 4)
+k_trellis_ac2(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
+              DcRec *__restrict__ rec, RecLayout rl, const SRec *__restrict__ srec, const uint32_t *__restrict__ splits)
+{
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
+  const CompGeom &c = g.c[ci];
+  long long lo, hi;
+  {
+    const uint4 sp = reinterpret_cast<const uint4 *>(splits)[blockIdx.y];
+    if (MM == 64) { lo = 0; hi = sp.x; } else if (MM == 32) { lo = sp.x; hi = sp.y; } else if (MM == 16) { lo = sp.y; hi = sp.z; } else { lo = sp.z; hi = sp.w; }
+  }
+  const int nchunks = (int)((hi - lo + T2_THREADS - 1) / T2_THREADS);
+  if ((int)blockIdx.x >= nchunks) return;
+  __shared__ __align__(16) float sA[64 * T2_THREADS];         // zero-distortion prefix, element i of thread tid at sA[i*128 + tid]
+  __shared__ __align__(16) float srate[10 * 64];              // rate[k][run] (:1163-1175), +inf where the reference skips
+  __shared__ __align__(16) uint4 sEnt[64];                    // per zigzag position {8*Q, reciprocal, weight, -}
+  __shared__ __align__(16) float swz[64];
+  __shared__ int sqL;
+  const int tid = threadIdx.x;
+  uint8_t *acsi = reinterpret_cast<uint8_t *>(sA);            // table build only
+  {
+    const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + (4 + c.ac_tbl);
+    for (int i = tid; i < 256; i += T2_THREADS) acsi[i] = ac->size[i];
+    if (tid < 64) {
+      const float w = tc->w_zz[c.qt][tid];
+      swz[tid] = w;
+      sEnt[tid] = make_uint4((unsigned)tc->q8_zz[c.qt][tid], tc->qmul_zz[c.qt][tid], __float_as_uint(w), 0u);
+    }
+    if (tid == 0) sqL = tc->qL[c.qt];
+  }
+  __syncthreads();
+  for (int e = tid; e < 640; e += T2_THREADS) {
+    const int k = e >> 6, run = e & 63;
+    const int zrl = acsi[0xF0], cb = acsi[16 * (run & 15) + k + 1];
+    const bool skip = cb == 0 || ((run >> 4) && zrl == 0) || run == 63;
+    srate[e] = skip ? __int_as_float(0x7F800000) : (float)(cb + (k + 1) + (run >> 4) * zrl);
+  }
+  const float eob = (float)acsi[0];
+  __syncthreads();                                             // acsi (aliasing sA) is dead from here on
+  const int maxq = (1 << tc->max_coef_bits) - 1;
+  const int qL = sqL;
+  const size_t rbase = (size_t)img * rl.per_image + rl.comp_off[ci];
+  const int use_norm = tc->use_norm;
+  const double p1 = tc->p1, p2 = tc->p2; const float lambda_const = tc->lambda_const;
+  float *A = sA + tid;
+
+#pragma unroll 1
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const long long tix = lo + (long long)chunk * T2_THREADS + tid;
+    if (tix >= hi) continue;
+    const SRec sr = srec[rbase + tix];
+    const unsigned lin = sr.lin;
+    const int by = lin / c.wib, bx = lin - by * c.wib;
+    const size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
+    const int16_t *raw16 = c.raw + blk * 64;
+    int16_t *o16 = c.coef + blk * 64;
+    uint4 rv[8];
+    {
+      const uint4 *r4 = reinterpret_cast<const uint4 *>(raw16);
+#pragma unroll
+      for (int v = 0; v < 8; v++) rv[v] = r4[v];
+    }
+#if T2_PREFETCH_OUT
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 16)); asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 32));
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 48));
+#endif
+    const unsigned dc_q = (unsigned)(unsigned short)o16[0];      // the DC value survives the rewrite
+    float lambda;
+    {
+      const float norm = (float)((double)sr.norm / 63.0);        // :1026-1035
+      if (use_norm) lambda = (float)(p1 / (p2 + (double)norm)); else lambda = lambda_const;
+      rec[rbase + lin].lambda_dc = lambda * swz[0];
+    }
+    // phase 1: accumulated zero distortion, zigzag order, serial fp32 (:1134)
+    float azd = 0.0f;
+    A[T2A(0)] = 0.0f;
+    {
+      const float2 l2 = make_float2(lambda, lambda);
+      const float2 bias = make_float2(-8421376.0f, -8421376.0f);   // -(2^23 + 2^15): undoes the exponent trick and the +32768 offset
+#pragma unroll
+      for (int v = 0; v < 8; v++) {
+        const unsigned aw[4] = {rv[v].x, rv[v].y, rv[v].z, rv[v].w};
+        const float4 w0 = reinterpret_cast<const float4 *>(swz)[2 * v], w1 = reinterpret_cast<const float4 *>(swz)[2 * v + 1];
+        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          const unsigned u = aw[jj] ^ 0x80008000u;               // both halves + 32768
+          float2 f = make_float2(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7632)));
+          f = __fadd2_rn(f, bias);                               // the raw values as floats, exact
+          float2 z = __fmul2_rn(__fmul2_rn(__fmul2_rn(f, f), l2), make_float2(ww[2 * jj], ww[2 * jj + 1]));
+          const int i = 8 * v + 2 * jj;
+          if (i != 0) { azd = z.x + azd; A[T2A(i)] = azd; }
+          azd = z.y + azd; A[T2A(i + 1)] = azd;
+        }
+      }
+    }
+    const float azd63 = azd;
+    const int m = __popcll(sr.nzmask);
+    unsigned long long fmask = 0;
+    if (MM == 64) trellis2_generic(m, sr.nzmask, A, raw16, o16, srate, sEnt, qL, lambda, maxq, azd63, eob, dc_q, fmask);
+    else trellis2_regs<MM>(m, sr.nzmask, A, raw16, o16, srate, sEnt, qL, lambda, maxq, azd63, eob, dc_q, fmask);
+    if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fmask;
+  }
+}
+
+void launch_trellis_ac2(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
+                        DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s)
+{
+  k_sort_blocks2<<<n * g.nc, 256, 0, s>>>(g, rec, rl, static_cast<SRec *>(srec), splits); LAUNCHED();
+  long long mb = 0;
+  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
+  const unsigned full = (unsigned)((mb + T2_THREADS - 1) / T2_THREADS);
+  // CTAs loop over their class's chunks: enough of them per (image, component) to fill the device, few enough to amortise the tables
+  unsigned gx = (unsigned)max(1, min((int)full, (148 * 6 * 4 + n * g.nc - 1) / (n * g.nc)));
+  dim3 grid(gx, n * g.nc);
+  // largest blocks first: the classes touch disjoint blocks
+  k_trellis_ac2<64><<<grid, T2_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, static_cast<const SRec *>(srec), splits); LAUNCHED();
+  k_trellis_ac2<32><<<grid, T2_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, static_cast<const SRec *>(srec), splits); LAUNCHED();
+  k_trellis_ac2<16><<<grid, T2_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, static_cast<const SRec *>(srec), splits); LAUNCHED();
+  k_trellis_ac2<8><<<grid, T2_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, static_cast<const SRec *>(srec), splits); LAUNCHED();
 }
 
 void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,

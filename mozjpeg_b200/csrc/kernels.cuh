@@ -37,6 +37,7 @@ struct Geom {
   int in_comps;        // samples per input pixel
   int max_coef_bits;   // data_precision + 2
   int cs_mode;         // 0: RGB->YCbCr  1: RGB->gray  2: pass-through
+  int px_first, px_swap; // RGB-family pixel order (JCS_EXT_*): first colour sample inside the pixel, blue-first storage
   size_t row_pitch, image_stride;
   // raw-data input (jpeg_write_raw_data, jcapistd.c:145-195): downsampled component planes instead of pixels;
   // plane ci holds at least hib*8 rows of wib*8 samples; pitch and stride in bytes
@@ -121,6 +122,10 @@ void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s);
 void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_set_stride, const SlotMasks &masks, int nsets, cudaStream_t s);
 void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                        DcRec *rec, const RecLayout &rl, const uint32_t *perm, const uint32_t *splits, int n, cudaStream_t s);
+// second-generation AC trellis: sorts the side records by non-zero count (srec: 16 bytes per real block, splits: 4 words per
+// (image, component)) and runs one class-specific kernel per count class
+void launch_trellis_ac2(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
+                        DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s);
 // use_scans_in_trellis: quantize_trellis restricted to the zigzag band [Ss, Se]
 void launch_trellis_ac_band(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                             DcRec *rec, const RecLayout &rl, int Ss, int Se, int n, cudaStream_t s);

@@ -114,7 +114,9 @@ int b200jpeg_default_colorspace(b200jpeg_params *p) {
   case B200JPEG_CS_GRAYSCALE: return b200jpeg_set_colorspace(p, B200JPEG_CS_GRAYSCALE);
   case B200JPEG_CS_RGB:       return b200jpeg_set_colorspace(p, B200JPEG_CS_YCbCr);
   case B200JPEG_CS_YCbCr:     return b200jpeg_set_colorspace(p, B200JPEG_CS_YCbCr);
-  default: b200::set_error("unsupported input colorspace %d", p->in_color_space); return B200JPEG_ERR_UNSUPPORTED;
+  default:
+    if (B200JPEG_CS_IS_RGB(p->in_color_space)) return b200jpeg_set_colorspace(p, B200JPEG_CS_YCbCr);     // jcparam.c:535-546
+    b200::set_error("unsupported input colorspace %d", p->in_color_space); return B200JPEG_ERR_UNSUPPORTED;
   }
 }
 
@@ -273,8 +275,11 @@ int b200jpeg_validate(const b200jpeg_params *p) {
     blocks_in_mcu += c->h_samp_factor * c->v_samp_factor;
   }
   if (blocks_in_mcu > 10) { set_error("Sampling factors too large for interleaved scan"); return B200JPEG_ERR_PARAM; }   // C_MAX_BLOCKS_IN_MCU
-  if (p->in_color_space == B200JPEG_CS_RGB) {
-    if (p->input_components != 3) { set_error("Bogus input colorspace"); return B200JPEG_ERR_PARAM; }
+  // jinit_color_converter (jccolor.c:618-648, :680-760): the JPEG colour space fixes the component count
+  if ((p->jpeg_color_space == B200JPEG_CS_GRAYSCALE && p->num_components != 1) ||
+      ((p->jpeg_color_space == B200JPEG_CS_YCbCr || p->jpeg_color_space == B200JPEG_CS_RGB) && p->num_components != 3)) { set_error("Bogus JPEG colorspace"); return B200JPEG_ERR_PARAM; }
+  if (B200JPEG_CS_IS_RGB(p->in_color_space)) {
+    if (p->input_components != B200JPEG_CS_PIXELSIZE(p->in_color_space)) { set_error("Bogus input colorspace"); return B200JPEG_ERR_PARAM; }   // rgb_pixelsize[], jccolor.c:640-660
     if (p->jpeg_color_space != B200JPEG_CS_YCbCr && p->jpeg_color_space != B200JPEG_CS_GRAYSCALE && p->jpeg_color_space != B200JPEG_CS_RGB) { set_error("Unsupported color conversion request"); return B200JPEG_ERR_PARAM; }
   } else if (p->in_color_space == B200JPEG_CS_GRAYSCALE) {
     if (p->input_components != 1 || p->jpeg_color_space != B200JPEG_CS_GRAYSCALE) { set_error("Unsupported color conversion request"); return B200JPEG_ERR_PARAM; }
@@ -295,6 +300,18 @@ int b200jpeg_validate(const b200jpeg_params *p) {
     //  Therefore skip all this checking" (jcmaster.c:285-291); the device path wants exactly the search script
     progressive = true;
     if (p->num_scans != (p->num_components == 1 ? 23 : 64) || (p->num_components != 1 && p->num_components != 3)) { set_error("optimize_scans needs the candidate script of jpeg_search_progression (jpeg_simple_progression with optimize_scans set)"); return B200JPEG_ERR_UNSUPPORTED; }
+    {
+      // the plan indexes components and MCU slots straight from the entries: they must be the search script itself
+      static thread_local b200jpeg_params ref;
+      ref = *p;
+      if (!search_progression(&ref) || ref.num_scans != p->num_scans) { set_error("optimize_scans needs the candidate script of jpeg_search_progression"); return B200JPEG_ERR_UNSUPPORTED; }
+      for (int i = 0; i < p->num_scans; i++) {
+        const b200jpeg_scan_info &a = p->scan_info[i], &b = ref.scan_info[i];
+        bool same = a.comps_in_scan == b.comps_in_scan && a.Ss == b.Ss && a.Se == b.Se && a.Ah == b.Ah && a.Al == b.Al;
+        for (int k = 0; same && k < b.comps_in_scan; k++) same = a.component_index[k] == b.component_index[k];
+        if (!same) { set_error("optimize_scans: scan script entry %d is not the candidate jpeg_search_progression generates", i + 1); return B200JPEG_ERR_UNSUPPORTED; }
+      }
+    }
   } else if (p->num_scans > 0) {
     if (p->num_scans > B200JPEG_MAX_SCANS) { set_error("Invalid scan script at entry 0"); return B200JPEG_ERR_PARAM; }
     const b200jpeg_scan_info *s = p->scan_info;

@@ -24,7 +24,23 @@ _ROOT = os.path.dirname(_HERE)
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
-from mozjpeg_b200 import _abi as A  # data layout of b200jpeg_params only
+
+
+def _sibling(name):
+    """mozjpeg_b200/<name>.py (pure Python: the parameter block's ctypes layout, the synthetic-image generator).  With
+    B200JPEG_ORACLE_STANDALONE=1 (bench.py's reference arm) the file is loaded by path, so that the process never
+    imports the package and therefore never maps libb200jpeg.so."""
+    if os.environ.get("B200JPEG_ORACLE_STANDALONE") == "1" and "mozjpeg_b200" not in sys.modules:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_b200_standalone_" + name, os.path.join(_ROOT, "mozjpeg_b200", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    import importlib
+    return importlib.import_module("mozjpeg_b200." + name)
+
+
+A = _sibling("_abi")  # data layout of b200jpeg_params only
 
 
 def build(quiet: bool = True) -> None:
@@ -292,7 +308,8 @@ def ref_cjpeg(ppm_path: str, switches: Sequence[str]) -> bytes:
     return r.stdout
 
 
-from mozjpeg_b200.synth import synth_image  # noqa: E402,F401  (input generator shared with bench.py)
+synth_image = _sibling("synth").synth_image  # input generator shared with bench.py
+synth_image12 = _sibling("synth").synth_image12
 
 
 def oracle_encode_coefs(p: A.Params, planes) -> bytes:

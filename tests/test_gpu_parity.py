@@ -285,3 +285,68 @@ def test_command_line_front_end(tmp_path):
                        cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     assert all(md5((tmp_path / f"in{i}.jpg").read_bytes()) == want["md5"] for i in range(3))
+
+
+# ---------------------------------------------------------------------------
+# pixel orders of the RGB family (jccolor.c:253-291 -> jccolext.c:30-75): the same picture stored as BGR / RGBX / XBGR /
+# ... must give the file the reference writes for the RGB order (its converters differ only in the sample offsets)
+# ---------------------------------------------------------------------------
+def _reorder(img, name):
+    from mozjpeg_b200 import _abi as A
+    _, size, ro, go, bo = A.CS_EXT[name]
+    rng = np.random.default_rng(7)
+    out = rng.integers(0, 256 if img.dtype == np.uint8 else 4096, img.shape[:2] + (size,), dtype=img.dtype)   # filler sample: noise
+    out[..., ro] = img[..., 0]; out[..., go] = img[..., 1]; out[..., bo] = img[..., 2]
+    return np.ascontiguousarray(out)
+
+
+@pytest.mark.parametrize("order", ["EXT_RGB", "EXT_RGBX", "EXT_BGR", "EXT_BGRX", "EXT_XBGR", "EXT_XRGB", "EXT_RGBA", "EXT_BGRA", "EXT_ABGR", "EXT_ARGB"])
+@pytest.mark.parametrize("sw,shape", [(["-baseline", "-quality", "75", "-sample", "2x2"], (203, 141)),
+                                      (["-quality", "80", "-fastcrush"], (64, 48)),
+                                      (["-baseline", "-quality", "60", "-grayscale"], (131, 77)),
+                                      (["-baseline", "-quality", "75", "-rgb"], (90, 50)),
+                                      (["-baseline", "-quality", "70", "-sample", "3x2"], (100, 61)),
+                                      (["-baseline", "-quality", "75", "-smooth", "20"], (97, 66)),
+                                      (["-precision", "12", "-quality", "75", "-notrellis", "-noovershoot", "-baseline", "-sample", "2x1"], (200, 40))],
+                         ids=["420", "fastcrush", "gray", "rgb", "3x2", "smooth", "12bit"])
+def test_pixel_orders(order, sw, shape):
+    import mozjpeg_b200 as mj
+    from mozjpeg_b200 import _abi as A
+    from mozjpeg_b200.synth import synth_image12
+    from oracle import oracle as O
+    from common import device_supports
+    w, h = shape
+    twelve = "-precision" in sw
+    img = synth_image12(3, w, h) if twelve else O.synth_image(3, w, h)
+    p = mj.params_from_switches(sw, w, h)
+    if not device_supports(p):
+        pytest.skip("parameter set not on the device path")
+    ref = O.oracle_encode(p, img).jpeg
+    q = mj.params_from_switches(sw, w, h)
+    q.in_color_space, q.input_components = A.CS_EXT[order][0], A.CS_EXT[order][1]
+    enc = mj.Encoder(0)
+    try:
+        out = enc.encode_batch(q, _reorder(img, order)[None])[0]
+    finally:
+        enc.close()
+    assert out == ref
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json's configurations at their stated sizes: md5s recorded from the unmodified reference
+# (tools/make_golden.py --fullsize -> tests/golden/fullsize_golden.json)
+# ---------------------------------------------------------------------------
+def _fullsize_cases():
+    import json
+    from common import GOLD
+    path = os.path.join(GOLD, "fullsize_golden.json")
+    return json.load(open(path))["cases"] if os.path.exists(path) else []
+
+
+@pytest.mark.parametrize("case", _fullsize_cases(), ids=case_id)
+def test_full_size_recorded_reference(encoder, case):
+    """4K baseline+trellis (configs[1]), 4K progressive jpgcrush script (configs[2]), 1080p q50/75/90 (configs[3]),
+    12-bit 4:4:4 4K (configs[4]) and the 4K library default: byte-identical to the reference at the stated sizes."""
+    img = case_image(case)
+    out = _encode(encoder, case["switches"], img)
+    assert len(out) == case["size"] and md5(out) == case["md5"]

@@ -135,10 +135,12 @@ need_tj = pytest.mark.skipif(not (os.path.exists(SHIM) and os.path.exists(TJBENC
 @pytest.mark.parametrize("opts", [["-subsamp", "420"], ["-subsamp", "444", "-optimize"], ["-subsamp", "422", "-progressive"],
                                   ["-subsamp", "gray"], ["-subsamp", "420", "-restart", "1"],
                                   ["-subsamp", "420", "-yuv"], ["-subsamp", "422", "-yuv", "-optimize"]], ids=lambda s: "_".join(x.lstrip("-") for x in s))
-def test_turbojpeg_api_runs_on_the_device(opts, tmp_path):
+@pytest.mark.parametrize("fmt", [None, "-rgb", "-rgbx", "-bgrx", "-xbgr", "-xrgb"], ids=lambda f: (f or "-bgr").lstrip("-"))
+def test_turbojpeg_api_runs_on_the_device(opts, fmt, tmp_path):
     """The TurboJPEG API (tj3Compress8, turbojpeg.c:1268-1340) sits on the libjpeg API exactly as in the reference
     (turbojpeg-mp.c:104-125); with the reference's turbojpeg.c linked dynamically against libjpeg (oracle/Makefile) the
-    shim is underneath it, and the reference's own tjbench writes the same files as without the shim.  -yuv goes through
+    shim is underneath it, and the reference's own tjbench writes the same files as without the shim, for every pixel
+    format it offers (its default is TJPF_BGR -> JCS_EXT_BGR, turbojpeg.c:330-397).  -yuv goes through
     tj3EncodeYUV8 (CPU colour conversion, the reference's) + tj3CompressFromYUVPlanes8 -> jpeg_write_raw_data."""
     import shutil
     outs = []
@@ -146,7 +148,7 @@ def test_turbojpeg_api_runs_on_the_device(opts, tmp_path):
         d = tmp_path / name
         d.mkdir()
         shutil.copyfile(PPM, d / "img.ppm")
-        r = subprocess.run([TJBENCH, "img.ppm", "75", "-rgb", "-quiet", "-benchtime", "0.01", "-warmup", "0", "-componly", *opts],
+        r = subprocess.run([TJBENCH, "img.ppm", "75", *([fmt] if fmt else []), "-quiet", "-benchtime", "0.01", "-warmup", "0", "-componly", *opts],
                            cwd=d, env=dict(os.environ, **env_extra), capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr + r.stdout
         if name == "dev":

@@ -44,6 +44,32 @@ def test_oracle_large_cases(built, size):
             assert md5(O.oracle_encode(p, img).jpeg) == c["md5"]
 
 
+def _fullsize_subset():
+    """The full-size fixture's cases the restatement finishes in seconds (the 4K scan search takes it a minute)."""
+    import json
+    from common import GOLD
+    path = os.path.join(GOLD, "fullsize_golden.json")
+    cases = json.load(open(path))["cases"] if os.path.exists(path) else []
+    keep = []
+    for c in cases:
+        sw = c["switches"]
+        if c["image"][0] in (300, 17, 26) and sw[0] in ("-baseline", "-fastcrush", "-precision"):
+            keep.append(c)
+    return keep
+
+
+@pytest.mark.parametrize("case", _fullsize_subset(), ids=case_id)
+def test_oracle_full_size_recorded_reference(built, case):
+    """BASELINE.json's configurations at their stated sizes (4K baseline + trellis, 4K progressive, 1080p q50/q90,
+    12-bit 4:4:4 4K): the restatement reproduces the reference's md5."""
+    import mozjpeg_b200 as mj
+    from oracle import oracle as O
+    img = case_image(case)
+    p = mj.params_from_switches(case["switches"], img.shape[1], img.shape[0], 3)
+    out = O.oracle_encode(p, img).jpeg
+    assert len(out) == case["size"] and md5(out) == case["md5"]
+
+
 def test_oracle_live_vs_reference_random_shapes(built):
     """Odd shapes x profiles, live against the compiled reference."""
     import mozjpeg_b200 as mj

@@ -141,7 +141,47 @@ def _key(image, sw):
     return json.dumps([image, sw])
 
 
+# BASELINE.json's configurations at their stated sizes (a separate fixture: each case costs the reference seconds to a
+# minute).  Images [seed, w, h] or [seed, w, h, 12]; seeds 1000.. are bench.py's first-rank inputs.
+FULLSIZE = [
+    ([300, 3840, 2160], ["-baseline", "-quality", "75", "-sample", "2x2"]),          # configs[1]
+    ([1000, 3840, 2160], ["-baseline", "-quality", "75", "-sample", "2x2"]),
+    ([300, 3840, 2160], ["-fastcrush", "-quality", "75", "-sample", "2x2"]),         # configs[2]
+    ([1000, 3840, 2160], ["-fastcrush", "-quality", "75", "-sample", "2x2"]),
+    ([17, 1920, 1080], ["-baseline", "-quality", "50", "-sample", "2x2"]),           # configs[3] sweep (q75 is in golden.json)
+    ([17, 1920, 1080], ["-baseline", "-quality", "90", "-sample", "2x2"]),
+    ([1001, 1920, 1080], ["-baseline", "-quality", "50", "-sample", "2x2"]),
+    ([1001, 1920, 1080], ["-baseline", "-quality", "75", "-sample", "2x2"]),
+    ([1001, 1920, 1080], ["-baseline", "-quality", "90", "-sample", "2x2"]),
+    ([26, 3840, 2160, 12], ["-precision", "12", "-sample", "1x1", "-quality", "75", "-notrellis", "-noovershoot", "-baseline"]),   # configs[4]
+    ([1000, 3840, 2160, 12], ["-precision", "12", "-sample", "1x1", "-quality", "75", "-notrellis", "-noovershoot", "-baseline"]),
+    ([300, 3840, 2160], ["-quality", "75", "-sample", "2x2"]),                       # the library default (scan search) at 4K
+]
+
+
+def fullsize():
+    from mozjpeg_b200.synth import synth_image12
+    path = os.path.join(GOLD, "fullsize_golden.json")
+    have = {}
+    if "--force" not in sys.argv and os.path.exists(path):
+        for c in json.load(open(path))["cases"]:
+            have[_key(c["image"], c["switches"])] = c
+    cases = []
+    for image, sw in FULLSIZE:
+        if _key(image, sw) in have:
+            cases.append(have[_key(image, sw)]); continue
+        im = synth_image12(*image[:3]) if len(image) > 3 else O.synth_image(*image)
+        a = O.ref_encode(im, sw)
+        cases.append({"image": image, "switches": sw, "md5": hashlib.md5(a).hexdigest(), "size": len(a)})
+        print(image, sw, len(a), flush=True)
+    json.dump({"generator": "tools/make_golden.py --fullsize", "reference": "mozilla/mozjpeg 5.0.0 (C path, WITH_SIMD=0), oracle/_ref", "cases": cases},
+              open(path, "w"), indent=0)
+    print("wrote", len(cases), "full-size cases")
+
+
 def main():
+    if "--fullsize" in sys.argv:
+        return fullsize()
     os.makedirs(GOLD, exist_ok=True)
     # cases already recorded are kept as they are unless --force is given (a full regeneration takes a while)
     have = {}
