@@ -76,11 +76,11 @@ using namespace b200;
 // intermediate HBM state of one chunk in flight
 struct Arena {
   b200::DevBuf d_planes;             // input smoothing: the pre-pass's component planes
-  b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm, d_srec, d_splits, d_best_al;
+  b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm, d_srec, d_splits, d_best_al, d_qimg, d_qsum, d_eo, d_es;
   b200::DevBuf d_blk_bits, d_tile_bits, d_tile_base, d_seg_corr, d_mark, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
   b200::Geom g;                      // the plan's geometry with this arena's coefficient pointers
   void release() {
-    b200::DevBuf *db[] = {&d_planes, &d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_srec, &d_splits, &d_best_al, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
+    b200::DevBuf *db[] = {&d_planes, &d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_srec, &d_splits, &d_best_al, &d_qimg, &d_qsum, &d_eo, &d_es, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
     for (b200::DevBuf *b : db) b->release();
     for (int i = 0; i < 4; i++) { d_coef[i].release(); d_raw[i].release(); d_plain[i].release(); }
   }
@@ -105,12 +105,12 @@ struct b200jpeg_encoder {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_streams = 2;
   // device buffers sized for the WHOLE batch
-  DevBuf d_src, d_tabs_scan, d_tabs_fixed, d_status, d_out_pos, d_scan_size, d_out, d_qt, d_tc, d_best_al_all;
+  DevBuf d_src, d_tabs_scan, d_tabs_fixed, d_status, d_out_pos, d_scan_size, d_out, d_qt, d_tc, d_best_al_all, d_qimg_all;
   size_t bitbuf_words_per_image = 0, out_cap_per_image = 0;
   double cap_factor = 0.25;      // entropy-coded bytes the buffers hold per coefficient; grows on overflow, falls back after calm batches
   int calm_batches = 0;
   // pinned host mirrors
-  PinBuf h_qt, h_tc, h_fixed, h_status, h_out_pos, h_scan_size, h_tabs, h_stage, h_best_al;
+  PinBuf h_qt, h_tc, h_fixed, h_status, h_out_pos, h_scan_size, h_tabs, h_stage, h_best_al, h_qinit, h_qimg;
   // finished files: bump-allocated from pinned arenas, valid until the next encode call
   std::vector<PinBuf> file_arenas; size_t arena_idx = 0, arena_off = 0;
   std::vector<std::pair<uint8_t *, size_t>> files;
@@ -138,6 +138,7 @@ struct ChunkIO {
   uint32_t *scan_size;              // [nscans][n]
   b200::DevHuff *tabs_scan;         // [n][nscans][8]
   int *best_al;                     // [2][n] scan search: best luma / chroma Al per image
+  uint16_t *qimg;                   // [n][4][64] trellis_q_opt: the re-fitted quantization tables per image (natural order)
 };
 
 namespace b200 {
@@ -387,6 +388,14 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
     if ((rc = a.d_srec.reserve((size_t)n * pl.sum_real_blocks * 16))) return rc;
     if ((rc = a.d_splits.reserve((size_t)n * 4 * 4 * 4))) return rc;
     if ((rc = a.d_best_al.reserve((size_t)n * 2 * 4))) return rc;
+    if (p->trellis_quant && p->trellis_q_opt) {
+      if ((rc = a.d_qimg.reserve((size_t)n * 512))) return rc;
+      if ((rc = a.d_qsum.reserve((size_t)n * 4 * 2 * 64 * 8))) return rc;
+    }
+    if (p->trellis_quant && p->trellis_eob_opt) {
+      if ((rc = a.d_eo.reserve((size_t)n * pl.sum_real_blocks * 16))) return rc;
+      if ((rc = a.d_es.reserve((size_t)n * pl.sum_real_blocks * 16))) return rc;
+    }
     if ((rc = a.d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
     if (pl.progressive) { if ((rc = a.d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = a.d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
     if ((rc = a.d_total_bits.reserve((size_t)n * 8))) return rc;
@@ -407,6 +416,11 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
   if ((rc = e->d_out_pos.reserve((size_t)n_total * (nscans + 1) * 8))) return rc;
   if ((rc = e->d_scan_size.reserve((size_t)n_total * nscans * 4))) return rc;
   if ((rc = e->d_best_al_all.reserve((size_t)n_total * 2 * 4))) return rc;
+  if (p->trellis_quant && p->trellis_q_opt) {
+    if ((rc = e->d_qimg_all.reserve((size_t)n_total * 512))) return rc;
+    if ((rc = e->h_qinit.reserve(512))) return rc;
+    memcpy(e->h_qinit.p, p->quant_tbl, 512);
+  }
   if ((rc = e->d_out.reserve(e->out_cap_per_image * n_total))) return rc;
   if ((rc = e->d_qt.reserve(sizeof(QuantTables)))) return rc;
   if ((rc = e->d_tc.reserve(sizeof(TrellisConsts)))) return rc;
@@ -482,64 +496,102 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   //      is ONE launch over all components of all images. ----
   if (pl.trellis) {
     if (e->keep_plain) for (int ci = 0; ci < g.nc; ci++) CU(cudaMemcpyAsync(A.d_plain[ci].p, A.d_coef[ci].p, pl.coef_bytes[ci] * n, cudaMemcpyDeviceToDevice, s));
-    const size_t hist_bytes_t = hist_bytes * g.nc;
     DevHuff *tset = A.d_tabs_trellis.as<DevHuff>();                                       // [img*nc + ci][8]
     // use_scans_in_trellis (jcmaster.c:451-467): two statistics -> tables -> quantize_trellis rounds per component, on
     // the zigzag bands 1..trellis_freq_split and the rest; otherwise one round on 1..63
     const int nband = p->use_scans_in_trellis ? 2 : 1;
     // trellis_num_loops > 1 repeats the rounds (jcmaster.c:453-465); later rounds start from the requantized
-    // coefficients, which the band kernel honours (it reads the values a block has on entry), so it serves those too
-    const bool generic_rounds = nband == 2 || p->trellis_num_loops > 1;
-    for (int loop = 0; loop < p->trellis_num_loops; loop++)
-    for (int band = 0; band < nband; band++) {
-    const int bSs = (nband == 2 && band == 1) ? p->trellis_freq_split + 1 : 1;
-    const int bSe = (nband == 2 && band == 0) ? p->trellis_freq_split : 63;
+    // coefficients, which the band kernel honours (it reads the values a block has on entry), so it serves those too;
+    // trellis_eob_opt and trellis_q_opt also run on it (it reports the per-block costs the EOB-run pass needs and takes
+    // per-image tables)
+    const bool qopt = p->trellis_q_opt != 0, eobopt = p->trellis_eob_opt != 0;
+    const bool generic_rounds = nband == 2 || p->trellis_num_loops > 1 || qopt || eobopt;
+    uint16_t *qimg = qopt ? A.d_qimg.as<uint16_t>() : nullptr;
+    if (qopt) {
+      // every image starts from the batch's tables (natural order, like JQUANT_TBL.quantval)
+      for (int i = 0; i < n; i++) CU(cudaMemcpyAsync(qimg + (size_t)i * 256, e->h_qinit.p, 512, cudaMemcpyHostToDevice, s));
+    }
+    // one statistics -> tables -> quantize_trellis round over the components of gr (all of them, or one)
+    auto round = [&](const Geom &gr, const RecLayout &rlr, int bSs, int bSe) -> int {
     if (!pl.progressive) {
       tm.mark("trellis_stats");
-      CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes_t, s));
-      launch_gather_comp(g, pl.rs, A.d_hist.as<uint32_t>(), status, n, s);
+      CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes * gr.nc, s));
+      launch_gather_comp(gr, pl.rs, A.d_hist.as<uint32_t>(), status, n, s);
       tm.mark("trellis_tables");
-      SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = g.nc;
-      for (int ci = 0; ci < g.nc; ci++) masks.m[ci] = (1u << g.c[ci].dc_tbl) | (1u << (4 + g.c[ci].ac_tbl));
-      launch_gen_tables(A.d_hist.as<uint32_t>(), tset, tabset, masks, n * g.nc, s);
+      SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = gr.nc;
+      for (int ci = 0; ci < gr.nc; ci++) masks.m[ci] = (1u << gr.c[ci].dc_tbl) | (1u << (4 + gr.c[ci].ac_tbl));
+      launch_gen_tables(A.d_hist.as<uint32_t>(), tset, tabset, masks, n * gr.nc, s);
     } else {
       // jcphuff statistics with Ss=1..63 (or the band), Al=0 (jcmaster.c:462-466), every AC symbol
       // pre-counted once (jcphuff.c:257-264); the DC table stays the supplied one.
-      for (int ci = 0; ci < g.nc; ci++) {
+      for (int ci = 0; ci < gr.nc; ci++) {
         ScanDesc ts; memset(&ts, 0, sizeof ts);
         ts.ncomps = 1; ts.ci[0] = ci; ts.Ss = bSs; ts.Se = bSe; ts.bim = 1; ts.k_count[0] = 1;
-        ts.per_row = g.c[ci].wib; ts.rows = g.c[ci].hib; ts.nblocks = (long long)ts.per_row * ts.rows;
+        ts.per_row = gr.c[ci].wib; ts.rows = gr.c[ci].hib; ts.nblocks = (long long)ts.per_row * ts.rows;
         ts.ri = p->restart_in_rows > 0 ? (int)std::min((long long)p->restart_in_rows * ts.per_row, 65535LL) : p->restart_interval;
         tm.mark("trellis_stats");
         CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
-        launch_seed_hist(A.d_hist.as<uint32_t>(), 4 + g.c[ci].ac_tbl, n, s);
-        launch_prog_prepare(g, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), A.d_tile_bits.as<int>(), A.d_tile_base.as<int>(), n, s);
-        launch_gather_prog(g, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), A.d_hist.as<uint32_t>(), status, n, s);
+        launch_seed_hist(A.d_hist.as<uint32_t>(), 4 + gr.c[ci].ac_tbl, n, s);
+        launch_prog_prepare(gr, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), A.d_tile_bits.as<int>(), A.d_tile_base.as<int>(), n, s);
+        launch_gather_prog(gr, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), A.d_hist.as<uint32_t>(), status, n, s);
         tm.mark("trellis_tables");
-        SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = 1u << (4 + g.c[ci].ac_tbl);
-        launch_gen_tables(A.d_hist.as<uint32_t>(), tset + (size_t)ci * HIST_SLOTS, tabset * g.nc, masks, n, s);
+        SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = 1u << (4 + gr.c[ci].ac_tbl);
+        launch_gen_tables(A.d_hist.as<uint32_t>(), tset + (size_t)ci * HIST_SLOTS, tabset * gr.nc, masks, n, s);
       }
     }
     if (!generic_rounds) {
       static const bool trellis_v1 = getenv("B200JPEG_TRELLIS_V1") != nullptr;       // A/B aid: the first-generation kernels
       if (trellis_v1) {
       tm.mark("trellis_sort");
-      launch_sort_blocks(g, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
+      launch_sort_blocks(gr, A.d_rec.as<DcRec>(), rlr, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
       tm.mark("trellis_ac");
-      launch_trellis_ac(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
+      launch_trellis_ac(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rlr, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
       } else {
+      static const bool trellis_v2 = getenv("B200JPEG_TRELLIS_V2") != nullptr;
       tm.mark("trellis_ac");
-      launch_trellis_ac2(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, A.d_srec.p, A.d_splits.as<uint32_t>(), n, s);
+      if (trellis_v2) launch_trellis_ac2(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rlr, A.d_srec.p, A.d_splits.as<uint32_t>(), n, s);
+      else launch_trellis_ac3(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rlr, A.d_srec.p, A.d_splits.as<uint32_t>(), n, s);
       }
     } else {
       tm.mark("trellis_ac");
-      launch_trellis_ac_band(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rl, bSs, bSe, n, s);
+      float4 *eo = eobopt ? A.d_eo.as<float4>() : nullptr;
+      launch_trellis_ac_band(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rlr, bSs, bSe, qimg, eo, n, s);
+      if (eobopt) launch_trellis_eob_rows(gr, tset, tabset, A.d_rec.as<DcRec>(), rlr, bSs, bSe, eo, A.d_es.p, n, s);
+      if (qopt) launch_qopt_sums(gr, A.d_qsum.as<long long>(), n, s);
     }
     if (p->trellis_quant_dc) {
       tm.mark("trellis_dc");
-      if (pl.progressive) launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rl, p->trellis_delta_dc_weight > 0.0f, n, s);
-      else launch_trellis_dc(g, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rl, p->trellis_delta_dc_weight > 0.0f, n, s);
+      if (pl.progressive) launch_trellis_dc(gr, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rlr, p->trellis_delta_dc_weight > 0.0f, n, s);
+      else launch_trellis_dc(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rlr, p->trellis_delta_dc_weight > 0.0f, n, s);
     }
+    return B200JPEG_OK;
+    };
+    auto band_Ss = [&](int band) { return (nband == 2 && band == 1) ? p->trellis_freq_split + 1 : 1; };
+    auto band_Se = [&](int band) { return (nband == 2 && band == 0) ? p->trellis_freq_split : 63; };
+    if (!qopt) {
+      // the components' chains are independent: every round is one launch set over all of them
+      for (int loop = 0; loop < p->trellis_num_loops; loop++)
+        for (int band = 0; band < nband; band++) { int rc = round(g, rl, band_Ss(band), band_Se(band)); if (rc) return rc; }
+    } else {
+      // trellis_q_opt re-fits the tables every `group` passes of the reference's pass list (jcmaster.c:1014-1030), which
+      // walks the components one after the other (pass -> component, :453-465): a table one component updates is the
+      // table the next component's rounds use, so the rounds run in that order, one component at a time
+      const int group = g.nc * (nband == 2 ? 4 : 2);
+      int pass_number = 0;
+      CU(cudaMemsetAsync(A.d_qsum.p, 0, (size_t)n * 4 * 2 * 64 * 8, s));
+      for (int ci = 0; ci < g.nc; ci++) {
+        Geom gs = g; gs.nc = 1; gs.c[0] = g.c[ci];
+        RecLayout rls = rl; rls.comp_off[0] = rl.comp_off[ci];
+        for (int loop = 0; loop < p->trellis_num_loops; loop++)
+          for (int band = 0; band < nband; band++) {
+            pass_number++;                                          // the statistics pass
+            if (pass_number % group == 1) CU(cudaMemsetAsync(A.d_qsum.p, 0, (size_t)n * 4 * 2 * 64 * 8, s));   // prepare_for_pass, jcmaster.c:687-698
+            int rc = round(gs, rls, band_Ss(band), band_Se(band)); if (rc) return rc;
+            if ((pass_number + 1) % group == 0) launch_qopt_update(A.d_qsum.as<long long>(), qimg, n, s);
+            pass_number++;                                          // the trellis pass
+          }
+      }
+      CU(cudaMemcpyAsync(io.qimg, qimg, (size_t)n * 512, cudaMemcpyDeviceToDevice, s));      // kept per chunk for the DQT markers
     }
     tm.mark("dummy");
     launch_dummy(g, n, s);
@@ -781,6 +833,7 @@ static int queue_meta(b200jpeg_encoder *e, const ChunkIO &io, int k)
   CU(cudaMemcpyAsync(e->h_status.as<uint32_t>() + io.i0, io.status, (size_t)io.n * 4, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(e->h_out_pos.as<unsigned long long>() + (size_t)io.i0 * (nscans + 1), io.out_pos, (size_t)io.n * (nscans + 1) * 8, cudaMemcpyDeviceToHost, s));
   if (pl.search) CU(cudaMemcpyAsync(e->h_best_al.as<int>() + (size_t)io.i0 * 2, io.best_al, (size_t)io.n * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (pl.trellis && e->params.trellis_q_opt) CU(cudaMemcpyAsync(e->h_qimg.as<uint16_t>() + (size_t)io.i0 * 256, io.qimg, (size_t)io.n * 512, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(e->h_scan_size.as<uint32_t>() + (size_t)io.i0 * nscans, io.scan_size, (size_t)io.n * nscans * 4, cudaMemcpyDeviceToHost, s));
   if (pl.optimize) {
     size_t ntab = (size_t)io.n * nscans * HIST_SLOTS;
@@ -940,7 +993,13 @@ static int finish_chunk(b200jpeg_encoder *e, const ChunkIO &io, int k)
           if (m & (1u << (4 + t))) { ts.ac[t] = &set[4 + t]; ts.ac_sent[t] = false; }
         }
       }
-      if (k2 == 0) write_frame_header(p, pl.progressive, o);
+      if (k2 == 0) {
+        if (pl.trellis && p->trellis_q_opt) {                       // this image's re-fitted tables go into its DQT (jcmaster.c:1014-1030)
+          static thread_local b200jpeg_params pq;
+          pq = *p; memcpy(pq.quant_tbl, e->h_qimg.as<uint16_t>() + (size_t)gi * 256, 512);
+          write_frame_header(&pq, pl.progressive, o);
+        } else write_frame_header(p, pl.progressive, o);
+      }
       if (pl.search) last_ri = sd.dri ? -1 : sd.ri;               // the candidate's header as it was buffered when it was coded
       write_scan_header(p, sd, ts, last_ri, (unsigned)sd.ri, o);
       hdr_end[k2] = hdr.size();
@@ -1049,6 +1108,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
     if ((rc = e->h_status.reserve((size_t)n_images * 4))) return rc;
     if ((rc = e->h_out_pos.reserve((size_t)n_images * (nscans + 1) * 8))) return rc;
     if ((rc = e->h_best_al.reserve((size_t)n_images * 2 * 4))) return rc;
+    if (p->trellis_quant && p->trellis_q_opt && (rc = e->h_qimg.reserve((size_t)n_images * 512))) return rc;
     if ((rc = e->h_scan_size.reserve((size_t)n_images * nscans * 4))) return rc;
     if ((rc = e->h_tabs.reserve((pl.optimize ? (size_t)n_images * nscans : 1) * HIST_SLOTS * sizeof(HostHuff)))) return rc;
   }
@@ -1104,6 +1164,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
       io.scan_size = e->d_scan_size.as<uint32_t>() + (size_t)io.i0 * nscans;
       io.tabs_scan = e->d_tabs_scan.as<DevHuff>() + (size_t)io.i0 * nscans * HIST_SLOTS;
       io.best_al = e->d_best_al_all.as<int>() + (size_t)io.i0 * 2;
+      io.qimg = e->d_qimg_all.as<uint16_t>() + (size_t)io.i0 * 256;
       if (!on_device) { tm.s = e->sc[io.slot]; tm.mark("h2d_wait"); CU(cudaStreamWaitEvent(e->sc[io.slot], e->ev_in[k], 0)); }
       if ((rc = run_pipeline(e, io, tm))) break;
       if (!device_only) {
@@ -1188,10 +1249,10 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
   if (e->s_in) cudaStreamSynchronize(e->s_in);
   if (e->s_out) cudaStreamSynchronize(e->s_out);
   if (e->sc[1]) cudaStreamSynchronize(e->sc[1]);
-  DevBuf *db[] = {&e->d_src, &e->d_tabs_scan, &e->d_tabs_fixed, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_out, &e->d_qt, &e->d_tc, &e->d_best_al_all};
+  DevBuf *db[] = {&e->d_src, &e->d_tabs_scan, &e->d_tabs_fixed, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_out, &e->d_qt, &e->d_tc, &e->d_best_al_all, &e->d_qimg_all};
   for (DevBuf *b : db) b->release();
   e->ar[0].release(); e->ar[1].release();
-  PinBuf *pb[] = {&e->h_qt, &e->h_tc, &e->h_fixed, &e->h_status, &e->h_out_pos, &e->h_scan_size, &e->h_tabs, &e->h_stage, &e->h_best_al};
+  PinBuf *pb[] = {&e->h_qt, &e->h_tc, &e->h_fixed, &e->h_status, &e->h_out_pos, &e->h_scan_size, &e->h_tabs, &e->h_stage, &e->h_best_al, &e->h_qinit, &e->h_qimg};
   for (PinBuf *b : pb) b->release();
   for (PinBuf &b : e->file_arenas) b.release();
   for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 namespace b200 {
 
@@ -501,6 +502,10 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
         *reinterpret_cast<uint4 *>(&sY[(rg * VMAX + rr) * YP + seg * 8]) = *reinterpret_cast<const uint4 *>(yv);
       }
     } else {
+      // EXT: the input is one of the other pixel orders (4-sample pixels and / or blue first); the plain RGB / YCbCr /
+      // gray instantiation carries none of that logic
+      auto convert = [&](auto ext_tag) {
+      constexpr bool EXT = decltype(ext_tag)::value;
       int sb[8 / HMAX], sr[8 / HMAX];
 #pragma unroll
       for (int i = 0; i < 8 / HMAX; i++) { sb[i] = 0; sr[i] = 0; }
@@ -510,24 +515,24 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
 #pragma unroll
       for (int rr = 0; rr < VMAX; rr++) {
         const int iy = min(y0 + rg * VMAX + rr, g.H - 1);
-        Px8 p = load_px8<IC, SB>(base, g.row_pitch, iy, xs, g.W, fast, px4, pfirst);
+        Px8 p = load_px8<IC, SB>(base, g.row_pitch, iy, xs, g.W, fast, EXT && px4, EXT ? pfirst : 0);
         int16_t yv[8];
 #pragma unroll
         for (int px = 0; px < 8; px++) {
           if (NC == 1) yv[px] = (int16_t)(px_sample<1, SB>(p, px, 0) - CENTRE);
           else {
             const int S0 = px_sample<3, SB>(p, px, 0), G = px_sample<3, SB>(p, px, 1), S2 = px_sample<3, SB>(p, px, 2);
-            const int R = pswap ? S2 : S0, B = pswap ? S0 : S2;
+            const int R = (EXT && pswap) ? S2 : S0, B = (EXT && pswap) ? S0 : S2;
             yv[px] = (int16_t)(((19595 * R + 38470 * G + 7471 * B + 32768) >> 16) - CENTRE);
           }
         }
         *reinterpret_cast<uint4 *>(&sY[(rg * VMAX + rr) * YP + seg * 8]) = *reinterpret_cast<const uint4 *>(yv);
         if (NC == 3) {
-          if (er != rg) p = load_px8<IC, SB>(base, g.row_pitch, min(y0 + er * VMAX + rr, g.H - 1), xs, g.W, fast, px4, pfirst);
+          if (er != rg) p = load_px8<IC, SB>(base, g.row_pitch, min(y0 + er * VMAX + rr, g.H - 1), xs, g.W, fast, EXT && px4, EXT ? pfirst : 0);
 #pragma unroll
           for (int px = 0; px < 8; px++) {
             const int S0 = px_sample<3, SB>(p, px, 0), G = px_sample<3, SB>(p, px, 1), S2 = px_sample<3, SB>(p, px, 2);
-            const int R = pswap ? S2 : S0, B = pswap ? S0 : S2;
+            const int R = (EXT && pswap) ? S2 : S0, B = (EXT && pswap) ? S0 : S2;
             sb[px / HMAX] += (-11059 * R - 21709 * G + 32768 * B + (CENTRE << 16) + 32767) >> 16;
             sr[px / HMAX] += (32768 * R - 27439 * G - 5329 * B + (CENTRE << 16) + 32767) >> 16;
           }
@@ -548,6 +553,8 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
         if (HMAX == 1) { *reinterpret_cast<uint4 *>(cb) = *reinterpret_cast<const uint4 *>(cbv); *reinterpret_cast<uint4 *>(cr) = *reinterpret_cast<const uint4 *>(crv); }
         else { *reinterpret_cast<uint2 *>(cb) = *reinterpret_cast<const uint2 *>(cbv); *reinterpret_cast<uint2 *>(cr) = *reinterpret_cast<const uint2 *>(crv); }
       }
+      };
+      if (px4 || pswap) convert(std::true_type{}); else convert(std::false_type{});
     }
     }
   }
@@ -1602,9 +1609,13 @@ __global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : TRELLIS_MIN_CT
 // option, so this kernel is written for exactness, not speed.  Also (re)writes lambda_dc for the DC trellis that
 // follows each pass, from the natural-order norm recomputed here (:1026-1035).
 // ---------------------------------------------------------------------
+// qimg: per-image quantization tables [img][4][64] (natural order) that trellis_q_opt has re-fitted, or nullptr for the
+// batch's tables; eo: per real block {zero-distortion cost of blanking the band, best cost without the EOB symbol,
+// has_eob} for the block-level EOB-run pass of trellis_eob_opt (k_trellis_eob_rows), or nullptr.
 __global__ void __launch_bounds__(128) k_trellis_ac_band(Geom g, const TrellisConsts *__restrict__ tc,
                                                          const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
-                                                         DcRec *__restrict__ rec, RecLayout rl, int Ss, int Se)
+                                                         DcRec *__restrict__ rec, RecLayout rl, int Ss, int Se,
+                                                         const uint16_t *__restrict__ qimg, float4 *__restrict__ eo)
 {
   const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
   const CompGeom &c = g.c[ci];
@@ -1616,7 +1627,12 @@ __global__ void __launch_bounds__(128) k_trellis_ac_band(Geom g, const TrellisCo
   {
     const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + (4 + c.ac_tbl);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) acsi[i] = ac->size[i];
-    if (threadIdx.x < 64) { swz[threadIdx.x] = tc->w_zz[c.qt][threadIdx.x]; sq8[threadIdx.x] = tc->q8_zz[c.qt][threadIdx.x]; }
+    if (threadIdx.x < 64) {
+      if (qimg) {                                                // jcdctmgr.c:1017-1021 on this image's current table
+        const int Q = qimg[((size_t)img * 4 + c.qt) * 64 + c_zz[threadIdx.x]];
+        swz[threadIdx.x] = (float)(1.0 / (double)(Q * Q)); sq8[threadIdx.x] = 8 * Q;
+      } else { swz[threadIdx.x] = tc->w_zz[c.qt][threadIdx.x]; sq8[threadIdx.x] = tc->q8_zz[c.qt][threadIdx.x]; }
+    }
   }
   __syncthreads();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1671,13 +1687,16 @@ __global__ void __launch_bounds__(128) k_trellis_ac_band(Geom g, const TrellisCo
   }
   int last = Ss - 1;
   float best = azd[Se] + (float)acsi[0];
+  float best_skip = azd[Se];                                   // :1189-1190 cost_all_zeros, best_cost_skip
   for (int i = Ss; i <= Se; i++) {
     if (cur[i] != 0) {
       float cst = acc[i] + azd[Se] - azd[i];
+      const float wo_eob = cst;
       if (i < Se) cst += (float)acsi[0];
-      if (cst < best) { best = cst; last = i; }
+      if (cst < best) { best = cst; last = i; best_skip = wo_eob; }
     }
   }
+  if (eo) eo[ridx] = make_float4(azd[Se], best_skip, __int_as_float((last < Se) + (last == Ss - 1)), 0.f);   // :1209 has_eob
   for (int i = Se; i >= Ss; ) {
     while (i > last) { cur[i] = 0; i--; }
     if (i < Ss) break;
@@ -1690,12 +1709,179 @@ __global__ void __launch_bounds__(128) k_trellis_ac_band(Geom g, const TrellisCo
   rec[ridx].nzmask = (rec[ridx].nzmask & ~bandmask) | bits;
 }
 void launch_trellis_ac_band(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                            DcRec *rec, const RecLayout &rl, int Ss, int Se, int n, cudaStream_t s)
+                            DcRec *rec, const RecLayout &rl, int Ss, int Se, const uint16_t *qimg, float4 *eo, int n, cudaStream_t s)
 {
   long long mb = 0;
   for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
   dim3 grid((unsigned)((mb + 127) / 128), n * g.nc);
-  k_trellis_ac_band<<<grid, 128, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, Ss, Se);
+  k_trellis_ac_band<<<grid, 128, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, Ss, Se, qimg, eo);
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------
+// trellis_eob_opt (jcdctmgr.c:981-996, :1224-1297): after the per-block search, a second dynamic program along each
+// block row decides which blocks to blank so that runs of all-zero blocks can share one EOBRUN symbol.  One warp per
+// (image, component, block row); the predecessor loop of :1232-1254 runs across the lanes (each lane keeps the first
+// minimum of its own ascending stripe, the warp then takes the smallest cost with ties to the smaller index, which is
+// the reference's strict-'<' scan order); the four per-block arrays live in the scratch `es` (16 bytes per block).
+// ---------------------------------------------------------------------
+// slot b of a row's scratch: accumulated_zero_block_cost[b+1], accumulated_block_cost[b+1], requires_eob[b+1] and
+// block_run_start[b]; index 0 of the three arrays is the constant initial state {0, 0, 0} (:991-995)
+struct EobState { float zero, cost; int start, req; };
+__global__ void __launch_bounds__(32) k_trellis_eob_rows(Geom g, const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
+                                                        DcRec *__restrict__ rec, RecLayout rl, int Ss, int Se,
+                                                        const float4 *__restrict__ eo, EobState *__restrict__ es /* one slot per real block */)
+{
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
+  const CompGeom &c = g.c[ci];
+  const int row = blockIdx.x;
+  if (row >= c.hib) return;
+  const int n = c.wib, lane = threadIdx.x;
+  __shared__ uint8_t acsi[256];
+  {
+    const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + (4 + c.ac_tbl);
+    for (int i = lane; i < 256; i += 32) acsi[i] = ac->size[i];
+  }
+  __syncwarp();
+  const size_t rbase = (size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * n;
+  const float4 *e = eo + rbase;
+  EobState *st = es + rbase;
+  auto state = [&](int i, float &zero, float &cost, int &req) {
+    if (i == 0) { zero = 0.f; cost = 0.f; req = 0; }
+    else { const EobState p = st[i - 1]; zero = p.zero; cost = p.cost; req = p.req; }
+  };
+  // the smallest cost over the lanes, ties to the smaller predecessor index (= the first minimum of the ascending scan)
+  auto warp_first_min = [&](float &best, int &best_i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, off); const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+      if (oi >= 0 && (best_i < 0 || ob < best || (ob == best && oi < best_i))) { best = ob; best_i = oi; }
+    }
+  };
+  float zb = 0.f;                                              // accumulated_zero_block_cost[bi]
+  for (int bi = 0; bi < n; bi++) {
+    const float4 me = e[bi];
+    const int has_eob = __float_as_int(me.z);
+    float best = 1e38f; int best_i = -1;
+    if (has_eob != 2) {                                        // :1232-1254
+      for (int i = lane; i <= bi; i += 32) {
+        float pz, pc; int pr; state(i, pz, pc, pr);
+        if (pr == 2) continue;
+        float cst = me.y;                                       // cost of coding a non-zero block
+        cst += zb; cst -= pz; cst += pc;
+        const int run = bi - i + pr, nb = nbits_of(run);
+        cst += (float)(acsi[16 * nb] + nb);
+        if (cst < best) { best = cst; best_i = i; }
+      }
+      warp_first_min(best, best_i);
+    }
+    __syncwarp();
+    const float znext = zb + me.x;
+    if (lane == 0) {
+      EobState nx; nx.zero = znext; nx.req = has_eob; nx.cost = best_i >= 0 ? best : 0.f; nx.start = best_i >= 0 ? best_i : 0;
+      st[bi] = nx;
+    }
+    zb = znext;
+    __syncwarp();
+  }
+  // :1258-1276 where the last run of blank blocks starts
+  int last_block = n;
+  {
+    float best = 1e38f; int best_i = -1;
+    for (int i = lane; i <= n; i += 32) {
+      float pz, pc; int pr; state(i, pz, pc, pr);
+      if (pr == 2) continue;
+      float cst = 0.0f;
+      cst += zb; cst -= pz;
+      const int run = n - i + pr, nb = nbits_of(run);
+      cst += (float)(acsi[16 * nb] + nb);
+      if (cst < best) { best = cst; best_i = i; }
+    }
+    warp_first_min(best, best_i);
+    if (best_i >= 0) last_block = best_i;
+  }
+  // :1277-1292 back-track; blanked blocks lose the band's coefficients (the lanes clear one block together)
+  last_block--;
+  int bi = n - 1;
+  const unsigned long long bandmask = ((Se >= 63 ? ~0ull : ((1ull << (Se + 1)) - 1ull))) & ~((1ull << Ss) - 1ull);
+  while (bi >= 0) {
+    while (bi > last_block) {
+      int16_t *blk = c.coef + (((size_t)img * c.hpad + row) * c.wpad + bi) * 64;
+      for (int k = Ss + lane; k <= Se; k += 32) blk[k] = 0;
+      if (lane == 0) rec[rbase + bi].nzmask &= ~bandmask;
+      bi--;
+    }
+    if (bi < 0) break;
+    last_block = st[bi].start - 1;
+    bi--;
+  }
+}
+void launch_trellis_eob_rows(const Geom &g, const DevHuff *tabs, size_t tabs_set_stride, DcRec *rec, const RecLayout &rl, int Ss, int Se,
+                             const float4 *eo, void *scratch, int n, cudaStream_t s)
+{
+  int mh = 0; for (int ci = 0; ci < g.nc; ci++) mh = max(mh, g.c[ci].hib);
+  k_trellis_eob_rows<<<dim3(mh, n * g.nc), 32, 0, s>>>(g, tabs, tabs_set_stride, rec, rl, Ss, Se, eo, static_cast<EobState *>(scratch));
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------
+// trellis_q_opt (jcdctmgr.c:1299-1306, jcmaster.c:1014-1030): per quantization table and coefficient position the
+// sums of raw * kept and 8 * kept^2 over the blocks requantized since the last table update (64-bit integers: the
+// reference adds the same integers in doubles, exactly), then the table entry becomes their rounded quotient.
+// ---------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_qopt_sums(Geom g, long long *__restrict__ qsum /* [img][4][2][64] natural order */)
+{
+  __shared__ long long sh[2][64];
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
+  const CompGeom &c = g.c[ci];
+  const long long nblk = (long long)c.wib * c.hib;
+  if ((long long)blockIdx.x * blockDim.x >= nblk) return;
+  if (threadIdx.x < 128) reinterpret_cast<long long *>(sh)[threadIdx.x] = 0;
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nblk) {
+    const int by = (int)(t / c.wib), bx = (int)(t - (long long)by * c.wib);
+    const size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
+    const int16_t *raw16 = c.raw + blk * 64, *co = c.coef + blk * 64;
+    for (int k = 1; k < 64; k++) {
+      const int v = co[k];
+      if (v) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(&sh[0][k]), (unsigned long long)(long long)((int)raw16[k] * v));
+        atomicAdd(reinterpret_cast<unsigned long long *>(&sh[1][k]), (unsigned long long)(long long)(8 * v * v));
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, k = threadIdx.x & 63;
+    const long long v = sh[which][k];
+    if (v) atomicAdd(reinterpret_cast<unsigned long long *>(&qsum[(((size_t)img * 4 + c.qt) * 2 + which) * 64 + c_zz[k]]), (unsigned long long)v);
+  }
+}
+__global__ void k_qopt_update(long long *__restrict__ qsum, uint16_t *__restrict__ qimg, int n)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // (img, table, position)
+  if (i >= n * 256) return;
+  const int j = i & 63, it = i >> 6;
+  if (j == 0) return;
+  const long long ns = qsum[((size_t)it * 2 + 0) * 64 + j], nc2 = qsum[((size_t)it * 2 + 1) * 64 + j];
+  if (nc2 != 0) {
+    int q = (int)((double)ns / (double)nc2 + 0.5);
+    if (q > 254) q = 254;
+    if (q < 1) q = 1;
+    qimg[(size_t)it * 64 + j] = (uint16_t)q;
+  }
+}
+void launch_qopt_sums(const Geom &g, long long *qsum, int n, cudaStream_t s)
+{
+  long long mb = 0;
+  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
+  k_qopt_sums<<<dim3((unsigned)((mb + 127) / 128), n * g.nc), 128, 0, s>>>(g, qsum);
+  LAUNCHED();
+}
+void launch_qopt_update(long long *qsum, uint16_t *qimg, int n, cudaStream_t s)
+{
+  k_qopt_update<<<(n * 256 + 255) / 256, 256, 0, s>>>(qsum, qimg, n);
   LAUNCHED();
 }
 
@@ -1714,7 +1900,7 @@ void launch_trellis_ac_band(const Geom &g, const TrellisConsts *tc, const DevHuf
 struct SRec { float norm; uint32_t lin; unsigned long long nzmask; };
 static_assert(sizeof(SRec) == 16, "SRec layout");
 
-__global__ void __launch_bounds__(256) k_sort_blocks2(Geom g, const DcRec *__restrict__ rec, RecLayout rl, SRec *__restrict__ srec, uint32_t *__restrict__ splits)
+__global__ void __launch_bounds__(256) k_sort_blocks2(Geom g, const DcRec *__restrict__ rec, RecLayout rl, SRec *__restrict__ srec, uint32_t *__restrict__ splits, int mid_max)
 {
   __shared__ unsigned cnt[64], start[64];
   const int ci = blockIdx.x % g.nc, img = blockIdx.x / g.nc;
@@ -1728,8 +1914,9 @@ __global__ void __launch_bounds__(256) k_sort_blocks2(Geom g, const DcRec *__res
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned a = 0; for (int k = 0; k < 64; k++) { start[k] = a; a += cnt[k]; }
-    // decreasing count: [0, s0) more than 32 non-zeros, [s0, s1) 17..32, [s1, s2) 9..16, [s2, nblk) at most 8
-    splits[4 * blockIdx.x] = start[63 - 32]; splits[4 * blockIdx.x + 1] = start[63 - 16]; splits[4 * blockIdx.x + 2] = start[63 - 8];
+    // decreasing count: [0, s0) more than 32 non-zeros, [s0, s1) 16..32 (17..32 for the second-generation kernels),
+    // [s1, s2) 9..15 (16), [s2, nblk) at most 8.  15 list slots per thread let 8 CTAs share an SM's shared memory.
+    splits[4 * blockIdx.x] = start[63 - 32]; splits[4 * blockIdx.x + 1] = start[63 - mid_max]; splits[4 * blockIdx.x + 2] = start[63 - 8];
     splits[4 * blockIdx.x + 3] = (uint32_t)nblk;
   }
   __syncthreads();
@@ -2071,7 +2258,7 @@ k_trellis_ac2(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__res
 void launch_trellis_ac2(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                         DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s)
 {
-  k_sort_blocks2<<<n * g.nc, 256, 0, s>>>(g, rec, rl, static_cast<SRec *>(srec), splits); LAUNCHED();
+  k_sort_blocks2<<<n * g.nc, 256, 0, s>>>(g, rec, rl, static_cast<SRec *>(srec), splits, 16); LAUNCHED();
   long long mb = 0;
   for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
   const unsigned full = (unsigned)((mb + T2_THREADS - 1) / T2_THREADS);
@@ -2083,6 +2270,279 @@ void launch_trellis_ac2(const Geom &g, const TrellisConsts *tc, const DevHuff *t
   k_trellis_ac2<32><<<grid, T2_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, static_cast<const SRec *>(srec), splits); LAUNCHED();
   k_trellis_ac2<16><<<grid, T2_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, static_cast<const SRec *>(srec), splits); LAUNCHED();
   k_trellis_ac2<8><<<grid, T2_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, static_cast<const SRec *>(srec), splits); LAUNCHED();
+}
+
+// =====================================================================
+// AC trellis, third generation: rolled loops over shared-memory lists (same arithmetic and selection rule as
+// k_trellis_ac, jcdctmgr.c:1121-1222).  One thread per block, blocks in sorted order (k_sort_blocks2), one kernel
+// instantiation per count class; the class only sizes the per-thread lists.
+//  * phase 1 walks the 63 raw coefficients once (packed fp32x2 conversion / squaring / weighting, scalar prefix chain
+//    in the reference's order) and PUSHES an entry {A[p-1], p | raw << 16} for every position p whose plain-quantized
+//    value is non-zero -- nothing else of the prefix is kept;
+//  * the search runs entry by entry with warp-uniform trip counts: per predecessor s one 8-byte record {-A[p_s], acc_s}
+//    and one word {4 p_s | ...} are read, T = (A[i-1] - A[p_s]) + acc_s is formed once and shared by the (up to 3
+//    unrolled) candidates, whose distortion is +inf on lanes that do not have them -- so no lane-dependent branch sits
+//    inside the predecessor loop; the number of unrolled candidates follows the warp's largest candidate count;
+//  * code size is a few hundred instructions (the first two generations unrolled the entry x predecessor loops into
+//    5-8 thousand and stalled on instruction fetch), registers ~50, shared memory 12 bytes per list slot and thread.
+// =====================================================================
+#define T3_THREADS 128
+template <int MM> struct T3Smem {
+  uint2 rec[MM][T3_THREADS];       // before the entry is processed: {A[p-1], p | raw << 16}; after: {-A[p], accumulated cost}
+  unsigned ew[MM][T3_THREADS];     // 4*p | chosen predecessor (1-based entry, 0 = block start) << 8 | chosen value << 16
+};
+
+template <int KN>
+__device__ __forceinline__ void t3_pred_loop(const int t, const uint2 *__restrict__ rec /* + tid */, const unsigned *__restrict__ ew /* + tid */,
+                                             const char *__restrict__ rb, const float before, const float d0, const float d1, const float d2,
+                                             float &kb0, int &ks0, float &kb1, int &ks1, float &kb2, int &ks2)
+{
+#pragma unroll 2
+  for (int s = 0; s < t; s++) {
+    const uint2 r = rec[s * T3_THREADS];
+    const int pos4 = (int)(ew[s * T3_THREADS] & 0xFCu);         // (stale words on idle lanes must still give aligned addresses)
+    const float T = (before + __uint_as_float(r.x)) + __uint_as_float(r.y);          // :1176
+    const char *ra = rb - pos4;
+    { const float c = (*reinterpret_cast<const float *>(ra) + d0) + T; if (c < kb0) { kb0 = c; ks0 = s + 1; } }
+    if (KN > 1) { const float c = (*reinterpret_cast<const float *>(ra + 256) + d1) + T; if (c < kb1) { kb1 = c; ks1 = s + 1; } }
+    if (KN > 2) { const float c = (*reinterpret_cast<const float *>(ra + 512) + d2) + T; if (c < kb2) { kb2 = c; ks2 = s + 1; } }
+  }
+}
+// distortion of candidate value `cand` at a position with divisor q, raw magnitude x (:1149-1151)
+__device__ __forceinline__ float t3_dist(const int cand, const int q, const int x, const float lambda, const float wl)
+{
+  const float fd = u2f_exact((unsigned)abs(cand * q - x));
+  return ((fd * fd) * lambda) * wl;
+}
+
+template <int MM>
+__global__ void __launch_bounds__(T3_THREADS, MM <= 15 ? 8 : MM <= 32 ? 4 : 2)
+k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
+              DcRec *__restrict__ rec, RecLayout rl, const SRec *__restrict__ srec, const uint32_t *__restrict__ splits)
+{
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
+  const CompGeom &c = g.c[ci];
+  long long lo, hi;
+  {
+    const uint4 sp = reinterpret_cast<const uint4 *>(splits)[blockIdx.y];
+    if (MM == 64) { lo = 0; hi = sp.x; } else if (MM == 32) { lo = sp.x; hi = sp.y; } else if (MM == 15) { lo = sp.y; hi = sp.z; } else { lo = sp.z; hi = sp.w; }
+  }
+  const int nchunks = (int)((hi - lo + T3_THREADS - 1) / T3_THREADS);
+  if ((int)blockIdx.x >= nchunks) return;
+  extern __shared__ __align__(16) unsigned char t3_dyn[];
+  T3Smem<MM> &L = *reinterpret_cast<T3Smem<MM> *>(t3_dyn);
+  // rate[k][run] (:1163-1175), +inf where the reference skips.  Lanes past their block's last entry run the loops on
+  // whatever the lists hold (their results are discarded): such reads stay within 256 bytes in front of the table
+  __shared__ __align__(16) float srate_pad[64 + 10 * 64];
+  float *srate = srate_pad + 64;
+  __shared__ __align__(16) uint4 sEnt[64];                    // per zigzag position {8*Q, reciprocal, weight, -}
+  __shared__ __align__(16) float swz[64];
+  __shared__ int sqL;
+  const int tid = threadIdx.x;
+  uint8_t *acsi = reinterpret_cast<uint8_t *>(t3_dyn);        // table build only
+  {
+    const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + (4 + c.ac_tbl);
+    for (int i = tid; i < 256; i += T3_THREADS) acsi[i] = ac->size[i];
+    if (tid < 64) {
+      const float w = tc->w_zz[c.qt][tid];
+      swz[tid] = w;
+      sEnt[tid] = make_uint4((unsigned)tc->q8_zz[c.qt][tid], tc->qmul_zz[c.qt][tid], __float_as_uint(w), 0u);
+    }
+    if (tid == 0) sqL = tc->qL[c.qt];
+  }
+  __syncthreads();
+  for (int e = tid; e < 640; e += T3_THREADS) {
+    const int k = e >> 6, run = e & 63;
+    const int zrl = acsi[0xF0], cb = acsi[16 * (run & 15) + k + 1];
+    const bool skip = cb == 0 || ((run >> 4) && zrl == 0) || run == 63;
+    srate[e] = skip ? __int_as_float(0x7F800000) : (float)(cb + (k + 1) + (run >> 4) * zrl);
+  }
+  const float eob = (float)acsi[0];
+  __syncthreads();                                             // acsi (aliasing the lists) is dead from here on
+  const int maxq = (1 << tc->max_coef_bits) - 1;
+  const int qL = sqL;
+  const size_t rbase = (size_t)img * rl.per_image + rl.comp_off[ci];
+  const int use_norm = tc->use_norm;
+  const double p1 = tc->p1, p2 = tc->p2; const float lambda_const = tc->lambda_const;
+  uint2 *myrec = &L.rec[0][tid]; unsigned *myew = &L.ew[0][tid];
+  const char *srate_b = reinterpret_cast<const char *>(srate);
+  const float INF = __int_as_float(0x7F800000);
+
+#pragma unroll 1
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const long long tix = lo + (long long)chunk * T3_THREADS + tid;
+    const bool live = tix < hi;                                // whole warps stay in step (warp reductions below); dead lanes do no memory traffic
+    SRec sr; sr.norm = 0.f; sr.lin = 0; sr.nzmask = 0;
+    if (live) sr = srec[rbase + tix];
+    const unsigned lin = sr.lin;
+    const int by = lin / c.wib, bx = lin - by * c.wib;
+    const size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
+    const int16_t *raw16 = c.raw + blk * 64;
+    int16_t *o16 = c.coef + blk * 64;
+    uint4 rv[8];
+#pragma unroll
+    for (int v = 0; v < 8; v++) rv[v] = make_uint4(0, 0, 0, 0);
+    unsigned dc_q = 0;
+    if (live) {
+      const uint4 *r4 = reinterpret_cast<const uint4 *>(raw16);
+#pragma unroll
+      for (int v = 0; v < 8; v++) rv[v] = r4[v];
+      dc_q = (unsigned)(unsigned short)o16[0];                 // the DC value survives the rewrite
+    }
+    float lambda;
+    {
+      const float norm = (float)((double)sr.norm / 63.0);      // :1026-1035
+      if (use_norm) lambda = (float)(p1 / (p2 + (double)norm)); else lambda = lambda_const;
+      if (live) rec[rbase + lin].lambda_dc = lambda * swz[0];
+    }
+    // phase 1: accumulated zero distortion, zigzag order, serial fp32 (:1134); entries pushed where the mask says so
+    const unsigned mlo = (unsigned)sr.nzmask, mhi = (unsigned)(sr.nzmask >> 32);
+    const int m = __popc(mlo) + __popc(mhi);
+    float azd = 0.0f;
+    {
+      uint2 *push = myrec;
+      const float2 l2 = make_float2(lambda, lambda);
+      const float2 bias = make_float2(-8421376.0f, -8421376.0f);   // -(2^23 + 2^15): undoes the exponent trick and the +32768 offset
+#pragma unroll
+      for (int v = 0; v < 8; v++) {
+        const unsigned aw[4] = {rv[v].x, rv[v].y, rv[v].z, rv[v].w};
+        const float4 w0 = reinterpret_cast<const float4 *>(swz)[2 * v], w1 = reinterpret_cast<const float4 *>(swz)[2 * v + 1];
+        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const unsigned mw = v < 4 ? mlo : mhi;                   // mask word holding this group's 8 bits
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          const unsigned u = aw[jj] ^ 0x80008000u;               // both halves + 32768
+          float2 f = make_float2(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7632)));
+          f = __fadd2_rn(f, bias);                               // the raw values as floats, exact
+          const float2 z = __fmul2_rn(__fmul2_rn(__fmul2_rn(f, f), l2), make_float2(ww[2 * jj], ww[2 * jj + 1]));
+          const int i = 8 * v + 2 * jj;
+          if (i != 0) {
+            // entry word: position | raw value << 16 (one byte permute)
+            if (mw & (1u << (i & 31))) { *push = make_uint2(__float_as_uint(azd), __byte_perm(aw[jj], (unsigned)i, 0x1054)); push += T3_THREADS; }
+            azd = z.x + azd;
+          }
+          if (mw & (1u << ((i + 1) & 31))) { *push = make_uint2(__float_as_uint(azd), __byte_perm(aw[jj], (unsigned)(i + 1), 0x3254)); push += T3_THREADS; }
+          azd = z.y + azd;
+        }
+      }
+    }
+    const float azd63 = azd;
+    // phase 2 (:1121-1185): entries in order; all lanes of the warp walk the same entry index.  The end-of-block choice
+    // (:1187-1207) rides along: an entry's cost of being the last one is known as soon as the entry is settled.
+    const int mmax = __reduce_max_sync(0xffffffffu, m);
+    int last = 0;
+    float best_cost = azd63 + eob;
+    // the entry's own constants (fetching them one entry ahead, behind the previous predecessor loop, measured no gain)
+    struct Ent { float before, wl, at; int i, rawv, x, q, qv; };
+    auto fetch = [&](int t) {
+      Ent n;
+      const uint2 e = myrec[t * T3_THREADS];
+      n.before = __uint_as_float(e.x);                          // A[i-1]
+      n.i = (int)(e.y & 63u); n.rawv = (int)e.y >> 16;
+      const uint4 en = sEnt[n.i];                               // {8*Q, reciprocal, weight bits, -}
+      n.x = abs(n.rawv); n.q = (int)en.x;
+      n.wl = __uint_as_float(en.z);
+      n.qv = min((int)(__umulhi((unsigned)(n.x + (n.q >> 1)) << 14, en.y) >> qL), maxq);      // :1136-1144
+      const float fx = u2f_exact((unsigned)n.x);
+      n.at = ((fx * fx) * lambda) * n.wl + n.before;            // A[i], as phase 1 formed it
+      return n;
+    };
+#pragma unroll 1
+    for (int t = 0; t < mmax; t++) {
+      const bool act = t < m;
+      const Ent ce = fetch(t);
+      const float before = ce.before, wl = ce.wl, at = ce.at;
+      const int i = ce.i, rawv = ce.rawv, x = ce.x, q = ce.q, qv = ce.qv;
+      const int nc = act ? nbits_of(qv) : 0;
+      const char *rb = srate_b + (i - 1) * 4;                   // rate of run i-1-j at rb[-4j] (+256 per candidate)
+      const int ncmax = __reduce_max_sync(0xffffffffu, nc);
+      // candidates 0..2 (values 1, 3, 7 below the last one, which is qv itself, :1146-1153); a lane that lacks a candidate
+      // gives it an infinite distortion.  Block start as predecessor first: run i-1, zero tail.
+      float kb0 = 1e38f, kb1 = 1e38f, kb2 = 1e38f; int ks0 = 0, ks1 = 0, ks2 = 0;
+      float best, d0, d1 = INF, d2 = INF; int best_s, best_k;
+      d0 = t3_dist(nc > 1 ? 1 : qv, q, x, lambda, wl);
+      kb0 = fminf((*reinterpret_cast<const float *>(rb) + d0) + before, kb0);
+      if (ncmax <= 1) {
+        t3_pred_loop<1>(t, myrec, myew, rb, before, d0, d1, d2, kb0, ks0, kb1, ks1, kb2, ks2);
+        best = kb0; best_s = ks0; best_k = kb0 < 1e38f ? 0 : -1;
+      } else {
+        d1 = nc > 1 ? t3_dist(nc > 2 ? 3 : qv, q, x, lambda, wl) : INF;
+        kb1 = fminf((*reinterpret_cast<const float *>(rb + 256) + d1) + before, kb1);
+        if (ncmax == 2) t3_pred_loop<2>(t, myrec, myew, rb, before, d0, d1, d2, kb0, ks0, kb1, ks1, kb2, ks2);
+        else {
+          d2 = nc > 2 ? t3_dist(nc > 3 ? 7 : qv, q, x, lambda, wl) : INF;
+          kb2 = fminf((*reinterpret_cast<const float *>(rb + 512) + d2) + before, kb2);
+          t3_pred_loop<3>(t, myrec, myew, rb, before, d0, d1, d2, kb0, ks0, kb1, ks1, kb2, ks2);
+        }
+        // over candidates: smallest cost, ties to the earlier predecessor, then to the earlier candidate (:1157-1184 in its scan order)
+        best = 1e38f; best_s = 0; best_k = -1;
+        if (kb0 < best) { best = kb0; best_s = ks0; best_k = 0; }
+        if (kb1 < best || (kb1 == best && ks1 < best_s)) { best = kb1; best_s = ks1; best_k = 1; }
+        if (ncmax > 2 && (kb2 < best || (kb2 == best && ks2 < best_s))) { best = kb2; best_s = ks2; best_k = 2; }
+#pragma unroll 1
+        for (int k = 3; k < ncmax; k++) {                        // values of 16 and more: rare
+          const float dk = k < nc ? t3_dist(k < nc - 1 ? (2 << k) - 1 : qv, q, x, lambda, wl) : INF;
+          const char *rk = rb + k * 256;
+          float kb = fminf((*reinterpret_cast<const float *>(rk) + dk) + before, 1e38f); int ks = 0;
+          float u1 = 1e38f, u2 = 1e38f; int v1 = 0, v2 = 0;
+          t3_pred_loop<1>(t, myrec, myew, rk, before, dk, INF, INF, kb, ks, u1, v1, u2, v2);
+          if (kb < best || (kb == best && ks < best_s)) { best = kb; best_s = ks; best_k = k; }
+        }
+      }
+      // the value this entry takes if it stays on the chain (:1179, :1143-1153)
+      const int cand = (best_k >= 0 && best_k < nc - 1) ? (2 << best_k) - 1 : qv;
+      const int sgn = rawv >> 31;
+      const int val = (cand ^ sgn) - sgn;
+      if (act) {
+        myrec[t * T3_THREADS] = make_uint2(__float_as_uint(-at), __float_as_uint(best));
+        myew[t * T3_THREADS] = (unsigned)(i << 2) | ((unsigned)best_s << 8) | ((unsigned)val << 16);
+        float cst = (best + azd63) - at;
+        if (i < 63) cst += eob;
+        if (cst < best_cost) { best_cost = cst; last = t + 1; }
+      }
+    }
+    if (live) {
+      // output: zeros except the back-tracked chain (:1211-1222)
+      uint4 *q4 = reinterpret_cast<uint4 *>(o16);
+      q4[0] = make_uint4(dc_q, 0, 0, 0);
+#pragma unroll
+      for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
+      unsigned long long fm = 0;
+      while (last != 0) {
+        const unsigned w = myew[(last - 1) * T3_THREADS];
+        const int pos = (int)((w & 0xFFu) >> 2), val = (int)w >> 16;
+        o16[pos] = (int16_t)val; if (val) fm |= 1ull << pos;
+        last = (int)((w >> 8) & 0xFFu);
+      }
+      if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fm;
+    }
+  }
+}
+
+template <int MM>
+static void launch_t3(dim3 grid, cudaStream_t s, const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
+                      DcRec *rec, const RecLayout &rl, const SRec *srec, const uint32_t *splits)
+{
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_trellis_ac3<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T3Smem<MM>)); attr_set = true; }
+  k_trellis_ac3<MM><<<grid, T3_THREADS, sizeof(T3Smem<MM>), s>>>(g, tc, tabs, tabs_set_stride, rec, rl, srec, splits); LAUNCHED();
+}
+void launch_trellis_ac3(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
+                        DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s)
+{
+  k_sort_blocks2<<<n * g.nc, 256, 0, s>>>(g, rec, rl, static_cast<SRec *>(srec), splits, 15); LAUNCHED();
+  long long mb = 0;
+  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
+  const unsigned full = (unsigned)((mb + T3_THREADS - 1) / T3_THREADS);
+  // CTAs loop over their class's chunks: enough of them per (image, component) to fill the device, few enough to amortise the tables
+  unsigned gx = (unsigned)max(1, min((int)full, (148 * 8 * 3 + n * g.nc - 1) / (n * g.nc)));
+  dim3 grid(gx, n * g.nc);
+  const SRec *sr = static_cast<const SRec *>(srec);
+  // largest blocks first: the classes touch disjoint blocks
+  launch_t3<64>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
+  launch_t3<32>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
+  launch_t3<15>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
+  launch_t3<8>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
 }
 
 void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,

@@ -126,9 +126,17 @@ void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *ta
 // (image, component)) and runs one class-specific kernel per count class
 void launch_trellis_ac2(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                         DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s);
+void launch_trellis_ac3(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
+                        DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s);
 // use_scans_in_trellis: quantize_trellis restricted to the zigzag band [Ss, Se]
 void launch_trellis_ac_band(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                            DcRec *rec, const RecLayout &rl, int Ss, int Se, int n, cudaStream_t s);
+                            DcRec *rec, const RecLayout &rl, int Ss, int Se, const uint16_t *qimg, float4 *eo, int n, cudaStream_t s);
+// trellis_eob_opt: block-level EOB-run pass over every block row (eo from the band kernel; scratch: 16 bytes per real block)
+void launch_trellis_eob_rows(const Geom &g, const DevHuff *tabs, size_t tabs_set_stride, DcRec *rec, const RecLayout &rl, int Ss, int Se,
+                             const float4 *eo, void *scratch, int n, cudaStream_t s);
+// trellis_q_opt: accumulate the table-fitting sums of the components in g ([img][4][2][64] int64) / re-fit the per-image tables
+void launch_qopt_sums(const Geom &g, long long *qsum, int n, cudaStream_t s);
+void launch_qopt_update(long long *qsum, uint16_t *qimg, int n, cudaStream_t s);
 void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                        const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int vertical, int n, cudaStream_t s);
 // tile_last / tile_first: int [n][ceil(nblocks/256)] scratch

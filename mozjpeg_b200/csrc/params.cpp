@@ -292,7 +292,7 @@ int b200jpeg_validate(const b200jpeg_params *p) {
   if (p->dct_method != B200JPEG_DCT_ISLOW && p->data_precision != 8) { set_error("dct_method %d at %d bits is not on the device path (JDCT_IFAST / JDCT_FLOAT: 8 bits only)", p->dct_method, p->data_precision); return B200JPEG_ERR_UNSUPPORTED; }
   if (p->smoothing_factor < 0 || p->smoothing_factor > 100) { set_error("smoothing_factor %d out of range 0..100", p->smoothing_factor); return B200JPEG_ERR_PARAM; }
   if (p->trellis_quant && p->use_scans_in_trellis && (p->trellis_freq_split < 1 || p->trellis_freq_split > 62)) { set_error("trellis_freq_split %d: the device path takes 1..62 with use_scans_in_trellis", p->trellis_freq_split); return B200JPEG_ERR_UNSUPPORTED; }
-  if (p->trellis_eob_opt || p->trellis_q_opt || p->trellis_num_loops < 1 || p->trellis_num_loops > 16) { set_error("non-default trellis option is not on the device path yet"); return B200JPEG_ERR_UNSUPPORTED; }
+  if (p->trellis_num_loops < 1 || p->trellis_num_loops > 16) { set_error("trellis_num_loops %d: the device path takes 1..16", p->trellis_num_loops); return B200JPEG_ERR_UNSUPPORTED; }
   // validate_script (jcmaster.c:252-436)
   bool progressive = false;
   if (p->num_scans > 0 && p->optimize_scans) {

@@ -98,7 +98,9 @@ def test_validation_errors(built):
     assert lib.b200jpeg_validate(C.byref(q)) == 0                      # input smoothing is on the device path
     q = p.copy(); q.smoothing_factor = 101
     assert lib.b200jpeg_validate(C.byref(q)) == A.ERR_PARAM
-    q = p.copy(); q.trellis_q_opt = 1
+    q = p.copy(); q.trellis_q_opt = 1; q.trellis_eob_opt = 1
+    assert lib.b200jpeg_validate(C.byref(q)) == 0                      # both optional trellis modes are on the device path
+    q = p.copy(); q.trellis_num_loops = 17
     assert lib.b200jpeg_validate(C.byref(q)) == A.ERR_UNSUPPORTED
     q = p.copy(); q.num_scans = 1; q.scan_info[0].comps_in_scan = 1; q.scan_info[0].Ss = 0; q.scan_info[0].Se = 63
     assert lib.b200jpeg_validate(C.byref(q)) == A.ERR_PARAM and b"transmit" in lib.b200jpeg_last_error()   # JERR_MISSING_DATA
