@@ -2,6 +2,7 @@
 // Compile with: -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
 #include "kernels.cuh"
 #include <cuda_fp16.h>
+#include <cuda.h>           // CUtensorMap (the encode function itself is fetched through the runtime, no libcuda link)
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -315,7 +316,7 @@ __device__ __forceinline__ Px8 load_px8(const uint8_t *__restrict__ base, size_t
 template <int IC, int SB>
 __device__ __forceinline__ int px_sample(const Px8 &r, int px, int ch)
 {
-  if (SB == 1) { int b = px * IC + ch; return (int)((r.w[b >> 2] >> (8 * (b & 3))) & 0xFFu); }
+  if (SB == 1) { int b = px * IC + ch; return (int)__byte_perm(r.w[b >> 2], 0u, 0x4440 | (b & 3)); }   // byte b of the packed row (one PRMT)
   int h = px * IC + ch; return (int)((r.w[h >> 1] >> (16 * (h & 1))) & 0xFFFu);
 }
 
@@ -411,7 +412,8 @@ __constant__ double c_aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0,
 template <int HMAX, int VMAX, int NC, bool QFAST, int PREC, int DCTM>
 __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, const uint8_t *__restrict__ src,
                                                       const QuantTables *__restrict__ qt, int dering,
-                                                      DcRec *__restrict__ rec, RecLayout rl, int write_raw)
+                                                      DcRec *__restrict__ rec, RecLayout rl, int write_raw,
+                                                      const __grid_constant__ CUtensorMap tmap, const int use_tma)
 {
   constexpr int TW = 128, TR = 8 * VMAX;
   constexpr int YBW = TW / 8, YB = YBW * VMAX;           // luma blocks in the tile
@@ -426,7 +428,8 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
   __shared__ __align__(16) int16_t sY[TR * YP];
   __shared__ __align__(16) int16_t sC[NC == 3 ? 2 * 8 * CP : 8];
   __shared__ __align__(16) wtype sW[NB * 72];
-  __shared__ __align__(16) unsigned char sIO[NB * 256];   // phases D/E: output staging
+  __shared__ __align__(128) unsigned char sIO[NB * 256];  // phase A: the tile's pixels as the TMA delivers them; phases D/E: output staging
+  __shared__ __align__(8) unsigned long long tma_bar;
   __shared__ uint2 sQC[NC][64];                           // quantizer constants per component, natural order
   __shared__ uint2 sMask[NB];                             // per block: zigzag positions of its non-zero AC values
   __shared__ int sQL[NC];
@@ -439,11 +442,53 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
   for (int i = tid; i < NC * 64; i += 128) { int ci = i >> 6, n = i & 63; const QuantConst &k = qt->q[g.c[ci].qt][n]; sQC[ci][n] = make_uint2(k.mul2, k.bias << 14); }
   if (tid < NC) sQL[tid] = qt->L[g.c[tid].qt];
 
-  // ---- A+B: thread (row group rg, segment seg) converts VMAX rows x 8 pixels straight from global memory:
-  //      colour conversion (jccolext.c:30-75) + box downsampling (jcsample.c) into centred int16 planes ----
+  // ---- A0: interior tiles of 8-bit RGB / gray input arrive by TMA: one thread posts the tile's box(es) of the
+  //      (bytes per row, rows, images) tensor map -- 128 pixels x TR rows, 192-byte boxes because a box dimension is
+  //      capped at 256 elements -- and everybody waits on the mbarrier the copies complete on.  Edge tiles (pixel
+  //      replication) and unaligned inputs keep the per-thread global loads. ----
+  constexpr int TMA_BOXW = IC == 3 ? 192 : 128, TMA_NBOX = IC == 3 ? 2 : 1;
+  static_assert(TMA_NBOX * TMA_BOXW * TR <= NB * 256, "the pixel tile fits the staging buffer it borrows");
+  const bool tma_tile = PREC == 8 && use_tma && x0 + TW <= g.W && y0 + TR <= g.H;
+  if (tma_tile) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((unsigned)(TMA_NBOX * TMA_BOXW * TR)) : "memory");
+#pragma unroll
+      for (int bx = 0; bx < TMA_NBOX; bx++)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     :: "r"((unsigned)__cvta_generic_to_shared(sIO + bx * TMA_BOXW * TR)), "l"(reinterpret_cast<unsigned long long>(&tmap)),
+                        "r"(x0 * IC + bx * TMA_BOXW), "r"(y0), "r"(img), "r"(bar) : "memory");
+    }
+    __syncthreads();                                             // the barrier word is initialised before anyone polls it
+    {
+      unsigned done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+    }
+  }
+
+  // ---- A+B: thread (row group rg, segment seg) converts VMAX rows x 8 pixels (from the TMA tile or straight from
+  //      global memory): colour conversion (jccolext.c:30-75) + box downsampling (jcsample.c) into centred int16 planes ----
   {
     const int rg = tid >> 4, seg = tid & 15;
     const int xs = x0 + seg * 8;
+    // this thread's 8 pixels of tile row `trow` out of the TMA tile
+    auto tma_px8 = [&](int trow) {
+      Px8 r;
+#pragma unroll
+      for (int i = 0; i < 12; i++) r.w[i] = 0;
+      if (IC == 3) {
+        const uint2 *q = reinterpret_cast<const uint2 *>(sIO + (seg >> 3) * (TMA_BOXW * TR) + trow * TMA_BOXW + (seg & 7) * 24);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { const uint2 a = q[i]; r.w[2 * i] = a.x; r.w[2 * i + 1] = a.y; }
+      } else {
+        const uint2 a = *reinterpret_cast<const uint2 *>(sIO + trow * TMA_BOXW + seg * 8);
+        r.w[0] = a.x; r.w[1] = a.y;
+      }
+      return r;
+    };
     if (g.raw_in) {
       // raw-data input: the planes are already converted and downsampled; only centre them (convsamp).  Samples past
       // the component's last real block are never used (those blocks are skipped on output), so they read as 0.
@@ -515,7 +560,7 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
 #pragma unroll
       for (int rr = 0; rr < VMAX; rr++) {
         const int iy = min(y0 + rg * VMAX + rr, g.H - 1);
-        Px8 p = load_px8<IC, SB>(base, g.row_pitch, iy, xs, g.W, fast, EXT && px4, EXT ? pfirst : 0);
+        Px8 p = (!EXT && tma_tile) ? tma_px8(rg * VMAX + rr) : load_px8<IC, SB>(base, g.row_pitch, iy, xs, g.W, fast, EXT && px4, EXT ? pfirst : 0);
         int16_t yv[8];
 #pragma unroll
         for (int px = 0; px < 8; px++) {
@@ -528,7 +573,7 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
         }
         *reinterpret_cast<uint4 *>(&sY[(rg * VMAX + rr) * YP + seg * 8]) = *reinterpret_cast<const uint4 *>(yv);
         if (NC == 3) {
-          if (er != rg) p = load_px8<IC, SB>(base, g.row_pitch, min(y0 + er * VMAX + rr, g.H - 1), xs, g.W, fast, EXT && px4, EXT ? pfirst : 0);
+          if (er != rg) p = (!EXT && tma_tile) ? tma_px8(er * VMAX + rr) : load_px8<IC, SB>(base, g.row_pitch, min(y0 + er * VMAX + rr, g.H - 1), xs, g.W, fast, EXT && px4, EXT ? pfirst : 0);
 #pragma unroll
           for (int px = 0; px < 8; px++) {
             const int S0 = px_sample<3, SB>(p, px, 0), G = px_sample<3, SB>(p, px, 1), S2 = px_sample<3, SB>(p, px, 2);
@@ -626,26 +671,29 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
   }
   __syncthreads();
 
-  // ---- D: column pass + quantize; lane j owns column j; zigzag placement in the staging buffer.
+  // ---- D: column pass + quantize; lane j owns column jc; zigzag placement in the staging buffer.
+  //      The four blocks a warp works on own their columns in rotated order (jc), so that their simultaneous 2-byte
+  //      stores into the dense 128-byte staging blocks fall into different banks (they were 4-way conflicts).
   //      With the trellis on, the 8 lanes also OR together the zigzag positions of the block's
   //      non-zero plain-quantized AC values for the side record (the trellis kernel finds its
   //      entries from that mask). ----
   int16_t *sQ = reinterpret_cast<int16_t *>(sIO);              // [NB][64] quantized, then [NB][64] raw
   int16_t *sR = sQ + NB * 64;
   static_assert(NB % 16 == 0, "whole warps walk the block list in step");
-  // zigzag positions of this lane's 8 coefficients (natural index 8r + j)
+  const int jc = (j + 2 * ((tid >> 3) & 3)) & 7;
+  // zigzag positions of this lane's 8 coefficients (natural index 8r + jc)
   int kz[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) {
 #if FWD_KZ_PACKED
-    kz[r] = (int)((c_izz_col[j] >> (8 * r)) & 63);
+    kz[r] = (int)((c_izz_col[jc] >> (8 * r)) & 63);
 #else
-    kz[r] = c_izz[8 * r + j];
+    kz[r] = c_izz[8 * r + jc];
 #endif
   }
 #pragma unroll 1
   for (int b = tid >> 3; b < NB; b += 16) {
-    const wtype *w = sW + b * 72 + j;
+    const wtype *w = sW + b * 72 + jc;
     const int ci = b < YB ? 0 : (1 + (b - YB) / CBW);
     int dd[8], qf[8];                                             // raw coefficients (integers) of this lane's column / float-path quantized values
     if (DCTM == 2) {
@@ -659,12 +707,12 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
         dd[r] = 0;
         if (write_raw) {
           float v = ff[r];
-          v = (float)((double)v / c_aan[j]);                      // i % 8 = column
+          v = (float)((double)v / c_aan[jc]);                     // i % 8 = column
           v = (float)((double)v / c_aan[r]);                      // i / 8 = row
           dd[r] = (v >= 0.0f) ? (int)((double)v + 0.5) : (int)((double)v - 0.5);
         }
         // ... and quantize_float :808-827
-        const float temp = ff[r] * fd[8 * r + j];
+        const float temp = ff[r] * fd[8 * r + jc];
         int q = (int)(int16_t)(__float2int_rz(temp + 16384.5f) - 16384);
         if (dering) q = max(-1023, min(1023, q));
         qf[r] = q;
@@ -676,7 +724,7 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
       const IfastConst *ic = qt->ifast[g.c[ci].qt];
 #pragma unroll
       for (int r = 0; r < 8; r++) {
-        const int nat = 8 * r + j;
+        const int nat = 8 * r + jc;
         // raw coefficient for the trellis, rescaled as forward_DCT does (jcdctmgr.c:729-746) ...
         dd[r] = 0;
         if (write_raw) { const int x = ws8[r], sc = c_aanscales[nat]; dd[r] = (x >= 0) ? (x * 32768 + sc) / (2 * sc) : (x * 32768 - sc) / (2 * sc); }
@@ -697,7 +745,7 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
     unsigned mlo = 0, mhi = 0;                                 // zigzag positions of this lane's non-zero AC values
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      const int nat = 8 * r + j;
+      const int nat = 8 * r + jc;
       const int k = kz[r];
       int qv;
       if (DCTM != 0) qv = qf[r];
@@ -718,7 +766,7 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
       // phase D2; the 8 lanes OR their non-zero masks together
       if (DCTM == 2) __syncwarp();                             // every lane has read its float column before the int16 view reuses the words
       int16_t *blk16 = reinterpret_cast<int16_t *>(sW + b * 72);     // the block's own words (also when sW holds floats)
-      int16_t *ww = blk16 + j;
+      int16_t *ww = blk16 + jc;
 #pragma unroll
       for (int r = 0; r < 8; r++) ww[8 * r] = (int16_t)dd[r];
       if (FWD_MASK_SQ && DCTM == 0) {
@@ -744,6 +792,7 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
       }
     }
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the bulk copies of phase E
   __syncthreads();
 
   // ---- D2: trellis side records, one thread per block: the serial fp32 sum of squares in NATURAL order
@@ -758,14 +807,21 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
       if (row >= c.hib || col >= c.wib) continue;
       const int4 *rows = reinterpret_cast<const int4 *>(reinterpret_cast<const int16_t *>(sW + b * 72));
       float norm = 0.0f; int raw_dc = 0;
+      // (float)(v * v) without the conversion unit: v as an exact float by the exponent trick, squared in fp32 -- the
+      // product of two 16-bit integers rounds to the same float as the converted integer square; two values per
+      // packed fp32x2 operation, the sum itself stays the reference's serial chain
+      const float2 bias = make_float2(-8421376.0f, -8421376.0f);   // -(2^23 + 2^15)
 #pragma unroll
       for (int r = 0; r < 8; r++) {
         const int4 rv = rows[r];
-        const int pw[4] = {rv.x, rv.y, rv.z, rv.w};
+        const unsigned pw[4] = {(unsigned)rv.x, (unsigned)rv.y, (unsigned)rv.z, (unsigned)rv.w};
 #pragma unroll
-        for (int cidx = 0; cidx < 8; cidx++) {
-          const int v = (int)(int16_t)((unsigned)pw[cidx >> 1] >> ((cidx & 1) * 16));
-          if (r == 0 && cidx == 0) raw_dc = v; else norm += (float)(v * v);
+        for (int cp = 0; cp < 4; cp++) {
+          const unsigned u = pw[cp] ^ 0x80008000u;
+          float2 f = make_float2(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7632)));
+          f = __fadd2_rn(f, bias); f = __fmul2_rn(f, f);
+          if (r == 0 && cp == 0) raw_dc = (int)(int16_t)(pw[0] & 0xFFFFu); else norm += f.x;
+          norm += f.y;
         }
       }
       const uint2 mk = sMask[b];
@@ -775,29 +831,74 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
     }
   }
 
-  // ---- E: whole blocks out, 16 bytes per thread-store ----
-  for (int i = tid; i < NB * 8; i += 128) {
-    int b = i >> 3, v = i & 7;
-    int ci, row, col;
-    if (b < YB) { ci = 0; int byl = b / YBW; row = ty * VMAX + byl; col = tx * YBW + (b - byl * YBW); }
-    else { int cb = b - YB; int which = cb / CBW; ci = 1 + which; row = ty; col = tx * CBW + (cb - which * CBW); }
-    const CompGeom &c = g.c[ci];
-    if (row >= c.hib || col >= c.wib) continue;
-    size_t blk = ((size_t)img * c.hpad + row) * c.wpad + col;
-    reinterpret_cast<uint4 *>(c.coef + blk * 64)[v] = reinterpret_cast<const uint4 *>(sQ + b * 64)[v];
-    if (write_raw) reinterpret_cast<uint4 *>(c.raw + blk * 64)[v] = reinterpret_cast<const uint4 *>(sR + b * 64)[v];   // only the trellis (and the debug tap) read the raw DCT
+  // ---- E: whole blocks out.  The blocks of one component's block row inside the tile are consecutive both in the
+  //      staging buffer and in the coefficient plane (128 bytes each), so each such run leaves as ONE asynchronous
+  //      bulk copy shared -> global (cp.async.bulk, the TMA engine), issued by one thread per run; the threads' own
+  //      shared-memory writes were ordered before the async proxy by the fence in front of the barrier above ----
+  {
+    constexpr int NRUN = VMAX + (NC == 3 ? 2 : 0);
+    if (tid < NRUN) {
+      int ci, row, col0, b0, maxblk;
+      if (tid < VMAX) { ci = 0; row = ty * VMAX + tid; col0 = tx * YBW; b0 = tid * YBW; maxblk = YBW; }
+      else { const int which = tid - VMAX; ci = 1 + which; row = ty; col0 = tx * CBW; b0 = YB + which * CBW; maxblk = CBW; }
+      const CompGeom &c = g.c[ci];
+      const int cnt = row < c.hib ? max(0, min(maxblk, c.wib - col0)) : 0;
+      if (cnt > 0) {
+        const size_t blk = ((size_t)img * c.hpad + row) * c.wpad + col0;
+        const unsigned bytes = (unsigned)cnt * 128u;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(c.coef + blk * 64), "r"((unsigned)__cvta_generic_to_shared(sQ + b0 * 64)), "r"(bytes) : "memory");
+        if (write_raw)                                           // only the trellis (and the debug tap) read the raw DCT
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       :: "l"(c.raw + blk * 64), "r"((unsigned)__cvta_generic_to_shared(sR + b0 * 64)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the staging buffer must outlive the reads
+      }
+    }
   }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder()
+{
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// The batch's pixels as a rank-3 byte tensor {W * samples per pixel, H, n}; box = one tile (or half of one) of the
+// forward kernel.  Returns 0 when the layout does not qualify (alignment, pixel order, sample size): the kernel
+// then loads with ordinary global loads.
+static int make_pixel_tensor_map(const Geom &g, const uint8_t *src, int n, int ic, int tile_rows, CUtensorMap *tm)
+{
+  static const bool off = getenv("B200JPEG_NO_TMA") != nullptr;     // A/B aid
+  memset(tm, 0, sizeof *tm);
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (off || !enc || g.raw_in || !src || g.in_comps != ic || g.px_swap || g.px_first || g.max_coef_bits != 10) return 0;
+  if (((size_t)src & 15) || (g.row_pitch & 15) || (n > 1 && (g.image_stride & 15))) return 0;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.W * ic, (cuuint64_t)g.H, (cuuint64_t)n};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.row_pitch, (cuuint64_t)(n > 1 ? g.image_stride : ((g.row_pitch * (size_t)g.H + 15) & ~(size_t)15))};
+  const cuuint32_t box[3] = {(cuuint32_t)(ic == 3 ? 192 : 128), (cuuint32_t)tile_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <bool QFAST, int PREC, int DCTM>
 static void launch_forward_tile(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s, bool gray, int write_raw)
 {
   dim3 grid((g.W + 127) / 128, g.mcu_rows, n);
-  if (gray) k_forward_tile<1, 1, 1, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
-  else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
-  else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
-  else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
-  else k_forward_tile<2, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw);
+  CUtensorMap tm;
+  const int use_tma = PREC == 8 ? make_pixel_tensor_map(g, src, n, gray ? 1 : 3, 8 * (gray ? 1 : g.vmax), &tm) : (memset(&tm, 0, sizeof tm), 0);
+  if (gray) k_forward_tile<1, 1, 1, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma);
+  else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma);
+  else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma);
+  else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma);
+  else k_forward_tile<2, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma);
 }
 // =====================================================================
 // Input smoothing (cinfo->smoothing_factor, cjpeg -smooth N).  The smoothing downsamplers (jcsample.c:298-455) read a
@@ -3312,19 +3413,21 @@ __global__ void __launch_bounds__(STUFF_THREADS) k_stuff_write(const uint32_t *_
 #define AUX_BRK 1u
 #define AUX_CONTRIB 2u
 
-__device__ __forceinline__ void load_block64(const int16_t *__restrict__ blk, int *v)
+// the block's coefficients of the band [Ss, Se] (zigzag positions; the other entries read as 0): only the 16-byte
+// pieces of the 128-byte block that the band touches are fetched -- a 1..8 scan moves one 32-byte sector per block
+__device__ __forceinline__ void load_block64(const int16_t *__restrict__ blk, int *v, int Ss = 0, int Se = 63)
 {
   const uint4 *b4 = reinterpret_cast<const uint4 *>(blk);
 #pragma unroll
   for (int q = 0; q < 8; q++) {
-    uint4 a = b4[q]; unsigned w[4] = {a.x, a.y, a.z, a.w};
+    uint4 a = make_uint4(0, 0, 0, 0);
+    if (8 * q + 7 >= Ss && 8 * q <= Se) a = b4[q];
+    unsigned w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
     for (int j = 0; j < 8; j++) v[8 * q + j] = (int)(int16_t)((w[j >> 1] >> ((j & 1) * 16)) & 0xFFFF);
   }
 }
 
-// A block is a run BOUNDARY if it breaks the pending EOBRUN (AUX_BRK), or opens the scan or a restart segment.
-// tile_last / tile_first[img][tile]: largest / smallest boundary index inside the tile (-1 / INT_MAX if none).
 __global__ void __launch_bounds__(256) k_prog_flags(Geom g, ScanDesc sd, uint32_t *__restrict__ aux, uint32_t *__restrict__ run_e,
                                                     int *__restrict__ tile_last, int *__restrict__ tile_first)
 {
@@ -3337,7 +3440,7 @@ __global__ void __launch_bounds__(256) k_prog_flags(Geom g, ScanDesc sd, uint32_
     int sci, k; long long mcu;
     const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
     int v[64];
-    load_block64(blk, v);
+    load_block64(blk, v, sd.Ss, sd.Se);
     unsigned brk = 0, contrib, tail = 0;
     if (sd.Ah == 0) {
       int lastnz = 0;
@@ -3483,7 +3586,13 @@ __device__ __forceinline__ void walk_prog_block(const int16_t *__restrict__ blk,
     return;
   }
   int v[64];
-  load_block64(blk, v);
+  // blocks without anything to say in this scan (no band value in a first scan; no newly non-zero value and no
+  // correction bit in a refinement scan) are not fetched at all
+  if ((aux & AUX_BRK) || (sd.Ah != 0 && (aux >> 2) != 0)) load_block64(blk, v, sd.Ss, sd.Se);
+  else {
+#pragma unroll
+    for (int i = 0; i < 64; i++) v[i] = 0;
+  }
   if (sd.Ah == 0) {                                      // encode_mcu_AC_first :648-737
     if (aux & AUX_BRK) {
       int r = 0;
