@@ -601,6 +601,8 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   //      scans are coded (the reference codes them one by one into memory buffers, jcmaster.c:668-674); the two
   //      frequency-split groups are coded at each image's best Al, chosen on the device in between. ----
   int *best_al = A.d_best_al.as<int>();                       // [2][n]: luma, chroma
+  // sequential scans after the trellis: the side records hold every block's final non-zero positions
+  const DcRec *nz_rec = (pl.trellis && !pl.progressive) ? A.d_rec.as<DcRec>() : nullptr;
   for (size_t j = 0; j < pl.order.size(); j++) {
     const int si = pl.order[j];
     ScanDesc sd = pl.scans[si];
@@ -633,7 +635,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
         tm.mark("scan_stats");
         CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
         if (pl.progressive) launch_gather_prog(g, sd, aux, run_e, A.d_hist.as<uint32_t>(), status, n, s);
-        else launch_gather_seq(g, sd, A.d_hist.as<uint32_t>(), status, n, s);
+        else launch_gather_seq(g, sd, nz_rec, rl, A.d_hist.as<uint32_t>(), status, n, s);
         tm.mark("scan_tables");
         SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = scan_slot_mask(pl, sd);
         launch_gen_tables(A.d_hist.as<uint32_t>(), tset, tstride, masks, n, s);
@@ -642,7 +644,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     } else { tabs = e->d_tabs_fixed.as<DevHuff>(); tstride = 0; }
     const size_t mark_words = (e->bitbuf_words_per_image * 4 / 8 + 64) / 4;
     tm.mark("block_bits");
-    launch_block_bits(g, sd, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), aux, run_e, status, n, s);
+    launch_block_bits(g, sd, nz_rec, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), aux, run_e, status, n, s);
     tm.mark("scan_layout");
     launch_scan_layout(sd, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
                        A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, A.d_total_bits.as<unsigned long long>(),
@@ -650,7 +652,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     tm.mark("encode");
     CU(cudaMemsetAsync(A.d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
     if (sd.ri) CU(cudaMemsetAsync(A.d_mark.p, 0, mark_words * 4 * n, s));
-    launch_encode(g, sd, (pl.trellis && !pl.progressive) ? A.d_rec.as<DcRec>() : nullptr, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
+    launch_encode(g, sd, nz_rec, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
                   A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, aux, run_e,
                   A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_mark.as<uint32_t>(), mark_words, status, n, s);
     tm.mark("stuff");

@@ -1118,6 +1118,11 @@ __device__ __forceinline__ void walk_seq_block(const int16_t *__restrict__ blk, 
 #ifndef SEQ_SPARSE_ENC
 #define SEQ_SPARSE_ENC 1
 #endif
+// the same sparse walk in the statistics and bit-count kernels: measured slower than the dense 16-byte loads there
+// (0.61 / 0.62 vs 0.53 / 0.57 ms per 64 4K images), so off
+#ifndef SEQ_SPARSE_STATS
+#define SEQ_SPARSE_STATS 0
+#endif
 // Zigzag positions of a scan-order block's non-zero AC coefficients, from the side records (the AC trellis leaves the
 // final ones there); dummy blocks have none.
 __device__ __forceinline__ unsigned long long block_nzmask(const Geom &g, const ScanDesc &sd, const DcRec *__restrict__ rec, const RecLayout &rl,
@@ -1172,7 +1177,9 @@ struct HistSink {
   __device__ void ac(int sym, int nb, int) { if (nb > maxbits) bad = 1; hist_inc(&ac_hist[sym]); }
 };
 
-__global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
+// nz_rec: the side records holding every block's final non-zero positions (after the AC trellis), or nullptr: the walk
+// then touches only those coefficients (and the 32-byte sectors they sit in) instead of the whole 128-byte block
+__global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ nz_rec, RecLayout rl, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
 {
   __shared__ unsigned sh[HIST_SLOTS * HIST_BINS];
   int img = blockIdx.y;
@@ -1185,7 +1192,8 @@ __global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, uint32_
     int last = prev_dc(g, sd, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
     HistSink sink{sh + c.dc_tbl * HIST_BINS, sh + (4 + c.ac_tbl) * HIST_BINS, 0, g.max_coef_bits};
-    walk_seq_block(blk, last, sink);
+    if (SEQ_SPARSE_STATS && nz_rec) walk_seq_sparse(blk, block_nzmask(g, sd, nz_rec, rl, img, sci, mcu, k), last, sink);
+    else walk_seq_block(blk, last, sink);
     if (sink.bad) atomicOr(&status[img], 2u);          // JERR_BAD_DCT_COEF
   }
   __syncthreads();
@@ -1232,10 +1240,10 @@ void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, ui
   LAUNCHED();
 }
 
-void launch_gather_seq(const Geom &g, const ScanDesc &sd, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
+void launch_gather_seq(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  k_gather_seq<<<grid, 256, 0, s>>>(g, sd, hist, status);
+  k_gather_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, rl, hist, status);
   LAUNCHED();
 }
 
@@ -3132,7 +3140,7 @@ __device__ __forceinline__ unsigned cta_excl_scan_256(unsigned v, unsigned *ws /
 
 // One tile = the 256 blocks of one CTA; tile_bits[img][tile] = bits the tile emits; blk_bits[img][t] = bits
 // the tile's blocks before t emit (exclusive prefix inside the tile).
-__global__ void __launch_bounds__(256) k_block_bits_seq(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
+__global__ void __launch_bounds__(256) k_block_bits_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ nz_rec, RecLayout rl, const DevHuff *__restrict__ tabs, size_t stride,
                                                         uint32_t *__restrict__ blk_bits, uint32_t *__restrict__ tile_bits, uint32_t *__restrict__ status)
 {
   __shared__ ScanTables st;
@@ -3148,7 +3156,8 @@ __global__ void __launch_bounds__(256) k_block_bits_seq(Geom g, ScanDesc sd, con
     int last = prev_dc(g, sd, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
     CountSink sink{st.size[c.dc_tbl], st.size[4 + c.ac_tbl], 0u, 0};
-    walk_seq_block(blk, last, sink);
+    if (SEQ_SPARSE_STATS && nz_rec) walk_seq_sparse(blk, block_nzmask(g, sd, nz_rec, rl, img, sci, mcu, k), last, sink);
+    else walk_seq_block(blk, last, sink);
     if (sink.bad) atomicOr(&status[img], 2u);
     bits = sink.bits;
   }
@@ -3827,12 +3836,12 @@ void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, 
   k_gather_prog<<<grid, 256, 0, s>>>(g, sd, aux, run_e, hist, status); LAUNCHED();
 }
 
-void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t stride, int progressive,
+void launch_block_bits(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t stride, int progressive,
                        uint32_t *blk_bits, uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
   if (progressive) k_block_bits_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, tile_bits, status);
-  else k_block_bits_seq<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_bits, tile_bits, status);
+  else k_block_bits_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, rl, tabs, stride, blk_bits, tile_bits, status);
   LAUNCHED();
 }
 void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint32_t *tile_bits, unsigned long long *tile_base,

@@ -117,7 +117,9 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
 void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, uint32_t *splits /* [n*nc][2] */, int n, cudaStream_t s);
 void launch_dummy(const Geom &g, int n, cudaStream_t s);
 void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
-void launch_gather_seq(const Geom &g, const ScanDesc &sd, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
+// nz_rec (here and in launch_block_bits / launch_encode): the side records holding every block's final non-zero positions
+// (trellis on, sequential scans), or nullptr
+void launch_gather_seq(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s);
 void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_set_stride, const SlotMasks &masks, int nsets, cudaStream_t s);
 void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
@@ -142,7 +144,7 @@ void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *ta
 // tile_last / tile_first: int [n][ceil(nblocks/256)] scratch
 void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int *tile_last, int *tile_first, int n, cudaStream_t s);
 void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
-void launch_block_bits(const Geom &g, const ScanDesc &sd, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
+void launch_block_bits(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
                        uint32_t *blk_bits, uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *status, int n, cudaStream_t s);
 // tile_base[img][tile] / seg_corr[img][segment] / total_bits[img] from the tile sums (and the restart interval)
 void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint32_t *tile_bits, unsigned long long *tile_base,
