@@ -69,12 +69,32 @@ typedef void (*finish_fn)(j_compress_ptr);
 typedef void (*abort_fn)(j_compress_ptr);
 typedef void (*marker_fn)(j_compress_ptr, int, const JOCTET *, unsigned int);
 
+#ifdef B200_SHIM_STANDALONE
+/* Standalone libjpeg.so.62 (integration/Makefile): the reference's unmodified objects are linked into the same library
+ * with the entry points this file takes over renamed b200ref_<name> (objcopy --redefine-sym), so "the reference's
+ * implementation" is a direct symbol instead of the next library in the search order. */
+#define B200REF(n) extern void b200ref_##n(void);
+B200REF(jpeg_start_compress) B200REF(jpeg_write_scanlines) B200REF(jpeg12_write_scanlines) B200REF(jpeg_write_raw_data)
+B200REF(jpeg_write_coefficients) B200REF(jpeg_finish_compress) B200REF(jpeg_abort_compress) B200REF(jpeg_destroy_compress)
+B200REF(jpeg_abort) B200REF(jpeg_destroy) B200REF(jpeg_write_marker) B200REF(jpeg_write_m_header) B200REF(jpeg_write_m_byte)
+#undef B200REF
+static void *next_sym(const char *name)
+{
+#define B200REF(n) if (!strcmp(name, #n)) return (void *)b200ref_##n;
+  B200REF(jpeg_start_compress) B200REF(jpeg_write_scanlines) B200REF(jpeg12_write_scanlines) B200REF(jpeg_write_raw_data)
+  B200REF(jpeg_write_coefficients) B200REF(jpeg_finish_compress) B200REF(jpeg_abort_compress) B200REF(jpeg_destroy_compress)
+  B200REF(jpeg_abort) B200REF(jpeg_destroy) B200REF(jpeg_write_marker) B200REF(jpeg_write_m_header) B200REF(jpeg_write_m_byte)
+#undef B200REF
+  fprintf(stderr, "b200 libjpeg: no reference implementation of %s in this library\n", name); abort();
+}
+#else
 static void *next_sym(const char *name)
 {
   void *p = dlsym(RTLD_NEXT, name);
   if (!p) { fprintf(stderr, "b200 shim: the reference's %s is not behind this library\n", name); abort(); }
   return p;
 }
+#endif
 
 static int find_active(j_compress_ptr cinfo)
 {

@@ -109,6 +109,7 @@ struct b200jpeg_encoder {
   size_t bitbuf_words_per_image = 0, out_cap_per_image = 0;
   double cap_factor = 0.25;      // entropy-coded bytes the buffers hold per coefficient; grows on overflow, falls back after calm batches
   int calm_batches = 0;
+  size_t max_image_scan_bytes = 0;   // largest entropy-coded size of one image in the last host-visible batch
   // pinned host mirrors
   PinBuf h_qt, h_tc, h_fixed, h_status, h_out_pos, h_scan_size, h_tabs, h_stage, h_best_al, h_qinit, h_qimg;
   // finished files: bump-allocated from pinned arenas, valid until the next encode call
@@ -1022,6 +1023,7 @@ static int finish_chunk(b200jpeg_encoder *e, const ChunkIO &io, int k)
     f[w++] = 0xFF; f[w++] = 0xD9;
     e->files[gi] = std::make_pair(f, w);
     e->last_scan_bytes += scan_bytes;
+    e->max_image_scan_bytes = std::max(e->max_image_scan_bytes, scan_bytes);
     e->last_file_bytes += w;
   }
   return B200JPEG_OK;
@@ -1117,7 +1119,14 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   Timer tm{e};
   const int nstreams = (nchunks > 1 && e->n_streams > 1) ? 2 : 1;
   e->sc[0] = e->stream;
-  if (e->calm_batches >= 2) e->cap_factor = 0.25;          // one incompressible batch does not enlarge the buffers for good
+  // one incompressible batch does not enlarge the buffers for good: after two batches without growth whose largest
+  // image would have fitted the initial size eight times over, fall back to it (batches that keep needing the room,
+  // e.g. 12-bit noise at 15 MB per image, keep it; device-only runs never shrink: their sizes are not read back)
+  {
+    long long tb = 0; for (int ci = 0; ci < pl.g.nc; ci++) tb += pl.g.c[ci].blocks_per_image;
+    if (e->calm_batches >= 2 && !device_only && e->cap_factor > 0.25 && e->max_image_scan_bytes * 8 < (size_t)((double)tb * 64 * 0.25)) e->cap_factor = 0.25;
+    if (!device_only) e->max_image_scan_bytes = 0;
+  }
   bool grew = false;
   for (int attempt = 0; attempt < 6; attempt++) {
     tm.idx = 0;

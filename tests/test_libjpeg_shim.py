@@ -177,3 +177,62 @@ def test_reference_cjpeg_12bit_runs_on_the_device(sw, tmp_path):
     assert "device path" in r.stderr, r.stderr
     plain = subprocess.run([CJPEG, *sw, str(ppm)], capture_output=True, timeout=300)
     assert plain.returncode == 0 and out.read_bytes() == plain.stdout
+
+
+# ---------------------------------------------------------------------------
+# The standalone drop-in: integration/_build/libjpeg.so.62 is a complete libjpeg (API v6.2) -- the reference's own
+# objects plus the shim, the 13 taken-over entry points of the reference renamed inside (integration/Makefile) -- that an
+# application links or loads like the stock library; cjpeg_b200 is the reference's cjpeg front end linked against it.
+# ---------------------------------------------------------------------------
+STD_LIB = os.path.join(ROOT, "integration", "_build", "libjpeg.so.62")
+STD_CJPEG = os.path.join(ROOT, "integration", "_build", "cjpeg_b200")
+need_std = pytest.mark.skipif(not (os.path.exists(STD_LIB) and os.path.exists(STD_CJPEG) and os.path.exists(CJPEG)),
+                              reason="standalone libjpeg.so.62 not built (needs /root/reference at build time)")
+
+
+@need_std
+def test_standalone_libjpeg_exports_the_v62_api():
+    """SURVEY 8(b) "must export" list, with the reference's symbol versions (libjpeg.map.in)."""
+    out = subprocess.check_output(["nm", "-D", "--defined-only", STD_LIB], text=True)
+    have = {}
+    for ln in out.splitlines():
+        f = ln.split()
+        if len(f) == 3 and f[1] == "T":
+            name, _, ver = f[2].partition("@@")
+            have[name] = ver
+    want = ["jpeg_std_error", "jpeg_CreateCompress", "jpeg_destroy_compress", "jpeg_abort_compress", "jpeg_stdio_dest", "jpeg_mem_dest",
+            "jpeg_set_defaults", "jpeg_set_colorspace", "jpeg_default_colorspace", "jpeg_set_quality", "jpeg_set_linear_quality",
+            "jpeg_add_quant_table", "jpeg_quality_scaling", "jpeg_float_quality_scaling", "jpeg_simple_progression", "jpeg_suppress_tables",
+            "jpeg_alloc_quant_table", "jpeg_alloc_huff_table", "jpeg_start_compress", "jpeg_write_scanlines", "jpeg12_write_scanlines",
+            "jpeg_write_raw_data", "jpeg_finish_compress", "jpeg_write_marker", "jpeg_write_m_header", "jpeg_write_m_byte", "jpeg_write_tables",
+            "jpeg_write_coefficients", "jpeg_c_bool_param_supported", "jpeg_c_set_bool_param", "jpeg_c_get_bool_param", "jpeg_c_int_param_supported",
+            "jpeg_c_set_int_param", "jpeg_c_get_int_param", "jpeg_c_float_param_supported", "jpeg_c_set_float_param", "jpeg_c_get_float_param",
+            "jpeg_CreateDecompress", "jpeg_read_header", "jpeg_read_coefficients"]
+    missing = [w for w in want if w not in have]
+    assert not missing, missing
+    assert have["jpeg_start_compress"] == "LIBJPEG_6.2" and have["jpeg_mem_dest"] == "LIBJPEGTURBO_6.2"
+    assert not [n for n in have if n.startswith("b200ref_")]              # the renamed reference entry points stay internal
+    soname = subprocess.check_output(["readelf", "-d", STD_LIB], text=True)
+    assert "libjpeg.so.62" in soname
+
+
+@need_std
+def test_standalone_libjpeg_without_a_device_is_the_reference():
+    """No LD_PRELOAD, no GPU: the library hands the object to the reference code it carries (same bytes as the reference)."""
+    env = dict(os.environ, MOZ_B200_FORCE_CPU="1")
+    sw = ["-quality", "75", "-fastcrush"]
+    a = subprocess.run([STD_CJPEG, *sw, PPM], env=env, capture_output=True, timeout=300)
+    b = subprocess.run([CJPEG, *sw, PPM], capture_output=True, timeout=300)
+    assert a.returncode == 0 and b.returncode == 0 and a.stdout == b.stdout and len(a.stdout) > 1000
+
+
+@need_std
+@pytest.mark.gpu
+@pytest.mark.parametrize("sw", DEVICE_SETS[:4] + [["-quality", "75"]], ids=lambda s: "_".join(x.lstrip("-") for x in s))
+def test_standalone_libjpeg_encodes_on_the_device(sw):
+    env = dict(os.environ, B200_SHIM_REQUIRE="1", B200_SHIM_VERBOSE="1")
+    a = subprocess.run([STD_CJPEG, *sw, PPM], env=env, capture_output=True, timeout=300)
+    assert a.returncode == 0, a.stderr
+    assert b"device path" in a.stderr, a.stderr
+    b = subprocess.run([CJPEG, *sw, PPM], capture_output=True, timeout=300)
+    assert b.returncode == 0 and a.stdout == b.stdout
