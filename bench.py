@@ -164,30 +164,40 @@ def cpu_reference_run(images, switches, threads, reps):
     return mp / dt, ("reference" if use_ref else "port"), dt
 
 
-def simd_proxy_run(images, threads, reps):
+_PROXY_IMAGES = None
+
+
+def _simd_proxy_worker(args):
+    import io
+    from PIL import Image
+    t, reps = args
+    pil = [Image.fromarray(im) for im in _PROXY_IMAGES]
+    for r in range(reps):
+        buf = io.BytesIO()
+        pil[(t + r) % len(pil)].save(buf, format="JPEG", quality=75, subsampling=2, optimize=False)
+    return reps
+
+
+def simd_proxy_run(images, procs, reps):
     """no NASM on these boxes, so the reference's SIMD objects cannot be built; Pillow's bundled
     libjpeg-turbo (AVX2) is the labelled proxy for the SIMD CPU path.  It can only encode the `-revert` profile (no
     trellis, no scan search, fixed Huffman tables) -- the profile SIMD actually accelerates: the trellis, 62 % of the
-    default profile's CPU time, has no SIMD implementation in the reference.  Returns MP/s or None."""
+    default profile's CPU time, has no SIMD implementation in the reference.  One forked worker process per
+    host thread (Pillow holds the GIL around its encoder loop).  Returns MP/s or None."""
+    global _PROXY_IMAGES
     try:
-        import io
-        from PIL import Image
+        import multiprocessing as mp
+        from PIL import Image  # noqa: F401
+        _PROXY_IMAGES = images
+        h, w = images[0].shape[:2]
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_simd_proxy_worker, [(t, 1) for t in range(procs)])          # workers up, images converted once
+            t0 = time.perf_counter()
+            done = sum(pool.map(_simd_proxy_worker, [(t, reps) for t in range(procs)]))
+            dt = time.perf_counter() - t0
+        return done * w * h / 1e6 / dt
     except Exception:
         return None
-    pil = [Image.fromarray(im) for im in images]
-    h, w = images[0].shape[:2]
-    done = [0] * threads
-
-    def work(t):
-        for r in range(reps):
-            buf = io.BytesIO()
-            pil[(t + r) % len(pil)].save(buf, format="JPEG", quality=75, subsampling=2, optimize=False)
-            done[t] += 1
-    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-    t0 = time.perf_counter()
-    for t in ths: t.start()
-    for t in ths: t.join()
-    return sum(done) * w * h / 1e6 / (time.perf_counter() - t0)
 
 
 def host_threads():
@@ -358,7 +368,8 @@ def measure(a, sw, enc, host, devbuf, base, rank, world, local, dev, stream, dis
     # ---- end to end through the public API: host pixels in, JPEG files out ----
     e2e_ms = None; jpeg_bytes = 0
     if not a.no_e2e:
-        jpeg_bytes = step_e2e()                       # warm (pinned output buffers get allocated)
+        for _ in range(2):                            # warm: output buffers grow to the workload's sizes, the pinned file arena is consolidated
+            jpeg_bytes = step_e2e()
         barrier()
         t0 = time.perf_counter()
         for _ in range(a.steps):

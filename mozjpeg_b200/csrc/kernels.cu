@@ -3595,13 +3595,7 @@ __device__ __forceinline__ void walk_prog_block(const int16_t *__restrict__ blk,
     return;
   }
   int v[64];
-  // blocks without anything to say in this scan (no band value in a first scan; no newly non-zero value and no
-  // correction bit in a refinement scan) are not fetched at all
-  if ((aux & AUX_BRK) || (sd.Ah != 0 && (aux >> 2) != 0)) load_block64(blk, v, sd.Ss, sd.Se);
-  else {
-#pragma unroll
-    for (int i = 0; i < 64; i++) v[i] = 0;
-  }
+  load_block64(blk, v);       // (band-limited or skipped loads were measured slower here: these walks are instruction-bound)
   if (sd.Ah == 0) {                                      // encode_mcu_AC_first :648-737
     if (aux & AUX_BRK) {
       int r = 0;
