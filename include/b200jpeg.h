@@ -93,8 +93,8 @@ typedef struct {
   /* source image (jpeglib.h:396-402) */
   int image_width, image_height;
   int input_components;
-  int in_color_space;
-  int data_precision;                     /* 8 (12 is a later row) */
+  int in_color_space;                     /* B200JPEG_CS_GRAYSCALE / RGB / YCbCr or one of the B200JPEG_CS_EXT_* pixel orders */
+  int data_precision;                     /* 8, or 12 (samples in uint16; trellis and deringing off, as the reference requires) */
   /* JPEG parameters */
   int jpeg_color_space;
   int num_components;
@@ -116,13 +116,13 @@ typedef struct {
   int write_Adobe_marker;
   /* mozjpeg extension parameters (jpegint.h:93-135, jcext.c) */
   int compress_profile;
-  int optimize_scans;                     /* scan search: not on the device path yet */
+  int optimize_scans;                     /* scan search over the jpeg_search_progression candidates (jcmaster.c:773-962) */
   int trellis_quant;
   int trellis_quant_dc;
-  int trellis_eob_opt;                    /* must be 0 */
+  int trellis_eob_opt;                    /* block-level EOB-run optimisation along each block row (jcdctmgr.c:1224-1297) */
   int use_lambda_weight_tbl;              /* no effect in the reference (jcdctmgr.c:971,1017) */
   int use_scans_in_trellis;               /* trellis in two AC bands split at trellis_freq_split (jcmaster.c:451-467) */
-  int trellis_q_opt;                      /* must be 0 */
+  int trellis_q_opt;                      /* re-fit the quantization tables to the kept coefficients (jcmaster.c:1014-1030); per image */
   int overshoot_deringing;
   int trellis_freq_split;
   int trellis_num_loops;                  /* 1..16 rounds of statistics + trellis per component (jcmaster.c:453-465) */
@@ -156,8 +156,8 @@ void b200jpeg_set_linear_quality(b200jpeg_params *p, int scale_factor, int force
 void b200jpeg_set_quality(b200jpeg_params *p, int quality, int force_baseline);
 /* cjpeg's jpeg_default_qtables: per-slot q_scale_factor (rdswitch.c:509-521) */
 void b200jpeg_default_qtables(b200jpeg_params *p, int force_baseline);
-/* jpeg_simple_progression (jcparam.c:859-1004); returns B200JPEG_ERR_UNSUPPORTED
- * if optimize_scans is set (the 64-scan search script is a later row). */
+/* jpeg_simple_progression (jcparam.c:859-1004); with optimize_scans set it installs the candidate script of
+ * jpeg_search_progression (jcparam.c:733-852: 64 scans, 23 for one component) like the reference. */
 int  b200jpeg_simple_progression(b200jpeg_params *p);
 /* std_huff_tables (jstdhuff.c) */
 void b200jpeg_std_huff_tables(b200jpeg_params *p);

@@ -76,11 +76,11 @@ using namespace b200;
 // intermediate HBM state of one chunk in flight
 struct Arena {
   b200::DevBuf d_planes;             // input smoothing: the pre-pass's component planes
-  b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_perm, d_srec, d_splits, d_best_al, d_qimg, d_qsum, d_eo, d_es;
+  b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_srec, d_splits, d_best_al, d_qimg, d_qsum, d_eo, d_es;
   b200::DevBuf d_blk_bits, d_tile_bits, d_tile_base, d_seg_corr, d_mark, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
   b200::Geom g;                      // the plan's geometry with this arena's coefficient pointers
   void release() {
-    b200::DevBuf *db[] = {&d_planes, &d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_perm, &d_srec, &d_splits, &d_best_al, &d_qimg, &d_qsum, &d_eo, &d_es, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
+    b200::DevBuf *db[] = {&d_planes, &d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_srec, &d_splits, &d_best_al, &d_qimg, &d_qsum, &d_eo, &d_es, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
     for (b200::DevBuf *b : db) b->release();
     for (int i = 0; i < 4; i++) { d_coef[i].release(); d_raw[i].release(); d_plain[i].release(); }
   }
@@ -385,9 +385,8 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
     if ((rc = a.d_tabs_trellis.reserve(tabset * 4 * n))) return rc;
     if ((rc = a.d_rec.reserve((size_t)n * pl.sum_real_blocks * sizeof(DcRec)))) return rc;
     if ((rc = a.d_bt.reserve((size_t)n * pl.sum_real_blocks * 8))) return rc;
-    if ((rc = a.d_perm.reserve((size_t)n * pl.sum_real_blocks * 4))) return rc;
     if ((rc = a.d_srec.reserve((size_t)n * pl.sum_real_blocks * 16))) return rc;
-    if ((rc = a.d_splits.reserve((size_t)n * 4 * 4 * 4))) return rc;
+    if ((rc = a.d_splits.reserve((size_t)n * 4 * (4 + 128) * 4))) return rc;      // class boundaries + the sort's counters
     if ((rc = a.d_best_al.reserve((size_t)n * 2 * 4))) return rc;
     if (p->trellis_quant && p->trellis_q_opt) {
       if ((rc = a.d_qimg.reserve((size_t)n * 512))) return rc;
@@ -541,18 +540,8 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
       }
     }
     if (!generic_rounds) {
-      static const bool trellis_v1 = getenv("B200JPEG_TRELLIS_V1") != nullptr;       // A/B aid: the first-generation kernels
-      if (trellis_v1) {
-      tm.mark("trellis_sort");
-      launch_sort_blocks(gr, A.d_rec.as<DcRec>(), rlr, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
       tm.mark("trellis_ac");
-      launch_trellis_ac(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rlr, A.d_perm.as<uint32_t>(), A.d_splits.as<uint32_t>(), n, s);
-      } else {
-      static const bool trellis_v2 = getenv("B200JPEG_TRELLIS_V2") != nullptr;
-      tm.mark("trellis_ac");
-      if (trellis_v2) launch_trellis_ac2(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rlr, A.d_srec.p, A.d_splits.as<uint32_t>(), n, s);
-      else launch_trellis_ac3(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rlr, A.d_srec.p, A.d_splits.as<uint32_t>(), n, s);
-      }
+      launch_trellis_ac3(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rlr, A.d_srec.p, A.d_splits.as<uint32_t>(), n, s);
     } else {
       tm.mark("trellis_ac");
       float4 *eo = eobopt ? A.d_eo.as<float4>() : nullptr;

@@ -1349,366 +1349,15 @@ __global__ void k_seed_hist(uint32_t *hist, int slot)
 void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s) { k_seed_hist<<<n, 256, 0, s>>>(hist, slot); LAUNCHED(); }
 
 // =====================================================================
-// trellis quantization, AC part: quantize_trellis (jcdctmgr.c:936-1330)
-// restricted to its default option set.  One thread per block.
-//   phase 1: norm (natural order, serial fp32), lambda, accumulated zero
-//            distortion (zigzag order, serial fp32), compact list of the
-//            positions whose plain-quantized value is non-zero;
-//   phase 2: for each listed position the best (predecessor, candidate) pair,
-//            strict '<' in (predecessor, candidate) order  (:1157-1184);
-//   phase 3: best end-of-block position (:1187-1207) and back-tracking
-//            (:1211-1222).
+// trellis quantization, AC part: quantize_trellis (jcdctmgr.c:936-1330).
+//   phase 1: lambda from the block's norm, accumulated zero distortion (zigzag order, serial fp32), an entry for
+//            every position whose plain-quantized value is non-zero;
+//   phase 2: for each entry the best (predecessor, candidate) pair, strict '<' in (predecessor, candidate) order
+//            (:1157-1184);
+//   phase 3: best end-of-block position (:1187-1207) and back-tracking (:1211-1222).
+// The default option set runs on k_trellis_ac3 (below, with the sorting kernels); the optional modes (two AC bands,
+// repeated rounds, EOB-run optimisation, table re-fitting) on the literal band kernel that follows.
 // =====================================================================
-#define TRELLIS_THREADS 128
-#ifndef TRELLIS_MIN_CTAS
-#define TRELLIS_MIN_CTAS 4           // register cap of the common class: 4 CTAs x 128 threads -> 128 registers (5 -> 96: slower, measured)
-#endif
-// The zero-distortion prefix A[0..63] of a thread's block: TRELLIS_SMEM_A keeps it in shared memory (element i of
-// thread tid at sA[i * TRELLIS_THREADS + tid]: conflict-free for any per-thread index) instead of local memory
-#ifndef TRELLIS_SMEM_A
-#define TRELLIS_SMEM_A 1
-#endif
-#if TRELLIS_SMEM_A
-#define AX(i) ((i) * TRELLIS_THREADS)
-#else
-#define AX(i) (i)
-#endif
-// rate table element type: fp16 (half the shared memory) or fp32 (no conversion in the inner loop)
-#ifndef TRELLIS_RATE_F32
-#define TRELLIS_RATE_F32 1
-#endif
-#if TRELLIS_RATE_F32
-typedef float rate_t;
-#define RATE_F(x) (x)
-#else
-typedef __half rate_t;
-#define RATE_F(x) __half2float(x)
-#endif
-
-// Order the real blocks of every (image, component) by decreasing number of
-// non-zero plain-quantized AC coefficients (counting sort on DcRec.nz), so that
-// the 32 blocks a warp of k_trellis_ac works on have similar trip counts.
-__global__ void __launch_bounds__(256) k_sort_blocks(Geom g, const DcRec *__restrict__ rec, RecLayout rl, uint32_t *__restrict__ perm, uint32_t *__restrict__ splits)
-{
-  __shared__ unsigned cnt[64], start[64];
-  const int ci = blockIdx.x % g.nc, img = blockIdx.x / g.nc;
-  const CompGeom &c = g.c[ci];
-  const long long nblk = (long long)c.wib * c.hib;
-  const DcRec *r = rec + (size_t)img * rl.per_image + rl.comp_off[ci];
-  uint32_t *p = perm + (size_t)img * rl.per_image + rl.comp_off[ci];
-  if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
-  __syncthreads();
-  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) atomicAdd(&cnt[63 - min((int)r[b].nz, 63)], 1u);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned a = 0; for (int k = 0; k < 64; k++) { start[k] = a; a += cnt[k]; }
-    // sorted order = decreasing count: [0, splits[0]) have more than 32 non-zeros, [splits[0], splits[1]) 17..32, the rest <= 16
-    splits[2 * blockIdx.x] = start[63 - 32]; splits[2 * blockIdx.x + 1] = start[63 - 16];
-  }
-  __syncthreads();
-  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) { unsigned pos = atomicAdd(&start[63 - min((int)r[b].nz, 63)], 1u); p[pos] = (uint32_t)b; }
-}
-void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, uint32_t *splits, int n, cudaStream_t s)
-{
-  k_sort_blocks<<<n * g.nc, 256, 0, s>>>(g, rec, rl, perm, splits);
-  LAUNCHED();
-}
-
-// Register fast path of the AC trellis for warps whose blocks all have at most
-// MM non-zero positions (blocks are sorted by that count, so this is the common
-// case): the compact lists are reloaded from local memory with STATIC indices
-// into registers, and the (entry, predecessor) loops are fully unrolled, so the
-// search touches no memory except the shared rate table.  Same arithmetic and
-// selection rule as the generic loop in k_trellis_ac.
-template <int MM>
-__device__ __forceinline__ void trellis_entries_regs(const int m, unsigned long long nzmask, const float *A,
-                                                     const int16_t *__restrict__ raw16, const int16_t *__restrict__ o16,
-                                                     const rate_t (*srate)[64], const float *swz, const int *sq8, const unsigned *sqdiv, const int qL,
-                                                     const float lambda, const int maxq, const float azd63, const float eob, const unsigned dc_q, unsigned long long &final_mask)
-{
-  int r_pos[MM]; float r_at[MM], r_acc[MM];
-  int r_rs[MM], r_val[MM];
-  {
-    unsigned lo = (unsigned)nzmask, hi = (unsigned)(nzmask >> 32);
-#pragma unroll
-    for (int t = 0; t < MM; t++) {
-      // next set bit, ascending (positions past the block's last non-zero read A[63], harmlessly)
-      int p = lo ? __ffs((int)lo) - 1 : (hi ? 31 + __ffs((int)hi) : 63);
-      if (lo) lo &= lo - 1; else hi &= hi - 1;
-      r_pos[t] = p; r_at[t] = A[AX(p)]; r_acc[t] = 0.f; r_rs[t] = 0; r_val[t] = 0;
-    }
-  }
-  int nraw = 0; float nbefore = 0.f;
-  if (m > 0) { nraw = raw16[r_pos[0]]; nbefore = A[AX(r_pos[0] - 1)]; }
-#pragma unroll
-  for (int t = 0; t < MM; t++) {
-    if (t < m) {
-      const int i = r_pos[t];
-      const int rawv = nraw; const float Ai1 = nbefore;
-      if (t + 1 < MM && t + 1 < m) { nraw = raw16[r_pos[t + 1]]; nbefore = A[AX(r_pos[t + 1] - 1)]; }
-      const int x = abs(rawv);
-      const int q = sq8[i];
-      const int qv = min((int)(__umulhi((unsigned)(x + (q >> 1)) << 14, sqdiv[i]) >> qL), maxq);      // :1136-1144
-      const int nc = nbits_of(qv);
-      const float wl = swz[i];
-      float best = 1e38f; int best_s = 0, best_k = -1;
-#pragma unroll 1
-      for (int k = 0; k < nc; k++) {
-        const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
-        const int delta = cand * q - x;
-        const float dist = (float)(delta * delta) * lambda * wl;                   // :1151
-        const rate_t *rk = &srate[k][i - 1];                                        // rk[-j] = rate for run i-1-j
-        float kb = 1e38f; int ks = 0;
-        {
-          float cost = RATE_F(rk[0]) + dist;
-          cost += (Ai1 - 0.0f) + 0.0f;
-          if (cost < kb) { kb = cost; ks = 0; }
-        }
-#pragma unroll
-        for (int s2 = 0; s2 < t; s2++) {
-          float cost = RATE_F(rk[-r_pos[s2]]) + dist;
-          cost += (Ai1 - r_at[s2]) + r_acc[s2];
-          if (cost < kb) { kb = cost; ks = s2 + 1; }
-        }
-        if (kb < best || (kb == best && ks < best_s)) { best = kb; best_s = ks; best_k = k; }
-      }
-      r_acc[t] = best; r_rs[t] = best_s;
-      // the value this entry takes if it stays on the chain (:1179, :1143-1153)
-      const int nc1 = nc - 1;
-      const int cand = (best_k >= 0 && best_k < nc1) ? (2 << best_k) - 1 : qv;
-      const int sgn = rawv >> 31;
-      r_val[t] = (cand ^ sgn) - sgn;
-    }
-  }
-  // best end-of-block position (:1187-1207)
-  int last = 0;
-  float best_cost = azd63 + eob;
-#pragma unroll
-  for (int t = 0; t < MM; t++) {
-    if (t < m) {
-      float cst = r_acc[t] + azd63 - r_at[t];
-      if (r_pos[t] < 63) cst += eob;
-      if (cst < best_cost) { best_cost = cst; last = t + 1; }
-    }
-  }
-  // output: zeros except the back-tracked chain (:1211-1222); DC slot untouched here
-  int16_t *o = const_cast<int16_t *>(o16);
-  uint4 *q4 = reinterpret_cast<uint4 *>(o);
-  q4[0] = make_uint4(dc_q, 0, 0, 0);
-#pragma unroll
-  for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
-  unsigned long long fm = 0;
-#pragma unroll
-  for (int t = MM - 1; t >= 0; t--) {
-    if (t + 1 == last) { o[r_pos[t]] = (int16_t)r_val[t]; if (SEQ_SPARSE_ENC && r_val[t]) fm |= 1ull << r_pos[t]; last = r_rs[t]; }
-  }
-  final_mask = fm;
-}
-
-// Shared memory per CTA: the rate table of the CTA's (image, component)
-//   rate[k][run] = ehufsi[16*(run&15) + k+1] + (k+1) + (run>>4)*ehufsi[0xF0]   (:1163-1175)
-// as fp16 (exact: <= 74), +inf where the reference skips the combination
-// (missing code, or run >= 16 without a ZRL code) -- an infinite cost never
-// passes the strict '<'.
-// Local memory per thread (L1 resident) holds compact per-entry lists indexed by
-// the entry's rank among the block's non-zero positions, which K1 left as a bit
-// mask in the side record: position, accumulated zero distortion at / before the
-// position, accumulated cost, chosen predecessor and candidate.
-// The (predecessor, candidate) minimum of :1157-1184 is taken candidate by
-// candidate: for each candidate the first predecessor with the smallest cost,
-// then over candidates the smallest cost, ties to the earlier predecessor, then
-// to the earlier candidate -- the same pair the reference's scan order keeps.
-// CLS selects the blocks by their number of non-zero positions m (class boundaries in sorted order from
-// k_sort_blocks).  CLS 1: 17 <= m <= 32, register path with 32 entries.  CLS 0: everything else -- warps
-// whose blocks all have m <= 16 take the 16-entry register path, the others (m > 32) the generic loops.
-template <int CLS>
-__global__ void __launch_bounds__(TRELLIS_THREADS, CLS == 1 ? 3 : TRELLIS_MIN_CTAS) k_trellis_ac(Geom g, const TrellisConsts *__restrict__ tc,
-                                                                   const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
-                                                                   DcRec *__restrict__ rec, RecLayout rl, const uint32_t *__restrict__ perm,
-                                                                   const uint32_t *__restrict__ splits)
-{
-  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
-  const CompGeom &c = g.c[ci];
-  {
-    // this CTA's slice of the sorted order against the class's range
-    const long long lo = splits[2 * blockIdx.y], hi = splits[2 * blockIdx.y + 1];      // [lo, hi) = the blocks with 17..32 non-zeros
-    const long long b0 = (long long)blockIdx.x * blockDim.x;
-    if (CLS == 1 ? (b0 >= hi || b0 + blockDim.x <= lo) : (b0 >= lo && b0 + blockDim.x <= hi)) return;
-  }
-  __shared__ rate_t srate[10][64];
-  __shared__ float swz[64];
-  __shared__ int sq8[64];
-  __shared__ unsigned sqdiv[64];              // exact (|x| + q/2) / q: umulhi((|x| + q/2) << 14, sqdiv[i]) >> qL  (table-uniform shift, like quant_fast)
-  __shared__ int sqL;
-  __shared__ uint8_t acsi[256];
-  const long long nblk = (long long)c.wib * c.hib;
-  if ((long long)blockIdx.x * blockDim.x >= nblk) return;
-  const int tid = threadIdx.x;
-  {
-    const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + (4 + c.ac_tbl);
-    for (int i = tid; i < 256; i += TRELLIS_THREADS) acsi[i] = ac->size[i];
-    if (tid < 64) { swz[tid] = tc->w_zz[c.qt][tid]; sq8[tid] = tc->q8_zz[c.qt][tid]; sqdiv[tid] = tc->qmul_zz[c.qt][tid]; }
-    if (tid == 0) sqL = tc->qL[c.qt];
-  }
-  __syncthreads();
-  for (int e = tid; e < 640; e += TRELLIS_THREADS) {
-    const int k = e >> 6, run = e & 63;
-    const int zrl = acsi[0xF0], cb = acsi[16 * (run & 15) + k + 1];
-    const bool skip = cb == 0 || ((run >> 4) && zrl == 0) || run == 63;
-#if TRELLIS_RATE_F32
-    srate[k][run] = skip ? __int_as_float(0x7F800000) : (float)(cb + (k + 1) + (run >> 4) * zrl);
-#else
-    srate[k][run] = skip ? __ushort_as_half((unsigned short)0x7C00) : __int2half_rn(cb + (k + 1) + (run >> 4) * zrl);
-#endif
-  }
-  __syncthreads();
-  const long long tix = (long long)blockIdx.x * blockDim.x + tid;
-  if (tix >= nblk) return;
-  const size_t rbase = (size_t)img * rl.per_image + rl.comp_off[ci];
-  const unsigned lin = perm[rbase + tix];
-  const int by = lin / c.wib, bx = lin - by * c.wib;
-  const size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
-  const int16_t *raw16 = c.raw + blk * 64;
-  int16_t *o16 = c.coef + blk * 64;
-  // the block's coefficient line is rewritten at the end (16-byte and 2-byte stores): have it in L2 by then, or every
-  // partial-sector store turns into a read-modify-write against DRAM
-  asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 16)); asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 32));
-  asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 48));
-  const unsigned dc_q = (unsigned)(unsigned short)o16[0];      // the DC value survives the rewrite: fetched now, needed only at the end
-  // lambda from the block's norm (K1 left the natural-order sum of squares in rec.f)   :1026-1035
-  float lambda; unsigned long long nzmask;
-  {
-    DcRec rr = rec[rbase + lin];
-    nzmask = rr.nzmask;
-    const int mcls = rr.nz;                                   // K1's count (the mask itself is replaced by the final one below)
-    if ((CLS == 1) != (mcls > 16 && mcls <= 32)) return;      // the other class's block
-    float norm = (float)((double)rr.lambda_dc / 63.0);
-    if (tc->use_norm) lambda = (float)(tc->p1 / (tc->p2 + (double)norm));
-    else lambda = tc->lambda_const;
-    rec[rbase + lin].lambda_dc = lambda * swz[0];
-  }
-  // phase 1: accumulated zero distortion (zigzag order, serial fp32), every position, to local memory   :1134
-#if TRELLIS_SMEM_A
-  __shared__ float sA[64 * TRELLIS_THREADS];
-  float *A = sA + tid;
-#else
-  float A[64];
-#endif
-  float azd = 0.0f;
-  A[AX(0)] = 0.0f;
-  {
-    const uint4 *r4 = reinterpret_cast<const uint4 *>(raw16);
-#pragma unroll
-    for (int v = 0; v < 8; v++) {
-      const uint4 a = r4[v];
-      const unsigned aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int jj = 0; jj < 8; jj++) {
-        const int i = 8 * v + jj;
-        if (i == 0) continue;
-        const int x = abs((int)(int16_t)((aw[jj >> 1] >> ((jj & 1) * 16)) & 0xFFFF));
-        azd = (float)(x * x) * lambda * swz[i] + azd;
-        A[AX(i)] = azd;
-      }
-    }
-  }
-  const float azd63 = azd;
-  const int maxq = (1 << tc->max_coef_bits) - 1;
-  const int m = __popcll(nzmask);
-  const int qL = sqL;
-  unsigned long long fmask = 0;                  // SEQ_SPARSE_ENC: positions that stay non-zero, for the sequential bit packer
-
-  if (CLS == 1) { trellis_entries_regs<32>(m, nzmask, A, raw16, o16, srate, swz, sq8, sqdiv, qL, lambda, maxq, azd63, (float)acsi[0], dc_q, fmask); if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fmask; return; }
-  // warps whose blocks all have few non-zero positions take the register path
-  {
-    const int mmax = __reduce_max_sync(__activemask(), m);
-    if (mmax <= 16) {
-      trellis_entries_regs<16>(m, nzmask, A, raw16, o16, srate, swz, sq8, sqdiv, qL, lambda, maxq, azd63, (float)acsi[0], dc_q, fmask);
-      if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fmask;
-      return;
-    }
-  }
-
-  // generic path: compact lists, indexed by rank among the non-zero positions
-  uint8_t e_pos[64], e_rs[64], e_k[64];
-  unsigned short e_qs[64];                         // plain-quantized magnitude (clamped) | sign of the raw value << 15
-  float e_at[64], e_before[64], e_acc[64];
-  {
-    int r = 0;
-    for (unsigned long long mm = nzmask; mm; mm &= mm - 1) {
-      const int p = __ffsll((long long)mm) - 1;
-      e_pos[r] = (uint8_t)p; e_at[r] = A[AX(p)]; e_before[r] = A[AX(p - 1)]; e_qs[r] = (unsigned short)raw16[p]; r++;
-    }
-  }
-
-  // phase 2   :1121-1185.  The entry's plain-quantized value comes from global memory (L2 resident: K1 just wrote it);
-  // the next entry's value is requested one iteration ahead.
-#pragma unroll 1
-  for (int t = 0; t < m; t++) {
-    const int i = e_pos[t];
-    const int rawv = (int)(short)e_qs[t];
-    const int x = abs(rawv);
-    const int q = sq8[i];
-    const int qv = min((int)(__umulhi((unsigned)(x + (q >> 1)) << 14, sqdiv[i]) >> qL), maxq);      // :1136-1144
-    e_qs[t] = (unsigned short)(qv | ((rawv >> 31) & 0x8000));
-    const int nc = nbits_of(qv);
-    const float wl = swz[i];
-    const float Ai1 = e_before[t];
-    float best = 1e38f; int best_s = 0, best_k = -1;
-#pragma unroll 1
-    for (int k = 0; k < nc; k++) {
-      const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
-      const int delta = cand * q - x;
-      const float dist = (float)(delta * delta) * lambda * wl;                   // :1151
-      const rate_t *rk = &srate[k][i - 1];                                        // rk[-j] = rate for run i-1-j
-      // predecessor "block start" (j = Ss-1): run = i-1, zero tail
-      float kb = 1e38f; int ks = 0;
-      {
-        float cost = RATE_F(rk[0]) + dist;
-        cost += (Ai1 - 0.0f) + 0.0f;
-        if (cost < kb) { kb = cost; ks = 0; }
-      }
-#pragma unroll 2
-      for (int s2 = 0; s2 < t; s2++) {
-        const int j = e_pos[s2];
-        float cost = RATE_F(rk[-j]) + dist;
-        cost += (Ai1 - e_at[s2]) + e_acc[s2];
-        if (cost < kb) { kb = cost; ks = s2 + 1; }
-      }
-      if (kb < best || (kb == best && ks < best_s)) { best = kb; best_s = ks; best_k = k; }
-    }
-    e_acc[t] = best; e_rs[t] = (uint8_t)best_s; e_k[t] = (uint8_t)(best_k < 0 ? 255 : best_k);
-  }
-
-  // phase 3: best end-of-block position (:1187-1207) and back-tracking (:1211-1222)
-  int last = 0;                                  // 1-based entry index, 0 = none
-  {
-    const float eob = (float)acsi[0];
-    float best_cost = azd63 + eob;
-    for (int t = 0; t < m; t++) {
-      float cst = e_acc[t] + azd63 - e_at[t];
-      if (e_pos[t] < 63) cst += eob;
-      if (cst < best_cost) { best_cost = cst; last = t + 1; }
-    }
-  }
-  // output: zeros except the back-tracked chain; DC slot untouched here
-  uint4 *q4 = reinterpret_cast<uint4 *>(o16);
-  q4[0] = make_uint4(dc_q, 0, 0, 0);
-#pragma unroll
-  for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
-  while (last != 0) {
-    const int t = last - 1;
-    const int qs = e_qs[t], qv = qs & 0x7FFF, nc = nbits_of(qv), k = e_k[t];
-    const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
-    const int sgn = -(qs >> 15);
-    const int outv = (cand ^ sgn) - sgn;
-    o16[e_pos[t]] = (int16_t)outv;
-    if (SEQ_SPARSE_ENC && outv) fmask |= 1ull << e_pos[t];
-    last = e_rs[t];
-  }
-  if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fmask;
-}
-
 // ---------------------------------------------------------------------
 // Optional trellis mode use_scans_in_trellis (jcmaster.c:451-467): the AC coefficients of a component are requantized
 // in two passes, zigzag positions 1..trellis_freq_split and the rest, each with Huffman tables gathered just before
@@ -1994,396 +1643,85 @@ void launch_qopt_update(long long *qsum, uint16_t *qimg, int n, cudaStream_t s)
   LAUNCHED();
 }
 
-// =====================================================================
-// AC trellis, second generation (same arithmetic as k_trellis_ac, jcdctmgr.c:1121-1222).
-//  * k_sort_blocks2 emits sorted RECORDS {norm, block index, non-zero mask} and four class boundaries per
-//    (image, component): blocks with more than 32 / 17..32 / 9..16 / at most 8 non-zero plain-quantized AC values;
-//  * one kernel instantiation per class (MM = capacity of the register-resident predecessor lists), launched over a
-//    small grid whose CTAs build the rate table once and then loop over the 128-block chunks of their class;
-//  * phase 1 converts the raw coefficients without I2F (exponent trick; fx*fx rounds like (float)(x*x)) and in packed
-//    fp32x2 operations (sm_100 add/mul.f32x2), the serial prefix sum stays a scalar chain in the reference's order;
-//  * per entry, T[s] = (A[i-1] - A[p_s]) + acc[s] is formed once and shared by all candidates (it does not depend on the
-//    candidate); candidates 0..2 are unrolled (immediate rate-table offsets), further ones loop;
-//  * per entry state is one packed word {4*position, chosen predecessor, chosen value}.
-// =====================================================================
+// sorted side record of the AC trellis: {norm, block index inside the component, non-zero mask}
 struct SRec { float norm; uint32_t lin; unsigned long long nzmask; };
 static_assert(sizeof(SRec) == 16, "SRec layout");
 
-__global__ void __launch_bounds__(256) k_sort_blocks2(Geom g, const DcRec *__restrict__ rec, RecLayout rl, SRec *__restrict__ srec, uint32_t *__restrict__ splits, int mid_max)
+// Counting sort of every (image, component)'s side records by their number of non-zero plain-quantized AC values,
+// in decreasing order, so that the 32 blocks a warp of the trellis kernel works on have similar trip counts; four class
+// boundaries per (image, component): [0, s0) more than 32 non-zeros, [s0, s1) mid_max+1..32, [s1, s2) 9..mid_max,
+// [s2, nblk) at most 8.  Spread over several CTAs per (image, component) (one CTA each left most SMs idle behind the
+// luma planes): k_sort_count adds each slice's counts per non-zero count to global counters, k_sort_scatter turns them
+// into class offsets, reserves a range per count and slice with one global atomic each and writes the records.  The
+// order inside a count is arbitrary (it only decides which blocks share a warp).  gcnt / gcur: [n*nc][64], zeroed.
+#define SORT_SLICE 4096
+__global__ void __launch_bounds__(256) k_sort_count(Geom g, const DcRec *__restrict__ rec, RecLayout rl, unsigned *__restrict__ gcnt)
+{
+  __shared__ unsigned cnt[64];
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
+  const CompGeom &c = g.c[ci];
+  const long long nblk = (long long)c.wib * c.hib, b0 = (long long)blockIdx.x * SORT_SLICE;
+  if (b0 >= nblk) return;
+  const DcRec *r = rec + (size_t)img * rl.per_image + rl.comp_off[ci];
+  if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long b1 = min(nblk, b0 + SORT_SLICE);
+  for (long long b = b0 + threadIdx.x; b < b1; b += blockDim.x) atomicAdd(&cnt[63 - min((int)r[b].nz, 63)], 1u);
+  __syncthreads();
+  if (threadIdx.x < 64 && cnt[threadIdx.x]) atomicAdd(&gcnt[(size_t)blockIdx.y * 64 + threadIdx.x], cnt[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(Geom g, const DcRec *__restrict__ rec, RecLayout rl, SRec *__restrict__ srec, uint32_t *__restrict__ splits,
+                                                      const unsigned *__restrict__ gcnt, unsigned *__restrict__ gcur, int mid_max)
 {
   __shared__ unsigned cnt[64], start[64];
-  const int ci = blockIdx.x % g.nc, img = blockIdx.x / g.nc;
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
   const CompGeom &c = g.c[ci];
-  const long long nblk = (long long)c.wib * c.hib;
+  const long long nblk = (long long)c.wib * c.hib, b0 = (long long)blockIdx.x * SORT_SLICE;
+  if (b0 >= nblk) return;
   const DcRec *r = rec + (size_t)img * rl.per_image + rl.comp_off[ci];
   SRec *p = srec + (size_t)img * rl.per_image + rl.comp_off[ci];
   if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
   __syncthreads();
-  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) atomicAdd(&cnt[63 - min((int)r[b].nz, 63)], 1u);
+  const long long b1 = min(nblk, b0 + SORT_SLICE);
+  for (long long b = b0 + threadIdx.x; b < b1; b += blockDim.x) atomicAdd(&cnt[63 - min((int)r[b].nz, 63)], 1u);
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned a = 0; for (int k = 0; k < 64; k++) { start[k] = a; a += cnt[k]; }
-    // decreasing count: [0, s0) more than 32 non-zeros, [s0, s1) 16..32 (17..32 for the second-generation kernels),
-    // [s1, s2) 9..15 (16), [s2, nblk) at most 8.  15 list slots per thread let 8 CTAs share an SM's shared memory.
-    splits[4 * blockIdx.x] = start[63 - 32]; splits[4 * blockIdx.x + 1] = start[63 - mid_max]; splits[4 * blockIdx.x + 2] = start[63 - 8];
-    splits[4 * blockIdx.x + 3] = (uint32_t)nblk;
+    unsigned a = 0;
+    for (int k = 0; k < 64; k++) { start[k] = a; a += gcnt[(size_t)blockIdx.y * 64 + k]; }
+    if (blockIdx.x == 0) {
+      splits[4 * blockIdx.y] = start[63 - 32]; splits[4 * blockIdx.y + 1] = start[63 - mid_max]; splits[4 * blockIdx.y + 2] = start[63 - 8];
+      splits[4 * blockIdx.y + 3] = (uint32_t)nblk;
+    }
   }
   __syncthreads();
-  for (long long b = threadIdx.x; b < nblk; b += blockDim.x) {
+  // this slice's range inside every count's run
+  if (threadIdx.x < 64) { const unsigned mine = cnt[threadIdx.x]; start[threadIdx.x] += mine ? atomicAdd(&gcur[(size_t)blockIdx.y * 64 + threadIdx.x], mine) : 0u; }
+  __syncthreads();
+  for (long long b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
     const uint4 q = reinterpret_cast<const uint4 *>(r)[b];        // {norm, raw_dc | nz << 16, mask lo, mask hi}
     const int nz = (int)((q.y >> 16) & 0xFF);
     const unsigned pos = atomicAdd(&start[63 - min(nz, 63)], 1u);
     reinterpret_cast<uint4 *>(p)[pos] = make_uint4(q.x, (unsigned)b, q.z, q.w);
   }
 }
+static void launch_sort2(const Geom &g, const DcRec *rec, const RecLayout &rl, SRec *srec, uint32_t *splits, unsigned *scratch /* [2][n*nc][64] */, int mid_max, int n, cudaStream_t s)
+{
+  long long mb = 0;
+  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
+  const size_t words = (size_t)n * g.nc * 64;
+  cudaMemsetAsync(scratch, 0, 2 * words * sizeof(unsigned), s);
+  dim3 grid((unsigned)((mb + SORT_SLICE - 1) / SORT_SLICE), n * g.nc);
+  k_sort_count<<<grid, 256, 0, s>>>(g, rec, rl, scratch); LAUNCHED();
+  k_sort_scatter<<<grid, 256, 0, s>>>(g, rec, rl, srec, splits, scratch, scratch + words, mid_max); LAUNCHED();
+}
 
-#ifndef T2_PACKED
-#define T2_PACKED 1
-#endif
-#ifndef T2_PREFETCH_OUT
-#define T2_PREFETCH_OUT 1
-#endif
-#ifndef T2_KSTATIC
-#define T2_KSTATIC 3
-#endif
-#ifndef T2_CTAS8
-#define T2_CTAS8 6
-#endif
-#ifndef T2_CTAS16
-#define T2_CTAS16 5
-#endif
-#define T2_THREADS 128
-#define T2A(i) ((i) * T2_THREADS)
 // exact int -> float for 0 <= v < 2^23 without the conversion unit
 __device__ __forceinline__ float u2f_exact(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
 
-template <int MM>
-__device__ __forceinline__ void trellis2_regs(const int m, unsigned long long nzmask, const float *__restrict__ A /* sA + tid */,
-                                              const int16_t *__restrict__ raw16, int16_t *__restrict__ o16,
-                                              const float *__restrict__ srate /* [10][64] */, const uint4 *__restrict__ sEnt, const int qL,
-                                              const float lambda, const int maxq, const float azd63, const float eob, const unsigned dc_q,
-                                              unsigned long long &final_mask)
-{
-  float nat[MM], acc[MM];            // -A[p_s], accumulated cost of entry s
-  unsigned ew[MM];                   // 4*p_s | chosen predecessor (1-based entry, 0 = block start) << 8 | chosen value << 16
-#pragma unroll
-  for (int t = 0; t < MM; t++) { nat[t] = 0.f; acc[t] = 0.f; ew[t] = 0u; }
-  unsigned lo = (unsigned)nzmask, hi = (unsigned)(nzmask >> 32);
-  int p_next = lo ? __ffs((int)lo) - 1 : (hi ? 31 + __ffs((int)hi) : 63);
-  if (lo) lo &= lo - 1; else hi &= hi - 1;
-  int raw_next = raw16[p_next];
-  const char *srate_b = reinterpret_cast<const char *>(srate);
-#pragma unroll
-  for (int t = 0; t < MM; t++) {
-    if (t < m) {
-      const int i = p_next, rawv = raw_next;
-      if (t + 1 < MM) {
-        p_next = lo ? __ffs((int)lo) - 1 : (hi ? 31 + __ffs((int)hi) : 63);
-        if (lo) lo &= lo - 1; else hi &= hi - 1;
-        raw_next = raw16[p_next];
-      }
-      const uint4 en = sEnt[i];                               // {8*Q, reciprocal, weight bits, -}
-      const float Ai1 = A[T2A(i - 1)], Ai = A[T2A(i)];
-      const int x = abs(rawv), q = (int)en.x;
-      const float wl = __uint_as_float(en.z);
-      const int qv = min((int)(__umulhi((unsigned)(x + (q >> 1)) << 14, en.y) >> qL), maxq);      // :1136-1144
-      const int nc = nbits_of(qv);
-      const char *rb = srate_b + (i - 1) * 4;                  // rate of run i-1-j at rb[-4j] (+256 per candidate)
-      // candidate-independent part of the cost per predecessor (:1176)
-      float T[MM + 1]; int ra[MM + 1];
-      T[0] = Ai1; ra[0] = 0;
-#if T2_PACKED
-#pragma unroll
-      for (int s = 0; s + 1 < t; s += 2) {
-        const float2 d = __fadd2_rn(__fadd2_rn(make_float2(Ai1, Ai1), make_float2(nat[s], nat[s + 1])), make_float2(acc[s], acc[s + 1]));
-        T[s + 1] = d.x; T[s + 2] = d.y;
-      }
-      if (t & 1) T[t] = (Ai1 + nat[t - 1]) + acc[t - 1];
-#else
-#pragma unroll
-      for (int s = 0; s < t; s++) T[s + 1] = (Ai1 + nat[s]) + acc[s];
-#endif
-#pragma unroll
-      for (int s = 0; s < t; s++) ra[s + 1] = -(int)(ew[s] & 0xFFu);
-      float best = 1e38f; int best_s = 0, best_k = -1;
-      auto eval_k = [&](const int k) {
-        const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
-        const int delta = cand * q - x;
-        const float fd = u2f_exact((unsigned)abs(delta));
-        const float dist = (fd * fd) * lambda * wl;                                // :1151
-        const char *rk = rb + k * 256;
-        float kb = 1e38f; int ks = 0;
-#if T2_PACKED
-        const float2 d2 = make_float2(dist, dist);
-#pragma unroll
-        for (int s = 0; s + 1 <= t; s += 2) {
-          const float2 r2 = make_float2(*reinterpret_cast<const float *>(rk + ra[s]), *reinterpret_cast<const float *>(rk + ra[s + 1]));
-          const float2 c2 = __fadd2_rn(__fadd2_rn(r2, d2), make_float2(T[s], T[s + 1]));
-          if (c2.x < kb) { kb = c2.x; ks = s; }
-          if (c2.y < kb) { kb = c2.y; ks = s + 1; }
-        }
-        if (!(t & 1)) {
-          const float cost = (*reinterpret_cast<const float *>(rk + ra[t]) + dist) + T[t];
-          if (cost < kb) { kb = cost; ks = t; }
-        }
-#else
-#pragma unroll
-        for (int s = 0; s <= t; s++) {
-          const float cost = (*reinterpret_cast<const float *>(rk + ra[s]) + dist) + T[s];
-          if (cost < kb) { kb = cost; ks = s; }
-        }
-#endif
-        if (kb < best || (kb == best && ks < best_s)) { best = kb; best_s = ks; best_k = k; }
-      };
-      // candidates 0..KS-1 unrolled (immediate table offsets), the rest in a loop; the 32-entry class keeps its code small
-      constexpr int KS = MM <= 16 ? T2_KSTATIC : 1;
-      eval_k(0);
-      if (KS > 1 && nc > 1) eval_k(1);
-      if (KS > 2 && nc > 2) eval_k(2);
-#pragma unroll 1
-      for (int k = KS; k < nc; k++) eval_k(k);
-      // the value this entry takes if it stays on the chain (:1179, :1143-1153)
-      const int cand = (best_k >= 0 && best_k < nc - 1) ? (2 << best_k) - 1 : qv;
-      const int sgn = rawv >> 31;
-      const int val = (cand ^ sgn) - sgn;
-      acc[t] = best; nat[t] = -Ai;
-      ew[t] = (unsigned)(i << 2) | ((unsigned)best_s << 8) | ((unsigned)val << 16);
-    }
-  }
-  // best end-of-block position (:1187-1207)
-  int last = 0;
-  float best_cost = azd63 + eob;
-#pragma unroll
-  for (int t = 0; t < MM; t++) {
-    if (t < m) {
-      float cst = (acc[t] + azd63) + nat[t];
-      if ((ew[t] & 0xFFu) < 63u * 4u) cst += eob;
-      if (cst < best_cost) { best_cost = cst; last = t + 1; }
-    }
-  }
-  // output: zeros except the back-tracked chain (:1211-1222)
-  uint4 *q4 = reinterpret_cast<uint4 *>(o16);
-  q4[0] = make_uint4(dc_q, 0, 0, 0);
-#pragma unroll
-  for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
-  unsigned long long fm = 0;
-#pragma unroll
-  for (int t = MM - 1; t >= 0; t--) {
-    if (t + 1 == last) {
-      const int pos = (int)((ew[t] & 0xFFu) >> 2); const int val = (int)ew[t] >> 16;
-      o16[pos] = (int16_t)val; if (val) fm |= 1ull << pos;
-      last = (int)((ew[t] >> 8) & 0xFFu);
-    }
-  }
-  final_mask = fm;
-}
-
-// m > 32: the same search over compact lists in local memory (rare at photographic quality settings)
-__device__ __noinline__ void trellis2_generic(const int m, unsigned long long nzmask, const float *__restrict__ A,
-                                              const int16_t *__restrict__ raw16, int16_t *__restrict__ o16,
-                                              const float *__restrict__ srate, const uint4 *__restrict__ sEnt, const int qL,
-                                              const float lambda, const int maxq, const float azd63, const float eob, const unsigned dc_q,
-                                              unsigned long long &final_mask)
-{
-  uint8_t e_pos[64], e_rs[64], e_k[64];
-  unsigned short e_qs[64];                         // plain-quantized magnitude (clamped) | sign of the raw value << 15
-  float e_at[64], e_before[64], e_acc[64];
-  {
-    int r = 0;
-    for (unsigned long long mm = nzmask; mm; mm &= mm - 1) {
-      const int p = __ffsll((long long)mm) - 1;
-      e_pos[r] = (uint8_t)p; e_at[r] = A[T2A(p)]; e_before[r] = A[T2A(p - 1)]; e_qs[r] = (unsigned short)raw16[p]; r++;
-    }
-  }
-#pragma unroll 1
-  for (int t = 0; t < m; t++) {
-    const int i = e_pos[t];
-    const int rawv = (int)(short)e_qs[t];
-    const int x = abs(rawv);
-    const uint4 en = sEnt[i];
-    const int q = (int)en.x;
-    const int qv = min((int)(__umulhi((unsigned)(x + (q >> 1)) << 14, en.y) >> qL), maxq);
-    e_qs[t] = (unsigned short)(qv | ((rawv >> 31) & 0x8000));
-    const int nc = nbits_of(qv);
-    const float wl = __uint_as_float(en.z);
-    const float Ai1 = e_before[t];
-    float best = 1e38f; int best_s = 0, best_k = -1;
-#pragma unroll 1
-    for (int k = 0; k < nc; k++) {
-      const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
-      const int delta = cand * q - x;
-      const float dist = (float)(delta * delta) * lambda * wl;
-      const float *rk = srate + k * 64 + (i - 1);
-      float kb = 1e38f; int ks = 0;
-      {
-        float cost = rk[0] + dist;
-        cost += (Ai1 - 0.0f) + 0.0f;
-        if (cost < kb) { kb = cost; ks = 0; }
-      }
-#pragma unroll 2
-      for (int s2 = 0; s2 < t; s2++) {
-        float cost = rk[-(int)e_pos[s2]] + dist;
-        cost += (Ai1 - e_at[s2]) + e_acc[s2];
-        if (cost < kb) { kb = cost; ks = s2 + 1; }
-      }
-      if (kb < best || (kb == best && ks < best_s)) { best = kb; best_s = ks; best_k = k; }
-    }
-    e_acc[t] = best; e_rs[t] = (uint8_t)best_s; e_k[t] = (uint8_t)(best_k < 0 ? 255 : best_k);
-  }
-  int last = 0;
-  {
-    float best_cost = azd63 + eob;
-    for (int t = 0; t < m; t++) {
-      float cst = e_acc[t] + azd63 - e_at[t];
-      if (e_pos[t] < 63) cst += eob;
-      if (cst < best_cost) { best_cost = cst; last = t + 1; }
-    }
-  }
-  uint4 *q4 = reinterpret_cast<uint4 *>(o16);
-  q4[0] = make_uint4(dc_q, 0, 0, 0);
-#pragma unroll
-  for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
-  unsigned long long fm = 0;
-  while (last != 0) {
-    const int t = last - 1;
-    const int qs = e_qs[t], qv = qs & 0x7FFF, nc = nbits_of(qv), k = e_k[t];
-    const int cand = (k < nc - 1) ? (2 << k) - 1 : qv;
-    const int sgn = -(qs >> 15);
-    const int outv = (cand ^ sgn) - sgn;
-    o16[e_pos[t]] = (int16_t)outv;
-    if (outv) fm |= 1ull << e_pos[t];
-    last = e_rs[t];
-  }
-  final_mask = fm;
-}
-
-// MM: 8 / 16 / 32 = register-resident lists of that capacity, 64 = generic (more than 32 entries)
-template <int MM>
-__global__ void __launch_bounds__(T2_THREADS, MM == 8 ? T2_CTAS8 : MM == 16 ? T2_CTAS16 : MM == 32 ? 3 : 4)
-k_trellis_ac2(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
-              DcRec *__restrict__ rec, RecLayout rl, const SRec *__restrict__ srec, const uint32_t *__restrict__ splits)
-{
-  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
-  const CompGeom &c = g.c[ci];
-  long long lo, hi;
-  {
-    const uint4 sp = reinterpret_cast<const uint4 *>(splits)[blockIdx.y];
-    if (MM == 64) { lo = 0; hi = sp.x; } else if (MM == 32) { lo = sp.x; hi = sp.y; } else if (MM == 16) { lo = sp.y; hi = sp.z; } else { lo = sp.z; hi = sp.w; }
-  }
-  const int nchunks = (int)((hi - lo + T2_THREADS - 1) / T2_THREADS);
-  if ((int)blockIdx.x >= nchunks) return;
-  __shared__ __align__(16) float sA[64 * T2_THREADS];         // zero-distortion prefix, element i of thread tid at sA[i*128 + tid]
-  __shared__ __align__(16) float srate[10 * 64];              // rate[k][run] (:1163-1175), +inf where the reference skips
-  __shared__ __align__(16) uint4 sEnt[64];                    // per zigzag position {8*Q, reciprocal, weight, -}
-  __shared__ __align__(16) float swz[64];
-  __shared__ int sqL;
-  const int tid = threadIdx.x;
-  uint8_t *acsi = reinterpret_cast<uint8_t *>(sA);            // table build only
-  {
-    const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + (4 + c.ac_tbl);
-    for (int i = tid; i < 256; i += T2_THREADS) acsi[i] = ac->size[i];
-    if (tid < 64) {
-      const float w = tc->w_zz[c.qt][tid];
-      swz[tid] = w;
-      sEnt[tid] = make_uint4((unsigned)tc->q8_zz[c.qt][tid], tc->qmul_zz[c.qt][tid], __float_as_uint(w), 0u);
-    }
-    if (tid == 0) sqL = tc->qL[c.qt];
-  }
-  __syncthreads();
-  for (int e = tid; e < 640; e += T2_THREADS) {
-    const int k = e >> 6, run = e & 63;
-    const int zrl = acsi[0xF0], cb = acsi[16 * (run & 15) + k + 1];
-    const bool skip = cb == 0 || ((run >> 4) && zrl == 0) || run == 63;
-    srate[e] = skip ? __int_as_float(0x7F800000) : (float)(cb + (k + 1) + (run >> 4) * zrl);
-  }
-  const float eob = (float)acsi[0];
-  __syncthreads();                                             // acsi (aliasing sA) is dead from here on
-  const int maxq = (1 << tc->max_coef_bits) - 1;
-  const int qL = sqL;
-  const size_t rbase = (size_t)img * rl.per_image + rl.comp_off[ci];
-  const int use_norm = tc->use_norm;
-  const double p1 = tc->p1, p2 = tc->p2; const float lambda_const = tc->lambda_const;
-  float *A = sA + tid;
-
-#pragma unroll 1
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    const long long tix = lo + (long long)chunk * T2_THREADS + tid;
-    if (tix >= hi) continue;
-    const SRec sr = srec[rbase + tix];
-    const unsigned lin = sr.lin;
-    const int by = lin / c.wib, bx = lin - by * c.wib;
-    const size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
-    const int16_t *raw16 = c.raw + blk * 64;
-    int16_t *o16 = c.coef + blk * 64;
-    uint4 rv[8];
-    {
-      const uint4 *r4 = reinterpret_cast<const uint4 *>(raw16);
-#pragma unroll
-      for (int v = 0; v < 8; v++) rv[v] = r4[v];
-    }
-#if T2_PREFETCH_OUT
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 16)); asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 32));
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(o16 + 48));
-#endif
-    const unsigned dc_q = (unsigned)(unsigned short)o16[0];      // the DC value survives the rewrite
-    float lambda;
-    {
-      const float norm = (float)((double)sr.norm / 63.0);        // :1026-1035
-      if (use_norm) lambda = (float)(p1 / (p2 + (double)norm)); else lambda = lambda_const;
-      rec[rbase + lin].lambda_dc = lambda * swz[0];
-    }
-    // phase 1: accumulated zero distortion, zigzag order, serial fp32 (:1134)
-    float azd = 0.0f;
-    A[T2A(0)] = 0.0f;
-    {
-      const float2 l2 = make_float2(lambda, lambda);
-      const float2 bias = make_float2(-8421376.0f, -8421376.0f);   // -(2^23 + 2^15): undoes the exponent trick and the +32768 offset
-#pragma unroll
-      for (int v = 0; v < 8; v++) {
-        const unsigned aw[4] = {rv[v].x, rv[v].y, rv[v].z, rv[v].w};
-        const float4 w0 = reinterpret_cast<const float4 *>(swz)[2 * v], w1 = reinterpret_cast<const float4 *>(swz)[2 * v + 1];
-        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-          const unsigned u = aw[jj] ^ 0x80008000u;               // both halves + 32768
-          float2 f = make_float2(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7632)));
-          f = __fadd2_rn(f, bias);                               // the raw values as floats, exact
-          float2 z = __fmul2_rn(__fmul2_rn(__fmul2_rn(f, f), l2), make_float2(ww[2 * jj], ww[2 * jj + 1]));
-          const int i = 8 * v + 2 * jj;
-          if (i != 0) { azd = z.x + azd; A[T2A(i)] = azd; }
-          azd = z.y + azd; A[T2A(i + 1)] = azd;
-        }
-      }
-    }
-    const float azd63 = azd;
-    const int m = __popcll(sr.nzmask);
-    unsigned long long fmask = 0;
-    if (MM == 64) trellis2_generic(m, sr.nzmask, A, raw16, o16, srate, sEnt, qL, lambda, maxq, azd63, eob, dc_q, fmask);
-    else trellis2_regs<MM>(m, sr.nzmask, A, raw16, o16, srate, sEnt, qL, lambda, maxq, azd63, eob, dc_q, fmask);
-    if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fmask;
-  }
-}
-
-void launch_trellis_ac2(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                        DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s)
-{
-  k_sort_blocks2<<<n * g.nc, 256, 0, s>>>(g, rec, rl, static_cast<SRec *>(srec), splits, 16); LAUNCHED();
-  long long mb = 0;
-  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
-  const unsigned full = (unsigned)((mb + T2_THREADS - 1) / T2_THREADS);
-  // CTAs loop over their class's chunks: enough of them per (image, component) to fill the device, few enough to amortise the tables
-  unsigned gx = (unsigned)max(1, min((int)full, (148 * 6 * 4 + n * g.nc - 1) / (n * g.nc)));
-  dim3 grid(gx, n * g.nc);
-  // largest blocks first: the classes touch disjoint blocks
-  k_trellis_ac2<64><<<grid, T2_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, static_cast<const SRec *>(srec), splits); LAUNCHED();
-  k_trellis_ac2<32><<<grid, T2_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, static_cast<const SRec *>(srec), splits); LAUNCHED();
-  k_trellis_ac2<16><<<grid, T2_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, static_cast<const SRec *>(srec), splits); LAUNCHED();
-  k_trellis_ac2<8><<<grid, T2_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, static_cast<const SRec *>(srec), splits); LAUNCHED();
-}
-
 // =====================================================================
-// AC trellis, third generation: rolled loops over shared-memory lists (same arithmetic and selection rule as
-// k_trellis_ac, jcdctmgr.c:1121-1222).  One thread per block, blocks in sorted order (k_sort_blocks2), one kernel
+// AC trellis (third generation; the first two unrolled the entry x predecessor loops over register-resident lists and
+// are in the history): rolled loops over shared-memory lists, jcdctmgr.c:1121-1222.  One thread per block, blocks in
+// sorted order (k_sort_count / k_sort_scatter), one kernel
 // instantiation per count class; the class only sizes the per-thread lists.
 //  * phase 1 walks the 63 raw coefficients once (packed fp32x2 conversion / squaring / weighting, scalar prefix chain
 //    in the reference's order) and PUSHES an entry {A[p-1], p | raw << 16} for every position p whose plain-quantized
@@ -2639,7 +1977,8 @@ static void launch_t3(dim3 grid, cudaStream_t s, const Geom &g, const TrellisCon
 void launch_trellis_ac3(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                         DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s)
 {
-  k_sort_blocks2<<<n * g.nc, 256, 0, s>>>(g, rec, rl, static_cast<SRec *>(srec), splits, 15); LAUNCHED();
+  // splits: 4 words per (image, component), followed by the sort's scratch counters (2 x 64 words each)
+  launch_sort2(g, rec, rl, static_cast<SRec *>(srec), splits, splits + (size_t)n * g.nc * 4, 15, n, s);
   long long mb = 0;
   for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
   const unsigned full = (unsigned)((mb + T3_THREADS - 1) / T3_THREADS);
@@ -2647,22 +1986,13 @@ void launch_trellis_ac3(const Geom &g, const TrellisConsts *tc, const DevHuff *t
   unsigned gx = (unsigned)max(1, min((int)full, (148 * 8 * 3 + n * g.nc - 1) / (n * g.nc)));
   dim3 grid(gx, n * g.nc);
   const SRec *sr = static_cast<const SRec *>(srec);
-  // largest blocks first: the classes touch disjoint blocks
-  launch_t3<64>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
-  launch_t3<32>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
+  // largest blocks first: the classes touch disjoint blocks.  The two big-list classes hold 2 / 4 CTAs per SM (96 / 48 KB of
+  // lists): a full-size grid of CTAs that mostly find their class empty costs more there than the few chunks are worth,
+  // so they get 8 / 16 CTAs per (image, component), still one to two waves when the classes are full (high quality settings)
+  launch_t3<64>(dim3(min(gx, 8u), grid.y), s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
+  launch_t3<32>(dim3(min(gx, 16u), grid.y), s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
   launch_t3<15>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
   launch_t3<8>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
-}
-
-void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                       DcRec *rec, const RecLayout &rl, const uint32_t *perm, const uint32_t *splits, int n, cudaStream_t s)
-{
-  long long mb = 0;
-  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
-  dim3 grid((unsigned)((mb + TRELLIS_THREADS - 1) / TRELLIS_THREADS), n * g.nc);
-  // largest blocks first (they sit at the front of the sorted order): the three classes touch disjoint blocks
-  k_trellis_ac<1><<<grid, TRELLIS_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, perm, splits); LAUNCHED();
-  k_trellis_ac<0><<<grid, TRELLIS_THREADS, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, perm, splits); LAUNCHED();
 }
 
 // =====================================================================

@@ -114,7 +114,6 @@ struct SlotMasks { uint32_t m[4]; int period; };
 void launch_prep_planes(const Geom &g, const uint8_t *src, int smoothing_factor, const PlanesOut &out, int n, cudaStream_t s);
 void launch_import_coefs(const Geom &g, int n, cudaStream_t s);     // raw_in == 2: planes hold JBLOCK rows
 void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dct_method /* J_DCT_METHOD */, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, int n, cudaStream_t s);
-void launch_sort_blocks(const Geom &g, const DcRec *rec, const RecLayout &rl, uint32_t *perm, uint32_t *splits /* [n*nc][2] */, int n, cudaStream_t s);
 void launch_dummy(const Geom &g, int n, cudaStream_t s);
 void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 // nz_rec (here and in launch_block_bits / launch_encode): the side records holding every block's final non-zero positions
@@ -122,12 +121,9 @@ void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, ui
 void launch_gather_seq(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s);
 void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_set_stride, const SlotMasks &masks, int nsets, cudaStream_t s);
-void launch_trellis_ac(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                       DcRec *rec, const RecLayout &rl, const uint32_t *perm, const uint32_t *splits, int n, cudaStream_t s);
-// second-generation AC trellis: sorts the side records by non-zero count (srec: 16 bytes per real block, splits: 4 words per
-// (image, component)) and runs one class-specific kernel per count class
-void launch_trellis_ac2(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                        DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s);
+// AC trellis of the default option set: sorts the side records by non-zero count (srec: 16 bytes per real block;
+// splits: 4 class boundaries per (image, component) followed by 128 words of sorting counters each) and runs one
+// class-specific kernel per count class
 void launch_trellis_ac3(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                         DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s);
 // use_scans_in_trellis: quantize_trellis restricted to the zigzag band [Ss, Se]

@@ -131,12 +131,9 @@ static b200jpeg_scan_info *fill_dc_scans(b200jpeg_scan_info *s, int n, int Ah, i
   if (n <= 4) { s->comps_in_scan = n; for (int ci = 0; ci < n; ci++) s->component_index[ci] = ci; s->Ss = s->Se = 0; s->Ah = Ah; s->Al = Al; return s + 1; }
   return fill_scans(s, n, 0, 0, Ah, Al);
 }
-// jpeg_simple_progression (jcparam.c:859-1004).  The optimize_scans branch
-// (jpeg_search_progression, :733-852) is a later row.
 // jpeg_search_progression (jcparam.c:733-852): the candidate list the scan
-// search (jcmaster.c:773-962) chooses from.  Installing it is supported so
-// that parameter state matches the reference; ENCODING with optimize_scans
-// still set is refused by b200jpeg_validate until scan search lands.
+// search (jcmaster.c:773-962) chooses from; jpeg_simple_progression installs it
+// when optimize_scans is set.
 static bool search_progression(b200jpeg_params *p) {
   int n = p->num_components;
   static const int frequency_split[5] = {2, 8, 5, 12, 18};
