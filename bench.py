@@ -506,6 +506,20 @@ def main():
                "simd": "none (C path: no NASM on the box, so the reference's x86-64 SIMD objects cannot be built)", "simd_proxy": simd,
                "sample": f"{threads * reps} images {W}x{H} ({reps} per host thread, {secs:.1f} s wall = {secs * threads:.0f} CPU-seconds), same switches"}
 
+    # ---- one image through the streaming entry points a libjpeg application drives (jpeg_start_compress /
+    #      jpeg_write_scanlines / jpeg_finish_compress shape of the C-ABI): wall-clock latency, rank 0 only ----
+    latency = None
+    if rank == 0 and a.precision == 8 and not a.no_e2e:
+        p1 = mj.params_from_switches(a.switches.split(), W, H)
+        one = np.ascontiguousarray(base[0])
+        lat = []
+        for rep in range(5):
+            t0 = time.perf_counter()
+            enc.start_compress(p1); enc.write_scanlines(one); data = enc.finish_compress()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        latency = {"ms": statistics.median(lat[1:]), "first_call_ms": lat[0], "bytes": len(data),
+                   "what": "b200jpeg_start_compress + write_scanlines (all rows, pageable host memory) + finish_compress, one image, median of 4"}
+
     if rank == 0:
         cfg = {"workload": workload_name(a), "images_per_gpu": B, "global_images": global_images,
                "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2" % (B * in_bytes / 1e9),
@@ -520,7 +534,7 @@ def main():
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_total"] / a.steps, "higher_is_better": True,
                 "scaling": a.scaling, "vs_baseline": None,
                 "dtype": ("u16 (12-bit) in / int32 DCT / u8 out" if a.precision == 12 else "u8 in / int32 DCT / fp32 trellis costs / u8 out"), "data": "synthetic",
-                "config": cfg, "clocks": r["clk"], "e2e": e2e, "gpu_launches": int(r["launches"]), "roofline": roofline, "cpu_baseline": cpu}
+                "config": cfg, "clocks": r["clk"], "e2e": e2e, "single_image_latency": latency, "gpu_launches": int(r["launches"]), "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
