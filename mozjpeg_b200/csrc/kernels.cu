@@ -1970,8 +1970,8 @@ template <int MM>
 static void launch_t3(dim3 grid, cudaStream_t s, const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                       DcRec *rec, const RecLayout &rl, const SRec *srec, const uint32_t *splits)
 {
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_trellis_ac3<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T3Smem<MM>)); attr_set = true; }
+  // per device: an application may hold encoders on several GPUs in one process, so the opt-in is not cached
+  if (sizeof(T3Smem<MM>) + 8192 > 48 * 1024) cudaFuncSetAttribute(k_trellis_ac3<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T3Smem<MM>));
   k_trellis_ac3<MM><<<grid, T3_THREADS, sizeof(T3Smem<MM>), s>>>(g, tc, tabs, tabs_set_stride, rec, rl, srec, splits); LAUNCHED();
 }
 void launch_trellis_ac3(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
@@ -2380,8 +2380,8 @@ void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *ta
   static const bool use_v1 = getenv("B200JPEG_DC_V1") != nullptr;      // A/B switch
   size_t smem2 = (size_t)DC2_WARPS * 3 * max_wib * 5;
   if (!use_v1 && smem2 <= 200 * 1024) {
-    static size_t attr2 = 0;
-    if (smem2 > 40 * 1024 && smem2 > attr2) { cudaFuncSetAttribute(k_trellis_dc_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cudaFuncSetAttribute(k_trellis_dc_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr2 = 200 * 1024; }
+    // (per device, so not cached: encoders on several GPUs may live in one process)
+    if (smem2 > 40 * 1024) { cudaFuncSetAttribute(k_trellis_dc_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cudaFuncSetAttribute(k_trellis_dc_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }
     dim3 grid((n_imcu + DC2_WARPS * 3 - 1) / (DC2_WARPS * 3), n * g.nc);
     // the DC quantizer per component as an exact multiply-shift division (like make_quant_consts)
     DcDiv dv; bool fast = true;
@@ -2403,8 +2403,7 @@ void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *ta
   size_t smem = (size_t)warps * 3 * max_wib * 11;
   if (smem > 200 * 1024) { warps = 1; smem = (size_t)3 * max_wib * 11; }
   if (smem <= 200 * 1024) {
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) { cudaFuncSetAttribute(k_trellis_dc_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = 200 * 1024; }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_trellis_dc_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid((n_imcu + warps * 3 - 1) / (warps * 3), n * g.nc);
     k_trellis_dc_warp<<<grid, warps * 32, smem, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, max_wib);
   } else {

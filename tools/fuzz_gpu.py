@@ -73,6 +73,10 @@ for it in range(cases):
             continue
     try:
         got = enc.encode_batch(q, arr)
+    except mj.B200JpegError as ex:
+        if ex.code == -2:                       # B200JPEG_ERR_UNSUPPORTED decided at encode time (e.g. fast / float DCT with a non-tiled sampling layout)
+            refused += 1; continue
+        bad += 1; print("DEVICE FAIL", sw, ext, order, (w, h, n), ex); continue
     except Exception as ex:
         bad += 1; print("DEVICE FAIL", sw, ext, order, (w, h, n), ex); continue
     tot += 1
