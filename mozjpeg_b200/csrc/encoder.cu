@@ -1070,9 +1070,6 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
   } else if (raw) {
     Geom &g = pl.g;
     if (p->data_precision != 8) { set_error("raw-data input is 8-bit only on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
-    bool gray = g.nc == 1 && g.hmax == 1 && g.vmax == 1;
-    bool ycc = g.nc == 3 && g.c[0].h == g.hmax && g.c[0].v == g.vmax && g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
-    if (!gray && !ycc && p->dct_method != B200JPEG_DCT_ISLOW) { set_error("raw-data input with the fast or float DCT: only 4:4:4/4:2:2/4:4:0/4:2:0 and single-component layouts are on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
     g.raw_in = 1;
     for (int ci = 0; ci < g.nc; ci++) {
       const size_t rows = (size_t)g.c[ci].hib * 8, cols = (size_t)g.c[ci].wib * 8;      // what compress_first_pass reads (jccoefct.c:262-353)
@@ -1082,12 +1079,6 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
       raw_off[ci] = raw_sum; raw_sum += (raw_total[ci] + 255) & ~(size_t)255;
       g.plane_pitch[ci] = raw->pitch[ci]; g.plane_stride[ci] = raw->stride[ci];
     }
-  }
-  if (!raw && (p->data_precision == 12 || p->dct_method != B200JPEG_DCT_ISLOW)) {
-    const Geom &g = pl.g;
-    bool gray = g.nc == 1 && g.hmax == 1 && g.vmax == 1 && (g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
-    bool ycc = g.nc == 3 && g.cs_mode == 0 && (g.in_comps == 3 || g.in_comps == 4) && g.c[0].h == g.hmax && g.c[0].v == g.vmax && g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
-    if (!gray && !ycc) { set_error("12-bit precision / fast and float DCT: only RGB->YCbCr 4:4:4/4:2:2/4:4:0/4:2:0 and grayscale layouts are on the device path"); return B200JPEG_ERR_UNSUPPORTED; }
   }
   const int nscans = (int)pl.scans.size();
   const int C = choose_chunk(e, pl, n_images, !on_device);

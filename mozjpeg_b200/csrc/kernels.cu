@@ -142,10 +142,89 @@ __device__ __forceinline__ unsigned quant_one(int x, QuantConst k, int dering)
   return (unsigned)(x < 0 ? -q : q);
 }
 
+// ---- JDCT_IFAST (jfdctfst.c:113-224): MULTIPLY = (v * c) >> 8, no rounding ----
+__device__ __forceinline__ void fdct_ifast_1d(int &d0, int &d1, int &d2, int &d3, int &d4, int &d5, int &d6, int &d7)
+{
+  int tmp0 = d0 + d7, tmp7 = d0 - d7, tmp1 = d1 + d6, tmp6 = d1 - d6;
+  int tmp2 = d2 + d5, tmp5 = d2 - d5, tmp3 = d3 + d4, tmp4 = d3 - d4;
+  int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  d0 = tmp10 + tmp11; d4 = tmp10 - tmp11;
+  int z1 = ((tmp12 + tmp13) * 181) >> 8;
+  d2 = tmp13 + z1; d6 = tmp13 - z1;
+  tmp10 = tmp4 + tmp5; tmp11 = tmp5 + tmp6; tmp12 = tmp6 + tmp7;
+  int z5 = ((tmp10 - tmp12) * 98) >> 8;
+  int z2 = ((tmp10 * 139) >> 8) + z5;
+  int z4 = ((tmp12 * 334) >> 8) + z5;
+  int z3 = (tmp11 * 181) >> 8;
+  int z11 = tmp7 + z3, z13 = tmp7 - z3;
+  d5 = z13 + z2; d3 = z13 - z2; d1 = z11 + z4; d7 = z11 - z4;
+}
+__constant__ short c_aanscales[64] = {
+  16384, 22725, 21407, 19266, 16384, 12873,  8867,  4520,
+  22725, 31521, 29692, 26722, 22725, 17855, 12299,  6270,
+  21407, 29692, 27969, 25172, 21407, 16819, 11585,  5906,
+  19266, 26722, 25172, 22654, 19266, 15137, 10426,  5315,
+  16384, 22725, 21407, 19266, 16384, 12873,  8867,  4520,
+  12873, 17855, 16819, 15137, 12873, 10114,  6967,  3552,
+   8867, 12299, 11585, 10426,  8867,  6967,  4799,  2446,
+   4520,  6270,  5906,  5315,  4520,  3552,  2446,  1247};
+
+// ---- JDCT_FLOAT (jfdctflt.c:59-167, AA&N): one 1-D pass, fp32, no contraction ----
+__device__ __forceinline__ void fdct_float_1d(float &d0, float &d1, float &d2, float &d3, float &d4, float &d5, float &d6, float &d7)
+{
+  float tmp0 = d0 + d7, tmp7 = d0 - d7, tmp1 = d1 + d6, tmp6 = d1 - d6;
+  float tmp2 = d2 + d5, tmp5 = d2 - d5, tmp3 = d3 + d4, tmp4 = d3 - d4;
+  float tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  d0 = tmp10 + tmp11; d4 = tmp10 - tmp11;
+  float z1 = (tmp12 + tmp13) * 0.707106781f;
+  d2 = tmp13 + z1; d6 = tmp13 - z1;
+  tmp10 = tmp4 + tmp5; tmp11 = tmp5 + tmp6; tmp12 = tmp6 + tmp7;
+  float z5 = (tmp10 - tmp12) * 0.382683433f;
+  float z2 = 0.541196100f * tmp10 + z5;
+  float z4 = 1.306562965f * tmp12 + z5;
+  float z3 = tmp11 * 0.707106781f;
+  float z11 = tmp7 + z3, z13 = tmp7 - z3;
+  d5 = z13 + z2; d3 = z13 - z2; d1 = z11 + z4; d7 = z11 - z4;
+}
+// float_preprocess_deringing (jcdctmgr.c:503-575) on 64 floats in natural order; catmull_rom takes DCTELEM (int)
+// values, so the float slopes are truncated on the way in
+__device__ __forceinline__ void deringing_block_float(float *data, int q0, float sum, int cnt)
+{
+  const float maxsample = 127.0f; const int size = 64;
+  const int a = min(31, 2 * q0); const float bq = (maxsample * size - sum) / (float)cnt;
+  const float maxovershoot = maxsample + ((float)a < bq ? (float)a : bq);
+  int n = 0;
+  do {
+    if (data[c_zz[n]] < maxsample) { n++; continue; }
+    int start = n;
+    while (++n < size && data[c_zz[n]] >= maxsample) {}
+    int end = n;
+    float f1 = data[c_zz[start >= 1 ? start - 1 : 0]], f2 = data[c_zz[start >= 2 ? start - 2 : 0]];
+    float l1 = data[c_zz[end < size - 1 ? end : size - 1]], l2 = data[c_zz[end < size - 2 ? end + 1 : size - 1]];
+    float fslope = fmaxf(f1 - f2, maxsample - f1), lslope = fmaxf(l1 - l2, maxsample - l1);
+    if (start == 0) fslope = lslope;
+    if (end == size) lslope = fslope;
+    int length = end - start;
+    float step = 1.f / (float)(length + 1), position = step;
+    for (int i = start; i < end; i++, position += step) {
+      float tmp = catmull_rom((int)(maxsample - fslope), 127, 127, (int)(maxsample - lslope), position, length);
+      data[c_zz[i]] = tmp < maxovershoot ? tmp : maxovershoot;
+    }
+    n++;
+  } while (n < size);
+}
+__constant__ double c_aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0, 0.785694958, 0.541196100, 0.275899379};
+
+// PREC: 8 or 12 (uint16 samples); DCTM: 0 = JDCT_ISLOW, 1 = JDCT_IFAST, 2 = JDCT_FLOAT (8-bit only), same arithmetic as
+// the tiled kernel's paths.
+template <int PREC, int DCTM>
 __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restrict__ src,
                                                  const QuantTables *__restrict__ qt, int dering,
                                                  DcRec *__restrict__ rec, RecLayout rl)
 {
+  constexpr int CENTRE = 1 << (PREC - 1);
+  constexpr int SB = PREC == 8 ? 1 : 2;
+  constexpr int P1 = PREC == 8 ? 2 : 1;                  // PASS1_BITS (jfdctint.c:80-86)
   const int ci = blockIdx.z % g.nc, img = blockIdx.z / g.nc;
   const CompGeom &c = g.c[ci];
   int bx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,6 +233,17 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
   const uint8_t *base = src + (size_t)img * g.image_stride;
   int ws[64];
   const int comp = g.cs_mode == 1 ? 0 : ci;
+  // one component sample of the pixel at `px` (12-bit samples are masked like the reference's RANGE_LIMIT, jccolext.c:52-54)
+  auto component = [&](const uint8_t *px) -> int {
+    if (SB == 1) return load_component(px, g.cs_mode, comp, g.px_first, g.px_swap);
+    const uint16_t *q = reinterpret_cast<const uint16_t *>(px);
+    const int first = g.px_first, swap = g.px_swap;
+    if (g.cs_mode == 2) return q[first + (swap ? 2 - comp : comp)] & 0xFFF;
+    const int r = q[first + (swap ? 2 : 0)] & 0xFFF, gg = q[first + 1] & 0xFFF, bb = q[first + (swap ? 0 : 2)] & 0xFFF;
+    if (comp == 0) return (19595 * r + 38470 * gg + 7471 * bb + 32768) >> 16;
+    if (comp == 1) return (-11059 * r - 21709 * gg + 32768 * bb + (CENTRE << 16) + 32767) >> 16;
+    return (32768 * r - 27439 * gg - 5329 * bb + (CENTRE << 16) + 32767) >> 16;
+  };
 #pragma unroll
   for (int y = 0; y < 8; y++) {
     int yo = by * 8 + y;
@@ -164,7 +254,8 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
     for (int x = 0; x < 8; x++) {
       int xo = bx * 8 + x;
       if (g.raw_in) {                                     // component planes (raw-data input / the smoothing pre-pass): only centre them
-        ws[8 * y + x] = (int)g.plane[ci][(size_t)img * g.plane_stride[ci] + (size_t)yo * g.plane_pitch[ci] + xo] - 128;
+        const uint8_t *q = g.plane[ci] + (size_t)img * g.plane_stride[ci] + (size_t)yo * g.plane_pitch[ci] + (size_t)xo * SB;
+        ws[8 * y + x] = (SB == 1 ? (int)*q : (int)*reinterpret_cast<const uint16_t *>(q)) - CENTRE;
         continue;
       }
       int sum = 0;
@@ -173,7 +264,7 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
         const uint8_t *row = base + (size_t)iy * g.row_pitch;
         for (int du = 0; du < c.hx; du++) {
           int ix = min(xo * c.hx + du, g.W - 1);          // expand_right_edge (jcsample.c:98-116)
-          sum += load_component(row + (size_t)ix * g.in_comps, g.cs_mode, comp, g.px_first, g.px_swap);
+          sum += component(row + (size_t)ix * g.in_comps * SB);
         }
       }
       int val;
@@ -181,33 +272,84 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
       else if (c.hx == 2 && c.vx == 1) val = (sum + (xo & 1)) >> 1;          // jcsample.c:226-254
       else if (c.hx == 2 && c.vx == 2) val = (sum + 1 + (xo & 1)) >> 2;      // jcsample.c:263-295
       else { int np = c.hx * c.vx; val = (sum + np / 2) / np; }              // jcsample.c:151-190
-      ws[8 * y + x] = val - 128;                                             // convsamp
+      ws[8 * y + x] = val - CENTRE;                                          // convsamp
     }
   }
-  if (dering) {
+  int qv[64];                                              // quantized values, natural order (fast / float DCT)
+  if (DCTM == 2) {
+    // convsamp_float -> float deringing -> jpeg_fdct_float -> quantize_float + the trellis' integer coefficients
+    float wf[64];
     int sum = 0, cnt = 0;
 #pragma unroll
-    for (int i = 0; i < 64; i++) { sum += ws[i]; cnt += (ws[i] >= 127); }
-    if (cnt != 0 && cnt != 64) {
-      int tmp[64];
+    for (int i = 0; i < 64; i++) { wf[i] = (float)ws[i]; sum += ws[i]; cnt += (ws[i] >= 127); }
+    if (dering && cnt != 0 && cnt != 64) deringing_block_float(wf, (int)qt->q[c.qt][0].d >> 3, (float)sum, cnt);
 #pragma unroll
-      for (int i = 0; i < 64; i++) tmp[i] = ws[i];
-      deringing_block(LocalAcc{tmp}, (int)qt->q[c.qt][0].d >> 3, sum, cnt);
+    for (int r = 0; r < 8; r++) fdct_float_1d(wf[8 * r], wf[8 * r + 1], wf[8 * r + 2], wf[8 * r + 3], wf[8 * r + 4], wf[8 * r + 5], wf[8 * r + 6], wf[8 * r + 7]);
 #pragma unroll
-      for (int i = 0; i < 64; i++) ws[i] = tmp[i];
+    for (int col = 0; col < 8; col++) fdct_float_1d(wf[col], wf[8 + col], wf[16 + col], wf[24 + col], wf[32 + col], wf[40 + col], wf[48 + col], wf[56 + col]);
+    const float *fd = qt->fdiv[c.qt];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+      float v = wf[i];
+      v = (float)((double)v / c_aan[i & 7]);               // forward_DCT_float :860-874
+      v = (float)((double)v / c_aan[i >> 3]);
+      ws[i] = (v >= 0.0f) ? (int)((double)v + 0.5) : (int)((double)v - 0.5);
+      int q = (int)(int16_t)(__float2int_rz(wf[i] * fd[i] + 16384.5f) - 16384);     // quantize_float :808-827
+      if (dering) q = max(-1023, min(1023, q));
+      qv[i] = q;
+    }
+  } else {
+    if (dering) {
+      int sum = 0, cnt = 0;
+#pragma unroll
+      for (int i = 0; i < 64; i++) { sum += ws[i]; cnt += (ws[i] >= 127); }
+      if (cnt != 0 && cnt != 64) {
+        int tmp[64];
+#pragma unroll
+        for (int i = 0; i < 64; i++) tmp[i] = ws[i];
+        deringing_block(LocalAcc{tmp}, (int)qt->q[c.qt][0].d >> 3, sum, cnt);
+#pragma unroll
+        for (int i = 0; i < 64; i++) ws[i] = tmp[i];
+      }
+    }
+    if (DCTM == 1) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) fdct_ifast_1d(ws[8 * r], ws[8 * r + 1], ws[8 * r + 2], ws[8 * r + 3], ws[8 * r + 4], ws[8 * r + 5], ws[8 * r + 6], ws[8 * r + 7]);
+#pragma unroll
+      for (int col = 0; col < 8; col++) fdct_ifast_1d(ws[col], ws[8 + col], ws[16 + col], ws[24 + col], ws[32 + col], ws[40 + col], ws[48 + col], ws[56 + col]);
+      const IfastConst *ic = qt->ifast[c.qt];
+#pragma unroll
+      for (int i = 0; i < 64; i++) {
+        const int x = ws[i], sc = c_aanscales[i];
+        const IfastConst k = ic[i];                         // reciprocal quantizer of jcdctmgr.c:611-645 on the scaled divisor
+        const int a = abs(x);
+        int q = (int)(int16_t)(int)(((unsigned long long)(unsigned)(a + (int)k.corr) * k.recip) >> (k.shift + 32));
+        if (x < 0) q = (int)(int16_t)(-q);
+        if (dering) q = max(-1023, min(1023, q));
+        qv[i] = q;
+        ws[i] = (x >= 0) ? (x * 32768 + sc) / (2 * sc) : (x * 32768 - sc) / (2 * sc);     // the trellis' coefficient (jcdctmgr.c:729-746)
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        fdct_1d<0, P1>(ws[8 * r], ws[8 * r + 1], ws[8 * r + 2], ws[8 * r + 3], ws[8 * r + 4], ws[8 * r + 5], ws[8 * r + 6], ws[8 * r + 7]);
+#pragma unroll
+      for (int col = 0; col < 8; col++)
+        fdct_1d<1, P1>(ws[col], ws[8 + col], ws[16 + col], ws[24 + col], ws[32 + col], ws[40 + col], ws[48 + col], ws[56 + col]);
     }
   }
-#pragma unroll
-  for (int r = 0; r < 8; r++)
-    fdct_1d<0>(ws[8 * r], ws[8 * r + 1], ws[8 * r + 2], ws[8 * r + 3], ws[8 * r + 4], ws[8 * r + 5], ws[8 * r + 6], ws[8 * r + 7]);
-#pragma unroll
-  for (int col = 0; col < 8; col++)
-    fdct_1d<1>(ws[col], ws[8 + col], ws[16 + col], ws[24 + col], ws[32 + col], ws[40 + col], ws[48 + col], ws[56 + col]);
-
+  const QuantConst *qc = qt->q[c.qt];
   if (rec) {       // side record for the trellis: norm numerator in natural order (jcdctmgr.c:1026-1029), raw DC, #non-zero ACs
     float norm = 0.0f; unsigned long long mask = 0;
 #pragma unroll
-    for (int i = 1; i < 64; i++) { norm += (float)(ws[i] * ws[i]); if (quant_one(ws[i], qt->q[c.qt][i], dering) != 0u) mask |= 1ull << c_izz[i]; }
+    for (int i = 1; i < 64; i++) {
+      norm += (float)(ws[i] * ws[i]);
+      // the trellis derives its entries from the RAW coefficient (qval = (|x| + q/2) / q, jcdctmgr.c:1136)
+      bool nz;
+      if (DCTM == 0) nz = quant_one(ws[i], qc[i], dering) != 0u;
+      else { const int dq = (int)qc[i].d; nz = abs(ws[i]) >= dq - dq / 2; }
+      if (nz) mask |= 1ull << c_izz[i];
+    }
     DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)ws[0]; rr.nz = (uint8_t)__popcll(mask); rr.pad = 0; rr.nzmask = mask;
     rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)by * c.wib + bx] = rr;
   }
@@ -216,9 +358,8 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
   size_t blk = ((size_t)img * c.hpad + by) * c.wpad + bx;
   uint4 *dq = reinterpret_cast<uint4 *>(c.coef + blk * 64);
   uint4 *dr = reinterpret_cast<uint4 *>(c.raw + blk * 64);
-  const QuantConst *qc = qt->q[c.qt];
   unsigned pq[32], pr[32];
-#define X(k, n) { unsigned qq = quant_one(ws[n], qc[n], dering) & 0xFFFFu, rr = (unsigned)ws[n] & 0xFFFFu; \
+#define X(k, n) { unsigned qq = (DCTM == 0 ? quant_one(ws[n], qc[n], dering) : (unsigned)qv[n]) & 0xFFFFu, rr = (unsigned)ws[n] & 0xFFFFu; \
                   if ((k) & 1) { pq[(k) >> 1] |= qq << 16; pr[(k) >> 1] |= rr << 16; } else { pq[(k) >> 1] = qq; pr[(k) >> 1] = rr; } }
   ZZ_LIST
 #undef X
@@ -329,78 +470,6 @@ __device__ __forceinline__ int quant_fast(int x, uint2 k, int L, int dering)
   return x < 0 ? -q : q;
 }
 
-// ---- JDCT_IFAST (jfdctfst.c:113-224): MULTIPLY = (v * c) >> 8, no rounding ----
-__device__ __forceinline__ void fdct_ifast_1d(int &d0, int &d1, int &d2, int &d3, int &d4, int &d5, int &d6, int &d7)
-{
-  int tmp0 = d0 + d7, tmp7 = d0 - d7, tmp1 = d1 + d6, tmp6 = d1 - d6;
-  int tmp2 = d2 + d5, tmp5 = d2 - d5, tmp3 = d3 + d4, tmp4 = d3 - d4;
-  int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
-  d0 = tmp10 + tmp11; d4 = tmp10 - tmp11;
-  int z1 = ((tmp12 + tmp13) * 181) >> 8;
-  d2 = tmp13 + z1; d6 = tmp13 - z1;
-  tmp10 = tmp4 + tmp5; tmp11 = tmp5 + tmp6; tmp12 = tmp6 + tmp7;
-  int z5 = ((tmp10 - tmp12) * 98) >> 8;
-  int z2 = ((tmp10 * 139) >> 8) + z5;
-  int z4 = ((tmp12 * 334) >> 8) + z5;
-  int z3 = (tmp11 * 181) >> 8;
-  int z11 = tmp7 + z3, z13 = tmp7 - z3;
-  d5 = z13 + z2; d3 = z13 - z2; d1 = z11 + z4; d7 = z11 - z4;
-}
-__constant__ short c_aanscales[64] = {
-  16384, 22725, 21407, 19266, 16384, 12873,  8867,  4520,
-  22725, 31521, 29692, 26722, 22725, 17855, 12299,  6270,
-  21407, 29692, 27969, 25172, 21407, 16819, 11585,  5906,
-  19266, 26722, 25172, 22654, 19266, 15137, 10426,  5315,
-  16384, 22725, 21407, 19266, 16384, 12873,  8867,  4520,
-  12873, 17855, 16819, 15137, 12873, 10114,  6967,  3552,
-   8867, 12299, 11585, 10426,  8867,  6967,  4799,  2446,
-   4520,  6270,  5906,  5315,  4520,  3552,  2446,  1247};
-
-// ---- JDCT_FLOAT (jfdctflt.c:59-167, AA&N): one 1-D pass, fp32, no contraction ----
-__device__ __forceinline__ void fdct_float_1d(float &d0, float &d1, float &d2, float &d3, float &d4, float &d5, float &d6, float &d7)
-{
-  float tmp0 = d0 + d7, tmp7 = d0 - d7, tmp1 = d1 + d6, tmp6 = d1 - d6;
-  float tmp2 = d2 + d5, tmp5 = d2 - d5, tmp3 = d3 + d4, tmp4 = d3 - d4;
-  float tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
-  d0 = tmp10 + tmp11; d4 = tmp10 - tmp11;
-  float z1 = (tmp12 + tmp13) * 0.707106781f;
-  d2 = tmp13 + z1; d6 = tmp13 - z1;
-  tmp10 = tmp4 + tmp5; tmp11 = tmp5 + tmp6; tmp12 = tmp6 + tmp7;
-  float z5 = (tmp10 - tmp12) * 0.382683433f;
-  float z2 = 0.541196100f * tmp10 + z5;
-  float z4 = 1.306562965f * tmp12 + z5;
-  float z3 = tmp11 * 0.707106781f;
-  float z11 = tmp7 + z3, z13 = tmp7 - z3;
-  d5 = z13 + z2; d3 = z13 - z2; d1 = z11 + z4; d7 = z11 - z4;
-}
-// float_preprocess_deringing (jcdctmgr.c:503-575) on 64 floats in natural order; catmull_rom takes DCTELEM (int)
-// values, so the float slopes are truncated on the way in
-__device__ __forceinline__ void deringing_block_float(float *data, int q0, float sum, int cnt)
-{
-  const float maxsample = 127.0f; const int size = 64;
-  const int a = min(31, 2 * q0); const float bq = (maxsample * size - sum) / (float)cnt;
-  const float maxovershoot = maxsample + ((float)a < bq ? (float)a : bq);
-  int n = 0;
-  do {
-    if (data[c_zz[n]] < maxsample) { n++; continue; }
-    int start = n;
-    while (++n < size && data[c_zz[n]] >= maxsample) {}
-    int end = n;
-    float f1 = data[c_zz[start >= 1 ? start - 1 : 0]], f2 = data[c_zz[start >= 2 ? start - 2 : 0]];
-    float l1 = data[c_zz[end < size - 1 ? end : size - 1]], l2 = data[c_zz[end < size - 2 ? end + 1 : size - 1]];
-    float fslope = fmaxf(f1 - f2, maxsample - f1), lslope = fmaxf(l1 - l2, maxsample - l1);
-    if (start == 0) fslope = lslope;
-    if (end == size) lslope = fslope;
-    int length = end - start;
-    float step = 1.f / (float)(length + 1), position = step;
-    for (int i = start; i < end; i++, position += step) {
-      float tmp = catmull_rom((int)(maxsample - fslope), 127, 127, (int)(maxsample - lslope), position, length);
-      data[c_zz[i]] = tmp < maxovershoot ? tmp : maxovershoot;
-    }
-    n++;
-  } while (n < size);
-}
-__constant__ double c_aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0, 0.785694958, 0.541196100, 0.275899379};
 
 // DCTM: 0 = JDCT_ISLOW, 1 = JDCT_IFAST, 2 = JDCT_FLOAT (1 and 2: 8-bit only)
 #ifndef FWD_MASK_SQ
@@ -983,11 +1052,14 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
     LAUNCHED();
     return;
   }
-  if (g.max_coef_bits == 14) { fprintf(stderr, "libb200jpeg: 12-bit input needs one of the tiled layouts\n"); return; }   // refused earlier by the encoder
+  // every other sampling layout (3x2, 4x1, luma-subsampled, RGB pass-through, ...): one thread per block
   int mw = 0, mh = 0;
   for (int ci = 0; ci < g.nc; ci++) { mw = max(mw, g.c[ci].wib); mh = max(mh, g.c[ci].hib); }
   dim3 grid((mw + 127) / 128, mh, n * g.nc);
-  k_forward<<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+  if (g.max_coef_bits == 14) k_forward<12, 0><<<grid, 128, 0, s>>>(g, src, qt, 0, nullptr, rl);
+  else if (dct_method == 2) k_forward<8, 2><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+  else if (dct_method == 1) k_forward<8, 1><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
+  else k_forward<8, 0><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
   LAUNCHED();
 }
 

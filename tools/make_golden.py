@@ -100,6 +100,12 @@ SWITCH_SETS_EXTRA = [
     ["-quality", "75", "-sample", "3x1"],
     ["-baseline", "-quality", "80", "-sample", "2x2,1x1,2x2"],
     ["-baseline", "-sample", "4x1,1x1,2x1", "-quality", "60"],
+    # fast / float DCT on sampling layouts outside the tiled kernel's (the one-thread-per-block forward kernel)
+    ["-baseline", "-quality", "75", "-sample", "3x1", "-dct", "fast"],
+    ["-quality", "80", "-sample", "4x2", "-dct", "float"],
+    ["-fastcrush", "-quality", "75", "-sample", "2x2,1x1,2x2", "-dct", "fast"],
+    ["-baseline", "-quality", "75", "-sample", "3x2", "-dct", "float", "-smooth", "20"],
+    ["-baseline", "-quality", "75", "-rgb", "-dct", "float"],
 ]
 # switches that name files (rdswitch.c read_quant_tables / set_quant_slots / read_scan_script); "@GOLD/" = tests/golden/
 SWITCH_SETS_FILES = [
@@ -132,6 +138,9 @@ SWITCH_SETS_12 = [
     ["-precision", "12", "-quality", "60", "-notrellis", "-noovershoot", "-fastcrush", "-sample", "2x1"],
     ["-precision", "12", "-quality", "75", "-notrellis", "-noovershoot", "-fastcrush", "-restart", "1"],
     ["-precision", "12", "-quality", "100", "-notrellis", "-noovershoot", "-baseline", "-sample", "1x2"],
+    # 12-bit on sampling layouts outside the tiled kernel's
+    ["-precision", "12", "-quality", "75", "-notrellis", "-noovershoot", "-baseline", "-sample", "3x2"],
+    ["-precision", "12", "-quality", "80", "-notrellis", "-noovershoot", "-fastcrush", "-sample", "4x1,1x1,2x1"],
 ]
 SYNTH12 = [(21, 16, 16), (22, 33, 17), (23, 200, 136), (24, 640, 480), (25, 1, 1)]
 SYNTH = [(11, 16, 16), (12, 33, 17), (13, 200, 136), (14, 640, 480), (15, 1, 1), (16, 8, 8), (17, 1920, 1080)]
