@@ -30,7 +30,7 @@ for it in range(cases):
     if prof == "-progressive": sw += ["-revert", "-progressive"] if rng.random() < 0.5 else ["-progressive"]
     elif prof: sw.append(prof)
     if rng.random() < 0.8: sw += ["-quality", str(rng.choice([5, 20, 40, 60, 75, 80, 85, 90, 95, 100]))]
-    if rng.random() < 0.5: sw += ["-sample", rng.choice(["1x1", "2x1", "1x2", "2x2", "3x1", "4x2", "2x2,1x1,2x2"] if not twelve else ["1x1", "2x1", "1x2", "2x2"])]
+    if rng.random() < 0.5: sw += ["-sample", rng.choice(["1x1", "2x1", "1x2", "2x2", "3x1", "4x2", "2x2,1x1,2x2", "4x1,1x1,2x1", "3x2"])]
     if rng.random() < 0.15 and not twelve: sw += ["-grayscale"]
     if rng.random() < 0.25: sw += ["-restart", rng.choice(["1", "2", "3B", "7B", "1B"])]
     if rng.random() < 0.15 and not twelve: sw += ["-dct", rng.choice(["fast", "float"])]
