@@ -217,6 +217,7 @@ __constant__ double c_aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0,
 
 // PREC: 8 or 12 (uint16 samples); DCTM: 0 = JDCT_ISLOW, 1 = JDCT_IFAST, 2 = JDCT_FLOAT (8-bit only), same arithmetic as
 // the tiled kernel's paths.
+__device__ __forceinline__ unsigned qc_d(const QuantTables *__restrict__ qt, int t, int i) { return qt->q[t][i].d; }   // 8 * quantval
 template <int PREC, int DCTM>
 __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restrict__ src,
                                                  const QuantTables *__restrict__ qt, int dering,
@@ -321,13 +322,20 @@ __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restri
 #pragma unroll
       for (int i = 0; i < 64; i++) {
         const int x = ws[i], sc = c_aanscales[i];
-        const IfastConst k = ic[i];                         // reciprocal quantizer of jcdctmgr.c:611-645 on the scaled divisor
         const int a = abs(x);
-        int q = (int)(int16_t)(int)(((unsigned long long)(unsigned)(a + (int)k.corr) * k.recip) >> (k.shift + 32));
+        int q;
+        if (PREC == 8) {
+          const IfastConst k = ic[i];                       // reciprocal quantizer of jcdctmgr.c:611-645 on the scaled divisor
+          q = (int)(int16_t)(int)(((unsigned long long)(unsigned)(a + (int)k.corr) * k.recip) >> (k.shift + 32));
+        } else {
+          // 12-bit build: the scaled divisor stays a JLONG (jcdctmgr.c:332-336) and quantize() divides literally (:646-678)
+          const int d = (int)(((long long)((int)qc_d(qt, c.qt, i) >> 3) * sc + (1 << 10)) >> 11);
+          q = (int)(int16_t)((a + (d >> 1)) / d);
+        }
         if (x < 0) q = (int)(int16_t)(-q);
         if (dering) q = max(-1023, min(1023, q));
         qv[i] = q;
-        ws[i] = (x >= 0) ? (x * 32768 + sc) / (2 * sc) : (x * 32768 - sc) / (2 * sc);     // the trellis' coefficient (jcdctmgr.c:729-746)
+        ws[i] = (int)((x >= 0) ? ((long long)x * 32768 + sc) / (2 * sc) : ((long long)x * 32768 - sc) / (2 * sc));     // the trellis' coefficient (jcdctmgr.c:729-746)
       }
     } else {
 #pragma unroll
@@ -1041,7 +1049,8 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
   bool ycc = g.nc == 3 && (g.raw_in || (g.cs_mode == 0 && (g.in_comps == 3 || g.in_comps == 4))) && g.c[0].h == g.hmax && g.c[0].v == g.vmax &&
              g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
   static const bool force_generic = getenv("B200JPEG_GENERIC_FORWARD") != nullptr;   // A/B switch for debugging
-  if (!force_generic && ((gray && g.hmax == 1 && g.vmax == 1) || ycc)) {
+  // (12-bit samples with the fast / float DCT: the one-thread-per-block kernel only)
+  if (!force_generic && ((gray && g.hmax == 1 && g.vmax == 1) || ycc) && !(g.max_coef_bits == 14 && dct_method != 0)) {
     if (g.max_coef_bits == 14) {                       // 12-bit samples (uint16)
       if (qfast) launch_forward_tile<true, 12, 0>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
       else launch_forward_tile<false, 12, 0>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
@@ -1056,7 +1065,11 @@ void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, in
   int mw = 0, mh = 0;
   for (int ci = 0; ci < g.nc; ci++) { mw = max(mw, g.c[ci].wib); mh = max(mh, g.c[ci].hib); }
   dim3 grid((mw + 127) / 128, mh, n * g.nc);
-  if (g.max_coef_bits == 14) k_forward<12, 0><<<grid, 128, 0, s>>>(g, src, qt, 0, nullptr, rl);
+  if (g.max_coef_bits == 14) {
+    if (dct_method == 2) k_forward<12, 2><<<grid, 128, 0, s>>>(g, src, qt, 0, nullptr, rl);
+    else if (dct_method == 1) k_forward<12, 1><<<grid, 128, 0, s>>>(g, src, qt, 0, nullptr, rl);
+    else k_forward<12, 0><<<grid, 128, 0, s>>>(g, src, qt, 0, nullptr, rl);
+  }
   else if (dct_method == 2) k_forward<8, 2><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
   else if (dct_method == 1) k_forward<8, 1><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);
   else k_forward<8, 0><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl);

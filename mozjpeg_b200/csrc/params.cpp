@@ -286,7 +286,6 @@ int b200jpeg_validate(const b200jpeg_params *p) {
   // things the reference can do that the device path cannot (yet)
   if (p->restart_interval < 0 || p->restart_interval > 65535 || p->restart_in_rows < 0) { set_error("restart interval out of range"); return B200JPEG_ERR_PARAM; }
   if (p->dct_method < B200JPEG_DCT_ISLOW || p->dct_method > B200JPEG_DCT_FLOAT) { set_error("unknown dct_method %d", p->dct_method); return B200JPEG_ERR_PARAM; }
-  if (p->dct_method != B200JPEG_DCT_ISLOW && p->data_precision != 8) { set_error("dct_method %d at %d bits is not on the device path (JDCT_IFAST / JDCT_FLOAT: 8 bits only)", p->dct_method, p->data_precision); return B200JPEG_ERR_UNSUPPORTED; }
   if (p->smoothing_factor < 0 || p->smoothing_factor > 100) { set_error("smoothing_factor %d out of range 0..100", p->smoothing_factor); return B200JPEG_ERR_PARAM; }
   if (p->trellis_quant && p->use_scans_in_trellis && (p->trellis_freq_split < 1 || p->trellis_freq_split > 62)) { set_error("trellis_freq_split %d: the device path takes 1..62 with use_scans_in_trellis", p->trellis_freq_split); return B200JPEG_ERR_UNSUPPORTED; }
   if (p->trellis_num_loops < 1 || p->trellis_num_loops > 16) { set_error("trellis_num_loops %d: the device path takes 1..16", p->trellis_num_loops); return B200JPEG_ERR_UNSUPPORTED; }

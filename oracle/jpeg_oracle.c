@@ -312,9 +312,21 @@ static void forward_block_ifast(const b200jpeg_params *p, int *ws, const uint16_
   for (i = 0; i < 8; i++) fdct_ifast_1d(ws + 8 * i, 1);
   for (i = 0; i < 8; i++) fdct_ifast_1d(ws + i, 8);
   for (i = 0; i < 64; i++) {                                   /* :729-746 */
-    int x = ws[i], sc = aanscales_ifast[i];
+    long x = ws[i], sc = aanscales_ifast[i];
     x = (x >= 0) ? (x * 32768 + sc) / (2 * sc) : (x * 32768 - sc) / (2 * sc);
     dr[i] = (int16_t)x;
+  }
+  if (p->data_precision != 8) {
+    /* 12-bit build (BITS_IN_JSAMPLE != 8): the scaled divisor is kept as a DCTELEM = JLONG (jcdctmgr.c:332-336, no
+     * reciprocal, no UINT16 truncation) and quantize() divides literally (:646-678) */
+    for (i = 0; i < 64; i++) {
+      long d = ((long)q[i] * aanscales_ifast[i] + (1L << 10)) >> 11;
+      long temp = ws[i], v;
+      if (temp < 0) { temp = -temp; temp += d >> 1; v = temp >= d ? -(temp / d) : 0; }
+      else { temp += d >> 1; v = temp >= d ? temp / d : 0; }
+      dq[i] = (int16_t)v;
+    }
+    return;
   }
   for (i = 0; i < 64; i++) {                                   /* quantize :611-645 */
     unsigned recip, corr; int shift, temp = ws[i], v;
@@ -1186,8 +1198,7 @@ int orc_encode(const b200jpeg_params *p, const uint8_t *pixels, size_t row_pitch
   e->raw_planes = g_raw_planes; e->raw_pitch = g_raw_pitch;
   /* 12-bit: no JBUF_REQUANT => no trellis (jccoefct.c:132-138); deringing is not usable at 12 bits (jcdctmgr.c:419) */
   if (p->data_precision == 12 && !g_coef_planes && (p->trellis_quant || p->overshoot_deringing)) { free(t); return B200JPEG_ERR_UNSUPPORTED; }   /* (no forward stage when transcoding) */
-  if ((p->data_precision != 8 && p->data_precision != 12) || (p->dct_method != B200JPEG_DCT_ISLOW && p->data_precision != 8) ||
-      p->trellis_num_loops < 1) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
+  if ((p->data_precision != 8 && p->data_precision != 12) || p->trellis_num_loops < 1) { free(t); return B200JPEG_ERR_UNSUPPORTED; }
   e->hmax = e->vmax = 1;
   for (ci = 0; ci < e->nc; ci++) { if (p->comp_info[ci].h_samp_factor > e->hmax) e->hmax = p->comp_info[ci].h_samp_factor; if (p->comp_info[ci].v_samp_factor > e->vmax) e->vmax = p->comp_info[ci].v_samp_factor; }
   e->mcus_per_row = (e->W + e->hmax * 8 - 1) / (e->hmax * 8); e->mcu_rows = (e->H + e->vmax * 8 - 1) / (e->vmax * 8);

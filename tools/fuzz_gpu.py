@@ -33,7 +33,7 @@ for it in range(cases):
     if rng.random() < 0.5: sw += ["-sample", rng.choice(["1x1", "2x1", "1x2", "2x2", "3x1", "4x2", "2x2,1x1,2x2", "4x1,1x1,2x1", "3x2"])]
     if rng.random() < 0.15 and not twelve: sw += ["-grayscale"]
     if rng.random() < 0.25: sw += ["-restart", rng.choice(["1", "2", "3B", "7B", "1B"])]
-    if rng.random() < 0.15 and not twelve: sw += ["-dct", rng.choice(["fast", "float"])]
+    if rng.random() < 0.15: sw += ["-dct", rng.choice(["fast", "float"])]
     if rng.random() < 0.1: sw += ["-smooth", str(rng.choice([1, 10, 50, 100]))]
     if twelve: sw = ["-precision", "12", "-notrellis", "-noovershoot"] + sw
     elif rng.random() < 0.15: sw += [rng.choice(["-notrellis", "-notrellis-dc", "-noovershoot", "-optimize"])]
