@@ -215,8 +215,8 @@ __device__ __forceinline__ void deringing_block_float(float *data, int q0, float
 }
 __constant__ double c_aan[8] = {1.0, 1.387039845, 1.306562965, 1.175875602, 1.0, 0.785694958, 0.541196100, 0.275899379};
 
-// PREC: 8 or 12 (uint16 samples); DCTM: 0 = JDCT_ISLOW, 1 = JDCT_IFAST, 2 = JDCT_FLOAT (8-bit only), same arithmetic as
-// the tiled kernel's paths.
+// PREC: 8 or 12 (uint16 samples); DCTM: 0 = JDCT_ISLOW, 1 = JDCT_IFAST, 2 = JDCT_FLOAT; same arithmetic as the tiled
+// kernel's paths, plus the 12-bit forms of the fast and the float DCT.
 __device__ __forceinline__ unsigned qc_d(const QuantTables *__restrict__ qt, int t, int i) { return qt->q[t][i].d; }   // 8 * quantval
 template <int PREC, int DCTM>
 __global__ void __launch_bounds__(128) k_forward(Geom g, const uint8_t *__restrict__ src,
@@ -479,7 +479,7 @@ __device__ __forceinline__ int quant_fast(int x, uint2 k, int L, int dering)
 }
 
 
-// DCTM: 0 = JDCT_ISLOW, 1 = JDCT_IFAST, 2 = JDCT_FLOAT (1 and 2: 8-bit only)
+// DCTM: 0 = JDCT_ISLOW, 1 = JDCT_IFAST, 2 = JDCT_FLOAT (1 and 2: 8-bit only in this kernel; 12-bit: k_forward)
 #ifndef FWD_MASK_SQ
 #define FWD_MASK_SQ 1
 #endif
