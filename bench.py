@@ -408,10 +408,16 @@ def main():
     numa = bind_to_gpu_numa_node(local)                # before the pinned buffers are allocated (first touch)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # keep stdout to the one JSON line: NCCL writes its version banner (and, with NCCL_DEBUG=INFO, its log) to the
+        # process's stdout when the communicator comes up, so file descriptor 1 points at stderr until it has
+        sys.stdout.flush()
+        saved_fd = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1); os.close(saved_fd)
     dev = torch.device("cuda", local)
     W, H = a.width, a.height
     # weak scaling: every rank encodes its own full batch; strong (cfg4): the batch is split over the ranks
