@@ -77,10 +77,10 @@ using namespace b200;
 struct Arena {
   b200::DevBuf d_planes;             // input smoothing: the pre-pass's component planes
   b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_srec, d_splits, d_best_al, d_qimg, d_qsum, d_eo, d_es;
-  b200::DevBuf d_blk_bits, d_tile_bits, d_tile_base, d_seg_corr, d_mark, d_ff_tile, d_blk_aux, d_blk_run, d_total_bits, d_bitbuf;
+  b200::DevBuf d_blk_bits, d_tile_bits, d_tile_base, d_seg_corr, d_mark, d_ff_tile, d_blk_aux, d_blk_run, d_blk_mask, d_total_bits, d_bitbuf;
   b200::Geom g;                      // the plan's geometry with this arena's coefficient pointers
   void release() {
-    b200::DevBuf *db[] = {&d_planes, &d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_srec, &d_splits, &d_best_al, &d_qimg, &d_qsum, &d_eo, &d_es, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_total_bits, &d_bitbuf};
+    b200::DevBuf *db[] = {&d_planes, &d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_srec, &d_splits, &d_best_al, &d_qimg, &d_qsum, &d_eo, &d_es, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_blk_mask, &d_total_bits, &d_bitbuf};
     for (b200::DevBuf *b : db) b->release();
     for (int i = 0; i < 4; i++) { d_coef[i].release(); d_raw[i].release(); d_plain[i].release(); }
   }
@@ -397,7 +397,7 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
       if ((rc = a.d_es.reserve((size_t)n * pl.sum_real_blocks * 16))) return rc;
     }
     if ((rc = a.d_blk_bits.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc;
-    if (pl.progressive) { if ((rc = a.d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = a.d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; }
+    if (pl.progressive) { if ((rc = a.d_blk_aux.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = a.d_blk_run.reserve((size_t)n * pl.max_scan_blocks * 4))) return rc; if ((rc = a.d_blk_mask.reserve((size_t)n * pl.max_scan_blocks * 24))) return rc; }
     if ((rc = a.d_total_bits.reserve((size_t)n * 8))) return rc;
     if ((rc = a.d_tile_bits.reserve((size_t)n * ((pl.max_scan_blocks + 255) / 256) * 4))) return rc;
     if ((rc = a.d_tile_base.reserve((size_t)n * ((pl.max_scan_blocks + 255) / 256) * 8))) return rc;
@@ -532,8 +532,8 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
         tm.mark("trellis_stats");
         CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
         launch_seed_hist(A.d_hist.as<uint32_t>(), 4 + gr.c[ci].ac_tbl, n, s);
-        launch_prog_prepare(gr, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), A.d_tile_bits.as<int>(), A.d_tile_base.as<int>(), n, s);
-        launch_gather_prog(gr, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), A.d_hist.as<uint32_t>(), status, n, s);
+        launch_prog_prepare(gr, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), A.d_blk_mask.as<unsigned long long>(), A.d_tile_bits.as<int>(), A.d_tile_base.as<int>(), n, s);
+        launch_gather_prog(gr, ts, A.d_blk_aux.as<uint32_t>(), A.d_blk_run.as<uint32_t>(), A.d_blk_mask.as<unsigned long long>(), A.d_hist.as<uint32_t>(), status, n, s);
         tm.mark("trellis_tables");
         SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = 1u << (4 + gr.c[ci].ac_tbl);
         launch_gen_tables(A.d_hist.as<uint32_t>(), tset + (size_t)ci * HIST_SLOTS, tabset * gr.nc, masks, n, s);
@@ -617,14 +617,15 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     const DevHuff *tabs; size_t tstride;
     const bool dc_refine = pl.progressive && sd.Ss == 0 && sd.Ah != 0;
     uint32_t *aux = A.d_blk_aux.as<uint32_t>(), *run_e = A.d_blk_run.as<uint32_t>();
-    if (pl.progressive && sd.Ss != 0) { tm.mark("eobrun_runs"); launch_prog_prepare(g, sd, aux, run_e, A.d_tile_bits.as<int>(), A.d_tile_base.as<int>(), n, s); }
+    unsigned long long *pm = A.d_blk_mask.as<unsigned long long>();
+    if (pl.progressive && sd.Ss != 0) { tm.mark("eobrun_runs"); launch_prog_prepare(g, sd, aux, run_e, pm, A.d_tile_bits.as<int>(), A.d_tile_base.as<int>(), n, s); }
     if (pl.optimize) {
       DevHuff *tset = io.tabs_scan + (size_t)si * HIST_SLOTS;                              // [img][scan][8]
       tstride = tabset * nscans;
       if (!dc_refine) {                                                                    // jcmaster.c:650-662
         tm.mark("scan_stats");
         CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
-        if (pl.progressive) launch_gather_prog(g, sd, aux, run_e, A.d_hist.as<uint32_t>(), status, n, s);
+        if (pl.progressive) launch_gather_prog(g, sd, aux, run_e, pm, A.d_hist.as<uint32_t>(), status, n, s);
         else launch_gather_seq(g, sd, nz_rec, rl, A.d_hist.as<uint32_t>(), status, n, s);
         tm.mark("scan_tables");
         SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = scan_slot_mask(pl, sd);
@@ -634,7 +635,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     } else { tabs = e->d_tabs_fixed.as<DevHuff>(); tstride = 0; }
     const size_t mark_words = (e->bitbuf_words_per_image * 4 / 8 + 64) / 4;
     tm.mark("block_bits");
-    launch_block_bits(g, sd, nz_rec, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), aux, run_e, status, n, s);
+    launch_block_bits(g, sd, nz_rec, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), aux, run_e, pm, status, n, s);
     tm.mark("scan_layout");
     launch_scan_layout(sd, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
                        A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, A.d_total_bits.as<unsigned long long>(),
@@ -643,7 +644,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     CU(cudaMemsetAsync(A.d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
     if (sd.ri) CU(cudaMemsetAsync(A.d_mark.p, 0, mark_words * 4 * n, s));
     launch_encode(g, sd, nz_rec, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
-                  A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, aux, run_e,
+                  A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, aux, run_e, pm,
                   A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_mark.as<uint32_t>(), mark_words, status, n, s);
     tm.mark("stuff");
     launch_stuff(A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_total_bits.as<unsigned long long>(), A.d_ff_tile.as<uint32_t>(),

@@ -2836,50 +2836,66 @@ __global__ void __launch_bounds__(STUFF_THREADS) k_stuff_write(const uint32_t *_
 #define AUX_BRK 1u
 #define AUX_CONTRIB 2u
 
-// the block's coefficients of the band [Ss, Se] (zigzag positions; the other entries read as 0): only the 16-byte
-// pieces of the 128-byte block that the band touches are fetched -- a 1..8 scan moves one 32-byte sector per block
-__device__ __forceinline__ void load_block64(const int16_t *__restrict__ blk, int *v, int Ss = 0, int Se = 63)
-{
-  const uint4 *b4 = reinterpret_cast<const uint4 *>(blk);
-#pragma unroll
-  for (int q = 0; q < 8; q++) {
-    uint4 a = make_uint4(0, 0, 0, 0);
-    if (8 * q + 7 >= Ss && 8 * q <= Se) a = b4[q];
-    unsigned w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-    for (int j = 0; j < 8; j++) v[8 * q + j] = (int)(int16_t)((w[j >> 1] >> ((j & 1) * 16)) & 0xFFFF);
-  }
-}
-
+// Per block of an AC scan, three 64-bit position masks (bit i = zigzag position i, only positions of the band):
+//   ev  : the coefficient is an event of the scan -- (|v| >> Al) != 0
+//   one : refinement scans, (|v| >> Al) == 1 (newly nonzero: run symbol + sign bit)
+//   bit : refinement scans, the bit the event sends -- sign for a 'one' (1 = positive, jcphuff.c:983), else the
+//         correction bit (|v| >> Al) & 1
+// kept in three planes [plane][img][block] so that the three symbol walks of the scan (statistics, bit counts, bit
+// emission) visit only the events instead of all 63 positions.  Only the 16-byte pieces of the 128-byte block that
+// the band touches are fetched -- a 1..8 scan moves one 32-byte sector per block.
 __global__ void __launch_bounds__(256) k_prog_flags(Geom g, ScanDesc sd, uint32_t *__restrict__ aux, uint32_t *__restrict__ run_e,
-                                                    int *__restrict__ tile_last, int *__restrict__ tile_first)
+                                                    unsigned long long *__restrict__ pm, int *__restrict__ tile_last, int *__restrict__ tile_first)
 {
   __shared__ int smax[8], smin[8];
   int img = blockIdx.y;
-  if (sd.al_img) sd.Al = sd.al_img[img];                 // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
+  const int Al = sd.al_img ? sd.al_img[img] : sd.Al;     // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int bmax = -1, bmin = 0x7fffffff;
   if (t < sd.nblocks) {
     int sci, k; long long mcu;
     const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
-    int v[64];
-    load_block64(blk, v, sd.Ss, sd.Se);
-    unsigned brk = 0, contrib, tail = 0;
-    if (sd.Ah == 0) {
-      int lastnz = 0;
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(blk);
+    unsigned evl = 0, evh = 0, onel = 0, oneh = 0, bitl = 0, bith = 0;
+    const bool refine = sd.Ah != 0;
 #pragma unroll
-      for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && (abs(v[i]) >> sd.Al) != 0) { brk = 1; lastnz = i; }
-      contrib = (lastnz != sd.Se);
-    } else {
-      int lastone = 0;
+    for (int q = 0; q < 8; q++) {
+      if (!(8 * q + 7 >= sd.Ss && 8 * q <= sd.Se)) continue;
+      const uint4 a = b4[q];
+      const unsigned w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && (abs(v[i]) >> sd.Al) == 1) { brk = 1; lastone = i; }
-#pragma unroll
-      for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && i > lastone && (abs(v[i]) >> sd.Al) > 1) tail++;
-      contrib = (lastone != sd.Se);
+      for (int j = 0; j < 8; j++) {
+        const int i = 8 * q + j;
+        const int v = (j & 1) ? (int)w[j >> 1] >> 16 : (int)(short)(w[j >> 1] & 0xFFFF);
+        const int sft = abs(v) >> Al;
+        const unsigned m = 1u << (i & 31);
+        unsigned &ev = i < 32 ? evl : evh, &one = i < 32 ? onel : oneh, &bit = i < 32 ? bitl : bith;
+        if (sft != 0) ev |= m;
+        if (refine) {
+          if (sft == 1) one |= m;
+          if (sft == 1 ? v >= 0 : (sft & 1)) bit |= m;
+        }
+      }
     }
-    aux[(size_t)img * sd.nblocks + t] = brk | (contrib << 1) | (tail << 2);
-    run_e[(size_t)img * sd.nblocks + t] = 0;
+    const unsigned long long band = (sd.Se == 63 ? ~0ull : ((1ull << (sd.Se + 1)) - 1)) & ~((1ull << sd.Ss) - 1);
+    const unsigned long long ev = (((unsigned long long)evh << 32) | evl) & band;
+    const unsigned long long one = (((unsigned long long)oneh << 32) | onel) & ev;
+    const unsigned long long bit = (((unsigned long long)bith << 32) | bitl) & ev;
+    unsigned brk, contrib, tail = 0;
+    if (!refine) {
+      brk = ev != 0;
+      contrib = !brk || (63 - __clzll((long long)ev)) != sd.Se;
+    } else {
+      brk = one != 0;
+      const int lastone = brk ? 63 - __clzll((long long)one) : 0;
+      tail = __popcll(ev & ~one & ~((2ull << lastone) - 1));         // correction bits after the last newly-nonzero coefficient
+      contrib = lastone != sd.Se;
+    }
+    const size_t plane = (size_t)gridDim.y * sd.nblocks, at = (size_t)img * sd.nblocks + t;
+    pm[at] = ev;
+    if (refine) { pm[plane + at] = one; pm[2 * plane + at] = bit; }
+    aux[at] = brk | (contrib << 1) | (tail << 2);
+    run_e[at] = 0;
     if (brk || t == 0 || (sd.ri && t % sd.ri == 0)) bmax = bmin = (int)t;
   }
   for (int o = 16; o; o >>= 1) { bmax = max(bmax, __shfl_xor_sync(0xffffffffu, bmax, o)); bmin = min(bmin, __shfl_xor_sync(0xffffffffu, bmin, o)); }
@@ -2994,13 +3010,22 @@ __global__ void __launch_bounds__(256) k_prog_runs(ScanDesc sd, const uint32_t *
 }
 
 // One block of a progressive scan, in stream order.  Sink: dc(nbits, bits),
-// ac(symbol, nbits, bits), raw(bits, n).
+// ac(symbol, nbits, bits), raw(bits, n).  AC scans walk the block's event masks (k_prog_flags): the zero runs are the
+// gaps between consecutive events, and a first scan fetches only the coefficients it codes.
 template <class Sink>
-__device__ __forceinline__ void walk_prog_block(const int16_t *__restrict__ blk, const ScanDesc &sd, int last_dc_shifted,
-                                                unsigned aux, unsigned runE, Sink &sink)
+__device__ __forceinline__ void flush_corrections(Sink &sink, unsigned long long &br, int &nbr)
+{
+  if (nbr > 32) sink.raw((unsigned)(br >> 32), nbr - 32);
+  if (nbr) sink.raw((unsigned)br, nbr > 32 ? 32 : nbr);
+  br = 0; nbr = 0;
+}
+template <class Sink>
+__device__ __forceinline__ void walk_prog_block(const int16_t *__restrict__ blk, const ScanDesc &sd, const int Al, int last_dc_shifted,
+                                                unsigned aux, unsigned runE, unsigned long long ev, unsigned long long one,
+                                                unsigned long long bit, Sink &sink)
 {
   if (sd.Ss == 0) {
-    int dc = (int)blk[0] >> sd.Al;                       // arithmetic shift (jcphuff.c:497)
+    int dc = (int)blk[0] >> Al;                       // arithmetic shift (jcphuff.c:497)
     if (sd.Ah == 0) {                                    // encode_mcu_DC_first :468-548
       int temp = dc - last_dc_shifted, temp2 = temp;
       if (temp < 0) { temp = -temp; temp2--; }
@@ -3008,63 +3033,49 @@ __device__ __forceinline__ void walk_prog_block(const int16_t *__restrict__ blk,
     } else sink.raw((unsigned)dc & 1u, 1);               // encode_mcu_DC_refine :746-786
     return;
   }
-  int v[64];
-  load_block64(blk, v);       // (band-limited or skipped loads were measured slower here: these walks are instruction-bound)
   if (sd.Ah == 0) {                                      // encode_mcu_AC_first :648-737
-    if (aux & AUX_BRK) {
-      int r = 0;
-#pragma unroll
-      for (int i = 1; i < 64; i++) {
-        if (i < sd.Ss || i > sd.Se) continue;
-        int temp = v[i], temp2 = temp >> 31;
-        temp = (temp ^ temp2) - temp2; temp >>= sd.Al;
-        if (temp == 0) { r++; continue; }
-        temp2 ^= temp;
-        while (r > 15) { sink.ac(0xF0, 0, 0); r -= 16; }
-        int nb = nbits_of(temp);
-        sink.ac((r << 4) + nb, nb, temp2);
-        r = 0;
-      }
+    int prev = sd.Ss - 1;
+    while (ev) {                                         // ev != 0 <=> the block breaks the pending EOB run
+      const int i = __ffsll((long long)ev) - 1;
+      ev &= ev - 1;
+      int r = i - prev - 1; prev = i;
+      int temp = blk[i], temp2 = temp >> 31;
+      temp = (temp ^ temp2) - temp2; temp >>= Al;
+      temp2 ^= temp;
+      while (r > 15) { sink.ac(0xF0, 0, 0); r -= 16; }
+      int nb = nbits_of(temp);
+      sink.ac((r << 4) + nb, nb, temp2);
     }
-  } else {                                               // encode_mcu_AC_refine :817-1017
-    unsigned long long br = 0; int nbr = 0;
-    if (aux & AUX_BRK) {
-      int EOB = 0;
-#pragma unroll
-      for (int i = 1; i < 64; i++) if (i >= sd.Ss && i <= sd.Se && (abs(v[i]) >> sd.Al) == 1) EOB = i;
-      int r = 0;
-#pragma unroll
-      for (int i = 1; i < 64; i++) {
-        if (i < sd.Ss || i > sd.Se) continue;
-        int a = abs(v[i]) >> sd.Al;
-        if (a == 0) { r++; continue; }
-        while (r > 15 && i <= EOB) {
-          sink.ac(0xF0, 0, 0); r -= 16;
-          if (nbr > 32) sink.raw((unsigned)(br >> 32), nbr - 32);
-          if (nbr) sink.raw((unsigned)br, nbr > 32 ? 32 : nbr);
-          br = 0; nbr = 0;
-        }
-        if (a > 1) { br = (br << 1) | (unsigned)(a & 1); nbr++; continue; }
-        sink.ac((r << 4) + 1, 0, 0);
-        sink.raw(v[i] < 0 ? 0u : 1u, 1);
-        if (nbr > 32) sink.raw((unsigned)(br >> 32), nbr - 32);
-        if (nbr) sink.raw((unsigned)br, nbr > 32 ? 32 : nbr);
-        br = 0; nbr = 0; r = 0;
-      }
-    } else {
-#pragma unroll
-      for (int i = 1; i < 64; i++) { if (i < sd.Ss || i > sd.Se) continue; int a = abs(v[i]) >> sd.Al; if (a > 1) { br = (br << 1) | (unsigned)(a & 1); nbr++; } }
-    }
-    // the EOBRUN symbol this block owns, then this block's tail correction bits
-    if (runE) { int nb = nbits_of((int)runE) - 1; sink.ac(nb << 4, nb, (int)runE); }
-    if (nbr > 32) sink.raw((unsigned)(br >> 32), nbr - 32);
-    if (nbr) sink.raw((unsigned)br, nbr > 32 ? 32 : nbr);
+    if (runE) { int nb = nbits_of((int)runE) - 1; sink.ac(nb << 4, nb, (int)runE); }   // emit_eobrun :409-431
     return;
   }
-  if (runE) { int nb = nbits_of((int)runE) - 1; sink.ac(nb << 4, nb, (int)runE); }   // emit_eobrun :409-431
+  // encode_mcu_AC_refine :817-1017
+  unsigned long long br = 0; int nbr = 0;
+  if (aux & AUX_BRK) {
+    const int EOB = 63 - __clzll((long long)one);
+    int prev = sd.Ss - 1, r = 0;
+    while (ev) {
+      const int i = __ffsll((long long)ev) - 1;
+      ev &= ev - 1;
+      r += i - prev - 1; prev = i;
+      const unsigned b = (unsigned)(bit >> i) & 1u;
+      while (r > 15 && i <= EOB) { sink.ac(0xF0, 0, 0); r -= 16; flush_corrections(sink, br, nbr); }
+      if (!((one >> i) & 1)) { br = (br << 1) | b; nbr++; continue; }
+      sink.ac((r << 4) + 1, 0, 0);
+      sink.raw(b, 1);
+      flush_corrections(sink, br, nbr);
+      r = 0;
+    }
+  } else {
+    nbr = __popcll(ev);
+    while (ev) { const int i = __ffsll((long long)ev) - 1; ev &= ev - 1; br = (br << 1) | ((unsigned)(bit >> i) & 1u); }
+  }
+  // the EOBRUN symbol this block owns, then this block's tail correction bits
+  if (runE) { int nb = nbits_of((int)runE) - 1; sink.ac(nb << 4, nb, (int)runE); }
+  flush_corrections(sink, br, nbr);
 }
 
-__device__ __forceinline__ int prev_dc_shifted(const Geom &g, const ScanDesc &sd, int img, long long t, int sci, long long mcu, int k)
+__device__ __forceinline__ int prev_dc_shifted(const Geom &g, const ScanDesc &sd, const int Al, int img, long long t, int sci, long long mcu, int k)
 {
   if (sd.Ss != 0 || sd.Ah != 0) return 0;
   long long tp;
@@ -3073,7 +3084,16 @@ __device__ __forceinline__ int prev_dc_shifted(const Geom &g, const ScanDesc &sd
   else return 0;
   int s2, k2; long long m2;
   const int16_t *p = block_ptr(g, sd, img, tp, s2, m2, k2);
-  return (int)p[0] >> sd.Al;
+  return (int)p[0] >> Al;
+}
+
+__device__ __forceinline__ void load_prog_aux(const ScanDesc &sd, const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
+                                              const unsigned long long *__restrict__ pm, int img, long long t, unsigned &a, unsigned &re,
+                                              unsigned long long &ev, unsigned long long &one, unsigned long long &bit)
+{
+  const size_t plane = (size_t)gridDim.y * sd.nblocks, at = (size_t)img * sd.nblocks + t;
+  a = aux[at]; re = run_e[at]; ev = pm[at];
+  if (sd.Ah != 0) { one = pm[plane + at]; bit = pm[2 * plane + at]; }
 }
 
 struct HistSinkP {
@@ -3093,22 +3113,23 @@ struct BitSinkP : BitSink {
 };
 
 __global__ void __launch_bounds__(256) k_gather_prog(Geom g, ScanDesc sd, const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
-                                                     uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
+                                                     const unsigned long long *__restrict__ pm, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
 {
   __shared__ unsigned sh[HIST_SLOTS * HIST_BINS];
   int img = blockIdx.y;
-  if (sd.al_img) sd.Al = sd.al_img[img];                 // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
+  const int Al = sd.al_img ? sd.al_img[img] : sd.Al;     // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
   for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < sd.nblocks) {
     int sci, k; long long mcu;
     const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
-    int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
+    int last = prev_dc_shifted(g, sd, Al, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
     HistSinkP sink{sh + c.dc_tbl * HIST_BINS, sh + (4 + c.ac_tbl) * HIST_BINS, 0, g.max_coef_bits};
-    unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
-    walk_prog_block(blk, sd, last, a, re, sink);
+    unsigned a = 0, re = 0; unsigned long long ev = 0, one = 0, bit = 0;
+    if (sd.Ss) load_prog_aux(sd, aux, run_e, pm, img, t, a, re, ev, one, bit);
+    walk_prog_block(blk, sd, Al, last, a, re, ev, one, bit, sink);
     if (sink.bad) atomicOr(&status[img], 2u);
   }
   __syncthreads();
@@ -3118,12 +3139,12 @@ __global__ void __launch_bounds__(256) k_gather_prog(Geom g, ScanDesc sd, const 
 
 __global__ void __launch_bounds__(256) k_block_bits_prog(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
                                                          const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
-                                                         uint32_t *__restrict__ blk_bits, uint32_t *__restrict__ tile_bits, uint32_t *__restrict__ status)
+                                                         const unsigned long long *__restrict__ pm, uint32_t *__restrict__ blk_bits, uint32_t *__restrict__ tile_bits, uint32_t *__restrict__ status)
 {
   __shared__ ScanTables st;
   __shared__ unsigned ws[8];
   int img = blockIdx.y;
-  if (sd.al_img) sd.Al = sd.al_img[img];                 // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
+  const int Al = sd.al_img ? sd.al_img[img] : sd.Al;     // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
   if (!(sd.Ss == 0 && sd.Ah != 0)) load_scan_tables(st, tabs, stride, img, g, sd, false);
   __syncthreads();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -3131,11 +3152,12 @@ __global__ void __launch_bounds__(256) k_block_bits_prog(Geom g, ScanDesc sd, co
   if (t < sd.nblocks) {
     int sci, k; long long mcu;
     const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
-    int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
+    int last = prev_dc_shifted(g, sd, Al, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
     CountSinkP sink{st.size[c.dc_tbl], st.size[4 + c.ac_tbl], 0u, 0};
-    unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
-    walk_prog_block(blk, sd, last, a, re, sink);
+    unsigned a = 0, re = 0; unsigned long long ev = 0, one = 0, bit = 0;
+    if (sd.Ss) load_prog_aux(sd, aux, run_e, pm, img, t, a, re, ev, one, bit);
+    walk_prog_block(blk, sd, Al, last, a, re, ev, one, bit, sink);
     if (sink.bad) atomicOr(&status[img], 2u);
     bits = sink.bits;
   }
@@ -3147,6 +3169,7 @@ __global__ void __launch_bounds__(256) k_block_bits_prog(Geom g, ScanDesc sd, co
 
 __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
                                                      const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
+                                                     const unsigned long long *__restrict__ pm,
                                                      const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits /* per-tile totals: not read here */,
                                                      const unsigned long long *__restrict__ tile_base,
                                                      const uint32_t *__restrict__ seg_corr, long long seg_stride,
@@ -3155,7 +3178,7 @@ __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const 
 {
   __shared__ ScanTables st;
   int img = blockIdx.y;
-  if (sd.al_img) sd.Al = sd.al_img[img];                 // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
+  const int Al = sd.al_img ? sd.al_img[img] : sd.Al;     // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
   if (!(sd.Ss == 0 && sd.Ah != 0)) load_scan_tables(st, tabs, stride, img, g, sd, true);
   __syncthreads();
   if (status[img] & ~1u) return;
@@ -3167,13 +3190,14 @@ __global__ void __launch_bounds__(256) k_encode_prog(Geom g, ScanDesc sd, const 
     if (sd.ri) off += seg_corr[(size_t)img * seg_stride + t / ((long long)sd.ri * sd.bim)];
     int sci, k; long long mcu;
     const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
-    int last = prev_dc_shifted(g, sd, img, t, sci, mcu, k);
+    int last = prev_dc_shifted(g, sd, Al, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
     BitSinkP sink;
     sink.buf = gbuf; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
     sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
-    unsigned a = sd.Ss ? aux[(size_t)img * sd.nblocks + t] : 0, re = sd.Ss ? run_e[(size_t)img * sd.nblocks + t] : 0;
-    walk_prog_block(blk, sd, last, a, re, sink);
+    unsigned a = 0, re = 0; unsigned long long ev = 0, one = 0, bit = 0;
+    if (sd.Ss) load_prog_aux(sd, aux, run_e, pm, img, t, a, re, ev, one, bit);
+    walk_prog_block(blk, sd, Al, last, a, re, ev, one, bit, sink);
     if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
     sink.finish();
   }
@@ -3228,27 +3252,27 @@ void launch_select_al(const Geom &g, const AlSearch &as, const DevHuff *tabs_sca
   LAUNCHED();
 }
 
-void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int *tile_last, int *tile_first, int n, cudaStream_t s)
+void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, unsigned long long *pm, int *tile_last, int *tile_first, int n, cudaStream_t s)
 {
   if (sd.Ss == 0) return;
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  k_prog_flags<<<grid, 256, 0, s>>>(g, sd, aux, run_e, tile_last, tile_first); LAUNCHED();
+  k_prog_flags<<<grid, 256, 0, s>>>(g, sd, aux, run_e, pm, tile_last, tile_first); LAUNCHED();
   if (sd.Ah == 0) {
     k_prog_tile_scan<<<n, 256, 0, s>>>((int)grid.x, tile_last, tile_first); LAUNCHED();
     k_prog_runs_first<<<grid, 256, 0, s>>>(sd, aux, run_e, tile_last, tile_first); LAUNCHED();
   } else { k_prog_runs<<<grid, 256, 0, s>>>(sd, aux, run_e); LAUNCHED(); }
 }
-void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
+void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, const unsigned long long *pm, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  k_gather_prog<<<grid, 256, 0, s>>>(g, sd, aux, run_e, hist, status); LAUNCHED();
+  k_gather_prog<<<grid, 256, 0, s>>>(g, sd, aux, run_e, pm, hist, status); LAUNCHED();
 }
 
 void launch_block_bits(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t stride, int progressive,
-                       uint32_t *blk_bits, uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *status, int n, cudaStream_t s)
+                       uint32_t *blk_bits, uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e, const unsigned long long *pm, uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  if (progressive) k_block_bits_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, tile_bits, status);
+  if (progressive) k_block_bits_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, pm, blk_bits, tile_bits, status);
   else k_block_bits_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, rl, tabs, stride, blk_bits, tile_bits, status);
   LAUNCHED();
 }
@@ -3262,11 +3286,11 @@ void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint
 }
 void launch_encode(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t stride, int progressive,
                    const uint32_t *blk_bits, const uint32_t *tile_bits, const unsigned long long *tile_base, const uint32_t *seg_corr, long long seg_stride,
-                   const uint32_t *blk_aux, const uint32_t *run_e,
+                   const uint32_t *blk_aux, const uint32_t *run_e, const unsigned long long *pm,
                    uint32_t *bitbuf, size_t bitbuf_stride_words, uint32_t *mark, size_t mark_stride_words, const uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
-  if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
+  if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, pm, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
   else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, rl, tabs, stride, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
   LAUNCHED();
 }

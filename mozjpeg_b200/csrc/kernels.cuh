@@ -137,11 +137,12 @@ void launch_qopt_sums(const Geom &g, long long *qsum, int n, cudaStream_t s);
 void launch_qopt_update(long long *qsum, uint16_t *qimg, int n, cudaStream_t s);
 void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                        const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int vertical, int n, cudaStream_t s);
-// tile_last / tile_first: int [n][ceil(nblocks/256)] scratch
-void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, int *tile_last, int *tile_first, int n, cudaStream_t s);
-void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
+// tile_last / tile_first: int [n][ceil(nblocks/256)] scratch; pm: the blocks' event masks of this AC scan,
+// unsigned long long [3][n][nblocks] (written here, read by the three symbol walks of the scan)
+void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, unsigned long long *pm, int *tile_last, int *tile_first, int n, cudaStream_t s);
+void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, const unsigned long long *pm, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_block_bits(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
-                       uint32_t *blk_bits, uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e, uint32_t *status, int n, cudaStream_t s);
+                       uint32_t *blk_bits, uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e, const unsigned long long *pm, uint32_t *status, int n, cudaStream_t s);
 // tile_base[img][tile] / seg_corr[img][segment] / total_bits[img] from the tile sums (and the restart interval)
 void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint32_t *tile_bits, unsigned long long *tile_base,
                         uint32_t *seg_corr, long long seg_stride, unsigned long long *total_bits, size_t capacity_bits,
@@ -150,7 +151,7 @@ void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint
 // nz_rec: the side records holding every block's final non-zero positions (trellis on, sequential scans), or nullptr
 void launch_encode(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
                    const uint32_t *blk_bits, const uint32_t *tile_bits, const unsigned long long *tile_base, const uint32_t *seg_corr, long long seg_stride,
-                   const uint32_t *blk_aux, const uint32_t *run_e,
+                   const uint32_t *blk_aux, const uint32_t *run_e, const unsigned long long *pm,
                    uint32_t *bitbuf, size_t bitbuf_image_stride_words, uint32_t *mark, size_t mark_stride_words, const uint32_t *status, int n, cudaStream_t s);
 size_t stuff_tiles(size_t bitbuf_image_stride_words);     // ff_tile entries per image
 void launch_stuff(const uint32_t *bitbuf, size_t bitbuf_image_stride_words, const unsigned long long *total_bits, uint32_t *ff_tile,
