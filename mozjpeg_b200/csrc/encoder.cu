@@ -78,9 +78,10 @@ struct Arena {
   b200::DevBuf d_planes;             // input smoothing: the pre-pass's component planes
   b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_srec, d_splits, d_best_al, d_qimg, d_qsum, d_eo, d_es;
   b200::DevBuf d_blk_bits, d_tile_bits, d_tile_base, d_seg_corr, d_mark, d_ff_tile, d_blk_aux, d_blk_run, d_blk_mask, d_total_bits, d_bitbuf;
+  b200::DevBuf d_sym, d_dcq;         // sequential scans after the trellis: symbol records + dense DC values (SymOut, kernels.cuh)
   b200::Geom g;                      // the plan's geometry with this arena's coefficient pointers
   void release() {
-    b200::DevBuf *db[] = {&d_planes, &d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_srec, &d_splits, &d_best_al, &d_qimg, &d_qsum, &d_eo, &d_es, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_blk_mask, &d_total_bits, &d_bitbuf};
+    b200::DevBuf *db[] = {&d_planes, &d_hist, &d_tabs_trellis, &d_rec, &d_bt, &d_srec, &d_splits, &d_best_al, &d_qimg, &d_qsum, &d_eo, &d_es, &d_blk_bits, &d_tile_bits, &d_tile_base, &d_seg_corr, &d_mark, &d_ff_tile, &d_blk_aux, &d_blk_run, &d_blk_mask, &d_total_bits, &d_bitbuf, &d_sym, &d_dcq};
     for (b200::DevBuf *b : db) b->release();
     for (int i = 0; i < 4; i++) { d_coef[i].release(); d_raw[i].release(); d_plain[i].release(); }
   }
@@ -357,6 +358,15 @@ static size_t smooth_plane_bytes(const Geom &g)
   return t;
 }
 
+// Sequential scans behind the default trellis (one round over 1..63 by k_trellis_ac3): the entropy stages read the symbol
+// records the trellis back-track leaves instead of the coefficient planes.  B200JPEG_SYMREC=0 keeps them on the planes.
+static bool use_symrec(const Plan &pl, const b200jpeg_params *p)
+{
+  static const bool off = getenv("B200JPEG_SYMREC") && getenv("B200JPEG_SYMREC")[0] == '0';
+  const bool generic_rounds = p->use_scans_in_trellis || p->trellis_num_loops > 1 || p->trellis_q_opt || p->trellis_eob_opt;
+  return !off && pl.trellis && !pl.progressive && !generic_rounds;
+}
+
 // Buffers and constants of one batch of n_total images processed in chunks of `chunk`.
 static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_pixels, size_t src_bytes, int n_arenas)
 {
@@ -387,6 +397,10 @@ static int prepare_batch(b200jpeg_encoder *e, int n_total, int chunk, bool host_
     if ((rc = a.d_bt.reserve((size_t)n * pl.sum_real_blocks * 8))) return rc;
     if ((rc = a.d_srec.reserve((size_t)n * pl.sum_real_blocks * 16))) return rc;
     if ((rc = a.d_splits.reserve((size_t)n * 4 * (4 + 128) * 4))) return rc;      // class boundaries + the sort's counters
+    if (use_symrec(pl, p)) {
+      if ((rc = a.d_sym.reserve((size_t)n * pl.sum_real_blocks * SYMREC_BYTES))) return rc;
+      if ((rc = a.d_dcq.reserve((size_t)n * pl.sum_real_blocks * 2))) return rc;
+    }
     if ((rc = a.d_best_al.reserve((size_t)n * 2 * 4))) return rc;
     if (p->trellis_quant && p->trellis_q_opt) {
       if ((rc = a.d_qimg.reserve((size_t)n * 512))) return rc;
@@ -490,6 +504,8 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   tm.mark("dummy");
   launch_dummy(g, n, s);
 
+  const bool symrec = use_symrec(pl, p);
+  const bool symstats = symrec && pl.optimize && nscans == 1;
   // ---- trellis phase (jcmaster.c pass list).  The three
   //      per-component chains (statistics on the plain-quantized coefficients
   //      -> optimal tables -> quantize_trellis) are independent, so each step
@@ -506,6 +522,11 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     // per-image tables)
     const bool qopt = p->trellis_q_opt != 0, eobopt = p->trellis_eob_opt != 0;
     const bool generic_rounds = nband == 2 || p->trellis_num_loops > 1 || qopt || eobopt;
+    // symbol records for the sequential scans that follow; with optimal tables for ONE scan over all components, the
+    // back-track also counts that scan's AC symbols (the histograms are free again once the trellis tables are built)
+    SymOut so; so.sym = symrec ? A.d_sym.as<uint8_t>() : nullptr; so.dcq = symrec ? A.d_dcq.as<int16_t>() : nullptr;
+    so.hist = symstats ? A.d_hist.as<uint32_t>() : nullptr;
+    so.keep_coef = e->keep_plain ? 1 : 0;                       // B200JPEG_KEEP_PLAIN=1: the debug taps read the final planes
     uint16_t *qimg = qopt ? A.d_qimg.as<uint16_t>() : nullptr;
     if (qopt) {
       // every image starts from the batch's tables (natural order, like JQUANT_TBL.quantval)
@@ -541,7 +562,8 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     }
     if (!generic_rounds) {
       tm.mark("trellis_ac");
-      launch_trellis_ac3(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rlr, A.d_srec.p, A.d_splits.as<uint32_t>(), n, s);
+      if (so.hist) CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
+      launch_trellis_ac3(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), rlr, A.d_srec.p, A.d_splits.as<uint32_t>(), so, n, s);
     } else {
       tm.mark("trellis_ac");
       float4 *eo = eobopt ? A.d_eo.as<float4>() : nullptr;
@@ -551,8 +573,8 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     }
     if (p->trellis_quant_dc) {
       tm.mark("trellis_dc");
-      if (pl.progressive) launch_trellis_dc(gr, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rlr, p->trellis_delta_dc_weight > 0.0f, n, s);
-      else launch_trellis_dc(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rlr, p->trellis_delta_dc_weight > 0.0f, n, s);
+      if (pl.progressive) launch_trellis_dc(gr, e->d_tc.as<TrellisConsts>(), e->d_tabs_fixed.as<DevHuff>(), 0, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rlr, p->trellis_delta_dc_weight > 0.0f, nullptr, 1, n, s);
+      else launch_trellis_dc(gr, e->d_tc.as<TrellisConsts>(), tset, tabset, A.d_rec.as<DcRec>(), A.d_bt.as<unsigned long long>(), rlr, p->trellis_delta_dc_weight > 0.0f, so.dcq, so.keep_coef, n, s);
     }
     return B200JPEG_OK;
     };
@@ -592,7 +614,9 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   //      frequency-split groups are coded at each image's best Al, chosen on the device in between. ----
   int *best_al = A.d_best_al.as<int>();                       // [2][n]: luma, chroma
   // sequential scans after the trellis: the side records hold every block's final non-zero positions
-  const DcRec *nz_rec = (pl.trellis && !pl.progressive) ? A.d_rec.as<DcRec>() : nullptr;
+  const DcRec *nz_rec = (pl.trellis && !pl.progressive && !symrec) ? A.d_rec.as<DcRec>() : nullptr;
+  const uint8_t *sym = symrec ? A.d_sym.as<uint8_t>() : nullptr;
+  const int16_t *dcq = symrec ? A.d_dcq.as<int16_t>() : nullptr;
   for (size_t j = 0; j < pl.order.size(); j++) {
     const int si = pl.order[j];
     ScanDesc sd = pl.scans[si];
@@ -624,8 +648,9 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
       tstride = tabset * nscans;
       if (!dc_refine) {                                                                    // jcmaster.c:650-662
         tm.mark("scan_stats");
-        CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
+        if (!symstats) CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
         if (pl.progressive) launch_gather_prog(g, sd, aux, run_e, pm, A.d_hist.as<uint32_t>(), status, n, s);
+        else if (symstats) launch_gather_seq_dc(g, sd, dcq, rl, A.d_hist.as<uint32_t>(), status, n, s);      // the AC counts are there already
         else launch_gather_seq(g, sd, nz_rec, rl, A.d_hist.as<uint32_t>(), status, n, s);
         tm.mark("scan_tables");
         SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = scan_slot_mask(pl, sd);
@@ -635,7 +660,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     } else { tabs = e->d_tabs_fixed.as<DevHuff>(); tstride = 0; }
     const size_t mark_words = (e->bitbuf_words_per_image * 4 / 8 + 64) / 4;
     tm.mark("block_bits");
-    launch_block_bits(g, sd, nz_rec, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), aux, run_e, pm, status, n, s);
+    launch_block_bits(g, sd, nz_rec, sym, dcq, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), aux, run_e, pm, status, n, s);
     tm.mark("scan_layout");
     launch_scan_layout(sd, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
                        A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, A.d_total_bits.as<unsigned long long>(),
@@ -643,7 +668,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     tm.mark("encode");
     CU(cudaMemsetAsync(A.d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
     if (sd.ri) CU(cudaMemsetAsync(A.d_mark.p, 0, mark_words * 4 * n, s));
-    launch_encode(g, sd, nz_rec, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
+    launch_encode(g, sd, nz_rec, sym, dcq, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
                   A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, aux, run_e, pm,
                   A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_mark.as<uint32_t>(), mark_words, status, n, s);
     tm.mark("stuff");

@@ -1168,14 +1168,14 @@ __device__ __forceinline__ int prev_dc(const Geom &g, const ScanDesc &sd, int im
 // Walks one block the way encode_one_block (jchuff.c:563-661) / htest_one_block
 // (jchuff.c:812-878) do, calling sink.dc(nbits, valuebits) and
 // sink.ac(symbol, nbits, valuebits) in stream order.
-template <class Sink>
-__device__ __forceinline__ void walk_seq_block(const int16_t *__restrict__ blk, int last_dc, Sink &sink)
+// ld(v): the block's v-th group of 8 zigzag-ordered coefficients (16 bytes)
+template <class Sink, class Load>
+__device__ __forceinline__ void walk_seq_chunks(Load ld, int last_dc, Sink &sink)
 {
-  const uint4 *b4 = reinterpret_cast<const uint4 *>(blk);
   int r = 0;
 #pragma unroll
   for (int v = 0; v < 8; v++) {
-    uint4 q = b4[v];
+    uint4 q = ld(v);
     unsigned w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -1198,6 +1198,12 @@ __device__ __forceinline__ void walk_seq_block(const int16_t *__restrict__ blk, 
     }
   }
   if (r > 0) sink.ac(0, 0, 0);
+}
+template <class Sink>
+__device__ __forceinline__ void walk_seq_block(const int16_t *__restrict__ blk, int last_dc, Sink &sink)
+{
+  const uint4 *b4 = reinterpret_cast<const uint4 *>(blk);
+  walk_seq_chunks([&](int v) { return b4[v]; }, last_dc, sink);
 }
 
 #ifndef SEQ_SPARSE_ENC
@@ -1248,10 +1254,123 @@ __device__ __forceinline__ void walk_seq_sparse(const int16_t *__restrict__ blk,
   if (prev != 63) sink.ac(0, 0, 0);
 }
 
+
+// ---------------------------------------------------------------------
+// Sequential scans after the AC trellis: the blocks' symbols come from the records the trellis back-track left (SymOut,
+// kernels.cuh) and the DC values from the dense array the DC trellis wrote -- the 128-byte coefficient blocks are not read.
+// ---------------------------------------------------------------------
+// scan-order block -> block coordinates inside its component (compress_output, jccoefct.c:498-553).  A scan has fewer
+// than 2^31 blocks (65500 x 65500 samples at most), so the arithmetic is 32-bit.
+struct ScanPos { int sci, k, mrow, mcol, row, col; unsigned mcu; };
+__device__ __forceinline__ void scan_place(const Geom &g, const ScanDesc &sd, ScanPos &p)
+{
+  const CompGeom &c = g.c[sd.ci[p.sci]];
+  const int mh = sd.ncomps == 1 ? 1 : c.v, mw = sd.ncomps == 1 ? 1 : c.h;
+  p.row = p.mrow * mh + sd.k_y[p.k]; p.col = p.mcol * mw + sd.k_x[p.k];
+}
+__device__ __forceinline__ ScanPos scan_coords(const Geom &g, const ScanDesc &sd, long long t)
+{
+  ScanPos p;
+  const unsigned tt = (unsigned)t, bim = (unsigned)sd.bim, per_row = (unsigned)sd.per_row;
+  p.mcu = bim == 1 ? tt : tt / bim; p.k = (int)(tt - p.mcu * bim);
+  p.sci = sd.k_comp[p.k];
+  p.mrow = (int)(p.mcu / per_row); p.mcol = (int)(p.mcu - (unsigned)p.mrow * per_row);
+  scan_place(g, sd, p);
+  return p;
+}
+// final DC value of the block at (row, col) of a component; d = the image's dense DC values of that component.  Dummy
+// blocks repeat a real block's value, the one k_dummy copies (jccoefct.c:312-345, :443-476)
+__device__ __forceinline__ int dense_dc(const CompGeom &c, const int16_t *__restrict__ d, int row, int col)
+{
+  if (row >= c.hib) { row = c.hib - 1; col = min(c.h == 1 ? col : (col / c.h) * c.h + c.h - 1, c.wib - 1); }
+  else if (col >= c.wib) col = c.wib - 1;
+  return d[(size_t)row * c.wib + col];
+}
+// DC value of the previous block of the same component in scan order (0 at the scan's start and after a restart marker):
+// the block before it in the same MCU, or the component's last block of the MCU before
+__device__ __forceinline__ int prev_dc_dense(const Geom &g, const ScanDesc &sd, const int16_t *__restrict__ dimg /* the image's dense DC values */,
+                                             const RecLayout &rl, const ScanPos &p)
+{
+  ScanPos q = p;
+  if (p.k > sd.k_first[p.sci]) q.k = p.k - 1;
+  else if (p.mcu > 0 && !(sd.ri && p.mcu % (unsigned)sd.ri == 0)) {                            // emit_restart resets last_dc_val (jchuff.c:681-683)
+    q.k = sd.k_first[p.sci] + sd.k_count[p.sci] - 1;
+    if (p.mcol > 0) q.mcol = p.mcol - 1; else { q.mrow = p.mrow - 1; q.mcol = sd.per_row - 1; }
+  } else return 0;
+  scan_place(g, sd, q);
+  const int ci = sd.ci[p.sci];
+  return dense_dc(g.c[ci], dimg + rl.comp_off[ci], q.row, q.col);
+}
+template <class Sink>
+__device__ __forceinline__ void emit_dc(int dcv, int last_dc, Sink &sink)
+{
+  int temp = dcv - last_dc, temp2 = temp;
+  if (temp < 0) { temp = -temp; temp2--; }
+  sink.dc(nbits_of(temp), temp2);
+}
+// encode_one_block (jchuff.c:563-661) / htest_one_block (:812-878) for scan block t from its record
+template <class Sink>
+__device__ __forceinline__ void walk_seq_rec(const Geom &g, const ScanDesc &sd, const uint8_t *__restrict__ sym, const int16_t *__restrict__ dcq, const RecLayout &rl,
+                                             int img, long long t, Sink &sink)
+{
+  const ScanPos sp = scan_coords(g, sd, t);
+  const int row = sp.row, col = sp.col;
+  const int ci = sd.ci[sp.sci];
+  const CompGeom &c = g.c[ci];
+  const int16_t *dimg = dcq + (size_t)img * rl.per_image;
+  const bool real = row < c.hib && col < c.wib;
+  const uint4 *r4 = reinterpret_cast<const uint4 *>(sym + ((size_t)img * rl.per_image + rl.comp_off[ci] + (real ? (size_t)row * c.wib + col : (size_t)0)) * SYMREC_BYTES);
+  uint4 q0 = make_uint4(1u, 0u, 0u, 0u);                       // a dummy block: one entry, EOB
+  if (real) q0 = r4[0];
+  emit_dc(dense_dc(c, dimg + rl.comp_off[ci], row, col), prev_dc_dense(g, sd, dimg, rl, sp), sink);
+  if (q0.x & 0x80u) {
+    // more symbols than a record holds: the coefficient block itself
+    const int16_t *blk = c.coef + (((size_t)img * c.hpad + row) * c.wpad + col) * 64;
+    int r = 0;
+    for (int p = 1; p < 64; p++) {
+      const int val = blk[p];
+      if (val == 0) { r++; continue; }
+      while (r > 15) { sink.ac(0xF0, 0, 0); r -= 16; }
+      int temp = val, temp2 = val;
+      if (temp < 0) { temp = -temp; temp2--; }
+      const int nb = nbits_of(temp);
+      sink.ac((r << 4) + nb, nb, temp2);
+      r = 0;
+    }
+    if (r > 0) sink.ac(0, 0, 0);
+    return;
+  }
+  const int n = (int)(q0.x & 0x7Fu);                          // entries at words 1..n, stream order = descending word index
+#pragma unroll 1
+  for (int v = n >> 2; v > 0; v--) {
+    const uint4 q = r4[v];
+    const unsigned e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 3; j >= 0; j--) if (4 * v + j <= n) sink.ac((int)(e[j] & 0xFFu), (int)(e[j] & 15u), (int)(e[j] >> 16));
+  }
+  if (n >= 3) sink.ac((int)(q0.w & 0xFFu), (int)(q0.w & 15u), (int)(q0.w >> 16));
+  if (n >= 2) sink.ac((int)(q0.z & 0xFFu), (int)(q0.z & 15u), (int)(q0.z >> 16));
+  if (n >= 1) sink.ac((int)(q0.y & 0xFFu), (int)(q0.y & 15u), (int)(q0.y >> 16));
+}
+
 // ---------------------------------------------------------------------
 // statistics pass (encode_mcu_gather, jchuff.c:886-915)
 // ---------------------------------------------------------------------
-// shared-memory histogram increment (warp-aggregating the atomics per counter was measured slower)
+// shared-memory histogram increment (warp-aggregating the atomics per counter was measured slower).  A few symbols
+// (EOB, 0x01, 0x11, 0x02) make up most of a scan, so the lanes of a warp mostly hit the same few counters; keeping
+// GATHER_COPIES copies of the histograms per CTA (a thread uses copy lane mod copies) was measured on B200: no gain with
+// 4 or 8 copies in the per-component kernel (0.52 vs 0.54 ms per 64 4K images), a loss in the per-scan kernels whose
+// copies are 8 KB each (0.97 vs 0.53 ms) -- same-counter serialisation is not what bounds these kernels.  Default 1.
+#ifndef GATHER_COPIES
+#define GATHER_COPIES 1
+#endif
+#ifndef GATHER_COPIES_SCAN
+#define GATHER_COPIES_SCAN 1
+#endif
+// blocks per CTA = GATHER_TILES * 256: zeroing and flushing the copies is paid once per CTA
+#ifndef GATHER_TILES
+#define GATHER_TILES 4
+#endif
 __device__ __forceinline__ void hist_inc(unsigned *addr)
 {
   atomicAdd(addr, 1u);
@@ -1266,70 +1385,150 @@ struct HistSink {
 // then touches only those coefficients (and the 32-byte sectors they sit in) instead of the whole 128-byte block
 __global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ nz_rec, RecLayout rl, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
 {
-  __shared__ unsigned sh[HIST_SLOTS * HIST_BINS];
+  __shared__ unsigned sh[GATHER_COPIES_SCAN][HIST_SLOTS * HIST_BINS];
   int img = blockIdx.y;
-  for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) sh[i] = 0;
+  for (int i = threadIdx.x; i < GATHER_COPIES_SCAN * HIST_SLOTS * HIST_BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
   __syncthreads();
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < sd.nblocks) {
+#pragma unroll 1
+  for (int tile = 0; tile < GATHER_TILES; tile++) {
+    long long t = ((long long)blockIdx.x * GATHER_TILES + tile) * blockDim.x + threadIdx.x;
+    if (t >= sd.nblocks) break;
     int sci, k; long long mcu;
     const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
     int last = prev_dc(g, sd, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
-    HistSink sink{sh + c.dc_tbl * HIST_BINS, sh + (4 + c.ac_tbl) * HIST_BINS, 0, g.max_coef_bits};
+    unsigned *mine = sh[threadIdx.x % GATHER_COPIES_SCAN];
+    HistSink sink{mine + c.dc_tbl * HIST_BINS, mine + (4 + c.ac_tbl) * HIST_BINS, 0, g.max_coef_bits};
     if (SEQ_SPARSE_STATS && nz_rec) walk_seq_sparse(blk, block_nzmask(g, sd, nz_rec, rl, img, sci, mcu, k), last, sink);
     else walk_seq_block(blk, last, sink);
     if (sink.bad) atomicOr(&status[img], 2u);          // JERR_BAD_DCT_COEF
   }
   __syncthreads();
   uint32_t *gh = hist + (size_t)img * HIST_SLOTS * HIST_BINS;
-  for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&gh[i], sh[i]);
+  for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) {
+    unsigned v = 0;
+#pragma unroll
+    for (int cp = 0; cp < GATHER_COPIES_SCAN; cp++) v += sh[cp][i];
+    if (v) atomicAdd(&gh[i], v);
+  }
 }
 // Trellis-phase statistics: every component as its own non-interleaved scan
 // (jcmaster.c:443-467), all components of all images in one launch;
 // histogram set index = img*nc + ci.
+// GATHER_STAGE: the CTA's 256 blocks arrive through shared memory -- 16-byte pieces in the order they lie in memory (8
+// consecutive lanes fetch one block's 128 bytes: 4 lines per request instead of 32), stored with the piece index XORed
+// by the block's low bits so that the per-thread read-back of whole blocks is conflict-free.
+#ifndef GATHER_STAGE
+#define GATHER_STAGE 1
+#endif
 __global__ void __launch_bounds__(256) k_gather_comp(Geom g, RestartSpec rs, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
 {
-  __shared__ unsigned sh[2 * HIST_BINS];
+  __shared__ unsigned sh[GATHER_COPIES][2 * HIST_BINS];
+  __shared__ __align__(16) uint4 stg[GATHER_STAGE ? 256 * 8 : 1];
   const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
   const CompGeom &c = g.c[ci];
   long long nblk = (long long)c.wib * c.hib;
-  if ((long long)blockIdx.x * blockDim.x >= nblk) return;
-  for (int i = threadIdx.x; i < 2 * HIST_BINS; i += blockDim.x) sh[i] = 0;
+  if ((long long)blockIdx.x * GATHER_TILES * blockDim.x >= nblk) return;
+  for (int i = threadIdx.x; i < GATHER_COPIES * 2 * HIST_BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
   __syncthreads();
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < nblk) {
-    int row = (int)(t / c.wib), col = (int)(t - (long long)row * c.wib);
-    const int16_t *base = c.coef + (size_t)img * c.blocks_per_image * 64;
-    const int16_t *blk = base + ((size_t)row * c.wpad + col) * 64;
-    int last = 0;
-    const long long ri = rs.in_rows > 0 ? min((long long)rs.in_rows * c.wib, 65535LL) : rs.interval;      // per_scan_setup, jcmaster.c:594-599
-    if (t > 0 && !(ri && t % ri == 0)) { int pr = col > 0 ? row : row - 1, pc = col > 0 ? col - 1 : c.wib - 1; last = base[((size_t)pr * c.wpad + pc) * 64]; }
-    HistSink sink{sh, sh + HIST_BINS, 0, g.max_coef_bits};
-    walk_seq_block(blk, last, sink);
-    if (sink.bad) atomicOr(&status[img], 2u);
+  const int16_t *base = c.coef + (size_t)img * c.blocks_per_image * 64;
+#pragma unroll 1
+  for (int tile = 0; tile < GATHER_TILES; tile++) {
+    const long long t0 = ((long long)blockIdx.x * GATHER_TILES + tile) * blockDim.x;
+    if (t0 >= nblk) break;
+    if (GATHER_STAGE) {
+      if (tile) __syncthreads();                             // the previous tile's blocks have been read
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int q = i * 256 + threadIdx.x, bq = q >> 3, part = q & 7;
+        const long long tb = t0 + bq;
+        if (tb < nblk) {
+          const int rowb = (int)(tb / c.wib), colb = (int)(tb - (long long)rowb * c.wib);
+          stg[bq * 8 + (part ^ (bq & 7))] = reinterpret_cast<const uint4 *>(base + ((size_t)rowb * c.wpad + colb) * 64)[part];
+        }
+      }
+      __syncthreads();
+    }
+    const long long t = t0 + threadIdx.x;
+    if (t < nblk) {
+      int row = (int)(t / c.wib), col = (int)(t - (long long)row * c.wib);
+      const int16_t *blk = base + ((size_t)row * c.wpad + col) * 64;
+      int last = 0;
+      const long long ri = rs.in_rows > 0 ? min((long long)rs.in_rows * c.wib, 65535LL) : rs.interval;      // per_scan_setup, jcmaster.c:594-599
+      if (t > 0 && !(ri && t % ri == 0)) { int pr = col > 0 ? row : row - 1, pc = col > 0 ? col - 1 : c.wib - 1; last = base[((size_t)pr * c.wpad + pc) * 64]; }
+      unsigned *mine = sh[threadIdx.x % GATHER_COPIES];
+      HistSink sink{mine, mine + HIST_BINS, 0, g.max_coef_bits};
+      if (GATHER_STAGE) { const uint4 *mb = stg + threadIdx.x * 8; const int sw = threadIdx.x & 7; walk_seq_chunks([&](int v) { return mb[v ^ sw]; }, last, sink); }
+      else walk_seq_block(blk, last, sink);
+      if (sink.bad) atomicOr(&status[img], 2u);
+    }
   }
   __syncthreads();
   uint32_t *gh = hist + ((size_t)img * g.nc + ci) * HIST_SLOTS * HIST_BINS;
   for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) {
-    if (sh[i]) atomicAdd(&gh[c.dc_tbl * HIST_BINS + i], sh[i]);
-    if (sh[HIST_BINS + i]) atomicAdd(&gh[(4 + c.ac_tbl) * HIST_BINS + i], sh[HIST_BINS + i]);
+    unsigned d = 0, a = 0;
+#pragma unroll
+    for (int cp = 0; cp < GATHER_COPIES; cp++) { d += sh[cp][i]; a += sh[cp][HIST_BINS + i]; }
+    if (d) atomicAdd(&gh[c.dc_tbl * HIST_BINS + i], d);
+    if (a) atomicAdd(&gh[(4 + c.ac_tbl) * HIST_BINS + i], a);
   }
 }
 void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
 {
   long long mb = 0;
   for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
-  dim3 grid((unsigned)((mb + 255) / 256), n * g.nc);
+  dim3 grid((unsigned)((mb + 256 * GATHER_TILES - 1) / (256 * GATHER_TILES)), n * g.nc);
   k_gather_comp<<<grid, 256, 0, s>>>(g, rs, hist, status);
   LAUNCHED();
 }
 
 void launch_gather_seq(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
 {
-  dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
+  dim3 grid((unsigned)((sd.nblocks + 256 * GATHER_TILES - 1) / (256 * GATHER_TILES)), n);
   k_gather_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, rl, hist, status);
   LAUNCHED();
+}
+
+// The DC half of a sequential scan's statistics, from the dense DC values (the AC half was counted by the AC trellis
+// back-track); dummy blocks add their EOB here.  GATHER_TILES * 256 scan blocks per CTA.
+__global__ void __launch_bounds__(256) k_gather_seq_dc(Geom g, ScanDesc sd, const int16_t *__restrict__ dcq, RecLayout rl, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
+{
+  __shared__ unsigned sdc[4][4][20], seob[4];
+  const int img = blockIdx.y;
+  for (int i = threadIdx.x; i < 4 * 4 * 20; i += blockDim.x) (&sdc[0][0][0])[i] = 0;
+  if (threadIdx.x < 4) seob[threadIdx.x] = 0;
+  __syncthreads();
+  const int16_t *dimg = dcq + (size_t)img * rl.per_image;
+#pragma unroll 1
+  for (int tile = 0; tile < GATHER_TILES; tile++) {
+    const long long t = ((long long)blockIdx.x * GATHER_TILES + tile) * blockDim.x + threadIdx.x;
+    if (t >= sd.nblocks) break;
+    const ScanPos sp = scan_coords(g, sd, t);
+    const int row = sp.row, col = sp.col;
+    const int ci = sd.ci[sp.sci];
+    const CompGeom &c = g.c[ci];
+    int temp = dense_dc(c, dimg + rl.comp_off[ci], row, col) - prev_dc_dense(g, sd, dimg, rl, sp);
+    if (temp < 0) temp = -temp;
+    const int nb = nbits_of(temp);
+    if (nb > g.max_coef_bits + 1) atomicOr(&status[img], 2u);          // JERR_BAD_DCT_COEF (jchuff.c:836)
+    atomicAdd(&sdc[threadIdx.x & 3][c.dc_tbl][min(nb, 19)], 1u);
+    if (!(row < c.hib && col < c.wib)) atomicAdd(&seob[c.ac_tbl], 1u);
+  }
+  __syncthreads();
+  uint32_t *gh = hist + (size_t)img * HIST_SLOTS * HIST_BINS;
+  if (threadIdx.x < 80) {
+    const int slot = threadIdx.x / 20, b = threadIdx.x % 20;
+    const unsigned v = sdc[0][slot][b] + sdc[1][slot][b] + sdc[2][slot][b] + sdc[3][slot][b];
+    if (v) atomicAdd(&gh[slot * HIST_BINS + b], v);
+  } else if (threadIdx.x < 84) {
+    const int slot = threadIdx.x - 80;
+    if (seob[slot]) atomicAdd(&gh[(4 + slot) * HIST_BINS], seob[slot]);
+  }
+}
+void launch_gather_seq_dc(const Geom &g, const ScanDesc &sd, const int16_t *dcq, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
+{
+  dim3 grid((unsigned)((sd.nblocks + 256 * GATHER_TILES - 1) / (256 * GATHER_TILES)), n);
+  k_gather_seq_dc<<<grid, 256, 0, s>>>(g, sd, dcq, rl, hist, status); LAUNCHED();
 }
 
 // =====================================================================
@@ -1819,6 +2018,12 @@ __device__ __forceinline__ float u2f_exact(unsigned v) { return __uint_as_float(
 //    5-8 thousand and stalled on instruction fetch), registers ~50, shared memory 12 bytes per list slot and thread.
 // =====================================================================
 #define T3_THREADS 128
+#ifndef SYMREC_DIRECT
+#define SYMREC_DIRECT 0
+#endif
+#ifndef T3_MINB_8
+#define T3_MINB_8 8            // resident CTAs per SM the compiler must allow for the <= 8 entries class
+#endif
 template <int MM> struct T3Smem {
   uint2 rec[MM][T3_THREADS];       // before the entry is processed: {A[p-1], p | raw << 16}; after: {-A[p], accumulated cost}
   unsigned ew[MM][T3_THREADS];     // 4*p | chosen predecessor (1-based entry, 0 = block start) << 8 | chosen value << 16
@@ -1848,9 +2053,9 @@ __device__ __forceinline__ float t3_dist(const int cand, const int q, const int 
 }
 
 template <int MM>
-__global__ void __launch_bounds__(T3_THREADS, MM <= 15 ? 8 : MM <= 32 ? 4 : 2)
+__global__ void __launch_bounds__(T3_THREADS, MM <= 8 ? T3_MINB_8 : MM <= 15 ? 8 : MM <= 32 ? 4 : 2)
 k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
-              DcRec *__restrict__ rec, RecLayout rl, const SRec *__restrict__ srec, const uint32_t *__restrict__ splits)
+              DcRec *__restrict__ rec, RecLayout rl, const SRec *__restrict__ srec, const uint32_t *__restrict__ splits, SymOut so)
 {
   const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
   const CompGeom &c = g.c[ci];
@@ -1870,7 +2075,10 @@ k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__res
   __shared__ __align__(16) uint4 sEnt[64];                    // per zigzag position {8*Q, reciprocal, weight, -}
   __shared__ __align__(16) float swz[64];
   __shared__ int sqL;
+  // final AC symbols of this CTA's blocks (so.hist): run * 10 + size - 1, then EOB, ZRL (sizes are at most 10 where the trellis runs)
+  __shared__ unsigned shist[164];
   const int tid = threadIdx.x;
+  for (int i = tid; i < 164; i += T3_THREADS) shist[i] = 0;
   uint8_t *acsi = reinterpret_cast<uint8_t *>(t3_dyn);        // table build only
   {
     const DevHuff *ac = reinterpret_cast<const DevHuff *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.y * tabs_set_stride) + (4 + c.ac_tbl);
@@ -1930,8 +2138,10 @@ k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__res
     // phase 1: accumulated zero distortion, zigzag order, serial fp32 (:1134); entries pushed where the mask says so
     const unsigned mlo = (unsigned)sr.nzmask, mhi = (unsigned)(sr.nzmask >> 32);
     const int m = __popc(mlo) + __popc(mhi);
+    const int mmax = __reduce_max_sync(0xffffffffu, m);
     float azd = 0.0f;
-    {
+    // (a warp whose 32 blocks have no entry at all -- the tail of the sorted order -- needs neither the prefix nor the search)
+    if (mmax != 0) {
       uint2 *push = myrec;
       const float2 l2 = make_float2(lambda, lambda);
       const float2 bias = make_float2(-8421376.0f, -8421376.0f);   // -(2^23 + 2^15): undoes the exponent trick and the +32768 offset
@@ -1961,7 +2171,6 @@ k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__res
     const float azd63 = azd;
     // phase 2 (:1121-1185): entries in order; all lanes of the warp walk the same entry index.  The end-of-block choice
     // (:1187-1207) rides along: an entry's cost of being the last one is known as soon as the entry is settled.
-    const int mmax = __reduce_max_sync(0xffffffffu, m);
     int last = 0;
     float best_cost = azd63 + eob;
     // the entry's own constants (fetching them one entry ahead, behind the previous predecessor loop, measured no gain)
@@ -2036,31 +2245,91 @@ k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__res
     if (live) {
       // output: zeros except the back-tracked chain (:1211-1222)
       uint4 *q4 = reinterpret_cast<uint4 *>(o16);
-      q4[0] = make_uint4(dc_q, 0, 0, 0);
+      auto write_block = [&](int lst) {
+        q4[0] = make_uint4(dc_q, 0, 0, 0);
 #pragma unroll
-      for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
-      unsigned long long fm = 0;
-      while (last != 0) {
-        const unsigned w = myew[(last - 1) * T3_THREADS];
-        const int pos = (int)((w & 0xFFu) >> 2), val = (int)w >> 16;
-        o16[pos] = (int16_t)val; if (val) fm |= 1ull << pos;
-        last = (int)((w >> 8) & 0xFFu);
+        for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
+        unsigned long long fm = 0;
+        while (lst != 0) {
+          const unsigned w = myew[(lst - 1) * T3_THREADS];
+          const int pos = (int)((w & 0xFFu) >> 2), val = (int)w >> 16;
+          o16[pos] = (int16_t)val; if (val) fm |= 1ull << pos;
+          lst = (int)((w >> 8) & 0xFFu);
+        }
+        return fm;
+      };
+      if (!so.sym) {
+        const unsigned long long fm = write_block(last);
+        if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fm;
+      } else {
+        // sequential scans follow: the back-track leaves the block's AC symbols as a record (header word: number of
+        // entries, bit 7 = more than SYMREC_SLOTS; entry = symbol | value bits << 16, LAST symbol of the stream first --
+        // encode_one_block's order, jchuff.c:600-661, reversed) and counts them for the scan's optimal tables
+        // (htest_one_block, jchuff.c:836-878).  The record is put together in this thread's {-A, cost} list, which is
+        // dead.  The coefficient block itself is rewritten only if somebody will read it: the debug tap, or the
+        // entropy stages when the record overflowed.
+        unsigned *scr = reinterpret_cast<unsigned *>(myrec);
+        int ns = 0;
+#if SYMREC_DIRECT
+        unsigned *gout = reinterpret_cast<unsigned *>(so.sym + (rbase + lin) * SYMREC_BYTES);      // A/B: entries straight to global memory
+        auto put_sym = [&](unsigned e) { if (ns < SYMREC_SLOTS) gout[ns + 1] = e; ns++; };
+#else
+        auto put_sym = [&](unsigned e) { if (ns < SYMREC_SLOTS) scr[((ns + 1) >> 1) * (T3_THREADS * 2) + ((ns + 1) & 1)] = e; ns++; };
+#endif
+        const int last0 = last;
+        unsigned w = last ? myew[(last - 1) * T3_THREADS] : 0u;
+        if (last == 0 || (w & 0xFCu) != (63u << 2)) { put_sym(0u); if (so.hist) atomicAdd(&shist[160], 1u); }      // EOB
+        while (last != 0) {
+          const int pos = (int)((w & 0xFFu) >> 2), val = (int)w >> 16;
+          const int pr = (int)((w >> 8) & 0xFFu);
+          const unsigned wn = pr ? myew[(pr - 1) * T3_THREADS] : 0u;
+          const int run = pos - (int)((wn & 0xFFu) >> 2) - 1;
+          const int nb = nbits_of(abs(val));
+          const unsigned vb = (unsigned)(val + (val >> 31)) & ((1u << nb) - 1u);
+          put_sym((unsigned)(((run & 15) << 4) | nb) | vb << 16);
+          for (int z = run >> 4; z > 0; z--) put_sym(0xF0u);
+          if (so.hist) { atomicAdd(&shist[(run & 15) * 10 + nb - 1], 1u); if (run >> 4) atomicAdd(&shist[161], (unsigned)(run >> 4)); }
+          last = pr; w = wn;
+        }
+#if SYMREC_DIRECT
+        gout[0] = ns > SYMREC_SLOTS ? 0x80u : (unsigned)ns; (void)scr;
+#else
+        scr[0] = ns > SYMREC_SLOTS ? 0x80u : (unsigned)ns;
+        // whole 32-byte sectors leave (the words past the last entry are whatever the list held)
+        const int nw = 1 + min(ns, SYMREC_SLOTS);
+        uint4 *dst = reinterpret_cast<uint4 *>(so.sym + (rbase + lin) * SYMREC_BYTES);
+        for (int v = 0; 4 * v < nw; v += 2) {
+          const uint2 a = myrec[(2 * v) * T3_THREADS], b = myrec[(2 * v + 1) * T3_THREADS];
+          const uint2 c2 = myrec[(2 * v + 2) * T3_THREADS], d2 = myrec[(2 * v + 3) * T3_THREADS];
+          dst[v] = make_uint4(a.x, a.y, b.x, b.y);
+          dst[v + 1] = make_uint4(c2.x, c2.y, d2.x, d2.y);
+        }
+#endif
+        so.dcq[rbase + lin] = (int16_t)dc_q;
+        if (so.keep_coef || ns > SYMREC_SLOTS) write_block(last0);
       }
-      if (SEQ_SPARSE_ENC) rec[rbase + lin].nzmask = fm;
+    }
+  }
+  if (so.hist) {
+    __syncthreads();
+    uint32_t *gh = so.hist + ((size_t)img * HIST_SLOTS + 4 + c.ac_tbl) * HIST_BINS;
+    for (int i = tid; i < 162; i += T3_THREADS) {
+      const unsigned v = shist[i];
+      if (v) atomicAdd(&gh[i < 160 ? (((i / 10) << 4) | (i % 10 + 1)) : i == 160 ? 0 : 0xF0], v);
     }
   }
 }
 
 template <int MM>
 static void launch_t3(dim3 grid, cudaStream_t s, const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                      DcRec *rec, const RecLayout &rl, const SRec *srec, const uint32_t *splits)
+                      DcRec *rec, const RecLayout &rl, const SRec *srec, const uint32_t *splits, const SymOut &so)
 {
   // per device: an application may hold encoders on several GPUs in one process, so the opt-in is not cached
   if (sizeof(T3Smem<MM>) + 8192 > 48 * 1024) cudaFuncSetAttribute(k_trellis_ac3<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T3Smem<MM>));
-  k_trellis_ac3<MM><<<grid, T3_THREADS, sizeof(T3Smem<MM>), s>>>(g, tc, tabs, tabs_set_stride, rec, rl, srec, splits); LAUNCHED();
+  k_trellis_ac3<MM><<<grid, T3_THREADS, sizeof(T3Smem<MM>), s>>>(g, tc, tabs, tabs_set_stride, rec, rl, srec, splits, so); LAUNCHED();
 }
 void launch_trellis_ac3(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                        DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s)
+                        DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, const SymOut &so, int n, cudaStream_t s)
 {
   // splits: 4 words per (image, component), followed by the sort's scratch counters (2 x 64 words each)
   launch_sort2(g, rec, rl, static_cast<SRec *>(srec), splits, splits + (size_t)n * g.nc * 4, 15, n, s);
@@ -2074,10 +2343,28 @@ void launch_trellis_ac3(const Geom &g, const TrellisConsts *tc, const DevHuff *t
   // largest blocks first: the classes touch disjoint blocks.  The two big-list classes hold 2 / 4 CTAs per SM (96 / 48 KB of
   // lists): a full-size grid of CTAs that mostly find their class empty costs more there than the few chunks are worth,
   // so they get 8 / 16 CTAs per (image, component), still one to two waves when the classes are full (high quality settings)
-  launch_t3<64>(dim3(min(gx, 8u), grid.y), s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
-  launch_t3<32>(dim3(min(gx, 16u), grid.y), s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
-  launch_t3<15>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
-  launch_t3<8>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits);
+  launch_t3<64>(dim3(min(gx, 8u), grid.y), s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits, so);
+  launch_t3<32>(dim3(min(gx, 16u), grid.y), s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits, so);
+  launch_t3<15>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits, so);
+  launch_t3<8>(grid, s, g, tc, tabs, tabs_set_stride, rec, rl, sr, splits, so);
+}
+
+// the real blocks' DC values gathered into the dense array (after the DC trellis kernels that do not write it themselves)
+__global__ void __launch_bounds__(256) k_dc_collect(Geom g, RecLayout rl, int16_t *__restrict__ dcq)
+{
+  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
+  const CompGeom &c = g.c[ci];
+  const long long nblk = (long long)c.wib * c.hib, t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nblk) return;
+  const int row = (int)(t / c.wib), col = (int)(t - (long long)row * c.wib);
+  dcq[(size_t)img * rl.per_image + rl.comp_off[ci] + t] = c.coef[(((size_t)img * c.hpad + row) * c.wpad + col) * 64];
+}
+static void launch_dc_collect(const Geom &g, const RecLayout &rl, int16_t *dcq, int n, cudaStream_t s)
+{
+  long long mb = 0;
+  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
+  dim3 grid((unsigned)((mb + 255) / 256), n * g.nc);
+  k_dc_collect<<<grid, 256, 0, s>>>(g, rl, dcq); LAUNCHED();
 }
 
 // =====================================================================
@@ -2290,6 +2577,12 @@ __global__ void __launch_bounds__(64) k_trellis_dc_warp(Geom g, const TrellisCon
 // Arithmetic, association order and tie-breaks are those of k_trellis_dc.
 // ---------------------------------------------------------------------
 #define DC2_WARPS 2
+// FAST instantiation: the rates of a step's 9 predecessor differences, |D0 -+ l|, come from one table indexed by the
+// signed difference (consecutive words from one base address) instead of abs / find-leading-one / table per difference
+#ifndef DC_TABLE
+#define DC_TABLE 1
+#endif
+#define DC_TAB_HALF 512
 struct DcDiv { unsigned mul[4]; int shift[4]; };
 // FLO: index of the most significant set bit, 0xFFFFFFFF for 0, so that
 // nbits(v) == bfind(v) + 1 (JPEG_NBITS) without the clz arithmetic.
@@ -2301,10 +2594,11 @@ __device__ __forceinline__ int bfind_u32(unsigned v) { int r; asm("bfind.u32 %0,
 template <bool FAST>
 __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const TrellisConsts *__restrict__ tc,
                                                                  const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
-                                                                 const DcRec *__restrict__ rec, RecLayout rl, int max_wib, DcDiv dv)
+                                                                 const DcRec *__restrict__ rec, RecLayout rl, int max_wib, DcDiv dv, int16_t *__restrict__ dcq, int write_coef)
 {
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ float T[36];                                   // T[1 + bfind(|d|)] = (float)(bits + ehufsi[bits])
+  __shared__ float Tt[(FAST && DC_TABLE) ? 2 * DC_TAB_HALF + 8 : 1];   // Tt[d + DC_TAB_HALF] = T[1 + bfind(|d|)], -DC_TAB_HALF <= d < DC_TAB_HALF + 8
   __shared__ DcRec stage[DC2_WARPS][3][32];
   const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
   const CompGeom &c = g.c[ci];
@@ -2313,6 +2607,10 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
     if (threadIdx.x < 33) T[threadIdx.x] = (float)((int)threadIdx.x + (int)dc->size[threadIdx.x & 255]);
   }
   __syncthreads();
+  if (FAST && DC_TABLE) {
+    for (int i = threadIdx.x; i < 2 * DC_TAB_HALF + 8; i += DC2_WARPS * 32) Tt[i] = T[1 + bfind_u32((unsigned)abs(i - DC_TAB_HALF))];
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane / 9, k = lane - grp * 9;                 // lanes 27..31: grp == 3 (help with loads only)
   const int gsel = grp < 3 ? grp : 0;
@@ -2374,8 +2672,16 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
         float rd[9];
         if (FAST) {
           const int D0 = cd - psgn * pbase, dstep = -psgn * pstep;
+          // |D0 + dstep l| = |E0 + l| with E0 = -+D0 when dstep = -+1 (every block but a row's first)
+          const int E0 = dstep < 0 ? -D0 : D0;
+          if (DC_TABLE && __all_sync(0xffffffffu, pstep != 0 && (unsigned)(E0 + DC_TAB_HALF) < (unsigned)(2 * DC_TAB_HALF))) {
+            const float *tp = Tt + (E0 + DC_TAB_HALF);
 #pragma unroll
-          for (int l = 0; l < 9; l++) rd[l] = T[1 + bfind_u32((unsigned)abs(D0 + dstep * l))] + dist;
+            for (int l = 0; l < 9; l++) rd[l] = tp[l] + dist;
+          } else {
+#pragma unroll
+            for (int l = 0; l < 9; l++) rd[l] = T[1 + bfind_u32((unsigned)abs(D0 + dstep * l))] + dist;
+          }
         } else {
 #pragma unroll
           for (int l = 0; l < 9; l++) {
@@ -2438,7 +2744,8 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
         if (cdv >= lim) cdv = lim - 1;
         if (cdv <= -lim) cdv = -lim + 1;
         if (sign) cdv = -cdv;
-        c.coef[(((size_t)img * c.hpad + rowg[gg]) * c.wpad + bi) * 64] = (int16_t)cdv;
+        if (write_coef) c.coef[(((size_t)img * c.hpad + rowg[gg]) * c.wpad + bi) * 64] = (int16_t)cdv;
+        if (dcq) dcq[comp_rec + (size_t)rowg[gg] * wib + bi] = (int16_t)cdv;
         if (bi == wib - 1) lastv = cdv;
       }
       lastv = __shfl_sync(0xffffffffu, lastv, (wib - 1) & 31);
@@ -2449,7 +2756,7 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
 }
 
 void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                       const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int vertical, int n, cudaStream_t s)
+                       const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int vertical, int16_t *dcq, int write_coef, int n, cudaStream_t s)
 {
   int n_imcu = 0, max_wib = 0;
   for (int ci = 0; ci < g.nc; ci++) { n_imcu = max(n_imcu, (g.c[ci].hib + g.c[ci].v - 1) / g.c[ci].v); max_wib = max(max_wib, g.c[ci].wib); }
@@ -2459,6 +2766,7 @@ void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *ta
     dim3 grid((n_imcu + 63) / 64, n * g.nc);
     k_trellis_dc<<<grid, 64, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, bt, rl);
     LAUNCHED();
+    if (dcq) launch_dc_collect(g, rl, dcq, n, s);
     return;
   }
   // warp-cooperative kernel when the chains' back pointers fit in shared memory
@@ -2479,8 +2787,8 @@ void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *ta
       int ncand = (2 + 60 / (int)(d >> 3)) | 1; if (ncand > 9) ncand = 9;
       fast = fast && ncand == 9 && (int)((32768 + d / 2) / d) + 9 < (1 << g.max_coef_bits) - 1;
     }
-    if (fast) k_trellis_dc_v2<true><<<grid, DC2_WARPS * 32, smem2, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, max_wib, dv);
-    else k_trellis_dc_v2<false><<<grid, DC2_WARPS * 32, smem2, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, max_wib, dv);
+    if (fast) k_trellis_dc_v2<true><<<grid, DC2_WARPS * 32, smem2, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, max_wib, dv, dcq, write_coef || !dcq);
+    else k_trellis_dc_v2<false><<<grid, DC2_WARPS * 32, smem2, s>>>(g, tc, tabs, tabs_set_stride, rec, rl, max_wib, dv, dcq, write_coef || !dcq);
     LAUNCHED();
     return;
   }
@@ -2496,6 +2804,7 @@ void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *ta
     k_trellis_dc<<<grid, 64, 0, s>>>(g, tc, tabs, tabs_set_stride, rec, bt, rl);
   }
   LAUNCHED();
+  if (dcq) launch_dc_collect(g, rl, dcq, n, s);
 }
 
 // =====================================================================
@@ -2554,7 +2863,8 @@ __device__ __forceinline__ unsigned cta_excl_scan_256(unsigned v, unsigned *ws /
 
 // One tile = the 256 blocks of one CTA; tile_bits[img][tile] = bits the tile emits; blk_bits[img][t] = bits
 // the tile's blocks before t emit (exclusive prefix inside the tile).
-__global__ void __launch_bounds__(256) k_block_bits_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ nz_rec, RecLayout rl, const DevHuff *__restrict__ tabs, size_t stride,
+__global__ void __launch_bounds__(256) k_block_bits_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ nz_rec, const uint8_t *__restrict__ sym, const int16_t *__restrict__ dcq,
+                                                        RecLayout rl, const DevHuff *__restrict__ tabs, size_t stride,
                                                         uint32_t *__restrict__ blk_bits, uint32_t *__restrict__ tile_bits, uint32_t *__restrict__ status)
 {
   __shared__ ScanTables st;
@@ -2564,7 +2874,13 @@ __global__ void __launch_bounds__(256) k_block_bits_seq(Geom g, ScanDesc sd, con
   __syncthreads();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned bits = 0;
-  if (t < sd.nblocks) {
+  if (t < sd.nblocks && sym) {
+    const CompGeom &c = g.c[sd.ci[sd.k_comp[(int)(t % sd.bim)]]];
+    CountSink sink{st.size[c.dc_tbl], st.size[4 + c.ac_tbl], 0u, 0};
+    walk_seq_rec(g, sd, sym, dcq, rl, img, t, sink);
+    if (sink.bad) atomicOr(&status[img], 2u);
+    bits = sink.bits;
+  } else if (t < sd.nblocks) {
     int sci, k; long long mcu;
     const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
     int last = prev_dc(g, sd, img, t, sci, mcu, k);
@@ -2668,7 +2984,8 @@ __device__ __forceinline__ void emit_restart_marker(BitSink &sink, const ScanDes
   atomicOr(&mark[byte >> 5], 1u << (byte & 31));
 }
 
-__global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ rec, RecLayout rl, const DevHuff *__restrict__ tabs, size_t stride,
+__global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ rec, const uint8_t *__restrict__ sym, const int16_t *__restrict__ dcq,
+                                                    RecLayout rl, const DevHuff *__restrict__ tabs, size_t stride,
                                                     const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits /* per-tile totals: not read here */,
                                                     const unsigned long long *__restrict__ tile_base,
                                                     const uint32_t *__restrict__ seg_corr, long long seg_stride,
@@ -2686,15 +3003,18 @@ __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const D
   if (t < sd.nblocks) {
     unsigned long long off = tb + blk_bits[(size_t)img * sd.nblocks + t];
     if (sd.ri) off += seg_corr[(size_t)img * seg_stride + t / ((long long)sd.ri * sd.bim)];
-    int sci, k; long long mcu;
-    const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
-    int last = prev_dc(g, sd, img, t, sci, mcu, k);
-    const CompGeom &c = g.c[sd.ci[sci]];
+    const CompGeom &c = g.c[sd.ci[sd.k_comp[(int)(t % sd.bim)]]];
     BitSink sink;
     sink.buf = gbuf; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
     sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
-    if (SEQ_SPARSE_ENC && rec) walk_seq_sparse(blk, block_nzmask(g, sd, rec, rl, img, sci, mcu, k), last, sink);
-    else walk_seq_block(blk, last, sink);
+    if (sym) walk_seq_rec(g, sd, sym, dcq, rl, img, t, sink);
+    else {
+      int sci, k; long long mcu;
+      const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
+      int last = prev_dc(g, sd, img, t, sci, mcu, k);
+      if (SEQ_SPARSE_ENC && rec) walk_seq_sparse(blk, block_nzmask(g, sd, rec, rl, img, sci, mcu, k), last, sink);
+      else walk_seq_block(blk, last, sink);
+    }
     if (sd.ri) emit_restart_marker(sink, sd, t, mark + (size_t)img * mark_stride_words);
     sink.finish();
   }
@@ -3115,18 +3435,21 @@ struct BitSinkP : BitSink {
 __global__ void __launch_bounds__(256) k_gather_prog(Geom g, ScanDesc sd, const uint32_t *__restrict__ aux, const uint32_t *__restrict__ run_e,
                                                      const unsigned long long *__restrict__ pm, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
 {
-  __shared__ unsigned sh[HIST_SLOTS * HIST_BINS];
+  __shared__ unsigned sh[GATHER_COPIES_SCAN][HIST_SLOTS * HIST_BINS];
   int img = blockIdx.y;
   const int Al = sd.al_img ? sd.al_img[img] : sd.Al;     // scan search: this scan's Al is the image's best Al so far (jcmaster.c:477-488)
-  for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) sh[i] = 0;
+  for (int i = threadIdx.x; i < GATHER_COPIES_SCAN * HIST_SLOTS * HIST_BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
   __syncthreads();
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < sd.nblocks) {
+#pragma unroll 1
+  for (int tile = 0; tile < GATHER_TILES; tile++) {
+    long long t = ((long long)blockIdx.x * GATHER_TILES + tile) * blockDim.x + threadIdx.x;
+    if (t >= sd.nblocks) break;
     int sci, k; long long mcu;
     const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
     int last = prev_dc_shifted(g, sd, Al, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
-    HistSinkP sink{sh + c.dc_tbl * HIST_BINS, sh + (4 + c.ac_tbl) * HIST_BINS, 0, g.max_coef_bits};
+    unsigned *mine = sh[threadIdx.x % GATHER_COPIES_SCAN];
+    HistSinkP sink{mine + c.dc_tbl * HIST_BINS, mine + (4 + c.ac_tbl) * HIST_BINS, 0, g.max_coef_bits};
     unsigned a = 0, re = 0; unsigned long long ev = 0, one = 0, bit = 0;
     if (sd.Ss) load_prog_aux(sd, aux, run_e, pm, img, t, a, re, ev, one, bit);
     walk_prog_block(blk, sd, Al, last, a, re, ev, one, bit, sink);
@@ -3134,7 +3457,12 @@ __global__ void __launch_bounds__(256) k_gather_prog(Geom g, ScanDesc sd, const 
   }
   __syncthreads();
   uint32_t *gh = hist + (size_t)img * HIST_SLOTS * HIST_BINS;
-  for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&gh[i], sh[i]);
+  for (int i = threadIdx.x; i < HIST_SLOTS * HIST_BINS; i += blockDim.x) {
+    unsigned v = 0;
+#pragma unroll
+    for (int cp = 0; cp < GATHER_COPIES_SCAN; cp++) v += sh[cp][i];
+    if (v) atomicAdd(&gh[i], v);
+  }
 }
 
 __global__ void __launch_bounds__(256) k_block_bits_prog(Geom g, ScanDesc sd, const DevHuff *__restrict__ tabs, size_t stride,
@@ -3264,16 +3592,16 @@ void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint3
 }
 void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, const unsigned long long *pm, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
 {
-  dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
+  dim3 grid((unsigned)((sd.nblocks + 256 * GATHER_TILES - 1) / (256 * GATHER_TILES)), n);
   k_gather_prog<<<grid, 256, 0, s>>>(g, sd, aux, run_e, pm, hist, status); LAUNCHED();
 }
 
-void launch_block_bits(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t stride, int progressive,
+void launch_block_bits(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const uint8_t *sym, const int16_t *dcq, const RecLayout &rl, const DevHuff *tabs, size_t stride, int progressive,
                        uint32_t *blk_bits, uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e, const unsigned long long *pm, uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
   if (progressive) k_block_bits_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, pm, blk_bits, tile_bits, status);
-  else k_block_bits_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, rl, tabs, stride, blk_bits, tile_bits, status);
+  else k_block_bits_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, sym, dcq, rl, tabs, stride, blk_bits, tile_bits, status);
   LAUNCHED();
 }
 void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint32_t *tile_bits, unsigned long long *tile_base,
@@ -3284,14 +3612,14 @@ void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint
   k_scan_layout<<<n, 256, 0, s>>>(sd, blk_bits, tile_bits, ntiles, tile_base, seg_corr, seg_stride, total_bits, capacity_bits, status);
   LAUNCHED();
 }
-void launch_encode(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t stride, int progressive,
+void launch_encode(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const uint8_t *sym, const int16_t *dcq, const RecLayout &rl, const DevHuff *tabs, size_t stride, int progressive,
                    const uint32_t *blk_bits, const uint32_t *tile_bits, const unsigned long long *tile_base, const uint32_t *seg_corr, long long seg_stride,
                    const uint32_t *blk_aux, const uint32_t *run_e, const unsigned long long *pm,
                    uint32_t *bitbuf, size_t bitbuf_stride_words, uint32_t *mark, size_t mark_stride_words, const uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 255) / 256), n);
   if (progressive) k_encode_prog<<<grid, 256, 0, s>>>(g, sd, tabs, stride, blk_aux, run_e, pm, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
-  else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, rl, tabs, stride, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
+  else k_encode_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, sym, dcq, rl, tabs, stride, blk_bits, tile_bits, tile_base, seg_corr, seg_stride, bitbuf, bitbuf_stride_words, mark, mark_stride_words, status);
   LAUNCHED();
 }
 size_t stuff_tiles(size_t bitbuf_stride_words) { return (bitbuf_stride_words + STUFF_TILE_WORDS - 1) / STUFF_TILE_WORDS; }

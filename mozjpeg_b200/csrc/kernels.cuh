@@ -105,6 +105,17 @@ struct RecLayout { long long per_image; long long comp_off[4]; };
 // which of the 8 table slots to (re)build for set i: m[i % period]
 struct SlotMasks { uint32_t m[4]; int period; };
 
+// Sequential scans after the AC trellis do not re-read the coefficient planes: the trellis back-track leaves, per real
+// block (indexed like the side records), a symbol record -- word 0: number of entries (bit 7: more than SYMREC_SLOTS, the
+// readers then walk the coefficient block), words 1..: one entry per AC symbol of the block, the stream's LAST symbol
+// first, entry = run/size symbol | value bits << 16 (ZRL and EOB are entries too) -- and the DC trellis a dense array of
+// the final DC values; `hist` (or nullptr) receives the blocks' AC symbol counts, [img][HIST_SLOTS][HIST_BINS].
+#define SYMREC_BYTES 128
+#define SYMREC_SLOTS 31
+// keep_coef: also rewrite the coefficient planes (the debug tap reads them); otherwise only blocks whose record overflowed
+// get their coefficients written back, and the planes keep the plain-quantized values elsewhere.
+struct SymOut { uint8_t *sym; int16_t *dcq; uint32_t *hist; int keep_coef; };
+
 #define HIST_BINS 257
 #define HIST_SLOTS 8          // [is_ac*4 + tbl_no]
 
@@ -125,7 +136,7 @@ void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_set_stri
 // splits: 4 class boundaries per (image, component) followed by 128 words of sorting counters each) and runs one
 // class-specific kernel per count class
 void launch_trellis_ac3(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                        DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, int n, cudaStream_t s);
+                        DcRec *rec, const RecLayout &rl, void *srec, uint32_t *splits, const SymOut &so, int n, cudaStream_t s);
 // use_scans_in_trellis: quantize_trellis restricted to the zigzag band [Ss, Se]
 void launch_trellis_ac_band(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
                             DcRec *rec, const RecLayout &rl, int Ss, int Se, const uint16_t *qimg, float4 *eo, int n, cudaStream_t s);
@@ -135,13 +146,19 @@ void launch_trellis_eob_rows(const Geom &g, const DevHuff *tabs, size_t tabs_set
 // trellis_q_opt: accumulate the table-fitting sums of the components in g ([img][4][2][64] int64) / re-fit the per-image tables
 void launch_qopt_sums(const Geom &g, long long *qsum, int n, cudaStream_t s);
 void launch_qopt_update(long long *qsum, uint16_t *qimg, int n, cudaStream_t s);
+// dcq (or nullptr): dense array of the final DC values, one per real block, indexed like the side records; with it and
+// write_coef == 0 the coefficient planes are not touched (where the kernel in use can do without)
 void launch_trellis_dc(const Geom &g, const TrellisConsts *tc, const DevHuff *tabs, size_t tabs_set_stride,
-                       const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int vertical, int n, cudaStream_t s);
+                       const DcRec *rec, unsigned long long *bt, const RecLayout &rl, int vertical, int16_t *dcq, int write_coef, int n, cudaStream_t s);
+// DC statistics of a sequential scan from the dense DC array (+ the EOB of every dummy block): with the AC counts the
+// trellis back-track left in `hist`, the scan's complete statistics (encode_mcu_gather, jchuff.c:886-915)
+void launch_gather_seq_dc(const Geom &g, const ScanDesc &sd, const int16_t *dcq, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 // tile_last / tile_first: int [n][ceil(nblocks/256)] scratch; pm: the blocks' event masks of this AC scan,
 // unsigned long long [3][n][nblocks] (written here, read by the three symbol walks of the scan)
 void launch_prog_prepare(const Geom &g, const ScanDesc &sd, uint32_t *aux, uint32_t *run_e, unsigned long long *pm, int *tile_last, int *tile_first, int n, cudaStream_t s);
 void launch_gather_prog(const Geom &g, const ScanDesc &sd, const uint32_t *aux, const uint32_t *run_e, const unsigned long long *pm, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
-void launch_block_bits(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
+// sym / dcq (here and in launch_encode): the symbol records and dense DC values of sequential scans after the trellis, or nullptr
+void launch_block_bits(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const uint8_t *sym, const int16_t *dcq, const RecLayout &rl, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
                        uint32_t *blk_bits, uint32_t *tile_bits, const uint32_t *blk_aux, const uint32_t *run_e, const unsigned long long *pm, uint32_t *status, int n, cudaStream_t s);
 // tile_base[img][tile] / seg_corr[img][segment] / total_bits[img] from the tile sums (and the restart interval)
 void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint32_t *tile_bits, unsigned long long *tile_base,
@@ -149,7 +166,7 @@ void launch_scan_layout(const ScanDesc &sd, const uint32_t *blk_bits, const uint
                         uint32_t *status, int n, cudaStream_t s);
 // mark: bitmap over the unstuffed bytes of each image (restart markers' 0xFF), only touched when sd.ri != 0
 // nz_rec: the side records holding every block's final non-zero positions (trellis on, sequential scans), or nullptr
-void launch_encode(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
+void launch_encode(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const uint8_t *sym, const int16_t *dcq, const RecLayout &rl, const DevHuff *tabs, size_t tabs_image_stride, int progressive,
                    const uint32_t *blk_bits, const uint32_t *tile_bits, const unsigned long long *tile_base, const uint32_t *seg_corr, long long seg_stride,
                    const uint32_t *blk_aux, const uint32_t *run_e, const unsigned long long *pm,
                    uint32_t *bitbuf, size_t bitbuf_image_stride_words, uint32_t *mark, size_t mark_stride_words, const uint32_t *status, int n, cudaStream_t s);
