@@ -527,6 +527,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     SymOut so; so.sym = symrec ? A.d_sym.as<uint8_t>() : nullptr; so.dcq = symrec ? A.d_dcq.as<int16_t>() : nullptr;
     so.hist = symstats ? A.d_hist.as<uint32_t>() : nullptr;
     so.keep_coef = e->keep_plain ? 1 : 0;                       // B200JPEG_KEEP_PLAIN=1: the debug taps read the final planes
+    so.dcq_ac = p->trellis_quant_dc ? 0 : 1;
     uint16_t *qimg = qopt ? A.d_qimg.as<uint16_t>() : nullptr;
     if (qopt) {
       // every image starts from the batch's tables (natural order, like JQUANT_TBL.quantval)
@@ -651,7 +652,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
         if (!symstats) CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes, s));
         if (pl.progressive) launch_gather_prog(g, sd, aux, run_e, pm, A.d_hist.as<uint32_t>(), status, n, s);
         else if (symstats) launch_gather_seq_dc(g, sd, dcq, rl, A.d_hist.as<uint32_t>(), status, n, s);      // the AC counts are there already
-        else launch_gather_seq(g, sd, nz_rec, rl, A.d_hist.as<uint32_t>(), status, n, s);
+        else launch_gather_seq(g, sd, nz_rec, sym, dcq, rl, A.d_hist.as<uint32_t>(), status, n, s);
         tm.mark("scan_tables");
         SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = 1; masks.m[0] = scan_slot_mask(pl, sd);
         launch_gen_tables(A.d_hist.as<uint32_t>(), tset, tstride, masks, n, s);

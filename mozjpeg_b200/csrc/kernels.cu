@@ -1383,7 +1383,8 @@ struct HistSink {
 
 // nz_rec: the side records holding every block's final non-zero positions (after the AC trellis), or nullptr: the walk
 // then touches only those coefficients (and the 32-byte sectors they sit in) instead of the whole 128-byte block
-__global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ nz_rec, RecLayout rl, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
+__global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ nz_rec, const uint8_t *__restrict__ sym, const int16_t *__restrict__ dcq,
+                                                    RecLayout rl, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
 {
   __shared__ unsigned sh[GATHER_COPIES_SCAN][HIST_SLOTS * HIST_BINS];
   int img = blockIdx.y;
@@ -1393,11 +1394,18 @@ __global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, const D
   for (int tile = 0; tile < GATHER_TILES; tile++) {
     long long t = ((long long)blockIdx.x * GATHER_TILES + tile) * blockDim.x + threadIdx.x;
     if (t >= sd.nblocks) break;
+    unsigned *mine = sh[threadIdx.x % GATHER_COPIES_SCAN];
+    if (sym) {                                         // symbol records (a scan script with several sequential scans: per-scan counts)
+      const CompGeom &c = g.c[sd.ci[sd.k_comp[(int)(t % sd.bim)]]];
+      HistSink sink{mine + c.dc_tbl * HIST_BINS, mine + (4 + c.ac_tbl) * HIST_BINS, 0, g.max_coef_bits};
+      walk_seq_rec(g, sd, sym, dcq, rl, img, t, sink);
+      if (sink.bad) atomicOr(&status[img], 2u);
+      continue;
+    }
     int sci, k; long long mcu;
     const int16_t *blk = block_ptr(g, sd, img, t, sci, mcu, k);
     int last = prev_dc(g, sd, img, t, sci, mcu, k);
     const CompGeom &c = g.c[sd.ci[sci]];
-    unsigned *mine = sh[threadIdx.x % GATHER_COPIES_SCAN];
     HistSink sink{mine + c.dc_tbl * HIST_BINS, mine + (4 + c.ac_tbl) * HIST_BINS, 0, g.max_coef_bits};
     if (SEQ_SPARSE_STATS && nz_rec) walk_seq_sparse(blk, block_nzmask(g, sd, nz_rec, rl, img, sci, mcu, k), last, sink);
     else walk_seq_block(blk, last, sink);
@@ -1419,7 +1427,7 @@ __global__ void __launch_bounds__(256) k_gather_seq(Geom g, ScanDesc sd, const D
 // consecutive lanes fetch one block's 128 bytes: 4 lines per request instead of 32), stored with the piece index XORed
 // by the block's low bits so that the per-thread read-back of whole blocks is conflict-free.
 #ifndef GATHER_STAGE
-#define GATHER_STAGE 1
+#define GATHER_STAGE 0
 #endif
 __global__ void __launch_bounds__(256) k_gather_comp(Geom g, RestartSpec rs, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
 {
@@ -1482,10 +1490,10 @@ void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, ui
   LAUNCHED();
 }
 
-void launch_gather_seq(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
+void launch_gather_seq(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const uint8_t *sym, const int16_t *dcq, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
 {
   dim3 grid((unsigned)((sd.nblocks + 256 * GATHER_TILES - 1) / (256 * GATHER_TILES)), n);
-  k_gather_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, rl, hist, status);
+  k_gather_seq<<<grid, 256, 0, s>>>(g, sd, nz_rec, sym, dcq, rl, hist, status);
   LAUNCHED();
 }
 
@@ -2022,7 +2030,10 @@ __device__ __forceinline__ float u2f_exact(unsigned v) { return __uint_as_float(
 #define SYMREC_DIRECT 0
 #endif
 #ifndef T3_MINB_8
-#define T3_MINB_8 8            // resident CTAs per SM the compiler must allow for the <= 8 entries class
+#define T3_MINB_8 8            // resident CTAs per SM the compiler must allow for the <= 8 entries class (12: measured slower)
+#endif
+#ifndef T3_MINB_15
+#define T3_MINB_15 8           // ... and for the 9..15 entries class
 #endif
 template <int MM> struct T3Smem {
   uint2 rec[MM][T3_THREADS];       // before the entry is processed: {A[p-1], p | raw << 16}; after: {-A[p], accumulated cost}
@@ -2053,7 +2064,7 @@ __device__ __forceinline__ float t3_dist(const int cand, const int q, const int 
 }
 
 template <int MM>
-__global__ void __launch_bounds__(T3_THREADS, MM <= 8 ? T3_MINB_8 : MM <= 15 ? 8 : MM <= 32 ? 4 : 2)
+__global__ void __launch_bounds__(T3_THREADS, MM <= 8 ? T3_MINB_8 : MM <= 15 ? T3_MINB_15 : MM <= 32 ? 4 : 2)
 k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__restrict__ tabs, size_t tabs_set_stride,
               DcRec *__restrict__ rec, RecLayout rl, const SRec *__restrict__ srec, const uint32_t *__restrict__ splits, SymOut so)
 {
@@ -2122,12 +2133,10 @@ k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__res
     uint4 rv[8];
 #pragma unroll
     for (int v = 0; v < 8; v++) rv[v] = make_uint4(0, 0, 0, 0);
-    unsigned dc_q = 0;
     if (live) {
       const uint4 *r4 = reinterpret_cast<const uint4 *>(raw16);
 #pragma unroll
       for (int v = 0; v < 8; v++) rv[v] = r4[v];
-      dc_q = (unsigned)(unsigned short)o16[0];                 // the DC value survives the rewrite
     }
     float lambda;
     {
@@ -2246,7 +2255,7 @@ k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__res
       // output: zeros except the back-tracked chain (:1211-1222)
       uint4 *q4 = reinterpret_cast<uint4 *>(o16);
       auto write_block = [&](int lst) {
-        q4[0] = make_uint4(dc_q, 0, 0, 0);
+        q4[0] = make_uint4((unsigned)(unsigned short)o16[0], 0, 0, 0);        // the DC value survives the rewrite
 #pragma unroll
         for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
         unsigned long long fm = 0;
@@ -2305,7 +2314,7 @@ k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__res
           dst[v + 1] = make_uint4(c2.x, c2.y, d2.x, d2.y);
         }
 #endif
-        so.dcq[rbase + lin] = (int16_t)dc_q;
+        if (so.dcq_ac) so.dcq[rbase + lin] = o16[0];                 // no DC trellis behind this kernel: the plain-quantized DC is final
         if (so.keep_coef || ns > SYMREC_SLOTS) write_block(last0);
       }
     }
@@ -2599,7 +2608,7 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ float T[36];                                   // T[1 + bfind(|d|)] = (float)(bits + ehufsi[bits])
   __shared__ float Tt[(FAST && DC_TABLE) ? 2 * DC_TAB_HALF + 8 : 1];   // Tt[d + DC_TAB_HALF] = T[1 + bfind(|d|)], -DC_TAB_HALF <= d < DC_TAB_HALF + 8
-  __shared__ DcRec stage[DC2_WARPS][3][32];
+  __shared__ int4 stage[DC2_WARPS][3][32];                  // per staged block {|raw DC|, qval - half, +1 / -1, lambda bits}: what a step needs of the record
   const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
   const CompGeom &c = g.c[ci];
   {
@@ -2648,25 +2657,26 @@ __global__ void __launch_bounds__(DC2_WARPS * 32) k_trellis_dc_v2(Geom g, const 
     for (int bi0 = 0; bi0 < wib; bi0 += 32) {
       __syncwarp();
 #pragma unroll
-      for (int gg = 0; gg < 3; gg++) stage[warp][gg][lane] = nxt[gg];
+      for (int gg = 0; gg < 3; gg++) {
+        const int raw = nxt[gg].raw_dc, x = abs(raw);
+        const int qval = (int)(((unsigned long long)(unsigned)(x + qhalf) * qmul) >> qshift);       // (x + q/2) / q, exact
+        stage[warp][gg][lane] = make_int4(x, qval - half, 1 + 2 * (raw >> 31), __float_as_int(nxt[gg].lambda_dc));
+      }
       __syncwarp();
       if (bi0 + 32 < wib) {
 #pragma unroll
         for (int gg = 0; gg < 3; gg++) nxt[gg] = rec[comp_rec + (size_t)rowg[gg] * wib + min(bi0 + 32 + lane, wib - 1)];
       }
       const int nstep = min(32, wib - bi0);
-      const DcRec *sp = &stage[warp][gsel][0];
+      const int4 *sp = &stage[warp][gsel][0];
 #pragma unroll 1
       for (int st = 0; st < nstep; st++) {
-        const DcRec r = sp[st];
-        const int raw = r.raw_dc, sign = raw >> 31, x = abs(raw);
-        const int qval = (int)(((unsigned long long)(unsigned)(x + qhalf) * qmul) >> qshift);       // (x + q/2) / q, exact
-        const int base = qval - half;
+        const int4 r = sp[st];
+        const int x = r.x, base = r.y, sgn = r.z;                   // |raw DC|, qval - half, sign
         int cd = base + k;
         if (!FAST) { if (cd >= lim) cd = lim - 1; if (cd <= -lim) cd = -lim + 1; }
         const int delta = cd * q - x;
-        const float dist = (float)(delta * delta) * r.lambda_dc;
-        const int sgn = 1 + 2 * sign;                             // +1 / -1
+        const float dist = (float)(delta * delta) * __int_as_float(r.w);
         cd *= sgn;
         // rate + distortion against every predecessor candidate l (independent of the Viterbi state)
         float rd[9];
@@ -2984,6 +2994,12 @@ __device__ __forceinline__ void emit_restart_marker(BitSink &sink, const ScanDes
   atomicOr(&mark[byte >> 5], 1u << (byte & 31));
 }
 
+// the sequential packer's AC symbols: code and size from one table word, code and value bits in one put (at most 16 + 14 bits)
+struct BitSinkQ : BitSink {
+  const uint32_t *acs;          // code | size << 16
+  __device__ void ac(int sym, int nb, int v) { const unsigned e = acs[sym]; put(((e & 0xFFFFu) << nb) | ((unsigned)v & ((1u << nb) - 1u)), (int)(e >> 16) + nb); }
+};
+
 __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const DcRec *__restrict__ rec, const uint8_t *__restrict__ sym, const int16_t *__restrict__ dcq,
                                                     RecLayout rl, const DevHuff *__restrict__ tabs, size_t stride,
                                                     const uint32_t *__restrict__ blk_bits, const uint32_t *__restrict__ tile_bits /* per-tile totals: not read here */,
@@ -2993,8 +3009,14 @@ __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const D
                                                     uint32_t *__restrict__ mark, size_t mark_stride_words, const uint32_t *__restrict__ status)
 {
   __shared__ ScanTables st;
+  __shared__ uint32_t acs[4][256];
   int img = blockIdx.y;
   load_scan_tables(st, tabs, stride, img, g, sd, true);
+  __syncthreads();
+  for (int i = 0; i < sd.ncomps; i++) {
+    const int sl = g.c[sd.ci[i]].ac_tbl;
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) acs[sl][k] = (uint32_t)st.code[4 + sl][k] | (uint32_t)st.size[4 + sl][k] << 16;
+  }
   __syncthreads();
   if (status[img] & ~1u) return;            // an earlier stage flagged this image (overflow / bad coefficient)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -3004,9 +3026,10 @@ __global__ void __launch_bounds__(256) k_encode_seq(Geom g, ScanDesc sd, const D
     unsigned long long off = tb + blk_bits[(size_t)img * sd.nblocks + t];
     if (sd.ri) off += seg_corr[(size_t)img * seg_stride + t / ((long long)sd.ri * sd.bim)];
     const CompGeom &c = g.c[sd.ci[sd.k_comp[(int)(t % sd.bim)]]];
-    BitSink sink;
+    BitSinkQ sink;
     sink.buf = gbuf; sink.widx = off >> 5; sink.acc = 0; sink.nacc = (int)(off & 31);
     sink.dco = st.code[c.dc_tbl]; sink.aco = st.code[4 + c.ac_tbl]; sink.dsz = st.size[c.dc_tbl]; sink.asz = st.size[4 + c.ac_tbl];
+    sink.acs = acs[c.ac_tbl];
     if (sym) walk_seq_rec(g, sd, sym, dcq, rl, img, t, sink);
     else {
       int sci, k; long long mcu;

@@ -114,7 +114,8 @@ struct SlotMasks { uint32_t m[4]; int period; };
 #define SYMREC_SLOTS 31
 // keep_coef: also rewrite the coefficient planes (the debug tap reads them); otherwise only blocks whose record overflowed
 // get their coefficients written back, and the planes keep the plain-quantized values elsewhere.
-struct SymOut { uint8_t *sym; int16_t *dcq; uint32_t *hist; int keep_coef; };
+// dcq_ac: the AC trellis fills dcq with the plain-quantized DC values (no DC trellis will follow and write the final ones).
+struct SymOut { uint8_t *sym; int16_t *dcq; uint32_t *hist; int keep_coef; int dcq_ac; };
 
 #define HIST_BINS 257
 #define HIST_SLOTS 8          // [is_ac*4 + tbl_no]
@@ -129,7 +130,7 @@ void launch_dummy(const Geom &g, int n, cudaStream_t s);
 void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 // nz_rec (here and in launch_block_bits / launch_encode): the side records holding every block's final non-zero positions
 // (trellis on, sequential scans), or nullptr
-void launch_gather_seq(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
+void launch_gather_seq(const Geom &g, const ScanDesc &sd, const DcRec *nz_rec, const uint8_t *sym, const int16_t *dcq, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 void launch_seed_hist(uint32_t *hist, int slot, int n, cudaStream_t s);
 void launch_gen_tables(const uint32_t *hist, DevHuff *tabs, size_t tabs_set_stride, const SlotMasks &masks, int nsets, cudaStream_t s);
 // AC trellis of the default option set: sorts the side records by non-zero count (srec: 16 bytes per real block;
