@@ -194,7 +194,7 @@ int  b200jpeg_encoder_set_stream(b200jpeg_encoder *enc, void *cuda_stream);
 int  b200jpeg_encoder_set_chunk_images(b200jpeg_encoder *enc, int images_per_chunk);
 /* Images per chunk the last batch was processed with (= images per kernel launch). */
 int  b200jpeg_last_chunk_images(const b200jpeg_encoder *enc);
-/* Consecutive chunks alternate between `n_streams` (1 or 2, default 2) compute
+/* Consecutive chunks rotate over `n_streams` (1 to 4, default 2; B200JPEG_STREAMS in the environment) compute
  * streams, each with its own intermediate arenas, so that one chunk's
  * latency-bound phases (serial Huffman table construction, trellis chains)
  * overlap the other's bandwidth-bound ones.  With 1 stream the per-stage times

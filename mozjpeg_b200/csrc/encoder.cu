@@ -74,6 +74,7 @@ struct Plan {                // everything derived from b200jpeg_params
 using namespace b200;
 
 // intermediate HBM state of one chunk in flight
+#define MAX_ARENAS 4
 struct Arena {
   b200::DevBuf d_planes;             // input smoothing: the pre-pass's component planes
   b200::DevBuf d_coef[4], d_raw[4], d_plain[4], d_hist, d_tabs_trellis, d_rec, d_bt, d_srec, d_splits, d_best_al, d_qimg, d_qsum, d_eo, d_es;
@@ -101,8 +102,8 @@ struct b200jpeg_encoder {
   bool keep_plain = false;
   // device arenas sized for ONE chunk; two of them so that consecutive chunks can run on two
   // streams and fill each other's latency-bound phases (serial table construction, trellis chains)
-  Arena ar[2];
-  cudaStream_t sc[2] = {nullptr, nullptr};   // sc[0] aliases `stream`
+  Arena ar[MAX_ARENAS];
+  cudaStream_t sc[MAX_ARENAS] = {nullptr, nullptr, nullptr, nullptr};   // sc[0] aliases `stream`
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_streams = 2;
   // device buffers sized for the WHOLE batch
@@ -476,6 +477,13 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
   for (int ci = 0; ci < 4; ci++) g.plane[ci] = io.plane[ci];
   uint32_t *status = io.status;
 
+  const bool symrec = use_symrec(pl, p);
+  const bool symstats = symrec && pl.optimize && nscans == 1;
+  // with symbol records nothing behind the trellis-phase statistics reads the plain-quantized planes: where the forward
+  // kernel can take those statistics itself (forward_takes_stats), it does, and does not write the planes
+  // (B200JPEG_FWD_STATS=0 keeps the separate pass; the debug tap and coefficient input need the planes)
+  static const bool fstats_off = !(getenv("B200JPEG_FWD_STATS") && getenv("B200JPEG_FWD_STATS")[0] == '1');     // measured slower: off unless asked for
+  const bool fstats = symrec && !fstats_off && !e->keep_plain && g.raw_in != 2 && forward_takes_stats(g, p->dct_method);
   // ---- pass 0 data path: colour/downsample/FDCT/quantize (compress_first_pass) ----
   RecLayout rl; memset(&rl, 0, sizeof rl);
   for (int ci = 0; ci < g.nc; ci++) { rl.comp_off[ci] = rl.per_image; rl.per_image += (long long)g.c[ci].wib * g.c[ci].hib; }
@@ -499,13 +507,13 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     gf.raw_in = 1;
     tm.mark("forward");
   }
-  launch_forward(gf, src_dev, e->d_qt.as<QuantTables>(), qfast, p->dct_method, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, e->keep_plain ? 1 : 0, n, s);
+  if (fstats) CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes * g.nc, s));       // the forward kernel adds the trellis-phase AC counts
+  const FwdStats fs = {fstats ? A.d_hist.as<uint32_t>() : nullptr, fstats ? A.d_dcq.as<int16_t>() : nullptr, status, fstats ? 0 : 1};
+  launch_forward(gf, src_dev, e->d_qt.as<QuantTables>(), qfast, p->dct_method, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, e->keep_plain ? 1 : 0, fs, n, s);
   }
   tm.mark("dummy");
   launch_dummy(g, n, s);
 
-  const bool symrec = use_symrec(pl, p);
-  const bool symstats = symrec && pl.optimize && nscans == 1;
   // ---- trellis phase (jcmaster.c pass list).  The three
   //      per-component chains (statistics on the plain-quantized coefficients
   //      -> optimal tables -> quantize_trellis) are independent, so each step
@@ -527,7 +535,8 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     SymOut so; so.sym = symrec ? A.d_sym.as<uint8_t>() : nullptr; so.dcq = symrec ? A.d_dcq.as<int16_t>() : nullptr;
     so.hist = symstats ? A.d_hist.as<uint32_t>() : nullptr;
     so.keep_coef = e->keep_plain ? 1 : 0;                       // B200JPEG_KEEP_PLAIN=1: the debug taps read the final planes
-    so.dcq_ac = p->trellis_quant_dc ? 0 : 1;
+    so.dcq_ac = (p->trellis_quant_dc || fstats) ? 0 : 1;
+    so.dc_dense = fstats ? 1 : 0;
     uint16_t *qimg = qopt ? A.d_qimg.as<uint16_t>() : nullptr;
     if (qopt) {
       // every image starts from the batch's tables (natural order, like JQUANT_TBL.quantval)
@@ -537,8 +546,11 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     auto round = [&](const Geom &gr, const RecLayout &rlr, int bSs, int bSe) -> int {
     if (!pl.progressive) {
       tm.mark("trellis_stats");
+      if (fstats) launch_gather_comp_dc(gr, pl.rs, A.d_dcq.as<int16_t>(), rlr, A.d_hist.as<uint32_t>(), status, n, s);     // the AC counts are there already
+      else {
       CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes * gr.nc, s));
       launch_gather_comp(gr, pl.rs, A.d_hist.as<uint32_t>(), status, n, s);
+      }
       tm.mark("trellis_tables");
       SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = gr.nc;
       for (int ci = 0; ci < gr.nc; ci++) masks.m[ci] = (1u << gr.c[ci].dc_tbl) | (1u << (4 + gr.c[ci].ac_tbl));
@@ -667,7 +679,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
                        A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, A.d_total_bits.as<unsigned long long>(),
                        (size_t)e->bitbuf_words_per_image * 32, status, n, s);
     tm.mark("encode");
-    CU(cudaMemsetAsync(A.d_bitbuf.p, 0, (size_t)e->bitbuf_words_per_image * 4 * n, s));
+    launch_zero_stream(A.d_bitbuf.as<uint32_t>(), e->bitbuf_words_per_image, A.d_total_bits.as<unsigned long long>(), n, s);
     if (sd.ri) CU(cudaMemsetAsync(A.d_mark.p, 0, mark_words * 4 * n, s));
     launch_encode(g, sd, nz_rec, sym, dcq, rl, tabs, tstride, pl.progressive, A.d_blk_bits.as<uint32_t>(), A.d_tile_bits.as<uint32_t>(), A.d_tile_base.as<unsigned long long>(),
                   A.d_seg_corr.as<uint32_t>(), pl.max_scan_blocks, aux, run_e, pm,
@@ -1124,7 +1136,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
     if ((rc = e->h_tabs.reserve((pl.optimize ? (size_t)n_images * nscans : 1) * HIST_SLOTS * sizeof(HostHuff)))) return rc;
   }
   Timer tm{e};
-  const int nstreams = (nchunks > 1 && e->n_streams > 1) ? 2 : 1;
+  const int nstreams = std::max(1, std::min(std::min(e->n_streams, MAX_ARENAS), nchunks));
   e->sc[0] = e->stream;
   // one incompressible batch does not enlarge the buffers for good: after two batches without growth whose largest
   // image would have fitted the initial size eight times over, fall back to it (batches that keep needing the room,
@@ -1140,7 +1152,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
     if ((rc = prepare_batch(e, n_images, C, !on_device, src_bytes, nstreams))) return rc;
     CU(cudaMemsetAsync(e->d_status.p, 0, (size_t)n_images * 4, e->stream));
     CU(cudaMemsetAsync(e->d_out_pos.p, 0, (size_t)n_images * (nscans + 1) * 8, e->stream));
-    if (nstreams > 1) { CU(cudaEventRecord(e->ev_fork, e->stream)); CU(cudaStreamWaitEvent(e->sc[1], e->ev_fork, 0)); }
+    if (nstreams > 1) { CU(cudaEventRecord(e->ev_fork, e->stream)); for (int i = 1; i < nstreams; i++) CU(cudaStreamWaitEvent(e->sc[i], e->ev_fork, 0)); }
     // stage every chunk's pixels up front on the copy stream; chunk k's kernels wait only for chunk k
     const uint8_t *src_base = static_cast<const uint8_t *>(pixels);
     const uint8_t *plane_base[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1193,7 +1205,7 @@ static int encode_common(b200jpeg_encoder *e, const b200jpeg_params *p, const vo
     }
     if (rc == B200JPEG_OK && !device_only && have_prev) rc = finish_chunk(e, prev, nchunks - 1);
     // the second stream joins the caller-visible one
-    if (nstreams > 1) { cudaEventRecord(e->ev_join, e->sc[1]); cudaStreamWaitEvent(e->stream, e->ev_join, 0); }
+    for (int i = 1; i < nstreams; i++) { cudaEventRecord(e->ev_join, e->sc[i]); cudaStreamWaitEvent(e->stream, e->ev_join, 0); }   // (a wait takes the record in front of it)
     if (rc < 0) { cudaStreamSynchronize(e->stream); cudaStreamSynchronize(e->s_in); cudaStreamSynchronize(e->s_out); return rc; }
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaStreamSynchronize(e->s_in));
@@ -1243,7 +1255,7 @@ int b200jpeg_encoder_create(b200jpeg_encoder **enc, int device)
   cudaError_t e2 = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking);
   if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&o->s_in, cudaStreamNonBlocking);
   if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&o->s_out, cudaStreamNonBlocking);
-  if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&o->sc[1], cudaStreamNonBlocking);
+  for (int i = 1; i < MAX_ARENAS; i++) if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&o->sc[i], cudaStreamNonBlocking);
   if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming);
   if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming);
   o->sc[0] = o->stream;
@@ -1254,7 +1266,7 @@ int b200jpeg_encoder_create(b200jpeg_encoder **enc, int device)
   const char *ch = getenv("B200JPEG_CHUNK_IMAGES");
   if (ch) o->chunk_images_override = atoi(ch);
   const char *ns = getenv("B200JPEG_STREAMS");
-  if (ns) o->n_streams = atoi(ns) > 1 ? 2 : 1;
+  if (ns) o->n_streams = std::max(1, std::min(atoi(ns), MAX_ARENAS));
   *enc = o;
   return B200JPEG_OK;
 }
@@ -1266,10 +1278,10 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
   cudaStreamSynchronize(e->stream);
   if (e->s_in) cudaStreamSynchronize(e->s_in);
   if (e->s_out) cudaStreamSynchronize(e->s_out);
-  if (e->sc[1]) cudaStreamSynchronize(e->sc[1]);
+  for (int i = 1; i < MAX_ARENAS; i++) if (e->sc[i]) cudaStreamSynchronize(e->sc[i]);
   DevBuf *db[] = {&e->d_src, &e->d_tabs_scan, &e->d_tabs_fixed, &e->d_status, &e->d_out_pos, &e->d_scan_size, &e->d_out, &e->d_qt, &e->d_tc, &e->d_best_al_all, &e->d_qimg_all};
   for (DevBuf *b : db) b->release();
-  e->ar[0].release(); e->ar[1].release();
+  for (int i = 0; i < MAX_ARENAS; i++) e->ar[i].release();
   PinBuf *pb[] = {&e->h_qt, &e->h_tc, &e->h_fixed, &e->h_status, &e->h_out_pos, &e->h_scan_size, &e->h_tabs, &e->h_stage, &e->h_best_al, &e->h_qinit, &e->h_qimg};
   for (PinBuf *b : pb) b->release();
   for (PinBuf &b : e->file_arenas) b.release();
@@ -1279,7 +1291,7 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
   if (e->own_stream) cudaStreamDestroy(e->stream);
   if (e->s_in) cudaStreamDestroy(e->s_in);
   if (e->s_out) cudaStreamDestroy(e->s_out);
-  if (e->sc[1]) cudaStreamDestroy(e->sc[1]);
+  for (int i = 1; i < MAX_ARENAS; i++) if (e->sc[i]) cudaStreamDestroy(e->sc[i]);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   delete e;
@@ -1287,7 +1299,7 @@ void b200jpeg_encoder_destroy(b200jpeg_encoder *e)
 
 int b200jpeg_encoder_set_streams(b200jpeg_encoder *e, int n_streams)
 {
-  if (!e || n_streams < 1 || n_streams > 2) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
+  if (!e || n_streams < 1 || n_streams > MAX_ARENAS) { set_error("bad argument"); return B200JPEG_ERR_PARAM; }
   e->n_streams = n_streams;
   return B200JPEG_OK;
 }

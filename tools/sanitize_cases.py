@@ -18,7 +18,8 @@ cases = [["-baseline", "-quality", "75", "-sample", "2x2"],          # forward (
          ["-baseline", "-quality", "75", "-smooth", "20"],           # smoothing pre-pass
          ["-baseline", "-quality", "75", "-sample", "3x2"],          # generic forward kernel
          ["-dct", "float", "-baseline", "-quality", "75"], ["-dct", "fast", "-baseline", "-quality", "75"],
-         ["-revert"], ["-baseline", "-grayscale", "-quality", "75"]]
+         ["-revert"], ["-baseline", "-grayscale", "-quality", "75"],
+         ["-scans", os.path.join(ROOT, "tests", "golden", "scans_b.txt"), "-quality", "80"]]   # two sequential scans: per-scan statistics from the symbol records
 n = 0
 for sw in cases:
     p = mj.params_from_switches(sw, w, h)
