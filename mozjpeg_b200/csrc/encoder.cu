@@ -479,11 +479,6 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
 
   const bool symrec = use_symrec(pl, p);
   const bool symstats = symrec && pl.optimize && nscans == 1;
-  // with symbol records nothing behind the trellis-phase statistics reads the plain-quantized planes: where the forward
-  // kernel can take those statistics itself (forward_takes_stats), it does, and does not write the planes
-  // (B200JPEG_FWD_STATS=0 keeps the separate pass; the debug tap and coefficient input need the planes)
-  static const bool fstats_off = !(getenv("B200JPEG_FWD_STATS") && getenv("B200JPEG_FWD_STATS")[0] == '1');     // measured slower: off unless asked for
-  const bool fstats = symrec && !fstats_off && !e->keep_plain && g.raw_in != 2 && forward_takes_stats(g, p->dct_method);
   // ---- pass 0 data path: colour/downsample/FDCT/quantize (compress_first_pass) ----
   RecLayout rl; memset(&rl, 0, sizeof rl);
   for (int ci = 0; ci < g.nc; ci++) { rl.comp_off[ci] = rl.per_image; rl.per_image += (long long)g.c[ci].wib * g.c[ci].hib; }
@@ -507,9 +502,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     gf.raw_in = 1;
     tm.mark("forward");
   }
-  if (fstats) CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes * g.nc, s));       // the forward kernel adds the trellis-phase AC counts
-  const FwdStats fs = {fstats ? A.d_hist.as<uint32_t>() : nullptr, fstats ? A.d_dcq.as<int16_t>() : nullptr, status, fstats ? 0 : 1};
-  launch_forward(gf, src_dev, e->d_qt.as<QuantTables>(), qfast, p->dct_method, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, e->keep_plain ? 1 : 0, fs, n, s);
+  launch_forward(gf, src_dev, e->d_qt.as<QuantTables>(), qfast, p->dct_method, pl.dering, pl.trellis ? A.d_rec.as<DcRec>() : nullptr, rl, e->keep_plain ? 1 : 0, n, s);
   }
   tm.mark("dummy");
   launch_dummy(g, n, s);
@@ -535,8 +528,7 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     SymOut so; so.sym = symrec ? A.d_sym.as<uint8_t>() : nullptr; so.dcq = symrec ? A.d_dcq.as<int16_t>() : nullptr;
     so.hist = symstats ? A.d_hist.as<uint32_t>() : nullptr;
     so.keep_coef = e->keep_plain ? 1 : 0;                       // B200JPEG_KEEP_PLAIN=1: the debug taps read the final planes
-    so.dcq_ac = (p->trellis_quant_dc || fstats) ? 0 : 1;
-    so.dc_dense = fstats ? 1 : 0;
+    so.dcq_ac = p->trellis_quant_dc ? 0 : 1;
     uint16_t *qimg = qopt ? A.d_qimg.as<uint16_t>() : nullptr;
     if (qopt) {
       // every image starts from the batch's tables (natural order, like JQUANT_TBL.quantval)
@@ -546,11 +538,8 @@ static int run_pipeline(b200jpeg_encoder *e, const ChunkIO &io, Timer &tm)
     auto round = [&](const Geom &gr, const RecLayout &rlr, int bSs, int bSe) -> int {
     if (!pl.progressive) {
       tm.mark("trellis_stats");
-      if (fstats) launch_gather_comp_dc(gr, pl.rs, A.d_dcq.as<int16_t>(), rlr, A.d_hist.as<uint32_t>(), status, n, s);     // the AC counts are there already
-      else {
       CU(cudaMemsetAsync(A.d_hist.p, 0, hist_bytes * gr.nc, s));
       launch_gather_comp(gr, pl.rs, A.d_hist.as<uint32_t>(), status, n, s);
-      }
       tm.mark("trellis_tables");
       SlotMasks masks; memset(&masks, 0, sizeof masks); masks.period = gr.nc;
       for (int ci = 0; ci < gr.nc; ci++) masks.m[ci] = (1u << gr.c[ci].dc_tbl) | (1u << (4 + gr.c[ci].ac_tbl));

@@ -490,7 +490,7 @@ template <int HMAX, int VMAX, int NC, bool QFAST, int PREC, int DCTM>
 __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, const uint8_t *__restrict__ src,
                                                       const QuantTables *__restrict__ qt, int dering,
                                                       DcRec *__restrict__ rec, RecLayout rl, int write_raw,
-                                                      const __grid_constant__ CUtensorMap tmap, const int use_tma, const FwdStats fs)
+                                                      const __grid_constant__ CUtensorMap tmap, const int use_tma)
 {
   constexpr int TW = 128, TR = 8 * VMAX;
   constexpr int YBW = TW / 8, YB = YBW * VMAX;           // luma blocks in the tile
@@ -510,13 +510,6 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
   __shared__ uint2 sQC[NC][64];                           // quantizer constants per component, natural order
   __shared__ uint2 sMask[NB];                             // per block: zigzag positions of its non-zero AC values
   __shared__ int sQL[NC];
-  // fs.hist: the trellis-phase AC statistics (htest_one_block over the plain-quantized blocks, jchuff.c:836-878) are taken
-  // here, from the staged blocks, instead of by a pass of its own over the coefficient planes
-  // (the CTA's counters: 16 bits each, two to a word -- a tile holds at most 48 blocks -- in the luma sample plane, which
-  // is dead once the row pass has read it: the kernel's shared memory stays at 8 CTAs per SM)
-  constexpr bool STATS = PREC == 8 && DCTM == 0;
-  unsigned *sHist = reinterpret_cast<unsigned *>(sY);
-  static_assert(NC * 128 * 4 <= TR * YP * 2, "the packed histograms fit the luma plane");
 
   const int tid = threadIdx.x;
   const int tx = blockIdx.x, ty = blockIdx.y, img = blockIdx.z;
@@ -755,7 +748,6 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
   }
   __syncthreads();
 
-  if (STATS && fs.hist) for (int i = tid; i < NC * 128; i += 128) sHist[i] = 0;      // (read again behind the barrier that ends phase D)
   // ---- D: column pass + quantize; lane j owns column jc; zigzag placement in the staging buffer.
   //      The four blocks a warp works on own their columns in rotated order (jc), so that their simultaneous 2-byte
   //      stores into the dense 128-byte staging blocks fall into different banks (they were 4-way conflicts).
@@ -913,43 +905,6 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
       DcRec rr; rr.lambda_dc = norm; rr.raw_dc = (int16_t)raw_dc; rr.nz = (uint8_t)(__popc(mk.x) + __popc(mk.y)); rr.pad = 0;
       rr.nzmask = ((unsigned long long)mk.y << 32) | mk.x;
       rec[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * c.wib + col] = rr;
-      if (fs.dcq) fs.dcq[(size_t)img * rl.per_image + rl.comp_off[ci] + (size_t)row * c.wib + col] = sQ[b * 64];      // plain-quantized DC
-    }
-    // ---- D3: AC symbols of the plain-quantized blocks into the CTA's histograms: work item = (block, 16 zigzag
-    //      positions); the threads D2 keeps busy come last.  A symbol's run is the distance to the next lower set bit
-    //      of the block's non-zero mask (integer DCT: the mask is exactly the staged values' non-zero pattern).
-    if (STATS && fs.hist) {
-      int bad = 0;
-      for (int it = 127 - tid; it < NB * 4; it += 128) {
-        const int b = it >> 2, seg = it & 3;
-        int ci, row, col;
-        if (b < YB) { ci = 0; int byl = b / YBW; row = ty * VMAX + byl; col = tx * YBW + (b - byl * YBW); }
-        else { int cb = b - YB; int which = cb / CBW; ci = 1 + which; row = ty; col = tx * CBW + (cb - which * CBW); }
-        const CompGeom &c = g.c[ci];
-        if (row >= c.hib || col >= c.wib) continue;
-        const uint2 mk = sMask[b];
-        const unsigned long long mask = ((unsigned long long)mk.y << 32) | mk.x;
-        unsigned sm = (unsigned)(mask >> (16 * seg)) & 0xFFFFu;
-        unsigned *h = sHist + (NC == 1 ? 0 : ci) * 128;
-        auto count = [&](int sym, unsigned by) { atomicAdd(&h[sym >> 1], by << (16 * (sym & 1))); };
-        while (sm) {
-          const int pos = 16 * seg + __ffs((int)sm) - 1;
-          sm &= sm - 1;
-          const int nb = nbits_of(abs((int)sQ[b * 64 + pos]));
-          const unsigned long long below = mask & ((1ull << pos) - 1ull);
-          const int run = pos - (below ? 63 - __clzll((long long)below) : 0) - 1;
-          if (nb > g.max_coef_bits) bad = 1;                      // JERR_BAD_DCT_COEF (jchuff.c:865)
-          count(((run & 15) << 4) | nb, 1u);
-          if (run >> 4) count(0xF0, (unsigned)(run >> 4));
-        }
-        if (seg == 3 && (mask >> 63) == 0) count(0, 1u);            // the block does not end on position 63: EOB
-      }
-      if (bad) atomicOr(&fs.status[img], 2u);
-      __syncthreads();
-      for (int i = tid; i < NC * 256; i += 128) {
-        const unsigned v = (sHist[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-        if (v) { const int ci = i >> 8; atomicAdd(&fs.hist[((size_t)img * g.nc + ci) * HIST_SLOTS * HIST_BINS + (4 + g.c[ci].ac_tbl) * HIST_BINS + (i & 255)], v); }
-      }
     }
   }
 
@@ -968,9 +923,8 @@ __global__ void __launch_bounds__(128, FWD_MIN_CTAS) k_forward_tile(Geom g, cons
       if (cnt > 0) {
         const size_t blk = ((size_t)img * c.hpad + row) * c.wpad + col0;
         const unsigned bytes = (unsigned)cnt * 128u;
-        if (fs.write_coef)                                       // (not when the statistics above were its only reader)
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                       :: "l"(c.coef + blk * 64), "r"((unsigned)__cvta_generic_to_shared(sQ + b0 * 64)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(c.coef + blk * 64), "r"((unsigned)__cvta_generic_to_shared(sQ + b0 * 64)), "r"(bytes) : "memory");
         if (write_raw)                                           // only the trellis (and the debug tap) read the raw DCT
           asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                        :: "l"(c.raw + blk * 64), "r"((unsigned)__cvta_generic_to_shared(sR + b0 * 64)), "r"(bytes) : "memory");
@@ -1012,16 +966,16 @@ static int make_pixel_tensor_map(const Geom &g, const uint8_t *src, int n, int i
 }
 
 template <bool QFAST, int PREC, int DCTM>
-static void launch_forward_tile(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s, bool gray, int write_raw, const FwdStats &fs)
+static void launch_forward_tile(const Geom &g, const uint8_t *src, const QuantTables *qt, int dering, DcRec *rec, const RecLayout &rl, int n, cudaStream_t s, bool gray, int write_raw)
 {
   dim3 grid((g.W + 127) / 128, g.mcu_rows, n);
   CUtensorMap tm;
   const int use_tma = PREC == 8 ? make_pixel_tensor_map(g, src, n, gray ? 1 : 3, 8 * (gray ? 1 : g.vmax), &tm) : (memset(&tm, 0, sizeof tm), 0);
-  if (gray) k_forward_tile<1, 1, 1, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma, fs);
-  else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma, fs);
-  else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma, fs);
-  else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma, fs);
-  else k_forward_tile<2, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma, fs);
+  if (gray) k_forward_tile<1, 1, 1, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma);
+  else if (g.hmax == 1 && g.vmax == 1) k_forward_tile<1, 1, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma);
+  else if (g.hmax == 2 && g.vmax == 1) k_forward_tile<2, 1, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma);
+  else if (g.hmax == 1 && g.vmax == 2) k_forward_tile<1, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma);
+  else k_forward_tile<2, 2, 3, QFAST, PREC, DCTM><<<grid, 128, 0, s>>>(g, src, qt, dering, rec, rl, write_raw, tm, use_tma);
 }
 // =====================================================================
 // Input smoothing (cinfo->smoothing_factor, cjpeg -smooth N).  The smoothing downsamplers (jcsample.c:298-455) read a
@@ -1087,34 +1041,23 @@ void launch_prep_planes(const Geom &g, const uint8_t *src, int smoothing_factor,
   LAUNCHED();
 }
 
-// the tiled kernel serves: full-size first component, (for colour) two 1x1-sampled chroma components
-static bool tile_layout(const Geom &g, bool &gray)
-{
-  gray = g.nc == 1 && (g.raw_in || g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
-  const bool ycc = g.nc == 3 && (g.raw_in || (g.cs_mode == 0 && (g.in_comps == 3 || g.in_comps == 4))) && g.c[0].h == g.hmax && g.c[0].v == g.vmax &&
-                   g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
-  static const bool force_generic = getenv("B200JPEG_GENERIC_FORWARD") != nullptr;   // A/B switch for debugging
-  return !force_generic && ((gray && g.hmax == 1 && g.vmax == 1) || ycc);
-}
-bool forward_takes_stats(const Geom &g, int dct_method)
-{
-  bool gray;
-  return tile_layout(g, gray) && g.max_coef_bits == 10 && dct_method == 0;
-}
-void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dct_method, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, const FwdStats &fs, int n, cudaStream_t s)
+void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dct_method, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, int n, cudaStream_t s)
 {
   const int write_raw = rec != nullptr || keep_raw;
-  const FwdStats fs0 = {nullptr, nullptr, nullptr, 1};           // the instantiations that take no statistics
-  bool gray;
+  // fast path: full-size first component, (for colour) two 1x1-sampled chroma components
+  bool gray = g.nc == 1 && (g.raw_in || g.cs_mode == 1 || (g.cs_mode == 2 && g.in_comps == 1));
+  bool ycc = g.nc == 3 && (g.raw_in || (g.cs_mode == 0 && (g.in_comps == 3 || g.in_comps == 4))) && g.c[0].h == g.hmax && g.c[0].v == g.vmax &&
+             g.c[1].h == 1 && g.c[1].v == 1 && g.c[2].h == 1 && g.c[2].v == 1 && g.hmax <= 2 && g.vmax <= 2;
+  static const bool force_generic = getenv("B200JPEG_GENERIC_FORWARD") != nullptr;   // A/B switch for debugging
   // (12-bit samples with the fast / float DCT: the one-thread-per-block kernel only)
-  if (tile_layout(g, gray) && !(g.max_coef_bits == 14 && dct_method != 0)) {
+  if (!force_generic && ((gray && g.hmax == 1 && g.vmax == 1) || ycc) && !(g.max_coef_bits == 14 && dct_method != 0)) {
     if (g.max_coef_bits == 14) {                       // 12-bit samples (uint16)
-      if (qfast) launch_forward_tile<true, 12, 0>(g, src, qt, 0, nullptr, rl, n, s, gray, 0, fs0);
-      else launch_forward_tile<false, 12, 0>(g, src, qt, 0, nullptr, rl, n, s, gray, 0, fs0);
-    } else if (dct_method == 2) launch_forward_tile<true, 8, 2>(g, src, qt, dering, rec, rl, n, s, gray, write_raw, fs0);
-    else if (dct_method == 1) launch_forward_tile<true, 8, 1>(g, src, qt, dering, rec, rl, n, s, gray, write_raw, fs0);
-    else if (qfast) launch_forward_tile<true, 8, 0>(g, src, qt, dering, rec, rl, n, s, gray, write_raw, fs);
-    else launch_forward_tile<false, 8, 0>(g, src, qt, dering, rec, rl, n, s, gray, write_raw, fs);
+      if (qfast) launch_forward_tile<true, 12, 0>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
+      else launch_forward_tile<false, 12, 0>(g, src, qt, 0, nullptr, rl, n, s, gray, 0);
+    } else if (dct_method == 2) launch_forward_tile<true, 8, 2>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
+    else if (dct_method == 1) launch_forward_tile<true, 8, 1>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
+    else if (qfast) launch_forward_tile<true, 8, 0>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
+    else launch_forward_tile<false, 8, 0>(g, src, qt, dering, rec, rl, n, s, gray, write_raw);
     LAUNCHED();
     return;
   }
@@ -1537,43 +1480,6 @@ __global__ void __launch_bounds__(256) k_gather_comp(Geom g, RestartSpec rs, uin
     if (d) atomicAdd(&gh[c.dc_tbl * HIST_BINS + i], d);
     if (a) atomicAdd(&gh[(4 + c.ac_tbl) * HIST_BINS + i], a);
   }
-}
-// The DC half of the trellis-phase statistics when the forward kernel took the AC half: every component as its own
-// non-interleaved scan in raster order, plain-quantized DC values from the dense array the forward kernel filled.
-__global__ void __launch_bounds__(256) k_gather_comp_dc(Geom g, RestartSpec rs, const int16_t *__restrict__ dcq, RecLayout rl, uint32_t *__restrict__ hist, uint32_t *__restrict__ status)
-{
-  __shared__ unsigned sdc[4][20];
-  const int ci = blockIdx.y % g.nc, img = blockIdx.y / g.nc;
-  const CompGeom &c = g.c[ci];
-  const long long nblk = (long long)c.wib * c.hib;
-  if ((long long)blockIdx.x * GATHER_TILES * blockDim.x >= nblk) return;
-  if (threadIdx.x < 80) (&sdc[0][0])[threadIdx.x] = 0;
-  __syncthreads();
-  const int16_t *d = dcq + (size_t)img * rl.per_image + rl.comp_off[ci];
-  const long long ri = rs.in_rows > 0 ? min((long long)rs.in_rows * c.wib, 65535LL) : rs.interval;      // per_scan_setup, jcmaster.c:594-599
-#pragma unroll 1
-  for (int tile = 0; tile < GATHER_TILES; tile++) {
-    const long long t = ((long long)blockIdx.x * GATHER_TILES + tile) * blockDim.x + threadIdx.x;
-    if (t >= nblk) break;
-    const int last = (t > 0 && !(ri && t % ri == 0)) ? d[t - 1] : 0;
-    int temp = d[t] - last;
-    if (temp < 0) temp = -temp;
-    const int nb = nbits_of(temp);
-    if (nb > g.max_coef_bits + 1) atomicOr(&status[img], 2u);          // JERR_BAD_DCT_COEF (jchuff.c:836)
-    atomicAdd(&sdc[threadIdx.x & 3][min(nb, 19)], 1u);
-  }
-  __syncthreads();
-  if (threadIdx.x < 20) {
-    const unsigned v = sdc[0][threadIdx.x] + sdc[1][threadIdx.x] + sdc[2][threadIdx.x] + sdc[3][threadIdx.x];
-    if (v) atomicAdd(&hist[((size_t)img * g.nc + ci) * HIST_SLOTS * HIST_BINS + c.dc_tbl * HIST_BINS + threadIdx.x], v);
-  }
-}
-void launch_gather_comp_dc(const Geom &g, const RestartSpec &rs, const int16_t *dcq, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
-{
-  long long mb = 0;
-  for (int ci = 0; ci < g.nc; ci++) mb = max(mb, (long long)g.c[ci].wib * g.c[ci].hib);
-  dim3 grid((unsigned)((mb + 256 * GATHER_TILES - 1) / (256 * GATHER_TILES)), n * g.nc);
-  k_gather_comp_dc<<<grid, 256, 0, s>>>(g, rs, dcq, rl, hist, status); LAUNCHED();
 }
 void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, uint32_t *status, int n, cudaStream_t s)
 {
@@ -2349,8 +2255,7 @@ k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__res
       // output: zeros except the back-tracked chain (:1211-1222)
       uint4 *q4 = reinterpret_cast<uint4 *>(o16);
       auto write_block = [&](int lst) {
-        // the DC value survives the rewrite (it sits in the dense array when the forward kernel wrote no coefficient planes)
-        q4[0] = make_uint4((unsigned)(unsigned short)(so.dc_dense ? so.dcq[rbase + lin] : o16[0]), 0, 0, 0);
+        q4[0] = make_uint4((unsigned)(unsigned short)o16[0], 0, 0, 0);        // the DC value survives the rewrite
 #pragma unroll
         for (int v = 1; v < 8; v++) q4[v] = make_uint4(0, 0, 0, 0);
         unsigned long long fm = 0;

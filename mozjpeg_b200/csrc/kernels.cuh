@@ -115,14 +115,7 @@ struct SlotMasks { uint32_t m[4]; int period; };
 // keep_coef: also rewrite the coefficient planes (the debug tap reads them); otherwise only blocks whose record overflowed
 // get their coefficients written back, and the planes keep the plain-quantized values elsewhere.
 // dcq_ac: the AC trellis fills dcq with the plain-quantized DC values (no DC trellis will follow and write the final ones).
-// dc_dense: dcq already holds the plain-quantized DC values (the forward kernel wrote them, and no coefficient planes).
-struct SymOut { uint8_t *sym; int16_t *dcq; uint32_t *hist; int keep_coef; int dcq_ac; int dc_dense; };
-// Trellis-phase statistics taken by the forward kernel itself (integer DCT, 8-bit samples, tiled layouts:
-// forward_takes_stats()): hist = the [img * nc + ci][HIST_SLOTS][HIST_BINS] sets receiving every component's AC symbol
-// counts, dcq = dense plain-quantized DC values (for the DC half, launch_gather_comp_dc), write_coef = 0: the
-// plain-quantized coefficient planes are not written at all.  {nullptr, nullptr, nullptr, 1} = none of this.
-struct FwdStats { uint32_t *hist; int16_t *dcq; uint32_t *status; int write_coef; };
-bool forward_takes_stats(const Geom &g, int dct_method);
+struct SymOut { uint8_t *sym; int16_t *dcq; uint32_t *hist; int keep_coef; int dcq_ac; };
 
 #define HIST_BINS 257
 #define HIST_SLOTS 8          // [is_ac*4 + tbl_no]
@@ -132,8 +125,7 @@ bool forward_takes_stats(const Geom &g, int dct_method);
 // the raw DCT plane is written only when the trellis (rec != nullptr) or the debug tap (keep_raw) will read it
 void launch_prep_planes(const Geom &g, const uint8_t *src, int smoothing_factor, const PlanesOut &out, int n, cudaStream_t s);
 void launch_import_coefs(const Geom &g, int n, cudaStream_t s);     // raw_in == 2: planes hold JBLOCK rows
-void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dct_method /* J_DCT_METHOD */, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, const FwdStats &fs, int n, cudaStream_t s);
-void launch_gather_comp_dc(const Geom &g, const RestartSpec &rs, const int16_t *dcq, const RecLayout &rl, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
+void launch_forward(const Geom &g, const uint8_t *src, const QuantTables *qt, int qfast, int dct_method /* J_DCT_METHOD */, int dering, DcRec *rec, const RecLayout &rl, int keep_raw, int n, cudaStream_t s);
 void launch_dummy(const Geom &g, int n, cudaStream_t s);
 void launch_gather_comp(const Geom &g, const RestartSpec &rs, uint32_t *hist, uint32_t *status, int n, cudaStream_t s);
 // nz_rec (here and in launch_block_bits / launch_encode): the side records holding every block's final non-zero positions
