@@ -1052,8 +1052,11 @@ static int choose_chunk(const b200jpeg_encoder *e, const Plan &pl, int n_images,
   const int grid_cap = 65535 / std::max(1, pl.g.nc);
   if (e->chunk_images_override > 0) return std::min(std::min(n_images, e->chunk_images_override), grid_cap);
   long long per = 0; for (int ci = 0; ci < pl.g.nc; ci++) per += pl.g.c[ci].blocks_per_image;
-  // pixels already in HBM: nothing to overlap, so chunks only bound the arenas (64 images of 4K 4:2:0)
-  if (!host_pixels) return (int)std::min<long long>(std::min(n_images, grid_cap), std::max(1LL, 12800000LL / std::max(1LL, per)));
+  // pixels already in HBM: no staging to overlap, so chunks only bound the arenas and give the two compute streams one
+  // large chunk each to run against each other (131 images of 4K 4:2:0: 256 images in chunks of 128 take 26.9 ms on B200,
+  // in chunks of 65 28.1, of 32 29.0; three streams x 86 images 27.5)
+  static const long long resident_target = getenv("B200JPEG_RESIDENT_CHUNK_BLOCKS") ? atoll(getenv("B200JPEG_RESIDENT_CHUNK_BLOCKS")) : 25600000LL;
+  if (!host_pixels) return (int)std::min<long long>(std::min(n_images, grid_cap), std::max(1LL, resident_target / std::max(1LL, per)));
   // about 1.6 M blocks (8 images of 3840x2160 4:2:0) per chunk: large enough to fill
   // the 148 SMs several waves deep, small enough that staging the next chunk's
   // pixels overlaps this chunk's kernels.

@@ -10,6 +10,8 @@
 //   raw[c]  : int16 [n][hpad_c][wpad_c][64]   FDCT output (x8 scale),  ZIGZAG order
 // (one 128-byte line per 8x8 block; wpad/hpad include the dummy blocks that
 // pad each component to whole interleaved MCUs, jccoefct.c:312-345).
+// Sequential scans behind the default trellis additionally keep, per real block, a 128-byte symbol record and a dense
+// int16 DC value (SymOut below): the entropy stages then read those, and coef[] keeps the plain-quantized values.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
