@@ -89,46 +89,94 @@ def metric_name(a):
 # clocks: sample nvidia-smi during the timed region
 # ---------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons of one GPU while it is under load.  NVML in-process every few ms (nvidia_ml_py), the
+    `nvidia-smi -lms` loop of the profiling recipe as the fallback; the device is addressed by UUID, so a
+    CUDA_VISIBLE_DEVICES remapping cannot point the sampler at another GPU.  It runs from before the warm-up; mark()
+    brackets the timed region and stop() reports the samples inside it (if the region was too short to catch one --
+    a few tens of ms -- the samples of warm-up + timed region, said so in "window")."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.index = index; self.proc = None; self.lines = []
-
-    def start(self):
+        self.index = index; self.proc = None; self.samples = []; self.source = None; self._stop = threading.Event(); self.th = None
+        self.sel = str(index)
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+            import torch
+            u = str(torch.cuda.get_device_properties(index).uuid)
+            self.sel = u if u.startswith("GPU-") else "GPU-" + u
         except Exception:
-            self.proc = None
+            pass
 
-    def _read(self):
+    def _nvml_loop(self, nv, h, mx):
+        bits = [(getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"), (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"), (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)); r = int(get_reasons(h))
+                self.samples.append((sm, mx, tuple(nm for b, nm in bits if r & b)))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def _smi_loop(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                self.samples.append((float(f[0]), float(f[1]), tuple(nm for nm, v in zip(self.NAMES, f[2:6]) if v.lower().startswith("active"))))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+
+    def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByUUID(self.sel) if self.sel.startswith("GPU-") else nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.th = threading.Thread(target=self._nvml_loop, args=(nv, h, mx), daemon=True); self.th.start()
+            return
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
+            self.th = threading.Thread(target=self._smi_loop, daemon=True); self.th.start()
+        except Exception:
+            self.proc = None
+
+    def mark(self) -> int:
+        return len(self.samples)
+
+    def stop(self, lo: int = 0, hi: int | None = None):
+        try:
+            return self._stop_impl(lo, hi)
+        except Exception as ex:                       # the sampler must never take the bench line down
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"clock sampler failed: {ex!r}"], "samples": 0}
+
+    def _stop_impl(self, lo: int = 0, hi: int | None = None):
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.th:
+            self.th.join(timeout=2)
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        hi = len(self.samples) if hi is None else hi
+        win, window = self.samples[lo:hi], "timed region"
+        if not win:
+            win, window = self.samples[:max(hi, lo + 1)] or self.samples, "warm-up + timed region (the timed region was shorter than one sampling period)"
+        sm = [x[0] for x in win]; mx = [x[1] for x in win]; reasons = set(r for x in win for r in x[2])
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source, "window": window}
 
 
 # ---------------------------------------------------------------------------
@@ -341,10 +389,11 @@ def measure(a, sw, enc, host, devbuf, base, rank, world, local, dev, stream, dis
         torch.cuda.synchronize()
 
     # ---- resident (kernel pipeline only) ----
+    clocks = ClockSampler(local); clocks.start()
     for _ in range(a.warmup):
         step_resident()
     barrier()
-    clocks = ClockSampler(local); clocks.start()
+    clk_lo = clocks.mark()
     l0 = enc.kernel_launches()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -352,6 +401,7 @@ def measure(a, sw, enc, host, devbuf, base, rank, world, local, dev, stream, dis
         step_resident()
     ev1.record(stream)
     barrier()
+    clk_hi = clocks.mark()
     ms_total = ev0.elapsed_time(ev1)
     launches = enc.kernel_launches() - l0
     # per-kernel times for the roofline: one extra, untimed pass with a single compute stream
@@ -361,8 +411,8 @@ def measure(a, sw, enc, host, devbuf, base, rank, world, local, dev, stream, dis
     torch.cuda.synchronize()
     stages = {k: v for k, v in enc.stage_times().items() if k not in ("h2d", "h2d_wait")}
     chunk = enc.chunk_images()
-    enc.set_streams(2)
-    clk = clocks.stop()
+    enc.set_streams(max(1, min(4, int(os.environ.get("B200JPEG_STREAMS", "2")))))
+    clk = clocks.stop(clk_lo, clk_hi)
     ms_total = max_over_ranks(ms_total, world, dev)
 
     # ---- end to end through the public API: host pixels in, JPEG files out ----

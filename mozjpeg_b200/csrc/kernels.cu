@@ -2035,6 +2035,11 @@ __device__ __forceinline__ float u2f_exact(unsigned v) { return __uint_as_float(
 #ifndef T3_MINB_15
 #define T3_MINB_15 8           // ... and for the 9..15 entries class
 #endif
+#ifndef T3_PRED_UNROLL
+#define T3_PRED_UNROLL 2       // predecessor loop: iterations in flight (their shared-memory loads are independent)
+#endif
+#define T3_PRAGMA_(x) _Pragma(#x)
+#define T3_PRAGMA_UNROLL(n) T3_PRAGMA_(unroll n)
 template <int MM> struct T3Smem {
   uint2 rec[MM][T3_THREADS];       // before the entry is processed: {A[p-1], p | raw << 16}; after: {-A[p], accumulated cost}
   unsigned ew[MM][T3_THREADS];     // 4*p | chosen predecessor (1-based entry, 0 = block start) << 8 | chosen value << 16
@@ -2045,7 +2050,7 @@ __device__ __forceinline__ void t3_pred_loop(const int t, const uint2 *__restric
                                              const char *__restrict__ rb, const float before, const float d0, const float d1, const float d2,
                                              float &kb0, int &ks0, float &kb1, int &ks1, float &kb2, int &ks2)
 {
-#pragma unroll 2
+T3_PRAGMA_UNROLL(T3_PRED_UNROLL)
   for (int s = 0; s < t; s++) {
     const uint2 r = rec[s * T3_THREADS];
     const int pos4 = (int)(ew[s * T3_THREADS] & 0xFCu);         // (stale words on idle lanes must still give aligned addresses)
