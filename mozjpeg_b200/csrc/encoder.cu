@@ -1056,7 +1056,14 @@ static int choose_chunk(const b200jpeg_encoder *e, const Plan &pl, int n_images,
   // large chunk each to run against each other (131 images of 4K 4:2:0: 256 images in chunks of 128 take 26.9 ms on B200,
   // in chunks of 65 28.1, of 32 29.0; three streams x 86 images 27.5)
   static const long long resident_target = getenv("B200JPEG_RESIDENT_CHUNK_BLOCKS") ? atoll(getenv("B200JPEG_RESIDENT_CHUNK_BLOCKS")) : 25600000LL;
-  if (!host_pixels) return (int)std::min<long long>(std::min(n_images, grid_cap), std::max(1LL, resident_target / std::max(1LL, per)));
+  if (!host_pixels) {
+    long long c = std::min<long long>(std::min(n_images, grid_cap), std::max(1LL, resident_target / std::max(1LL, per)));
+    // a batch that fits one chunk still goes out as two when each half fills the device several waves deep (1.6 M blocks,
+    // 8 images of 4K 4:2:0): the second compute stream then runs against the first, and the latency-bound launches
+    // (table generation, scan layout: a few dozen warps each, 64 times over with the scan search) stop idling the GPU
+    if (c >= n_images && e->n_streams > 1 && (long long)n_images * per >= 2 * 1600000LL) c = (n_images + 1) / 2;
+    return (int)c;
+  }
   // about 1.6 M blocks (8 images of 3840x2160 4:2:0) per chunk: large enough to fill
   // the 148 SMs several waves deep, small enough that staging the next chunk's
   // pixels overlaps this chunk's kernels.
