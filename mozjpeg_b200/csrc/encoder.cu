@@ -1058,10 +1058,11 @@ static int choose_chunk(const b200jpeg_encoder *e, const Plan &pl, int n_images,
   static const long long resident_target = getenv("B200JPEG_RESIDENT_CHUNK_BLOCKS") ? atoll(getenv("B200JPEG_RESIDENT_CHUNK_BLOCKS")) : 25600000LL;
   if (!host_pixels) {
     long long c = std::min<long long>(std::min(n_images, grid_cap), std::max(1LL, resident_target / std::max(1LL, per)));
-    // a batch that fits one chunk still goes out as two when each half fills the device several waves deep (1.6 M blocks,
-    // 8 images of 4K 4:2:0): the second compute stream then runs against the first, and the latency-bound launches
-    // (table generation, scan layout: a few dozen warps each, 64 times over with the scan search) stop idling the GPU
-    if (c >= n_images && e->n_streams > 1 && (long long)n_images * per >= 2 * 1600000LL) c = (n_images + 1) / 2;
+    // a batch that fits one chunk goes out as two, one per compute stream, when the halves stay large (6.4 M blocks, 33
+    // images of 4K 4:2:0): halves of 64 images run 10 % faster than the whole on one stream (both the baseline and the
+    // progressive profile), halves of 16 images slower (library default profile, 32 x 4K: 36.2 vs 33.9 ms -- the 64
+    // candidate scans' kernels lose more by shrinking than the latency-bound table / layout launches gain by overlapping)
+    if (c >= n_images && e->n_streams > 1 && (long long)n_images * per >= 2 * 6400000LL) c = (n_images + 1) / 2;
     return (int)c;
   }
   // about 1.6 M blocks (8 images of 3840x2160 4:2:0) per chunk: large enough to fill
