@@ -1319,7 +1319,14 @@ __device__ __forceinline__ void walk_seq_rec(const Geom &g, const ScanDesc &sd, 
   const CompGeom &c = g.c[ci];
   const int16_t *dimg = dcq + (size_t)img * rl.per_image;
   const bool real = row < c.hib && col < c.wib;
-  const uint4 *r4 = reinterpret_cast<const uint4 *>(sym + ((size_t)img * rl.per_image + rl.comp_off[ci] + (real ? (size_t)row * c.wib + col : (size_t)0)) * SYMREC_BYTES);
+  const size_t ridx = (size_t)img * rl.per_image + rl.comp_off[ci] + (real ? (size_t)row * c.wib + col : (size_t)0);
+#if SYMREC_SPLIT
+  const uint4 *r4 = reinterpret_cast<const uint4 *>(sym + ridx * (SYMREC_BYTES / 2));
+  const uint4 *r4hi = reinterpret_cast<const uint4 *>(sym + (size_t)rl.sym_hi + ridx * (SYMREC_BYTES / 2)) - 4;      // words 16..31 = pieces 4..7
+#else
+  const uint4 *r4 = reinterpret_cast<const uint4 *>(sym + ridx * SYMREC_BYTES);
+  const uint4 *r4hi = r4;
+#endif
   uint4 q0 = make_uint4(1u, 0u, 0u, 0u);                       // a dummy block: one entry, EOB
   if (real) q0 = r4[0];
   emit_dc(dense_dc(c, dimg + rl.comp_off[ci], row, col), prev_dc_dense(g, sd, dimg, rl, sp), sink);
@@ -1343,7 +1350,7 @@ __device__ __forceinline__ void walk_seq_rec(const Geom &g, const ScanDesc &sd, 
   const int n = (int)(q0.x & 0x7Fu);                          // entries at words 1..n, stream order = descending word index
 #pragma unroll 1
   for (int v = n >> 2; v > 0; v--) {
-    const uint4 q = r4[v];
+    const uint4 q = v < 4 ? r4[v] : r4hi[v];
     const unsigned e[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int j = 3; j >= 0; j--) if (4 * v + j <= n) sink.ac((int)(e[j] & 0xFFu), (int)(e[j] & 15u), (int)(e[j] >> 16));
@@ -2029,6 +2036,7 @@ __device__ __forceinline__ float u2f_exact(unsigned v) { return __uint_as_float(
 #ifndef SYMREC_DIRECT
 #define SYMREC_DIRECT 0
 #endif
+static_assert(!(SYMREC_DIRECT && SYMREC_SPLIT), "the direct-store A/B aid writes whole 128-byte slots");
 #ifndef T3_MINB_8
 #define T3_MINB_8 8            // resident CTAs per SM the compiler must allow for the <= 8 entries class (12: measured slower)
 #endif
@@ -2317,10 +2325,16 @@ k_trellis_ac3(Geom g, const TrellisConsts *__restrict__ tc, const DevHuff *__res
         scr[0] = ns > SYMREC_SLOTS ? 0x80u : (unsigned)ns;
         // whole 32-byte sectors leave (the words past the last entry are whatever the list held)
         const int nw = 1 + min(ns, SYMREC_SLOTS);
-        uint4 *dst = reinterpret_cast<uint4 *>(so.sym + (rbase + lin) * SYMREC_BYTES);
+#if SYMREC_SPLIT
+        uint4 *dlo = reinterpret_cast<uint4 *>(so.sym + (rbase + lin) * (SYMREC_BYTES / 2));
+        uint4 *dhi = reinterpret_cast<uint4 *>(so.sym + (size_t)rl.sym_hi + (rbase + lin) * (SYMREC_BYTES / 2)) - 4;
+#else
+        uint4 *dlo = reinterpret_cast<uint4 *>(so.sym + (rbase + lin) * SYMREC_BYTES), *dhi = dlo;
+#endif
         for (int v = 0; 4 * v < nw; v += 2) {
           const uint2 a = myrec[(2 * v) * T3_THREADS], b = myrec[(2 * v + 1) * T3_THREADS];
           const uint2 c2 = myrec[(2 * v + 2) * T3_THREADS], d2 = myrec[(2 * v + 3) * T3_THREADS];
+          uint4 *dst = v < 4 ? dlo : dhi;
           dst[v] = make_uint4(a.x, a.y, b.x, b.y);
           dst[v + 1] = make_uint4(c2.x, c2.y, d2.x, d2.y);
         }

@@ -103,7 +103,8 @@ static_assert(sizeof(DevHuff) == 17 + 256 + 1 + 12 + 2 + 512 + 256, "DevHuff lay
 struct DcRec { float lambda_dc; int16_t raw_dc; uint8_t nz; uint8_t pad; unsigned long long nzmask; };
 static_assert(sizeof(DcRec) == 16, "DcRec layout");
 // where component ci's records start inside an image's record array
-struct RecLayout { long long per_image; long long comp_off[4]; };
+// sym_hi: byte offset of the symbol records' second plane (SYMREC_SPLIT below) = images in the chunk * per_image * 64
+struct RecLayout { long long per_image; long long comp_off[4]; long long sym_hi; };
 // which of the 8 table slots to (re)build for set i: m[i % period]
 struct SlotMasks { uint32_t m[4]; int period; };
 
@@ -114,6 +115,13 @@ struct SlotMasks { uint32_t m[4]; int period; };
 // the final DC values; `hist` (or nullptr) receives the blocks' AC symbol counts, [img][HIST_SLOTS][HIST_BINS].
 #define SYMREC_BYTES 128
 #define SYMREC_SLOTS 31
+// SYMREC_SPLIT: a record lives in two 64-byte halves, words 0..15 in plane 0 and words 16..31 in plane 1 (both indexed like
+// the side records), instead of one 128-byte slot: the readers fetch the header and the first entries of every block, and
+// L2 fills whole 128-byte lines -- with one slot per line the bit-count and packing kernels moved 26 / 28 MB per 4K image
+// for ~8 MB of entries; with two blocks per line the second plane is touched only by blocks of 16 and more symbols.
+#ifndef SYMREC_SPLIT
+#define SYMREC_SPLIT 1
+#endif
 // keep_coef: also rewrite the coefficient planes (the debug tap reads them); otherwise only blocks whose record overflowed
 // get their coefficients written back, and the planes keep the plain-quantized values elsewhere.
 // dcq_ac: the AC trellis fills dcq with the plain-quantized DC values (no DC trellis will follow and write the final ones).
