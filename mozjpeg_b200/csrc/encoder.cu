@@ -1071,6 +1071,11 @@ static int choose_chunk(const b200jpeg_encoder *e, const Plan &pl, int n_images,
   // pixels overlaps this chunk's kernels.
   static const long long target = getenv("B200JPEG_CHUNK_BLOCKS") ? atoll(getenv("B200JPEG_CHUNK_BLOCKS")) : 1600000LL;
   long long c = std::max(1LL, target / std::max(1LL, per));
+  // scan search: the 64 candidate scans make the device the slower side (1 ms per 4K image against 0.45 ms of staging) and
+  // launch ~700 kernels per chunk, so chunks are four times larger, but a batch still goes out in at least two so that the
+  // second half's staging hides behind the first half's kernels (32 x 4K end to end on B200: chunks of 8 / 16 / 32 images
+  // 51.4 / 41.2 / 45.7 ms)
+  if (pl.search) c = std::max(1LL, std::min(4 * c, ((long long)n_images + 1) / 2));
   return (int)std::min<long long>(std::min(n_images, grid_cap), c);
 }
 
