@@ -52,3 +52,32 @@ def test_reference_arm_under_torchrun_prints_once(built):
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "reference"
+
+
+def _bench_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def test_clock_sampler_window_and_fallback():
+    """bench.py's `clocks` entry: the samples between the two marks are the ones reported (median SM clock, union of the
+    throttle reasons), a timed region shorter than one sampling period falls back to warm-up + timed region and says so,
+    and a box without NVML / nvidia-smi yields a null entry instead of an exception."""
+    b = _bench_module()
+    c = b.ClockSampler(0)
+    c.start(); out = c.stop(0, None)                      # no GPU here: neither source comes up
+    assert out["samples"] == 0 and out["sm_mhz"] is None
+    c = b.ClockSampler(0); c.source = "nvml"
+    c.samples = [(1500.0, 1965.0, ()), (1600.0, 1965.0, ())]                       # warm-up
+    lo = c.mark()
+    c.samples += [(1965.0, 1965.0, ()), (1950.0, 1965.0, ("sw_power_cap",)), (1965.0, 1965.0, ())]
+    hi = c.mark()
+    c.samples += [(900.0, 1965.0, ("hw_slowdown",))]                               # after the timed region: not reported
+    out = c.stop(lo, hi)
+    assert out["samples"] == 3 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["window"] == "timed region"
+    c = b.ClockSampler(0); c.source = "nvml"; c.samples = [(1800.0, 1965.0, ())]
+    out = c.stop(1, 1)                                    # nothing inside the marks
+    assert out["samples"] == 1 and out["window"].startswith("warm-up")
